@@ -1,0 +1,209 @@
+/* rssm_rollout.h -- C ABI of the B200 latent-rollout library (librssm_rollout.so).
+ *
+ * The reference (Mamo1031/Multimodal-MTRSSM) is pure Python and has NO FFI for this path; its boundary
+ * is a set of Python methods.  Each entry point below replaces the body of one of them (paths relative
+ * to /root/reference/src/multimodal_rssm/models/):
+ *
+ *   rssm_mrssm_rollout_fwd   MoPoE_MRSSM.rollout_representation   mrssm/mopoe_mrssm/core.py:184-260
+ *                            (after the encoders, :215-216; includes Transition.forward networks.py:151-173,
+ *                             the posterior heads :62-84, the MoPoE fusion :112-163,241-251, the samples
+ *                             state.py:17 and the per-(b,t) KL terms of core.py:212-216)
+ *   rssm_mrssm_rollout_bwd   autograd (BPTT) of the above
+ *   rssm_mrssm_imagine_fwd   BaseRSSM.rollout_transition           core.py:170-185
+ *   rssm_mtrssm_rollout_fwd  MoPoE_MMTRSSM.rollout_representation  mmtrssm/mopoe_mmtrssm/core.py:364-494
+ *                            (MTRNN :40-61, lower prior :263-287, heads :241-261, fusion :436-455,
+ *                             higher prior/posterior :289-319, samples :456,:464 and mmtrssm/state.py:48-49,
+ *                             KL terms of :589-600)
+ *   rssm_mtrssm_rollout_bwd  autograd (BPTT) of the above
+ *   rssm_mtrssm_imagine_fwd  MoPoE_MMTRSSM.rollout_transition      mmtrssm/mopoe_mmtrssm/core.py:496-544
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (8-byte aligned); the library borrows it for the
+ *     duration of the launch on `stream` (a cudaStream_t passed as void*; NULL = default stream) and keeps
+ *     no state between calls (re-entrant across streams; MTRNN.hidden is an explicit input/output).
+ *   - weights use PyTorch layouts ([out, in] row-major Linear / GRUCell weights), read in place.
+ *   - categorical noise is caller-supplied: uniforms u in [0,1), one per (b, t, group); the draw is
+ *     idx = min(K-1, #{k : cdf_k <= u}).
+ *   - return value: 0 = ok, non-zero = error; rssm_last_error() returns a thread-local message.
+ *   - supported sizes (anything else returns an error, never a fallback):
+ *       deter = hidden = 32, stochastic size C*K = 16 with K in {2,4,8,16}, embed = 64, action even, 2..8.
+ *   - precision: RSSM_PRECISION_FP32 = every contraction as a 3-way bf16 split on the tensor cores with fp32
+ *     accumulation (fp32-level accuracy); RSSM_PRECISION_BF16 = single bf16 operands, fp32 accumulation,
+ *     fp32 state/epilogues.
+ */
+#ifndef RSSM_ROLLOUT_H_
+#define RSSM_ROLLOUT_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSSM_ABI_VERSION 1
+#define RSSM_PRECISION_FP32 0
+#define RSSM_PRECISION_BF16 1
+
+/* floats per (b,t) of the opaque records exchanged between fwd and bwd */
+#define MRSSM_SAVED_FLOATS 320
+#define MRSSM_DPRE_FLOATS 336
+#define MTRSSM_SAVED_FLOATS 192
+#define MTRSSM_DPRE_FLOATS 304
+
+/* ---- MoPoE-MRSSM -------------------------------------------------------------------------------------- */
+typedef struct {
+    int B, T;       /* sequences, steps */
+    int A, E, D, H; /* action, obs-embed, deterministic, MLP hidden sizes */
+    int C, K;       /* category_size (groups) x class_size (classes per group) */
+    int precision;  /* RSSM_PRECISION_* */
+} RssmMrssmDims;
+
+/* state_dict names in comments */
+typedef struct {
+    const float *asp_w1, *asp_b1, *asp_w2, *asp_b2; /* transition.action_state_projector.{0,2}.{weight,bias}  [H,A+S] [H] [H,H] [H] */
+    const float *w_ih, *w_hh, *b_ih, *b_hh;         /* transition.rnn_cell.{weight_ih,weight_hh,bias_ih,bias_hh}   [3D,H] [3D,D] [3D] [3D] */
+    const float *pr_w1, *pr_b1, *pr_w2, *pr_b2;     /* transition.rnn_to_prior_projector.{0,2}.*                   [H,D] [H] [S,H] [S] */
+    const float *au_w1, *au_b1, *au_w2, *au_b2;     /* audio_representation.rnn_to_post_projector.{0,2}.*          [H,D+E] [H] [S,H] [S] */
+    const float *vi_w1, *vi_b1, *vi_w2, *vi_b2;     /* vision_representation.rnn_to_post_projector.{0,2}.*         [H,D+E] [H] [S,H] [S] */
+} RssmMrssmWeights;
+
+typedef struct { /* same shapes; ACCUMULATED INTO (caller zero-fills) */
+    float *asp_w1, *asp_b1, *asp_w2, *asp_b2;
+    float *w_ih, *w_hh, *b_ih, *b_hh;
+    float *pr_w1, *pr_b1, *pr_w2, *pr_b2;
+    float *au_w1, *au_b1, *au_w2, *au_b2;
+    float *vi_w1, *vi_b1, *vi_w2, *vi_b2;
+} RssmMrssmWeightGrads;
+
+typedef struct {
+    const float *actions;  /* [B,T,A] */
+    const float *embed_a;  /* [B,T,E] audio encoder output */
+    const float *embed_v;  /* [B,T,E] vision encoder output */
+    const float *h0;       /* [B,D]   prev_state.deter */
+    const float *z0;       /* [B,S]   prev_state.stoch */
+    const float *u_post;   /* [B,T,C] uniforms for the mixed-posterior draw */
+    const float *u_prior;  /* [B,T,C] uniforms for the prior State's own draw; NULL = do not draw */
+} RssmMrssmInputs;
+
+typedef struct {
+    float *feature;      /* [B,T,D+S] posterior.feature = [deter | stoch]            (state.py:18) */
+    float *prior_probs;  /* [B,T,C,K] prior.distribution                                          */
+    float *post_probs;   /* [B,T,C,K] posterior.distribution                                      */
+    float *prior_stoch;  /* [B,T,S]   prior.stoch (one-hot); may be NULL                          */
+    float *kl;           /* [B,T]     sum_c KL(post_c || prior_c), before mean / balancing / coeff */
+    float *saved;        /* [B,T,MRSSM_SAVED_FLOATS] for the backward; NULL = inference             */
+} RssmMrssmOutputs;
+
+typedef struct {           /* upstream gradients; any pointer may be NULL (= zero) except d_feature */
+    const float *d_feature;     /* [B,T,D+S] */
+    const float *d_prior_probs; /* [B,T,C,K] */
+    const float *d_post_probs;  /* [B,T,C,K] */
+    const float *d_prior_stoch; /* [B,T,S]   */
+    const float *d_kl;          /* [B,T]     */
+    float kl_wq, kl_wp;         /* weights of the gradient paths of `kl` into posterior / prior:
+                                   (1,1) plain KL; (1-a, a) KL balancing with a = 0.8 */
+} RssmMrssmUpstream;
+
+typedef struct {
+    float *d_actions; /* [B,T,A]; may be NULL */
+    float *d_embed_a; /* [B,T,E] */
+    float *d_embed_v; /* [B,T,E] */
+    float *d_h0;      /* [B,D]   */
+    float *d_z0;      /* [B,S]   */
+    float *dpre;      /* [B,T,MRSSM_DPRE_FLOATS] workspace */
+} RssmMrssmInputGrads;
+
+int rssm_mrssm_rollout_fwd(const RssmMrssmDims *dims, const RssmMrssmWeights *w, const RssmMrssmInputs *in,
+                           const RssmMrssmOutputs *out, void *stream);
+int rssm_mrssm_rollout_bwd(const RssmMrssmDims *dims, const RssmMrssmWeights *w, const RssmMrssmInputs *in,
+                           const RssmMrssmOutputs *fwd_out, const RssmMrssmUpstream *up, const RssmMrssmInputGrads *gin,
+                           const RssmMrssmWeightGrads *gw, void *stream);
+/* imagination: out->feature [B,T,D+S] = [deter | prior sample], out->prior_probs; in->u_prior required;
+   in->embed_*, in->u_post, out->post_probs/prior_stoch/kl/saved ignored */
+int rssm_mrssm_imagine_fwd(const RssmMrssmDims *dims, const RssmMrssmWeights *w, const RssmMrssmInputs *in,
+                           const RssmMrssmOutputs *out, void *stream);
+
+/* ---- MoPoE-MMTRSSM ------------------------------------------------------------------------------------- */
+typedef struct {
+    int B, T;
+    int A, E, HD, LD, HH, HR; /* action, embed, higher/lower deter, head hidden, representation hidden */
+    int CL, KL, CH, KH;       /* l_dist / h_dist: category_size x class_size */
+    float l_tau, h_tau;
+    int precision;
+} RssmMtrssmDims;
+
+typedef struct {
+    const float *l_d2h_w, *l_d2h_b, *l_in_w, *l_in_b; /* l_rnn._d2h.{weight,bias} [LD,LD] [LD]; l_rnn._input2h.* [LD,A+LS+HS] [LD] */
+    const float *h_d2h_w, *h_d2h_b, *h_in_w, *h_in_b; /* h_rnn._d2h.* [HD,HD] [HD]; h_rnn._input2h.* [HD,HS] [HD] */
+    const float *lp_w1, *lp_b1, *lp_w2, *lp_b2;       /* l_prior.{0,2}.*      [HH,LD] [HH] [LS,HH] [LS] */
+    const float *hp_w1, *hp_b1, *hp_w2, *hp_b2;       /* h_prior.{0,2}.*      [HH,HD] [HH] [HS,HH] [HS] */
+    const float *hq_w1, *hq_b1, *hq_w2, *hq_b2;       /* h_posterior.{0,2}.*  [HH,LD+HD] [HH] [HS,HH] [HS] */
+    const float *au_w1, *au_b1, *au_w2, *au_b2;       /* audio_representation.rnn_to_post_projector.{0,2}.* [HR,LD+E] [HR] [LS,HR] [LS] */
+    const float *vi_w1, *vi_b1, *vi_w2, *vi_b2;       /* vision_representation.rnn_to_post_projector.{0,2}.* */
+} RssmMtrssmWeights;
+
+typedef struct { /* ACCUMULATED INTO (caller zero-fills) */
+    float *l_d2h_w, *l_d2h_b, *l_in_w, *l_in_b;
+    float *h_d2h_w, *h_d2h_b, *h_in_w, *h_in_b;
+    float *lp_w1, *lp_b1, *lp_w2, *lp_b2;
+    float *hp_w1, *hp_b1, *hp_w2, *hp_b2;
+    float *hq_w1, *hq_b1, *hq_w2, *hq_b2;
+    float *au_w1, *au_b1, *au_w2, *au_b2;
+    float *vi_w1, *vi_b1, *vi_w2, *vi_b2;
+} RssmMtrssmWeightGrads;
+
+typedef struct {
+    const float *actions, *embed_a, *embed_v;  /* [B,T,A] [B,T,E] [B,T,E] */
+    const float *deter_h0, *deter_l0;          /* [B,HD] [B,LD]  prev_state.deter_*  */
+    const float *hidden_h0, *hidden_l0;        /* [B,HD] [B,LD]  prev_state.hidden_* (MTRNN.hidden) */
+    const float *stoch_h0, *stoch_l0;          /* [B,HS] [B,LS]  prev_state.stoch_*  */
+    const float *u_post_l, *u_post_h;          /* [B,T,CL] [B,T,CH] */
+    const float *u_prior_l, *u_prior_h;        /* [B,T,CL] [B,T,CH]; both NULL = do not draw */
+} RssmMtrssmInputs;
+
+typedef struct {
+    float *feature;                         /* [B,T,HD+HS+LD+LS] = [deter_h | stoch_h | deter_l | stoch_l] (mmtrssm/state.py:51) */
+    float *hidden_h, *hidden_l;             /* [B,T,HD] [B,T,LD] MTRNN.hidden after the update */
+    float *prior_probs_h, *prior_probs_l;   /* [B,T,CH,KH] [B,T,CL,KL] */
+    float *post_probs_h, *post_probs_l;
+    float *prior_stoch_h, *prior_stoch_l;   /* [B,T,HS] [B,T,LS]; may be NULL */
+    float *kl_l, *kl_h;                     /* [B,T] each */
+    float *saved;                           /* [B,T,MTRSSM_SAVED_FLOATS]; NULL = inference */
+} RssmMtrssmOutputs;
+
+typedef struct {
+    const float *d_feature;                          /* required */
+    const float *d_prior_probs_h, *d_prior_probs_l;  /* optional (NULL = zero) ... */
+    const float *d_post_probs_h, *d_post_probs_l;
+    const float *d_prior_stoch_h, *d_prior_stoch_l;
+    const float *d_kl_l, *d_kl_h;
+    float kl_wq, kl_wp;
+} RssmMtrssmUpstream;
+
+typedef struct {
+    float *d_actions;                       /* may be NULL */
+    float *d_embed_a, *d_embed_v;
+    float *d_deter_h0, *d_deter_l0, *d_hidden_h0, *d_hidden_l0, *d_stoch_h0, *d_stoch_l0;
+    float *dpre;                            /* [B,T,MTRSSM_DPRE_FLOATS] workspace */
+} RssmMtrssmInputGrads;
+
+int rssm_mtrssm_rollout_fwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights *w, const RssmMtrssmInputs *in,
+                            const RssmMtrssmOutputs *out, void *stream);
+int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights *w, const RssmMtrssmInputs *in,
+                            const RssmMtrssmOutputs *fwd_out, const RssmMtrssmUpstream *up, const RssmMtrssmInputGrads *gin,
+                            const RssmMtrssmWeightGrads *gw, void *stream);
+/* imagination: feature = [deter_h | prior sample h | deter_l | prior sample l], hidden_*, prior_probs_*;
+   u_prior_* required */
+int rssm_mtrssm_imagine_fwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights *w, const RssmMtrssmInputs *in,
+                            const RssmMtrssmOutputs *out, void *stream);
+
+/* ---- misc ------------------------------------------------------------------------------------------------ */
+int rssm_abi_version(void);
+const char *rssm_last_error(void);
+/* number of kernels launched by this library in this process (all threads) */
+long long rssm_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSSM_ROLLOUT_H_ */

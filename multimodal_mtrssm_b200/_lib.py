@@ -1,0 +1,139 @@
+"""ctypes binding of librssm_rollout.so (C ABI: include/rssm_rollout.h).
+
+There is NO fallback: if the library is missing it is built in-tree with nvcc; if that fails, or a
+call returns non-zero, a RuntimeError is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from functools import lru_cache
+
+import torch
+
+from .build import LIB, build_library
+
+PRECISION_FP32 = 0
+PRECISION_BF16 = 1
+ABI_VERSION = 1
+MRSSM_SAVED_FLOATS, MRSSM_DPRE_FLOATS = 320, 336
+MTRSSM_SAVED_FLOATS, MTRSSM_DPRE_FLOATS = 192, 304
+
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+def _struct(name: str, fields: list[tuple[str, type]]) -> type:
+    return type(name, (C.Structure,), {"_fields_": fields})
+
+
+def _ptrs(names: str) -> list[tuple[str, type]]:
+    return [(n, _fp) for n in names.split()]
+
+
+_MR_W = "asp_w1 asp_b1 asp_w2 asp_b2 w_ih w_hh b_ih b_hh pr_w1 pr_b1 pr_w2 pr_b2 au_w1 au_b1 au_w2 au_b2 vi_w1 vi_b1 vi_w2 vi_b2"
+_MT_W = (
+    "l_d2h_w l_d2h_b l_in_w l_in_b h_d2h_w h_d2h_b h_in_w h_in_b lp_w1 lp_b1 lp_w2 lp_b2 hp_w1 hp_b1 hp_w2 hp_b2 "
+    "hq_w1 hq_b1 hq_w2 hq_b2 au_w1 au_b1 au_w2 au_b2 vi_w1 vi_b1 vi_w2 vi_b2"
+)
+MR_WEIGHT_FIELDS = tuple(_MR_W.split())
+MT_WEIGHT_FIELDS = tuple(_MT_W.split())
+
+MrssmDims = _struct("RssmMrssmDims", [(n, C.c_int) for n in "B T A E D H C K precision".split()])
+MrssmWeights = _struct("RssmMrssmWeights", _ptrs(_MR_W))
+MrssmWeightGrads = _struct("RssmMrssmWeightGrads", _ptrs(_MR_W))
+MrssmInputs = _struct("RssmMrssmInputs", _ptrs("actions embed_a embed_v h0 z0 u_post u_prior"))
+MrssmOutputs = _struct("RssmMrssmOutputs", _ptrs("feature prior_probs post_probs prior_stoch kl saved"))
+MrssmUpstream = _struct(
+    "RssmMrssmUpstream",
+    _ptrs("d_feature d_prior_probs d_post_probs d_prior_stoch d_kl") + [("kl_wq", C.c_float), ("kl_wp", C.c_float)],
+)
+MrssmInputGrads = _struct("RssmMrssmInputGrads", _ptrs("d_actions d_embed_a d_embed_v d_h0 d_z0 dpre"))
+
+MtrssmDims = _struct(
+    "RssmMtrssmDims",
+    [(n, C.c_int) for n in "B T A E HD LD HH HR CL KL CH KH".split()]
+    + [("l_tau", C.c_float), ("h_tau", C.c_float), ("precision", C.c_int)],
+)
+MtrssmWeights = _struct("RssmMtrssmWeights", _ptrs(_MT_W))
+MtrssmWeightGrads = _struct("RssmMtrssmWeightGrads", _ptrs(_MT_W))
+MtrssmInputs = _struct(
+    "RssmMtrssmInputs",
+    _ptrs(
+        "actions embed_a embed_v deter_h0 deter_l0 hidden_h0 hidden_l0 stoch_h0 stoch_l0 "
+        "u_post_l u_post_h u_prior_l u_prior_h"
+    ),
+)
+MtrssmOutputs = _struct(
+    "RssmMtrssmOutputs",
+    _ptrs(
+        "feature hidden_h hidden_l prior_probs_h prior_probs_l post_probs_h post_probs_l "
+        "prior_stoch_h prior_stoch_l kl_l kl_h saved"
+    ),
+)
+MtrssmUpstream = _struct(
+    "RssmMtrssmUpstream",
+    _ptrs(
+        "d_feature d_prior_probs_h d_prior_probs_l d_post_probs_h d_post_probs_l d_prior_stoch_h d_prior_stoch_l "
+        "d_kl_l d_kl_h"
+    )
+    + [("kl_wq", C.c_float), ("kl_wp", C.c_float)],
+)
+MtrssmInputGrads = _struct(
+    "RssmMtrssmInputGrads",
+    _ptrs("d_actions d_embed_a d_embed_v d_deter_h0 d_deter_l0 d_hidden_h0 d_hidden_l0 d_stoch_h0 d_stoch_l0 dpre"),
+)
+
+EXPORTS = (
+    "rssm_mrssm_rollout_fwd", "rssm_mrssm_rollout_bwd", "rssm_mrssm_imagine_fwd",
+    "rssm_mtrssm_rollout_fwd", "rssm_mtrssm_rollout_bwd", "rssm_mtrssm_imagine_fwd",
+    "rssm_abi_version", "rssm_last_error", "rssm_kernel_launch_count",
+)
+
+
+@lru_cache(maxsize=1)
+def lib() -> C.CDLL:
+    """Load (building first if needed) the CUDA library.  Raises if it cannot be had."""
+    path = build_library()
+    handle = C.CDLL(str(path))
+    for name in EXPORTS:
+        if not hasattr(handle, name):
+            raise RuntimeError(f"{LIB.name} does not export {name}")
+    handle.rssm_last_error.restype = C.c_char_p
+    handle.rssm_kernel_launch_count.restype = C.c_longlong
+    P = C.c_void_p
+    for name in EXPORTS[:6]:
+        getattr(handle, name).restype = C.c_int
+    handle.rssm_mrssm_rollout_fwd.argtypes = [P] * 5
+    handle.rssm_mrssm_imagine_fwd.argtypes = [P] * 5
+    handle.rssm_mrssm_rollout_bwd.argtypes = [P] * 8
+    handle.rssm_mtrssm_rollout_fwd.argtypes = [P] * 5
+    handle.rssm_mtrssm_imagine_fwd.argtypes = [P] * 5
+    handle.rssm_mtrssm_rollout_bwd.argtypes = [P] * 8
+    if handle.rssm_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{LIB.name}: ABI version {handle.rssm_abi_version()} != {ABI_VERSION}")
+    return handle
+
+
+def call(fn_name: str, *args) -> None:  # noqa: ANN002
+    """Invoke an entry point on the current CUDA stream; non-zero status -> RuntimeError."""
+    handle = lib()
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    status = getattr(handle, fn_name)(*[C.byref(a) if a is not None else None for a in args], stream)
+    if status != 0:
+        raise RuntimeError(f"{fn_name} failed: {handle.rssm_last_error().decode()}")
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    """Device pointer of a contiguous fp32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise RuntimeError(
+            f"rollout kernels need contiguous fp32 CUDA tensors, got device={t.device} dtype={t.dtype} "
+            f"contiguous={t.is_contiguous()}"
+        )
+    return t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(lib().rssm_kernel_launch_count())

@@ -1,0 +1,460 @@
+// Warp-tile primitives for the RSSM/MTRSSM rollout kernels (sm_100a).
+//
+// Execution model: ONE WARP OWNS 16 SEQUENCES (batch rows) and walks all T steps without any
+// block-level synchronisation.  Every activation of a step lives in registers in the
+// mma.m16n8k16 accumulator layout ("C tile": 16 rows x 8 cols, 4 floats per lane):
+//     lane = 4*g + t;   c[0],c[1] -> (row g,   cols 2t, 2t+1)
+//                       c[2],c[3] -> (row g+8, cols 2t, 2t+1)
+// Two adjacent C tiles re-pack, lane-locally (no shuffles, no shared memory), into one
+// m16n8k16 A operand k-tile, so a chain  GEMM -> activation -> GEMM  never leaves the register
+// file.  Weights are packed once per CTA into shared memory as ready-made B fragments
+// (`pack_weight`), so the inner loop is  LDS.64 + MMA.
+//
+// Precision policy NS (number of bf16 splits per operand):
+//   NS = 1  bf16 operands, fp32 accumulate                      -> "bf16 tensor-core path"
+//   NS = 3  x = h + m + l (three bf16 terms, 24 significand bits), the six products
+//           hH, hM, mH, mM, hL, lH are accumulated in fp32      -> "fp32-parity path"
+//           (dropped terms are <= 2^-23 relative; matches fp32 FFMA to ~1e-6)
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rssm {
+
+// ------------------------------------------------------------------------------------------
+// bf16 packing / splitting
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x (low 16 bits) = lo
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// splits (x0,x1) into NS bf16x2 words: out[0]=hi, out[1]=mid, out[2]=lo
+template <int NS>
+__device__ __forceinline__ void split_pack(float x0, float x1, uint32_t (&out)[NS]) {
+    __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+    {
+        __nv_bfloat162 v(h0, h1);
+        out[0] = *reinterpret_cast<uint32_t*>(&v);
+    }
+    if constexpr (NS == 3) {
+        float r0 = x0 - __bfloat162float(h0), r1 = x1 - __bfloat162float(h1);
+        __nv_bfloat16 m0 = __float2bfloat16_rn(r0), m1 = __float2bfloat16_rn(r1);
+        float s0 = r0 - __bfloat162float(m0), s1 = r1 - __bfloat162float(m1);
+        __nv_bfloat162 vm(m0, m1);
+        out[1] = *reinterpret_cast<uint32_t*>(&vm);
+        out[2] = pack_bf16(s0, s1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// MMA
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], const uint2 b) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+
+// A operand: KT k-tiles of 16, NS splits.  r[s][kt][0..3] per the PTX m16n8k16 A layout:
+//   [0] (row g, k 2t..2t+1) [1] (row g+8, k 2t..) [2] (row g, k 2t+8..) [3] (row g+8, k 2t+8..)
+template <int NS, int KT>
+struct AFrag {
+    uint32_t r[NS][KT][4];
+};
+
+// two adjacent C tiles (cols 16kt .. 16kt+15) -> k-tile kt of an A operand
+template <int NS, int KT>
+__device__ __forceinline__ void set_ktile(AFrag<NS, KT>& a, int kt, const float (&c0)[4], const float (&c1)[4]) {
+    uint32_t p[NS];
+    split_pack<NS>(c0[0], c0[1], p);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a.r[s][kt][0] = p[s];
+    split_pack<NS>(c0[2], c0[3], p);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a.r[s][kt][1] = p[s];
+    split_pack<NS>(c1[0], c1[1], p);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a.r[s][kt][2] = p[s];
+    split_pack<NS>(c1[2], c1[3], p);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a.r[s][kt][3] = p[s];
+}
+
+template <int NS, int KT>
+__device__ __forceinline__ void to_afrag(AFrag<NS, KT>& a, const float (&c)[2 * KT][4]) {
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) set_ktile<NS, KT>(a, kt, c[2 * kt], c[2 * kt + 1]);
+}
+
+// acc[NT tiles] += A[16 x 16KT] * B, B = packed weight block in shared memory laid out
+// [split][kt][nt][lane] as uint2 (see pack_weight)
+template <int NS, int KT, int NT>
+__device__ __forceinline__ void gemm(float (&acc)[NT][4], const AFrag<NS, KT>& a, const uint2* __restrict__ w, int lane) {
+    constexpr int SPLIT = KT * NT * 32;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const uint2* p = w + (kt * NT + nt) * 32 + lane;
+            const uint2 bh = p[0];
+            if constexpr (NS == 1) {
+                mma_bf16(acc[nt], a.r[0][kt], bh);
+            } else {
+                const uint2 bm = p[SPLIT], bl = p[2 * SPLIT];
+                mma_bf16(acc[nt], a.r[0][kt], bl);  // smallest terms first
+                mma_bf16(acc[nt], a.r[2][kt], bh);
+                mma_bf16(acc[nt], a.r[1][kt], bm);
+                mma_bf16(acc[nt], a.r[0][kt], bm);
+                mma_bf16(acc[nt], a.r[1][kt], bh);
+                mma_bf16(acc[nt], a.r[0][kt], bh);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing (cooperative, whole CTA, once per launch)
+// ------------------------------------------------------------------------------------------
+// Packs B[k][n] for k in [0,16KT), n in [0,8NT):
+//   TRANS == false:  B[k][n] = W[(n0+n)*ld + k0 + k]   (y = x W^T, forward; PyTorch [out,in] weight)
+//   TRANS == true :  B[k][n] = W[(n0+k)*ld + k0 + n]   (dx = dy W,  data gradient)
+// with zero padding outside k < kvalid / n < nvalid.  dst layout [split][kt][nt][lane] uint2.
+template <int NS, bool TRANS>
+__device__ __forceinline__ void pack_weight(uint2* __restrict__ dst, const float* __restrict__ W, int ld, int n0, int k0,
+                                            int kvalid, int nvalid, int KT, int NT, int tid, int nthreads) {
+    const int total = KT * NT * 32;
+    for (int idx = tid; idx < total; idx += nthreads) {
+        const int lane = idx & 31, tile = idx >> 5;
+        const int nt = tile % NT, kt = tile / NT;
+        const int g = lane >> 2, t = lane & 3;
+        const int n = nt * 8 + g;
+        float w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = kt * 16 + 2 * t + (j & 1) + ((j >> 1) << 3);
+            float v = 0.f;
+            if (k < kvalid && n < nvalid) v = TRANS ? W[(size_t)(n0 + k) * ld + k0 + n] : W[(size_t)(n0 + n) * ld + k0 + k];
+            w[j] = v;
+        }
+        uint32_t lo[NS], hi[NS];
+        split_pack<NS>(w[0], w[1], lo);
+        split_pack<NS>(w[2], w[3], hi);
+#pragma unroll
+        for (int s = 0; s < NS; ++s) dst[s * total + idx] = make_uint2(lo[s], hi[s]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// C-tile helpers
+// ------------------------------------------------------------------------------------------
+// per-lane row context of a 16-row warp tile
+struct Rows {
+    int rA, rB;   // clamped row indices (always valid for loads)
+    bool vA, vB;  // row really exists (stores)
+    int g, t;     // lane = 4g + t
+};
+
+__device__ __forceinline__ Rows make_rows(int row0, int B, int lane) {
+    Rows r;
+    r.g = lane >> 2;
+    r.t = lane & 3;
+    const int a = row0 + r.g, b = a + 8;
+    r.vA = a < B;
+    r.vB = b < B;
+    r.rA = a < B ? a : B - 1;
+    r.rB = b < B ? b : B - 1;
+    return r;
+}
+
+template <int NT>
+__device__ __forceinline__ void init_bias(float (&acc)[NT][4], const float* __restrict__ bias, int t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const float2 b = *reinterpret_cast<const float2*>(bias + nt * 8 + 2 * t);
+        acc[nt][0] = b.x, acc[nt][1] = b.y, acc[nt][2] = b.x, acc[nt][3] = b.y;
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void zero_c(float (&acc)[NT][4]) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+}
+
+// pA/pB: pointers to column 0 of this tile group in row A / row B
+template <int NT>
+__device__ __forceinline__ void load_c(float (&c)[NT][4], const float* __restrict__ pA, const float* __restrict__ pB, int t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const float2 a = *reinterpret_cast<const float2*>(pA + nt * 8 + 2 * t);
+        const float2 b = *reinterpret_cast<const float2*>(pB + nt * 8 + 2 * t);
+        c[nt][0] = a.x, c[nt][1] = a.y, c[nt][2] = b.x, c[nt][3] = b.y;
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void store_c(const float (&c)[NT][4], float* __restrict__ pA, float* __restrict__ pB, const Rows& r) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        if (r.vA) *reinterpret_cast<float2*>(pA + nt * 8 + 2 * r.t) = make_float2(c[nt][0], c[nt][1]);
+        if (r.vB) *reinterpret_cast<float2*>(pB + nt * 8 + 2 * r.t) = make_float2(c[nt][2], c[nt][3]);
+    }
+}
+
+// store only columns < nvalid (e.g. the 6 action columns of an 8-wide tile)
+__device__ __forceinline__ void store_c_partial(const float (&c)[4], float* __restrict__ pA, float* __restrict__ pB, const Rows& r,
+                                                int nvalid) {
+    const int c0 = 2 * r.t;
+    if (c0 + 1 < nvalid) {
+        if (r.vA) *reinterpret_cast<float2*>(pA + c0) = make_float2(c[0], c[1]);
+        if (r.vB) *reinterpret_cast<float2*>(pB + c0) = make_float2(c[2], c[3]);
+    } else if (c0 < nvalid) {
+        if (r.vA) pA[c0] = c[0];
+        if (r.vB) pB[c0] = c[2];
+    }
+}
+
+// A operand straight from global fp32 rows; columns >= kvalid read as zero
+template <int NS, int KT>
+__device__ __forceinline__ void load_a_global(AFrag<NS, KT>& a, const float* __restrict__ pA, const float* __restrict__ pB, int t,
+                                              int kvalid) {
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        float c0[4], c1[4];
+        const int k0 = kt * 16 + 2 * t, k1 = k0 + 8;
+        if (k0 + 1 < kvalid) {
+            const float2 x = *reinterpret_cast<const float2*>(pA + k0), y = *reinterpret_cast<const float2*>(pB + k0);
+            c0[0] = x.x, c0[1] = x.y, c0[2] = y.x, c0[3] = y.y;
+        } else {
+            c0[0] = k0 < kvalid ? pA[k0] : 0.f, c0[1] = 0.f, c0[2] = k0 < kvalid ? pB[k0] : 0.f, c0[3] = 0.f;
+        }
+        if (k1 + 1 < kvalid) {
+            const float2 x = *reinterpret_cast<const float2*>(pA + k1), y = *reinterpret_cast<const float2*>(pB + k1);
+            c1[0] = x.x, c1[1] = x.y, c1[2] = y.x, c1[3] = y.y;
+        } else {
+            c1[0] = k1 < kvalid ? pA[k1] : 0.f, c1[1] = 0.f, c1[2] = k1 < kvalid ? pB[k1] : 0.f, c1[3] = 0.f;
+        }
+        set_ktile<NS, KT>(a, kt, c0, c1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// elementwise math (fp32; accurate libm variants -- parity first)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float eluf_(float x) { return x > 0.f ? x : expm1f(x); }
+// d ELU / d pre, from the POST-activation value y: y > 0 -> 1, else exp(x) = y + 1
+__device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
+
+struct EluOp {
+    __device__ __forceinline__ float operator()(float x) const { return eluf_(x); }
+};
+
+template <int NT, typename F>
+__device__ __forceinline__ void map_c(float (&c)[NT][4], F f) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[nt][j] = f(c[nt][j]);
+}
+
+// ------------------------------------------------------------------------------------------
+// categorical helpers on a 16-wide logit vector = 2 C tiles.  Group = K consecutive columns.
+// Row A uses c[nt][0..1], row B uses c[nt][2..3]; `h` = 0 (row A) or 1 (row B).
+// ------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+
+// reduce a per-(tile,row) in-lane value over the K-column group it belongs to; result in v[0], v[1]
+template <int K, bool MAX>
+__device__ __forceinline__ void group_reduce(float (&v)[2]) {
+    static_assert(K == 2 || K == 4 || K == 8 || K == 16, "class_size must be 2, 4, 8 or 16");
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+        if constexpr (K >= 4) {
+            const float o = __shfl_xor_sync(FULL, v[nt], 1);
+            v[nt] = MAX ? fmaxf(v[nt], o) : v[nt] + o;
+        }
+        if constexpr (K >= 8) {
+            const float o = __shfl_xor_sync(FULL, v[nt], 2);
+            v[nt] = MAX ? fmaxf(v[nt], o) : v[nt] + o;
+        }
+    }
+    if constexpr (K == 16) {
+        const float m = MAX ? fmaxf(v[0], v[1]) : v[0] + v[1];
+        v[0] = v[1] = m;
+    }
+}
+
+// per-group softmax (MultiOneHotFactory, A1): p = exp(x - max_g) / sum_g
+template <int K>
+__device__ __forceinline__ void softmax_groups(const float (&x)[2][4], float (&p)[2][4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float m[2] = {fmaxf(x[0][2 * h], x[0][2 * h + 1]), fmaxf(x[1][2 * h], x[1][2 * h + 1])};
+        group_reduce<K, true>(m);
+        float e[2][2], s[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            e[nt][0] = expf(x[nt][2 * h] - m[nt]);
+            e[nt][1] = expf(x[nt][2 * h + 1] - m[nt]);
+            s[nt] = e[nt][0] + e[nt][1];
+        }
+        group_reduce<K, false>(s);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            p[nt][2 * h] = e[nt][0] / s[nt];
+            p[nt][2 * h + 1] = e[nt][1] / s[nt];
+        }
+    }
+}
+
+// log_softmax over the FLAT 16 columns (F.log_softmax(dim=-1)); optionally also the softmax
+__device__ __forceinline__ void log_softmax_flat(const float (&x)[2][4], float (&ls)[2][4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float m[2] = {fmaxf(x[0][2 * h], x[0][2 * h + 1]), fmaxf(x[1][2 * h], x[1][2 * h + 1])};
+        group_reduce<16, true>(m);
+        float s[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) s[nt] = expf(x[nt][2 * h] - m[0]) + expf(x[nt][2 * h + 1] - m[0]);
+        group_reduce<16, false>(s);
+        const float lse = m[0] + logf(s[0]);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            ls[nt][2 * h] = x[nt][2 * h] - lse;
+            ls[nt][2 * h + 1] = x[nt][2 * h + 1] - lse;
+        }
+    }
+}
+
+// MoPoE fusion (mopoe_mrssm/core.py:241-251,135-154): mixed = logsumexp([la, lv, la+lv] + log(1/3)) on
+// flat log-softmaxes.  Also returns the per-expert responsibilities needed by the backward:
+//   ra = (e^la + e^{la+lv}) / (e^la + e^lv + e^{la+lv}),  rv likewise.
+__device__ __forceinline__ void mopoe_mix(const float (&ls_a)[2][4], const float (&ls_v)[2][4], float (&mixed)[2][4],
+                                          float (*ra)[4], float (*rv)[4]) {
+    const float LOG_THIRD = -1.0986122886681098f;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = ls_a[nt][j], v = ls_v[nt][j], f = a + v;
+            const float mx = fmaxf(a, fmaxf(v, f));
+            const float ea = expf(a - mx), ev = expf(v - mx), ef = expf(f - mx);
+            const float s = ea + ev + ef;
+            mixed[nt][j] = LOG_THIRD + mx + logf(s);
+            if (ra != nullptr) {
+                ra[nt][j] = (ea + ef) / s;
+                rv[nt][j] = (ev + ef) / s;
+            }
+        }
+}
+
+// Inverse-CDF categorical draw (A2): idx = min(K-1, #{k : cdf_k <= u}), cdf accumulated in class order.
+// p: per-group probabilities (2 tiles); uA/uB: pointers to this row's uniforms u[c], c = 0..16/K-1.
+// Writes the exact one-hot into z (C-tile layout).
+template <int K>
+__device__ __forceinline__ void sample_onehot(const float (&p)[2][4], const float* __restrict__ uA, const float* __restrict__ uB,
+                                              float (&z)[2][4], int lane) {
+    const int t = lane & 3, qbase = lane & ~3;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            // group of my two columns (cols 8nt+2t, +1), and my first column's position inside it
+            int grp, pos;
+            if constexpr (K == 2) grp = nt * 4 + t, pos = 0;
+            if constexpr (K == 4) grp = nt * 2 + (t >> 1), pos = 2 * (t & 1);
+            if constexpr (K == 8) grp = nt, pos = 2 * t;
+            if constexpr (K == 16) grp = 0, pos = 8 * nt + 2 * t;
+            const float u = (h == 0 ? uA : uB)[grp];
+            float cdf = 0.f;
+            int idx = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                // owner of class k of my group: tile nt', quad position t', slot j
+                int src_nt, src_t;
+                if constexpr (K == 2) src_nt = nt, src_t = t;
+                if constexpr (K == 4) src_nt = nt, src_t = 2 * (t >> 1) + (k >> 1);
+                if constexpr (K == 8) src_nt = nt, src_t = k >> 1;
+                if constexpr (K == 16) src_nt = k >> 3, src_t = (k & 7) >> 1;
+                float pk = p[src_nt][2 * h + (k & 1)];
+                if constexpr (K > 2) pk = __shfl_sync(FULL, pk, qbase + src_t);
+                cdf += pk;
+                if (k < K - 1) idx += (cdf <= u) ? 1 : 0;
+            }
+            z[nt][2 * h] = (idx == pos) ? 1.f : 0.f;
+            z[nt][2 * h + 1] = (idx == pos + 1) ? 1.f : 0.f;
+        }
+    }
+}
+
+// backward of the per-group softmax: dx = p * (dp - sum_g p dp)
+template <int K>
+__device__ __forceinline__ void softmax_groups_bwd(const float (&p)[2][4], const float (&dp)[2][4], float (&dx)[2][4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float s[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) s[nt] = p[nt][2 * h] * dp[nt][2 * h] + p[nt][2 * h + 1] * dp[nt][2 * h + 1];
+        group_reduce<K, false>(s);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            dx[nt][2 * h] = p[nt][2 * h] * (dp[nt][2 * h] - s[nt]);
+            dx[nt][2 * h + 1] = p[nt][2 * h + 1] * (dp[nt][2 * h + 1] - s[nt]);
+        }
+    }
+}
+
+// backward of the flat log_softmax: dx = dls - softmax(x) * sum(dls), softmax(x) = exp(ls)
+__device__ __forceinline__ void log_softmax_flat_bwd(const float (&ls)[2][4], const float (&dls)[2][4], float (&dx)[2][4]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float s[2] = {dls[0][2 * h] + dls[0][2 * h + 1], dls[1][2 * h] + dls[1][2 * h + 1]};
+        group_reduce<16, false>(s);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            dx[nt][2 * h] = dls[nt][2 * h] - expf(ls[nt][2 * h]) * s[0];
+            dx[nt][2 * h + 1] = dls[nt][2 * h + 1] - expf(ls[nt][2 * h + 1]) * s[0];
+        }
+    }
+}
+
+// KL(q || p) summed over all 16 columns of a row (torch.distributions OneHotCategorical KL with its
+// eps clamp on the logs); result valid in every lane of the quad: out[0] row A, out[1] row B
+__device__ __forceinline__ float clamp_log(float p) {
+    const float eps = 1.1920928955078125e-07f;
+    return logf(fminf(fmaxf(p, eps), 1.f - eps));
+}
+__device__ __forceinline__ void kl_rows(const float (&q)[2][4], const float (&p)[2][4], float (&out)[2]) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float s[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            s[nt] = q[nt][2 * h] * (clamp_log(q[nt][2 * h]) - clamp_log(p[nt][2 * h])) +
+                    q[nt][2 * h + 1] * (clamp_log(q[nt][2 * h + 1]) - clamp_log(p[nt][2 * h + 1]));
+        }
+        group_reduce<16, false>(s);
+        out[h] = s[0];
+    }
+}
+
+// d KL / d q (weight wq) and d KL / d p (weight wp), added into dq / dp.  dkl[h] = upstream grad of the
+// row's KL.  dKL/dq_k = log q_k - log p_k + 1 ; dKL/dp_k = -q_k / p_k.
+__device__ __forceinline__ void kl_rows_bwd(const float (&q)[2][4], const float (&p)[2][4], const float (&dkl)[2], float wq, float wp,
+                                            float (&dq)[2][4], float (&dp)[2][4]) {
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float g = dkl[j >> 1];
+            dq[nt][j] += g * wq * (clamp_log(q[nt][j]) - clamp_log(p[nt][j]) + 1.f);
+            dp[nt][j] -= g * wp * q[nt][j] / fmaxf(p[nt][j], 1.1920928955078125e-07f);
+        }
+}
+
+}  // namespace rssm

@@ -1,0 +1,537 @@
+// MoPoE-MMTRSSM (fast/slow multi-timescale) latent rollout: persistent forward (+ imagination) and
+// fused BPTT backward kernels.
+//
+// Reference semantics (paths relative to /root/reference/src/multimodal_rssm/models/mmtrssm/):
+//   forward  : MoPoE_MMTRSSM.rollout_representation     mopoe_mmtrssm/core.py:364-494
+//              MTRNN._compute_mtrnn (leaky integrator)    mopoe_mmtrssm/core.py:40-61
+//              _compute_lower_prior                       mopoe_mmtrssm/core.py:263-287
+//              _compute_lower_posterior_with_logits       mopoe_mmtrssm/core.py:241-261
+//              MoPoE fusion (inline)                      mopoe_mmtrssm/core.py:436-455
+//              _compute_higher_prior_posterior            mopoe_mmtrssm/core.py:289-319
+//              MTState.__init__ (samples, feature order)  state.py:19-51
+//   imagine  : MoPoE_MMTRSSM.rollout_transition          mopoe_mmtrssm/core.py:496-544
+//   backward : autograd of the above
+//
+// MTRNN.hidden (a mutable module attribute in the reference, :38,:59) is a functional input/output
+// here.  `l_posterior` and the dummy `transition` are never evaluated by the reference rollout
+// (:405-490) and have no kernel-side counterpart.
+//
+// Fixed sizes of this instantiation: hd = ld = 32, hs = ls = 16, head hidden 32, E = 64, A <= 8.
+// feature layout (state.py:51): [deter_h 0:32 | stoch_h 32:48 | deter_l 48:80 | stoch_l 80:96].
+#include "frag.cuh"
+#include "kernels.h"
+
+namespace rssm {
+
+namespace mt {
+// ---- forward weight blocks (tile offsets) ----------------------------------------------------------
+constexpr int L_D2H = 0;              // d_l_prev (32) -> l pre (32)       KT2 NT4
+constexpr int L_IN_ZL = L_D2H + 8;    // z_l_prev (16) -> l pre            KT1 NT4
+constexpr int L_IN_ZH = L_IN_ZL + 4;  // z_h_prev (16) -> l pre            KT1 NT4
+constexpr int L_IN_A = L_IN_ZH + 4;   // action        -> l pre            KT1 NT4
+constexpr int H_D2H = L_IN_A + 4;     // d_h_prev      -> h pre            KT2 NT4
+constexpr int H_IN = H_D2H + 8;       // z_h_prev      -> h pre            KT1 NT4
+constexpr int LP1 = H_IN + 4, LP2 = LP1 + 8;
+constexpr int HP1 = LP2 + 4, HP2 = HP1 + 8;
+constexpr int HQ1L = HP2 + 4, HQ1H = HQ1L + 8, HQ2 = HQ1H + 8;
+constexpr int A1H = HQ2 + 4, A1E = A1H + 8, A2 = A1E + 16;
+constexpr int V1H = A2 + 4, V1E = V1H + 8, V2 = V1E + 16;
+constexpr int FWD_TILES = V2 + 4;  // 132
+constexpr int B_L = 0, B_H = 32, B_LP1 = 64, B_LP2 = 96, B_HP1 = 112, B_HP2 = 144, B_HQ1 = 160, B_HQ2 = 192, B_A1 = 208,
+              B_A2 = 240, B_V1 = 256, B_V2 = 288, FWD_BIAS = 304;
+// ---- backward (transposed) weight blocks -----------------------------------------------------------
+constexpr int T_A2 = 0, T_V2 = 4, T_LP2 = 8, T_HP2 = 12, T_HQ2 = 16;                       // KT1 NT4
+constexpr int T_A1H = 20, T_V1H = 28, T_LP1 = 36, T_HP1 = 44, T_HQ1L = 52, T_HQ1H = 60;   // KT2 NT4
+constexpr int T_A1E = 68, T_V1E = 84;                                                       // KT2 NT8
+constexpr int T_L_D2H = 100, T_H_D2H = 108;                                                 // KT2 NT4
+constexpr int T_L_IN_ZL = 116, T_L_IN_ZH = 120, T_H_IN = 124;                               // KT2 NT2
+constexpr int T_L_IN_A = 128;                                                               // KT2 NT1
+constexpr int BWD_TILES = 130;
+}  // namespace mt
+
+namespace mts {  // saved record (MTRSSM_SAVED_FLOATS = 192)
+constexpr int LP_HID = 0, HP_HID = 32, HQ_HID = 64, A_HID = 96, V_HID = 128, LA = 160, LV = 176;
+}
+namespace mtd {  // dpre record (MTRSSM_DPRE_FLOATS = 304)
+constexpr int L = 0, H = 32, LP1 = 64, LPL = 96, HP1 = 112, HPL = 144, HQ1 = 160, HQL = 192, A1 = 208, LA = 240, V1 = 256, LV = 288;
+}
+
+template <int NS>
+__device__ __forceinline__ uint2* wblk(uint2* W, int tile_off) {
+    return W + (size_t)NS * tile_off * 32;
+}
+
+// hidden -> ELU -> logits for a 32-wide hidden layer whose pre-activation is already accumulated
+template <int NS>
+__device__ __forceinline__ void head_l2(float (&acc)[4][4], float (&logits)[2][4], const float* bias2, const uint2* w2, float* svA,
+                                        float* svB, int sv_off, const Rows& r, int lane) {
+    map_c<4>(acc, EluOp{});
+    if (svA) store_c<4>(acc, svA + sv_off, svB + sv_off, r);
+    AFrag<NS, 2> f1;
+    to_afrag<NS, 2>(f1, acc);
+    init_bias<2>(logits, bias2, r.t);
+    gemm<NS, 2, 2>(logits, f1, w2, lane);
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+template <int NS, int KL, int KH, bool IMAGINE>
+__global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* W = reinterpret_cast<uint2*>(smem_raw);
+    float* bias = reinterpret_cast<float*>(W + (size_t)NS * mt::FWD_TILES * 32);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int A = p.A;
+    {
+        using namespace mt;
+        const int ldin = A + 32;
+        pack_weight<NS, false>(wblk<NS>(W, L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, false>(wblk<NS>(W, L_IN_ZL), p.w.l_in_w, ldin, 0, A, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, false>(wblk<NS>(W, L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, false>(wblk<NS>(W, L_IN_A), p.w.l_in_w, ldin, 0, 0, A, 32, 1, 4, tid, nthr);
+        pack_weight<NS, false>(wblk<NS>(W, H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, false>(wblk<NS>(W, H_IN), p.w.h_in_w, 16, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, false>(wblk<NS>(W, LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, false>(wblk<NS>(W, LP2), p.w.lp_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
+        pack_weight<NS, false>(wblk<NS>(W, HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, false>(wblk<NS>(W, HP2), p.w.hp_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
+        if (!IMAGINE) {
+            pack_weight<NS, false>(wblk<NS>(W, HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4, tid, nthr);
+            pack_weight<NS, false>(wblk<NS>(W, HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4, tid, nthr);
+            pack_weight<NS, false>(wblk<NS>(W, HQ2), p.w.hq_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
+            pack_weight<NS, false>(wblk<NS>(W, A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
+            pack_weight<NS, false>(wblk<NS>(W, A1E), p.w.au_w1, 96, 0, 32, 64, 32, 4, 4, tid, nthr);
+            pack_weight<NS, false>(wblk<NS>(W, A2), p.w.au_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
+            pack_weight<NS, false>(wblk<NS>(W, V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
+            pack_weight<NS, false>(wblk<NS>(W, V1E), p.w.vi_w1, 96, 0, 32, 64, 32, 4, 4, tid, nthr);
+            pack_weight<NS, false>(wblk<NS>(W, V2), p.w.vi_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
+        }
+        for (int i = tid; i < FWD_BIAS; i += nthr) {
+            float v;
+            if (i < B_H) v = p.w.l_d2h_b[i] + p.w.l_in_b[i];
+            else if (i < B_LP1) v = p.w.h_d2h_b[i - B_H] + p.w.h_in_b[i - B_H];
+            else if (i < B_LP2) v = p.w.lp_b1[i - B_LP1];
+            else if (i < B_HP1) v = p.w.lp_b2[i - B_LP2];
+            else if (i < B_HP2) v = p.w.hp_b1[i - B_HP1];
+            else if (i < B_HQ1) v = p.w.hp_b2[i - B_HP2];
+            else if (IMAGINE) v = 0.f;
+            else if (i < B_HQ2) v = p.w.hq_b1[i - B_HQ1];
+            else if (i < B_A1) v = p.w.hq_b2[i - B_HQ2];
+            else if (i < B_A2) v = p.w.au_b1[i - B_A1];
+            else if (i < B_V1) v = p.w.au_b2[i - B_A2];
+            else if (i < B_V2) v = p.w.vi_b1[i - B_V1];
+            else v = p.w.vi_b2[i - B_V2];
+            bias[i] = v;
+        }
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int row0 = (blockIdx.x * (nthr >> 5) + warp) * 16;
+    if (row0 >= p.B) return;
+    const Rows r = make_rows(row0, p.B, lane);
+    const int T = p.T;
+    constexpr int CL = 16 / KL, CH = 16 / KH, F = 96;
+    const float keep_l = 1.f - p.inv_tau_l, keep_h = 1.f - p.inv_tau_h;
+
+    // carried state
+    float ul[4][4], uh[4][4];
+    load_c<4>(ul, p.hidden_l0 + (size_t)r.rA * 32, p.hidden_l0 + (size_t)r.rB * 32, r.t);
+    load_c<4>(uh, p.hidden_h0 + (size_t)r.rA * 32, p.hidden_h0 + (size_t)r.rB * 32, r.t);
+    AFrag<NS, 2> dlf, dhf;
+    AFrag<NS, 1> zlf, zhf;
+    {
+        float c[4][4];
+        load_c<4>(c, p.deter_l0 + (size_t)r.rA * 32, p.deter_l0 + (size_t)r.rB * 32, r.t);
+        to_afrag<NS, 2>(dlf, c);
+        load_c<4>(c, p.deter_h0 + (size_t)r.rA * 32, p.deter_h0 + (size_t)r.rB * 32, r.t);
+        to_afrag<NS, 2>(dhf, c);
+        float z[2][4];
+        load_c<2>(z, p.stoch_l0 + (size_t)r.rA * 16, p.stoch_l0 + (size_t)r.rB * 16, r.t);
+        to_afrag<NS, 1>(zlf, z);
+        load_c<2>(z, p.stoch_h0 + (size_t)r.rA * 16, p.stoch_h0 + (size_t)r.rB * 16, r.t);
+        to_afrag<NS, 1>(zhf, z);
+    }
+
+    for (int t = 0; t < T; ++t) {
+        const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
+        float* svA = p.saved ? p.saved + iA * MTRSSM_SAVED_FLOATS : nullptr;
+        float* svB = p.saved ? p.saved + iB * MTRSSM_SAVED_FLOATS : nullptr;
+
+        // ---- two leaky-integrator cells (mopoe_mmtrssm/core.py:59-60), both from the PREVIOUS state ----
+        {
+            float pl[4][4], ph[4][4];
+            init_bias<4>(pl, bias + mt::B_L, r.t);
+            AFrag<NS, 1> fa;
+            load_a_global<NS, 1>(fa, p.actions + iA * A, p.actions + iB * A, r.t, A);
+            gemm<NS, 2, 4>(pl, dlf, wblk<NS>(W, mt::L_D2H), lane);
+            gemm<NS, 1, 4>(pl, zlf, wblk<NS>(W, mt::L_IN_ZL), lane);
+            gemm<NS, 1, 4>(pl, zhf, wblk<NS>(W, mt::L_IN_ZH), lane);
+            gemm<NS, 1, 4>(pl, fa, wblk<NS>(W, mt::L_IN_A), lane);
+            init_bias<4>(ph, bias + mt::B_H, r.t);
+            gemm<NS, 2, 4>(ph, dhf, wblk<NS>(W, mt::H_D2H), lane);
+            gemm<NS, 1, 4>(ph, zhf, wblk<NS>(W, mt::H_IN), lane);
+            float dl[4][4], dh[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ul[nt][j] = keep_l * ul[nt][j] + pl[nt][j] * p.inv_tau_l;
+                    uh[nt][j] = keep_h * uh[nt][j] + ph[nt][j] * p.inv_tau_h;
+                    dl[nt][j] = tanhf(ul[nt][j]);
+                    dh[nt][j] = tanhf(uh[nt][j]);
+                }
+            store_c<4>(dh, p.feature + iA * F, p.feature + iB * F, r);
+            store_c<4>(dl, p.feature + iA * F + 48, p.feature + iB * F + 48, r);
+            store_c<4>(uh, p.hidden_h + iA * 32, p.hidden_h + iB * 32, r);
+            store_c<4>(ul, p.hidden_l + iA * 32, p.hidden_l + iB * 32, r);
+            to_afrag<NS, 2>(dlf, dl);
+            to_afrag<NS, 2>(dhf, dh);
+        }
+        // ---- priors (:285-286, :311-312) ------------------------------------------------------------------
+        float ppl[2][4], pph[2][4];
+        {
+            float acc[4][4], lg[2][4];
+            init_bias<4>(acc, bias + mt::B_LP1, r.t);
+            gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, mt::LP1), lane);
+            head_l2<NS>(acc, lg, bias + mt::B_LP2, wblk<NS>(W, mt::LP2), svA, svB, mts::LP_HID, r, lane);
+            softmax_groups<KL>(lg, ppl);
+            store_c<2>(ppl, p.prior_probs_l + iA * 16, p.prior_probs_l + iB * 16, r);
+            init_bias<4>(acc, bias + mt::B_HP1, r.t);
+            gemm<NS, 2, 4>(acc, dhf, wblk<NS>(W, mt::HP1), lane);
+            head_l2<NS>(acc, lg, bias + mt::B_HP2, wblk<NS>(W, mt::HP2), svA, svB, mts::HP_HID, r, lane);
+            softmax_groups<KH>(lg, pph);
+            store_c<2>(pph, p.prior_probs_h + iA * 16, p.prior_probs_h + iB * 16, r);
+        }
+        if (p.u_prior_l != nullptr) {  // prior MTState ctor draws h then l (:467-474 -> state.py:48-49)
+            float zh[2][4], zl[2][4];
+            sample_onehot<KH>(pph, p.u_prior_h + iA * CH, p.u_prior_h + iB * CH, zh, lane);
+            sample_onehot<KL>(ppl, p.u_prior_l + iA * CL, p.u_prior_l + iB * CL, zl, lane);
+            if (IMAGINE) {  // prev_state = prior_state (:542)
+                store_c<2>(zh, p.feature + iA * F + 32, p.feature + iB * F + 32, r);
+                store_c<2>(zl, p.feature + iA * F + 80, p.feature + iB * F + 80, r);
+                to_afrag<NS, 1>(zhf, zh);
+                to_afrag<NS, 1>(zlf, zl);
+            } else if (p.prior_stoch_l != nullptr) {
+                store_c<2>(zh, p.prior_stoch_h + iA * 16, p.prior_stoch_h + iB * 16, r);
+                store_c<2>(zl, p.prior_stoch_l + iA * 16, p.prior_stoch_l + iB * 16, r);
+            }
+        }
+        if constexpr (!IMAGINE) {
+        // ---- lower posterior: modality heads on d_l (:422-433), MoPoE fusion (:436-455), sample (:456) ----
+        float la[2][4], lv[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const float* emb = m == 0 ? p.embed_a : p.embed_v;
+            float acc[4][4];
+            init_bias<4>(acc, bias + (m == 0 ? mt::B_A1 : mt::B_V1), r.t);
+            AFrag<NS, 4> fe;
+            load_a_global<NS, 4>(fe, emb + iA * 64, emb + iB * 64, r.t, 64);
+            gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, m == 0 ? mt::A1H : mt::V1H), lane);
+            gemm<NS, 4, 4>(acc, fe, wblk<NS>(W, m == 0 ? mt::A1E : mt::V1E), lane);
+            float (&lg)[2][4] = m == 0 ? la : lv;
+            head_l2<NS>(acc, lg, bias + (m == 0 ? mt::B_A2 : mt::B_V2), wblk<NS>(W, m == 0 ? mt::A2 : mt::V2), svA, svB,
+                        m == 0 ? mts::A_HID : mts::V_HID, r, lane);
+            if (svA) store_c<2>(lg, svA + (m == 0 ? mts::LA : mts::LV), svB + (m == 0 ? mts::LA : mts::LV), r);
+        }
+        {
+            float lsa[2][4], lsv[2][4], mixed[2][4], q[2][4], zs[2][4];
+            log_softmax_flat(la, lsa);
+            log_softmax_flat(lv, lsv);
+            mopoe_mix(lsa, lsv, mixed, nullptr, nullptr);
+            softmax_groups<KL>(mixed, q);
+            store_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r);
+            sample_onehot<KL>(q, p.u_post_l + iA * CL, p.u_post_l + iB * CL, zs, lane);
+            store_c<2>(zs, p.feature + iA * F + 80, p.feature + iB * F + 80, r);
+            to_afrag<NS, 1>(zlf, zs);
+            float kl[2];
+            kl_rows(q, ppl, kl);
+            if (r.t == 0) {
+                if (r.vA) p.kl_l[iA] = kl[0];
+                if (r.vB) p.kl_l[iB] = kl[1];
+            }
+        }
+        // ---- higher posterior on [d_l ; d_h] (:315-317), sample (:464) -------------------------------------
+        {
+            float acc[4][4], lg[2][4], q[2][4], zs[2][4];
+            init_bias<4>(acc, bias + mt::B_HQ1, r.t);
+            gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, mt::HQ1L), lane);
+            gemm<NS, 2, 4>(acc, dhf, wblk<NS>(W, mt::HQ1H), lane);
+            head_l2<NS>(acc, lg, bias + mt::B_HQ2, wblk<NS>(W, mt::HQ2), svA, svB, mts::HQ_HID, r, lane);
+            softmax_groups<KH>(lg, q);
+            store_c<2>(q, p.post_probs_h + iA * 16, p.post_probs_h + iB * 16, r);
+            sample_onehot<KH>(q, p.u_post_h + iA * CH, p.u_post_h + iB * CH, zs, lane);
+            store_c<2>(zs, p.feature + iA * F + 32, p.feature + iB * F + 32, r);
+            to_afrag<NS, 1>(zhf, zs);
+            float kl[2];
+            kl_rows(q, pph, kl);
+            if (r.t == 0) {
+                if (r.vA) p.kl_h[iA] = kl[0];
+                if (r.vB) p.kl_h[iB] = kl[1];
+            }
+        }
+        }  // !IMAGINE
+    }
+}
+
+// ================================================================================================
+// backward
+// ================================================================================================
+// d logits (16) -> through W2^T -> * ELU'(hidden) -> dpre1 (stored) ; returns dpre1 as A operand
+template <int NS>
+__device__ __forceinline__ void head_bwd(const float (&dlogit)[2][4], const uint2* w2t, const float* svA, const float* svB,
+                                         int sv_off, float* dpA, float* dpB, int dp_logit_off, int dp1_off, AFrag<NS, 2>& f1,
+                                         const Rows& r, int lane) {
+    store_c<2>(dlogit, dpA + dp_logit_off, dpB + dp_logit_off, r);
+    AFrag<NS, 1> fl;
+    to_afrag<NS, 1>(fl, dlogit);
+    float dhid[4][4], hid[4][4];
+    zero_c<4>(dhid);
+    gemm<NS, 1, 4>(dhid, fl, w2t, lane);
+    load_c<4>(hid, svA + sv_off, svB + sv_off, r.t);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dhid[nt][j] *= elu_grad_from_out(hid[nt][j]);
+    store_c<4>(dhid, dpA + dp1_off, dpB + dp1_off, r);
+    to_afrag<NS, 2>(f1, dhid);
+}
+
+template <int NT>
+__device__ __forceinline__ void add_global(float (&acc)[NT][4], const float* base, size_t offA, size_t offB, int t) {
+    if (base == nullptr) return;
+    float g[NT][4];
+    load_c<NT>(g, base + offA, base + offB, t);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[nt][j] += g[nt][j];
+}
+
+template <int NS, int KL, int KH>
+__global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2* W = reinterpret_cast<uint2*>(smem_raw);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int A = p.A;
+    {
+        using namespace mt;
+        const int ldin = A + 32;
+        pack_weight<NS, true>(wblk<NS>(W, T_A2), p.w.au_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_V2), p.w.vi_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_LP2), p.w.lp_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_HP2), p.w.hp_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_HQ2), p.w.hq_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_A1E), p.w.au_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_V1E), p.w.vi_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZL), p.w.l_in_w, ldin, 0, A, 32, 16, 2, 2, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 32, 16, 2, 2, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_H_IN), p.w.h_in_w, 16, 0, 0, 32, 16, 2, 2, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_A), p.w.l_in_w, ldin, 0, 0, 32, A, 2, 1, tid, nthr);
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+    const int row0 = (blockIdx.x * (nthr >> 5) + warp) * 16;
+    if (row0 >= p.B) return;
+    const Rows r = make_rows(row0, p.B, lane);
+    const int T = p.T;
+    constexpr int F = 96;
+    const float keep_l = 1.f - p.inv_tau_l, keep_h = 1.f - p.inv_tau_h;
+
+    // carried gradients (w.r.t. the state handed from step t to step t+1)
+    float ddl[4][4], ddh[4][4], dul[4][4], duh[4][4], dzl[2][4], dzh[2][4];
+    zero_c<4>(ddl), zero_c<4>(ddh), zero_c<4>(dul), zero_c<4>(duh), zero_c<2>(dzl), zero_c<2>(dzh);
+
+    for (int t = T - 1; t >= 0; --t) {
+        const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
+        const float* svA = p.saved + iA * MTRSSM_SAVED_FLOATS;
+        const float* svB = p.saved + iB * MTRSSM_SAVED_FLOATS;
+        float* dpA = p.dpre + iA * MTRSSM_DPRE_FLOATS;
+        float* dpB = p.dpre + iB * MTRSSM_DPRE_FLOATS;
+
+        add_global<4>(ddh, p.d_feature, iA * F, iB * F, r.t);
+        add_global<2>(dzh, p.d_feature, iA * F + 32, iB * F + 32, r.t);  // straight-through: d stoch -> d probs
+        add_global<4>(ddl, p.d_feature, iA * F + 48, iB * F + 48, r.t);
+        add_global<2>(dzl, p.d_feature, iA * F + 80, iB * F + 80, r.t);
+
+        // ---- higher layer: posterior + prior heads ------------------------------------------------------
+        {
+            float q[2][4], pp[2][4], dpp[2][4];
+            load_c<2>(q, p.post_probs_h + iA * 16, p.post_probs_h + iB * 16, r.t);
+            load_c<2>(pp, p.prior_probs_h + iA * 16, p.prior_probs_h + iB * 16, r.t);
+            add_global<2>(dzh, p.d_post_probs_h, iA * 16, iB * 16, r.t);
+            zero_c<2>(dpp);
+            add_global<2>(dpp, p.d_prior_probs_h, iA * 16, iB * 16, r.t);
+            add_global<2>(dpp, p.d_prior_stoch_h, iA * 16, iB * 16, r.t);
+            if (p.d_kl_h != nullptr) {
+                const float dkl[2] = {p.d_kl_h[iA], p.d_kl_h[iB]};
+                kl_rows_bwd(q, pp, dkl, p.kl_wq, p.kl_wp, dzh, dpp);
+            }
+            float dlg[2][4];
+            AFrag<NS, 2> f1;
+            softmax_groups_bwd<KH>(q, dzh, dlg);
+            head_bwd<NS>(dlg, wblk<NS>(W, mt::T_HQ2), svA, svB, mts::HQ_HID, dpA, dpB, mtd::HQL, mtd::HQ1, f1, r, lane);
+            gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_HQ1L), lane);
+            gemm<NS, 2, 4>(ddh, f1, wblk<NS>(W, mt::T_HQ1H), lane);
+            softmax_groups_bwd<KH>(pp, dpp, dlg);
+            head_bwd<NS>(dlg, wblk<NS>(W, mt::T_HP2), svA, svB, mts::HP_HID, dpA, dpB, mtd::HPL, mtd::HP1, f1, r, lane);
+            gemm<NS, 2, 4>(ddh, f1, wblk<NS>(W, mt::T_HP1), lane);
+        }
+        // ---- lower layer: MoPoE posterior + prior head ------------------------------------------------------
+        {
+            float q[2][4], pp[2][4], dpp[2][4];
+            load_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r.t);
+            load_c<2>(pp, p.prior_probs_l + iA * 16, p.prior_probs_l + iB * 16, r.t);
+            add_global<2>(dzl, p.d_post_probs_l, iA * 16, iB * 16, r.t);
+            zero_c<2>(dpp);
+            add_global<2>(dpp, p.d_prior_probs_l, iA * 16, iB * 16, r.t);
+            add_global<2>(dpp, p.d_prior_stoch_l, iA * 16, iB * 16, r.t);
+            if (p.d_kl_l != nullptr) {
+                const float dkl[2] = {p.d_kl_l[iA], p.d_kl_l[iB]};
+                kl_rows_bwd(q, pp, dkl, p.kl_wq, p.kl_wp, dzl, dpp);
+            }
+            float dla[2][4], dlv[2][4];
+            {
+                float dm[2][4], la[2][4], lv[2][4], lsa[2][4], lsv[2][4], mixed[2][4], ra[2][4], rv[2][4];
+                softmax_groups_bwd<KL>(q, dzl, dm);
+                load_c<2>(la, svA + mts::LA, svB + mts::LA, r.t);
+                load_c<2>(lv, svA + mts::LV, svB + mts::LV, r.t);
+                log_softmax_flat(la, lsa);
+                log_softmax_flat(lv, lsv);
+                mopoe_mix(lsa, lsv, mixed, ra, rv);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        ra[nt][j] *= dm[nt][j];
+                        rv[nt][j] *= dm[nt][j];
+                    }
+                log_softmax_flat_bwd(lsa, ra, dla);
+                log_softmax_flat_bwd(lsv, rv, dlv);
+            }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                AFrag<NS, 2> f1;
+                head_bwd<NS>(m == 0 ? dla : dlv, wblk<NS>(W, m == 0 ? mt::T_A2 : mt::T_V2), svA, svB,
+                             m == 0 ? mts::A_HID : mts::V_HID, dpA, dpB, m == 0 ? mtd::LA : mtd::LV, m == 0 ? mtd::A1 : mtd::V1, f1,
+                             r, lane);
+                gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, m == 0 ? mt::T_A1H : mt::T_V1H), lane);
+                float de[8][4];
+                zero_c<8>(de);
+                gemm<NS, 2, 8>(de, f1, wblk<NS>(W, m == 0 ? mt::T_A1E : mt::T_V1E), lane);
+                float* dE = m == 0 ? p.d_embed_a : p.d_embed_v;
+                store_c<8>(de, dE + iA * 64, dE + iB * 64, r);
+            }
+            float dlg[2][4];
+            AFrag<NS, 2> f1;
+            softmax_groups_bwd<KL>(pp, dpp, dlg);
+            head_bwd<NS>(dlg, wblk<NS>(W, mt::T_LP2), svA, svB, mts::LP_HID, dpA, dpB, mtd::LPL, mtd::LP1, f1, r, lane);
+            gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_LP1), lane);
+        }
+        // ---- the two leaky integrators: u = keep*u_prev + pre/tau, d = tanh(u) -------------------------------
+        {
+            float dh[4][4], dl[4][4], ph[4][4], pl[4][4];
+            load_c<4>(dh, p.feature + iA * F, p.feature + iB * F, r.t);
+            load_c<4>(dl, p.feature + iA * F + 48, p.feature + iB * F + 48, r.t);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float gh = duh[nt][j] + ddh[nt][j] * (1.f - dh[nt][j] * dh[nt][j]);
+                    const float gl = dul[nt][j] + ddl[nt][j] * (1.f - dl[nt][j] * dl[nt][j]);
+                    ph[nt][j] = gh * p.inv_tau_h;
+                    pl[nt][j] = gl * p.inv_tau_l;
+                    duh[nt][j] = gh * keep_h;
+                    dul[nt][j] = gl * keep_l;
+                }
+            store_c<4>(pl, dpA + mtd::L, dpB + mtd::L, r);
+            store_c<4>(ph, dpA + mtd::H, dpB + mtd::H, r);
+            AFrag<NS, 2> fl, fh;
+            to_afrag<NS, 2>(fl, pl);
+            to_afrag<NS, 2>(fh, ph);
+            zero_c<4>(ddl), zero_c<4>(ddh), zero_c<2>(dzl), zero_c<2>(dzh);
+            gemm<NS, 2, 4>(ddl, fl, wblk<NS>(W, mt::T_L_D2H), lane);
+            gemm<NS, 2, 4>(ddh, fh, wblk<NS>(W, mt::T_H_D2H), lane);
+            gemm<NS, 2, 2>(dzl, fl, wblk<NS>(W, mt::T_L_IN_ZL), lane);
+            gemm<NS, 2, 2>(dzh, fl, wblk<NS>(W, mt::T_L_IN_ZH), lane);
+            gemm<NS, 2, 2>(dzh, fh, wblk<NS>(W, mt::T_H_IN), lane);
+            if (p.d_actions != nullptr) {
+                float da[1][4];
+                zero_c<1>(da);
+                gemm<NS, 2, 1>(da, fl, wblk<NS>(W, mt::T_L_IN_A), lane);
+                store_c_partial(da[0], p.d_actions + iA * A, p.d_actions + iB * A, r, A);
+            }
+        }
+    }
+    store_c<4>(ddh, p.d_deter_h0 + (size_t)r.rA * 32, p.d_deter_h0 + (size_t)r.rB * 32, r);
+    store_c<4>(ddl, p.d_deter_l0 + (size_t)r.rA * 32, p.d_deter_l0 + (size_t)r.rB * 32, r);
+    store_c<4>(duh, p.d_hidden_h0 + (size_t)r.rA * 32, p.d_hidden_h0 + (size_t)r.rB * 32, r);
+    store_c<4>(dul, p.d_hidden_l0 + (size_t)r.rA * 32, p.d_hidden_l0 + (size_t)r.rB * 32, r);
+    store_c<2>(dzh, p.d_stoch_h0 + (size_t)r.rA * 16, p.d_stoch_h0 + (size_t)r.rB * 16, r);
+    store_c<2>(dzl, p.d_stoch_l0 + (size_t)r.rA * 16, p.d_stoch_l0 + (size_t)r.rB * 16, r);
+}
+
+// ================================================================================================
+// launchers
+// ================================================================================================
+static int pick_warps_per_cta(int B) {
+    const int warps = (B + 15) / 16;
+    if (warps <= 2 * 148) return 1;
+    if (warps <= 4 * 148) return 2;
+    return 4;
+}
+
+template <typename KernelT, typename ArgsT>
+static cudaError_t launch(KernelT kernel, const ArgsT& args, int B, size_t smem, cudaStream_t stream) {
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    const int wpc = pick_warps_per_cta(B);
+    const int ctas = ((B + 15) / 16 + wpc - 1) / wpc;
+    kernel<<<ctas, wpc * 32, smem, stream>>>(args);
+    return cudaGetLastError();
+}
+
+// supported (class_size_l, class_size_h) pairs; default.yaml is (4, 2)
+#define MT_DISPATCH(KERNEL, ...)                                                              \
+    if (a.KL == 4 && a.KH == 2) return launch(KERNEL<NS, 4, 2 __VA_ARGS__>, a, a.B, smem, s); \
+    if (a.KL == 4 && a.KH == 4) return launch(KERNEL<NS, 4, 4 __VA_ARGS__>, a, a.B, smem, s); \
+    if (a.KL == 2 && a.KH == 2) return launch(KERNEL<NS, 2, 2 __VA_ARGS__>, a, a.B, smem, s); \
+    if (a.KL == 8 && a.KH == 8) return launch(KERNEL<NS, 8, 8 __VA_ARGS__>, a, a.B, smem, s); \
+    if (a.KL == 16 && a.KH == 16) return launch(KERNEL<NS, 16, 16 __VA_ARGS__>, a, a.B, smem, s); \
+    return cudaErrorInvalidValue;
+
+template <int NS, bool IMAGINE>
+static cudaError_t launch_mtrssm_fwd_k(const MtrssmFwdArgs& a, cudaStream_t s) {
+    const size_t smem = (size_t)NS * mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float);
+#define COMMA_IMAGINE , IMAGINE
+    MT_DISPATCH(mtrssm_fwd_kernel, COMMA_IMAGINE)
+#undef COMMA_IMAGINE
+}
+
+cudaError_t launch_mtrssm_fwd(const MtrssmFwdArgs& a, int precision, bool imagine, cudaStream_t s) {
+    if (precision == RSSM_PRECISION_FP32)
+        return imagine ? launch_mtrssm_fwd_k<3, true>(a, s) : launch_mtrssm_fwd_k<3, false>(a, s);
+    return imagine ? launch_mtrssm_fwd_k<1, true>(a, s) : launch_mtrssm_fwd_k<1, false>(a, s);
+}
+
+template <int NS>
+static cudaError_t launch_mtrssm_bwd_k(const MtrssmBwdArgs& a, cudaStream_t s) {
+    const size_t smem = (size_t)NS * mt::BWD_TILES * 32 * sizeof(uint2);
+    MT_DISPATCH(mtrssm_bwd_kernel, )
+}
+
+cudaError_t launch_mtrssm_bwd(const MtrssmBwdArgs& a, int precision, cudaStream_t s) {
+    return precision == RSSM_PRECISION_FP32 ? launch_mtrssm_bwd_k<3>(a, s) : launch_mtrssm_bwd_k<1>(a, s);
+}
+
+}  // namespace rssm

@@ -1,0 +1,418 @@
+"""torch custom ops (with autograd) over the C-ABI rollout library.
+
+Ops (namespace `mtrssm_b200`):
+  mrssm_rollout / mrssm_rollout_bwd / mrssm_imagine      -- MoPoE-MRSSM
+  mtrssm_rollout / mtrssm_rollout_bwd / mtrssm_imagine   -- MoPoE-MMTRSSM
+
+They are thin: allocate outputs with torch, pass raw device pointers to `librssm_rollout.so` on the current
+CUDA stream.  CUDA only -- a CPU tensor raises; there is no eager fallback.
+
+Weight order of the `weights` list follows `_lib.MR_WEIGHT_FIELDS` / `_lib.MT_WEIGHT_FIELDS`.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import ptr
+
+__all__ = ["mrssm_rollout", "mrssm_imagine", "mtrssm_rollout", "mtrssm_imagine", "kl_path_weights"]
+
+KL_BALANCE_ALPHA = 0.8
+
+
+def kl_path_weights(use_balancing: bool) -> tuple[float, float]:
+    """(weight of d KL/d posterior, weight of d KL/d prior): balanced = (1-a, a), plain = (1, 1)."""
+    return (1.0 - KL_BALANCE_ALPHA, KL_BALANCE_ALPHA) if use_balancing else (1.0, 1.0)
+
+
+def _c(t: Optional[Tensor]) -> Optional[Tensor]:
+    return None if t is None else t.contiguous()
+
+
+def _fill(struct, names: Sequence[str], tensors: Sequence[Optional[Tensor]]):  # noqa: ANN001
+    for n, t in zip(names, tensors):
+        setattr(struct, n, ptr(t))
+    return struct
+
+
+# =================================================================================================
+# MoPoE-MRSSM
+# =================================================================================================
+def _mr_dims(actions: Tensor, K: int, precision: int) -> _lib.MrssmDims:
+    B, T, A = actions.shape
+    return _lib.MrssmDims(B=B, T=T, A=A, E=64, D=32, H=32, C=16 // K, K=K, precision=precision)
+
+
+def _mr_check(weights: Sequence[Tensor], embed_a: Tensor, h0: Tensor, z0: Tensor) -> None:
+    if len(weights) != len(_lib.MR_WEIGHT_FIELDS):
+        raise RuntimeError(f"expected {len(_lib.MR_WEIGHT_FIELDS)} weight tensors, got {len(weights)}")
+    if embed_a.shape[-1] != 64 or h0.shape[-1] != 32 or z0.shape[-1] != 16 or tuple(weights[4].shape) != (96, 32):
+        raise RuntimeError(
+            "fused MRSSM rollout supports deterministic_size = hidden_size = 32, obs_embed_size = 64, "
+            f"class_size*category_size = 16 (got embed {embed_a.shape[-1]}, deter {h0.shape[-1]}, stoch {z0.shape[-1]}, "
+            f"weight_ih {tuple(weights[4].shape)})"
+        )
+
+
+@torch.library.custom_op("mtrssm_b200::mrssm_rollout", mutates_args=())
+def mrssm_rollout_op(
+    weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, h0: Tensor, z0: Tensor,
+    u_post: Tensor, u_prior: Optional[Tensor], K: int, precision: int, kl_wq: float, kl_wp: float, save: bool,
+) -> List[Tensor]:
+    _mr_check(weights, embed_a, h0, z0)
+    B, T, _ = actions.shape
+    dev = actions.device
+    feature = torch.empty(B, T, 48, device=dev)
+    prior_probs = torch.empty(B, T, 16 // K, K, device=dev)
+    post_probs = torch.empty_like(prior_probs)
+    prior_stoch = torch.empty(B, T, 16, device=dev) if u_prior is not None else torch.empty(0, device=dev)
+    kl = torch.empty(B, T, device=dev)
+    saved = torch.empty(B, T, _lib.MRSSM_SAVED_FLOATS, device=dev) if save else torch.empty(0, device=dev)
+    w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
+    inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0 u_post u_prior".split(),
+                (actions, embed_a, embed_v, h0, z0, u_post, u_prior))
+    out = _fill(_lib.MrssmOutputs(), "feature prior_probs post_probs prior_stoch kl saved".split(),
+                (feature, prior_probs, post_probs, prior_stoch if u_prior is not None else None, kl, saved if save else None))
+    _lib.call("rssm_mrssm_rollout_fwd", _mr_dims(actions, K, precision), w, inp, out)
+    return [feature, prior_probs, post_probs, prior_stoch, kl, saved]
+
+
+@mrssm_rollout_op.register_fake
+def _(weights, actions, embed_a, embed_v, h0, z0, u_post, u_prior, K, precision, kl_wq, kl_wp, save):  # noqa: ANN001
+    B, T, _ = actions.shape
+    e = actions.new_empty
+    return [e(B, T, 48), e(B, T, 16 // K, K), e(B, T, 16 // K, K), e(B, T, 16) if u_prior is not None else e(0), e(B, T),
+            e(B, T, _lib.MRSSM_SAVED_FLOATS) if save else e(0)]
+
+
+@torch.library.custom_op("mtrssm_b200::mrssm_rollout_bwd", mutates_args=())
+def mrssm_rollout_bwd_op(
+    weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, h0: Tensor, z0: Tensor,
+    feature: Tensor, prior_probs: Tensor, post_probs: Tensor, saved: Tensor,
+    d_feature: Optional[Tensor], d_prior_probs: Optional[Tensor], d_post_probs: Optional[Tensor],
+    d_prior_stoch: Optional[Tensor], d_kl: Optional[Tensor], K: int, precision: int, kl_wq: float, kl_wp: float,
+) -> List[Tensor]:
+    B, T, A = actions.shape
+    dev = actions.device
+    if d_feature is None:
+        d_feature = torch.zeros_like(feature)
+    sizes = [t.numel() for t in weights]
+    flat = torch.zeros(sum(sizes), device=dev)
+    gws = [g.view_as(t) for g, t in zip(flat.split(sizes), weights)]
+    d_actions = torch.empty(B, T, A, device=dev)
+    d_embed_a = torch.empty(B, T, 64, device=dev)
+    d_embed_v = torch.empty(B, T, 64, device=dev)
+    d_h0 = torch.empty(B, 32, device=dev)
+    d_z0 = torch.empty(B, 16, device=dev)
+    dpre = torch.empty(B, T, _lib.MRSSM_DPRE_FLOATS, device=dev)
+    w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
+    gw = _fill(_lib.MrssmWeightGrads(), _lib.MR_WEIGHT_FIELDS, gws)
+    inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0".split(), (actions, embed_a, embed_v, h0, z0))
+    out = _fill(_lib.MrssmOutputs(), "feature prior_probs post_probs saved".split(), (feature, prior_probs, post_probs, saved))
+    up = _fill(_lib.MrssmUpstream(), "d_feature d_prior_probs d_post_probs d_prior_stoch d_kl".split(),
+               (_c(d_feature), _c(d_prior_probs), _c(d_post_probs), _c(d_prior_stoch), _c(d_kl)))
+    up.kl_wq, up.kl_wp = kl_wq, kl_wp
+    gin = _fill(_lib.MrssmInputGrads(), "d_actions d_embed_a d_embed_v d_h0 d_z0 dpre".split(),
+                (d_actions, d_embed_a, d_embed_v, d_h0, d_z0, dpre))
+    _lib.call("rssm_mrssm_rollout_bwd", _mr_dims(actions, K, precision), w, inp, out, up, gin, gw)
+    return [flat, d_actions, d_embed_a, d_embed_v, d_h0, d_z0]  # flat = all weight grads, split by the caller
+
+
+@mrssm_rollout_bwd_op.register_fake
+def _(weights, actions, embed_a, embed_v, h0, z0, feature, prior_probs, post_probs, saved, d_feature, d_prior_probs,  # noqa: ANN001
+      d_post_probs, d_prior_stoch, d_kl, K, precision, kl_wq, kl_wp):
+    return [actions.new_empty(sum(t.numel() for t in weights)), torch.empty_like(actions), torch.empty_like(embed_a),
+            torch.empty_like(embed_v), torch.empty_like(h0), torch.empty_like(z0)]
+
+
+def _mr_setup(ctx, inputs, output) -> None:  # noqa: ANN001
+    weights, actions, embed_a, embed_v, h0, z0, u_post, u_prior, K, precision, kl_wq, kl_wp, save = inputs
+    feature, prior_probs, post_probs, prior_stoch, kl, saved = output
+    if not save:
+        raise RuntimeError("mrssm_rollout was called with save=False but a gradient is required")
+    ctx.set_materialize_grads(False)
+    ctx.nw = len(weights)
+    ctx.has_prior_stoch = u_prior is not None
+    ctx.cfg = (K, precision, kl_wq, kl_wp)
+    ctx.save_for_backward(*weights, actions, embed_a, embed_v, h0, z0, feature, prior_probs, post_probs, saved)
+
+
+def _mr_backward(ctx, grads):  # noqa: ANN001
+    d_feature, d_prior_probs, d_post_probs, d_prior_stoch, d_kl, _ = grads
+    saved_t = ctx.saved_tensors
+    weights, rest = list(saved_t[: ctx.nw]), saved_t[ctx.nw:]
+    actions, embed_a, embed_v, h0, z0, feature, prior_probs, post_probs, saved = rest
+    K, precision, kl_wq, kl_wp = ctx.cfg
+    res = mrssm_rollout_bwd_op(
+        weights, actions, embed_a, embed_v, h0, z0, feature, prior_probs, post_probs, saved, d_feature, d_prior_probs,
+        d_post_probs, d_prior_stoch if ctx.has_prior_stoch else None, d_kl, K, precision, kl_wq, kl_wp,
+    )
+    flat, d_actions, d_ea, d_ev, d_h0, d_z0 = res
+    gws = [g.view_as(w) for g, w in zip(flat.split([w.numel() for w in weights]), weights)]
+    return gws, d_actions, d_ea, d_ev, d_h0, d_z0, None, None, None, None, None, None, None
+
+
+mrssm_rollout_op.register_autograd(_mr_backward, setup_context=_mr_setup)
+
+
+def mrssm_rollout(
+    weights: Sequence[Tensor], *, actions: Tensor, embed_a: Tensor, embed_v: Tensor, h0: Tensor, z0: Tensor,
+    u_post: Tensor, u_prior: Optional[Tensor] = None, class_size: int = 4, precision: int = _lib.PRECISION_FP32,
+    use_kl_balancing: bool = True,
+) -> dict[str, Tensor]:
+    """Fused MoPoE-MRSSM rollout_representation on encoder outputs (mrssm/mopoe_mrssm/core.py:184-260).
+
+    Returns feature [B,T,48] = [deter | post_stoch], prior_probs / post_probs [B,T,C,K], prior_stoch
+    [B,T,16] (only when `u_prior` is given) and kl [B,T] = sum_c KL(post_c || prior_c) whose gradient is
+    routed with the KL-balancing weights chosen here.
+    """
+    save = torch.is_grad_enabled() and any(t.requires_grad for t in (*weights, actions, embed_a, embed_v, h0, z0))
+    wq, wp = kl_path_weights(use_kl_balancing)
+    feature, prior_probs, post_probs, prior_stoch, kl, _ = mrssm_rollout_op(
+        [w.contiguous() for w in weights], actions.contiguous(), embed_a.contiguous(), embed_v.contiguous(),
+        h0.contiguous(), z0.contiguous(), u_post.contiguous(), _c(u_prior), class_size, precision, wq, wp, save,
+    )
+    return {"feature": feature, "prior_probs": prior_probs, "post_probs": post_probs,
+            "prior_stoch": prior_stoch if u_prior is not None else None, "kl": kl}
+
+
+@torch.library.custom_op("mtrssm_b200::mrssm_imagine", mutates_args=())
+def mrssm_imagine_op(weights: Sequence[Tensor], actions: Tensor, h0: Tensor, z0: Tensor, u: Tensor, K: int,
+                     precision: int) -> List[Tensor]:
+    B, T, _ = actions.shape
+    dev = actions.device
+    feature = torch.empty(B, T, 48, device=dev)
+    probs = torch.empty(B, T, 16 // K, K, device=dev)
+    w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
+    inp = _fill(_lib.MrssmInputs(), "actions h0 z0 u_prior".split(), (actions, h0, z0, u))
+    out = _fill(_lib.MrssmOutputs(), "feature prior_probs".split(), (feature, probs))
+    _lib.call("rssm_mrssm_imagine_fwd", _mr_dims(actions, K, precision), w, inp, out)
+    return [feature, probs]
+
+
+@mrssm_imagine_op.register_fake
+def _(weights, actions, h0, z0, u, K, precision):  # noqa: ANN001
+    B, T, _ = actions.shape
+    return [actions.new_empty(B, T, 48), actions.new_empty(B, T, 16 // K, K)]
+
+
+def mrssm_imagine(weights: Sequence[Tensor], *, actions: Tensor, h0: Tensor, z0: Tensor, u: Tensor, class_size: int = 4,
+                  precision: int = _lib.PRECISION_FP32) -> dict[str, Tensor]:
+    """Fused BaseRSSM.rollout_transition (core.py:170-185).  Forward only (the reference calls it under no_grad)."""
+    with torch.no_grad():
+        feature, probs = mrssm_imagine_op([w.contiguous() for w in weights], actions.contiguous(), h0.contiguous(),
+                                          z0.contiguous(), u.contiguous(), class_size, precision)
+    return {"feature": feature, "probs": probs}
+
+
+# =================================================================================================
+# MoPoE-MMTRSSM
+# =================================================================================================
+def _mt_dims(actions: Tensor, KL: int, KH: int, l_tau: float, h_tau: float, precision: int) -> _lib.MtrssmDims:
+    B, T, A = actions.shape
+    return _lib.MtrssmDims(B=B, T=T, A=A, E=64, HD=32, LD=32, HH=32, HR=32, CL=16 // KL, KL=KL, CH=16 // KH, KH=KH,
+                           l_tau=l_tau, h_tau=h_tau, precision=precision)
+
+
+_MT_STATE = "deter_h0 deter_l0 hidden_h0 hidden_l0 stoch_h0 stoch_l0".split()
+
+
+def _mt_check(weights: Sequence[Tensor], embed_a: Tensor, state: Sequence[Tensor]) -> None:
+    if len(weights) != len(_lib.MT_WEIGHT_FIELDS):
+        raise RuntimeError(f"expected {len(_lib.MT_WEIGHT_FIELDS)} weight tensors, got {len(weights)}")
+    shapes = [s.shape[-1] for s in state]
+    if embed_a.shape[-1] != 64 or shapes != [32, 32, 32, 32, 16, 16] or tuple(weights[8].shape) != (32, 32):
+        raise RuntimeError(
+            "fused MMTRSSM rollout supports hd_dim = ld_dim = 32, hs_dim = ls_dim = 16, head hidden 32, obs_embed_size 64 "
+            f"(got embed {embed_a.shape[-1]}, state widths {shapes}, l_prior.0 {tuple(weights[8].shape)})"
+        )
+
+
+@torch.library.custom_op("mtrssm_b200::mtrssm_rollout", mutates_args=())
+def mtrssm_rollout_op(
+    weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, state: Sequence[Tensor],
+    u_post_l: Tensor, u_post_h: Tensor, u_prior_l: Optional[Tensor], u_prior_h: Optional[Tensor],
+    KL: int, KH: int, l_tau: float, h_tau: float, precision: int, kl_wq: float, kl_wp: float, save: bool,
+) -> List[Tensor]:
+    _mt_check(weights, embed_a, state)
+    B, T, _ = actions.shape
+    dev = actions.device
+    e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
+    feature, hidden_h, hidden_l = e(B, T, 96), e(B, T, 32), e(B, T, 32)
+    prior_h, post_h = e(B, T, 16 // KH, KH), e(B, T, 16 // KH, KH)
+    prior_l, post_l = e(B, T, 16 // KL, KL), e(B, T, 16 // KL, KL)
+    has_prior = u_prior_l is not None
+    pz_h, pz_l = (e(B, T, 16), e(B, T, 16)) if has_prior else (e(0), e(0))
+    kl_l, kl_h = e(B, T), e(B, T)
+    saved = e(B, T, _lib.MTRSSM_SAVED_FLOATS) if save else e(0)
+    w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
+    inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE, "u_post_l", "u_post_h", "u_prior_l", "u_prior_h"],
+                (actions, embed_a, embed_v, *state, u_post_l, u_post_h, u_prior_l, u_prior_h))
+    out = _fill(
+        _lib.MtrssmOutputs(),
+        "feature hidden_h hidden_l prior_probs_h prior_probs_l post_probs_h post_probs_l prior_stoch_h prior_stoch_l kl_l kl_h saved".split(),
+        (feature, hidden_h, hidden_l, prior_h, prior_l, post_h, post_l, pz_h if has_prior else None, pz_l if has_prior else None,
+         kl_l, kl_h, saved if save else None),
+    )
+    _lib.call("rssm_mtrssm_rollout_fwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out)
+    return [feature, hidden_h, hidden_l, prior_h, prior_l, post_h, post_l, pz_h, pz_l, kl_l, kl_h, saved]
+
+
+@mtrssm_rollout_op.register_fake
+def _(weights, actions, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, u_prior_h, KL, KH, l_tau, h_tau, precision,  # noqa: ANN001
+      kl_wq, kl_wp, save):
+    B, T, _ = actions.shape
+    e = actions.new_empty
+    pz = e(B, T, 16) if u_prior_l is not None else e(0)
+    return [e(B, T, 96), e(B, T, 32), e(B, T, 32), e(B, T, 16 // KH, KH), e(B, T, 16 // KL, KL), e(B, T, 16 // KH, KH),
+            e(B, T, 16 // KL, KL), pz, torch.empty_like(pz), e(B, T), e(B, T), e(B, T, _lib.MTRSSM_SAVED_FLOATS) if save else e(0)]
+
+
+@torch.library.custom_op("mtrssm_b200::mtrssm_rollout_bwd", mutates_args=())
+def mtrssm_rollout_bwd_op(
+    weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, state: Sequence[Tensor],
+    feature: Tensor, prior_h: Tensor, prior_l: Tensor, post_h: Tensor, post_l: Tensor, saved: Tensor,
+    d_feature: Optional[Tensor], d_prior_h: Optional[Tensor], d_prior_l: Optional[Tensor], d_post_h: Optional[Tensor],
+    d_post_l: Optional[Tensor], d_pz_h: Optional[Tensor], d_pz_l: Optional[Tensor], d_kl_l: Optional[Tensor],
+    d_kl_h: Optional[Tensor], KL: int, KH: int, l_tau: float, h_tau: float, precision: int, kl_wq: float, kl_wp: float,
+) -> List[Tensor]:
+    B, T, A = actions.shape
+    dev = actions.device
+    if d_feature is None:
+        d_feature = torch.zeros_like(feature)
+    sizes = [t.numel() for t in weights]
+    flat = torch.zeros(sum(sizes), device=dev)
+    gws = [g.view_as(t) for g, t in zip(flat.split(sizes), weights)]
+    e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
+    d_actions, d_ea, d_ev = e(B, T, A), e(B, T, 64), e(B, T, 64)
+    d_state = [e(B, 32), e(B, 32), e(B, 32), e(B, 32), e(B, 16), e(B, 16)]
+    dpre = e(B, T, _lib.MTRSSM_DPRE_FLOATS)
+    w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
+    gw = _fill(_lib.MtrssmWeightGrads(), _lib.MT_WEIGHT_FIELDS, gws)
+    inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE], (actions, embed_a, embed_v, *state))
+    out = _fill(_lib.MtrssmOutputs(), "feature prior_probs_h prior_probs_l post_probs_h post_probs_l saved".split(),
+                (feature, prior_h, prior_l, post_h, post_l, saved))
+    up = _fill(
+        _lib.MtrssmUpstream(),
+        "d_feature d_prior_probs_h d_prior_probs_l d_post_probs_h d_post_probs_l d_prior_stoch_h d_prior_stoch_l d_kl_l d_kl_h".split(),
+        tuple(_c(t) for t in (d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h)),
+    )
+    up.kl_wq, up.kl_wp = kl_wq, kl_wp
+    gin = _fill(_lib.MtrssmInputGrads(),
+                ["d_actions", "d_embed_a", "d_embed_v", *("d_" + n for n in _MT_STATE), "dpre"],
+                (d_actions, d_ea, d_ev, *d_state, dpre))
+    _lib.call("rssm_mtrssm_rollout_bwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out, up, gin, gw)
+    return [flat, d_actions, d_ea, d_ev, *d_state]  # flat = all weight grads, split by the caller
+
+
+@mtrssm_rollout_bwd_op.register_fake
+def _(weights, actions, embed_a, embed_v, state, feature, prior_h, prior_l, post_h, post_l, saved, d_feature, d_prior_h,  # noqa: ANN001
+      d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp):
+    return [actions.new_empty(sum(t.numel() for t in weights)), torch.empty_like(actions), torch.empty_like(embed_a),
+            torch.empty_like(embed_v), *[torch.empty_like(t) for t in state]]
+
+
+def _mt_setup(ctx, inputs, output) -> None:  # noqa: ANN001
+    (weights, actions, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, u_prior_h, KL, KH, l_tau, h_tau, precision,
+     kl_wq, kl_wp, save) = inputs
+    feature, hidden_h, hidden_l, prior_h, prior_l, post_h, post_l, pz_h, pz_l, kl_l, kl_h, saved = output
+    if not save:
+        raise RuntimeError("mtrssm_rollout was called with save=False but a gradient is required")
+    ctx.set_materialize_grads(False)
+    ctx.nw = len(weights)
+    ctx.has_prior_stoch = u_prior_l is not None
+    ctx.cfg = (KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp)
+    ctx.save_for_backward(*weights, actions, embed_a, embed_v, *state, feature, prior_h, prior_l, post_h, post_l, saved)
+
+
+def _mt_backward(ctx, grads):  # noqa: ANN001
+    # gradients w.r.t. the hidden_h / hidden_l OUTPUTS are not propagated ("limits")
+    d_feature, _dhh, _dhl, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h, _ = grads
+    if _dhh is not None or _dhl is not None:
+        raise RuntimeError("gradients flowing into the hidden_h / hidden_l outputs of the fused MMTRSSM rollout are not supported")
+    t = ctx.saved_tensors
+    weights = list(t[: ctx.nw])
+    actions, embed_a, embed_v = t[ctx.nw: ctx.nw + 3]
+    state = list(t[ctx.nw + 3: ctx.nw + 9])
+    feature, prior_h, prior_l, post_h, post_l, saved = t[ctx.nw + 9:]
+    KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp = ctx.cfg
+    hp = ctx.has_prior_stoch
+    res = mtrssm_rollout_bwd_op(
+        weights, actions, embed_a, embed_v, state, feature, prior_h, prior_l, post_h, post_l, saved, d_feature, d_prior_h,
+        d_prior_l, d_post_h, d_post_l, d_pz_h if hp else None, d_pz_l if hp else None, d_kl_l, d_kl_h, KL, KH, l_tau, h_tau,
+        precision, kl_wq, kl_wp,
+    )
+    flat, d_actions, d_ea, d_ev = res[:4]
+    d_state = list(res[4:])
+    gws = [g.view_as(w) for g, w in zip(flat.split([w.numel() for w in weights]), weights)]
+    return (gws, d_actions, d_ea, d_ev, d_state, None, None, None, None, None, None, None, None, None, None, None, None)
+
+
+mtrssm_rollout_op.register_autograd(_mt_backward, setup_context=_mt_setup)
+
+
+def mtrssm_rollout(
+    weights: Sequence[Tensor], *, actions: Tensor, embed_a: Tensor, embed_v: Tensor, deter_h0: Tensor, deter_l0: Tensor,
+    hidden_h0: Tensor, hidden_l0: Tensor, stoch_h0: Tensor, stoch_l0: Tensor, u_post_l: Tensor, u_post_h: Tensor,
+    u_prior_l: Optional[Tensor] = None, u_prior_h: Optional[Tensor] = None, class_size_l: int = 4, class_size_h: int = 2,
+    l_tau: float = 2.0, h_tau: float = 4.0, precision: int = _lib.PRECISION_FP32, use_kl_balancing: bool = True,
+) -> dict[str, Tensor]:
+    """Fused MoPoE-MMTRSSM rollout_representation on encoder outputs (mmtrssm/mopoe_mmtrssm/core.py:364-494).
+
+    feature [B,T,96] = [deter_h | stoch_h | deter_l | stoch_l] (mmtrssm/state.py:51).
+    """
+    state = [deter_h0, deter_l0, hidden_h0, hidden_l0, stoch_h0, stoch_l0]
+    save = torch.is_grad_enabled() and any(t.requires_grad for t in (*weights, actions, embed_a, embed_v, *state))
+    wq, wp = kl_path_weights(use_kl_balancing)
+    out = mtrssm_rollout_op(
+        [w.contiguous() for w in weights], actions.contiguous(), embed_a.contiguous(), embed_v.contiguous(),
+        [s.contiguous() for s in state], u_post_l.contiguous(), u_post_h.contiguous(), _c(u_prior_l), _c(u_prior_h),
+        class_size_l, class_size_h, float(l_tau), float(h_tau), precision, wq, wp, save,
+    )
+    names = ("feature hidden_h hidden_l prior_probs_h prior_probs_l post_probs_h post_probs_l prior_stoch_h prior_stoch_l "
+             "kl_l kl_h").split()
+    res = dict(zip(names, out[:-1]))
+    if u_prior_l is None:
+        res["prior_stoch_h"] = res["prior_stoch_l"] = None
+    return res
+
+
+@torch.library.custom_op("mtrssm_b200::mtrssm_imagine", mutates_args=())
+def mtrssm_imagine_op(weights: Sequence[Tensor], actions: Tensor, state: Sequence[Tensor], u_l: Tensor, u_h: Tensor,
+                      KL: int, KH: int, l_tau: float, h_tau: float, precision: int) -> List[Tensor]:
+    B, T, _ = actions.shape
+    dev = actions.device
+    e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
+    feature, hidden_h, hidden_l = e(B, T, 96), e(B, T, 32), e(B, T, 32)
+    probs_h, probs_l = e(B, T, 16 // KH, KH), e(B, T, 16 // KL, KL)
+    w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
+    inp = _fill(_lib.MtrssmInputs(), ["actions", *_MT_STATE, "u_prior_l", "u_prior_h"], (actions, *state, u_l, u_h))
+    out = _fill(_lib.MtrssmOutputs(), "feature hidden_h hidden_l prior_probs_h prior_probs_l".split(),
+                (feature, hidden_h, hidden_l, probs_h, probs_l))
+    _lib.call("rssm_mtrssm_imagine_fwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out)
+    return [feature, hidden_h, hidden_l, probs_h, probs_l]
+
+
+@mtrssm_imagine_op.register_fake
+def _(weights, actions, state, u_l, u_h, KL, KH, l_tau, h_tau, precision):  # noqa: ANN001
+    B, T, _ = actions.shape
+    e = actions.new_empty
+    return [e(B, T, 96), e(B, T, 32), e(B, T, 32), e(B, T, 16 // KH, KH), e(B, T, 16 // KL, KL)]
+
+
+def mtrssm_imagine(
+    weights: Sequence[Tensor], *, actions: Tensor, deter_h0: Tensor, deter_l0: Tensor, hidden_h0: Tensor, hidden_l0: Tensor,
+    stoch_h0: Tensor, stoch_l0: Tensor, u_l: Tensor, u_h: Tensor, class_size_l: int = 4, class_size_h: int = 2,
+    l_tau: float = 2.0, h_tau: float = 4.0, precision: int = _lib.PRECISION_FP32,
+) -> dict[str, Tensor]:
+    """Fused MoPoE_MMTRSSM.rollout_transition (mmtrssm/mopoe_mmtrssm/core.py:496-544).  Forward only."""
+    state = [s.contiguous() for s in (deter_h0, deter_l0, hidden_h0, hidden_l0, stoch_h0, stoch_l0)]
+    with torch.no_grad():
+        out = mtrssm_imagine_op([w.contiguous() for w in weights], actions.contiguous(), state, u_l.contiguous(),
+                                u_h.contiguous(), class_size_l, class_size_h, float(l_tau), float(h_tau), precision)
+    return dict(zip("feature hidden_h hidden_l probs_h probs_l".split(), out))

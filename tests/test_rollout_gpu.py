@@ -1,0 +1,420 @@
+"""GPU parity: CUDA rollout kernels (through the C ABI / custom ops) vs the CPU oracle and the golden fixtures.
+
+Tolerances (north_star): fp32 path -- 1e-5 relative (atol 1e-6 on O(1) quantities) for means/probs/latents/ELBO
+terms and 1e-4 relative (atol 1e-6) for gradients accumulated over B*T; bf16 path -- stated per test below.
+Discrete draws are compared exactly; uniforms are kept `eps` away from CDF boundaries of the oracle trajectory so
+that rounding-level differences cannot flip a draw (helpers.*_safe_uniforms).
+"""
+
+import pytest
+import torch
+
+from oracle import rssm_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = dict(rtol=1e-5, atol=2e-6)
+GRAD_TOL = dict(rtol=1e-4, atol=2e-6)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from multimodal_mtrssm_b200 import params as P
+    from multimodal_mtrssm_b200 import rollout_ops as R
+
+    return R, P
+
+
+def cuda(d):
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+
+
+# ---------------------------------------------------------------------------------------------------
+# MRSSM
+# ---------------------------------------------------------------------------------------------------
+def run_mrssm(R, P, params, inp, K, precision=0, grad=False, upstream=None, use_balancing=True):
+    w = {k: v.cuda().requires_grad_(grad) for k, v in params.items()}
+    x = cuda(inp)
+    if grad:
+        for k in ("actions", "embed_a", "embed_v", "h0", "z0"):
+            x[k] = x[k].requires_grad_(True)
+    out = R.mrssm_rollout(P.mrssm_weight_list(w), class_size=K, precision=precision, use_kl_balancing=use_balancing, **x)
+    if grad:
+        loss = sum((out[k] * upstream[k].cuda()).sum() for k in upstream)
+        loss.backward()
+    torch.cuda.synchronize()
+    return out, w, x
+
+
+def oracle_mrssm(params, inp, C, K, grad=False, upstream=None, use_balancing=True, forced=None):
+    w = {k: v.clone().requires_grad_(grad) for k, v in params.items()}
+    x = dict(inp)
+    if grad:
+        for k in ("actions", "embed_a", "embed_v", "h0", "z0"):
+            x[k] = x[k].clone().requires_grad_(True)
+    res = O.mrssm_rollout(w, C=C, K=K, forced_post_idx=forced, **x)
+    res["kl"] = O.kl_per_sample(res["post_probs"], res["prior_probs"], use_balancing)
+    res["feature"] = res["post_feature"]
+    if grad:
+        loss = sum((res[k] * upstream[k]).sum() for k in upstream)
+        loss.backward()
+    return res, w, x
+
+
+def mrssm_upstream(B, T, C, K, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {
+        "feature": torch.randn(B, T, 48, generator=g), "kl": torch.randn(B, T, generator=g),
+        "post_probs": torch.randn(B, T, C, K, generator=g), "prior_probs": torch.randn(B, T, C, K, generator=g),
+        "prior_stoch": torch.randn(B, T, 16, generator=g),
+    }
+
+
+@pytest.mark.parametrize("B,T,K", [(37, 9, 4), (1, 1, 4), (16, 3, 2), (33, 5, 8), (8, 30, 16)])
+def test_mrssm_forward_fp32(ops, B, T, K):
+    R, P = ops
+    C = 16 // K
+    params = H.make_params(H.MR_SHAPES)
+    inp = H.mrssm_inputs(B, T, C, K)
+    H.mrssm_safe_uniforms(params, inp, C, K, eps=2e-4)
+    want, _, _ = oracle_mrssm(params, inp, C, K)
+    got, _, _ = run_mrssm(R, P, params, inp, K)
+    rep = H.Report(f"mrssm fwd fp32 B={B} T={T} K={K}")
+    rep.check("deter", got["feature"][..., :32], want["deter"], **FWD_TOL)
+    rep.check("post_stoch", got["feature"][..., 32:], want["post_stoch"], **FWD_TOL)
+    rep.check("prior_probs", got["prior_probs"], want["prior_probs"], **FWD_TOL)
+    rep.check("post_probs", got["post_probs"], want["post_probs"], **FWD_TOL)
+    rep.check("prior_stoch", got["prior_stoch"], want["prior_stoch"], **FWD_TOL)
+    rep.check("kl", got["kl"], want["kl"], rtol=1e-5, atol=1e-6)
+    rep.finish()
+    assert torch.equal(got["feature"][..., 32:].cpu().reshape(B, T, C, K).argmax(-1), want["post_idx"])
+
+
+@pytest.mark.parametrize("B,T,K,balancing", [(37, 9, 4, True), (5, 30, 4, False), (20, 4, 2, True)])
+def test_mrssm_backward_fp32(ops, B, T, K, balancing):
+    R, P = ops
+    C = 16 // K
+    params = H.make_params(H.MR_SHAPES)
+    inp = H.mrssm_inputs(B, T, C, K)
+    H.mrssm_safe_uniforms(params, inp, C, K, eps=2e-4)
+    up = mrssm_upstream(B, T, C, K)
+    _, w_ref, x_ref = oracle_mrssm(params, inp, C, K, grad=True, upstream=up, use_balancing=balancing)
+    _, w, x = run_mrssm(R, P, params, inp, K, grad=True, upstream=up, use_balancing=balancing)
+    rep = H.Report(f"mrssm bwd fp32 B={B} T={T} K={K} balancing={balancing}")
+    for k in ("embed_a", "embed_v", "actions", "h0", "z0"):
+        rep.check("d " + k, x[k].grad, x_ref[k].grad, **GRAD_TOL)
+    for k in w:
+        scale = float(w_ref[k].grad.abs().max())
+        rep.check("d " + k.replace("rnn_to_", "").replace("_projector", ""), w[k].grad, w_ref[k].grad, rtol=1e-4, atol=1e-5 * max(scale, 1e-3))
+    rep.finish()
+
+
+def test_mrssm_only_kl_loss_and_no_prior_sample(ops):
+    """Upstream gradient only through kl (d_feature absent) and without the prior's own draw."""
+    R, P = ops
+    B, T, C, K = 19, 6, 4, 4
+    params = H.make_params(H.MR_SHAPES)
+    inp = H.mrssm_inputs(B, T, C, K)
+    H.mrssm_safe_uniforms(params, inp, C, K, eps=2e-4)
+    inp["u_prior"] = None
+    up = {"kl": torch.full((B, T), 1.0 / (B * T))}
+    _, w_ref, _ = oracle_mrssm(params, inp, C, K, grad=True, upstream=up)
+    out, w, _ = run_mrssm(R, P, params, inp, K, grad=True, upstream=up)
+    assert out["prior_stoch"] is None
+    rep = H.Report("mrssm kl-only backward")
+    for k in w:
+        scale = float(w_ref[k].grad.abs().max())
+        rep.check("d " + k, w[k].grad, w_ref[k].grad, rtol=1e-4, atol=1e-5 * max(scale, 1e-4))
+    rep.finish()
+
+
+def test_mrssm_imagine_fp32(ops):
+    R, P = ops
+    B, T, C, K = 21, 11, 4, 4
+    params = H.make_params(H.MR_SHAPES)
+    inp = H.mrssm_inputs(B, T, C, K)
+    g = torch.Generator().manual_seed(5)
+    u = torch.rand(B, T, C, generator=g)
+    for _ in range(50):
+        want = O.mrssm_imagine(params, actions=inp["actions"], h0=inp["h0"], z0=inp["z0"], u=u, C=C, K=K)
+        bad = O.cdf_margin(want["probs"], u) < 2e-4
+        if not bad.any():
+            break
+        u[bad] = torch.rand(int(bad.sum()), generator=g)
+    w = {k: v.cuda() for k, v in params.items()}
+    got = R.mrssm_imagine(P.mrssm_weight_list(w), actions=inp["actions"].cuda(), h0=inp["h0"].cuda(), z0=inp["z0"].cuda(),
+                          u=u.cuda(), class_size=K)
+    rep = H.Report("mrssm imagine fp32")
+    rep.check("deter", got["feature"][..., :32], want["deter"], **FWD_TOL)
+    rep.check("stoch", got["feature"][..., 32:], want["stoch"], **FWD_TOL)
+    rep.check("probs", got["probs"], want["probs"], **FWD_TOL)
+    rep.finish()
+
+
+def test_mrssm_golden_fixture(ops, golden_dir):
+    """The CUDA path against vectors produced by the reference's own code (tests/golden/make_golden.py)."""
+    R, P = ops
+    g = torch.load(golden_dir / "mrssm_default.pt")
+    dims, inp, out = g["dims"], g["inputs"], g["outputs"]
+    w = {k: v.cuda().requires_grad_(True) for k, v in g["params"].items() if not k.startswith("representation.")}
+    x = {k: inp[k].cuda().requires_grad_(True) for k in ("embed_a", "embed_v", "h0", "z0")}
+    res = R.mrssm_rollout(P.mrssm_weight_list(w), actions=inp["actions"].cuda(), u_post=inp["u_post"].cuda(),
+                          u_prior=inp["u_prior"].cuda(), class_size=dims["K"], **x)
+    rep = H.Report("mrssm golden (reference code) vs CUDA")
+    rep.check("post_feature", res["feature"], out["post_feature"], **FWD_TOL)
+    rep.check("post_probs", res["post_probs"], out["post_probs"], **FWD_TOL)
+    rep.check("prior_probs", res["prior_probs"], out["prior_probs"], **FWD_TOL)
+    rep.check("prior_stoch", res["prior_stoch"], out["prior_stoch"], **FWD_TOL)
+    kl = res["kl"].mean() * dims["kl_coeff"]
+    rep.check("kl", kl, g["loss"]["kl"], rtol=1e-5, atol=1e-7)
+    ((res["feature"] * g["upstream"]["d_post_feature"].cuda()).sum() + kl).backward()
+    rep.check("d embed_a", x["embed_a"].grad, g["grads"]["embed_a"], **GRAD_TOL)
+    rep.check("d embed_v", x["embed_v"].grad, g["grads"]["embed_v"], **GRAD_TOL)
+    rep.check("d z0", x["z0"].grad, g["grads"]["z0"], **GRAD_TOL)
+    # golden h0 / prior-projector grads include the initial_state path through z0 (core.py:133-135); compare the rest
+    for k, ref in g["grads"]["params"].items():
+        if k.startswith(("representation.", "transition.rnn_to_prior_projector")):
+            continue
+        rep.check("d " + k, w[k].grad, ref, rtol=1e-4, atol=1e-5 * max(float(ref.abs().max()), 1e-3))
+    rep.finish()
+
+
+def test_mrssm_bf16_teacher_forced(ops):
+    """bf16 tensor-core path.  Stated tolerance: 3e-2 absolute on O(1) states/probs (bf16 operands, 8-bit mantissa,
+    error compounding over T steps of recurrence), samples self-consistent with the kernel's own probabilities."""
+    R, P = ops
+    B, T, C, K = 64, 16, 4, 4
+    params = H.make_params(H.MR_SHAPES)
+    inp = H.mrssm_inputs(B, T, C, K)
+    got, _, _ = run_mrssm(R, P, params, inp, K, precision=1)
+    idx = got["feature"][..., 32:].cpu().reshape(B, T, C, K).argmax(-1)
+    want, _, _ = oracle_mrssm(params, inp, C, K, forced=idx)
+    rep = H.Report("mrssm fwd bf16 (teacher-forced on the kernel's draws)")
+    rep.check("deter", got["feature"][..., :32], want["deter"], rtol=0, atol=3e-2)
+    rep.check("prior_probs", got["prior_probs"], want["prior_probs"], rtol=0, atol=3e-2)
+    rep.check("post_probs", got["post_probs"], want["post_probs"], rtol=0, atol=3e-2)
+    rep.finish()
+    # the kernel's draw is the inverse-CDF draw of ITS OWN probabilities
+    self_idx = O.inverse_cdf_index(got["post_probs"].cpu(), inp["u_post"])
+    margin = O.cdf_margin(got["post_probs"].cpu(), inp["u_post"])
+    assert bool(((self_idx == idx) | (margin < 1e-5)).all())
+    onehot = got["feature"][..., 32:].cpu().reshape(B, T, C, K)
+    assert bool(((onehot == 0) | (onehot == 1)).all()) and bool((onehot.sum(-1) == 1).all())
+
+
+# ---------------------------------------------------------------------------------------------------
+# MMTRSSM
+# ---------------------------------------------------------------------------------------------------
+MT_GRAD_IN = ("actions", "embed_a", "embed_v", "deter_h0", "deter_l0", "hidden_h0", "hidden_l0", "stoch_h0", "stoch_l0")
+
+
+def run_mtrssm(R, P, params, inp, dims, precision=0, grad=False, upstream=None, use_balancing=True):
+    w = {k: v.cuda().requires_grad_(grad) for k, v in params.items()}
+    x = cuda(inp)
+    if grad:
+        for k in MT_GRAD_IN:
+            x[k] = x[k].requires_grad_(True)
+    out = R.mtrssm_rollout(P.mtrssm_weight_list(w), class_size_l=dims["KL"], class_size_h=dims["KH"], l_tau=dims["l_tau"],
+                           h_tau=dims["h_tau"], precision=precision, use_kl_balancing=use_balancing, **x)
+    if grad:
+        sum((out[k] * upstream[k].cuda()).sum() for k in upstream).backward()
+    torch.cuda.synchronize()
+    return out, w, x
+
+
+def oracle_mtrssm(params, inp, dims, grad=False, upstream=None, use_balancing=True, forced=(None, None)):
+    w = {k: v.clone().requires_grad_(grad) for k, v in params.items()}
+    x = dict(inp)
+    if grad:
+        for k in MT_GRAD_IN:
+            x[k] = x[k].clone().requires_grad_(True)
+    res = O.mtrssm_rollout(w, dims=dims, forced_idx_l=forced[0], forced_idx_h=forced[1], **x)
+    res["kl_l"] = O.kl_per_sample(res["post_probs_l"], res["prior_probs_l"], use_balancing)
+    res["kl_h"] = O.kl_per_sample(res["post_probs_h"], res["prior_probs_h"], use_balancing)
+    res["feature"] = res["post_feature"]
+    if grad:
+        sum((res[k] * upstream[k]).sum() for k in upstream).backward()
+    return res, w, x
+
+
+def mtrssm_upstream(B, T, dims, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    return {
+        "feature": r(B, T, 96), "kl_l": r(B, T), "kl_h": r(B, T),
+        "post_probs_l": r(B, T, dims["CL"], dims["KL"]), "post_probs_h": r(B, T, dims["CH"], dims["KH"]),
+        "prior_probs_l": r(B, T, dims["CL"], dims["KL"]), "prior_probs_h": r(B, T, dims["CH"], dims["KH"]),
+        "prior_stoch_l": r(B, T, 16), "prior_stoch_h": r(B, T, 16),
+    }
+
+
+MT_FWD_KEYS = ("hidden_h", "hidden_l", "prior_probs_h", "prior_probs_l", "post_probs_h", "post_probs_l", "prior_stoch_h",
+               "prior_stoch_l", "kl_l", "kl_h")
+
+
+@pytest.mark.parametrize("B,T,dims", [
+    (37, 9, H.MT_DIMS), (1, 1, H.MT_DIMS), (16, 30, H.MT_DIMS),
+    (18, 5, dict(CL=4, KL=4, CH=4, KH=4, l_tau=1.5, h_tau=8.0)),
+    (9, 4, dict(CL=8, KL=2, CH=8, KH=2, l_tau=2.0, h_tau=3.0)),
+])
+def test_mtrssm_forward_fp32(ops, B, T, dims):
+    R, P = ops
+    params = H.make_params(H.MT_SHAPES)
+    inp = H.mtrssm_inputs(B, T, dims)
+    H.mtrssm_safe_uniforms(params, inp, dims, eps=2e-4)
+    want, _, _ = oracle_mtrssm(params, inp, dims)
+    got, _, _ = run_mtrssm(R, P, params, inp, dims)
+    rep = H.Report(f"mtrssm fwd fp32 B={B} T={T} {dims}")
+    rep.check("feature", got["feature"], want["post_feature"], **FWD_TOL)
+    for k in MT_FWD_KEYS:
+        rep.check(k, got[k], want[k], **FWD_TOL)
+    rep.finish()
+
+
+@pytest.mark.parametrize("B,T,balancing", [(37, 9, True), (6, 30, False)])
+def test_mtrssm_backward_fp32(ops, B, T, balancing):
+    R, P = ops
+    dims = H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    inp = H.mtrssm_inputs(B, T, dims)
+    H.mtrssm_safe_uniforms(params, inp, dims, eps=2e-4)
+    up = mtrssm_upstream(B, T, dims)
+    _, w_ref, x_ref = oracle_mtrssm(params, inp, dims, grad=True, upstream=up, use_balancing=balancing)
+    _, w, x = run_mtrssm(R, P, params, inp, dims, grad=True, upstream=up, use_balancing=balancing)
+    rep = H.Report(f"mtrssm bwd fp32 B={B} T={T} balancing={balancing}")
+    for k in MT_GRAD_IN:
+        rep.check("d " + k, x[k].grad, x_ref[k].grad, **GRAD_TOL)
+    for k in w:
+        scale = float(w_ref[k].grad.abs().max())
+        rep.check("d " + k.replace("rnn_to_post_projector", "post"), w[k].grad, w_ref[k].grad, rtol=1e-4, atol=1e-5 * max(scale, 1e-3))
+    rep.finish()
+
+
+def test_mtrssm_imagine_fp32(ops):
+    R, P = ops
+    B, T, dims = 21, 11, H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    inp = H.mtrssm_inputs(B, T, dims)
+    state = {k: inp[k] for k in ("deter_h0", "deter_l0", "hidden_h0", "hidden_l0", "stoch_h0", "stoch_l0")}
+    g = torch.Generator().manual_seed(5)
+    u_l, u_h = torch.rand(B, T, dims["CL"], generator=g), torch.rand(B, T, dims["CH"], generator=g)
+    for _ in range(50):
+        want = O.mtrssm_imagine(params, actions=inp["actions"], u_l=u_l, u_h=u_h, dims=dims, **state)
+        bad_l, bad_h = O.cdf_margin(want["probs_l"], u_l) < 2e-4, O.cdf_margin(want["probs_h"], u_h) < 2e-4
+        if not (bad_l.any() or bad_h.any()):
+            break
+        u_l[bad_l] = torch.rand(int(bad_l.sum()), generator=g)
+        u_h[bad_h] = torch.rand(int(bad_h.sum()), generator=g)
+    w = {k: v.cuda() for k, v in params.items()}
+    got = R.mtrssm_imagine(P.mtrssm_weight_list(w), actions=inp["actions"].cuda(), u_l=u_l.cuda(), u_h=u_h.cuda(),
+                           class_size_l=dims["KL"], class_size_h=dims["KH"], l_tau=dims["l_tau"], h_tau=dims["h_tau"], **cuda(state))
+    rep = H.Report("mtrssm imagine fp32")
+    f = got["feature"]
+    for name, a, b in (("deter_h", f[..., :32], want["deter_h"]), ("stoch_h", f[..., 32:48], want["stoch_h"]),
+                       ("deter_l", f[..., 48:80], want["deter_l"]), ("stoch_l", f[..., 80:], want["stoch_l"]),
+                       ("hidden_h", got["hidden_h"], want["hidden_h"]), ("hidden_l", got["hidden_l"], want["hidden_l"]),
+                       ("probs_h", got["probs_h"], want["probs_h"]), ("probs_l", got["probs_l"], want["probs_l"])):
+        rep.check(name, a, b, **FWD_TOL)
+    rep.finish()
+
+
+def test_mtrssm_golden_fixture(ops, golden_dir):
+    R, P = ops
+    g = torch.load(golden_dir / "mtrssm_default.pt")
+    dims, inp, out = g["dims"], g["inputs"], g["outputs"]
+    w = {k: v.cuda().requires_grad_(True) for k, v in g["params"].items()}
+    names = ("embed_a", "embed_v", "deter_h0", "deter_l0", "hidden_h0", "hidden_l0", "stoch_h0", "stoch_l0")
+    x = {k: inp[k].cuda().requires_grad_(True) for k in names}
+    u = {k: inp[k].cuda() for k in ("u_post_l", "u_post_h", "u_prior_l", "u_prior_h")}
+    res = R.mtrssm_rollout(P.mtrssm_weight_list(w), actions=inp["actions"].cuda(), class_size_l=dims["KL"], class_size_h=dims["KH"],
+                           l_tau=dims["l_tau"], h_tau=dims["h_tau"], **x, **u)
+    rep = H.Report("mtrssm golden (reference code) vs CUDA")
+    rep.check("post_feature", res["feature"], out["post_feature"], **FWD_TOL)
+    for k in ("hidden_h", "hidden_l", "post_probs_h", "post_probs_l", "prior_probs_h", "prior_probs_l", "prior_stoch_h", "prior_stoch_l"):
+        rep.check(k, res[k], out[k], **FWD_TOL)
+    kl_l = res["kl_l"].mean() * dims["kl_coeff"]
+    kl_h = res["kl_h"].mean() * dims["kl_coeff"] * dims["w_kl_h"]
+    rep.check("kl", kl_l, g["loss"]["kl"], rtol=1e-5, atol=1e-7)
+    rep.check("kl_h", kl_h, g["loss"]["kl_h"], rtol=1e-5, atol=1e-7)
+    ((res["feature"] * g["upstream"]["d_post_feature"].cuda()).sum() + kl_l + kl_h).backward()
+    for k in ("embed_a", "embed_v", "stoch_h0", "stoch_l0"):
+        rep.check("d " + k, x[k].grad, g["grads"][k], **GRAD_TOL)
+    for k, ref in g["grads"]["params"].items():
+        if k.startswith(("l_prior", "h_prior")):  # golden adds the initial_state path through stoch_*0
+            continue
+        rep.check("d " + k, w[k].grad, ref, rtol=1e-4, atol=1e-5 * max(float(ref.abs().max()), 1e-3))
+    rep.finish()
+
+
+def test_mtrssm_bf16_teacher_forced(ops):
+    """bf16 tensor-core path; stated tolerance 3e-2 absolute on O(1) states/probs (see the MRSSM twin)."""
+    R, P = ops
+    B, T, dims = 64, 16, H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    inp = H.mtrssm_inputs(B, T, dims)
+    got, _, _ = run_mtrssm(R, P, params, inp, dims, precision=1)
+    f = got["feature"].cpu()
+    idx_h = f[..., 32:48].reshape(B, T, dims["CH"], dims["KH"]).argmax(-1)
+    idx_l = f[..., 80:].reshape(B, T, dims["CL"], dims["KL"]).argmax(-1)
+    want, _, _ = oracle_mtrssm(params, inp, dims, forced=(idx_l, idx_h))
+    rep = H.Report("mtrssm fwd bf16 (teacher-forced)")
+    rep.check("deter_h", f[..., :32], want["deter_h"], rtol=0, atol=3e-2)
+    rep.check("deter_l", f[..., 48:80], want["deter_l"], rtol=0, atol=3e-2)
+    for k in ("hidden_h", "hidden_l", "prior_probs_h", "prior_probs_l", "post_probs_h", "post_probs_l"):
+        rep.check(k, got[k], want[k], rtol=0, atol=3e-2)
+    rep.finish()
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at benchmark scale, error behaviour
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", [0, 1])
+def test_mtrssm_large_batch_properties(ops, precision):
+    """B=4096, T=30 (bench scale): distributions normalise, samples are one-hot and equal the inverse-CDF draw of the
+    kernel's own probabilities, and rolling out in two chained chunks equals one rollout (state hand-over)."""
+    R, P = ops
+    B, T, dims = 4096, 30, H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    inp = cuda(H.mtrssm_inputs(B, T, dims))
+    w = P.mtrssm_weight_list({k: v.cuda() for k, v in params.items()})
+    kw = dict(class_size_l=4, class_size_h=2, l_tau=2.0, h_tau=4.0, precision=precision)
+    full = R.mtrssm_rollout(w, **inp, **kw)
+    for k in ("prior_probs_h", "prior_probs_l", "post_probs_h", "post_probs_l"):
+        s = full[k].sum(-1)
+        assert torch.allclose(s, torch.ones_like(s), atol=1e-5), k
+    zl = full["feature"][..., 80:].reshape(B, T, 4, 4)
+    assert bool(((zl == 0) | (zl == 1)).all()) and bool((zl.sum(-1) == 1).all())
+    idx = O.inverse_cdf_index(full["post_probs_l"].cpu(), inp["u_post_l"].cpu())
+    margin = O.cdf_margin(full["post_probs_l"].cpu(), inp["u_post_l"].cpu())
+    assert bool(((idx == zl.argmax(-1).cpu()) | (margin < 1e-5)).all())
+    # chained chunks
+    t0 = 13
+    cut = lambda d, a, b: {k: (v[:, a:b].contiguous() if v.dim() == 3 and v.shape[1] == T else v) for k, v in d.items()}  # noqa: E731
+    first = R.mtrssm_rollout(w, **cut(inp, 0, t0), **kw)
+    f = first["feature"][:, -1]
+    nxt = cut(inp, t0, T)
+    nxt.update(deter_h0=f[:, :32], stoch_h0=f[:, 32:48], deter_l0=f[:, 48:80], stoch_l0=f[:, 80:],
+               hidden_h0=first["hidden_h"][:, -1], hidden_l0=first["hidden_l"][:, -1])
+    second = R.mtrssm_rollout(w, **nxt, **kw)
+    assert torch.equal(torch.cat([first["feature"], second["feature"]], 1), full["feature"])
+    assert torch.equal(torch.cat([first["kl_l"], second["kl_l"]], 1), full["kl_l"])
+
+
+def test_unsupported_sizes_and_devices_fail_loudly(ops):
+    R, P = ops
+    params = H.make_params(H.MR_SHAPES)
+    inp = H.mrssm_inputs(4, 3)
+    w = P.mrssm_weight_list({k: v.cuda() for k, v in params.items()})
+    bad = cuda(inp)
+    bad["embed_a"] = torch.randn(4, 3, 32, device="cuda")
+    with pytest.raises(RuntimeError, match="supports"):
+        R.mrssm_rollout(w, **bad)
+    with pytest.raises(RuntimeError):  # CPU tensors: no fallback
+        R.mrssm_rollout(P.mrssm_weight_list(params), **inp)
+    odd = cuda(H.mrssm_inputs(4, 3))
+    odd["actions"] = torch.randn(4, 3, 5, device="cuda")
+    with pytest.raises(RuntimeError):
+        R.mrssm_rollout(w, **odd)
