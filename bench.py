@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- latent steps/s (B*T, rollout fwd + BPTT bwd) of the fused MoPoE-MMTRSSM rollout on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # ours  (torchrun launches it for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference arm: CPU, host cores
+
+Workload (BASELINE.json configs[1]): MoPoE-MMTRSSM at the default.yaml sizes
+(hd=ld=32, hs=ls=16, heads 32, E=64, A=6, tau 2/4, KL balancing), T=30, synthetic encoder embeddings, actions
+and noise.  default.yaml's batch of 8 cannot occupy a GPU, so the per-GPU batch is 16384 sequences (weak
+scaling: every rank processes its own 16384); the B=8 latency is reported beside it (`default_batch8`).
+
+A step = one pass of the hot path over one batch: forward rollout kernel, backward (BPTT) kernel, weight-gradient
+kernel (+ one NCCL allreduce of the flat weight-gradient bucket when N > 1).  `value` has the inputs resident in
+HBM; `e2e` goes through the public API (`rollout_ops.mtrssm_rollout` + autograd) with pinned-host inputs copied
+in and the loss + weight gradients copied out every step.  One JSON line on stdout (rank 0).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "latent_steps_per_sec"
+UNIT = "latent steps/s (B*T, rollout fwd+bwd)"
+# fp32 mandatory I/O per (b,t): inputs (A + 2E)*4 = 536 B, MMTRSSM outputs 1024 B; fwd+bwd = 2x
+FWD_BYTES_PER_BT = 536 + 1024
+STEP_BYTES_PER_BT = 2 * FWD_BYTES_PER_BT
+FWD_FLOPS_PER_BT = 33152
+
+
+def parse() -> argparse.Namespace:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16384, help="sequences per GPU")
+    ap.add_argument("--seq-len", type=int, default=30)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=256, help="sequences in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp32-path / B=8 side measurements")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.samples: list[list[str]] = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self) -> None:
+        assert self.proc is not None and self.proc.stdout is not None
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) == 6:
+                self.samples.append(parts)
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+class DirectMtrssm:
+    """Pre-allocated buffers + direct C-ABI calls: exactly the three kernels of the hot path, no allocator traffic."""
+
+    def __init__(self, B: int, T: int, precision: int, device: torch.device) -> None:
+        from multimodal_mtrssm_b200 import _lib, synthetic
+        from multimodal_mtrssm_b200.params import mtrssm_weight_list
+
+        self.lib, self.B, self.T = _lib, B, T
+        self.params = {k: v.to(device) for k, v in synthetic.mtrssm_params().items()}
+        self.weights = mtrssm_weight_list(self.params)
+        self.inp = {k: v.to(device) for k, v in synthetic.mtrssm_batch(B, T).items()}
+        g = torch.Generator().manual_seed(7)
+        self.d_feature = torch.randn(B, T, 96, generator=g).to(device)
+        self.d_kl = torch.full((B, T), 1.0 / (B * T), device=device)
+        e = lambda *s: torch.empty(*s, device=device)  # noqa: E731
+        self.out = {
+            "feature": e(B, T, 96), "hidden_h": e(B, T, 32), "hidden_l": e(B, T, 32),
+            "prior_probs_h": e(B, T, 8, 2), "prior_probs_l": e(B, T, 4, 4), "post_probs_h": e(B, T, 8, 2), "post_probs_l": e(B, T, 4, 4),
+            "kl_l": e(B, T), "kl_h": e(B, T), "saved": e(B, T, _lib.MTRSSM_SAVED_FLOATS),
+        }
+        self.gin = {
+            "d_actions": e(B, T, 6), "d_embed_a": e(B, T, 64), "d_embed_v": e(B, T, 64), "d_deter_h0": e(B, 32), "d_deter_l0": e(B, 32),
+            "d_hidden_h0": e(B, 32), "d_hidden_l0": e(B, 32), "d_stoch_h0": e(B, 16), "d_stoch_l0": e(B, 16),
+            "dpre": e(B, T, _lib.MTRSSM_DPRE_FLOATS),
+        }
+        sizes = [w.numel() for w in self.weights]
+        self.flat_grad = torch.zeros(sum(sizes), device=device)
+        self.gws = [g_.view_as(w) for g_, w in zip(self.flat_grad.split(sizes), self.weights)]
+        L = _lib
+        self.c_dims = L.MtrssmDims(B=B, T=T, A=6, E=64, HD=32, LD=32, HH=32, HR=32, CL=4, KL=4, CH=8, KH=2, l_tau=2.0, h_tau=4.0,
+                                   precision=precision)
+        fill = lambda st, d: [setattr(st, k, L.ptr(v)) for k, v in d.items()] and st  # noqa: E731
+        self.c_w = fill(L.MtrssmWeights(), dict(zip(L.MT_WEIGHT_FIELDS, self.weights)))
+        self.c_gw = fill(L.MtrssmWeightGrads(), dict(zip(L.MT_WEIGHT_FIELDS, self.gws)))
+        self.c_in = fill(L.MtrssmInputs(), self.inp)
+        self.c_out = fill(L.MtrssmOutputs(), self.out)
+        self.c_up = fill(L.MtrssmUpstream(), {"d_feature": self.d_feature, "d_kl_l": self.d_kl, "d_kl_h": self.d_kl})
+        self.c_up.kl_wq, self.c_up.kl_wp = 0.2, 0.8
+        self.c_gin = fill(L.MtrssmInputGrads(), self.gin)
+
+    def fwd(self) -> None:
+        self.lib.call("rssm_mtrssm_rollout_fwd", self.c_dims, self.c_w, self.c_in, self.c_out)
+
+    def bwd_data(self) -> None:
+        self.lib.call("rssm_mtrssm_rollout_bwd", self.c_dims, self.c_w, self.c_in, self.c_out, self.c_up, self.c_gin, None)
+
+    def wgrad(self) -> None:
+        self.flat_grad.zero_()
+        self.lib.call("rssm_mtrssm_wgrad", self.c_dims, self.c_in, self.c_out, self.gin["dpre"].data_ptr(), self.c_gw)
+
+    def input_bytes(self) -> int:
+        return sum(v.numel() * 4 for v in self.inp.values())
+
+
+def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
+    import torch.distributed as dist
+
+    def step(evs=None):
+        if evs:
+            evs[0].record()
+        run.fwd()
+        if evs:
+            evs[1].record()
+        run.bwd_data()
+        if evs:
+            evs[2].record()
+        run.wgrad()
+        if world > 1:
+            dist.all_reduce(run.flat_grad)
+        if evs:
+            evs[3].record()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(steps):
+        step(evs[i])
+    end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = start.elapsed_time(end)
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t)
+    seg = [[e[i].elapsed_time(e[i + 1]) for e in evs] for i in range(3)]
+    return {"total_ms": total_ms, "fwd_ms": statistics.mean(seg[0]), "bwd_ms": statistics.mean(seg[1]),
+            "wgrad_ms": statistics.mean(seg[2])}
+
+
+def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int, device: torch.device) -> dict:
+    """Same metric through the public API with HOST buffers: pinned inputs -> H2D, rollout + autograd, loss and flat
+    weight gradient -> D2H, every step."""
+    import torch.distributed as dist
+
+    from multimodal_mtrssm_b200 import rollout_ops as R
+    from multimodal_mtrssm_b200 import synthetic
+    from multimodal_mtrssm_b200.params import mtrssm_weight_list
+
+    params = {k: v.to(device).requires_grad_(True) for k, v in synthetic.mtrssm_params().items()}
+    weights = mtrssm_weight_list(params)
+    host = {k: v.pin_memory() for k, v in synthetic.mtrssm_batch(B, T).items()}
+    g = torch.Generator().manual_seed(7)
+    host_up = torch.randn(B, T, 96, generator=g).pin_memory()
+    n_w = sum(w.numel() for w in weights)
+    host_out = torch.empty(n_w + 1).pin_memory()
+    h2d = sum(v.numel() * 4 for v in host.values()) + host_up.numel() * 4
+
+    def step() -> None:
+        dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        up = host_up.to(device, non_blocking=True)
+        out = R.mtrssm_rollout(weights, precision=precision, **dev)
+        loss = (out["feature"] * up).sum() + out["kl_l"].mean() + out["kl_h"].mean()
+        grads = torch.autograd.grad(loss, weights)
+        flat = torch.cat([loss.detach().reshape(1), *[g_.reshape(-1) for g_ in grads]])
+        if world > 1:
+            dist.all_reduce(flat)
+        host_out.copy_(flat, non_blocking=True)
+
+    for _ in range(max(1, warmup // 2)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = max(3, steps // 2)
+    start.record()
+    for _ in range(n):
+        step()
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return {"value": world * B * T * n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (n_w + 1) * 4,
+            "ms_per_step": ms / n, "steps": n}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (the ONLY place bench.py touches oracle/)
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(B: int, T: int, literal: bool, budget_s: float) -> dict:
+    """Times the CPU oracle (fp32, all host threads) on a bounded sample of the same workload: fwd + autograd bwd."""
+    from multimodal_mtrssm_b200 import synthetic
+    from oracle import rssm_oracle as O
+
+    dims = dict(CL=4, KL=4, CH=8, KH=2, l_tau=2.0, h_tau=4.0)
+    params = {k: v.clone().requires_grad_(True) for k, v in synthetic.mtrssm_params().items()}
+    inp = synthetic.mtrssm_batch(B, T)
+    g = torch.Generator().manual_seed(7)
+    up = torch.randn(B, T, 96, generator=g)
+
+    def step() -> None:
+        if literal:
+            x = {k: v for k, v in inp.items() if not k.startswith("u_")}
+            res = O.mtrssm_rollout_literal(params, dims=dims, **x)
+        else:
+            res = O.mtrssm_rollout(params, dims=dims, u_prior_l=None, u_prior_h=None, **inp)
+        kl_l = O.kl_per_sample(res["post_probs_l"], res["prior_probs_l"], True).mean()
+        kl_h = O.kl_per_sample(res["post_probs_h"], res["prior_probs_h"], True).mean()
+        loss = (res["post_feature"] * up).sum() + kl_l + kl_h
+        torch.autograd.grad(loss, list(params.values()), allow_unused=True)
+
+    step()  # warm-up
+    t0 = time.perf_counter()
+    step()
+    one = time.perf_counter() - t0
+    reps = max(1, min(10, int(budget_s / max(one, 1e-3))))
+    times = [one]
+    for _ in range(reps - 1):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    best = statistics.median(times)
+    return {"value": B * T / best, "unit": UNIT, "cores": torch.get_num_threads(), "ms_per_step": best * 1e3,
+            "sample": f"oracle {'literal (reference structure, global RNG)' if literal else 'functional'} fp32 fwd+autograd bwd, "
+                      f"B={B} T={T} of the same workload, median of {len(times)}"}
+
+
+def run_reference(args: argparse.Namespace) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = min(args.batch, max(args.cpu_batch, 256))
+    for _ in range(max(0, min(args.warmup, 1))):
+        pass
+    res = cpu_oracle_rate(B, args.seq_len, literal=True, budget_s=6.0 * max(1, min(args.steps, 5)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MoPoE-MMTRSSM default.yaml sizes, rollout fwd+bwd, T=%d, bounded CPU sample B=%d" % (args.seq_len, B)},
+        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference cannot be imported here (lightning/torchrl/distribution_extension absent, SURVEY.md §8(c)); "
+                "this is the oracle restatement with the reference's per-step structure on the host cores",
+    }
+    print(json.dumps(line))
+
+
+def main() -> None:
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+    from multimodal_mtrssm_b200 import _lib
+
+    precision = _lib.PRECISION_BF16 if args.precision == "bf16" else _lib.PRECISION_FP32
+    B, T = args.batch, args.seq_len
+    launches0 = _lib.launch_count()
+    run = DirectMtrssm(B, T, precision, device)
+    sampler = ClockSampler(local) if rank == 0 else None
+    res = time_direct(run, args.steps, args.warmup, world)
+    clocks = sampler.stop() if sampler else None
+    launches = (_lib.launch_count() - launches0) // (args.steps + args.warmup)
+    e2e = time_e2e(B, T, precision, args.steps, args.warmup, world, device)
+
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        other = DirectMtrssm(B, T, _lib.PRECISION_FP32 if precision == _lib.PRECISION_BF16 else _lib.PRECISION_BF16, device)
+        r2 = time_direct(other, max(3, args.steps // 2), 3, 1)
+        n2 = max(3, args.steps // 2)
+        extras["fp32_path" if precision == _lib.PRECISION_BF16 else "bf16_path"] = {
+            "value": B * T * n2 / (r2["total_ms"] * 1e-3), "ms_per_step": r2["total_ms"] / n2,
+            "fwd_ms": r2["fwd_ms"], "bwd_ms": r2["bwd_ms"], "wgrad_ms": r2["wgrad_ms"]}
+        del other
+        small = DirectMtrssm(8, T, precision, device)
+        r3 = time_direct(small, 50, 10, 1)
+        extras["default_batch8"] = {"B": 8, "T": T, "value": 8 * T * 50 / (r3["total_ms"] * 1e-3), "us_per_step": r3["total_ms"] / 50 * 1e3}
+        del small
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    if rank != 0:
+        return
+
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    ms_step = res["total_ms"] / args.steps
+    value = world * B * T / (ms_step * 1e-3)
+    seg = {"mtrssm_fwd_kernel": res["fwd_ms"], "mtrssm_bwd_kernel": res["bwd_ms"], "wgrad_kernel": res["wgrad_ms"]}
+    dominant = max(seg, key=seg.get)
+    # algorithmic bytes of the dominant launch: forward = fwd I/O; backward (bwd kernel + its wgrad pass) = fwd I/O again
+    if dominant == "mtrssm_fwd_kernel":
+        alg_bytes, dur_ms, what = FWD_BYTES_PER_BT * B * T, seg[dominant], "forward rollout kernel"
+    else:
+        alg_bytes, dur_ms = FWD_BYTES_PER_BT * B * T, res["bwd_ms"] + res["wgrad_ms"]
+        what = "backward = BPTT kernel + weight-gradient kernel (dominant: %s)" % dominant
+    achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if precision == _lib.PRECISION_BF16 else "f32", "data": "synthetic",
+        "config": {
+            "workload": "cfg2: MoPoE-MMTRSSM default.yaml sizes (hd=ld=32, hs=ls=16, E=64, A=6), rollout fwd+bwd on synthetic "
+                        "vision+audio embeddings/actions", "batch_per_gpu": B, "seq_len": T, "global_batch": world * B,
+            "parallelism": f"dp{world} (batch-sharded, one flat-bucket NCCL allreduce of the weight gradients)" if world > 1 else "single GPU",
+            "l2": f"inputs {run.input_bytes() / 1e6:.0f} MB + outputs/records per step exceed the 126 MB L2 (no flush needed)",
+            "precision": "bf16 operands / fp32 accumulate+state (tensor-core path)" if precision == _lib.PRECISION_BF16
+                         else "3-way bf16 split, fp32-level accuracy",
+        },
+        "kernel_ms": seg,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "kernel": what, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes},
+        "roofline_step": {"algorithmic_bytes": STEP_BYTES_PER_BT * B * T, "achieved_gbs": STEP_BYTES_PER_BT * B * T / (ms_step * 1e-3) / 1e9,
+                          "frac_of_hbm": STEP_BYTES_PER_BT * B * T / (ms_step * 1e-3) / 1e9 / peak,
+                          "tensor_tflops": 3 * FWD_FLOPS_PER_BT * B * T / (ms_step * 1e-3) / 1e12},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, **extras,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_oracle_rate(args.cpu_batch, T, literal=False, budget_s=12.0)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "sample")} | {"kind": "port"}
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -8,7 +8,7 @@
  *                            (after the encoders, :215-216; includes Transition.forward networks.py:151-173,
  *                             the posterior heads :62-84, the MoPoE fusion :112-163,241-251, the samples
  *                             state.py:17 and the per-(b,t) KL terms of core.py:212-216)
- *   rssm_mrssm_rollout_bwd   autograd (BPTT) of the above
+ *   rssm_mrssm_rollout_bwd   autograd (BPTT) of the above; rssm_mrssm_wgrad = its weight-gradient half
  *   rssm_mrssm_imagine_fwd   BaseRSSM.rollout_transition           core.py:170-185
  *   rssm_mtrssm_rollout_fwd  MoPoE_MMTRSSM.rollout_representation  mmtrssm/mopoe_mmtrssm/core.py:364-494
  *                            (MTRNN :40-61, lower prior :263-287, heads :241-261, fusion :436-455,
@@ -118,6 +118,10 @@ int rssm_mrssm_rollout_fwd(const RssmMrssmDims *dims, const RssmMrssmWeights *w,
 int rssm_mrssm_rollout_bwd(const RssmMrssmDims *dims, const RssmMrssmWeights *w, const RssmMrssmInputs *in,
                            const RssmMrssmOutputs *fwd_out, const RssmMrssmUpstream *up, const RssmMrssmInputGrads *gin,
                            const RssmMrssmWeightGrads *gw, void *stream);
+/* weight gradients only (the second half of rssm_mrssm_rollout_bwd, which calls it when gw != NULL):
+   dW += dpre^T . layer inputs over all (b,t).  `dpre` is the workspace the backward filled. */
+int rssm_mrssm_wgrad(const RssmMrssmDims *dims, const RssmMrssmInputs *in, const RssmMrssmOutputs *fwd_out, const float *dpre,
+                     const RssmMrssmWeightGrads *gw, void *stream);
 /* imagination: out->feature [B,T,D+S] = [deter | prior sample], out->prior_probs; in->u_prior required;
    in->embed_*, in->u_post, out->post_probs/prior_stoch/kl/saved ignored */
 int rssm_mrssm_imagine_fwd(const RssmMrssmDims *dims, const RssmMrssmWeights *w, const RssmMrssmInputs *in,
@@ -192,6 +196,8 @@ int rssm_mtrssm_rollout_fwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights 
 int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights *w, const RssmMtrssmInputs *in,
                             const RssmMtrssmOutputs *fwd_out, const RssmMtrssmUpstream *up, const RssmMtrssmInputGrads *gin,
                             const RssmMtrssmWeightGrads *gw, void *stream);
+int rssm_mtrssm_wgrad(const RssmMtrssmDims *dims, const RssmMtrssmInputs *in, const RssmMtrssmOutputs *fwd_out, const float *dpre,
+                      const RssmMtrssmWeightGrads *gw, void *stream);
 /* imagination: feature = [deter_h | prior sample h | deter_l | prior sample l], hidden_*, prior_probs_*;
    u_prior_* required */
 int rssm_mtrssm_imagine_fwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights *w, const RssmMtrssmInputs *in,

@@ -86,6 +86,7 @@ MtrssmInputGrads = _struct(
 EXPORTS = (
     "rssm_mrssm_rollout_fwd", "rssm_mrssm_rollout_bwd", "rssm_mrssm_imagine_fwd",
     "rssm_mtrssm_rollout_fwd", "rssm_mtrssm_rollout_bwd", "rssm_mtrssm_imagine_fwd",
+    "rssm_mrssm_wgrad", "rssm_mtrssm_wgrad",
     "rssm_abi_version", "rssm_last_error", "rssm_kernel_launch_count",
 )
 
@@ -101,8 +102,10 @@ def lib() -> C.CDLL:
     handle.rssm_last_error.restype = C.c_char_p
     handle.rssm_kernel_launch_count.restype = C.c_longlong
     P = C.c_void_p
-    for name in EXPORTS[:6]:
+    for name in EXPORTS[:8]:
         getattr(handle, name).restype = C.c_int
+    handle.rssm_mrssm_wgrad.argtypes = [P] * 6
+    handle.rssm_mtrssm_wgrad.argtypes = [P] * 6
     handle.rssm_mrssm_rollout_fwd.argtypes = [P] * 5
     handle.rssm_mrssm_imagine_fwd.argtypes = [P] * 5
     handle.rssm_mrssm_rollout_bwd.argtypes = [P] * 8
@@ -118,7 +121,8 @@ def call(fn_name: str, *args) -> None:  # noqa: ANN002
     """Invoke an entry point on the current CUDA stream; non-zero status -> RuntimeError."""
     handle = lib()
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    status = getattr(handle, fn_name)(*[C.byref(a) if a is not None else None for a in args], stream)
+    cargs = [None if a is None else (C.c_void_p(a) if isinstance(a, int) else C.byref(a)) for a in args]
+    status = getattr(handle, fn_name)(*cargs, stream)
     if status != 0:
         raise RuntimeError(f"{fn_name} failed: {handle.rssm_last_error().decode()}")
 

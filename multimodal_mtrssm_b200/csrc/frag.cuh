@@ -245,13 +245,31 @@ __device__ __forceinline__ void load_a_global(AFrag<NS, KT>& a, const float* __r
 // ------------------------------------------------------------------------------------------
 // elementwise math (fp32; accurate libm variants -- parity first)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-__device__ __forceinline__ float eluf_(float x) { return x > 0.f ? x : expm1f(x); }
+// FAST = false: accurate libm (fp32-parity path).  FAST = true: MUFU approximations (ex2/lg2/tanh/rcp.approx,
+// ~2^-11 relative) -- used by the bf16 tensor-core path, whose operands are already rounded to 8 bits.
+template <bool FAST>
+struct Math {
+    static __device__ __forceinline__ float exp(float x) { return FAST ? __expf(x) : expf(x); }
+    static __device__ __forceinline__ float log(float x) { return FAST ? __logf(x) : logf(x); }
+    static __device__ __forceinline__ float div(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+    static __device__ __forceinline__ float tanh(float x) {
+        if constexpr (FAST) {
+            float y;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+            return y;
+        } else {
+            return tanhf(x);
+        }
+    }
+    static __device__ __forceinline__ float sigmoid(float x) { return div(1.f, 1.f + exp(-x)); }
+    static __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : (FAST ? __expf(x) - 1.f : expm1f(x)); }
+};
 // d ELU / d pre, from the POST-activation value y: y > 0 -> 1, else exp(x) = y + 1
 __device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
 
+template <bool FAST>
 struct EluOp {
-    __device__ __forceinline__ float operator()(float x) const { return eluf_(x); }
+    __device__ __forceinline__ float operator()(float x) const { return Math<FAST>::elu(x); }
 };
 
 template <int NT, typename F>
@@ -290,7 +308,7 @@ __device__ __forceinline__ void group_reduce(float (&v)[2]) {
 }
 
 // per-group softmax (MultiOneHotFactory, A1): p = exp(x - max_g) / sum_g
-template <int K>
+template <int K, bool FAST>
 __device__ __forceinline__ void softmax_groups(const float (&x)[2][4], float (&p)[2][4]) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -299,20 +317,21 @@ __device__ __forceinline__ void softmax_groups(const float (&x)[2][4], float (&p
         float e[2][2], s[2];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
-            e[nt][0] = expf(x[nt][2 * h] - m[nt]);
-            e[nt][1] = expf(x[nt][2 * h + 1] - m[nt]);
+            e[nt][0] = Math<FAST>::exp(x[nt][2 * h] - m[nt]);
+            e[nt][1] = Math<FAST>::exp(x[nt][2 * h + 1] - m[nt]);
             s[nt] = e[nt][0] + e[nt][1];
         }
         group_reduce<K, false>(s);
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
-            p[nt][2 * h] = e[nt][0] / s[nt];
-            p[nt][2 * h + 1] = e[nt][1] / s[nt];
+            p[nt][2 * h] = Math<FAST>::div(e[nt][0], s[nt]);
+            p[nt][2 * h + 1] = Math<FAST>::div(e[nt][1], s[nt]);
         }
     }
 }
 
 // log_softmax over the FLAT 16 columns (F.log_softmax(dim=-1)); optionally also the softmax
+template <bool FAST>
 __device__ __forceinline__ void log_softmax_flat(const float (&x)[2][4], float (&ls)[2][4]) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -320,9 +339,9 @@ __device__ __forceinline__ void log_softmax_flat(const float (&x)[2][4], float (
         group_reduce<16, true>(m);
         float s[2];
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) s[nt] = expf(x[nt][2 * h] - m[0]) + expf(x[nt][2 * h + 1] - m[0]);
+        for (int nt = 0; nt < 2; ++nt) s[nt] = Math<FAST>::exp(x[nt][2 * h] - m[0]) + Math<FAST>::exp(x[nt][2 * h + 1] - m[0]);
         group_reduce<16, false>(s);
-        const float lse = m[0] + logf(s[0]);
+        const float lse = m[0] + Math<FAST>::log(s[0]);
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
             ls[nt][2 * h] = x[nt][2 * h] - lse;
@@ -334,6 +353,7 @@ __device__ __forceinline__ void log_softmax_flat(const float (&x)[2][4], float (
 // MoPoE fusion (mopoe_mrssm/core.py:241-251,135-154): mixed = logsumexp([la, lv, la+lv] + log(1/3)) on
 // flat log-softmaxes.  Also returns the per-expert responsibilities needed by the backward:
 //   ra = (e^la + e^{la+lv}) / (e^la + e^lv + e^{la+lv}),  rv likewise.
+template <bool FAST>
 __device__ __forceinline__ void mopoe_mix(const float (&ls_a)[2][4], const float (&ls_v)[2][4], float (&mixed)[2][4],
                                           float (*ra)[4], float (*rv)[4]) {
     const float LOG_THIRD = -1.0986122886681098f;
@@ -343,12 +363,12 @@ __device__ __forceinline__ void mopoe_mix(const float (&ls_a)[2][4], const float
         for (int j = 0; j < 4; ++j) {
             const float a = ls_a[nt][j], v = ls_v[nt][j], f = a + v;
             const float mx = fmaxf(a, fmaxf(v, f));
-            const float ea = expf(a - mx), ev = expf(v - mx), ef = expf(f - mx);
+            const float ea = Math<FAST>::exp(a - mx), ev = Math<FAST>::exp(v - mx), ef = Math<FAST>::exp(f - mx);
             const float s = ea + ev + ef;
-            mixed[nt][j] = LOG_THIRD + mx + logf(s);
+            mixed[nt][j] = LOG_THIRD + mx + Math<FAST>::log(s);
             if (ra != nullptr) {
-                ra[nt][j] = (ea + ef) / s;
-                rv[nt][j] = (ev + ef) / s;
+                ra[nt][j] = Math<FAST>::div(ea + ef, s);
+                rv[nt][j] = Math<FAST>::div(ev + ef, s);
             }
         }
 }
@@ -410,6 +430,7 @@ __device__ __forceinline__ void softmax_groups_bwd(const float (&p)[2][4], const
 }
 
 // backward of the flat log_softmax: dx = dls - softmax(x) * sum(dls), softmax(x) = exp(ls)
+template <bool FAST>
 __device__ __forceinline__ void log_softmax_flat_bwd(const float (&ls)[2][4], const float (&dls)[2][4], float (&dx)[2][4]) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -417,26 +438,28 @@ __device__ __forceinline__ void log_softmax_flat_bwd(const float (&ls)[2][4], co
         group_reduce<16, false>(s);
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
-            dx[nt][2 * h] = dls[nt][2 * h] - expf(ls[nt][2 * h]) * s[0];
-            dx[nt][2 * h + 1] = dls[nt][2 * h + 1] - expf(ls[nt][2 * h + 1]) * s[0];
+            dx[nt][2 * h] = dls[nt][2 * h] - Math<FAST>::exp(ls[nt][2 * h]) * s[0];
+            dx[nt][2 * h + 1] = dls[nt][2 * h + 1] - Math<FAST>::exp(ls[nt][2 * h + 1]) * s[0];
         }
     }
 }
 
 // KL(q || p) summed over all 16 columns of a row (torch.distributions OneHotCategorical KL with its
 // eps clamp on the logs); result valid in every lane of the quad: out[0] row A, out[1] row B
+template <bool FAST>
 __device__ __forceinline__ float clamp_log(float p) {
     const float eps = 1.1920928955078125e-07f;
-    return logf(fminf(fmaxf(p, eps), 1.f - eps));
+    return Math<FAST>::log(fminf(fmaxf(p, eps), 1.f - eps));
 }
+template <bool FAST>
 __device__ __forceinline__ void kl_rows(const float (&q)[2][4], const float (&p)[2][4], float (&out)[2]) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         float s[2];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
-            s[nt] = q[nt][2 * h] * (clamp_log(q[nt][2 * h]) - clamp_log(p[nt][2 * h])) +
-                    q[nt][2 * h + 1] * (clamp_log(q[nt][2 * h + 1]) - clamp_log(p[nt][2 * h + 1]));
+            s[nt] = q[nt][2 * h] * (clamp_log<FAST>(q[nt][2 * h]) - clamp_log<FAST>(p[nt][2 * h])) +
+                    q[nt][2 * h + 1] * (clamp_log<FAST>(q[nt][2 * h + 1]) - clamp_log<FAST>(p[nt][2 * h + 1]));
         }
         group_reduce<16, false>(s);
         out[h] = s[0];
@@ -445,6 +468,7 @@ __device__ __forceinline__ void kl_rows(const float (&q)[2][4], const float (&p)
 
 // d KL / d q (weight wq) and d KL / d p (weight wp), added into dq / dp.  dkl[h] = upstream grad of the
 // row's KL.  dKL/dq_k = log q_k - log p_k + 1 ; dKL/dp_k = -q_k / p_k.
+template <bool FAST>
 __device__ __forceinline__ void kl_rows_bwd(const float (&q)[2][4], const float (&p)[2][4], const float (&dkl)[2], float wq, float wp,
                                             float (&dq)[2][4], float (&dp)[2][4]) {
 #pragma unroll
@@ -452,8 +476,8 @@ __device__ __forceinline__ void kl_rows_bwd(const float (&q)[2][4], const float 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float g = dkl[j >> 1];
-            dq[nt][j] += g * wq * (clamp_log(q[nt][j]) - clamp_log(p[nt][j]) + 1.f);
-            dp[nt][j] -= g * wp * q[nt][j] / fmaxf(p[nt][j], 1.1920928955078125e-07f);
+            dq[nt][j] += g * wq * (clamp_log<FAST>(q[nt][j]) - clamp_log<FAST>(p[nt][j]) + 1.f);
+            dp[nt][j] -= g * wp * Math<FAST>::div(q[nt][j], fmaxf(p[nt][j], 1.1920928955078125e-07f));
         }
 }
 

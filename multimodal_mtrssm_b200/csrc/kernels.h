@@ -53,22 +53,37 @@ struct MtrssmBwdArgs {
 cudaError_t launch_mtrssm_fwd(const MtrssmFwdArgs& a, int precision, bool imagine, cudaStream_t s);
 cudaError_t launch_mtrssm_bwd(const MtrssmBwdArgs& a, int precision, cudaStream_t s);
 
-// ---- batched weight gradient: dW[n][col0 + k] += sum_rows dY[row][n] * X[row'][k] ------------------
-// rows = (b,t), b < B, t < T.  X row for (b,t): shift == 0 -> X[(b*T + t) * ldx]; shift == 1 -> the
-// PREVIOUS step's row, X[(b*T + t - 1) * ldx] for t > 0 and X0[b * ldx0] for t == 0.
-struct WgradJob {
-    const float* dY;
-    const float* X;
-    const float* X0;
+// ---- batched weight gradients on the tensor cores (wgrad_kernel.cu) -----------------------------------------------
+// A staged shared-memory row holds, per (b,t), the dpre record followed by every layer's input, as bf16 columns.
+struct WgradSeg {       // one source column range copied into the staged row
+    const float* ptr;   // row (b,t) at ptr + (b*T + t) * ld          (shift == 0)
+    const float* ptr0;  // shift == 1: row (b,t-1) for t > 0, ptr0 + b * ld0 for t == 0
+    int ld, ld0, ncols /* multiple of 4 */, valid /* real columns, rest zero */, dst /* staged column */, shift, vec;
+};
+struct WgradOut {  // destination of one part: dW[n][k] at dW + n*ldw + k for k < kvalid; up to two bias vectors
     float* dW;
-    float* db;  // optional: db[n] += sum_rows dY[row][n]
-    int ldy, ldx, ldx0, ldw, N, K, shift;
+    float* db0;
+    float* db1;
+    int ldw, kvalid;
 };
-constexpr int MAX_WGRAD_JOBS = 24;
-struct WgradArgs {
-    int B, T, njobs;
-    WgradJob jobs[MAX_WGRAD_JOBS];
+constexpr int MAX_WGRAD_SEGS = 16, MAX_WGRAD_OUTS = 24;
+struct WgradMmaArgs {
+    int B, T, nseg, stride;
+    WgradSeg seg[MAX_WGRAD_SEGS];
+    WgradOut out[MAX_WGRAD_OUTS];
 };
-cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t s);
+// model: 0 = MMTRSSM, 1 = MRSSM
+cudaError_t launch_wgrad_mma(const WgradMmaArgs& a, int model, int precision, cudaStream_t s);
+
+// staged-row column layouts (bf16 elements) and part ids
+namespace wgl_mt {
+constexpr int DP = 0, XLD = 304, XLZ = 336, XLA = 368, XHD = 376, XHI = 408, XQ = 424, XA = 488, XV = 584, HID = 680, STRIDE = 840;
+enum { O_LD, O_LIZ, O_LIA, O_HD, O_HI, O_LP1, O_LP2, O_HP1, O_HP2, O_HQ1, O_HQ2, O_A1A, O_A1B, O_A2, O_V1A, O_V1B, O_V2, N_OUT };
+}  // namespace wgl_mt
+namespace wgl_mr {
+constexpr int DP = 0, XASPZ = 336, XASPA = 352, XH1 = 360, XX2 = 392, XHP = 424, XA = 456, XV = 552, HID = 648, STRIDE = 744;
+enum { O_ASP1Z, O_ASP1A, O_ASP2, O_IHR, O_IHZ, O_IHN, O_HHR, O_HHZ, O_HHN, O_P1, O_P2, O_A1A, O_A1B, O_A2, O_V1A, O_V1B_L, O_V1B_R, O_V2, N_OUT };
+}  // namespace wgl_mr
+static_assert((wgl_mt::STRIDE * 2 / 16) % 2 == 1 && (wgl_mr::STRIDE * 2 / 16) % 2 == 1, "row stride must be an odd number of 16B chunks (ldmatrix bank-conflict free)");
 
 }  // namespace rssm

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             load_a_global<NS, 1>(fa, p.actions + iA * A, p.actions + iB * A, r.t, A);
             gemm<NS, 1, 4>(acc, zf, wblock<NS>(W, mr::ASP1Z), lane);
             gemm<NS, 1, 4>(acc, fa, wblock<NS>(W, mr::ASP1A), lane);
-            map_c<4>(acc, EluOp{});
+            map_c<4>(acc, EluOp<NS == 1>{});
             if (svA) store_c<4>(acc, svA + mrs::ASP_HID, svB + mrs::ASP_HID, r);
             AFrag<NS, 2> f1;
             to_afrag<NS, 2>(f1, acc);
@@ -185,9 +185,9 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    rg[nt][j] = sigmoidf_(grz[nt][j]);
-                    zg[nt][j] = sigmoidf_(grz[4 + nt][j]);
-                    ng[nt][j] = tanhf(gin[nt][j] + rg[nt][j] * ghn[nt][j]);
+                    rg[nt][j] = Math<NS == 1>::sigmoid(grz[nt][j]);
+                    zg[nt][j] = Math<NS == 1>::sigmoid(grz[4 + nt][j]);
+                    ng[nt][j] = Math<NS == 1>::tanh(gin[nt][j] + rg[nt][j] * ghn[nt][j]);
                     h[nt][j] = (h[nt][j] - ng[nt][j]) * zg[nt][j] + ng[nt][j];
                 }
             if (svA) {
@@ -205,14 +205,14 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             float acc[4][4];
             init_bias<4>(acc, bias + mr::B_P1, r.t);
             gemm<NS, 2, 4>(acc, hf, wblock<NS>(W, mr::P1), lane);
-            map_c<4>(acc, EluOp{});
+            map_c<4>(acc, EluOp<NS == 1>{});
             if (svA) store_c<4>(acc, svA + mrs::P_HID, svB + mrs::P_HID, r);
             AFrag<NS, 2> f1;
             to_afrag<NS, 2>(f1, acc);
             float lp[2][4];
             init_bias<2>(lp, bias + mr::B_P2, r.t);
             gemm<NS, 2, 2>(lp, f1, wblock<NS>(W, mr::P2), lane);
-            softmax_groups<K>(lp, pp);
+            softmax_groups<K, NS == 1>(lp, pp);
             store_c<2>(pp, p.prior_probs + iA * 16, p.prior_probs + iB * 16, r);
         }
         if (p.u_prior != nullptr) {  // State(prior) draws its own sample (networks.py:173 -> state.py:17)
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             load_a_global<NS, 4>(fe, emb + iA * 64, emb + iB * 64, r.t, 64);
             gemm<NS, 2, 4>(acc, hf, wblock<NS>(W, m == 0 ? mr::A1H : mr::V1H), lane);
             gemm<NS, 4, 4>(acc, fe, wblock<NS>(W, m == 0 ? mr::A1E : mr::V1E), lane);
-            map_c<4>(acc, EluOp{});
+            map_c<4>(acc, EluOp<NS == 1>{});
             if (svA) store_c<4>(acc, svA + (m == 0 ? mrs::A_HID : mrs::V_HID), svB + (m == 0 ? mrs::A_HID : mrs::V_HID), r);
             AFrag<NS, 2> f1;
             to_afrag<NS, 2>(f1, acc);
@@ -249,16 +249,16 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
         // ---- MoPoE fusion, factory, sample, KL (mopoe_mrssm/core.py:241-251,135-163) --------------
         {
             float lsa[2][4], lsv[2][4], mixed[2][4], q[2][4], zs[2][4];
-            log_softmax_flat(la, lsa);
-            log_softmax_flat(lv, lsv);
-            mopoe_mix(lsa, lsv, mixed, nullptr, nullptr);
-            softmax_groups<K>(mixed, q);
+            log_softmax_flat<NS == 1>(la, lsa);
+            log_softmax_flat<NS == 1>(lv, lsv);
+            mopoe_mix<NS == 1>(lsa, lsv, mixed, nullptr, nullptr);
+            softmax_groups<K, NS == 1>(mixed, q);
             store_c<2>(q, p.post_probs + iA * 16, p.post_probs + iB * 16, r);
             sample_onehot<K>(q, p.u_post + iA * C, p.u_post + iB * C, zs, lane);
             store_c<2>(zs, p.feature + iA * F + 32, p.feature + iB * F + 32, r);
             to_afrag<NS, 1>(zf, zs);  // prev_state = mixed_posterior (mopoe_mrssm/core.py:256)
             float kl[2];
-            kl_rows(q, pp, kl);
+            kl_rows<NS == 1>(q, pp, kl);
             if (r.t == 0) {
                 if (r.vA) p.kl[iA] = kl[0];
                 if (r.vB) p.kl[iB] = kl[1];
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
         }
         if (p.d_kl != nullptr) {
             const float dkl[2] = {p.d_kl[iA], p.d_kl[iB]};
-            kl_rows_bwd(q, pp, dkl, p.kl_wq, p.kl_wp, dq, dpp);
+            kl_rows_bwd<NS == 1>(q, pp, dkl, p.kl_wq, p.kl_wp, dq, dpp);
         }
 
         // ---- posterior: factory softmax -> MoPoE mix -> flat log-softmaxes -> heads -----------------
@@ -369,9 +369,9 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
             float la[2][4], lv[2][4], lsa[2][4], lsv[2][4], mixed[2][4], ra[2][4], rv[2][4];
             load_c<2>(la, svA + mrs::LA, svB + mrs::LA, r.t);
             load_c<2>(lv, svA + mrs::LV, svB + mrs::LV, r.t);
-            log_softmax_flat(la, lsa);
-            log_softmax_flat(lv, lsv);
-            mopoe_mix(lsa, lsv, mixed, ra, rv);
+            log_softmax_flat<NS == 1>(la, lsa);
+            log_softmax_flat<NS == 1>(lv, lsv);
+            mopoe_mix<NS == 1>(lsa, lsv, mixed, ra, rv);
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -379,8 +379,8 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
                     ra[nt][j] *= dm[nt][j];
                     rv[nt][j] *= dm[nt][j];
                 }
-            log_softmax_flat_bwd(lsa, ra, dla);
-            log_softmax_flat_bwd(lsv, rv, dlv);
+            log_softmax_flat_bwd<NS == 1>(lsa, ra, dla);
+            log_softmax_flat_bwd<NS == 1>(lsv, rv, dlv);
         }
         store_c<2>(dla, dpA + mrd::LA, dpB + mrd::LA, r);
         store_c<2>(dlv, dpA + mrd::LV, dpB + mrd::LV, r);

@@ -65,7 +65,7 @@ __device__ __forceinline__ uint2* wblk(uint2* W, int tile_off) {
 template <int NS>
 __device__ __forceinline__ void head_l2(float (&acc)[4][4], float (&logits)[2][4], const float* bias2, const uint2* w2, float* svA,
                                         float* svB, int sv_off, const Rows& r, int lane) {
-    map_c<4>(acc, EluOp{});
+    map_c<4>(acc, EluOp<NS == 1>{});
     if (svA) store_c<4>(acc, svA + sv_off, svB + sv_off, r);
     AFrag<NS, 2> f1;
     to_afrag<NS, 2>(f1, acc);
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) 
                 for (int j = 0; j < 4; ++j) {
                     ul[nt][j] = keep_l * ul[nt][j] + pl[nt][j] * p.inv_tau_l;
                     uh[nt][j] = keep_h * uh[nt][j] + ph[nt][j] * p.inv_tau_h;
-                    dl[nt][j] = tanhf(ul[nt][j]);
-                    dh[nt][j] = tanhf(uh[nt][j]);
+                    dl[nt][j] = Math<NS == 1>::tanh(ul[nt][j]);
+                    dh[nt][j] = Math<NS == 1>::tanh(uh[nt][j]);
                 }
             store_c<4>(dh, p.feature + iA * F, p.feature + iB * F, r);
             store_c<4>(dl, p.feature + iA * F + 48, p.feature + iB * F + 48, r);
@@ -196,12 +196,12 @@ __global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) 
             init_bias<4>(acc, bias + mt::B_LP1, r.t);
             gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, mt::LP1), lane);
             head_l2<NS>(acc, lg, bias + mt::B_LP2, wblk<NS>(W, mt::LP2), svA, svB, mts::LP_HID, r, lane);
-            softmax_groups<KL>(lg, ppl);
+            softmax_groups<KL, NS == 1>(lg, ppl);
             store_c<2>(ppl, p.prior_probs_l + iA * 16, p.prior_probs_l + iB * 16, r);
             init_bias<4>(acc, bias + mt::B_HP1, r.t);
             gemm<NS, 2, 4>(acc, dhf, wblk<NS>(W, mt::HP1), lane);
             head_l2<NS>(acc, lg, bias + mt::B_HP2, wblk<NS>(W, mt::HP2), svA, svB, mts::HP_HID, r, lane);
-            softmax_groups<KH>(lg, pph);
+            softmax_groups<KH, NS == 1>(lg, pph);
             store_c<2>(pph, p.prior_probs_h + iA * 16, p.prior_probs_h + iB * 16, r);
         }
         if (p.u_prior_l != nullptr) {  // prior MTState ctor draws h then l (:467-474 -> state.py:48-49)
@@ -237,16 +237,16 @@ __global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) 
         }
         {
             float lsa[2][4], lsv[2][4], mixed[2][4], q[2][4], zs[2][4];
-            log_softmax_flat(la, lsa);
-            log_softmax_flat(lv, lsv);
-            mopoe_mix(lsa, lsv, mixed, nullptr, nullptr);
-            softmax_groups<KL>(mixed, q);
+            log_softmax_flat<NS == 1>(la, lsa);
+            log_softmax_flat<NS == 1>(lv, lsv);
+            mopoe_mix<NS == 1>(lsa, lsv, mixed, nullptr, nullptr);
+            softmax_groups<KL, NS == 1>(mixed, q);
             store_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r);
             sample_onehot<KL>(q, p.u_post_l + iA * CL, p.u_post_l + iB * CL, zs, lane);
             store_c<2>(zs, p.feature + iA * F + 80, p.feature + iB * F + 80, r);
             to_afrag<NS, 1>(zlf, zs);
             float kl[2];
-            kl_rows(q, ppl, kl);
+            kl_rows<NS == 1>(q, ppl, kl);
             if (r.t == 0) {
                 if (r.vA) p.kl_l[iA] = kl[0];
                 if (r.vB) p.kl_l[iB] = kl[1];
@@ -259,13 +259,13 @@ __global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) 
             gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, mt::HQ1L), lane);
             gemm<NS, 2, 4>(acc, dhf, wblk<NS>(W, mt::HQ1H), lane);
             head_l2<NS>(acc, lg, bias + mt::B_HQ2, wblk<NS>(W, mt::HQ2), svA, svB, mts::HQ_HID, r, lane);
-            softmax_groups<KH>(lg, q);
+            softmax_groups<KH, NS == 1>(lg, q);
             store_c<2>(q, p.post_probs_h + iA * 16, p.post_probs_h + iB * 16, r);
             sample_onehot<KH>(q, p.u_post_h + iA * CH, p.u_post_h + iB * CH, zs, lane);
             store_c<2>(zs, p.feature + iA * F + 32, p.feature + iB * F + 32, r);
             to_afrag<NS, 1>(zhf, zs);
             float kl[2];
-            kl_rows(q, pph, kl);
+            kl_rows<NS == 1>(q, pph, kl);
             if (r.t == 0) {
                 if (r.vA) p.kl_h[iA] = kl[0];
                 if (r.vB) p.kl_h[iB] = kl[1];
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) 
             add_global<2>(dpp, p.d_prior_stoch_h, iA * 16, iB * 16, r.t);
             if (p.d_kl_h != nullptr) {
                 const float dkl[2] = {p.d_kl_h[iA], p.d_kl_h[iB]};
-                kl_rows_bwd(q, pp, dkl, p.kl_wq, p.kl_wp, dzh, dpp);
+                kl_rows_bwd<NS == 1>(q, pp, dkl, p.kl_wq, p.kl_wp, dzh, dpp);
             }
             float dlg[2][4];
             AFrag<NS, 2> f1;
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) 
             add_global<2>(dpp, p.d_prior_stoch_l, iA * 16, iB * 16, r.t);
             if (p.d_kl_l != nullptr) {
                 const float dkl[2] = {p.d_kl_l[iA], p.d_kl_l[iB]};
-                kl_rows_bwd(q, pp, dkl, p.kl_wq, p.kl_wp, dzl, dpp);
+                kl_rows_bwd<NS == 1>(q, pp, dkl, p.kl_wq, p.kl_wp, dzl, dpp);
             }
             float dla[2][4], dlv[2][4];
             {
@@ -406,9 +406,9 @@ __global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) 
                 softmax_groups_bwd<KL>(q, dzl, dm);
                 load_c<2>(la, svA + mts::LA, svB + mts::LA, r.t);
                 load_c<2>(lv, svA + mts::LV, svB + mts::LV, r.t);
-                log_softmax_flat(la, lsa);
-                log_softmax_flat(lv, lsv);
-                mopoe_mix(lsa, lsv, mixed, ra, rv);
+                log_softmax_flat<NS == 1>(la, lsa);
+                log_softmax_flat<NS == 1>(lv, lsv);
+                mopoe_mix<NS == 1>(lsa, lsv, mixed, ra, rv);
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -416,8 +416,8 @@ __global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) 
                         ra[nt][j] *= dm[nt][j];
                         rv[nt][j] *= dm[nt][j];
                     }
-                log_softmax_flat_bwd(lsa, ra, dla);
-                log_softmax_flat_bwd(lsv, rv, dlv);
+                log_softmax_flat_bwd<NS == 1>(lsa, ra, dla);
+                log_softmax_flat_bwd<NS == 1>(lsv, rv, dlv);
             }
 #pragma unroll
             for (int m = 0; m < 2; ++m) {

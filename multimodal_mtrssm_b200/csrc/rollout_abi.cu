@@ -3,6 +3,7 @@
 // caller's stream.  No hidden state; errors are reported through a thread-local message.
 #include <atomic>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 
 #include "kernels.h"
@@ -60,11 +61,19 @@ int check_mtrssm(const RssmMtrssmDims* d) {
         if ((ptr) == nullptr) return fail("required pointer %s is NULL", #ptr); \
     } while (0)
 
-void add_job(rssm::WgradArgs& a, const float* dY, int ldy, int N, const float* X, int ldx, int K, float* dW, int ldw, float* db,
-             int shift = 0, const float* X0 = nullptr, int ldx0 = 0) {
-    rssm::WgradJob& j = a.jobs[a.njobs++];
-    j.dY = dY, j.ldy = ldy, j.N = N, j.X = X, j.ldx = ldx, j.K = K, j.dW = dW, j.ldw = ldw, j.db = db;
-    j.shift = shift, j.X0 = X0 ? X0 : X, j.ldx0 = X0 ? ldx0 : ldx;
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+void add_seg(rssm::WgradMmaArgs& a, int dst, const float* ptr, int ld, int valid, int shift = 0, const float* ptr0 = nullptr,
+             int ld0 = 0) {
+    rssm::WgradSeg& s = a.seg[a.nseg++];
+    s.ptr = ptr, s.ptr0 = ptr0 ? ptr0 : ptr, s.ld = ld, s.ld0 = ptr0 ? ld0 : ld;
+    s.valid = valid, s.ncols = (valid + 3) & ~3, s.dst = dst, s.shift = shift;
+    s.vec = (valid % 4 == 0) && (s.ld % 4 == 0) && (s.ld0 % 4 == 0) && aligned16(s.ptr) && aligned16(s.ptr0);
+}
+
+void set_out(rssm::WgradMmaArgs& a, int id, float* dW, int ldw, int kvalid, float* db0 = nullptr, float* db1 = nullptr) {
+    rssm::WgradOut& o = a.out[id];
+    o.dW = dW, o.ldw = ldw, o.kvalid = kvalid, o.db0 = db0, o.db1 = db1;
 }
 
 }  // namespace
@@ -130,35 +139,54 @@ int rssm_mrssm_rollout_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, co
     g_launches.fetch_add(1);
     if (check_cuda(rssm::launch_mrssm_bwd(a, d->precision, s), "mrssm backward launch")) return 1;
     if (gw == nullptr) return 0;
+    return rssm_mrssm_wgrad(d, in, fo, gin->dpre, gw, stream);
+}
 
-    // weight gradients: dW = dpre^T . layer input  (record offsets: mrssm_kernels.cu, namespaces mrs / mrd)
-    const int A = d->A, F = 48, SV = MRSSM_SAVED_FLOATS, DP = MRSSM_DPRE_FLOATS;
-    const float *dp = gin->dpre, *sv = fo->saved, *feat = fo->feature;
-    rssm::WgradArgs j{};
-    j.B = d->B, j.T = d->T;
-    // action_state_projector.0 : input [action | z_prev]
-    add_job(j, dp + 0, DP, 32, in->actions, A, A, gw->asp_w1, A + 16, gw->asp_b1);
-    add_job(j, dp + 0, DP, 32, feat + 32, F, 16, gw->asp_w1 + A, A + 16, nullptr, 1, in->z0, 16);
-    // action_state_projector.2 : input asp hidden
-    add_job(j, dp + 32, DP, 32, sv + 0, SV, 32, gw->asp_w2, 32, gw->asp_b2);
-    // GRU: weight_ih <- [dpre_r,dpre_z,dpre_n] x x2 ; weight_hh <- [dpre_r,dpre_z | d h_n] x h_prev
-    add_job(j, dp + 64, DP, 96, sv + 32, SV, 32, gw->w_ih, 32, gw->b_ih);
-    add_job(j, dp + 64, DP, 64, feat, F, 32, gw->w_hh, 32, gw->b_hh, 1, in->h0, 32);
-    add_job(j, dp + 160, DP, 32, feat, F, 32, gw->w_hh + 64 * 32, 32, gw->b_hh + 64, 1, in->h0, 32);
-    // prior head
-    add_job(j, dp + 192, DP, 32, feat, F, 32, gw->pr_w1, 32, gw->pr_b1);
-    add_job(j, dp + 224, DP, 16, sv + 192, SV, 32, gw->pr_w2, 32, gw->pr_b2);
-    // audio / vision heads : input [deter | embed]
-    add_job(j, dp + 240, DP, 32, feat, F, 32, gw->au_w1, 96, gw->au_b1);
-    add_job(j, dp + 240, DP, 32, in->embed_a, 64, 64, gw->au_w1 + 32, 96, nullptr);
-    add_job(j, dp + 272, DP, 16, sv + 224, SV, 32, gw->au_w2, 32, gw->au_b2);
-    add_job(j, dp + 288, DP, 32, feat, F, 32, gw->vi_w1, 96, gw->vi_b1);
-    add_job(j, dp + 288, DP, 32, in->embed_v, 64, 64, gw->vi_w1 + 32, 96, nullptr);
-    add_job(j, dp + 320, DP, 16, sv + 256, SV, 32, gw->vi_w2, 32, gw->vi_b2);
-    for (int i = 0; i < j.njobs; ++i)
-        if (j.jobs[i].dW == nullptr) return fail("weight-gradient pointer of job %d is NULL", i);
+int rssm_mrssm_wgrad(const RssmMrssmDims* d, const RssmMrssmInputs* in, const RssmMrssmOutputs* fo, const float* dpre,
+                     const RssmMrssmWeightGrads* gw, void* stream) {
+    if (check_mrssm(d)) return 1;
+    REQUIRE(in); REQUIRE(fo); REQUIRE(dpre); REQUIRE(gw);
+    REQUIRE(in->actions); REQUIRE(in->embed_a); REQUIRE(in->embed_v); REQUIRE(in->h0); REQUIRE(in->z0);
+    REQUIRE(fo->feature); REQUIRE(fo->saved);
+    // staged-row layout and part ids: kernels.h (wgl_mr); record offsets: mrssm_kernels.cu (mrs / mrd)
+    using namespace rssm::wgl_mr;
+    const int A = d->A, F = 48, SV = MRSSM_SAVED_FLOATS, DPF = MRSSM_DPRE_FLOATS;
+    const float *sv = fo->saved, *feat = fo->feature;
+    rssm::WgradMmaArgs j{};
+    j.B = d->B, j.T = d->T, j.stride = STRIDE;
+    add_seg(j, DP, dpre, DPF, DPF);
+    add_seg(j, XASPZ, feat + 32, F, 16, 1, in->z0, 16);   // z_prev
+    add_seg(j, XASPA, in->actions, A, A);                 // action (+ zero pad to 8)
+    add_seg(j, XH1, sv + 0, SV, 32);                      // asp hidden
+    add_seg(j, XX2, sv + 32, SV, 32);                     // x2 (GRU input)
+    add_seg(j, XHP, feat, F, 32, 1, in->h0, 32);          // h_prev
+    add_seg(j, XA, feat, F, 32);                          // [h | embed_a]
+    add_seg(j, XA + 32, in->embed_a, 64, 64);
+    add_seg(j, XV, feat, F, 32);                          // [h | embed_v]
+    add_seg(j, XV + 32, in->embed_v, 64, 64);
+    add_seg(j, HID, sv + 192, SV, 96);                    // prior / audio / vision hidden
+    set_out(j, O_ASP1Z, gw->asp_w1 + A, A + 16, 16, gw->asp_b1);
+    set_out(j, O_ASP1A, gw->asp_w1, A + 16, A);
+    set_out(j, O_ASP2, gw->asp_w2, 32, 32, gw->asp_b2);
+    set_out(j, O_IHR, gw->w_ih, 32, 32, gw->b_ih);
+    set_out(j, O_IHZ, gw->w_ih + 32 * 32, 32, 32, gw->b_ih + 32);
+    set_out(j, O_IHN, gw->w_ih + 64 * 32, 32, 32, gw->b_ih + 64);
+    set_out(j, O_HHR, gw->w_hh, 32, 32, gw->b_hh);
+    set_out(j, O_HHZ, gw->w_hh + 32 * 32, 32, 32, gw->b_hh + 32);
+    set_out(j, O_HHN, gw->w_hh + 64 * 32, 32, 32, gw->b_hh + 64);
+    set_out(j, O_P1, gw->pr_w1, 32, 32, gw->pr_b1);
+    set_out(j, O_P2, gw->pr_w2, 32, 32, gw->pr_b2);
+    set_out(j, O_A1A, gw->au_w1, 96, 96, gw->au_b1);
+    set_out(j, O_A1B, gw->au_w1 + 16 * 96, 96, 96, gw->au_b1 + 16);
+    set_out(j, O_A2, gw->au_w2, 32, 32, gw->au_b2);
+    set_out(j, O_V1A, gw->vi_w1, 96, 96, gw->vi_b1);
+    set_out(j, O_V1B_L, gw->vi_w1 + 16 * 96, 96, 48, gw->vi_b1 + 16);
+    set_out(j, O_V1B_R, gw->vi_w1 + 16 * 96 + 48, 96, 48);
+    set_out(j, O_V2, gw->vi_w2, 32, 32, gw->vi_b2);
+    for (int i = 0; i < N_OUT; ++i)
+        if (j.out[i].dW == nullptr) return fail("weight-gradient pointer of part %d is NULL", i);
     g_launches.fetch_add(1);
-    return check_cuda(rssm::launch_wgrad(j, s), "mrssm wgrad launch");
+    return check_cuda(rssm::launch_wgrad_mma(j, 1, d->precision, static_cast<cudaStream_t>(stream)), "mrssm wgrad launch");
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -235,39 +263,58 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
     g_launches.fetch_add(1);
     if (check_cuda(rssm::launch_mtrssm_bwd(a, d->precision, s), "mtrssm backward launch")) return 1;
     if (gw == nullptr) return 0;
+    return rssm_mtrssm_wgrad(d, in, fo, gin->dpre, gw, stream);
+}
 
-    // record offsets: mtrssm_kernels.cu, namespaces mts / mtd; feature = [d_h 0 | z_h 32 | d_l 48 | z_l 80]
-    const int A = d->A, F = 96, SV = MTRSSM_SAVED_FLOATS, DP = MTRSSM_DPRE_FLOATS, LDIN = A + 32;
-    const float *dp = gin->dpre, *sv = fo->saved, *feat = fo->feature;
-    rssm::WgradArgs j{};
-    j.B = d->B, j.T = d->T;
+int rssm_mtrssm_wgrad(const RssmMtrssmDims* d, const RssmMtrssmInputs* in, const RssmMtrssmOutputs* fo, const float* dpre,
+                      const RssmMtrssmWeightGrads* gw, void* stream) {
+    if (check_mtrssm(d)) return 1;
+    REQUIRE(in); REQUIRE(fo); REQUIRE(dpre); REQUIRE(gw);
+    REQUIRE(in->actions); REQUIRE(in->embed_a); REQUIRE(in->embed_v); REQUIRE(in->deter_h0); REQUIRE(in->deter_l0);
+    REQUIRE(in->stoch_h0); REQUIRE(in->stoch_l0); REQUIRE(fo->feature); REQUIRE(fo->saved);
+    // staged-row layout and part ids: kernels.h (wgl_mt); record offsets: mtrssm_kernels.cu (mts / mtd);
+    // feature = [d_h 0 | z_h 32 | d_l 48 | z_l 80]
+    using namespace rssm::wgl_mt;
+    const int A = d->A, F = 96, SV = MTRSSM_SAVED_FLOATS, DPF = MTRSSM_DPRE_FLOATS, LDIN = A + 32;
+    const float *sv = fo->saved, *feat = fo->feature;
+    rssm::WgradMmaArgs j{};
+    j.B = d->B, j.T = d->T, j.stride = STRIDE;
+    add_seg(j, DP, dpre, DPF, DPF);
+    add_seg(j, XLD, feat + 48, F, 32, 1, in->deter_l0, 32);     // d_l_prev
+    add_seg(j, XLZ, feat + 80, F, 16, 1, in->stoch_l0, 16);     // z_l_prev
+    add_seg(j, XLZ + 16, feat + 32, F, 16, 1, in->stoch_h0, 16);  // z_h_prev
+    add_seg(j, XLA, in->actions, A, A);                          // action (+ zero pad to 8)
+    add_seg(j, XHD, feat + 0, F, 32, 1, in->deter_h0, 32);      // d_h_prev
+    add_seg(j, XHI, feat + 32, F, 16, 1, in->stoch_h0, 16);     // z_h_prev
+    add_seg(j, XQ, feat + 48, F, 32);                            // [d_l | d_h]
+    add_seg(j, XQ + 32, feat + 0, F, 32);
+    add_seg(j, XA, feat + 48, F, 32);                            // [d_l | embed_a]
+    add_seg(j, XA + 32, in->embed_a, 64, 64);
+    add_seg(j, XV, feat + 48, F, 32);                            // [d_l | embed_v]
+    add_seg(j, XV + 32, in->embed_v, 64, 64);
+    add_seg(j, HID, sv, SV, 160);                                // the five head hiddens
     // l_rnn: pre_l = _d2h(d_l_prev) + _input2h([action | z_l_prev | z_h_prev]); both biases see sum(dpre_l)
-    add_job(j, dp + 0, DP, 32, feat + 48, F, 32, gw->l_d2h_w, 32, gw->l_d2h_b, 1, in->deter_l0, 32);
-    add_job(j, dp + 0, DP, 32, in->actions, A, A, gw->l_in_w, LDIN, gw->l_in_b);
-    add_job(j, dp + 0, DP, 32, feat + 80, F, 16, gw->l_in_w + A, LDIN, nullptr, 1, in->stoch_l0, 16);
-    add_job(j, dp + 0, DP, 32, feat + 32, F, 16, gw->l_in_w + A + 16, LDIN, nullptr, 1, in->stoch_h0, 16);
-    // h_rnn: pre_h = _d2h(d_h_prev) + _input2h(z_h_prev)
-    add_job(j, dp + 32, DP, 32, feat + 0, F, 32, gw->h_d2h_w, 32, gw->h_d2h_b, 1, in->deter_h0, 32);
-    add_job(j, dp + 32, DP, 32, feat + 32, F, 16, gw->h_in_w, 16, gw->h_in_b, 1, in->stoch_h0, 16);
-    // l_prior / h_prior / h_posterior
-    add_job(j, dp + 64, DP, 32, feat + 48, F, 32, gw->lp_w1, 32, gw->lp_b1);
-    add_job(j, dp + 96, DP, 16, sv + 0, SV, 32, gw->lp_w2, 32, gw->lp_b2);
-    add_job(j, dp + 112, DP, 32, feat + 0, F, 32, gw->hp_w1, 32, gw->hp_b1);
-    add_job(j, dp + 144, DP, 16, sv + 32, SV, 32, gw->hp_w2, 32, gw->hp_b2);
-    add_job(j, dp + 160, DP, 32, feat + 48, F, 32, gw->hq_w1, 64, gw->hq_b1);
-    add_job(j, dp + 160, DP, 32, feat + 0, F, 32, gw->hq_w1 + 32, 64, nullptr);
-    add_job(j, dp + 192, DP, 16, sv + 64, SV, 32, gw->hq_w2, 32, gw->hq_b2);
-    // audio / vision heads on [d_l | embed]
-    add_job(j, dp + 208, DP, 32, feat + 48, F, 32, gw->au_w1, 96, gw->au_b1);
-    add_job(j, dp + 208, DP, 32, in->embed_a, 64, 64, gw->au_w1 + 32, 96, nullptr);
-    add_job(j, dp + 240, DP, 16, sv + 96, SV, 32, gw->au_w2, 32, gw->au_b2);
-    add_job(j, dp + 256, DP, 32, feat + 48, F, 32, gw->vi_w1, 96, gw->vi_b1);
-    add_job(j, dp + 256, DP, 32, in->embed_v, 64, 64, gw->vi_w1 + 32, 96, nullptr);
-    add_job(j, dp + 288, DP, 16, sv + 128, SV, 32, gw->vi_w2, 32, gw->vi_b2);
-    for (int i = 0; i < j.njobs; ++i)
-        if (j.jobs[i].dW == nullptr) return fail("weight-gradient pointer of job %d is NULL", i);
+    set_out(j, O_LD, gw->l_d2h_w, 32, 32, gw->l_d2h_b, gw->l_in_b);
+    set_out(j, O_LIZ, gw->l_in_w + A, LDIN, 32);
+    set_out(j, O_LIA, gw->l_in_w, LDIN, A);
+    set_out(j, O_HD, gw->h_d2h_w, 32, 32, gw->h_d2h_b, gw->h_in_b);
+    set_out(j, O_HI, gw->h_in_w, 16, 16);
+    set_out(j, O_LP1, gw->lp_w1, 32, 32, gw->lp_b1);
+    set_out(j, O_LP2, gw->lp_w2, 32, 32, gw->lp_b2);
+    set_out(j, O_HP1, gw->hp_w1, 32, 32, gw->hp_b1);
+    set_out(j, O_HP2, gw->hp_w2, 32, 32, gw->hp_b2);
+    set_out(j, O_HQ1, gw->hq_w1, 64, 64, gw->hq_b1);
+    set_out(j, O_HQ2, gw->hq_w2, 32, 32, gw->hq_b2);
+    set_out(j, O_A1A, gw->au_w1, 96, 96, gw->au_b1);
+    set_out(j, O_A1B, gw->au_w1 + 16 * 96, 96, 96, gw->au_b1 + 16);
+    set_out(j, O_A2, gw->au_w2, 32, 32, gw->au_b2);
+    set_out(j, O_V1A, gw->vi_w1, 96, 96, gw->vi_b1);
+    set_out(j, O_V1B, gw->vi_w1 + 16 * 96, 96, 96, gw->vi_b1 + 16);
+    set_out(j, O_V2, gw->vi_w2, 32, 32, gw->vi_b2);
+    for (int i = 0; i < N_OUT; ++i)
+        if (j.out[i].dW == nullptr) return fail("weight-gradient pointer of part %d is NULL", i);
     g_launches.fetch_add(1);
-    return check_cuda(rssm::launch_wgrad(j, s), "mtrssm wgrad launch");
+    return check_cuda(rssm::launch_wgrad_mma(j, 0, d->precision, static_cast<cudaStream_t>(stream)), "mtrssm wgrad launch");
 }
 
 }  // extern "C"

@@ -1,83 +1,261 @@
-// Batched weight gradients for the rollout: for every layer ("job")
-//     dW[n][k] += sum over (b,t) of dY[(b,t)][n] * X[(b,t) or (b,t-1)][k],   db[n] += sum dY[(b,t)][n]
-// where dY is a slice of the backward kernel's per-(b,t) "dpre" record and X a slice of the forward
-// kernel's outputs / saved record / inputs.  The recurrence carries only data gradients, so this pass
-// is embarrassingly parallel over (b,t): grid = (row chunks, jobs).
+// Batched weight gradients of the rollout on the tensor cores.
 //
-// v1: fp32 FFMA, 4x4 register micro-tiles, operands streamed through L1 (each CTA re-reads a row only
-// from L1), one atomicAdd per output element per CTA.  Accumulates into dW/db (caller zero-fills).
+// For every layer:  dW[n][k] += sum_{(b,t)} dY[(b,t)][n] * X[(b,t)][k],   db[n] += sum_{(b,t)} dY[(b,t)][n]
+// with dY a slice of the backward kernel's per-(b,t) "dpre" record and X the layer's input (outputs of the
+// forward kernel, its saved record, or kernel inputs; "previous-step" inputs are the row (b,t-1), or the
+// initial state for t == 0).  The recurrence only carries data gradients, so this pass is embarrassingly
+// parallel over (b,t).
+//
+// Design: a CTA stages ROWS = 32 consecutive (b,t) rows ONCE from HBM (coalesced float4) into shared memory
+// as bf16 (NS planes: 1 = bf16 path, 3 = hi/mid/lo split for the fp32-parity path), laid out per layer input so
+// that every layer is one contiguous column range.  Eight warps then each own a fixed set of 16x8 output tiles
+// (<= 20, register accumulators that live across the CTA's whole row loop) and compute
+//     acc[n-tile][k-tile] += dY^T[16 n x 16 rows] * X[16 rows x 8 k]        (mma.m16n8k16, K = rows)
+// with both operands fetched by ldmatrix.trans.  Bias gradients ride along as one extra MMA per n-tile
+// against a constant "ones" B fragment.  At the end every CTA adds its partial sums to global memory
+// (one atomicAdd per output element per CTA).  HBM traffic = each staged column read exactly once.
 #include <stdint.h>
 
+#include "frag.cuh"
 #include "kernels.h"
 
 namespace rssm {
 
-__global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a) {
-    const WgradJob& j = a.jobs[blockIdx.y];
-    const int tiles_k = (j.K + 3) >> 2, tiles_n = (j.N + 3) >> 2, ntiles = tiles_n * tiles_k;
-    const int nslices = 256 / ntiles > 0 ? 256 / ntiles : 1;
-    const int tid = threadIdx.x;
-    const int R = a.B * a.T, T = a.T;
-    const int per = (R + gridDim.x - 1) / gridDim.x;
-    const int c0 = blockIdx.x * per, c1 = min(R, c0 + per);
+namespace wg {
 
-    const int slice = tid / ntiles, tile = tid % ntiles;
-    if (slice >= nslices) return;  // no block-level synchronisation below
-    {
-        const int tn = tile / tiles_k, tk = tile % tiles_k;
-        const int n0 = tn * 4, k0 = tk * 4;
-        const bool vec = (j.N % 4 == 0) && (j.K % 4 == 0) && (j.ldy % 4 == 0) && (j.ldx % 4 == 0) && (j.ldx0 % 4 == 0) &&
-                         ((reinterpret_cast<uintptr_t>(j.dY) | reinterpret_cast<uintptr_t>(j.X) |
-                           reinterpret_cast<uintptr_t>(j.X0)) % 16 == 0);
-        float acc[4][4] = {};
-        float bsum[4] = {};
-        for (int row = c0 + slice; row < c1; row += nslices) {
-            const float* dy = j.dY + (size_t)row * j.ldy + n0;
-            const float* x;
-            if (j.shift) {
-                const int b = row / T, t = row - b * T;
-                x = (t > 0 ? j.X + (size_t)(row - 1) * j.ldx : j.X0 + (size_t)b * j.ldx0) + k0;
-            } else {
-                x = j.X + (size_t)row * j.ldx + k0;
-            }
-            float d[4], v[4];
-            if (vec) {
-                const float4 d4 = *reinterpret_cast<const float4*>(dy), v4 = *reinterpret_cast<const float4*>(x);
-                d[0] = d4.x, d[1] = d4.y, d[2] = d4.z, d[3] = d4.w;
-                v[0] = v4.x, v[1] = v4.y, v[2] = v4.z, v[3] = v4.w;
-            } else {
+constexpr int ROWS = 32;
+constexpr int MAX_TILES = 20;
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_ptr) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* smem_ptr) {
+    const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+
+// One part: MT n-tiles of dY (16 columns each, starting at staged column colY) times NT k-tiles of X (8 columns
+// each, starting at staged column colX), accumulators acc[OFF .. OFF + MT*NT), bias accumulators (if BIAS) at
+// acc[OFF + MT*NT .. + MT).
+template <int NS, int MT, int NT, int OFF, bool BIAS>
+__device__ __forceinline__ void part(float (&acc)[MAX_TILES][4], const __nv_bfloat16* __restrict__ sm, int stride, int plane,
+                                     int colY, int colX, int lane) {
+    static_assert(OFF + MT * NT + (BIAS ? MT : 0) <= MAX_TILES, "too many tiles for one warp");
+    const int lr = lane & 7, m8 = (lane >> 3) & 1, m16 = (lane >> 4) & 1;
+    const uint32_t one2 = (lane >> 2) == 0 ? 0x3f803f80u : 0u;  // bf16 (1,1) in lanes holding output column 0
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    d[i] = n0 + i < j.N ? dy[i] : 0.f;
-                    v[i] = k0 + i < j.K ? x[i] : 0.f;
+    for (int ks = 0; ks < ROWS / 16; ++ks) {
+        const int r0 = ks * 16;
+        uint32_t a[NS][MT][4];
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+                ldmatrix_x4_trans(a[s][mt], sm + (size_t)s * plane + (size_t)(r0 + lr + m16 * 8) * stride + colY + 16 * mt + m8 * 8);
+        if constexpr (BIAS) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                mma_bf16(acc[OFF + MT * NT + mt], a[0][mt], make_uint2(one2, one2));
+                if constexpr (NS == 3) {
+                    mma_bf16(acc[OFF + MT * NT + mt], a[1][mt], make_uint2(one2, one2));
+                    mma_bf16(acc[OFF + MT * NT + mt], a[2][mt], make_uint2(one2, one2));
                 }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                bsum[i] += d[i];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) acc[i][k] = fmaf(d[i], v[k], acc[i][k]);
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (n0 + i >= j.N) continue;
+        for (int np = 0; np < (NT + 1) / 2; ++np) {
+            const bool pair = 2 * np + 1 < NT;
+            uint32_t b[NS][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k0 + k < j.K) atomicAdd(j.dW + (size_t)(n0 + i) * j.ldw + k0 + k, acc[i][k]);
-            if (j.db != nullptr && tk == 0) atomicAdd(j.db + n0 + i, bsum[i]);
+            for (int s = 0; s < NS; ++s) {
+                const __nv_bfloat16* base = sm + (size_t)s * plane + (size_t)(r0 + lr + m8 * 8) * stride + colX + 16 * np;
+                if (pair) {
+                    ldmatrix_x4_trans(b[s], base + m16 * 8);
+                } else {
+                    uint32_t t2[2];
+                    ldmatrix_x2_trans(t2, base);
+                    b[s][0] = t2[0], b[s][1] = t2[1], b[s][2] = 0u, b[s][3] = 0u;
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1 && !pair) break;
+                const int nt = 2 * np + h;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    float (&c)[4] = acc[OFF + mt * NT + nt];
+                    if constexpr (NS == 1) {
+                        mma_bf16(c, a[0][mt], make_uint2(b[0][2 * h], b[0][2 * h + 1]));
+                    } else {
+                        mma_bf16(c, a[0][mt], make_uint2(b[2][2 * h], b[2][2 * h + 1]));
+                        mma_bf16(c, a[2][mt], make_uint2(b[0][2 * h], b[0][2 * h + 1]));
+                        mma_bf16(c, a[1][mt], make_uint2(b[1][2 * h], b[1][2 * h + 1]));
+                        mma_bf16(c, a[0][mt], make_uint2(b[1][2 * h], b[1][2 * h + 1]));
+                        mma_bf16(c, a[1][mt], make_uint2(b[0][2 * h], b[0][2 * h + 1]));
+                        mma_bf16(c, a[0][mt], make_uint2(b[0][2 * h], b[0][2 * h + 1]));
+                    }
+                }
+            }
         }
     }
 }
 
-cudaError_t launch_wgrad(const WgradArgs& a, cudaStream_t s) {
-    if (a.njobs <= 0) return cudaSuccess;
-    const int R = a.B * a.T;
-    int chunks = (R + 255) / 256;
-    if (chunks > 74) chunks = 74;
-    if (chunks < 1) chunks = 1;
-    wgrad_kernel<<<dim3(chunks, a.njobs), 256, 0, s>>>(a);
+// adds a part's accumulators to global memory
+template <int MT, int NT, int OFF, bool BIAS>
+__device__ __forceinline__ void flush(const float (&acc)[MAX_TILES][4], const WgradOut& o, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float (&c)[4] = acc[OFF + mt * NT + nt];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = 16 * mt + g + (j >> 1) * 8, k = 8 * nt + 2 * t + (j & 1);
+                if (k < o.kvalid) atomicAdd(o.dW + (size_t)n * o.ldw + k, c[j]);
+            }
+        }
+        if constexpr (BIAS) {
+            if (t == 0) {
+                const float (&c)[4] = acc[OFF + MT * NT + mt];
+                if (o.db0) atomicAdd(o.db0 + 16 * mt + g, c[0]), atomicAdd(o.db0 + 16 * mt + g + 8, c[2]);
+                if (o.db1) atomicAdd(o.db1 + 16 * mt + g, c[0]), atomicAdd(o.db1 + 16 * mt + g + 8, c[2]);
+            }
+        }
+    }
+}
+
+// ---- per-model programs: which warp owns which parts (see the layout tables in rollout_abi.cu) ---------------------
+// MODE 0: accumulate one staged block; MODE 1: flush to global
+#define PART(MT, NT, OFF, BIAS, COLY, COLX, OUT)                                  \
+    if (MODE == 0) part<NS, MT, NT, OFF, BIAS>(acc, sm, stride, plane, COLY, COLX, lane); \
+    else flush<MT, NT, OFF, BIAS>(acc, outs[OUT], lane);
+
+template <int NS, int MODE>
+__device__ __forceinline__ void program_mtrssm(float (&acc)[MAX_TILES][4], const __nv_bfloat16* sm, int stride, int plane,
+                                               const WgradOut* outs, int warp, int lane) {
+    using namespace wgl_mt;
+    switch (warp) {
+        case 0: PART(2, 4, 0, true, DP + 0, XLD, O_LD) PART(2, 4, 10, false, DP + 0, XLZ, O_LIZ)
+                PART(2, 1, 18, false, DP + 0, XLA, O_LIA) break;
+        case 1: PART(2, 4, 0, true, DP + 32, XHD, O_HD) PART(2, 2, 10, false, DP + 32, XHI, O_HI)
+                PART(1, 4, 14, true, DP + 96, HID + 0, O_LP2) break;
+        case 2: PART(2, 4, 0, true, DP + 64, XQ + 0, O_LP1) PART(2, 4, 10, true, DP + 112, XQ + 32, O_HP1) break;
+        case 3: PART(2, 8, 0, true, DP + 160, XQ, O_HQ1) break;
+        case 4: PART(1, 12, 0, true, DP + 208, XA, O_A1A) PART(1, 4, 13, true, DP + 240, HID + 96, O_A2) break;
+        case 5: PART(1, 12, 0, true, DP + 224, XA, O_A1B) PART(1, 4, 13, true, DP + 144, HID + 32, O_HP2) break;
+        case 6: PART(1, 12, 0, true, DP + 256, XV, O_V1A) PART(1, 4, 13, true, DP + 288, HID + 128, O_V2) break;
+        default: PART(1, 12, 0, true, DP + 272, XV, O_V1B) PART(1, 4, 13, true, DP + 192, HID + 64, O_HQ2) break;
+    }
+}
+
+template <int NS, int MODE>
+__device__ __forceinline__ void program_mrssm(float (&acc)[MAX_TILES][4], const __nv_bfloat16* sm, int stride, int plane,
+                                              const WgradOut* outs, int warp, int lane) {
+    using namespace wgl_mr;
+    switch (warp) {
+        case 0: PART(2, 2, 0, true, DP + 0, XASPZ, O_ASP1Z) PART(2, 1, 6, false, DP + 0, XASPA, O_ASP1A)
+                PART(2, 4, 8, true, DP + 32, XH1, O_ASP2) break;
+        case 1: PART(2, 4, 0, true, DP + 64, XX2, O_IHR) PART(2, 4, 10, true, DP + 96, XX2, O_IHZ) break;
+        case 2: PART(2, 4, 0, true, DP + 128, XX2, O_IHN) PART(2, 4, 10, true, DP + 64, XHP, O_HHR) break;
+        case 3: PART(2, 4, 0, true, DP + 96, XHP, O_HHZ) PART(2, 4, 10, true, DP + 160, XHP, O_HHN) break;
+        case 4: PART(2, 4, 0, true, DP + 192, XA, O_P1) PART(1, 4, 10, true, DP + 224, HID + 0, O_P2)
+                PART(1, 4, 15, true, DP + 272, HID + 32, O_A2) break;
+        case 5: PART(1, 12, 0, true, DP + 240, XA, O_A1A) PART(1, 4, 13, true, DP + 320, HID + 64, O_V2) break;
+        case 6: PART(1, 12, 0, true, DP + 256, XA, O_A1B) PART(1, 6, 13, true, DP + 304, XV, O_V1B_L) break;
+        default: PART(1, 12, 0, true, DP + 288, XV, O_V1A) PART(1, 6, 13, false, DP + 304, XV + 48, O_V1B_R) break;
+    }
+}
+#undef PART
+
+// ---- staging: global fp32 -> shared bf16 planes ---------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void stage_block(__nv_bfloat16* sm, int stride, int plane, const WgradMmaArgs& a, int row_base, int tid) {
+    const int R = a.B * a.T, T = a.T;
+    for (int si = 0; si < a.nseg; ++si) {
+        const WgradSeg& sg = a.seg[si];
+        const int c4n = sg.ncols >> 2;  // float4 chunks per row (ncols is a multiple of 4, zero-padded by `valid`)
+        for (int i = tid; i < ROWS * c4n; i += THREADS) {
+            const int row = i / c4n, c = (i - row * c4n) * 4;
+            const int r = row_base + row;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (r < R) {
+                const float* src;
+                if (sg.shift) {
+                    const int b = r / T, t = r - b * T;
+                    src = t > 0 ? sg.ptr + (size_t)(r - 1) * sg.ld : sg.ptr0 + (size_t)b * sg.ld0;
+                } else {
+                    src = sg.ptr + (size_t)r * sg.ld;
+                }
+                if (sg.vec && c + 3 < sg.valid) {
+                    const float4 q = *reinterpret_cast<const float4*>(src + c);
+                    v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (c + j < sg.valid) v[j] = src[c + j];
+                }
+            }
+            uint32_t lo[NS], hi[NS];
+            split_pack<NS>(v[0], v[1], lo);
+            split_pack<NS>(v[2], v[3], hi);
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                *reinterpret_cast<uint2*>(sm + (size_t)s * plane + (size_t)row * stride + sg.dst + c) = make_uint2(lo[s], hi[s]);
+        }
+    }
+}
+
+template <int NS, int MODEL>
+__global__ void __launch_bounds__(THREADS) wgrad_mma_kernel(const WgradMmaArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+    const int stride = a.stride, plane = ROWS * a.stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float acc[MAX_TILES][4];
+#pragma unroll
+    for (int i = 0; i < MAX_TILES; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+    const int nblocks = (a.B * a.T + ROWS - 1) / ROWS;
+    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        stage_block<NS>(sm, stride, plane, a, blk * ROWS, tid);
+        __syncthreads();
+        if (MODEL == 0) program_mtrssm<NS, 0>(acc, sm, stride, plane, a.out, warp, lane);
+        else program_mrssm<NS, 0>(acc, sm, stride, plane, a.out, warp, lane);
+        __syncthreads();
+    }
+    if (MODEL == 0) program_mtrssm<NS, 1>(acc, sm, stride, plane, a.out, warp, lane);
+    else program_mrssm<NS, 1>(acc, sm, stride, plane, a.out, warp, lane);
+}
+
+}  // namespace wg
+
+template <int NS, int MODEL>
+static cudaError_t launch_wgrad_k(const WgradMmaArgs& a, cudaStream_t s) {
+    const size_t smem = (size_t)NS * wg::ROWS * a.stride * sizeof(__nv_bfloat16);
+    auto kernel = wg::wgrad_mma_kernel<NS, MODEL>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int per_sm = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wg::THREADS, smem);
+    if (err != cudaSuccess) return err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int nblocks = (a.B * a.T + wg::ROWS - 1) / wg::ROWS;
+    int grid = sms * (per_sm > 0 ? per_sm : 1);
+    if (grid > nblocks) grid = nblocks;
+    kernel<<<grid, wg::THREADS, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad_mma(const WgradMmaArgs& a, int model, int precision, cudaStream_t s) {
+    if (precision == RSSM_PRECISION_FP32) return model == 0 ? launch_wgrad_k<3, 0>(a, s) : launch_wgrad_k<3, 1>(a, s);
+    return model == 0 ? launch_wgrad_k<1, 0>(a, s) : launch_wgrad_k<1, 1>(a, s);
 }
 
 }  // namespace rssm
