@@ -121,12 +121,13 @@ class DirectMtrssm:
         self.out = {
             "feature": e(B, T, 96), "hidden_h": e(B, T, 32), "hidden_l": e(B, T, 32),
             "prior_probs_h": e(B, T, 8, 2), "prior_probs_l": e(B, T, 4, 4), "post_probs_h": e(B, T, 8, 2), "post_probs_l": e(B, T, 4, 4),
-            "kl_l": e(B, T), "kl_h": e(B, T), "saved": e(B, T, _lib.MTRSSM_SAVED_FLOATS),
+            "kl_l": e(B, T), "kl_h": e(B, T),
+            "saved": torch.empty(B, T, _lib.MTRSSM_SAVED_FLOATS, device=device, dtype=_lib.record_dtype(precision)),
         }
         self.gin = {
             "d_actions": e(B, T, 6), "d_embed_a": e(B, T, 64), "d_embed_v": e(B, T, 64), "d_deter_h0": e(B, 32), "d_deter_l0": e(B, 32),
             "d_hidden_h0": e(B, 32), "d_hidden_l0": e(B, 32), "d_stoch_h0": e(B, 16), "d_stoch_l0": e(B, 16),
-            "dpre": e(B, T, _lib.MTRSSM_DPRE_FLOATS),
+            "dpre": torch.empty(B, T, _lib.MTRSSM_DPRE_FLOATS, device=device, dtype=_lib.record_dtype(precision)),
         }
         sizes = [w.numel() for w in self.weights]
         self.flat_grad = torch.zeros(sum(sizes), device=device)

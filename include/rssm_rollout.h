@@ -44,7 +44,8 @@ extern "C" {
 #define RSSM_PRECISION_FP32 0
 #define RSSM_PRECISION_BF16 1
 
-/* floats per (b,t) of the opaque records exchanged between fwd and bwd */
+/* ELEMENTS per (b,t) of the opaque records exchanged between fwd, bwd and wgrad.  Element type: fp32 with
+   RSSM_PRECISION_FP32, bf16 with RSSM_PRECISION_BF16 (so bytes = elements * 4 or * 2). */
 #define MRSSM_SAVED_FLOATS 320
 #define MRSSM_DPRE_FLOATS 336
 #define MTRSSM_SAVED_FLOATS 192
@@ -91,7 +92,7 @@ typedef struct {
     float *post_probs;   /* [B,T,C,K] posterior.distribution                                      */
     float *prior_stoch;  /* [B,T,S]   prior.stoch (one-hot); may be NULL                          */
     float *kl;           /* [B,T]     sum_c KL(post_c || prior_c), before mean / balancing / coeff */
-    float *saved;        /* [B,T,MRSSM_SAVED_FLOATS] for the backward; NULL = inference             */
+    void *saved;         /* [B,T,MRSSM_SAVED_FLOATS] record elements for the backward; NULL = inference */
 } RssmMrssmOutputs;
 
 typedef struct {           /* upstream gradients; any pointer may be NULL (= zero) except d_feature */
@@ -110,7 +111,7 @@ typedef struct {
     float *d_embed_v; /* [B,T,E] */
     float *d_h0;      /* [B,D]   */
     float *d_z0;      /* [B,S]   */
-    float *dpre;      /* [B,T,MRSSM_DPRE_FLOATS] workspace */
+    void *dpre;       /* [B,T,MRSSM_DPRE_FLOATS] record elements, workspace */
 } RssmMrssmInputGrads;
 
 int rssm_mrssm_rollout_fwd(const RssmMrssmDims *dims, const RssmMrssmWeights *w, const RssmMrssmInputs *in,
@@ -120,7 +121,7 @@ int rssm_mrssm_rollout_bwd(const RssmMrssmDims *dims, const RssmMrssmWeights *w,
                            const RssmMrssmWeightGrads *gw, void *stream);
 /* weight gradients only (the second half of rssm_mrssm_rollout_bwd, which calls it when gw != NULL):
    dW += dpre^T . layer inputs over all (b,t).  `dpre` is the workspace the backward filled. */
-int rssm_mrssm_wgrad(const RssmMrssmDims *dims, const RssmMrssmInputs *in, const RssmMrssmOutputs *fwd_out, const float *dpre,
+int rssm_mrssm_wgrad(const RssmMrssmDims *dims, const RssmMrssmInputs *in, const RssmMrssmOutputs *fwd_out, const void *dpre,
                      const RssmMrssmWeightGrads *gw, void *stream);
 /* imagination: out->feature [B,T,D+S] = [deter | prior sample], out->prior_probs; in->u_prior required;
    in->embed_*, in->u_post, out->post_probs/prior_stoch/kl/saved ignored */
@@ -172,7 +173,7 @@ typedef struct {
     float *post_probs_h, *post_probs_l;
     float *prior_stoch_h, *prior_stoch_l;   /* [B,T,HS] [B,T,LS]; may be NULL */
     float *kl_l, *kl_h;                     /* [B,T] each */
-    float *saved;                           /* [B,T,MTRSSM_SAVED_FLOATS]; NULL = inference */
+    void *saved;                            /* [B,T,MTRSSM_SAVED_FLOATS] record elements; NULL = inference */
 } RssmMtrssmOutputs;
 
 typedef struct {
@@ -188,7 +189,7 @@ typedef struct {
     float *d_actions;                       /* may be NULL */
     float *d_embed_a, *d_embed_v;
     float *d_deter_h0, *d_deter_l0, *d_hidden_h0, *d_hidden_l0, *d_stoch_h0, *d_stoch_l0;
-    float *dpre;                            /* [B,T,MTRSSM_DPRE_FLOATS] workspace */
+    void *dpre;                             /* [B,T,MTRSSM_DPRE_FLOATS] record elements, workspace */
 } RssmMtrssmInputGrads;
 
 int rssm_mtrssm_rollout_fwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights *w, const RssmMtrssmInputs *in,
@@ -196,7 +197,7 @@ int rssm_mtrssm_rollout_fwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights 
 int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights *w, const RssmMtrssmInputs *in,
                             const RssmMtrssmOutputs *fwd_out, const RssmMtrssmUpstream *up, const RssmMtrssmInputGrads *gin,
                             const RssmMtrssmWeightGrads *gw, void *stream);
-int rssm_mtrssm_wgrad(const RssmMtrssmDims *dims, const RssmMtrssmInputs *in, const RssmMtrssmOutputs *fwd_out, const float *dpre,
+int rssm_mtrssm_wgrad(const RssmMtrssmDims *dims, const RssmMtrssmInputs *in, const RssmMtrssmOutputs *fwd_out, const void *dpre,
                       const RssmMtrssmWeightGrads *gw, void *stream);
 /* imagination: feature = [deter_h | prior sample h | deter_l | prior sample l], hidden_*, prior_probs_*;
    u_prior_* required */

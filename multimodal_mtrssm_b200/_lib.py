@@ -131,12 +131,17 @@ def ptr(t: torch.Tensor | None) -> int | None:
     """Device pointer of a contiguous fp32 CUDA tensor (None -> NULL)."""
     if t is None:
         return None
-    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+    if not (t.is_cuda and t.dtype in (torch.float32, torch.bfloat16) and t.is_contiguous()):
         raise RuntimeError(
-            f"rollout kernels need contiguous fp32 CUDA tensors, got device={t.device} dtype={t.dtype} "
-            f"contiguous={t.is_contiguous()}"
+            f"rollout kernels need contiguous fp32 CUDA tensors (bf16 only for the opaque records), got device={t.device} "
+            f"dtype={t.dtype} contiguous={t.is_contiguous()}"
         )
     return t.data_ptr()
+
+
+def record_dtype(precision: int) -> torch.dtype:
+    """Element type of the opaque saved / dpre records (include/rssm_rollout.h)."""
+    return torch.bfloat16 if precision == PRECISION_BF16 else torch.float32
 
 
 def launch_count() -> int:

@@ -205,6 +205,52 @@ __device__ __forceinline__ void store_c(const float (&c)[NT][4], float* __restri
     }
 }
 
+// ---- per-(b,t) records exchanged between forward, backward and wgrad: fp32 on the fp32-parity path (NS = 3),
+// bf16 on the bf16 path (NS = 1; the values are MMA operands there anyway, so nothing is lost for the contractions)
+template <int NS>
+struct Rec {
+    using T = float;
+};
+template <>
+struct Rec<1> {
+    using T = __nv_bfloat16;
+};
+
+template <int NT>
+__device__ __forceinline__ void store_rec(const float (&c)[NT][4], float* __restrict__ pA, float* __restrict__ pB, const Rows& r) {
+    store_c<NT>(c, pA, pB, r);
+}
+template <int NT>
+__device__ __forceinline__ void store_rec(const float (&c)[NT][4], __nv_bfloat16* __restrict__ pA, __nv_bfloat16* __restrict__ pB,
+                                          const Rows& r) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        if (r.vA) *reinterpret_cast<uint32_t*>(pA + nt * 8 + 2 * r.t) = pack_bf16(c[nt][0], c[nt][1]);
+        if (r.vB) *reinterpret_cast<uint32_t*>(pB + nt * 8 + 2 * r.t) = pack_bf16(c[nt][2], c[nt][3]);
+    }
+}
+template <int NT>
+__device__ __forceinline__ void load_rec(float (&c)[NT][4], const float* __restrict__ pA, const float* __restrict__ pB, int t) {
+    load_c<NT>(c, pA, pB, t);
+}
+template <int NT>
+__device__ __forceinline__ void load_rec(float (&c)[NT][4], const __nv_bfloat16* __restrict__ pA, const __nv_bfloat16* __restrict__ pB,
+                                         int t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(pA + nt * 8 + 2 * t);
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(pB + nt * 8 + 2 * t);
+        c[nt][0] = __low2float(a), c[nt][1] = __high2float(a), c[nt][2] = __low2float(b), c[nt][3] = __high2float(b);
+    }
+}
+
+// L2 prefetch (next step's rows): converts the DRAM round trip of a step's dependent loads into L2 hits.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// whole range [p, p + bytes): p 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void prefetch_bulk_l2(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // store only columns < nvalid (e.g. the 6 action columns of an 8-wide tile)
 __device__ __forceinline__ void store_c_partial(const float (&c)[4], float* __restrict__ pA, float* __restrict__ pB, const Rows& r,
                                                 int nvalid) {

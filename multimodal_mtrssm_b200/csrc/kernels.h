@@ -11,16 +11,19 @@ struct MrssmFwdArgs {
     int B, T, A, K;
     RssmMrssmWeights w;
     const float *actions, *embed_a, *embed_v, *h0, *z0, *u_post, *u_prior;
-    float *feature, *prior_probs, *post_probs, *prior_stoch, *kl, *saved;
+    float *feature, *prior_probs, *post_probs, *prior_stoch, *kl;
+    void* saved;  // Rec<NS>::T [B,T,MRSSM_SAVED_FLOATS]
 };
 
 struct MrssmBwdArgs {
     int B, T, A, K;
     float kl_wq, kl_wp;
     RssmMrssmWeights w;
-    const float *h0, *feature, *prior_probs, *post_probs, *saved;
+    const float *h0, *feature, *prior_probs, *post_probs;
+    const void* saved;
     const float *d_feature, *d_prior_probs, *d_post_probs, *d_prior_stoch, *d_kl;
-    float *dpre, *d_actions, *d_embed_a, *d_embed_v, *d_h0, *d_z0;
+    void* dpre;
+    float *d_actions, *d_embed_a, *d_embed_v, *d_h0, *d_z0;
 };
 
 cudaError_t launch_mrssm_fwd(const MrssmFwdArgs& a, int precision, bool imagine, cudaStream_t s);
@@ -36,17 +39,20 @@ struct MtrssmFwdArgs {
     const float *u_post_l, *u_post_h, *u_prior_l, *u_prior_h;
     float *feature, *hidden_h, *hidden_l;
     float *prior_probs_h, *prior_probs_l, *post_probs_h, *post_probs_l, *prior_stoch_h, *prior_stoch_l;
-    float *kl_l, *kl_h, *saved;
+    float *kl_l, *kl_h;
+    void* saved;
 };
 
 struct MtrssmBwdArgs {
     int B, T, A, KL, KH;
     float inv_tau_l, inv_tau_h, kl_wq, kl_wp;
     RssmMtrssmWeights w;
-    const float *feature, *prior_probs_h, *prior_probs_l, *post_probs_h, *post_probs_l, *saved;
+    const float *feature, *prior_probs_h, *prior_probs_l, *post_probs_h, *post_probs_l;
+    const void* saved;
     const float *d_feature, *d_prior_probs_h, *d_prior_probs_l, *d_post_probs_h, *d_post_probs_l;
     const float *d_prior_stoch_h, *d_prior_stoch_l, *d_kl_l, *d_kl_h;
-    float *dpre, *d_actions, *d_embed_a, *d_embed_v;
+    void* dpre;
+    float *d_actions, *d_embed_a, *d_embed_v;
     float *d_deter_h0, *d_deter_l0, *d_hidden_h0, *d_hidden_l0, *d_stoch_h0, *d_stoch_l0;
 };
 
@@ -55,10 +61,14 @@ cudaError_t launch_mtrssm_bwd(const MtrssmBwdArgs& a, int precision, cudaStream_
 
 // ---- batched weight gradients on the tensor cores (wgrad_kernel.cu) -----------------------------------------------
 // A staged shared-memory row holds, per (b,t), the dpre record followed by every layer's input, as bf16 columns.
-struct WgradSeg {       // one source column range copied into the staged row
-    const float* ptr;   // row (b,t) at ptr + (b*T + t) * ld          (shift == 0)
-    const float* ptr0;  // shift == 1: row (b,t-1) for t > 0, ptr0 + b * ld0 for t == 0
-    int ld, ld0, ncols /* multiple of 4 */, valid /* real columns, rest zero */, dst /* staged column */, shift, vec;
+struct WgradSeg {       // one source column range copied into the staged row, in chunks of 4 elements
+    const char* ptr;    // row (b,t) at ptr + (b*T + t) * ld_bytes          (shift == 0)
+    const char* ptr0;   // shift == 1: row (b,t-1) for t > 0, ptr0 + b * ld0_bytes for t == 0
+    int ld_bytes, ld0_bytes;
+    int c4_begin, c4_end;  // staged 4-element chunk range [begin, end) of this segment (staged column = 4 * chunk)
+    int valid;             // real source elements; the rest of the range is zero padding
+    int shift;
+    int kind;              // 0: fp32, 16-byte loads; 1: fp32, guarded scalar loads; 2: bf16, 8-byte copies
 };
 struct WgradOut {  // destination of one part: dW[n][k] at dW + n*ldw + k for k < kvalid; up to two bias vectors
     float* dW;
@@ -68,7 +78,7 @@ struct WgradOut {  // destination of one part: dW[n][k] at dW + n*ldw + k for k 
 };
 constexpr int MAX_WGRAD_SEGS = 16, MAX_WGRAD_OUTS = 24;
 struct WgradMmaArgs {
-    int B, T, nseg, stride;
+    int B, T, nseg, stride;  // stride: staged row length in bf16 elements = 4 * (last c4_end)
     WgradSeg seg[MAX_WGRAD_SEGS];
     WgradOut out[MAX_WGRAD_OUTS];
 };

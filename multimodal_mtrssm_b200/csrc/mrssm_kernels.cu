@@ -133,6 +133,8 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
     const int T = p.T;
     constexpr int C = 16 / K;
     constexpr int F = 48;
+    using RT = typename Rec<NS>::T;
+    RT* saved = reinterpret_cast<RT*>(p.saved);
 
     // carried state: h (fp32 C tiles + A operand), z_prev (A operand)
     float h[4][4];
@@ -148,8 +150,19 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
 
     for (int t = 0; t < T; ++t) {
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
-        float* svA = p.saved ? p.saved + iA * MRSSM_SAVED_FLOATS : nullptr;
-        float* svB = p.saved ? p.saved + iB * MRSSM_SAVED_FLOATS : nullptr;
+        RT* svA = saved ? saved + iA * MRSSM_SAVED_FLOATS : nullptr;
+        RT* svB = saved ? saved + iB * MRSSM_SAVED_FLOATS : nullptr;
+        if (t + 1 < T) {  // pull the next step's inputs into L2 while this step computes (lanes 0,1 -> row A; 2,3 -> row B)
+            const size_t in = (r.t < 2 ? iA : iB) + 1;
+            if (r.t & 1) {
+                if (!IMAGINE) prefetch_bulk_l2(p.embed_v + in * 64, 256);
+                prefetch_l2(p.actions + in * A);
+            } else {
+                if (!IMAGINE) prefetch_bulk_l2(p.embed_a + in * 64, 256);
+                if (!IMAGINE) prefetch_l2(p.u_post + in * C);
+                if (p.u_prior) prefetch_l2(p.u_prior + in * C);
+            }
+        }
 
         // ---- action_state_projector (networks.py:168-169) ----------------------------------------
         AFrag<NS, 2> fx;
@@ -161,13 +174,13 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             gemm<NS, 1, 4>(acc, zf, wblock<NS>(W, mr::ASP1Z), lane);
             gemm<NS, 1, 4>(acc, fa, wblock<NS>(W, mr::ASP1A), lane);
             map_c<4>(acc, EluOp<NS == 1>{});
-            if (svA) store_c<4>(acc, svA + mrs::ASP_HID, svB + mrs::ASP_HID, r);
+            if (svA) store_rec<4>(acc, svA + mrs::ASP_HID, svB + mrs::ASP_HID, r);
             AFrag<NS, 2> f1;
             to_afrag<NS, 2>(f1, acc);
             float x2[4][4];
             init_bias<4>(x2, bias + mr::B_ASP2, r.t);
             gemm<NS, 2, 4>(x2, f1, wblock<NS>(W, mr::ASP2), lane);
-            if (svA) store_c<4>(x2, svA + mrs::X2, svB + mrs::X2, r);
+            if (svA) store_rec<4>(x2, svA + mrs::X2, svB + mrs::X2, r);
             to_afrag<NS, 2>(fx, x2);
         }
         // ---- GRUCell (networks.py:170) -----------------------------------------------------------
@@ -191,10 +204,10 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
                     h[nt][j] = (h[nt][j] - ng[nt][j]) * zg[nt][j] + ng[nt][j];
                 }
             if (svA) {
-                store_c<4>(rg, svA + mrs::R, svB + mrs::R, r);
-                store_c<4>(zg, svA + mrs::Z, svB + mrs::Z, r);
-                store_c<4>(ng, svA + mrs::N, svB + mrs::N, r);
-                store_c<4>(ghn, svA + mrs::HN, svB + mrs::HN, r);
+                store_rec<4>(rg, svA + mrs::R, svB + mrs::R, r);
+                store_rec<4>(zg, svA + mrs::Z, svB + mrs::Z, r);
+                store_rec<4>(ng, svA + mrs::N, svB + mrs::N, r);
+                store_rec<4>(ghn, svA + mrs::HN, svB + mrs::HN, r);
             }
             store_c<4>(h, p.feature + iA * F, p.feature + iB * F, r);
             to_afrag<NS, 2>(hf, h);
@@ -206,7 +219,7 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             init_bias<4>(acc, bias + mr::B_P1, r.t);
             gemm<NS, 2, 4>(acc, hf, wblock<NS>(W, mr::P1), lane);
             map_c<4>(acc, EluOp<NS == 1>{});
-            if (svA) store_c<4>(acc, svA + mrs::P_HID, svB + mrs::P_HID, r);
+            if (svA) store_rec<4>(acc, svA + mrs::P_HID, svB + mrs::P_HID, r);
             AFrag<NS, 2> f1;
             to_afrag<NS, 2>(f1, acc);
             float lp[2][4];
@@ -238,13 +251,13 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             gemm<NS, 2, 4>(acc, hf, wblock<NS>(W, m == 0 ? mr::A1H : mr::V1H), lane);
             gemm<NS, 4, 4>(acc, fe, wblock<NS>(W, m == 0 ? mr::A1E : mr::V1E), lane);
             map_c<4>(acc, EluOp<NS == 1>{});
-            if (svA) store_c<4>(acc, svA + (m == 0 ? mrs::A_HID : mrs::V_HID), svB + (m == 0 ? mrs::A_HID : mrs::V_HID), r);
+            if (svA) store_rec<4>(acc, svA + (m == 0 ? mrs::A_HID : mrs::V_HID), svB + (m == 0 ? mrs::A_HID : mrs::V_HID), r);
             AFrag<NS, 2> f1;
             to_afrag<NS, 2>(f1, acc);
             float (&lg)[2][4] = m == 0 ? la : lv;
             init_bias<2>(lg, bias + (m == 0 ? mr::B_A2 : mr::B_V2), r.t);
             gemm<NS, 2, 2>(lg, f1, wblock<NS>(W, m == 0 ? mr::A2 : mr::V2), lane);
-            if (svA) store_c<2>(lg, svA + (m == 0 ? mrs::LA : mrs::LV), svB + (m == 0 ? mrs::LA : mrs::LV), r);
+            if (svA) store_rec<2>(lg, svA + (m == 0 ? mrs::LA : mrs::LV), svB + (m == 0 ? mrs::LA : mrs::LV), r);
         }
         // ---- MoPoE fusion, factory, sample, KL (mopoe_mrssm/core.py:241-251,135-163) --------------
         {
@@ -306,6 +319,9 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
     const Rows r = make_rows(row0, p.B, lane);
     const int T = p.T;
     constexpr int F = 48;
+    using RT = typename Rec<NS>::T;
+    const RT* saved = reinterpret_cast<const RT*>(p.saved);
+    RT* dpre = reinterpret_cast<RT*>(p.dpre);
 
     float dh[4][4], dz[2][4];  // carried: d loss / d deter[t], d loss / d post_stoch[t] from step t+1
     zero_c<4>(dh);
@@ -313,10 +329,22 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
 
     for (int t = T - 1; t >= 0; --t) {
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
-        const float* svA = p.saved + iA * MRSSM_SAVED_FLOATS;
-        const float* svB = p.saved + iB * MRSSM_SAVED_FLOATS;
-        float* dpA = p.dpre + iA * MRSSM_DPRE_FLOATS;
-        float* dpB = p.dpre + iB * MRSSM_DPRE_FLOATS;
+        const RT* svA = saved + iA * MRSSM_SAVED_FLOATS;
+        const RT* svB = saved + iB * MRSSM_SAVED_FLOATS;
+        RT* dpA = dpre + iA * MRSSM_DPRE_FLOATS;
+        RT* dpB = dpre + iB * MRSSM_DPRE_FLOATS;
+        if (t > 0) {  // pull step t-1's rows into L2 (lanes 0,1 -> row A; 2,3 -> row B)
+            const size_t ip = (r.t < 2 ? iA : iB) - 1;
+            if (r.t & 1) {
+                prefetch_bulk_l2(saved + ip * MRSSM_SAVED_FLOATS, MRSSM_SAVED_FLOATS * sizeof(RT));
+                if (p.d_kl) prefetch_l2(p.d_kl + ip);
+            } else {
+                prefetch_bulk_l2(p.d_feature + ip * F, F * 4);
+                prefetch_bulk_l2(p.post_probs + ip * 16, 64);
+                prefetch_bulk_l2(p.prior_probs + ip * 16, 64);
+                if (t > 1) prefetch_bulk_l2(p.feature + (ip - 1) * F, 128);
+            }
+        }
 
         // upstream gradient on feature = [deter | post_stoch]
         {
@@ -367,8 +395,8 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
             float dm[2][4];
             softmax_groups_bwd<K>(q, dq, dm);
             float la[2][4], lv[2][4], lsa[2][4], lsv[2][4], mixed[2][4], ra[2][4], rv[2][4];
-            load_c<2>(la, svA + mrs::LA, svB + mrs::LA, r.t);
-            load_c<2>(lv, svA + mrs::LV, svB + mrs::LV, r.t);
+            load_rec<2>(la, svA + mrs::LA, svB + mrs::LA, r.t);
+            load_rec<2>(lv, svA + mrs::LV, svB + mrs::LV, r.t);
             log_softmax_flat<NS == 1>(la, lsa);
             log_softmax_flat<NS == 1>(lv, lsv);
             mopoe_mix<NS == 1>(lsa, lsv, mixed, ra, rv);
@@ -382,8 +410,8 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
             log_softmax_flat_bwd<NS == 1>(lsa, ra, dla);
             log_softmax_flat_bwd<NS == 1>(lsv, rv, dlv);
         }
-        store_c<2>(dla, dpA + mrd::LA, dpB + mrd::LA, r);
-        store_c<2>(dlv, dpA + mrd::LV, dpB + mrd::LV, r);
+        store_rec<2>(dla, dpA + mrd::LA, dpB + mrd::LA, r);
+        store_rec<2>(dlv, dpA + mrd::LV, dpB + mrd::LV, r);
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
             float (&dl)[2][4] = m == 0 ? dla : dlv;
@@ -392,12 +420,12 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
             float dhid[4][4], hid[4][4];
             zero_c<4>(dhid);
             gemm<NS, 1, 4>(dhid, fl, wblock<NS>(W, m == 0 ? mr::T_A2 : mr::T_V2), lane);
-            load_c<4>(hid, svA + (m == 0 ? mrs::A_HID : mrs::V_HID), svB + (m == 0 ? mrs::A_HID : mrs::V_HID), r.t);
+            load_rec<4>(hid, svA + (m == 0 ? mrs::A_HID : mrs::V_HID), svB + (m == 0 ? mrs::A_HID : mrs::V_HID), r.t);
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dhid[nt][j] *= elu_grad_from_out(hid[nt][j]);
-            store_c<4>(dhid, dpA + (m == 0 ? mrd::A1 : mrd::V1), dpB + (m == 0 ? mrd::A1 : mrd::V1), r);
+            store_rec<4>(dhid, dpA + (m == 0 ? mrd::A1 : mrd::V1), dpB + (m == 0 ? mrd::A1 : mrd::V1), r);
             AFrag<NS, 2> f1;
             to_afrag<NS, 2>(f1, dhid);
             gemm<NS, 2, 4>(dh, f1, wblock<NS>(W, m == 0 ? mr::T_A1H : mr::T_V1H), lane);
@@ -411,18 +439,18 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
         {
             float dlp[2][4];
             softmax_groups_bwd<K>(pp, dpp, dlp);
-            store_c<2>(dlp, dpA + mrd::PL, dpB + mrd::PL, r);
+            store_rec<2>(dlp, dpA + mrd::PL, dpB + mrd::PL, r);
             AFrag<NS, 1> fl;
             to_afrag<NS, 1>(fl, dlp);
             float dhid[4][4], hid[4][4];
             zero_c<4>(dhid);
             gemm<NS, 1, 4>(dhid, fl, wblock<NS>(W, mr::T_P2), lane);
-            load_c<4>(hid, svA + mrs::P_HID, svB + mrs::P_HID, r.t);
+            load_rec<4>(hid, svA + mrs::P_HID, svB + mrs::P_HID, r.t);
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dhid[nt][j] *= elu_grad_from_out(hid[nt][j]);
-            store_c<4>(dhid, dpA + mrd::P1, dpB + mrd::P1, r);
+            store_rec<4>(dhid, dpA + mrd::P1, dpB + mrd::P1, r);
             AFrag<NS, 2> f1;
             to_afrag<NS, 2>(f1, dhid);
             gemm<NS, 2, 4>(dh, f1, wblock<NS>(W, mr::T_P1), lane);
@@ -431,10 +459,10 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
         float dx2[4][4];
         {
             float rg[4][4], zg[4][4], ng[4][4], hn[4][4], hp[4][4];
-            load_c<4>(rg, svA + mrs::R, svB + mrs::R, r.t);
-            load_c<4>(zg, svA + mrs::Z, svB + mrs::Z, r.t);
-            load_c<4>(ng, svA + mrs::N, svB + mrs::N, r.t);
-            load_c<4>(hn, svA + mrs::HN, svB + mrs::HN, r.t);
+            load_rec<4>(rg, svA + mrs::R, svB + mrs::R, r.t);
+            load_rec<4>(zg, svA + mrs::Z, svB + mrs::Z, r.t);
+            load_rec<4>(ng, svA + mrs::N, svB + mrs::N, r.t);
+            load_rec<4>(hn, svA + mrs::HN, svB + mrs::HN, r.t);
             if (t > 0) load_c<4>(hp, p.feature + (iA - 1) * F, p.feature + (iB - 1) * F, r.t);
             else load_c<4>(hp, p.h0 + (size_t)r.rA * 32, p.h0 + (size_t)r.rB * 32, r.t);
             float dpr[4][4], dpz[4][4], dpn[4][4], dhn[4][4];
@@ -452,10 +480,10 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
                     dpz[nt][j] = dzg * z * (1.f - z);
                     dh[nt][j] = g * z;  // direct path h' <- h_prev
                 }
-            store_c<4>(dpr, dpA + mrd::GI, dpB + mrd::GI, r);
-            store_c<4>(dpz, dpA + mrd::GI + 32, dpB + mrd::GI + 32, r);
-            store_c<4>(dpn, dpA + mrd::GI + 64, dpB + mrd::GI + 64, r);
-            store_c<4>(dhn, dpA + mrd::HN, dpB + mrd::HN, r);
+            store_rec<4>(dpr, dpA + mrd::GI, dpB + mrd::GI, r);
+            store_rec<4>(dpz, dpA + mrd::GI + 32, dpB + mrd::GI + 32, r);
+            store_rec<4>(dpn, dpA + mrd::GI + 64, dpB + mrd::GI + 64, r);
+            store_rec<4>(dhn, dpA + mrd::HN, dpB + mrd::HN, r);
             AFrag<NS, 2> fr, fz, fn;
             to_afrag<NS, 2>(fr, dpr);
             to_afrag<NS, 2>(fz, dpz);
@@ -471,18 +499,18 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
         }
         // ---- action_state_projector ------------------------------------------------------------------
         {
-            store_c<4>(dx2, dpA + mrd::X2, dpB + mrd::X2, r);
+            store_rec<4>(dx2, dpA + mrd::X2, dpB + mrd::X2, r);
             AFrag<NS, 2> f2;
             to_afrag<NS, 2>(f2, dx2);
             float dhid[4][4], hid[4][4];
             zero_c<4>(dhid);
             gemm<NS, 2, 4>(dhid, f2, wblock<NS>(W, mr::T_ASP2), lane);
-            load_c<4>(hid, svA + mrs::ASP_HID, svB + mrs::ASP_HID, r.t);
+            load_rec<4>(hid, svA + mrs::ASP_HID, svB + mrs::ASP_HID, r.t);
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dhid[nt][j] *= elu_grad_from_out(hid[nt][j]);
-            store_c<4>(dhid, dpA + mrd::ASP1, dpB + mrd::ASP1, r);
+            store_rec<4>(dhid, dpA + mrd::ASP1, dpB + mrd::ASP1, r);
             AFrag<NS, 2> f1;
             to_afrag<NS, 2>(f1, dhid);
             zero_c<2>(dz);

@@ -63,10 +63,10 @@ __device__ __forceinline__ uint2* wblk(uint2* W, int tile_off) {
 
 // hidden -> ELU -> logits for a 32-wide hidden layer whose pre-activation is already accumulated
 template <int NS>
-__device__ __forceinline__ void head_l2(float (&acc)[4][4], float (&logits)[2][4], const float* bias2, const uint2* w2, float* svA,
-                                        float* svB, int sv_off, const Rows& r, int lane) {
+__device__ __forceinline__ void head_l2(float (&acc)[4][4], float (&logits)[2][4], const float* bias2, const uint2* w2,
+                                        typename Rec<NS>::T* svA, typename Rec<NS>::T* svB, int sv_off, const Rows& r, int lane) {
     map_c<4>(acc, EluOp<NS == 1>{});
-    if (svA) store_c<4>(acc, svA + sv_off, svB + sv_off, r);
+    if (svA) store_rec<4>(acc, svA + sv_off, svB + sv_off, r);
     AFrag<NS, 2> f1;
     to_afrag<NS, 2>(f1, acc);
     init_bias<2>(logits, bias2, r.t);
@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) 
     const int T = p.T;
     constexpr int CL = 16 / KL, CH = 16 / KH, F = 96;
     const float keep_l = 1.f - p.inv_tau_l, keep_h = 1.f - p.inv_tau_h;
+    using RT = typename Rec<NS>::T;
+    RT* saved = reinterpret_cast<RT*>(p.saved);
 
     // carried state
     float ul[4][4], uh[4][4];
@@ -156,8 +158,20 @@ __global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) 
 
     for (int t = 0; t < T; ++t) {
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
-        float* svA = p.saved ? p.saved + iA * MTRSSM_SAVED_FLOATS : nullptr;
-        float* svB = p.saved ? p.saved + iB * MTRSSM_SAVED_FLOATS : nullptr;
+        RT* svA = saved ? saved + iA * MTRSSM_SAVED_FLOATS : nullptr;
+        RT* svB = saved ? saved + iB * MTRSSM_SAVED_FLOATS : nullptr;
+        if (t + 1 < T) {  // pull the next step's inputs into L2 while this step computes (lanes 0,1 -> row A; 2,3 -> row B)
+            const size_t in = (r.t < 2 ? iA : iB) + 1;
+            if (r.t & 1) {
+                if (!IMAGINE) prefetch_bulk_l2(p.embed_v + in * 64, 256);
+                prefetch_l2(p.actions + in * A);
+                if (!IMAGINE) prefetch_l2(p.u_post_h + in * CH);
+            } else {
+                if (!IMAGINE) prefetch_bulk_l2(p.embed_a + in * 64, 256);
+                if (!IMAGINE) prefetch_l2(p.u_post_l + in * CL);
+                if (p.u_prior_l) prefetch_l2(p.u_prior_l + in * CL), prefetch_l2(p.u_prior_h + in * CH);
+            }
+        }
 
         // ---- two leaky-integrator cells (mopoe_mmtrssm/core.py:59-60), both from the PREVIOUS state ----
         {
@@ -233,7 +247,7 @@ __global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) 
             float (&lg)[2][4] = m == 0 ? la : lv;
             head_l2<NS>(acc, lg, bias + (m == 0 ? mt::B_A2 : mt::B_V2), wblk<NS>(W, m == 0 ? mt::A2 : mt::V2), svA, svB,
                         m == 0 ? mts::A_HID : mts::V_HID, r, lane);
-            if (svA) store_c<2>(lg, svA + (m == 0 ? mts::LA : mts::LV), svB + (m == 0 ? mts::LA : mts::LV), r);
+            if (svA) store_rec<2>(lg, svA + (m == 0 ? mts::LA : mts::LV), svB + (m == 0 ? mts::LA : mts::LV), r);
         }
         {
             float lsa[2][4], lsv[2][4], mixed[2][4], q[2][4], zs[2][4];
@@ -280,21 +294,22 @@ __global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) 
 // ================================================================================================
 // d logits (16) -> through W2^T -> * ELU'(hidden) -> dpre1 (stored) ; returns dpre1 as A operand
 template <int NS>
-__device__ __forceinline__ void head_bwd(const float (&dlogit)[2][4], const uint2* w2t, const float* svA, const float* svB,
-                                         int sv_off, float* dpA, float* dpB, int dp_logit_off, int dp1_off, AFrag<NS, 2>& f1,
-                                         const Rows& r, int lane) {
-    store_c<2>(dlogit, dpA + dp_logit_off, dpB + dp_logit_off, r);
+__device__ __forceinline__ void head_bwd(const float (&dlogit)[2][4], const uint2* w2t, const typename Rec<NS>::T* svA,
+                                         const typename Rec<NS>::T* svB, int sv_off, typename Rec<NS>::T* dpA,
+                                         typename Rec<NS>::T* dpB, int dp_logit_off, int dp1_off, AFrag<NS, 2>& f1, const Rows& r,
+                                         int lane) {
+    store_rec<2>(dlogit, dpA + dp_logit_off, dpB + dp_logit_off, r);
     AFrag<NS, 1> fl;
     to_afrag<NS, 1>(fl, dlogit);
     float dhid[4][4], hid[4][4];
     zero_c<4>(dhid);
     gemm<NS, 1, 4>(dhid, fl, w2t, lane);
-    load_c<4>(hid, svA + sv_off, svB + sv_off, r.t);
+    load_rec<4>(hid, svA + sv_off, svB + sv_off, r.t);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dhid[nt][j] *= elu_grad_from_out(hid[nt][j]);
-    store_c<4>(dhid, dpA + dp1_off, dpB + dp1_off, r);
+    store_rec<4>(dhid, dpA + dp1_off, dpB + dp1_off, r);
     to_afrag<NS, 2>(f1, dhid);
 }
 
@@ -347,6 +362,9 @@ __global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) 
     const int T = p.T;
     constexpr int F = 96;
     const float keep_l = 1.f - p.inv_tau_l, keep_h = 1.f - p.inv_tau_h;
+    using RT = typename Rec<NS>::T;
+    const RT* saved = reinterpret_cast<const RT*>(p.saved);
+    RT* dpre = reinterpret_cast<RT*>(p.dpre);
 
     // carried gradients (w.r.t. the state handed from step t to step t+1)
     float ddl[4][4], ddh[4][4], dul[4][4], duh[4][4], dzl[2][4], dzh[2][4];
@@ -354,10 +372,25 @@ __global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) 
 
     for (int t = T - 1; t >= 0; --t) {
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
-        const float* svA = p.saved + iA * MTRSSM_SAVED_FLOATS;
-        const float* svB = p.saved + iB * MTRSSM_SAVED_FLOATS;
-        float* dpA = p.dpre + iA * MTRSSM_DPRE_FLOATS;
-        float* dpB = p.dpre + iB * MTRSSM_DPRE_FLOATS;
+        const RT* svA = saved + iA * MTRSSM_SAVED_FLOATS;
+        const RT* svB = saved + iB * MTRSSM_SAVED_FLOATS;
+        RT* dpA = dpre + iA * MTRSSM_DPRE_FLOATS;
+        RT* dpB = dpre + iB * MTRSSM_DPRE_FLOATS;
+        if (t > 0) {  // pull step t-1's rows into L2 (lanes 0,1 -> row A; 2,3 -> row B)
+            const size_t ip = (r.t < 2 ? iA : iB) - 1;
+            if (r.t & 1) {
+                prefetch_bulk_l2(saved + ip * MTRSSM_SAVED_FLOATS, MTRSSM_SAVED_FLOATS * sizeof(RT));
+                prefetch_bulk_l2(p.feature + ip * F, F * 4);
+                if (p.d_kl_l) prefetch_l2(p.d_kl_l + ip);
+                if (p.d_kl_h) prefetch_l2(p.d_kl_h + ip);
+            } else {
+                prefetch_bulk_l2(p.d_feature + ip * F, F * 4);
+                prefetch_bulk_l2(p.post_probs_h + ip * 16, 64);
+                prefetch_bulk_l2(p.post_probs_l + ip * 16, 64);
+                prefetch_bulk_l2(p.prior_probs_h + ip * 16, 64);
+                prefetch_bulk_l2(p.prior_probs_l + ip * 16, 64);
+            }
+        }
 
         add_global<4>(ddh, p.d_feature, iA * F, iB * F, r.t);
         add_global<2>(dzh, p.d_feature, iA * F + 32, iB * F + 32, r.t);  // straight-through: d stoch -> d probs
@@ -404,8 +437,8 @@ __global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) 
             {
                 float dm[2][4], la[2][4], lv[2][4], lsa[2][4], lsv[2][4], mixed[2][4], ra[2][4], rv[2][4];
                 softmax_groups_bwd<KL>(q, dzl, dm);
-                load_c<2>(la, svA + mts::LA, svB + mts::LA, r.t);
-                load_c<2>(lv, svA + mts::LV, svB + mts::LV, r.t);
+                load_rec<2>(la, svA + mts::LA, svB + mts::LA, r.t);
+                load_rec<2>(lv, svA + mts::LV, svB + mts::LV, r.t);
                 log_softmax_flat<NS == 1>(la, lsa);
                 log_softmax_flat<NS == 1>(lv, lsv);
                 mopoe_mix<NS == 1>(lsa, lsv, mixed, ra, rv);
@@ -454,8 +487,8 @@ __global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) 
                     duh[nt][j] = gh * keep_h;
                     dul[nt][j] = gl * keep_l;
                 }
-            store_c<4>(pl, dpA + mtd::L, dpB + mtd::L, r);
-            store_c<4>(ph, dpA + mtd::H, dpB + mtd::H, r);
+            store_rec<4>(pl, dpA + mtd::L, dpB + mtd::L, r);
+            store_rec<4>(ph, dpA + mtd::H, dpB + mtd::H, r);
             AFrag<NS, 2> fl, fh;
             to_afrag<NS, 2>(fl, pl);
             to_afrag<NS, 2>(fh, ph);

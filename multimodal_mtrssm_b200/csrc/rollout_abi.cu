@@ -63,13 +63,26 @@ int check_mtrssm(const RssmMtrssmDims* d) {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-void add_seg(rssm::WgradMmaArgs& a, int dst, const float* ptr, int ld, int valid, int shift = 0, const float* ptr0 = nullptr,
-             int ld0 = 0) {
+// appends a source segment at staged column `dst` (segments must be added in increasing, gap-free dst order).
+// `elem` = element size in bytes of the source (4: fp32, 2: bf16); ptr/ptr0 are element pointers of that type.
+void add_seg(rssm::WgradMmaArgs& a, int dst, const void* ptr, int ld, int valid, int elem = 4, int shift = 0,
+             const void* ptr0 = nullptr, int ld0 = 0) {
     rssm::WgradSeg& s = a.seg[a.nseg++];
-    s.ptr = ptr, s.ptr0 = ptr0 ? ptr0 : ptr, s.ld = ld, s.ld0 = ptr0 ? ld0 : ld;
-    s.valid = valid, s.ncols = (valid + 3) & ~3, s.dst = dst, s.shift = shift;
-    s.vec = (valid % 4 == 0) && (s.ld % 4 == 0) && (s.ld0 % 4 == 0) && aligned16(s.ptr) && aligned16(s.ptr0);
+    s.ptr = static_cast<const char*>(ptr), s.ptr0 = static_cast<const char*>(ptr0 ? ptr0 : ptr);
+    s.ld_bytes = ld * elem, s.ld0_bytes = (ptr0 ? ld0 : ld) * elem;
+    s.valid = valid, s.shift = shift;
+    s.c4_begin = dst / 4, s.c4_end = s.c4_begin + (valid + 3) / 4;
+    if (elem == 2) {
+        s.kind = 2;
+    } else {
+        const bool vec = (valid % 4 == 0) && (s.ld_bytes % 16 == 0) && (s.ld0_bytes % 16 == 0) && aligned16(s.ptr) && aligned16(s.ptr0);
+        s.kind = vec ? 0 : 1;
+    }
+    a.stride = s.c4_end * 4;
 }
+
+// element pointer arithmetic on the opaque records (fp32 or bf16 depending on the precision)
+const void* rec_at(const void* base, int elem_off, int elem) { return static_cast<const char*>(base) + (size_t)elem_off * elem; }
 
 void set_out(rssm::WgradMmaArgs& a, int id, float* dW, int ldw, int kvalid, float* db0 = nullptr, float* db1 = nullptr) {
     rssm::WgradOut& o = a.out[id];
@@ -142,7 +155,7 @@ int rssm_mrssm_rollout_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, co
     return rssm_mrssm_wgrad(d, in, fo, gin->dpre, gw, stream);
 }
 
-int rssm_mrssm_wgrad(const RssmMrssmDims* d, const RssmMrssmInputs* in, const RssmMrssmOutputs* fo, const float* dpre,
+int rssm_mrssm_wgrad(const RssmMrssmDims* d, const RssmMrssmInputs* in, const RssmMrssmOutputs* fo, const void* dpre,
                      const RssmMrssmWeightGrads* gw, void* stream) {
     if (check_mrssm(d)) return 1;
     REQUIRE(in); REQUIRE(fo); REQUIRE(dpre); REQUIRE(gw);
@@ -151,20 +164,23 @@ int rssm_mrssm_wgrad(const RssmMrssmDims* d, const RssmMrssmInputs* in, const Rs
     // staged-row layout and part ids: kernels.h (wgl_mr); record offsets: mrssm_kernels.cu (mrs / mrd)
     using namespace rssm::wgl_mr;
     const int A = d->A, F = 48, SV = MRSSM_SAVED_FLOATS, DPF = MRSSM_DPRE_FLOATS;
-    const float *sv = fo->saved, *feat = fo->feature;
+    const int RE = d->precision == RSSM_PRECISION_BF16 ? 2 : 4;  // record element size
+    const void* sv = fo->saved;
+    const float* feat = fo->feature;
     rssm::WgradMmaArgs j{};
-    j.B = d->B, j.T = d->T, j.stride = STRIDE;
-    add_seg(j, DP, dpre, DPF, DPF);
-    add_seg(j, XASPZ, feat + 32, F, 16, 1, in->z0, 16);   // z_prev
-    add_seg(j, XASPA, in->actions, A, A);                 // action (+ zero pad to 8)
-    add_seg(j, XH1, sv + 0, SV, 32);                      // asp hidden
-    add_seg(j, XX2, sv + 32, SV, 32);                     // x2 (GRU input)
-    add_seg(j, XHP, feat, F, 32, 1, in->h0, 32);          // h_prev
-    add_seg(j, XA, feat, F, 32);                          // [h | embed_a]
+    j.B = d->B, j.T = d->T;
+    add_seg(j, DP, dpre, DPF, DPF, RE);
+    add_seg(j, XASPZ, feat + 32, F, 16, 4, 1, in->z0, 16);  // z_prev
+    add_seg(j, XASPA, in->actions, A, A);                   // action (+ zero pad to 8)
+    add_seg(j, XH1, rec_at(sv, 0, RE), SV, 32, RE);         // asp hidden
+    add_seg(j, XX2, rec_at(sv, 32, RE), SV, 32, RE);        // x2 (GRU input)
+    add_seg(j, XHP, feat, F, 32, 4, 1, in->h0, 32);         // h_prev
+    add_seg(j, XA, feat, F, 32);                            // [h | embed_a]
     add_seg(j, XA + 32, in->embed_a, 64, 64);
-    add_seg(j, XV, feat, F, 32);                          // [h | embed_v]
+    add_seg(j, XV, feat, F, 32);                            // [h | embed_v]
     add_seg(j, XV + 32, in->embed_v, 64, 64);
-    add_seg(j, HID, sv + 192, SV, 96);                    // prior / audio / vision hidden
+    add_seg(j, HID, rec_at(sv, 192, RE), SV, 96, RE);       // prior / audio / vision hidden
+    if (j.stride != STRIDE) return fail("internal: MRSSM staged row is %d columns, expected %d", j.stride, STRIDE);
     set_out(j, O_ASP1Z, gw->asp_w1 + A, A + 16, 16, gw->asp_b1);
     set_out(j, O_ASP1A, gw->asp_w1, A + 16, A);
     set_out(j, O_ASP2, gw->asp_w2, 32, 32, gw->asp_b2);
@@ -266,7 +282,7 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
     return rssm_mtrssm_wgrad(d, in, fo, gin->dpre, gw, stream);
 }
 
-int rssm_mtrssm_wgrad(const RssmMtrssmDims* d, const RssmMtrssmInputs* in, const RssmMtrssmOutputs* fo, const float* dpre,
+int rssm_mtrssm_wgrad(const RssmMtrssmDims* d, const RssmMtrssmInputs* in, const RssmMtrssmOutputs* fo, const void* dpre,
                       const RssmMtrssmWeightGrads* gw, void* stream) {
     if (check_mtrssm(d)) return 1;
     REQUIRE(in); REQUIRE(fo); REQUIRE(dpre); REQUIRE(gw);
@@ -276,23 +292,26 @@ int rssm_mtrssm_wgrad(const RssmMtrssmDims* d, const RssmMtrssmInputs* in, const
     // feature = [d_h 0 | z_h 32 | d_l 48 | z_l 80]
     using namespace rssm::wgl_mt;
     const int A = d->A, F = 96, SV = MTRSSM_SAVED_FLOATS, DPF = MTRSSM_DPRE_FLOATS, LDIN = A + 32;
-    const float *sv = fo->saved, *feat = fo->feature;
+    const int RE = d->precision == RSSM_PRECISION_BF16 ? 2 : 4;  // record element size
+    const void* sv = fo->saved;
+    const float* feat = fo->feature;
     rssm::WgradMmaArgs j{};
-    j.B = d->B, j.T = d->T, j.stride = STRIDE;
-    add_seg(j, DP, dpre, DPF, DPF);
-    add_seg(j, XLD, feat + 48, F, 32, 1, in->deter_l0, 32);     // d_l_prev
-    add_seg(j, XLZ, feat + 80, F, 16, 1, in->stoch_l0, 16);     // z_l_prev
-    add_seg(j, XLZ + 16, feat + 32, F, 16, 1, in->stoch_h0, 16);  // z_h_prev
-    add_seg(j, XLA, in->actions, A, A);                          // action (+ zero pad to 8)
-    add_seg(j, XHD, feat + 0, F, 32, 1, in->deter_h0, 32);      // d_h_prev
-    add_seg(j, XHI, feat + 32, F, 16, 1, in->stoch_h0, 16);     // z_h_prev
+    j.B = d->B, j.T = d->T;
+    add_seg(j, DP, dpre, DPF, DPF, RE);
+    add_seg(j, XLD, feat + 48, F, 32, 4, 1, in->deter_l0, 32);       // d_l_prev
+    add_seg(j, XLZ, feat + 80, F, 16, 4, 1, in->stoch_l0, 16);       // z_l_prev
+    add_seg(j, XLZ + 16, feat + 32, F, 16, 4, 1, in->stoch_h0, 16);  // z_h_prev
+    add_seg(j, XLA, in->actions, A, A);                               // action (+ zero pad to 8)
+    add_seg(j, XHD, feat + 0, F, 32, 4, 1, in->deter_h0, 32);        // d_h_prev
+    add_seg(j, XHI, feat + 32, F, 16, 4, 1, in->stoch_h0, 16);       // z_h_prev
     add_seg(j, XQ, feat + 48, F, 32);                            // [d_l | d_h]
     add_seg(j, XQ + 32, feat + 0, F, 32);
     add_seg(j, XA, feat + 48, F, 32);                            // [d_l | embed_a]
     add_seg(j, XA + 32, in->embed_a, 64, 64);
     add_seg(j, XV, feat + 48, F, 32);                            // [d_l | embed_v]
     add_seg(j, XV + 32, in->embed_v, 64, 64);
-    add_seg(j, HID, sv, SV, 160);                                // the five head hiddens
+    add_seg(j, HID, sv, SV, 160, RE);                            // the five head hiddens
+    if (j.stride != STRIDE) return fail("internal: MMTRSSM staged row is %d columns, expected %d", j.stride, STRIDE);
     // l_rnn: pre_l = _d2h(d_l_prev) + _input2h([action | z_l_prev | z_h_prev]); both biases see sum(dpre_l)
     set_out(j, O_LD, gw->l_d2h_w, 32, 32, gw->l_d2h_b, gw->l_in_b);
     set_out(j, O_LIZ, gw->l_in_w + A, LDIN, 32);

@@ -172,57 +172,111 @@ __device__ __forceinline__ void program_mrssm(float (&acc)[MAX_TILES][4], const 
 }
 #undef PART
 
-// ---- staging: global fp32 -> shared bf16 planes ---------------------------------------------------------------
+// ---- staging: global (fp32 or bf16) -> shared bf16 planes ----------------------------------------------------------
+// The staged row is tiled by the segments' 4-element chunk ranges.  A per-chunk descriptor table in shared memory
+// (built once per CTA) turns "chunk c of row r" into one address computation.  A warp stages whole rows: its lanes
+// first ISSUE the loads of all their chunks of the row (independent 16/8-byte loads in flight together), then
+// convert and store -- one DRAM round trip per row per warp, and no per-chunk integer division.
+struct ChunkDesc {
+    const char* ptr;  // source of this chunk in row 0 (ptr0: in batch element 0 of the initial-state tensor)
+    int ld;           // row stride in bytes
+    int flags;        // kind (bits 0-1) | shift (bit 2) | valid elements 0..4 (bits 4-6)
+};
+
 template <int NS>
-__device__ __forceinline__ void stage_block(__nv_bfloat16* sm, int stride, int plane, const WgradMmaArgs& a, int row_base, int tid) {
-    const int R = a.B * a.T, T = a.T;
-    for (int si = 0; si < a.nseg; ++si) {
-        const WgradSeg& sg = a.seg[si];
-        const int c4n = sg.ncols >> 2;  // float4 chunks per row (ncols is a multiple of 4, zero-padded by `valid`)
-        for (int i = tid; i < ROWS * c4n; i += THREADS) {
-            const int row = i / c4n, c = (i - row * c4n) * 4;
-            const int r = row_base + row;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (r < R) {
-                const float* src;
-                if (sg.shift) {
-                    const int b = r / T, t = r - b * T;
-                    src = t > 0 ? sg.ptr + (size_t)(r - 1) * sg.ld : sg.ptr0 + (size_t)b * sg.ld0;
-                } else {
-                    src = sg.ptr + (size_t)r * sg.ld;
-                }
-                if (sg.vec && c + 3 < sg.valid) {
-                    const float4 q = *reinterpret_cast<const float4*>(src + c);
-                    v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
-                } else {
+__device__ __forceinline__ void stage_block(__nv_bfloat16* sm, int stride, int plane, const ChunkDesc* __restrict__ desc,
+                                            const ChunkDesc* __restrict__ desc0, int B, int T, int row_base, int warp, int lane) {
+    constexpr int MAXJ = 8;  // up to 256 chunks (1024 staged columns) per row
+    const int R = B * T;
+    const int cpr = stride >> 2;
+    for (int row = warp; row < ROWS; row += THREADS / 32) {
+        const int r = row_base + row;
+        const bool live = r < R;
+        const int b = r / T, t = r - b * T;
+        uint4 raw[MAXJ];
+        int flg[MAXJ];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (c + j < sg.valid) v[j] = src[c + j];
+        for (int j = 0; j < MAXJ; ++j) {
+            const int c = lane + 32 * j;
+            raw[j] = make_uint4(0u, 0u, 0u, 0u);
+            flg[j] = 0;
+            if (c < cpr) {
+                ChunkDesc d = desc[c];
+                const int nvalid = live ? (d.flags >> 4) & 7 : 0;
+                flg[j] = (d.flags & 3) | (nvalid << 4) | 0x100;
+                if (nvalid > 0) {
+                    const char* src;
+                    if (d.flags & 4) {
+                        if (t > 0) {
+                            src = d.ptr + (size_t)(r - 1) * d.ld;
+                        } else {
+                            const ChunkDesc d0 = desc0[c];
+                            src = d0.ptr + (size_t)b * d0.ld;
+                        }
+                    } else {
+                        src = d.ptr + (size_t)r * d.ld;
+                    }
+                    const int kind = d.flags & 3;
+                    if (kind == 0) {
+                        raw[j] = *reinterpret_cast<const uint4*>(src);
+                    } else if (kind == 2) {
+                        const uint2 q = *reinterpret_cast<const uint2*>(src);
+                        raw[j].x = q.x, raw[j].y = q.y;
+                    } else {
+                        const float* f = reinterpret_cast<const float*>(src);
+                        raw[j].x = __float_as_uint(f[0]);
+                        if (nvalid > 1) raw[j].y = __float_as_uint(f[1]);
+                        if (nvalid > 2) raw[j].z = __float_as_uint(f[2]);
+                        if (nvalid > 3) raw[j].w = __float_as_uint(f[3]);
+                    }
                 }
             }
-            uint32_t lo[NS], hi[NS];
-            split_pack<NS>(v[0], v[1], lo);
-            split_pack<NS>(v[2], v[3], hi);
+        }
 #pragma unroll
-            for (int s = 0; s < NS; ++s)
-                *reinterpret_cast<uint2*>(sm + (size_t)s * plane + (size_t)row * stride + sg.dst + c) = make_uint2(lo[s], hi[s]);
+        for (int j = 0; j < MAXJ; ++j) {
+            if (!(flg[j] & 0x100)) continue;
+            const int off = row * stride + (lane + 32 * j) * 4;
+            if ((flg[j] & 3) == 2) {  // already bf16 (bf16 path only)
+                *reinterpret_cast<uint2*>(sm + off) = make_uint2(raw[j].x, raw[j].y);
+            } else {
+                uint32_t lo[NS], hi[NS];
+                split_pack<NS>(__uint_as_float(raw[j].x), __uint_as_float(raw[j].y), lo);
+                split_pack<NS>(__uint_as_float(raw[j].z), __uint_as_float(raw[j].w), hi);
+#pragma unroll
+                for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(sm + (size_t)s * plane + off) = make_uint2(lo[s], hi[s]);
+            }
         }
     }
 }
 
 template <int NS, int MODEL>
-__global__ void __launch_bounds__(THREADS) wgrad_mma_kernel(const WgradMmaArgs a) {
+__global__ void __launch_bounds__(THREADS, NS == 1 ? 2 : 1) wgrad_mma_kernel(const WgradMmaArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     const int stride = a.stride, plane = ROWS * a.stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // per-chunk descriptors in shared memory (per-thread indexing of kernel parameters would push the whole
+    // parameter block into local memory)
+    __shared__ ChunkDesc desc[256], desc0[256];
+    for (int c = tid; c < (stride >> 2); c += THREADS) {
+        int si = 0;
+        while (c >= a.seg[si].c4_end) ++si;
+        const WgradSeg& sg = a.seg[si];
+        const int e = (c - sg.c4_begin) * 4, esz = sg.kind == 2 ? 2 : 4;
+        int nvalid = sg.valid - e;
+        nvalid = nvalid > 4 ? 4 : (nvalid < 0 ? 0 : nvalid);
+        desc[c].ptr = sg.ptr + (size_t)e * esz, desc[c].ld = sg.ld_bytes;
+        desc[c].flags = sg.kind | (sg.shift ? 4 : 0) | (nvalid << 4);
+        desc0[c].ptr = sg.ptr0 + (size_t)e * esz, desc0[c].ld = sg.ld0_bytes, desc0[c].flags = 0;
+    }
+    __syncthreads();
     float acc[MAX_TILES][4];
 #pragma unroll
     for (int i = 0; i < MAX_TILES; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
     const int nblocks = (a.B * a.T + ROWS - 1) / ROWS;
     for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-        stage_block<NS>(sm, stride, plane, a, blk * ROWS, tid);
+        stage_block<NS>(sm, stride, plane, desc, desc0, a.B, a.T, blk * ROWS, warp, lane);
         __syncthreads();
         if (MODEL == 0) program_mtrssm<NS, 0>(acc, sm, stride, plane, a.out, warp, lane);
         else program_mrssm<NS, 0>(acc, sm, stride, plane, a.out, warp, lane);

@@ -31,7 +31,8 @@ def kl_path_weights(use_balancing: bool) -> tuple[float, float]:
 
 
 def _c(t: Optional[Tensor]) -> Optional[Tensor]:
-    return None if t is None else t.contiguous()
+    """contiguous fp32 (inputs may arrive in half precision under autocast; state and I/O of the kernels are fp32)"""
+    return None if t is None else t.float().contiguous()
 
 
 def _fill(struct, names: Sequence[str], tensors: Sequence[Optional[Tensor]]):  # noqa: ANN001
@@ -72,7 +73,7 @@ def mrssm_rollout_op(
     post_probs = torch.empty_like(prior_probs)
     prior_stoch = torch.empty(B, T, 16, device=dev) if u_prior is not None else torch.empty(0, device=dev)
     kl = torch.empty(B, T, device=dev)
-    saved = torch.empty(B, T, _lib.MRSSM_SAVED_FLOATS, device=dev) if save else torch.empty(0, device=dev)
+    saved = torch.empty(B, T, _lib.MRSSM_SAVED_FLOATS, device=dev, dtype=_lib.record_dtype(precision)) if save else torch.empty(0, device=dev)
     w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
     inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0 u_post u_prior".split(),
                 (actions, embed_a, embed_v, h0, z0, u_post, u_prior))
@@ -87,7 +88,7 @@ def _(weights, actions, embed_a, embed_v, h0, z0, u_post, u_prior, K, precision,
     B, T, _ = actions.shape
     e = actions.new_empty
     return [e(B, T, 48), e(B, T, 16 // K, K), e(B, T, 16 // K, K), e(B, T, 16) if u_prior is not None else e(0), e(B, T),
-            e(B, T, _lib.MRSSM_SAVED_FLOATS) if save else e(0)]
+            e(B, T, _lib.MRSSM_SAVED_FLOATS, dtype=_lib.record_dtype(precision)) if save else e(0)]
 
 
 @torch.library.custom_op("mtrssm_b200::mrssm_rollout_bwd", mutates_args=())
@@ -109,7 +110,7 @@ def mrssm_rollout_bwd_op(
     d_embed_v = torch.empty(B, T, 64, device=dev)
     d_h0 = torch.empty(B, 32, device=dev)
     d_z0 = torch.empty(B, 16, device=dev)
-    dpre = torch.empty(B, T, _lib.MRSSM_DPRE_FLOATS, device=dev)
+    dpre = torch.empty(B, T, _lib.MRSSM_DPRE_FLOATS, device=dev, dtype=_lib.record_dtype(precision))
     w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
     gw = _fill(_lib.MrssmWeightGrads(), _lib.MR_WEIGHT_FIELDS, gws)
     inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0".split(), (actions, embed_a, embed_v, h0, z0))
@@ -174,8 +175,8 @@ def mrssm_rollout(
     save = torch.is_grad_enabled() and any(t.requires_grad for t in (*weights, actions, embed_a, embed_v, h0, z0))
     wq, wp = kl_path_weights(use_kl_balancing)
     feature, prior_probs, post_probs, prior_stoch, kl, _ = mrssm_rollout_op(
-        [w.contiguous() for w in weights], actions.contiguous(), embed_a.contiguous(), embed_v.contiguous(),
-        h0.contiguous(), z0.contiguous(), u_post.contiguous(), _c(u_prior), class_size, precision, wq, wp, save,
+        [_c(w) for w in weights], _c(actions), _c(embed_a), _c(embed_v), _c(h0), _c(z0), _c(u_post), _c(u_prior),
+        class_size, precision, wq, wp, save,
     )
     return {"feature": feature, "prior_probs": prior_probs, "post_probs": post_probs,
             "prior_stoch": prior_stoch if u_prior is not None else None, "kl": kl}
@@ -205,8 +206,7 @@ def mrssm_imagine(weights: Sequence[Tensor], *, actions: Tensor, h0: Tensor, z0:
                   precision: int = _lib.PRECISION_FP32) -> dict[str, Tensor]:
     """Fused BaseRSSM.rollout_transition (core.py:170-185).  Forward only (the reference calls it under no_grad)."""
     with torch.no_grad():
-        feature, probs = mrssm_imagine_op([w.contiguous() for w in weights], actions.contiguous(), h0.contiguous(),
-                                          z0.contiguous(), u.contiguous(), class_size, precision)
+        feature, probs = mrssm_imagine_op([_c(w) for w in weights], _c(actions), _c(h0), _c(z0), _c(u), class_size, precision)
     return {"feature": feature, "probs": probs}
 
 
@@ -249,7 +249,7 @@ def mtrssm_rollout_op(
     has_prior = u_prior_l is not None
     pz_h, pz_l = (e(B, T, 16), e(B, T, 16)) if has_prior else (e(0), e(0))
     kl_l, kl_h = e(B, T), e(B, T)
-    saved = e(B, T, _lib.MTRSSM_SAVED_FLOATS) if save else e(0)
+    saved = torch.empty(B, T, _lib.MTRSSM_SAVED_FLOATS, device=dev, dtype=_lib.record_dtype(precision)) if save else e(0)
     w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
     inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE, "u_post_l", "u_post_h", "u_prior_l", "u_prior_h"],
                 (actions, embed_a, embed_v, *state, u_post_l, u_post_h, u_prior_l, u_prior_h))
@@ -270,7 +270,7 @@ def _(weights, actions, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, 
     e = actions.new_empty
     pz = e(B, T, 16) if u_prior_l is not None else e(0)
     return [e(B, T, 96), e(B, T, 32), e(B, T, 32), e(B, T, 16 // KH, KH), e(B, T, 16 // KL, KL), e(B, T, 16 // KH, KH),
-            e(B, T, 16 // KL, KL), pz, torch.empty_like(pz), e(B, T), e(B, T), e(B, T, _lib.MTRSSM_SAVED_FLOATS) if save else e(0)]
+            e(B, T, 16 // KL, KL), pz, torch.empty_like(pz), e(B, T), e(B, T), e(B, T, _lib.MTRSSM_SAVED_FLOATS, dtype=_lib.record_dtype(precision)) if save else e(0)]
 
 
 @torch.library.custom_op("mtrssm_b200::mtrssm_rollout_bwd", mutates_args=())
@@ -291,7 +291,7 @@ def mtrssm_rollout_bwd_op(
     e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
     d_actions, d_ea, d_ev = e(B, T, A), e(B, T, 64), e(B, T, 64)
     d_state = [e(B, 32), e(B, 32), e(B, 32), e(B, 32), e(B, 16), e(B, 16)]
-    dpre = e(B, T, _lib.MTRSSM_DPRE_FLOATS)
+    dpre = torch.empty(B, T, _lib.MTRSSM_DPRE_FLOATS, device=dev, dtype=_lib.record_dtype(precision))
     w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
     gw = _fill(_lib.MtrssmWeightGrads(), _lib.MT_WEIGHT_FIELDS, gws)
     inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE], (actions, embed_a, embed_v, *state))
@@ -370,8 +370,8 @@ def mtrssm_rollout(
     save = torch.is_grad_enabled() and any(t.requires_grad for t in (*weights, actions, embed_a, embed_v, *state))
     wq, wp = kl_path_weights(use_kl_balancing)
     out = mtrssm_rollout_op(
-        [w.contiguous() for w in weights], actions.contiguous(), embed_a.contiguous(), embed_v.contiguous(),
-        [s.contiguous() for s in state], u_post_l.contiguous(), u_post_h.contiguous(), _c(u_prior_l), _c(u_prior_h),
+        [_c(w) for w in weights], _c(actions), _c(embed_a), _c(embed_v), [_c(s) for s in state], _c(u_post_l), _c(u_post_h),
+        _c(u_prior_l), _c(u_prior_h),
         class_size_l, class_size_h, float(l_tau), float(h_tau), precision, wq, wp, save,
     )
     names = ("feature hidden_h hidden_l prior_probs_h prior_probs_l post_probs_h post_probs_l prior_stoch_h prior_stoch_l "
@@ -411,8 +411,8 @@ def mtrssm_imagine(
     l_tau: float = 2.0, h_tau: float = 4.0, precision: int = _lib.PRECISION_FP32,
 ) -> dict[str, Tensor]:
     """Fused MoPoE_MMTRSSM.rollout_transition (mmtrssm/mopoe_mmtrssm/core.py:496-544).  Forward only."""
-    state = [s.contiguous() for s in (deter_h0, deter_l0, hidden_h0, hidden_l0, stoch_h0, stoch_l0)]
+    state = [_c(s) for s in (deter_h0, deter_l0, hidden_h0, hidden_l0, stoch_h0, stoch_l0)]
     with torch.no_grad():
-        out = mtrssm_imagine_op([w.contiguous() for w in weights], actions.contiguous(), state, u_l.contiguous(),
-                                u_h.contiguous(), class_size_l, class_size_h, float(l_tau), float(h_tau), precision)
+        out = mtrssm_imagine_op([_c(w) for w in weights], _c(actions), state, _c(u_l), _c(u_h), class_size_l, class_size_h,
+                                float(l_tau), float(h_tau), precision)
     return dict(zip("feature hidden_h hidden_l probs_h probs_l".split(), out))
