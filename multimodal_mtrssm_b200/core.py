@@ -1,0 +1,144 @@
+"""`BaseRSSM` -- mirror of the reference's `models/core.py` (:13-266).
+
+Same constructor, abstract hooks, `initial_state`, `rollout_representation`, `rollout_transition`, `shared_step`,
+`training_step`, `validation_step` and logged keys.  It is a `lightning.LightningModule` when lightning is
+installed, otherwise an `nn.Module` with the two members the methods need (`device`, `log_dict`), so the same class
+is driven by LightningCLI there and by a plain loop here."""
+
+from __future__ import annotations
+
+from abc import abstractmethod
+
+import torch
+from torch import Tensor, nn
+
+from .distribution import kl_divergence
+from .networks import Representation, Transition
+from .state import State, stack_states
+
+try:  # pragma: no cover - lightning is absent in the build image
+    from lightning import LightningModule as _Base
+except ImportError:
+
+    class _Base(nn.Module):  # type: ignore[no-redef]
+        """Minimal LightningModule surface used by the RSSM classes."""
+
+        @property
+        def device(self) -> torch.device:
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+        def log_dict(self, *_args, **_kwargs) -> None:  # noqa: ANN002, ANN003
+            return None
+
+
+class BaseRSSM(_Base):
+    """Base RSSM (reference: models/core.py:13-31)."""
+
+    #: None = follow autocast (bf16 tensor-core path when `torch.is_autocast_enabled()`, else the fp32-parity path);
+    #: "fp32" / "bf16" force one.
+    rollout_precision: str | None = None
+
+    def __init__(
+        self,
+        *,
+        representation: Representation,
+        transition: Transition,
+        init_proj: nn.Module,
+        kl_coeff: float,
+        use_kl_balancing: bool,
+    ) -> None:
+        super().__init__()
+        self.representation = representation
+        self.transition = transition
+        self.init_proj = init_proj
+        self.kl_coeff = kl_coeff
+        self.use_kl_balancing = use_kl_balancing
+
+    # ---- hooks the variants implement (core.py:33-119) --------------------------------------------------------
+    @abstractmethod
+    def encode_observation(self, observation): ...  # noqa: ANN001, ANN201
+
+    @abstractmethod
+    def decode_state(self, state): ...  # noqa: ANN001, ANN201
+
+    @abstractmethod
+    def compute_reconstruction_loss(self, reconstructions, targets): ...  # noqa: ANN001, ANN201
+
+    @abstractmethod
+    def get_observations_from_batch(self, batch): ...  # noqa: ANN001, ANN201
+
+    @abstractmethod
+    def get_initial_observation(self, observations): ...  # noqa: ANN001, ANN201
+
+    @abstractmethod
+    def get_targets_from_batch(self, batch): ...  # noqa: ANN001, ANN201
+
+    # ---- precision policy -----------------------------------------------------------------------------------------
+    def _precision(self) -> int:
+        from . import _lib
+
+        if self.rollout_precision is not None:
+            return {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[self.rollout_precision]
+        return _lib.PRECISION_BF16 if torch.is_autocast_enabled() else _lib.PRECISION_FP32
+
+    # ---- reference API ----------------------------------------------------------------------------------------------
+    def initial_state(self, observation) -> State:  # noqa: ANN001
+        """core.py:121-135: encode -> init_proj -> prior head -> factory -> State (samples)."""
+        deter = self.init_proj(self.encode_observation(observation))
+        logits = self.transition.rnn_to_prior_projector(deter)
+        return State(deter=deter, distribution=self.representation.distribution_factory(logits)).to(self.device)
+
+    def rollout_representation(self, *, actions: Tensor, observations, prev_state: State) -> tuple[State, State]:  # noqa: ANN001
+        """core.py:137-168: the unimodal per-step loop (kept for API parity; both shipped models override it)."""
+        obs_embed = self.encode_observation(observations)
+        priors, posteriors = [], []
+        for t in range(obs_embed.shape[1]):
+            prior = self.transition(actions[:, t], prev_state)
+            posterior = self.representation(obs_embed[:, t], prior)
+            priors.append(prior)
+            posteriors.append(posterior)
+            prev_state = posterior
+        return stack_states(posteriors, dim=1), stack_states(priors, dim=1)
+
+    def rollout_transition(self, *, actions: Tensor, prev_state: State) -> State:
+        """core.py:170-185: imagination, the prior's own sample is fed back."""
+        priors = []
+        for t in range(actions.shape[1]):
+            prev_state = self.transition(actions[:, t], prev_state)
+            priors.append(prev_state)
+        return stack_states(priors, dim=1)
+
+    def shared_step(self, batch: tuple[Tensor, ...]) -> dict[str, Tensor]:
+        """core.py:187-221: recon + kl_coeff * KL(posterior || prior)."""
+        observations = self.get_observations_from_batch(batch)
+        posterior, prior = self.rollout_representation(
+            actions=batch[0],  # the action is always first (core.py:197)
+            observations=observations,
+            prev_state=self.initial_state(self.get_initial_observation(observations)),
+        )
+        loss_dict = self.compute_reconstruction_loss(self.decode_state(posterior), self.get_targets_from_batch(batch))
+        kl = kl_divergence(
+            q=posterior.distribution.independent(1), p=prior.distribution.independent(1), use_balancing=self.use_kl_balancing
+        ).mul(self.kl_coeff)
+        loss_dict["kl"] = kl
+        loss_dict["loss"] = loss_dict["recon"] + kl
+        return loss_dict
+
+    def _step(self, batch: tuple[Tensor, ...], stage: str) -> dict[str, Tensor]:
+        loss_dict = self.shared_step(batch)
+        out = {f"{stage}/{k}": v for k, v in loss_dict.items()}
+        if stage == "train":
+            out = {"loss": loss_dict["loss"], **out}  # Lightning's automatic optimisation needs "loss" (core.py:234-236)
+        self.log_dict(out, prog_bar=True, sync_dist=True, on_step=False, on_epoch=True)
+        return out
+
+    def training_step(self, batch: tuple[Tensor, ...], _: int) -> dict[str, Tensor]:
+        """core.py:223-244"""
+        return self._step(batch, "train")
+
+    def validation_step(self, batch: tuple[Tensor, ...], _batch_index: int) -> dict[str, Tensor]:
+        """core.py:246-266"""
+        return self._step(batch, "val")

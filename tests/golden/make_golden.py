@@ -192,7 +192,11 @@ def golden_mrssm(ref, B: int, T: int, Ti: int) -> dict:  # noqa: ANN001
         imag = model.rollout_transition(actions=act_im, prev_state=post[:, -1])
         u_imag = torch.stack(list(NOISE.log), 1)
 
+    full_grads = {k: (torch.zeros_like(v) if v.grad is None else v.grad.clone()) for k, v in model.named_parameters()}
     return {
+        "full_state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+        "full_grads": full_grads,
+        "batch": tuple(t.clone() for t in batch),
         "dims": dict(B=B, T=T, Ti=Ti, A=6, E=E, D=32, H=32, C=4, K=4, kl_coeff=1.0, use_kl_balancing=True),
         "params": {k: v.detach().clone() for k, v in params.items()},
         "inputs": {
@@ -290,7 +294,11 @@ def golden_mtrssm(ref, B: int, T: int, Ti: int) -> dict:  # noqa: ANN001
         u_imag_h = torch.stack(log[0::2], 1)
         u_imag_l = torch.stack(log[1::2], 1)
 
+    full_grads = {k: (torch.zeros_like(v) if v.grad is None else v.grad.clone()) for k, v in model.named_parameters()}
     return {
+        "full_state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+        "full_grads": full_grads,
+        "batch": tuple(t.clone() for t in batch),
         "dims": dict(
             B=B, T=T, Ti=Ti, A=6, E=E, HD=32, LD=32, HR=32, HH=32, CL=4, KL=4, CH=8, KH=2,
             l_tau=2.0, h_tau=4.0, kl_coeff=1.0, w_kl_h=1.0, use_kl_balancing=True,

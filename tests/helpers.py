@@ -139,3 +139,78 @@ class Report:
     def finish(self) -> None:
         print(f"\n== {self.title}\n" + "\n".join(self.rows))
         assert not self.failed, f"{self.title}: mismatches in {self.failed}"
+
+
+# ---- tiny encoder/decoder modules with the same parameter names as tests/golden/make_golden.py's stand-ins -------
+class LinEncoder(torch.nn.Module):
+    def __init__(self) -> None:
+        super().__init__()
+        self.lin = torch.nn.Linear(32 * 32, 64)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.lin(x.flatten(start_dim=-3))
+
+
+class LinDecoder(torch.nn.Module):
+    def __init__(self, feature: int) -> None:
+        super().__init__()
+        self.lin = torch.nn.Linear(feature, 32 * 32)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return torch.tanh(self.lin(x)).reshape(*x.shape[:-1], 1, 32, 32)
+
+
+class RandQueue:
+    """Context manager: `torch.rand` pops pre-recorded uniforms (golden noise) in call order."""
+
+    def __init__(self, values: list[torch.Tensor]) -> None:
+        self.values = list(values)
+
+    def __enter__(self):
+        self._orig = torch.rand
+
+        def fake(*size, device=None, dtype=None, generator=None, **_kw):
+            v = self.values.pop(0)
+            shape = tuple(size[0]) if len(size) == 1 and not isinstance(size[0], int) else tuple(size)
+            assert tuple(v.shape) == shape, (tuple(v.shape), shape)
+            return v.to(device=device) if device is not None else v.clone()
+
+        torch.rand = fake
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand = self._orig
+        return False
+
+
+def build_mrssm_model():
+    """Product MoPoE_MRSSM at the default.yaml sizes with LinEncoder/LinDecoder (golden-compatible state_dict)."""
+    from multimodal_mtrssm_b200.mlp import MLP
+    from multimodal_mtrssm_b200.mopoe_mrssm import MoPoE_MRSSM
+    from multimodal_mtrssm_b200.networks import Representation, Transition
+
+    rep = dict(deterministic_size=32, hidden_size=32, obs_embed_size=64, distribution_config=[4, 4], activation_name="ELU")
+    return MoPoE_MRSSM(
+        audio_representation=Representation(**rep), vision_representation=Representation(**rep),
+        transition=Transition(deterministic_size=32, hidden_size=32, action_size=6, distribution_config=[4, 4], activation_name="ELU"),
+        audio_encoder=LinEncoder(), vision_encoder=LinEncoder(), audio_decoder=LinDecoder(48), vision_decoder=LinDecoder(48),
+        init_proj=MLP(in_features=64, out_features=32, num_cells=200, depth=1), kl_coeff=1, use_kl_balancing=True,
+    )
+
+
+def build_mtrssm_model():
+    from multimodal_mtrssm_b200.distribution import MultiOneHotFactory
+    from multimodal_mtrssm_b200.mlp import MLP
+    from multimodal_mtrssm_b200.mopoe_mmtrssm import MoPoE_MMTRSSM
+    from multimodal_mtrssm_b200.networks import Representation
+
+    rep = dict(deterministic_size=32, hidden_size=32, obs_embed_size=64, distribution_config=[4, 4], activation_name="ELU")
+    head = lambda i: MLP(in_features=i, out_features=16, num_cells=32, depth=1, activation_class=torch.nn.ELU)  # noqa: E731
+    return MoPoE_MMTRSSM(
+        audio_representation=Representation(**rep), vision_representation=Representation(**rep),
+        audio_encoder=LinEncoder(), vision_encoder=LinEncoder(), audio_decoder=LinDecoder(96), vision_decoder=LinDecoder(96),
+        init_proj=MLP(in_features=64, out_features=64, num_cells=200, depth=1), kl_coeff=1, use_kl_balancing=True,
+        action_size=6, hd_dim=32, hs_dim=16, ld_dim=32, ls_dim=16, l_tau=2.0, h_tau=4.0,
+        l_prior=head(32), l_posterior=head(96), h_prior=head(32), h_posterior=head(64),
+        l_dist=MultiOneHotFactory(class_size=4, category_size=4), h_dist=MultiOneHotFactory(class_size=2, category_size=8), w_kl_h=1.0,
+    )

@@ -1,0 +1,265 @@
+"""CPU tests of the host-side mirror of the reference interface, the C-ABI surface and the
+data-parallel plumbing.  No GPU compute is launched here."""
+
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.distributions as td
+
+from oracle import rssm_oracle as O
+from tests import helpers as H
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "multimodal_mtrssm_b200"
+
+
+# ---- containers (models/state.py, models/mmtrssm/state.py) ---------------------------------------------------------
+def _state(B=3, T=None):
+    from multimodal_mtrssm_b200.distribution import Distribution
+    from multimodal_mtrssm_b200.state import State
+
+    shape = (B,) if T is None else (B, T)
+    probs = torch.softmax(torch.randn(*shape, 4, 4), -1)
+    return State(deter=torch.randn(*shape, 32), distribution=Distribution(probs))
+
+
+def test_state_samples_in_constructor_and_builds_feature():
+    s = _state()
+    onehot = s.stoch.detach().reshape(3, 4, 4)
+    assert torch.allclose(onehot.sum(-1), torch.ones(3, 4)) and bool(((onehot.round() == 0) | (onehot.round() == 1)).all())
+    assert torch.equal(s.feature, torch.cat([s.deter, s.stoch], -1))  # state.py:18
+
+
+def test_stack_index_cat_roundtrip():
+    from multimodal_mtrssm_b200.state import cat_states, stack_states
+
+    steps = [_state() for _ in range(5)]
+    st = stack_states(steps, dim=1)
+    assert st.deter.shape == (3, 5, 32) and st.distribution.probs.shape == (3, 5, 4, 4)
+    for t, s in enumerate(steps):
+        assert torch.equal(st[:, t].deter, s.deter) and torch.equal(st[:, t].stoch, s.stoch)
+        assert torch.equal(st[:, t].distribution.probs, s.distribution.probs)
+    both = cat_states([st[:, :2], st[:, 2:]], dim=1)
+    assert torch.equal(both.feature, st.feature)
+    assert len(list(iter(st))) == 3 and st.unsqueeze(0).squeeze(0).deter.shape == st.deter.shape
+    assert st.detach().deter.requires_grad is False and st.clone().deter.data_ptr() != st.deter.data_ptr()
+
+
+def test_mtstate_feature_order_and_cat_takes_last_hidden():
+    from multimodal_mtrssm_b200.distribution import Distribution
+    from multimodal_mtrssm_b200.mtstate import MTState, cat_mtstates, stack_mtstates
+
+    def mk():
+        return MTState(
+            deter_h=torch.randn(2, 32), deter_l=torch.randn(2, 32), hidden_h=torch.randn(2, 32), hidden_l=torch.randn(2, 32),
+            distribution_h=Distribution(torch.softmax(torch.randn(2, 8, 2), -1)), distribution_l=Distribution(torch.softmax(torch.randn(2, 4, 4), -1)),
+        )
+
+    s = mk()
+    assert torch.equal(s.feature, torch.cat([s.deter_h, s.stoch_h, s.deter_l, s.stoch_l], -1))  # mmtrssm/state.py:51
+    st = stack_mtstates([mk() for _ in range(4)], dim=1)
+    assert st.feature.shape == (2, 4, 96) and st.hidden_l.shape == (2, 4, 32)
+    a, b = st[:, :1], st[:, 1:]
+    cat = cat_mtstates([a, b], dim=1)
+    assert torch.equal(cat.feature, st.feature) and torch.equal(cat.hidden_h, b.hidden_h)  # state.py:237-238
+    assert torch.equal(st.clone().distribution_h.probs, st.distribution_h.probs)
+
+
+# ---- third-party stand-ins (A1..A6) --------------------------------------------------------------------------------
+def test_distribution_shim_matches_torch_distributions():
+    from multimodal_mtrssm_b200.distribution import Distribution, MultiOneHotFactory, kl_divergence
+
+    torch.manual_seed(0)
+    logits_q, logits_p = torch.randn(6, 5, 16, requires_grad=True), torch.randn(6, 5, 16, requires_grad=True)
+    fac = MultiOneHotFactory(class_size=2, category_size=8)
+    q, p = fac(logits_q), fac(logits_p)
+    assert q.probs.shape == (6, 5, 8, 2)  # A1: [category, class], softmax over class
+    want = td.kl_divergence(q.independent(1), p.independent(1)).mean()
+    torch.testing.assert_close(kl_divergence(q=q.independent(1), p=p.independent(1), use_balancing=False), want)
+    bal = kl_divergence(q=q.independent(1), p=p.independent(1), use_balancing=True)
+    torch.testing.assert_close(bal, O.kl_per_sample(q.probs, p.probs, True).mean())
+    gq, gp = torch.autograd.grad(bal, [logits_q, logits_p], retain_graph=True)
+    gq1, gp1 = torch.autograd.grad(O.kl_per_sample(q.probs, p.probs, False).mean(), [logits_q, logits_p], retain_graph=True)
+    torch.testing.assert_close(gq, 0.2 * gq1)  # A5 balancing split
+    torch.testing.assert_close(gp, 0.8 * gp1)
+    z = q.rsample()
+    assert z.shape == (6, 5, 16)  # A2: flattened
+    (gz,) = torch.autograd.grad((z * torch.arange(16.0)).sum(), q.probs)
+    torch.testing.assert_close(gz, torch.arange(16.0).reshape(8, 2).expand(6, 5, 8, 2))  # straight-through
+
+
+def test_mlp_stand_in_layout_and_default_activation():
+    from multimodal_mtrssm_b200.mlp import MLP
+
+    m = MLP(in_features=64, out_features=32, num_cells=200, depth=1)
+    assert list(m.state_dict()) == ["0.weight", "0.bias", "2.weight", "2.bias"] and isinstance(m[1], torch.nn.Tanh)  # A6
+    assert isinstance(MLP(4, 2, 8, activation_class="torch.nn.ELU")[1], torch.nn.ELU)
+
+
+def test_likelihood_matches_reference_formula():
+    from multimodal_mtrssm_b200.objective import likelihood
+
+    pred, tgt = torch.randn(2, 3, 1, 8, 8), torch.randn(2, 3, 1, 8, 8)
+    want = -td.Independent(td.Normal(pred, 1.0), 3).log_prob(tgt).mean()  # objective.py:21-23
+    torch.testing.assert_close(likelihood(pred, tgt, event_ndims=3), want)
+    want2 = -td.Independent(td.Normal(pred, 0.5), 3).log_prob(tgt).mean()
+    torch.testing.assert_close(likelihood(pred, tgt, event_ndims=3, scale=0.5), want2)
+
+
+# ---- single-step modules against the oracle ------------------------------------------------------------------------
+def test_transition_and_mtrnn_single_step_match_oracle():
+    from multimodal_mtrssm_b200.distribution import Distribution
+    from multimodal_mtrssm_b200.mopoe_mmtrssm import MTRNN
+    from multimodal_mtrssm_b200.networks import Transition
+    from multimodal_mtrssm_b200.state import State
+
+    torch.manual_seed(1)
+    tr = Transition(deterministic_size=32, hidden_size=32, action_size=6, distribution_config=[4, 4], activation_name="ELU")
+    params = {"transition." + k: v for k, v in tr.state_dict().items()}
+    prev = State(deter=torch.randn(5, 32), distribution=Distribution(torch.softmax(torch.randn(5, 4, 4), -1)))
+    act = torch.randn(5, 6)
+    got = tr(act, prev)
+    deter, probs, _ = O.mrssm_transition(params, act, prev.deter, prev.stoch, 4, 4)
+    torch.testing.assert_close(got.deter, deter)
+    torch.testing.assert_close(got.distribution.probs, probs)
+    cell = MTRNN(input_dim=38, hidden_dim=32, tau=2.0)
+    cp = {"l_rnn." + k: v for k, v in cell.state_dict().items()}
+    x, d, u = torch.randn(5, 38), torch.randn(5, 32), torch.randn(5, 32)
+    cell.hidden = u
+    want_d, want_u = O.mtrnn(cp, "l_rnn", x, d, u, 2.0)
+    torch.testing.assert_close(cell(x, d), want_d)
+    torch.testing.assert_close(cell.hidden, want_u)
+
+
+# ---- error behaviour (SURVEY.md §8(b) "Errors") ----------------------------------------------------------------------
+def test_reference_error_behaviour():
+    from multimodal_mtrssm_b200.mopoe_mmtrssm import MTRNN
+    from multimodal_mtrssm_b200.networks import Representation
+
+    with pytest.raises(ValueError, match="2 elements"):
+        Representation(deterministic_size=32, hidden_size=32, obs_embed_size=64, distribution_config=[4, 4, 4])
+    with pytest.raises(AssertionError, match="tau"):
+        MTRNN(4, 4, tau=1.0)
+    for model in (H.build_mrssm_model(), H.build_mtrssm_model()):
+        with pytest.raises(TypeError, match="requires tuple"):
+            model.rollout_representation(actions=torch.zeros(1, 2, 6), observations=torch.zeros(1, 2, 1, 32, 32), prev_state=None)
+
+
+def test_no_cpu_fallback():
+    """The product path is CUDA-only: CPU tensors raise instead of silently running an eager/oracle path."""
+    from multimodal_mtrssm_b200 import params as P
+    from multimodal_mtrssm_b200 import rollout_ops as R
+
+    with pytest.raises(RuntimeError):
+        R.mrssm_rollout(P.mrssm_weight_list(H.make_params(H.MR_SHAPES)), **H.mrssm_inputs(2, 2))
+    src = "\n".join(p.read_text() for p in PKG.rglob("*.py")) + "\n".join(p.read_text() for p in (PKG / "csrc").glob("*"))
+    assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), "the product must not import the oracle"
+
+
+# ---- state_dict / class-path compatibility -------------------------------------------------------------------------
+def test_state_dict_keys_match_reference(golden_dir):
+    for name, build in (("mrssm_default.pt", H.build_mrssm_model), ("mtrssm_default.pt", H.build_mtrssm_model)):
+        g = torch.load(golden_dir / name)
+        model = build()
+        ours = model.state_dict()
+        assert set(ours) == set(g["full_state_dict"]), set(ours) ^ set(g["full_state_dict"])
+        assert all(ours[k].shape == v.shape for k, v in g["full_state_dict"].items())
+        model.load_state_dict(g["full_state_dict"], strict=True)
+        # alias kept: representation.* is audio_representation.* (mopoe_mrssm/core.py:49,55)
+        assert model.representation is model.audio_representation
+    mt = H.build_mtrssm_model().state_dict()
+    for dead in ("transition.rnn_cell.weight_ih", "l_posterior.0.weight", "l_rnn._d2h.weight", "h_rnn._input2h.bias"):
+        assert dead in mt
+
+
+def test_class_paths_and_yaml_configs_instantiate():
+    from multimodal_mtrssm_b200 import compat
+
+    compat.install()
+    import importlib
+
+    for path, cls in (("multimodal_rssm.models.mrssm.mopoe_mrssm", "MoPoE_MRSSM"), ("multimodal_rssm.models.mmtrssm.mopoe_mmtrssm", "MoPoE_MMTRSSM"),
+                      ("multimodal_rssm.models.networks", "Transition"), ("multimodal_rssm.models.mmtrssm", "cat_mtstates"),
+                      ("multimodal_rssm.models", "stack_states"), ("multimodal_rssm.models.objective", "likelihood")):
+        assert hasattr(importlib.import_module(path), cls)
+    yamls = [PKG / "configs" / "mopoe_mrssm_default.yaml", PKG / "configs" / "mopoe_mmtrssm_default.yaml"]
+    ref = Path("/root/reference/src/multimodal_rssm/models")
+    if ref.exists():  # the reference's own configs, where the reference checkout is available
+        yamls += [ref / "mrssm/mopoe_mrssm/configs/default.yaml", ref / "mmtrssm/mopoe_mmtrssm/configs/default.yaml"]
+    for y in yamls:
+        model = compat.load_model(y)
+        assert type(model).__module__.startswith("multimodal_mtrssm_b200")
+        assert len(model.rollout_weights()) in (20, 28)
+
+
+# ---- C ABI ----------------------------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    from multimodal_mtrssm_b200 import _lib
+
+    header = (ROOT / "include" / "rssm_rollout.h").read_text()
+    declared = set(re.findall(r"\b(rssm_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    handle = _lib.lib()  # builds with nvcc if needed; loads without a GPU
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert handle.rssm_abi_version() == _lib.ABI_VERSION
+    import ctypes as C
+
+    assert C.sizeof(_lib.MrssmWeights) == 20 * 8 and C.sizeof(_lib.MtrssmWeights) == 28 * 8
+
+
+# ---- data parallel plumbing (gloo, world size 2) ------------------------------------------------------------------------
+DP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["REPO"])
+from multimodal_mtrssm_b200.dp import FlatGradBucket, broadcast_parameters, reduce_metrics, shard_batch
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["PORT"], rank=rank, world_size=world)
+torch.manual_seed(100 + rank)                      # different init per rank on purpose
+net = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
+dead = torch.nn.Linear(3, 3)                        # never used: grad stays None (MMTRSSM's dummy transition)
+broadcast_parameters(net)
+g = torch.Generator().manual_seed(5)
+x, y = torch.randn(8, 6, generator=g), torch.randn(8, 1, generator=g)
+xs, ys = shard_batch((x, y), rank, world)
+loss = (net(xs) - ys).square().mean()
+loss.backward()
+bucket = FlatGradBucket(list(net.parameters()) + list(dead.parameters()))
+n = bucket.allreduce()
+ref = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
+ref.load_state_dict(net.state_dict())
+(ref(x) - y).square().mean().backward()            # full-batch gradient
+for a, b in zip(net.parameters(), ref.parameters()):
+    torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-6)
+assert all(p.grad is None for p in dead.parameters()) and n == sum(p.numel() for p in net.parameters())
+m = reduce_metrics({"loss": loss, "k": torch.tensor(float(rank))})
+torch.testing.assert_close(m["k"], torch.tensor(0.5))
+torch.testing.assert_close(m["loss"], (ref(x) - y).square().mean().detach(), rtol=1e-5, atol=1e-6)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_flat_bucket_allreduce_world_size_2(tmp_path):
+    script = tmp_path / "dp_worker.py"
+    script.write_text(DP_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [
+        subprocess.Popen([sys.executable, str(script)], env={**os.environ, "RANK": str(r), "WORLD_SIZE": "2", "PORT": port, "REPO": str(ROOT)},
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        for r in range(2)
+    ]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+def test_shard_batch_rejects_ragged():
+    from multimodal_mtrssm_b200.dp import shard_batch
+
+    with pytest.raises(ValueError, match="divisible"):
+        shard_batch((torch.zeros(5, 2),), 0, 2)

@@ -1,0 +1,160 @@
+"""GPU tests of the drop-in model classes: the product's `shared_step` / rollouts (fused CUDA kernels behind the
+reference's Python interface) against golden vectors produced by the reference's own `shared_step`."""
+
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _tol(ref):
+    return dict(rtol=1e-4, atol=2e-5 * max(float(ref.abs().max()), 1e-3))
+
+
+def test_mrssm_shared_step_matches_reference_losses_and_all_gradients(golden_dir):
+    """Drop-in check: same weights (state_dict), same batch, same noise -> same loss dict and the same gradient on
+    EVERY parameter (encoders, decoders, init_proj and the rollout), including the initial_state paths."""
+    g = torch.load(golden_dir / "mrssm_default.pt")
+    model = H.build_mrssm_model()
+    model.load_state_dict(g["full_state_dict"], strict=True)
+    model.cuda()
+    inp = g["inputs"]
+    batch = tuple(t.cuda() for t in g["batch"])
+    # product noise order: initial_state draw, then the rollout's u_post, u_prior (mopoe_mrssm.py)
+    with H.RandQueue([inp["u_z0"], inp["u_post"], inp["u_prior"]]) as q:
+        loss = model.shared_step(batch)
+        assert not q.values
+    rep = H.Report("MoPoE_MRSSM.shared_step vs the reference's shared_step")
+    for k, v in g["loss"].items():
+        rep.check(k, loss[k], v, rtol=1e-5, atol=1e-6)
+    loss["loss"].backward()
+    for k, p in model.named_parameters():
+        rep.check("d " + k, p.grad if p.grad is not None else torch.zeros_like(p), g["full_grads"][k], **_tol(g["full_grads"][k]))
+    rep.finish()
+
+
+def test_mtrssm_shared_step_matches_reference_losses_and_all_gradients(golden_dir):
+    g = torch.load(golden_dir / "mtrssm_default.pt")
+    model = H.build_mtrssm_model()
+    model.load_state_dict(g["full_state_dict"], strict=True)
+    model.cuda()
+    inp = g["inputs"]
+    batch = tuple(t.cuda() for t in g["batch"])
+    # initial_state draws h then l (mmtrssm/state.py:48-49); the rollout draws post_l, post_h, prior_l, prior_h
+    noise = [inp["u_h0"], inp["u_l0"], inp["u_post_l"], inp["u_post_h"], inp["u_prior_l"], inp["u_prior_h"]]
+    with H.RandQueue(noise) as q:
+        loss = model.shared_step(batch)
+        assert not q.values
+    rep = H.Report("MoPoE_MMTRSSM.shared_step vs the reference's shared_step")
+    for k, v in g["loss"].items():
+        rep.check(k, loss[k], v, rtol=1e-5, atol=1e-6)
+    loss["loss"].backward()
+    dead = 0
+    for k, p in model.named_parameters():
+        if p.grad is None:  # the reference leaves these without gradient too
+            assert k.startswith(("transition.", "l_posterior.")), k
+            assert not g["full_grads"][k].any()
+            dead += 1
+            continue
+        rep.check("d " + k, p.grad, g["full_grads"][k], **_tol(g["full_grads"][k]))
+    assert dead > 0
+    rep.finish()
+
+
+def test_rollout_transition_matches_reference_imagination(golden_dir):
+    """callbacks' usage (mrssm/callback.py:184-188): imagination from posterior[:, -1]."""
+    for name, build in (("mrssm_default.pt", H.build_mrssm_model), ("mtrssm_default.pt", H.build_mtrssm_model)):
+        g = torch.load(golden_dir / name)
+        model = build()
+        model.load_state_dict(g["full_state_dict"], strict=True)
+        model.cuda()
+        im, out = g["imagine"], g["outputs"]
+        rep = H.Report(f"{type(model).__name__}.rollout_transition vs reference")
+        with torch.no_grad():
+            if "deter" in out:
+                from multimodal_mtrssm_b200.distribution import Distribution
+                from multimodal_mtrssm_b200.state import State
+
+                prev = State(deter=out["deter"][:, -1].cuda(), stoch=out["post_stoch"][:, -1].cuda(),
+                             distribution=Distribution(out["post_probs"][:, -1].cuda()))
+                with H.RandQueue([im["u"]]):
+                    got = model.rollout_transition(actions=im["actions"].cuda(), prev_state=prev)
+                rep.check("deter", got.deter, im["deter"], rtol=1e-5, atol=2e-6)
+                rep.check("stoch", got.stoch, im["stoch"], rtol=1e-5, atol=2e-6)
+                rep.check("probs", got.distribution.probs, im["probs"], rtol=1e-5, atol=2e-6)
+                assert got.feature.shape == (*im["deter"].shape[:2], 48)
+            else:
+                from multimodal_mtrssm_b200.distribution import Distribution
+                from multimodal_mtrssm_b200.mtstate import MTState
+
+                last = lambda k: out[k][:, -1].cuda()  # noqa: E731
+                prev = MTState(deter_h=last("deter_h"), deter_l=last("deter_l"), hidden_h=last("hidden_h"), hidden_l=last("hidden_l"),
+                               stoch_h=last("post_stoch_h"), stoch_l=last("post_stoch_l"),
+                               distribution_h=Distribution(last("post_probs_h")), distribution_l=Distribution(last("post_probs_l")))
+                with H.RandQueue([im["u_l"], im["u_h"]]):
+                    got = model.rollout_transition(actions=im["actions"].cuda(), prev_state=prev)
+                for k in ("deter_h", "deter_l", "hidden_h", "hidden_l", "stoch_h", "stoch_l"):
+                    rep.check(k, getattr(got, k), im[k], rtol=1e-5, atol=2e-6)
+                rep.check("probs_h", got.distribution_h.probs, im["probs_h"], rtol=1e-5, atol=2e-6)
+                rep.check("probs_l", got.distribution_l.probs, im["probs_l"], rtol=1e-5, atol=2e-6)
+        rep.finish()
+
+
+def test_fused_states_behave_like_reference_states():
+    """Consumers slice / concatenate the stacked States (mrssm/callback.py:184-188,222-225)."""
+    from multimodal_mtrssm_b200.distribution import kl_divergence
+    from multimodal_mtrssm_b200.state import cat_states
+
+    torch.manual_seed(0)
+    model = H.build_mrssm_model().cuda()
+    B, T = 6, 9
+    batch = tuple(t.cuda() for t in (torch.randn(B, T, 6), torch.rand(B, T, 1, 32, 32), torch.rand(B, T, 1, 32, 32)))
+    obs = (batch[1], batch[2])
+    post, prior = model.rollout_representation(actions=batch[0], observations=obs, prev_state=model.initial_state((obs[0][:, 0], obs[1][:, 0])))
+    assert post.feature.shape == (B, T, 48) and post.deter.data_ptr() == post.feature.data_ptr()  # views of one tensor
+    assert torch.equal(post.deter, prior.deter)  # posterior reuses the prior's deter (mopoe_mrssm/core.py:83,163)
+    assert torch.equal(post[:, 3].feature, post.feature[:, 3])
+    again = cat_states([post[:, :4], post[:, 4:]], dim=1)
+    assert torch.equal(again.feature, post.feature)
+    # fused KL == KL recomputed from the returned probabilities
+    fused = kl_divergence(q=post.distribution.independent(1), p=prior.distribution.independent(1), use_balancing=True)
+    sliced = kl_divergence(q=post[:, :].distribution.independent(1), p=prior[:, :].distribution.independent(1), use_balancing=True)
+    torch.testing.assert_close(fused, sliced, rtol=1e-5, atol=1e-7)
+    with torch.no_grad():
+        imag = model.rollout_transition(actions=batch[0][:, :4], prev_state=post[:, -1])
+    assert imag.feature.shape == (B, 4, 48)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        model.rollout_transition(actions=batch[0][:, :4].requires_grad_(True), prev_state=post[:, -1])
+
+
+def test_autocast_selects_the_bf16_path_and_training_reduces_the_loss():
+    from multimodal_mtrssm_b200 import _lib
+
+    torch.manual_seed(0)
+    model = H.build_mtrssm_model().cuda()
+    assert model._precision() == _lib.PRECISION_FP32
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert model._precision() == _lib.PRECISION_BF16
+    B, T = 32, 12
+    g = torch.Generator().manual_seed(1)
+    obs = torch.rand(B, T, 1, 32, 32, generator=g).cuda() * 2 - 1
+    batch = (torch.randn(B, T, 6, generator=g).cuda(), obs, obs.flip(-1), None, obs, obs.flip(-1))
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    losses = []
+    for _ in range(25):
+        opt.zero_grad(set_to_none=True)
+        out = model.training_step(batch, 0)
+        out["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+        opt.step()
+        losses.append(float(out["loss"]))
+    assert losses[-1] < losses[0] and all(map(lambda v: v == v, losses)), losses
+    assert set(out) == {"loss", "train/loss", "train/recon", "train/recon/audio", "train/recon/vision", "train/kl", "train/kl_h"}
