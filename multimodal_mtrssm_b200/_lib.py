@@ -7,6 +7,7 @@ call returns non-zero, a RuntimeError is raised.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from functools import lru_cache
 
 import torch
@@ -94,7 +95,8 @@ EXPORTS = (
 @lru_cache(maxsize=1)
 def lib() -> C.CDLL:
     """Load (building first if needed) the CUDA library.  Raises if it cannot be had."""
-    path = build_library()
+    override = os.environ.get("RSSM_ROLLOUT_LIB")  # experiments / profiling builds of the same ABI
+    path = override if override else build_library()
     handle = C.CDLL(str(path))
     for name in EXPORTS:
         if not hasattr(handle, name):

@@ -152,17 +152,6 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
         RT* svA = saved ? saved + iA * MRSSM_SAVED_FLOATS : nullptr;
         RT* svB = saved ? saved + iB * MRSSM_SAVED_FLOATS : nullptr;
-        if (t + 1 < T) {  // pull the next step's inputs into L2 while this step computes (lanes 0,1 -> row A; 2,3 -> row B)
-            const size_t in = (r.t < 2 ? iA : iB) + 1;
-            if (r.t & 1) {
-                if (!IMAGINE) prefetch_bulk_l2(p.embed_v + in * 64, 256);
-                prefetch_l2(p.actions + in * A);
-            } else {
-                if (!IMAGINE) prefetch_bulk_l2(p.embed_a + in * 64, 256);
-                if (!IMAGINE) prefetch_l2(p.u_post + in * C);
-                if (p.u_prior) prefetch_l2(p.u_prior + in * C);
-            }
-        }
 
         // ---- action_state_projector (networks.py:168-169) ----------------------------------------
         AFrag<NS, 2> fx;
@@ -333,18 +322,6 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
         const RT* svB = saved + iB * MRSSM_SAVED_FLOATS;
         RT* dpA = dpre + iA * MRSSM_DPRE_FLOATS;
         RT* dpB = dpre + iB * MRSSM_DPRE_FLOATS;
-        if (t > 0) {  // pull step t-1's rows into L2 (lanes 0,1 -> row A; 2,3 -> row B)
-            const size_t ip = (r.t < 2 ? iA : iB) - 1;
-            if (r.t & 1) {
-                prefetch_bulk_l2(saved + ip * MRSSM_SAVED_FLOATS, MRSSM_SAVED_FLOATS * sizeof(RT));
-                if (p.d_kl) prefetch_l2(p.d_kl + ip);
-            } else {
-                prefetch_bulk_l2(p.d_feature + ip * F, F * 4);
-                prefetch_bulk_l2(p.post_probs + ip * 16, 64);
-                prefetch_bulk_l2(p.prior_probs + ip * 16, 64);
-                if (t > 1) prefetch_bulk_l2(p.feature + (ip - 1) * F, 128);
-            }
-        }
 
         // upstream gradient on feature = [deter | post_stoch]
         {

@@ -76,8 +76,11 @@ __device__ __forceinline__ void head_l2(float (&acc)[4][4], float (&logits)[2][4
 // ================================================================================================
 // forward
 // ================================================================================================
+#ifndef RSSM_MIN_CTAS
+#define RSSM_MIN_CTAS 1
+#endif
 template <int NS, int KL, int KH, bool IMAGINE>
-__global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) {
+__global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_kernel(const MtrssmFwdArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* W = reinterpret_cast<uint2*>(smem_raw);
     float* bias = reinterpret_cast<float*>(W + (size_t)NS * mt::FWD_TILES * 32);
@@ -160,18 +163,6 @@ __global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) 
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
         RT* svA = saved ? saved + iA * MTRSSM_SAVED_FLOATS : nullptr;
         RT* svB = saved ? saved + iB * MTRSSM_SAVED_FLOATS : nullptr;
-        if (t + 1 < T) {  // pull the next step's inputs into L2 while this step computes (lanes 0,1 -> row A; 2,3 -> row B)
-            const size_t in = (r.t < 2 ? iA : iB) + 1;
-            if (r.t & 1) {
-                if (!IMAGINE) prefetch_bulk_l2(p.embed_v + in * 64, 256);
-                prefetch_l2(p.actions + in * A);
-                if (!IMAGINE) prefetch_l2(p.u_post_h + in * CH);
-            } else {
-                if (!IMAGINE) prefetch_bulk_l2(p.embed_a + in * 64, 256);
-                if (!IMAGINE) prefetch_l2(p.u_post_l + in * CL);
-                if (p.u_prior_l) prefetch_l2(p.u_prior_l + in * CL), prefetch_l2(p.u_prior_h + in * CH);
-            }
-        }
 
         // ---- two leaky-integrator cells (mopoe_mmtrssm/core.py:59-60), both from the PREVIOUS state ----
         {
@@ -235,8 +226,14 @@ __global__ void __launch_bounds__(128) mtrssm_fwd_kernel(const MtrssmFwdArgs p) 
         if constexpr (!IMAGINE) {
         // ---- lower posterior: modality heads on d_l (:422-433), MoPoE fusion (:436-455), sample (:456) ----
         float la[2][4], lv[2][4];
+#ifdef RSSM_EXP_SMALL_BODY  // timing experiment only (wrong results): evaluate ONE modality head, half the code
+        zero_c<2>(lv);
+#pragma unroll
+        for (int m = 0; m < 1; ++m) {
+#else
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
+#endif
             const float* emb = m == 0 ? p.embed_a : p.embed_v;
             float acc[4][4];
             init_bias<4>(acc, bias + (m == 0 ? mt::B_A1 : mt::B_V1), r.t);
@@ -325,7 +322,7 @@ __device__ __forceinline__ void add_global(float (&acc)[NT][4], const float* bas
 }
 
 template <int NS, int KL, int KH>
-__global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) {
+__global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_kernel(const MtrssmBwdArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* W = reinterpret_cast<uint2*>(smem_raw);
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -376,21 +373,6 @@ __global__ void __launch_bounds__(128) mtrssm_bwd_kernel(const MtrssmBwdArgs p) 
         const RT* svB = saved + iB * MTRSSM_SAVED_FLOATS;
         RT* dpA = dpre + iA * MTRSSM_DPRE_FLOATS;
         RT* dpB = dpre + iB * MTRSSM_DPRE_FLOATS;
-        if (t > 0) {  // pull step t-1's rows into L2 (lanes 0,1 -> row A; 2,3 -> row B)
-            const size_t ip = (r.t < 2 ? iA : iB) - 1;
-            if (r.t & 1) {
-                prefetch_bulk_l2(saved + ip * MTRSSM_SAVED_FLOATS, MTRSSM_SAVED_FLOATS * sizeof(RT));
-                prefetch_bulk_l2(p.feature + ip * F, F * 4);
-                if (p.d_kl_l) prefetch_l2(p.d_kl_l + ip);
-                if (p.d_kl_h) prefetch_l2(p.d_kl_h + ip);
-            } else {
-                prefetch_bulk_l2(p.d_feature + ip * F, F * 4);
-                prefetch_bulk_l2(p.post_probs_h + ip * 16, 64);
-                prefetch_bulk_l2(p.post_probs_l + ip * 16, 64);
-                prefetch_bulk_l2(p.prior_probs_h + ip * 16, 64);
-                prefetch_bulk_l2(p.prior_probs_l + ip * 16, 64);
-            }
-        }
 
         add_global<4>(ddh, p.d_feature, iA * F, iB * F, r.t);
         add_global<2>(dzh, p.d_feature, iA * F + 32, iB * F + 32, r.t);  // straight-through: d stoch -> d probs
@@ -535,6 +517,11 @@ static cudaError_t launch(KernelT kernel, const ArgsT& args, int B, size_t smem,
 }
 
 // supported (class_size_l, class_size_h) pairs; default.yaml is (4, 2)
+#ifdef RSSM_EXP_ONLY_DEFAULT
+#define MT_DISPATCH(KERNEL, ...)                                                              \
+    if (a.KL == 4 && a.KH == 2) return launch(KERNEL<NS, 4, 2 __VA_ARGS__>, a, a.B, smem, s); \
+    return cudaErrorInvalidValue;
+#else
 #define MT_DISPATCH(KERNEL, ...)                                                              \
     if (a.KL == 4 && a.KH == 2) return launch(KERNEL<NS, 4, 2 __VA_ARGS__>, a, a.B, smem, s); \
     if (a.KL == 4 && a.KH == 4) return launch(KERNEL<NS, 4, 4 __VA_ARGS__>, a, a.B, smem, s); \
@@ -542,6 +529,7 @@ static cudaError_t launch(KernelT kernel, const ArgsT& args, int B, size_t smem,
     if (a.KL == 8 && a.KH == 8) return launch(KERNEL<NS, 8, 8 __VA_ARGS__>, a, a.B, smem, s); \
     if (a.KL == 16 && a.KH == 16) return launch(KERNEL<NS, 16, 16 __VA_ARGS__>, a, a.B, smem, s); \
     return cudaErrorInvalidValue;
+#endif
 
 template <int NS, bool IMAGINE>
 static cudaError_t launch_mtrssm_fwd_k(const MtrssmFwdArgs& a, cudaStream_t s) {

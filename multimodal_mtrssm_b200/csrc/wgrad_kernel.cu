@@ -6,7 +6,7 @@
 // initial state for t == 0).  The recurrence only carries data gradients, so this pass is embarrassingly
 // parallel over (b,t).
 //
-// Design: a CTA stages ROWS = 32 consecutive (b,t) rows ONCE from HBM (coalesced float4) into shared memory
+// Design: a CTA stages ROWS = 32 (16 on the fp32 path) consecutive (b,t) rows ONCE from HBM (cp.async) into shared memory
 // as bf16 (NS planes: 1 = bf16 path, 3 = hi/mid/lo split for the fp32-parity path), laid out per layer input so
 // that every layer is one contiguous column range.  Eight warps then each own a fixed set of 16x8 output tiles
 // (<= 20, register accumulators that live across the CTA's whole row loop) and compute
@@ -23,7 +23,7 @@ namespace rssm {
 
 namespace wg {
 
-constexpr int ROWS = 32;
+__host__ __device__ constexpr int rows_of(int ns) { return ns == 1 ? 32 : 16; }  // (b,t) rows staged per block
 constexpr int MAX_TILES = 20;
 constexpr int THREADS = 256;
 
@@ -44,6 +44,7 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* 
 template <int NS, int MT, int NT, int OFF, bool BIAS>
 __device__ __forceinline__ void part(float (&acc)[MAX_TILES][4], const __nv_bfloat16* __restrict__ sm, int stride, int plane,
                                      int colY, int colX, int lane) {
+    constexpr int ROWS = rows_of(NS);
     static_assert(OFF + MT * NT + (BIAS ? MT : 0) <= MAX_TILES, "too many tiles for one warp");
     const int lr = lane & 7, m8 = (lane >> 3) & 1, m16 = (lane >> 4) & 1;
     const uint32_t one2 = (lane >> 2) == 0 ? 0x3f803f80u : 0u;  // bf16 (1,1) in lanes holding output column 0
@@ -173,110 +174,126 @@ __device__ __forceinline__ void program_mrssm(float (&acc)[MAX_TILES][4], const 
 #undef PART
 
 // ---- staging: global (fp32 or bf16) -> shared bf16 planes ----------------------------------------------------------
-// The staged row is tiled by the segments' 4-element chunk ranges.  A per-chunk descriptor table in shared memory
-// (built once per CTA) turns "chunk c of row r" into one address computation.  A warp stages whole rows: its lanes
-// first ISSUE the loads of all their chunks of the row (independent 16/8-byte loads in flight together), then
-// convert and store -- one DRAM round trip per row per warp, and no per-chunk integer division.
+// The staged row is tiled by the segments' 4-element chunk ranges; a per-chunk descriptor table in shared memory
+// (built once per CTA) turns "chunk c of row r" into one address computation.  All of a block's bytes are moved by
+// cp.async (LDGSTS): every load of the block is in flight at once and none of them holds a register.
+//   * bf16 sources (the dpre / saved records on the bf16 path) land directly in their operand position;
+//   * fp32 sources land in a raw staging area and are converted (and split, NS = 3) by a second smem->smem pass.
 struct ChunkDesc {
     const char* ptr;  // source of this chunk in row 0 (ptr0: in batch element 0 of the initial-state tensor)
     int ld;           // row stride in bytes
-    int flags;        // kind (bits 0-1) | shift (bit 2) | valid elements 0..4 (bits 4-6)
+    int flags;        // kind (bits 0-1) | shift (bit 2) | valid elements 0..4 (bits 4-6) | raw chunk index (bits 8-15)
 };
 
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc, int bytes /*4,8,16*/, int src_bytes) {
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+    if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+    else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+// issue the cp.asyncs of one block (no waiting)
 template <int NS>
-__device__ __forceinline__ void stage_block(__nv_bfloat16* sm, int stride, int plane, const ChunkDesc* __restrict__ desc,
+__device__ __forceinline__ void stage_issue(__nv_bfloat16* sm, float* raw, int stride, int raw_cpr, const ChunkDesc* __restrict__ desc,
                                             const ChunkDesc* __restrict__ desc0, int B, int T, int row_base, int warp, int lane) {
-    constexpr int MAXJ = 8;  // up to 256 chunks (1024 staged columns) per row
+    constexpr int ROWS = rows_of(NS);
     const int R = B * T;
     const int cpr = stride >> 2;
     for (int row = warp; row < ROWS; row += THREADS / 32) {
         const int r = row_base + row;
         const bool live = r < R;
-        const int b = r / T, t = r - b * T;
-        uint4 raw[MAXJ];
-        int flg[MAXJ];
-#pragma unroll
-        for (int j = 0; j < MAXJ; ++j) {
-            const int c = lane + 32 * j;
-            raw[j] = make_uint4(0u, 0u, 0u, 0u);
-            flg[j] = 0;
-            if (c < cpr) {
-                ChunkDesc d = desc[c];
-                const int nvalid = live ? (d.flags >> 4) & 7 : 0;
-                flg[j] = (d.flags & 3) | (nvalid << 4) | 0x100;
-                if (nvalid > 0) {
-                    const char* src;
-                    if (d.flags & 4) {
-                        if (t > 0) {
-                            src = d.ptr + (size_t)(r - 1) * d.ld;
-                        } else {
-                            const ChunkDesc d0 = desc0[c];
-                            src = d0.ptr + (size_t)b * d0.ld;
-                        }
+        const int b = live ? r / T : 0, t = live ? r - b * T : 1;
+        for (int c = lane; c < cpr; c += 32) {
+            const ChunkDesc d = desc[c];
+            const int kind = d.flags & 3, nvalid = live ? (d.flags >> 4) & 7 : 0;
+            const char* src = d.ptr;  // any valid address when nothing is read (src_bytes = 0 -> zero fill)
+            if (nvalid > 0) {
+                if (d.flags & 4) {
+                    if (t > 0) {
+                        src = d.ptr + (size_t)(r - 1) * d.ld;
                     } else {
-                        src = d.ptr + (size_t)r * d.ld;
+                        const ChunkDesc d0 = desc0[c];
+                        src = d0.ptr + (size_t)b * d0.ld;
                     }
-                    const int kind = d.flags & 3;
-                    if (kind == 0) {
-                        raw[j] = *reinterpret_cast<const uint4*>(src);
-                    } else if (kind == 2) {
-                        const uint2 q = *reinterpret_cast<const uint2*>(src);
-                        raw[j].x = q.x, raw[j].y = q.y;
-                    } else {
-                        const float* f = reinterpret_cast<const float*>(src);
-                        raw[j].x = __float_as_uint(f[0]);
-                        if (nvalid > 1) raw[j].y = __float_as_uint(f[1]);
-                        if (nvalid > 2) raw[j].z = __float_as_uint(f[2]);
-                        if (nvalid > 3) raw[j].w = __float_as_uint(f[3]);
-                    }
+                } else {
+                    src = d.ptr + (size_t)r * d.ld;
+                }
+            }
+            if (kind == 2) {  // bf16 -> operand position
+                cp_async(sm + (size_t)row * stride + c * 4, src, 8, nvalid * 2);
+            } else {
+                float* dst = raw + ((size_t)row * raw_cpr + ((d.flags >> 8) & 0xff)) * 4;
+                if (kind == 0) {
+                    cp_async(dst, src, 16, nvalid * 4);
+                } else {  // fp32 rows that are only 8-byte aligned (actions): two 8-byte pieces
+                    cp_async(dst, src, 8, (nvalid >= 2 ? 2 : nvalid) * 4);
+                    cp_async(dst + 2, nvalid > 2 ? src + 8 : src, 8, (nvalid > 2 ? nvalid - 2 : 0) * 4);
                 }
             }
         }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// raw fp32 staging area -> bf16 operand planes
+template <int NS>
+__device__ __forceinline__ void stage_convert(__nv_bfloat16* sm, const float* raw, int stride, int plane, int raw_cpr,
+                                              const uint8_t* __restrict__ chunk_of_raw, int tid) {
+    constexpr int ROWS = rows_of(NS);
+    for (int i = tid; i < ROWS * raw_cpr; i += THREADS) {
+        const int row = i / raw_cpr, k = i - row * raw_cpr;
+        const float4 v = *reinterpret_cast<const float4*>(raw + (size_t)i * 4);
+        uint32_t lo[NS], hi[NS];
+        split_pack<NS>(v.x, v.y, lo);
+        split_pack<NS>(v.z, v.w, hi);
+        const int off = row * stride + chunk_of_raw[k] * 4;
 #pragma unroll
-        for (int j = 0; j < MAXJ; ++j) {
-            if (!(flg[j] & 0x100)) continue;
-            const int off = row * stride + (lane + 32 * j) * 4;
-            if ((flg[j] & 3) == 2) {  // already bf16 (bf16 path only)
-                *reinterpret_cast<uint2*>(sm + off) = make_uint2(raw[j].x, raw[j].y);
-            } else {
-                uint32_t lo[NS], hi[NS];
-                split_pack<NS>(__uint_as_float(raw[j].x), __uint_as_float(raw[j].y), lo);
-                split_pack<NS>(__uint_as_float(raw[j].z), __uint_as_float(raw[j].w), hi);
-#pragma unroll
-                for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(sm + (size_t)s * plane + off) = make_uint2(lo[s], hi[s]);
-            }
-        }
+        for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(sm + (size_t)s * plane + off) = make_uint2(lo[s], hi[s]);
     }
 }
 
 template <int NS, int MODEL>
 __global__ void __launch_bounds__(THREADS, NS == 1 ? 2 : 1) wgrad_mma_kernel(const WgradMmaArgs a) {
+    constexpr int ROWS = rows_of(NS);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     const int stride = a.stride, plane = ROWS * a.stride;
+    float* raw = reinterpret_cast<float*>(sm + (size_t)NS * plane);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // per-chunk descriptors in shared memory (per-thread indexing of kernel parameters would push the whole
-    // parameter block into local memory)
+    // parameter block into local memory).  fp32 chunks get consecutive slots in the raw staging row.
     __shared__ ChunkDesc desc[256], desc0[256];
-    for (int c = tid; c < (stride >> 2); c += THREADS) {
-        int si = 0;
-        while (c >= a.seg[si].c4_end) ++si;
-        const WgradSeg& sg = a.seg[si];
-        const int e = (c - sg.c4_begin) * 4, esz = sg.kind == 2 ? 2 : 4;
-        int nvalid = sg.valid - e;
-        nvalid = nvalid > 4 ? 4 : (nvalid < 0 ? 0 : nvalid);
-        desc[c].ptr = sg.ptr + (size_t)e * esz, desc[c].ld = sg.ld_bytes;
-        desc[c].flags = sg.kind | (sg.shift ? 4 : 0) | (nvalid << 4);
-        desc0[c].ptr = sg.ptr0 + (size_t)e * esz, desc0[c].ld = sg.ld0_bytes, desc0[c].flags = 0;
+    __shared__ uint8_t chunk_of_raw[256];
+    __shared__ int raw_cpr_s;
+    if (tid == 0) {
+        int nraw = 0;
+        for (int c = 0; c < (stride >> 2); ++c) {
+            int si = 0;
+            while (c >= a.seg[si].c4_end) ++si;
+            const WgradSeg& sg = a.seg[si];
+            const int e = (c - sg.c4_begin) * 4, esz = sg.kind == 2 ? 2 : 4;
+            int nvalid = sg.valid - e;
+            nvalid = nvalid > 4 ? 4 : (nvalid < 0 ? 0 : nvalid);
+            int slot = 0;
+            if (sg.kind != 2) slot = nraw, chunk_of_raw[nraw++] = (uint8_t)c;
+            desc[c].ptr = sg.ptr + (size_t)e * esz, desc[c].ld = sg.ld_bytes;
+            desc[c].flags = sg.kind | (sg.shift ? 4 : 0) | (nvalid << 4) | (slot << 8);
+            desc0[c].ptr = sg.ptr0 + (size_t)e * esz, desc0[c].ld = sg.ld0_bytes, desc0[c].flags = 0;
+        }
+        raw_cpr_s = nraw;
     }
     __syncthreads();
+    const int raw_cpr = raw_cpr_s;
     float acc[MAX_TILES][4];
 #pragma unroll
     for (int i = 0; i < MAX_TILES; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
     const int nblocks = (a.B * a.T + ROWS - 1) / ROWS;
     for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-        stage_block<NS>(sm, stride, plane, desc, desc0, a.B, a.T, blk * ROWS, warp, lane);
+        stage_issue<NS>(sm, raw, stride, raw_cpr, desc, desc0, a.B, a.T, blk * ROWS, warp, lane);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        stage_convert<NS>(sm, raw, stride, plane, raw_cpr, chunk_of_raw, tid);
         __syncthreads();
         if (MODEL == 0) program_mtrssm<NS, 0>(acc, sm, stride, plane, a.out, warp, lane);
         else program_mrssm<NS, 0>(acc, sm, stride, plane, a.out, warp, lane);
@@ -290,7 +307,11 @@ __global__ void __launch_bounds__(THREADS, NS == 1 ? 2 : 1) wgrad_mma_kernel(con
 
 template <int NS, int MODEL>
 static cudaError_t launch_wgrad_k(const WgradMmaArgs& a, cudaStream_t s) {
-    const size_t smem = (size_t)NS * wg::ROWS * a.stride * sizeof(__nv_bfloat16);
+    // operand planes + raw fp32 staging of the fp32-sourced chunks
+    int raw_chunks = 0;
+    for (int i = 0; i < a.nseg; ++i)
+        if (a.seg[i].kind != 2) raw_chunks += a.seg[i].c4_end - a.seg[i].c4_begin;
+    const size_t smem = (size_t)wg::rows_of(NS) * ((size_t)NS * a.stride * sizeof(__nv_bfloat16) + (size_t)raw_chunks * 16);
     auto kernel = wg::wgrad_mma_kernel<NS, MODEL>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
@@ -300,7 +321,7 @@ static cudaError_t launch_wgrad_k(const WgradMmaArgs& a, cudaStream_t s) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int nblocks = (a.B * a.T + wg::ROWS - 1) / wg::ROWS;
+    const int nblocks = (a.B * a.T + wg::rows_of(NS) - 1) / wg::rows_of(NS);
     int grid = sms * (per_sm > 0 ? per_sm : 1);
     if (grid > nblocks) grid = nblocks;
     kernel<<<grid, wg::THREADS, smem, s>>>(a);
