@@ -175,8 +175,8 @@ __device__ __forceinline__ void program_mrssm(float (&acc)[MAX_TILES][4], const 
 
 // ---- staging: global (fp32 or bf16) -> shared bf16 planes ----------------------------------------------------------
 // The staged row is tiled by the segments' 4-element chunk ranges; a per-chunk descriptor table in shared memory
-// (built once per CTA) turns "chunk c of row r" into one address computation.  All of a block's bytes are moved by
-// cp.async (LDGSTS): every load of the block is in flight at once and none of them holds a register.
+// All of a block's bytes are moved by bulk asynchronous copies (cp.async.bulk, one per (segment,row) piece, completion
+// on an mbarrier): every load of the block is in flight at once and none of them holds a register.
 //   * bf16 sources (the dpre / saved records on the bf16 path) land directly in their operand position;
 //   * fp32 sources land in a raw staging area and are converted (and split, NS = 3) by a second smem->smem pass.
 struct ChunkDesc {
@@ -192,44 +192,76 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc, int b
     else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
-// issue the cp.asyncs of one block (no waiting)
+// ---- mbarrier + bulk-copy (TMA 1-D) helpers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bounded wait: a lost transaction traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+// Issue one block: one bulk copy per (segment, row) piece -- bf16 pieces straight into their operand position, fp32
+// pieces into the raw area; rows that only allow 8-byte alignment (actions) go through cp.async.  `total_tx` bytes
+// are announced on the mbarrier by thread 0.  Dead rows (tail block) are zero-filled by plain stores.
 template <int NS>
-__device__ __forceinline__ void stage_issue(__nv_bfloat16* sm, float* raw, int stride, int raw_cpr, const ChunkDesc* __restrict__ desc,
-                                            const ChunkDesc* __restrict__ desc0, int B, int T, int row_base, int warp, int lane) {
+__device__ __forceinline__ void stage_issue(__nv_bfloat16* sm, float* raw, int stride, int raw_cpr, const WgradSeg* __restrict__ segs,
+                                            const int* __restrict__ seg_slot, int nseg, int B, int T, int row_base, uint64_t* bar,
+                                            int tid) {
     constexpr int ROWS = rows_of(NS);
     const int R = B * T;
-    const int cpr = stride >> 2;
-    for (int row = warp; row < ROWS; row += THREADS / 32) {
+    const int nlive = min(ROWS, R - row_base);
+    if (tid == 0) {
+        uint32_t per_row = 0;
+        for (int si = 0; si < nseg; ++si)
+            if (segs[si].kind != 1) per_row += segs[si].valid * (segs[si].kind == 2 ? 2 : 4);
+        mbar_expect_tx(bar, per_row * nlive);
+    }
+    for (int job = tid; job < nseg * ROWS; job += THREADS) {
+        const int si = job / ROWS, row = job - si * ROWS;
+        const WgradSeg sg = segs[si];
         const int r = row_base + row;
-        const bool live = r < R;
-        const int b = live ? r / T : 0, t = live ? r - b * T : 1;
-        for (int c = lane; c < cpr; c += 32) {
-            const ChunkDesc d = desc[c];
-            const int kind = d.flags & 3, nvalid = live ? (d.flags >> 4) & 7 : 0;
-            const char* src = d.ptr;  // any valid address when nothing is read (src_bytes = 0 -> zero fill)
-            if (nvalid > 0) {
-                if (d.flags & 4) {
-                    if (t > 0) {
-                        src = d.ptr + (size_t)(r - 1) * d.ld;
-                    } else {
-                        const ChunkDesc d0 = desc0[c];
-                        src = d0.ptr + (size_t)b * d0.ld;
-                    }
-                } else {
-                    src = d.ptr + (size_t)r * d.ld;
-                }
+        const int esz = sg.kind == 2 ? 2 : 4;
+        char* dst = sg.kind == 2 ? reinterpret_cast<char*>(sm + (size_t)row * stride + sg.c4_begin * 4)
+                                 : reinterpret_cast<char*>(raw + ((size_t)row * raw_cpr + seg_slot[si]) * 4);
+        const int nbytes = ((sg.valid + 3) & ~3) * esz;  // padded piece (pad columns are zeroed once at kernel start)
+        if (r >= R) {  // tail: zero the piece
+            for (int o = 0; o < nbytes; o += 8) *reinterpret_cast<uint2*>(dst + o) = make_uint2(0u, 0u);
+            continue;
+        }
+        const char* src;
+        if (sg.shift) {
+            const int b = r / T, t = r - b * T;
+            src = t > 0 ? sg.ptr + (size_t)(r - 1) * sg.ld_bytes : sg.ptr0 + (size_t)b * sg.ld0_bytes;
+        } else {
+            src = sg.ptr + (size_t)r * sg.ld_bytes;
+        }
+        if (sg.kind == 1) {  // 8-byte aligned fp32 rows: cp.async pieces (completion via cp.async.wait_group)
+            for (int e = 0; e < sg.valid; e += 2) {
+                const int n = min(2, sg.valid - e) * 4;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst + e * 4)), "l"(src + e * 4), "r"(n) : "memory");
             }
-            if (kind == 2) {  // bf16 -> operand position
-                cp_async(sm + (size_t)row * stride + c * 4, src, 8, nvalid * 2);
-            } else {
-                float* dst = raw + ((size_t)row * raw_cpr + ((d.flags >> 8) & 0xff)) * 4;
-                if (kind == 0) {
-                    cp_async(dst, src, 16, nvalid * 4);
-                } else {  // fp32 rows that are only 8-byte aligned (actions): two 8-byte pieces
-                    cp_async(dst, src, 8, (nvalid >= 2 ? 2 : nvalid) * 4);
-                    cp_async(dst + 2, nvalid > 2 ? src + 8 : src, 8, (nvalid > 2 ? nvalid - 2 : 0) * 4);
-                }
-            }
+        } else {
+            bulk_g2s(dst, src, sg.valid * esz, bar);
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -260,43 +292,48 @@ __global__ void __launch_bounds__(THREADS, NS == 1 ? 2 : 1) wgrad_mma_kernel(con
     const int stride = a.stride, plane = ROWS * a.stride;
     float* raw = reinterpret_cast<float*>(sm + (size_t)NS * plane);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // per-chunk descriptors in shared memory (per-thread indexing of kernel parameters would push the whole
-    // parameter block into local memory).  fp32 chunks get consecutive slots in the raw staging row.
-    __shared__ ChunkDesc desc[256], desc0[256];
+    // segment table, first raw slot of every fp32 segment, raw-chunk -> staged-chunk map, one mbarrier
+    __shared__ WgradSeg segs[MAX_WGRAD_SEGS];
+    __shared__ int seg_slot[MAX_WGRAD_SEGS];
     __shared__ uint8_t chunk_of_raw[256];
     __shared__ int raw_cpr_s;
+    __shared__ __align__(8) uint64_t bar;
+    if (tid < a.nseg) segs[tid] = a.seg[tid];
     if (tid == 0) {
         int nraw = 0;
-        for (int c = 0; c < (stride >> 2); ++c) {
-            int si = 0;
-            while (c >= a.seg[si].c4_end) ++si;
-            const WgradSeg& sg = a.seg[si];
-            const int e = (c - sg.c4_begin) * 4, esz = sg.kind == 2 ? 2 : 4;
-            int nvalid = sg.valid - e;
-            nvalid = nvalid > 4 ? 4 : (nvalid < 0 ? 0 : nvalid);
-            int slot = 0;
-            if (sg.kind != 2) slot = nraw, chunk_of_raw[nraw++] = (uint8_t)c;
-            desc[c].ptr = sg.ptr + (size_t)e * esz, desc[c].ld = sg.ld_bytes;
-            desc[c].flags = sg.kind | (sg.shift ? 4 : 0) | (nvalid << 4) | (slot << 8);
-            desc0[c].ptr = sg.ptr0 + (size_t)e * esz, desc0[c].ld = sg.ld0_bytes, desc0[c].flags = 0;
+        for (int si = 0; si < a.nseg; ++si) {
+            seg_slot[si] = nraw;
+            if (a.seg[si].kind != 2)
+                for (int c = a.seg[si].c4_begin; c < a.seg[si].c4_end; ++c) chunk_of_raw[nraw++] = (uint8_t)c;
         }
         raw_cpr_s = nraw;
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const int raw_cpr = raw_cpr_s;
+    // zero both areas once: pad columns are never written again (bulk copies move only the valid elements)
+    for (int i = tid; i < (int)(((size_t)NS * plane * 2 + (size_t)ROWS * raw_cpr * 16) / 16); i += THREADS)
+        reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    uint32_t phase = 0;
     float acc[MAX_TILES][4];
 #pragma unroll
     for (int i = 0; i < MAX_TILES; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
     const int nblocks = (a.B * a.T + ROWS - 1) / ROWS;
     for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-        stage_issue<NS>(sm, raw, stride, raw_cpr, desc, desc0, a.B, a.T, blk * ROWS, warp, lane);
+        stage_issue<NS>(sm, raw, stride, raw_cpr, segs, seg_slot, a.nseg, a.B, a.T, blk * ROWS, &bar, tid);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        mbar_wait(&bar, phase);
+        phase ^= 1;
         __syncthreads();
         stage_convert<NS>(sm, raw, stride, plane, raw_cpr, chunk_of_raw, tid);
         __syncthreads();
         if (MODEL == 0) program_mtrssm<NS, 0>(acc, sm, stride, plane, a.out, warp, lane);
         else program_mrssm<NS, 0>(acc, sm, stride, plane, a.out, warp, lane);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order our smem reads before the next bulk writes
         __syncthreads();
     }
     if (MODEL == 0) program_mtrssm<NS, 1>(acc, sm, stride, plane, a.out, warp, lane);
