@@ -303,6 +303,102 @@ __device__ __forceinline__ void load_a_global(AFrag<NS, KT>& a, const float* __r
 }
 
 // ------------------------------------------------------------------------------------------
+// per-warp input staging (forward kernels): the next step's inputs of the warp's 16 rows are pulled into shared
+// memory with cp.async while the current step computes, so the step never waits on a global load.
+// Stage layout (floats): EA[16][64] | EV[16][64] | ACT[16][8] | U0[16][8] | U1[16][8].  The two embedding tiles use a
+// 16-byte-chunk XOR swizzle (chunk ^ 2*(row & 3)) so that the mma A-fragment read pattern (lane (g,t) reads 8 bytes
+// at column 16kt + 2t of row g) is bank-conflict free without padding.
+// ------------------------------------------------------------------------------------------
+namespace stg {
+constexpr int EA = 0, EV = 1024, ACT = 2048, U0 = 2176, U1 = 2304, FLOATS = 2432;  // 9728 bytes per stage
+}
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Issue the copies of step `t` for the warp tile starting at row0 into `stage`.
+//   ea/ev: [B,T,64] fp32;  act: [B,T,A] fp32 (A even, <= 8);  u0/u1: [B,T,n0] / [B,T,n1] fp32 with n0, n1 in {1,2,4,8}
+//   (rows of 4*n bytes; n = 1,2 use 4/8-byte copies).  Any of ea/ev/u0/u1 may be null (skipped).
+__device__ __forceinline__ void stage_inputs(float* stage, const float* __restrict__ ea, const float* __restrict__ ev,
+                                             const float* __restrict__ act, int A, const float* __restrict__ u0, int n0,
+                                             const float* __restrict__ u1, int n1, int row0, int B, int T, int t, int lane) {
+    // embeddings: 16 rows x 16 chunks each -> lane owns chunk (lane & 15) of rows (lane >> 4) + 2i
+    const int chunk = lane & 15;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rl = (lane >> 4) + 2 * i;
+        const int row = min(row0 + rl, B - 1);
+        const size_t src = ((size_t)row * T + t) * 64 + chunk * 4;
+        const int dst = rl * 64 + ((chunk ^ (2 * (rl & 3))) << 2);
+        if (ea != nullptr) cp_async16(stage + stg::EA + dst, ea + src);
+        if (ev != nullptr) cp_async16(stage + stg::EV + dst, ev + src);
+    }
+    // small rows: lane -> (row = lane & 15, half = lane >> 4)
+    {
+        const int rl = lane & 15, half = lane >> 4;
+        const int row = min(row0 + rl, B - 1);
+        const size_t idx = (size_t)row * T + t;
+        // actions: A/2 pieces of 8 bytes; half 0 copies pieces 0,1 and half 1 pieces 2,3
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int piece = 2 * half + k;
+            if (2 * piece < A) cp_async8(stage + stg::ACT + rl * 8 + 2 * piece, act + idx * A + 2 * piece);
+        }
+        const float* us[2] = {u0, u1};
+        const int ns[2] = {n0, n1};
+        const int offs[2] = {stg::U0, stg::U1};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (us[k] == nullptr) continue;
+            const int n = ns[k];
+            float* d = stage + offs[k] + rl * 8;
+            const float* sp = us[k] + idx * n;
+            if (n == 8) {
+                cp_async16(d + 4 * half, sp + 4 * half);
+            } else if (n == 4) {
+                if (half == 0) cp_async16(d, sp);
+            } else if (n == 2) {
+                if (half == 0) cp_async8(d, sp);
+            } else if (half == 0) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(d)), "l"(sp) : "memory");
+            }
+        }
+    }
+    cp_async_commit();
+}
+
+// A operand (KT = 4, 64 columns) from a swizzled staged embedding tile
+template <int NS>
+__device__ __forceinline__ void load_a_staged64(AFrag<NS, 4>& a, const float* tile, int g, int t) {
+    const int sw = 2 * (g & 3);  // same for row g and row g + 8
+    const float* pA = tile + g * 64;
+    const float* pB = tile + (g + 8) * 64;
+    const int in = (2 * t) & 3;
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+        const int c0 = (((4 * kt + (t >> 1)) ^ sw) << 2) + in, c1 = (((4 * kt + (t >> 1) + 2) ^ sw) << 2) + in;
+        const float2 x0 = *reinterpret_cast<const float2*>(pA + c0), y0 = *reinterpret_cast<const float2*>(pB + c0);
+        const float2 x1 = *reinterpret_cast<const float2*>(pA + c1), y1 = *reinterpret_cast<const float2*>(pB + c1);
+        const float q0[4] = {x0.x, x0.y, y0.x, y0.y}, q1[4] = {x1.x, x1.y, y1.x, y1.y};
+        set_ktile<NS, 4>(a, kt, q0, q1);
+    }
+}
+
+// A operand (KT = 1) from the staged action rows ACT[16][8] (columns >= A are zero)
+template <int NS>
+__device__ __forceinline__ void load_a_staged_act(AFrag<NS, 1>& a, const float* act, int g, int t) {
+    const float2 x = *reinterpret_cast<const float2*>(act + g * 8 + 2 * t), y = *reinterpret_cast<const float2*>(act + (g + 8) * 8 + 2 * t);
+    const float q0[4] = {x.x, x.y, y.x, y.y}, q1[4] = {0.f, 0.f, 0.f, 0.f};
+    set_ktile<NS, 1>(a, 0, q0, q1);
+}
+
+// ------------------------------------------------------------------------------------------
 // elementwise math (fp32; accurate libm variants -- parity first)
 // ------------------------------------------------------------------------------------------
 // FAST = false: accurate libm (fp32-parity path).  FAST = true: MUFU approximations (ex2/lg2/tanh/rcp.approx,

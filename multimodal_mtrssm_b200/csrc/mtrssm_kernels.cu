@@ -139,6 +139,15 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
     const float keep_l = 1.f - p.inv_tau_l, keep_h = 1.f - p.inv_tau_h;
     using RT = typename Rec<NS>::T;
     RT* saved = reinterpret_cast<RT*>(p.saved);
+    // per-warp double-buffered input staging (see frag.cuh, namespace stg)
+    // (bf16 path only: on the fp32-parity path the 3-way split weights need the shared memory)
+    constexpr bool STAGED = !IMAGINE && NS == 1;
+    float* stage_base = bias + mt::FWD_BIAS + warp * 2 * stg::FLOATS;
+    if (STAGED) {
+        for (int i = lane; i < 2 * stg::FLOATS; i += 32) stage_base[i] = 0.f;  // action pad columns stay zero
+        __syncwarp();
+        stage_inputs(stage_base, p.embed_a, p.embed_v, p.actions, A, p.u_post_l, CL, p.u_post_h, CH, row0, p.B, T, 0, lane);
+    }
 
     // carried state
     float ul[4][4], uh[4][4];
@@ -163,13 +172,22 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
         RT* svA = saved ? saved + iA * MTRSSM_SAVED_FLOATS : nullptr;
         RT* svB = saved ? saved + iB * MTRSSM_SAVED_FLOATS : nullptr;
+        const float* stage = stage_base + (t & 1) * stg::FLOATS;
+        if (STAGED) {
+            cp_async_wait_all();  // this step's inputs have landed ...
+            __syncwarp();         // ... for every lane, and every lane is done reading the other stage
+            if (t + 1 < T)
+                stage_inputs(stage_base + ((t + 1) & 1) * stg::FLOATS, p.embed_a, p.embed_v, p.actions, A, p.u_post_l, CL, p.u_post_h,
+                             CH, row0, p.B, T, t + 1, lane);
+        }
 
         // ---- two leaky-integrator cells (mopoe_mmtrssm/core.py:59-60), both from the PREVIOUS state ----
         {
             float pl[4][4], ph[4][4];
             init_bias<4>(pl, bias + mt::B_L, r.t);
             AFrag<NS, 1> fa;
-            load_a_global<NS, 1>(fa, p.actions + iA * A, p.actions + iB * A, r.t, A);
+            if (STAGED) load_a_staged_act<NS>(fa, stage + stg::ACT, r.g, r.t);
+            else load_a_global<NS, 1>(fa, p.actions + iA * A, p.actions + iB * A, r.t, A);
             gemm<NS, 2, 4>(pl, dlf, wblk<NS>(W, mt::L_D2H), lane);
             gemm<NS, 1, 4>(pl, zlf, wblk<NS>(W, mt::L_IN_ZL), lane);
             gemm<NS, 1, 4>(pl, zhf, wblk<NS>(W, mt::L_IN_ZH), lane);
@@ -234,11 +252,11 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
 #pragma unroll
         for (int m = 0; m < 2; ++m) {
 #endif
-            const float* emb = m == 0 ? p.embed_a : p.embed_v;
             float acc[4][4];
             init_bias<4>(acc, bias + (m == 0 ? mt::B_A1 : mt::B_V1), r.t);
             AFrag<NS, 4> fe;
-            load_a_global<NS, 4>(fe, emb + iA * 64, emb + iB * 64, r.t, 64);
+            if (STAGED) load_a_staged64<NS>(fe, stage + (m == 0 ? stg::EA : stg::EV), r.g, r.t);
+            else load_a_global<NS, 4>(fe, (m == 0 ? p.embed_a : p.embed_v) + iA * 64, (m == 0 ? p.embed_a : p.embed_v) + iB * 64, r.t, 64);
             gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, m == 0 ? mt::A1H : mt::V1H), lane);
             gemm<NS, 4, 4>(acc, fe, wblk<NS>(W, m == 0 ? mt::A1E : mt::V1E), lane);
             float (&lg)[2][4] = m == 0 ? la : lv;
@@ -253,7 +271,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
             mopoe_mix<NS == 1>(lsa, lsv, mixed, nullptr, nullptr);
             softmax_groups<KL, NS == 1>(mixed, q);
             store_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r);
-            sample_onehot<KL>(q, p.u_post_l + iA * CL, p.u_post_l + iB * CL, zs, lane);
+            if (STAGED) sample_onehot<KL>(q, stage + stg::U0 + r.g * 8, stage + stg::U0 + (r.g + 8) * 8, zs, lane);
+            else sample_onehot<KL>(q, p.u_post_l + iA * CL, p.u_post_l + iB * CL, zs, lane);
             store_c<2>(zs, p.feature + iA * F + 80, p.feature + iB * F + 80, r);
             to_afrag<NS, 1>(zlf, zs);
             float kl[2];
@@ -272,7 +291,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
             head_l2<NS>(acc, lg, bias + mt::B_HQ2, wblk<NS>(W, mt::HQ2), svA, svB, mts::HQ_HID, r, lane);
             softmax_groups<KH, NS == 1>(lg, q);
             store_c<2>(q, p.post_probs_h + iA * 16, p.post_probs_h + iB * 16, r);
-            sample_onehot<KH>(q, p.u_post_h + iA * CH, p.u_post_h + iB * CH, zs, lane);
+            if (STAGED) sample_onehot<KH>(q, stage + stg::U1 + r.g * 8, stage + stg::U1 + (r.g + 8) * 8, zs, lane);
+            else sample_onehot<KH>(q, p.u_post_h + iA * CH, p.u_post_h + iB * CH, zs, lane);
             store_c<2>(zs, p.feature + iA * F + 32, p.feature + iB * F + 32, r);
             to_afrag<NS, 1>(zhf, zs);
             float kl[2];
@@ -533,7 +553,9 @@ static cudaError_t launch(KernelT kernel, const ArgsT& args, int B, size_t smem,
 
 template <int NS, bool IMAGINE>
 static cudaError_t launch_mtrssm_fwd_k(const MtrssmFwdArgs& a, cudaStream_t s) {
-    const size_t smem = (size_t)NS * mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float);
+    // weights + biases (+ per-warp input staging, sized for the largest CTA of 4 warps)
+    const size_t smem = (size_t)NS * mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float) +
+                        (IMAGINE || NS != 1 ? 0 : 4 * 2 * stg::FLOATS * sizeof(float));
 #define COMMA_IMAGINE , IMAGINE
     MT_DISPATCH(mtrssm_fwd_kernel, COMMA_IMAGINE)
 #undef COMMA_IMAGINE
