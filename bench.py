@@ -354,6 +354,15 @@ def main() -> None:
         r3 = time_direct(small, 50, 10, 1)
         extras["default_batch8"] = {"B": 8, "T": T, "value": 8 * T * 50 / (r3["total_ms"] * 1e-3), "us_per_step": r3["total_ms"] / 50 * 1e3}
         del small
+        # the other batch sizes SURVEY.md 8(d) asks for, and cfg4 (long horizon); same dims, same kernels
+        extras["other_workloads"] = []
+        for name, b_, t_ in (("cfg2 B=256", 256, T), ("cfg2 B=4096", 4096, T), ("cfg4 B=256 T=512", 256, 512)):
+            w = DirectMtrssm(b_, t_, precision, device)
+            rr = time_direct(w, 10, 3, 1)
+            extras["other_workloads"].append({"workload": name, "B": b_, "T": t_, "value": b_ * t_ * 10 / (rr["total_ms"] * 1e-3),
+                                              "ms_per_step": rr["total_ms"] / 10,
+                                              "frac_of_hbm": STEP_BYTES_PER_BT * b_ * t_ / (rr["total_ms"] / 10 * 1e-3) / 1e9 / 6464.9})
+            del w
     if world > 1:
         import torch.distributed as dist
 

@@ -7,7 +7,16 @@
 //                       c[2],c[3] -> (row g+8, cols 2t, 2t+1)
 // Two adjacent C tiles re-pack, lane-locally (no shuffles, no shared memory), into one
 // m16n8k16 A operand k-tile, so a chain  GEMM -> activation -> GEMM  never leaves the register
-// file.  Weights are packed once per CTA into shared memory as ready-made B fragments
+// file.
+//
+// LOGICAL COLUMN MAPPING.  The assignment of a layer's neurons to MMA column positions is free (the
+// weight packer applies it on both the N and the K side), so it is chosen for memory coalescing: inside every
+// block of 16 logical columns (= a pair of C tiles 2j, 2j+1 = one A k-tile j)
+//     tile 2j  , position 2t+i  <->  logical column 16j + 4t + i        (i = 0,1)
+//     tile 2j+1, position 2t+i  <->  logical column 16j + 4t + 2 + i
+// i.e. lane t of a quad owns the FOUR CONSECUTIVE logical columns 16j+4t .. 16j+4t+3 of its row: every global /
+// record access is one 16-byte (8-byte for bf16) access per lane per 16-block, and categorical groups of
+// class size 2 or 4 are lane-local.  Weights are packed once per CTA into shared memory as ready-made B fragments
 // (`pack_weight`), so the inner loop is  LDS.64 + MMA.
 //
 // Precision policy NS (number of bf16 splits per operand):
@@ -123,6 +132,10 @@ __device__ __forceinline__ void gemm(float (&acc)[NT][4], const AFrag<NS, KT>& a
 //   TRANS == false:  B[k][n] = W[(n0+n)*ld + k0 + k]   (y = x W^T, forward; PyTorch [out,in] weight)
 //   TRANS == true :  B[k][n] = W[(n0+k)*ld + k0 + n]   (dx = dy W,  data gradient)
 // with zero padding outside k < kvalid / n < nvalid.  dst layout [split][kt][nt][lane] uint2.
+// logical column of MMA C/B column position q (0..7) of n-tile nt, and of A/B k position kp (0..15) of k-tile kt
+__host__ __device__ constexpr int lcol(int nt, int q) { return 16 * (nt >> 1) + 4 * (q >> 1) + 2 * (nt & 1) + (q & 1); }
+__host__ __device__ constexpr int lk(int kt, int kp) { return 16 * kt + 4 * ((kp & 7) >> 1) + 2 * (kp >> 3) + (kp & 1); }
+
 template <int NS, bool TRANS>
 __device__ __forceinline__ void pack_weight(uint2* __restrict__ dst, const float* __restrict__ W, int ld, int n0, int k0,
                                             int kvalid, int nvalid, int KT, int NT, int tid, int nthreads) {
@@ -131,11 +144,11 @@ __device__ __forceinline__ void pack_weight(uint2* __restrict__ dst, const float
         const int lane = idx & 31, tile = idx >> 5;
         const int nt = tile % NT, kt = tile / NT;
         const int g = lane >> 2, t = lane & 3;
-        const int n = nt * 8 + g;
+        const int n = lcol(nt, g);  // B fragment: column n-position = g
         float w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int k = kt * 16 + 2 * t + (j & 1) + ((j >> 1) << 3);
+            const int k = lk(kt, 2 * t + (j & 1) + ((j >> 1) << 3));  // B fragment: k-positions 2t, 2t+1, 2t+8, 2t+9
             float v = 0.f;
             if (k < kvalid && n < nvalid) v = TRANS ? W[(size_t)(n0 + k) * ld + k0 + n] : W[(size_t)(n0 + n) * ld + k0 + k];
             w[j] = v;
@@ -172,10 +185,12 @@ __device__ __forceinline__ Rows make_rows(int row0, int B, int lane) {
 
 template <int NT>
 __device__ __forceinline__ void init_bias(float (&acc)[NT][4], const float* __restrict__ bias, int t) {
+    static_assert(NT % 2 == 0, "activations come in 16-column blocks");
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        const float2 b = *reinterpret_cast<const float2*>(bias + nt * 8 + 2 * t);
-        acc[nt][0] = b.x, acc[nt][1] = b.y, acc[nt][2] = b.x, acc[nt][3] = b.y;
+    for (int j = 0; j < NT / 2; ++j) {
+        const float4 b = *reinterpret_cast<const float4*>(bias + 16 * j + 4 * t);
+        acc[2 * j][0] = b.x, acc[2 * j][1] = b.y, acc[2 * j][2] = b.x, acc[2 * j][3] = b.y;
+        acc[2 * j + 1][0] = b.z, acc[2 * j + 1][1] = b.w, acc[2 * j + 1][2] = b.z, acc[2 * j + 1][3] = b.w;
     }
 }
 
@@ -185,27 +200,30 @@ __device__ __forceinline__ void zero_c(float (&acc)[NT][4]) {
     for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 }
 
-// pA/pB: pointers to column 0 of this tile group in row A / row B
+// pA/pB: pointers to logical column 0 of this group of NT/2 16-column blocks in row A / row B (16-byte aligned)
 template <int NT>
 __device__ __forceinline__ void load_c(float (&c)[NT][4], const float* __restrict__ pA, const float* __restrict__ pB, int t) {
+    static_assert(NT % 2 == 0, "activations come in 16-column blocks");
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        const float2 a = *reinterpret_cast<const float2*>(pA + nt * 8 + 2 * t);
-        const float2 b = *reinterpret_cast<const float2*>(pB + nt * 8 + 2 * t);
-        c[nt][0] = a.x, c[nt][1] = a.y, c[nt][2] = b.x, c[nt][3] = b.y;
+    for (int j = 0; j < NT / 2; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(pA + 16 * j + 4 * t);
+        const float4 b = *reinterpret_cast<const float4*>(pB + 16 * j + 4 * t);
+        c[2 * j][0] = a.x, c[2 * j][1] = a.y, c[2 * j + 1][0] = a.z, c[2 * j + 1][1] = a.w;
+        c[2 * j][2] = b.x, c[2 * j][3] = b.y, c[2 * j + 1][2] = b.z, c[2 * j + 1][3] = b.w;
     }
 }
 
 template <int NT>
 __device__ __forceinline__ void store_c(const float (&c)[NT][4], float* __restrict__ pA, float* __restrict__ pB, const Rows& r) {
+    static_assert(NT % 2 == 0, "activations come in 16-column blocks");
 #ifdef RSSM_EXP_NO_STORES  // timing experiment only: keep a data dependency, skip the traffic
     if (c[0][0] == 1.2345e-30f) *pA = c[0][1];
     return;
 #endif
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        if (r.vA) *reinterpret_cast<float2*>(pA + nt * 8 + 2 * r.t) = make_float2(c[nt][0], c[nt][1]);
-        if (r.vB) *reinterpret_cast<float2*>(pB + nt * 8 + 2 * r.t) = make_float2(c[nt][2], c[nt][3]);
+    for (int j = 0; j < NT / 2; ++j) {
+        if (r.vA) *reinterpret_cast<float4*>(pA + 16 * j + 4 * r.t) = make_float4(c[2 * j][0], c[2 * j][1], c[2 * j + 1][0], c[2 * j + 1][1]);
+        if (r.vB) *reinterpret_cast<float4*>(pB + 16 * j + 4 * r.t) = make_float4(c[2 * j][2], c[2 * j][3], c[2 * j + 1][2], c[2 * j + 1][3]);
     }
 }
 
@@ -232,9 +250,13 @@ __device__ __forceinline__ void store_rec(const float (&c)[NT][4], __nv_bfloat16
     return;
 #endif
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        if (r.vA) *reinterpret_cast<uint32_t*>(pA + nt * 8 + 2 * r.t) = pack_bf16(c[nt][0], c[nt][1]);
-        if (r.vB) *reinterpret_cast<uint32_t*>(pB + nt * 8 + 2 * r.t) = pack_bf16(c[nt][2], c[nt][3]);
+    for (int j = 0; j < NT / 2; ++j) {
+        if (r.vA)
+            *reinterpret_cast<uint2*>(pA + 16 * j + 4 * r.t) =
+                make_uint2(pack_bf16(c[2 * j][0], c[2 * j][1]), pack_bf16(c[2 * j + 1][0], c[2 * j + 1][1]));
+        if (r.vB)
+            *reinterpret_cast<uint2*>(pB + 16 * j + 4 * r.t) =
+                make_uint2(pack_bf16(c[2 * j][2], c[2 * j][3]), pack_bf16(c[2 * j + 1][2], c[2 * j + 1][3]));
     }
 }
 template <int NT>
@@ -245,10 +267,13 @@ template <int NT>
 __device__ __forceinline__ void load_rec(float (&c)[NT][4], const __nv_bfloat16* __restrict__ pA, const __nv_bfloat16* __restrict__ pB,
                                          int t) {
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(pA + nt * 8 + 2 * t);
-        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(pB + nt * 8 + 2 * t);
-        c[nt][0] = __low2float(a), c[nt][1] = __high2float(a), c[nt][2] = __low2float(b), c[nt][3] = __high2float(b);
+    for (int j = 0; j < NT / 2; ++j) {
+        const uint2 a = *reinterpret_cast<const uint2*>(pA + 16 * j + 4 * t);
+        const uint2 b = *reinterpret_cast<const uint2*>(pB + 16 * j + 4 * t);
+        const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162*>(&a.x), a1 = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
+        const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&b.x), b1 = *reinterpret_cast<const __nv_bfloat162*>(&b.y);
+        c[2 * j][0] = __low2float(a0), c[2 * j][1] = __high2float(a0), c[2 * j + 1][0] = __low2float(a1), c[2 * j + 1][1] = __high2float(a1);
+        c[2 * j][2] = __low2float(b0), c[2 * j][3] = __high2float(b0), c[2 * j + 1][2] = __low2float(b1), c[2 * j + 1][3] = __high2float(b1);
     }
 }
 
@@ -265,38 +290,36 @@ __device__ __forceinline__ void prefetch_bulk_l2(const void* p, uint32_t bytes) 
 #endif
 }
 
-// store only columns < nvalid (e.g. the 6 action columns of an 8-wide tile)
-__device__ __forceinline__ void store_c_partial(const float (&c)[4], float* __restrict__ pA, float* __restrict__ pB, const Rows& r,
+// store the logical columns < nvalid (nvalid even, <= 16) of ONE 16-column block, e.g. the action gradient;
+// rows need only be 8-byte aligned
+__device__ __forceinline__ void store_c_partial(const float (&c)[2][4], float* __restrict__ pA, float* __restrict__ pB, const Rows& r,
                                                 int nvalid) {
-    const int c0 = 2 * r.t;
+    const int c0 = 4 * r.t;
     if (c0 + 1 < nvalid) {
-        if (r.vA) *reinterpret_cast<float2*>(pA + c0) = make_float2(c[0], c[1]);
-        if (r.vB) *reinterpret_cast<float2*>(pB + c0) = make_float2(c[2], c[3]);
-    } else if (c0 < nvalid) {
-        if (r.vA) pA[c0] = c[0];
-        if (r.vB) pB[c0] = c[2];
+        if (r.vA) *reinterpret_cast<float2*>(pA + c0) = make_float2(c[0][0], c[0][1]);
+        if (r.vB) *reinterpret_cast<float2*>(pB + c0) = make_float2(c[0][2], c[0][3]);
+    }
+    if (c0 + 3 < nvalid) {
+        if (r.vA) *reinterpret_cast<float2*>(pA + c0 + 2) = make_float2(c[1][0], c[1][1]);
+        if (r.vB) *reinterpret_cast<float2*>(pB + c0 + 2) = make_float2(c[1][2], c[1][3]);
     }
 }
 
-// A operand straight from global fp32 rows; columns >= kvalid read as zero
+// A operand straight from global fp32 rows (8-byte aligned); logical columns >= kvalid (even) read as zero
 template <int NS, int KT>
 __device__ __forceinline__ void load_a_global(AFrag<NS, KT>& a, const float* __restrict__ pA, const float* __restrict__ pB, int t,
                                               int kvalid) {
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt) {
-        float c0[4], c1[4];
-        const int k0 = kt * 16 + 2 * t, k1 = k0 + 8;
+        float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+        const int k0 = kt * 16 + 4 * t;
         if (k0 + 1 < kvalid) {
             const float2 x = *reinterpret_cast<const float2*>(pA + k0), y = *reinterpret_cast<const float2*>(pB + k0);
             c0[0] = x.x, c0[1] = x.y, c0[2] = y.x, c0[3] = y.y;
-        } else {
-            c0[0] = k0 < kvalid ? pA[k0] : 0.f, c0[1] = 0.f, c0[2] = k0 < kvalid ? pB[k0] : 0.f, c0[3] = 0.f;
         }
-        if (k1 + 1 < kvalid) {
-            const float2 x = *reinterpret_cast<const float2*>(pA + k1), y = *reinterpret_cast<const float2*>(pB + k1);
+        if (k0 + 3 < kvalid) {
+            const float2 x = *reinterpret_cast<const float2*>(pA + k0 + 2), y = *reinterpret_cast<const float2*>(pB + k0 + 2);
             c1[0] = x.x, c1[1] = x.y, c1[2] = y.x, c1[3] = y.y;
-        } else {
-            c1[0] = k1 < kvalid ? pA[k1] : 0.f, c1[1] = 0.f, c1[2] = k1 < kvalid ? pB[k1] : 0.f, c1[3] = 0.f;
         }
         set_ktile<NS, KT>(a, kt, c0, c1);
     }
@@ -306,8 +329,8 @@ __device__ __forceinline__ void load_a_global(AFrag<NS, KT>& a, const float* __r
 // per-warp input staging (forward kernels): the next step's inputs of the warp's 16 rows are pulled into shared
 // memory with cp.async while the current step computes, so the step never waits on a global load.
 // Stage layout (floats): EA[16][64] | EV[16][64] | ACT[16][8] | U0[16][8] | U1[16][8].  The two embedding tiles use a
-// 16-byte-chunk XOR swizzle (chunk ^ 2*(row & 3)) so that the mma A-fragment read pattern (lane (g,t) reads 8 bytes
-// at column 16kt + 2t of row g) is bank-conflict free without padding.
+// 16-byte-chunk XOR swizzle (chunk ^ 4*(row & 1)) so that the mma A-fragment read pattern (lane (g,t) reads the 16 bytes
+// at logical column 16kt + 4t of row g) is bank-conflict free without padding.
 // ------------------------------------------------------------------------------------------
 namespace stg {
 constexpr int EA = 0, EV = 1024, ACT = 2048, U0 = 2176, U1 = 2304, FLOATS = 2432;  // 9728 bytes per stage
@@ -335,7 +358,7 @@ __device__ __forceinline__ void stage_inputs(float* stage, const float* __restri
         const int rl = (lane >> 4) + 2 * i;
         const int row = min(row0 + rl, B - 1);
         const size_t src = ((size_t)row * T + t) * 64 + chunk * 4;
-        const int dst = rl * 64 + ((chunk ^ (2 * (rl & 3))) << 2);
+        const int dst = rl * 64 + ((chunk ^ (4 * (rl & 1))) << 2);
         if (ea != nullptr) cp_async16(stage + stg::EA + dst, ea + src);
         if (ev != nullptr) cp_async16(stage + stg::EV + dst, ev + src);
     }
@@ -376,16 +399,14 @@ __device__ __forceinline__ void stage_inputs(float* stage, const float* __restri
 // A operand (KT = 4, 64 columns) from a swizzled staged embedding tile
 template <int NS>
 __device__ __forceinline__ void load_a_staged64(AFrag<NS, 4>& a, const float* tile, int g, int t) {
-    const int sw = 2 * (g & 3);  // same for row g and row g + 8
+    const int sw = 4 * (g & 1);  // same for row g and row g + 8
     const float* pA = tile + g * 64;
     const float* pB = tile + (g + 8) * 64;
-    const int in = (2 * t) & 3;
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt) {
-        const int c0 = (((4 * kt + (t >> 1)) ^ sw) << 2) + in, c1 = (((4 * kt + (t >> 1) + 2) ^ sw) << 2) + in;
-        const float2 x0 = *reinterpret_cast<const float2*>(pA + c0), y0 = *reinterpret_cast<const float2*>(pB + c0);
-        const float2 x1 = *reinterpret_cast<const float2*>(pA + c1), y1 = *reinterpret_cast<const float2*>(pB + c1);
-        const float q0[4] = {x0.x, x0.y, y0.x, y0.y}, q1[4] = {x1.x, x1.y, y1.x, y1.y};
+        const int c = ((4 * kt + t) ^ sw) << 2;
+        const float4 x = *reinterpret_cast<const float4*>(pA + c), y = *reinterpret_cast<const float4*>(pB + c);
+        const float q0[4] = {x.x, x.y, y.x, y.y}, q1[4] = {x.z, x.w, y.z, y.w};
         set_ktile<NS, 4>(a, kt, q0, q1);
     }
 }
@@ -393,8 +414,12 @@ __device__ __forceinline__ void load_a_staged64(AFrag<NS, 4>& a, const float* ti
 // A operand (KT = 1) from the staged action rows ACT[16][8] (columns >= A are zero)
 template <int NS>
 __device__ __forceinline__ void load_a_staged_act(AFrag<NS, 1>& a, const float* act, int g, int t) {
-    const float2 x = *reinterpret_cast<const float2*>(act + g * 8 + 2 * t), y = *reinterpret_cast<const float2*>(act + (g + 8) * 8 + 2 * t);
-    const float q0[4] = {x.x, x.y, y.x, y.y}, q1[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+    if (t < 2) {
+        x = *reinterpret_cast<const float4*>(act + g * 8 + 4 * t);
+        y = *reinterpret_cast<const float4*>(act + (g + 8) * 8 + 4 * t);
+    }
+    const float q0[4] = {x.x, x.y, y.x, y.y}, q1[4] = {x.z, x.w, y.z, y.w};
     set_ktile<NS, 1>(a, 0, q0, q1);
 }
 
@@ -453,24 +478,22 @@ __device__ __forceinline__ void map_c(float (&c)[NT][4], F f) {
 // ------------------------------------------------------------------------------------------
 constexpr unsigned FULL = 0xffffffffu;
 
-// reduce a per-(tile,row) in-lane value over the K-column group it belongs to; result in v[0], v[1]
+// reduce a per-(tile,row) in-lane value over the K-column group it belongs to; result in v[0], v[1].
+// A lane owns logical columns 4t..4t+3 of the 16: tile 0 holds (4t, 4t+1), tile 1 holds (4t+2, 4t+3).
 template <int K, bool MAX>
 __device__ __forceinline__ void group_reduce(float (&v)[2]) {
     static_assert(K == 2 || K == 4 || K == 8 || K == 16, "class_size must be 2, 4, 8 or 16");
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-        if constexpr (K >= 4) {
-            const float o = __shfl_xor_sync(FULL, v[nt], 1);
-            v[nt] = MAX ? fmaxf(v[nt], o) : v[nt] + o;
-        }
-        if constexpr (K >= 8) {
-            const float o = __shfl_xor_sync(FULL, v[nt], 2);
-            v[nt] = MAX ? fmaxf(v[nt], o) : v[nt] + o;
-        }
-    }
-    if constexpr (K == 16) {
+    if constexpr (K >= 4) {
         const float m = MAX ? fmaxf(v[0], v[1]) : v[0] + v[1];
         v[0] = v[1] = m;
+    }
+    if constexpr (K >= 8) {
+        const float o = __shfl_xor_sync(FULL, v[0], 1);
+        v[0] = v[1] = MAX ? fmaxf(v[0], o) : v[0] + o;
+    }
+    if constexpr (K == 16) {
+        const float o = __shfl_xor_sync(FULL, v[0], 2);
+        v[0] = v[1] = MAX ? fmaxf(v[0], o) : v[0] + o;
     }
 }
 
@@ -548,34 +571,37 @@ __device__ __forceinline__ void sample_onehot(const float (&p)[2][4], const floa
                                               float (&z)[2][4], int lane) {
     const int t = lane & 3, qbase = lane & ~3;
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
+    for (int h = 0; h < 2; ++h) {
+        const float* u = h == 0 ? uA : uB;
+        const float mine[4] = {p[0][2 * h], p[0][2 * h + 1], p[1][2 * h], p[1][2 * h + 1]};  // logical columns 4t .. 4t+3
+        int hit[4];  // hit[i]: my i-th column is the drawn class of its group
+        if constexpr (K == 2) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            // group of my two columns (cols 8nt+2t, +1), and my first column's position inside it
-            int grp, pos;
-            if constexpr (K == 2) grp = nt * 4 + t, pos = 0;
-            if constexpr (K == 4) grp = nt * 2 + (t >> 1), pos = 2 * (t & 1);
-            if constexpr (K == 8) grp = nt, pos = 2 * t;
-            if constexpr (K == 16) grp = 0, pos = 8 * nt + 2 * t;
-            const float u = (h == 0 ? uA : uB)[grp];
+            for (int half = 0; half < 2; ++half) {
+                const int idx = mine[2 * half] <= u[2 * t + half] ? 1 : 0;
+                hit[2 * half] = idx == 0, hit[2 * half + 1] = idx == 1;
+            }
+        } else {
+            constexpr int LANES = K / 4;  // quad lanes per group
+            const int first = t & ~(LANES - 1), pos = 4 * (t & (LANES - 1));
+            const float uu = u[t / LANES];
             float cdf = 0.f;
             int idx = 0;
 #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                // owner of class k of my group: tile nt', quad position t', slot j
-                int src_nt, src_t;
-                if constexpr (K == 2) src_nt = nt, src_t = t;
-                if constexpr (K == 4) src_nt = nt, src_t = 2 * (t >> 1) + (k >> 1);
-                if constexpr (K == 8) src_nt = nt, src_t = k >> 1;
-                if constexpr (K == 16) src_nt = k >> 3, src_t = (k & 7) >> 1;
-                float pk = p[src_nt][2 * h + (k & 1)];
-                if constexpr (K > 2) pk = __shfl_sync(FULL, pk, qbase + src_t);
-                cdf += pk;
-                if (k < K - 1) idx += (cdf <= u) ? 1 : 0;
+            for (int s = 0; s < LANES; ++s) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float pk = mine[i];
+                    if constexpr (LANES > 1) pk = __shfl_sync(FULL, pk, qbase + first + s);
+                    cdf += pk;
+                    if (4 * s + i < K - 1) idx += (cdf <= uu) ? 1 : 0;
+                }
             }
-            z[nt][2 * h] = (idx == pos) ? 1.f : 0.f;
-            z[nt][2 * h + 1] = (idx == pos + 1) ? 1.f : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) hit[i] = idx == pos + i;
         }
+        z[0][2 * h] = hit[0] ? 1.f : 0.f, z[0][2 * h + 1] = hit[1] ? 1.f : 0.f;
+        z[1][2 * h] = hit[2] ? 1.f : 0.f, z[1][2 * h + 1] = hit[3] ? 1.f : 0.f;
     }
 }
 

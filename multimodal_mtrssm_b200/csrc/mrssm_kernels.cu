@@ -59,8 +59,8 @@ constexpr int T_HH_Z = T_HH_R + 8;
 constexpr int T_HH_N = T_HH_Z + 8;
 constexpr int T_ASP2 = T_HH_N + 8;   // d x2 -> d asp hidden                         KT2 NT4
 constexpr int T_ASP1Z = T_ASP2 + 8;  // dpre asp1 -> d z_prev (16)                   KT2 NT2
-constexpr int T_ASP1A = T_ASP1Z + 4; // dpre asp1 -> d action (8)                    KT2 NT1
-constexpr int BWD_TILES = T_ASP1A + 2;  // 130
+constexpr int T_ASP1A = T_ASP1Z + 4; // dpre asp1 -> d action (one 16-block)          KT2 NT2
+constexpr int BWD_TILES = T_ASP1A + 4;  // 132
 }  // namespace mr
 
 // saved-for-backward record, floats per (b,t)   (kernels.h: MRSSM_SAVED_FLOATS = 320)
@@ -135,6 +135,14 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
     constexpr int F = 48;
     using RT = typename Rec<NS>::T;
     RT* saved = reinterpret_cast<RT*>(p.saved);
+    // per-warp double-buffered input staging (frag.cuh, namespace stg); bf16 path only (smem budget)
+    constexpr bool STAGED = !IMAGINE && NS == 1;
+    float* stage_base = bias + mr::FWD_BIAS + warp * 2 * stg::FLOATS;
+    if (STAGED) {
+        for (int i = lane; i < 2 * stg::FLOATS; i += 32) stage_base[i] = 0.f;  // action pad columns stay zero
+        __syncwarp();
+        stage_inputs(stage_base, p.embed_a, p.embed_v, p.actions, A, p.u_post, C, nullptr, 0, row0, p.B, T, 0, lane);
+    }
 
     // carried state: h (fp32 C tiles + A operand), z_prev (A operand)
     float h[4][4];
@@ -152,6 +160,14 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
         RT* svA = saved ? saved + iA * MRSSM_SAVED_FLOATS : nullptr;
         RT* svB = saved ? saved + iB * MRSSM_SAVED_FLOATS : nullptr;
+        const float* stage = stage_base + (t & 1) * stg::FLOATS;
+        if (STAGED) {
+            cp_async_wait_all();  // this step's inputs have landed ...
+            __syncwarp();         // ... for every lane, and every lane is done reading the other stage
+            if (t + 1 < T)
+                stage_inputs(stage_base + ((t + 1) & 1) * stg::FLOATS, p.embed_a, p.embed_v, p.actions, A, p.u_post, C, nullptr, 0, row0,
+                             p.B, T, t + 1, lane);
+        }
 
         // ---- action_state_projector (networks.py:168-169) ----------------------------------------
         AFrag<NS, 2> fx;
@@ -159,7 +175,8 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             float acc[4][4];
             init_bias<4>(acc, bias + mr::B_ASP1, r.t);
             AFrag<NS, 1> fa;
-            load_a_global<NS, 1>(fa, p.actions + iA * A, p.actions + iB * A, r.t, A);
+            if (STAGED) load_a_staged_act<NS>(fa, stage + stg::ACT, r.g, r.t);
+            else load_a_global<NS, 1>(fa, p.actions + iA * A, p.actions + iB * A, r.t, A);
             gemm<NS, 1, 4>(acc, zf, wblock<NS>(W, mr::ASP1Z), lane);
             gemm<NS, 1, 4>(acc, fa, wblock<NS>(W, mr::ASP1A), lane);
             map_c<4>(acc, EluOp<NS == 1>{});
@@ -236,7 +253,8 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             float acc[4][4];
             init_bias<4>(acc, bias + (m == 0 ? mr::B_A1 : mr::B_V1), r.t);
             AFrag<NS, 4> fe;
-            load_a_global<NS, 4>(fe, emb + iA * 64, emb + iB * 64, r.t, 64);
+            if (STAGED) load_a_staged64<NS>(fe, stage + (m == 0 ? stg::EA : stg::EV), r.g, r.t);
+            else load_a_global<NS, 4>(fe, emb + iA * 64, emb + iB * 64, r.t, 64);
             gemm<NS, 2, 4>(acc, hf, wblock<NS>(W, m == 0 ? mr::A1H : mr::V1H), lane);
             gemm<NS, 4, 4>(acc, fe, wblock<NS>(W, m == 0 ? mr::A1E : mr::V1E), lane);
             map_c<4>(acc, EluOp<NS == 1>{});
@@ -256,7 +274,8 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             mopoe_mix<NS == 1>(lsa, lsv, mixed, nullptr, nullptr);
             softmax_groups<K, NS == 1>(mixed, q);
             store_c<2>(q, p.post_probs + iA * 16, p.post_probs + iB * 16, r);
-            sample_onehot<K>(q, p.u_post + iA * C, p.u_post + iB * C, zs, lane);
+            if (STAGED) sample_onehot<K>(q, stage + stg::U0 + r.g * 8, stage + stg::U0 + (r.g + 8) * 8, zs, lane);
+            else sample_onehot<K>(q, p.u_post + iA * C, p.u_post + iB * C, zs, lane);
             store_c<2>(zs, p.feature + iA * F + 32, p.feature + iB * F + 32, r);
             to_afrag<NS, 1>(zf, zs);  // prev_state = mixed_posterior (mopoe_mrssm/core.py:256)
             float kl[2];
@@ -298,7 +317,7 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
         pack_weight<NS, true>(wblock<NS>(W, T_HH_N), p.w.w_hh, 32, 64, 0, 32, 32, 2, 4, tid, nthr);
         pack_weight<NS, true>(wblock<NS>(W, T_ASP2), p.w.asp_w2, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
         pack_weight<NS, true>(wblock<NS>(W, T_ASP1Z), p.w.asp_w1, ldasp, 0, A, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_ASP1A), p.w.asp_w1, ldasp, 0, 0, 32, A, 2, 1, tid, nthr);
+        pack_weight<NS, true>(wblock<NS>(W, T_ASP1A), p.w.asp_w1, ldasp, 0, 0, 32, A, 2, 2, tid, nthr);
     }
     __syncthreads();
 
@@ -493,10 +512,10 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
             zero_c<2>(dz);
             gemm<NS, 2, 2>(dz, f1, wblock<NS>(W, mr::T_ASP1Z), lane);
             if (p.d_actions != nullptr) {
-                float da[1][4];
-                zero_c<1>(da);
-                gemm<NS, 2, 1>(da, f1, wblock<NS>(W, mr::T_ASP1A), lane);
-                store_c_partial(da[0], p.d_actions + iA * A, p.d_actions + iB * A, r, A);
+                float da[2][4];
+                zero_c<2>(da);
+                gemm<NS, 2, 2>(da, f1, wblock<NS>(W, mr::T_ASP1A), lane);
+                store_c_partial(da, p.d_actions + iA * A, p.d_actions + iB * A, r, A);
             }
         }
     }
@@ -526,7 +545,8 @@ static cudaError_t launch(KernelT kernel, const ArgsT& args, int B, size_t smem,
 
 template <int NS, bool IMAGINE>
 static cudaError_t launch_mrssm_fwd_k(const MrssmFwdArgs& a, cudaStream_t s) {
-    const size_t smem = (size_t)NS * mr::FWD_TILES * 32 * sizeof(uint2) + mr::FWD_BIAS * sizeof(float);
+    const size_t smem = (size_t)NS * mr::FWD_TILES * 32 * sizeof(uint2) + mr::FWD_BIAS * sizeof(float) +
+                        (IMAGINE || NS != 1 ? 0 : 4 * 2 * stg::FLOATS * sizeof(float));
     switch (a.K) {
         case 2: return launch(mrssm_fwd_kernel<NS, 2, IMAGINE>, a, a.B, smem, s);
         case 4: return launch(mrssm_fwd_kernel<NS, 4, IMAGINE>, a, a.B, smem, s);

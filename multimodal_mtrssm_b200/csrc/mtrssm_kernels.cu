@@ -45,8 +45,8 @@ constexpr int T_A1H = 20, T_V1H = 28, T_LP1 = 36, T_HP1 = 44, T_HQ1L = 52, T_HQ1
 constexpr int T_A1E = 68, T_V1E = 84;                                                       // KT2 NT8
 constexpr int T_L_D2H = 100, T_H_D2H = 108;                                                 // KT2 NT4
 constexpr int T_L_IN_ZL = 116, T_L_IN_ZH = 120, T_H_IN = 124;                               // KT2 NT2
-constexpr int T_L_IN_A = 128;                                                               // KT2 NT1
-constexpr int BWD_TILES = 130;
+constexpr int T_L_IN_A = 128;                                                               // KT2 NT2 (one 16-block)
+constexpr int BWD_TILES = 132;
 }  // namespace mt
 
 namespace mts {  // saved record (MTRSSM_SAVED_FLOATS = 192)
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
         pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZL), p.w.l_in_w, ldin, 0, A, 32, 16, 2, 2, tid, nthr);
         pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 32, 16, 2, 2, tid, nthr);
         pack_weight<NS, true>(wblk<NS>(W, T_H_IN), p.w.h_in_w, 16, 0, 0, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_A), p.w.l_in_w, ldin, 0, 0, 32, A, 2, 1, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_A), p.w.l_in_w, ldin, 0, 0, 32, A, 2, 2, tid, nthr);
     }
     __syncthreads();
 
@@ -501,10 +501,10 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
             gemm<NS, 2, 2>(dzh, fl, wblk<NS>(W, mt::T_L_IN_ZH), lane);
             gemm<NS, 2, 2>(dzh, fh, wblk<NS>(W, mt::T_H_IN), lane);
             if (p.d_actions != nullptr) {
-                float da[1][4];
-                zero_c<1>(da);
-                gemm<NS, 2, 1>(da, fl, wblk<NS>(W, mt::T_L_IN_A), lane);
-                store_c_partial(da[0], p.d_actions + iA * A, p.d_actions + iB * A, r, A);
+                float da[2][4];
+                zero_c<2>(da);
+                gemm<NS, 2, 2>(da, fl, wblk<NS>(W, mt::T_L_IN_A), lane);
+                store_c_partial(da, p.d_actions + iA * A, p.d_actions + iB * A, r, A);
             }
         }
     }
