@@ -344,6 +344,8 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>  // wait until at most N of the most recently committed groups are still pending
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Issue the copies of step `t` for the warp tile starting at row0 into `stage`.
 //   ea/ev: [B,T,64] fp32;  act: [B,T,A] fp32 (A even, <= 8);  u0/u1: [B,T,n0] / [B,T,n1] fp32 with n0, n1 in {1,2,4,8}

@@ -309,19 +309,105 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
 // ================================================================================================
 // backward
 // ================================================================================================
-// d logits (16) -> through W2^T -> * ELU'(hidden) -> dpre1 (stored) ; returns dpre1 as A operand
+// ---- per-warp staging of the backward kernel's per-step inputs (bf16 path) ---------------------------------------
+// Single-buffered "consume early, refill at once": each buffer is read by step t and, right after its last read,
+// re-filled with cp.async for step t-1, which then has most of a step to land.  Rows are swizzled at 16-byte chunk
+// granularity so the fragment-pattern reads are bank-conflict free.  Layout (32-bit words per warp):
+//   DF [16][96]  d_feature            | PR [16][64] post_h | post_l | prior_h | prior_l
+//   SV [16][96]  saved record (bf16)  | FT [16][64] deter_h | deter_l
+namespace bst {
+constexpr int DF = 0, PR = 1536, SV = 2560, FT = 4096, WORDS = 5120;  // 20480 bytes per warp
+}
+
+__device__ __forceinline__ int sw32(int chunk, int row) { return chunk ^ (4 * (row & 1)); }   // fp32 rows, float4 reads
+__device__ __forceinline__ int sw16(int chunk, int row) { return chunk ^ (2 * (row & 3)); }   // bf16 rows, 8-byte reads
+
+__device__ __forceinline__ size_t stage_row_index(int row0, int rl, int B, int T, int t) {
+    return (size_t)min(row0 + rl, B - 1) * T + t;
+}
+
+// d_feature + the four probability tensors of step t (one cp.async group)
+__device__ __forceinline__ void bstage_dfp(float* st, const MtrssmBwdArgs& p, int row0, int t, int lane) {
+    if (t >= 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {  // 16 rows x 24 chunks
+            const int i = lane + 32 * k, rl = i / 24, c = i - rl * 24;
+            cp_async16(st + bst::DF + rl * 96 + 4 * sw32(c, rl), p.d_feature + stage_row_index(row0, rl, p.B, p.T, t) * 96 + 4 * c);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // 16 rows x (4 tensors x 4 chunks)
+            const int i = lane + 32 * k, rl = i >> 4, c = i & 15, which = c >> 2;
+            const float* src = which == 0 ? p.post_probs_h : which == 1 ? p.post_probs_l : which == 2 ? p.prior_probs_h : p.prior_probs_l;
+            cp_async16(st + bst::PR + rl * 64 + 4 * sw32(c, rl), src + stage_row_index(row0, rl, p.B, p.T, t) * 16 + 4 * (c & 3));
+        }
+    }
+    cp_async_commit();
+}
+
+// the saved record (bf16, 384 bytes per row) of step t
+__device__ __forceinline__ void bstage_sv(float* st, const __nv_bfloat16* saved, int row0, int B, int T, int t, int lane) {
+    if (t >= 0) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {  // 16 rows x 24 chunks
+            const int i = lane + 32 * k, rl = i / 24, c = i - rl * 24;
+            cp_async16(st + bst::SV + rl * 96 + 4 * sw16(c, rl), saved + stage_row_index(row0, rl, B, T, t) * MTRSSM_SAVED_FLOATS + 8 * c);
+        }
+    }
+    cp_async_commit();
+}
+
+// deter_h (feature[0:32]) and deter_l (feature[48:80]) of step t
+__device__ __forceinline__ void bstage_ft(float* st, const float* feature, int row0, int B, int T, int t, int lane) {
+    if (t >= 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // 16 rows x 16 chunks
+            const int i = lane + 32 * k, rl = i >> 4, c = i & 15;
+            cp_async16(st + bst::FT + rl * 64 + 4 * sw32(c, rl), feature + stage_row_index(row0, rl, B, T, t) * 96 + (c < 8 ? 4 * c : 48 + 4 * (c - 8)));
+        }
+    }
+    cp_async_commit();
+}
+
+// NT tiles starting at logical column col0 of a staged fp32 buffer with `stride` words per row
+template <int NT>
+__device__ __forceinline__ void load_staged(float (&c)[NT][4], const float* buf, int stride, int col0, int g, int t) {
+#pragma unroll
+    for (int j = 0; j < NT / 2; ++j) {
+        const int ch = sw32(col0 / 4 + 4 * j + t, g);
+        const float4 a = *reinterpret_cast<const float4*>(buf + g * stride + 4 * ch);
+        const float4 b = *reinterpret_cast<const float4*>(buf + (g + 8) * stride + 4 * ch);
+        c[2 * j][0] = a.x, c[2 * j][1] = a.y, c[2 * j + 1][0] = a.z, c[2 * j + 1][1] = a.w;
+        c[2 * j][2] = b.x, c[2 * j][3] = b.y, c[2 * j + 1][2] = b.z, c[2 * j + 1][3] = b.w;
+    }
+}
+
+// NT tiles starting at record element `off` of the staged bf16 saved rows
+template <int NT>
+__device__ __forceinline__ void load_staged_rec(float (&c)[NT][4], const float* buf, int off, int g, int t) {
+#pragma unroll
+    for (int j = 0; j < NT / 2; ++j) {
+        const int e = off + 16 * j + 4 * t;                 // bf16 element index in the row
+        const int w = 4 * sw16(e >> 3, g) + ((e >> 1) & 3);  // 32-bit word: swizzled 16-byte chunk + offset inside it
+        const uint2 a = *reinterpret_cast<const uint2*>(buf + g * 96 + w), b = *reinterpret_cast<const uint2*>(buf + (g + 8) * 96 + w);
+        const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162*>(&a.x), a1 = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
+        const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&b.x), b1 = *reinterpret_cast<const __nv_bfloat162*>(&b.y);
+        c[2 * j][0] = __low2float(a0), c[2 * j][1] = __high2float(a0), c[2 * j + 1][0] = __low2float(a1), c[2 * j + 1][1] = __high2float(a1);
+        c[2 * j][2] = __low2float(b0), c[2 * j][3] = __high2float(b0), c[2 * j + 1][2] = __low2float(b1), c[2 * j + 1][3] = __high2float(b1);
+    }
+}
+
+// d logits (16) -> through W2^T -> * ELU'(hidden) -> dpre1 (stored) ; returns dpre1 as A operand.
+// `hid` = the head's saved post-ELU hidden.
 template <int NS>
-__device__ __forceinline__ void head_bwd(const float (&dlogit)[2][4], const uint2* w2t, const typename Rec<NS>::T* svA,
-                                         const typename Rec<NS>::T* svB, int sv_off, typename Rec<NS>::T* dpA,
+__device__ __forceinline__ void head_bwd(const float (&dlogit)[2][4], const uint2* w2t, const float (&hid)[4][4], typename Rec<NS>::T* dpA,
                                          typename Rec<NS>::T* dpB, int dp_logit_off, int dp1_off, AFrag<NS, 2>& f1, const Rows& r,
                                          int lane) {
     store_rec<2>(dlogit, dpA + dp_logit_off, dpB + dp_logit_off, r);
     AFrag<NS, 1> fl;
     to_afrag<NS, 1>(fl, dlogit);
-    float dhid[4][4], hid[4][4];
+    float dhid[4][4];
     zero_c<4>(dhid);
     gemm<NS, 1, 4>(dhid, fl, w2t, lane);
-    load_rec<4>(hid, svA + sv_off, svB + sv_off, r.t);
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -382,6 +468,14 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
     using RT = typename Rec<NS>::T;
     const RT* saved = reinterpret_cast<const RT*>(p.saved);
     RT* dpre = reinterpret_cast<RT*>(p.dpre);
+    // per-warp staging of this kernel's per-step inputs (bf16 path; see namespace bst)
+    constexpr bool STAGED = NS == 1;
+    float* st = reinterpret_cast<float*>(W + (size_t)NS * mt::BWD_TILES * 32) + warp * bst::WORDS;
+    if constexpr (STAGED) {  // cp.async groups in flight, oldest first: DFP(t), SV(t), FT(t)
+        bstage_dfp(st, p, row0, T - 1, lane);
+        bstage_sv(st, reinterpret_cast<const __nv_bfloat16*>(p.saved), row0, p.B, T, T - 1, lane);
+        bstage_ft(st, p.feature, row0, p.B, T, T - 1, lane);
+    }
 
     // carried gradients (w.r.t. the state handed from step t to step t+1)
     float ddl[4][4], ddh[4][4], dul[4][4], duh[4][4], dzl[2][4], dzh[2][4];
@@ -394,16 +488,52 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
         RT* dpA = dpre + iA * MTRSSM_DPRE_FLOATS;
         RT* dpB = dpre + iB * MTRSSM_DPRE_FLOATS;
 
-        add_global<4>(ddh, p.d_feature, iA * F, iB * F, r.t);
-        add_global<2>(dzh, p.d_feature, iA * F + 32, iB * F + 32, r.t);  // straight-through: d stoch -> d probs
-        add_global<4>(ddl, p.d_feature, iA * F + 48, iB * F + 48, r.t);
-        add_global<2>(dzl, p.d_feature, iA * F + 80, iB * F + 80, r.t);
+        float hid[4][4];  // a head's saved hidden, fetched from the staged record or from global memory
+        auto load_hid = [&](int off) {
+            if constexpr (STAGED) load_staged_rec<4>(hid, st + bst::SV, off, r.g, r.t);
+            else load_rec<4>(hid, svA + off, svB + off, r.t);
+        };
+        if constexpr (STAGED) {
+            cp_async_wait<1>();  // DFP(t) and SV(t) have landed (FT(t) may still be in flight)
+            __syncwarp();
+            float g4[4][4], g2[2][4];
+            load_staged<4>(g4, st + bst::DF, 96, 0, r.g, r.t);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ddh[nt][j] += g4[nt][j];
+            load_staged<2>(g2, st + bst::DF, 96, 32, r.g, r.t);  // straight-through: d stoch -> d probs
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dzh[nt][j] += g2[nt][j];
+            load_staged<4>(g4, st + bst::DF, 96, 48, r.g, r.t);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ddl[nt][j] += g4[nt][j];
+            load_staged<2>(g2, st + bst::DF, 96, 80, r.g, r.t);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dzl[nt][j] += g2[nt][j];
+        } else {
+            add_global<4>(ddh, p.d_feature, iA * F, iB * F, r.t);
+            add_global<2>(dzh, p.d_feature, iA * F + 32, iB * F + 32, r.t);  // straight-through: d stoch -> d probs
+            add_global<4>(ddl, p.d_feature, iA * F + 48, iB * F + 48, r.t);
+            add_global<2>(dzl, p.d_feature, iA * F + 80, iB * F + 80, r.t);
+        }
 
         // ---- higher layer: posterior + prior heads ------------------------------------------------------
         {
             float q[2][4], pp[2][4], dpp[2][4];
-            load_c<2>(q, p.post_probs_h + iA * 16, p.post_probs_h + iB * 16, r.t);
-            load_c<2>(pp, p.prior_probs_h + iA * 16, p.prior_probs_h + iB * 16, r.t);
+            if constexpr (STAGED) {
+                load_staged<2>(q, st + bst::PR, 64, 0, r.g, r.t);
+                load_staged<2>(pp, st + bst::PR, 64, 32, r.g, r.t);
+            } else {
+                load_c<2>(q, p.post_probs_h + iA * 16, p.post_probs_h + iB * 16, r.t);
+                load_c<2>(pp, p.prior_probs_h + iA * 16, p.prior_probs_h + iB * 16, r.t);
+            }
             add_global<2>(dzh, p.d_post_probs_h, iA * 16, iB * 16, r.t);
             zero_c<2>(dpp);
             add_global<2>(dpp, p.d_prior_probs_h, iA * 16, iB * 16, r.t);
@@ -415,18 +545,27 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
             float dlg[2][4];
             AFrag<NS, 2> f1;
             softmax_groups_bwd<KH>(q, dzh, dlg);
-            head_bwd<NS>(dlg, wblk<NS>(W, mt::T_HQ2), svA, svB, mts::HQ_HID, dpA, dpB, mtd::HQL, mtd::HQ1, f1, r, lane);
+            load_hid(mts::HQ_HID);
+            head_bwd<NS>(dlg, wblk<NS>(W, mt::T_HQ2), hid, dpA, dpB, mtd::HQL, mtd::HQ1, f1, r, lane);
             gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_HQ1L), lane);
             gemm<NS, 2, 4>(ddh, f1, wblk<NS>(W, mt::T_HQ1H), lane);
             softmax_groups_bwd<KH>(pp, dpp, dlg);
-            head_bwd<NS>(dlg, wblk<NS>(W, mt::T_HP2), svA, svB, mts::HP_HID, dpA, dpB, mtd::HPL, mtd::HP1, f1, r, lane);
+            load_hid(mts::HP_HID);
+            head_bwd<NS>(dlg, wblk<NS>(W, mt::T_HP2), hid, dpA, dpB, mtd::HPL, mtd::HP1, f1, r, lane);
             gemm<NS, 2, 4>(ddh, f1, wblk<NS>(W, mt::T_HP1), lane);
         }
         // ---- lower layer: MoPoE posterior + prior head ------------------------------------------------------
         {
             float q[2][4], pp[2][4], dpp[2][4];
-            load_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r.t);
-            load_c<2>(pp, p.prior_probs_l + iA * 16, p.prior_probs_l + iB * 16, r.t);
+            if constexpr (STAGED) {
+                load_staged<2>(q, st + bst::PR, 64, 16, r.g, r.t);
+                load_staged<2>(pp, st + bst::PR, 64, 48, r.g, r.t);
+                __syncwarp();  // every lane is done with DF / PR: refill them for the next (earlier) step
+                bstage_dfp(st, p, row0, t - 1, lane);
+            } else {
+                load_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r.t);
+                load_c<2>(pp, p.prior_probs_l + iA * 16, p.prior_probs_l + iB * 16, r.t);
+            }
             add_global<2>(dzl, p.d_post_probs_l, iA * 16, iB * 16, r.t);
             zero_c<2>(dpp);
             add_global<2>(dpp, p.d_prior_probs_l, iA * 16, iB * 16, r.t);
@@ -439,8 +578,13 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
             {
                 float dm[2][4], la[2][4], lv[2][4], lsa[2][4], lsv[2][4], mixed[2][4], ra[2][4], rv[2][4];
                 softmax_groups_bwd<KL>(q, dzl, dm);
-                load_rec<2>(la, svA + mts::LA, svB + mts::LA, r.t);
-                load_rec<2>(lv, svA + mts::LV, svB + mts::LV, r.t);
+                if constexpr (STAGED) {
+                    load_staged_rec<2>(la, st + bst::SV, mts::LA, r.g, r.t);
+                    load_staged_rec<2>(lv, st + bst::SV, mts::LV, r.g, r.t);
+                } else {
+                    load_rec<2>(la, svA + mts::LA, svB + mts::LA, r.t);
+                    load_rec<2>(lv, svA + mts::LV, svB + mts::LV, r.t);
+                }
                 log_softmax_flat<NS == 1>(la, lsa);
                 log_softmax_flat<NS == 1>(lv, lsv);
                 mopoe_mix<NS == 1>(lsa, lsv, mixed, ra, rv);
@@ -457,9 +601,9 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 AFrag<NS, 2> f1;
-                head_bwd<NS>(m == 0 ? dla : dlv, wblk<NS>(W, m == 0 ? mt::T_A2 : mt::T_V2), svA, svB,
-                             m == 0 ? mts::A_HID : mts::V_HID, dpA, dpB, m == 0 ? mtd::LA : mtd::LV, m == 0 ? mtd::A1 : mtd::V1, f1,
-                             r, lane);
+                load_hid(m == 0 ? mts::A_HID : mts::V_HID);
+                head_bwd<NS>(m == 0 ? dla : dlv, wblk<NS>(W, m == 0 ? mt::T_A2 : mt::T_V2), hid, dpA, dpB, m == 0 ? mtd::LA : mtd::LV,
+                             m == 0 ? mtd::A1 : mtd::V1, f1, r, lane);
                 gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, m == 0 ? mt::T_A1H : mt::T_V1H), lane);
                 float de[8][4];
                 zero_c<8>(de);
@@ -470,14 +614,28 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
             float dlg[2][4];
             AFrag<NS, 2> f1;
             softmax_groups_bwd<KL>(pp, dpp, dlg);
-            head_bwd<NS>(dlg, wblk<NS>(W, mt::T_LP2), svA, svB, mts::LP_HID, dpA, dpB, mtd::LPL, mtd::LP1, f1, r, lane);
+            load_hid(mts::LP_HID);
+            if constexpr (STAGED) {
+                __syncwarp();  // last read of the staged saved record: refill it
+                bstage_sv(st, reinterpret_cast<const __nv_bfloat16*>(p.saved), row0, p.B, T, t - 1, lane);
+            }
+            head_bwd<NS>(dlg, wblk<NS>(W, mt::T_LP2), hid, dpA, dpB, mtd::LPL, mtd::LP1, f1, r, lane);
             gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_LP1), lane);
         }
         // ---- the two leaky integrators: u = keep*u_prev + pre/tau, d = tanh(u) -------------------------------
         {
             float dh[4][4], dl[4][4], ph[4][4], pl[4][4];
-            load_c<4>(dh, p.feature + iA * F, p.feature + iB * F, r.t);
-            load_c<4>(dl, p.feature + iA * F + 48, p.feature + iB * F + 48, r.t);
+            if constexpr (STAGED) {
+                cp_async_wait<2>();  // FT(t) has landed (DFP(t-1), SV(t-1) may still be in flight)
+                __syncwarp();
+                load_staged<4>(dh, st + bst::FT, 64, 0, r.g, r.t);
+                load_staged<4>(dl, st + bst::FT, 64, 32, r.g, r.t);
+                __syncwarp();
+                bstage_ft(st, p.feature, row0, p.B, T, t - 1, lane);
+            } else {
+                load_c<4>(dh, p.feature + iA * F, p.feature + iB * F, r.t);
+                load_c<4>(dl, p.feature + iA * F + 48, p.feature + iB * F + 48, r.t);
+            }
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -569,7 +727,7 @@ cudaError_t launch_mtrssm_fwd(const MtrssmFwdArgs& a, int precision, bool imagin
 
 template <int NS>
 static cudaError_t launch_mtrssm_bwd_k(const MtrssmBwdArgs& a, cudaStream_t s) {
-    const size_t smem = (size_t)NS * mt::BWD_TILES * 32 * sizeof(uint2);
+    const size_t smem = (size_t)NS * mt::BWD_TILES * 32 * sizeof(uint2) + (NS == 1 ? 4 * bst::WORDS * sizeof(float) : 0);
     MT_DISPATCH(mtrssm_bwd_kernel, )
 }
 
