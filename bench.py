@@ -6,8 +6,9 @@
 
 Workload (BASELINE.json configs[1]): MoPoE-MMTRSSM at the default.yaml sizes
 (hd=ld=32, hs=ls=16, heads 32, E=64, A=6, tau 2/4, KL balancing), T=30, synthetic encoder embeddings, actions
-and noise.  default.yaml's batch of 8 cannot occupy a GPU, so the per-GPU batch is 16384 sequences (weak
-scaling: every rank processes its own 16384); the B=8 latency is reported beside it (`default_batch8`).
+and noise.  default.yaml's batch of 8 cannot occupy a GPU, so the per-GPU batch is 37888 sequences (= 148 SMs x 256:
+two full waves of the kernels' 16-sequence warp tiles; weak scaling: every rank processes its own 37888).  The B=8
+latency (`default_batch8`) and B = 256 / 4096 / 16384 and cfg4 (`other_workloads`) are reported beside it.
 
 A step = one pass of the hot path over one batch: forward rollout kernel, backward (BPTT) kernel, weight-gradient
 kernel (+ one NCCL allreduce of the flat weight-gradient bucket when N > 1).  `value` has the inputs resident in
@@ -46,7 +47,7 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16384, help="sequences per GPU")
+    ap.add_argument("--batch", type=int, default=37888, help="sequences per GPU (default 148 SMs x 256 = two full waves of 16-sequence warp tiles)")
     ap.add_argument("--seq-len", type=int, default=30)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences in the bounded CPU sample")
@@ -356,7 +357,7 @@ def main() -> None:
         del small
         # the other batch sizes SURVEY.md 8(d) asks for, and cfg4 (long horizon); same dims, same kernels
         extras["other_workloads"] = []
-        for name, b_, t_ in (("cfg2 B=256", 256, T), ("cfg2 B=4096", 4096, T), ("cfg4 B=256 T=512", 256, 512)):
+        for name, b_, t_ in (("cfg2 B=256", 256, T), ("cfg2 B=4096", 4096, T), ("cfg2 B=16384", 16384, T), ("cfg4 B=256 T=512", 256, 512)):
             w = DirectMtrssm(b_, t_, precision, device)
             rr = time_direct(w, 10, 3, 1)
             extras["other_workloads"].append({"workload": name, "B": b_, "T": t_, "value": b_ * t_ * 10 / (rr["total_ms"] * 1e-3),
