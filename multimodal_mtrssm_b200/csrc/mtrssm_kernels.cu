@@ -322,47 +322,67 @@ constexpr int DF = 0, PR = 1536, SV = 2560, FT = 4096, WORDS = 5120;  // 20480 b
 __device__ __forceinline__ int sw32(int chunk, int row) { return chunk ^ (4 * (row & 1)); }   // fp32 rows, float4 reads
 __device__ __forceinline__ int sw16(int chunk, int row) { return chunk ^ (2 * (row & 3)); }   // bf16 rows, 8-byte reads
 
-__device__ __forceinline__ size_t stage_row_index(int row0, int rl, int B, int T, int t) {
-    return (size_t)min(row0 + rl, B - 1) * T + t;
+// Lane -> piece mapping of the staging copies.  A lane always copies the SAME 16-byte chunk column c8 = lane & 7 (plus
+// 8-chunk groups) of the FOUR rows rq + 4j (rq = lane >> 3, j = 0..3): every shared-memory destination is one per-lane
+// base plus a compile-time offset (the swizzle term depends only on rq, since 4j does not change row & 1 / row & 3), and
+// every source is one of four (row, t) element indices times the tensor's row stride -- nothing loop-invariant is left
+// for the compiler to hoist into (and spill from) registers.
+struct StageLane {
+    int idx[4];          // (clamped row rq + 4j) * T + t, decremented once per step
+    int c8, rq;
+};
+__device__ __forceinline__ StageLane make_stage_lane(int row0, int B, int T, int t, int lane) {
+    StageLane s;
+    s.c8 = lane & 7, s.rq = lane >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s.idx[j] = min(row0 + s.rq + 4 * j, B - 1) * T + t;
+    return s;
 }
 
-// d_feature + the four probability tensors of step t (one cp.async group)
-__device__ __forceinline__ void bstage_dfp(float* st, const MtrssmBwdArgs& p, int row0, int t, int lane) {
-    if (t >= 0) {
+// d_feature + the four probability tensors of the step the lane indices point at (one cp.async group)
+__device__ __forceinline__ void bstage_dfp(float* st, const MtrssmBwdArgs& p, const StageLane& s, int dt, bool live) {
+    if (live) {
+        float* d = st + bst::DF + s.rq * 96 + 4 * (s.c8 ^ (4 * (s.rq & 1)));
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {  // 16 rows x 24 chunks
-            const int i = lane + 32 * k, rl = i / 24, c = i - rl * 24;
-            cp_async16(st + bst::DF + rl * 96 + 4 * sw32(c, rl), p.d_feature + stage_row_index(row0, rl, p.B, p.T, t) * 96 + 4 * c);
-        }
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // 16 rows x (4 tensors x 4 chunks)
-            const int i = lane + 32 * k, rl = i >> 4, c = i & 15, which = c >> 2;
-            const float* src = which == 0 ? p.post_probs_h : which == 1 ? p.post_probs_l : which == 2 ? p.prior_probs_h : p.prior_probs_l;
-            cp_async16(st + bst::PR + rl * 64 + 4 * sw32(c, rl), src + stage_row_index(row0, rl, p.B, p.T, t) * 16 + 4 * (c & 3));
+            for (int cg = 0; cg < 3; ++cg)  // 16 rows x 24 chunks
+                cp_async16(d + j * 384 + cg * 32, p.d_feature + (size_t)(s.idx[j] + dt) * 96 + 32 * cg + 4 * s.c8);
+        // 16 rows x (4 tensors x 4 chunks): chunk 8*cgrp + c8  ->  tensor 2*cgrp + (c8 >> 2), its chunk c8 & 3
+        float* d2 = st + bst::PR + s.rq * 64 + 4 * (s.c8 ^ (4 * (s.rq & 1)));
+        const bool hi = (s.c8 >> 2) != 0;
+        const float* src0 = hi ? p.post_probs_l : p.post_probs_h;
+        const float* src1 = hi ? p.prior_probs_l : p.prior_probs_h;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cp_async16(d2 + j * 256, src0 + (size_t)(s.idx[j] + dt) * 16 + 4 * (s.c8 & 3));
+            cp_async16(d2 + j * 256 + 32, src1 + (size_t)(s.idx[j] + dt) * 16 + 4 * (s.c8 & 3));
         }
     }
     cp_async_commit();
 }
 
-// the saved record (bf16, 384 bytes per row) of step t
-__device__ __forceinline__ void bstage_sv(float* st, const __nv_bfloat16* saved, int row0, int B, int T, int t, int lane) {
-    if (t >= 0) {
+// the saved record (bf16, 384 bytes per row)
+__device__ __forceinline__ void bstage_sv(float* st, const __nv_bfloat16* saved, const StageLane& s, int dt, bool live) {
+    if (live) {
+        float* d = st + bst::SV + s.rq * 96 + 4 * (s.c8 ^ (2 * (s.rq & 3)));
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {  // 16 rows x 24 chunks
-            const int i = lane + 32 * k, rl = i / 24, c = i - rl * 24;
-            cp_async16(st + bst::SV + rl * 96 + 4 * sw16(c, rl), saved + stage_row_index(row0, rl, B, T, t) * MTRSSM_SAVED_FLOATS + 8 * c);
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int cg = 0; cg < 3; ++cg)  // 16 rows x 24 chunks
+                cp_async16(d + j * 384 + cg * 32, saved + (size_t)(s.idx[j] + dt) * MTRSSM_SAVED_FLOATS + 64 * cg + 8 * s.c8);
     }
     cp_async_commit();
 }
 
-// deter_h (feature[0:32]) and deter_l (feature[48:80]) of step t
-__device__ __forceinline__ void bstage_ft(float* st, const float* feature, int row0, int B, int T, int t, int lane) {
-    if (t >= 0) {
+// deter_h (feature[0:32]) and deter_l (feature[48:80])
+__device__ __forceinline__ void bstage_ft(float* st, const float* feature, const StageLane& s, int dt, bool live) {
+    if (live) {
+        float* d = st + bst::FT + s.rq * 64 + 4 * (s.c8 ^ (4 * (s.rq & 1)));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // 16 rows x 16 chunks
-            const int i = lane + 32 * k, rl = i >> 4, c = i & 15;
-            cp_async16(st + bst::FT + rl * 64 + 4 * sw32(c, rl), feature + stage_row_index(row0, rl, B, T, t) * 96 + (c < 8 ? 4 * c : 48 + 4 * (c - 8)));
+        for (int j = 0; j < 4; ++j) {
+            cp_async16(d + j * 256, feature + (size_t)(s.idx[j] + dt) * 96 + 4 * s.c8);
+            cp_async16(d + j * 256 + 32, feature + (size_t)(s.idx[j] + dt) * 96 + 48 + 4 * s.c8);
         }
     }
     cp_async_commit();
@@ -471,12 +491,18 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
     // per-warp staging of this kernel's per-step inputs (bf16 path; see namespace bst)
     constexpr bool STAGED = NS == 1;
     float* st = reinterpret_cast<float*>(W + (size_t)NS * mt::BWD_TILES * 32) + warp * bst::WORDS;
+    StageLane sl = make_stage_lane(row0, p.B, T, T - 1, lane);
     if constexpr (STAGED) {  // cp.async groups in flight, oldest first: DFP(t), SV(t), FT(t)
-        bstage_dfp(st, p, row0, T - 1, lane);
-        bstage_sv(st, reinterpret_cast<const __nv_bfloat16*>(p.saved), row0, p.B, T, T - 1, lane);
-        bstage_ft(st, p.feature, row0, p.B, T, T - 1, lane);
+        bstage_dfp(st, p, sl, 0, true);
+        bstage_sv(st, reinterpret_cast<const __nv_bfloat16*>(p.saved), sl, 0, true);
+        bstage_ft(st, p.feature, sl, 0, true);
     }
 
+    // upstream KL gradients: lane t of a quad fetches ONE of the quad's four values (0: kl_h row A, 1: kl_h row B,
+    // 2: kl_l row A, 3: kl_l row B) one step ahead; the step gathers them with quad shuffles
+    const float* dkl_src = (r.t < 2) ? p.d_kl_h : p.d_kl_l;
+    const size_t dkl_row = (size_t)((r.t & 1) ? r.rB : r.rA) * T;
+    float dkl_next = dkl_src != nullptr ? dkl_src[dkl_row + T - 1] : 0.f;
     // carried gradients (w.r.t. the state handed from step t to step t+1)
     float ddl[4][4], ddh[4][4], dul[4][4], duh[4][4], dzl[2][4], dzh[2][4];
     zero_c<4>(ddl), zero_c<4>(ddh), zero_c<4>(dul), zero_c<4>(duh), zero_c<2>(dzl), zero_c<2>(dzh);
@@ -488,6 +514,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
         RT* dpA = dpre + iA * MTRSSM_DPRE_FLOATS;
         RT* dpB = dpre + iB * MTRSSM_DPRE_FLOATS;
 
+        const float dkl_cur = dkl_next;
+        if (t > 0 && dkl_src != nullptr) dkl_next = dkl_src[dkl_row + t - 1];
         float hid[4][4];  // a head's saved hidden, fetched from the staged record or from global memory
         auto load_hid = [&](int off) {
             if constexpr (STAGED) load_staged_rec<4>(hid, st + bst::SV, off, r.g, r.t);
@@ -539,7 +567,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
             add_global<2>(dpp, p.d_prior_probs_h, iA * 16, iB * 16, r.t);
             add_global<2>(dpp, p.d_prior_stoch_h, iA * 16, iB * 16, r.t);
             if (p.d_kl_h != nullptr) {
-                const float dkl[2] = {p.d_kl_h[iA], p.d_kl_h[iB]};
+                const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 0), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 1)};
                 kl_rows_bwd<NS == 1>(q, pp, dkl, p.kl_wq, p.kl_wp, dzh, dpp);
             }
             float dlg[2][4];
@@ -561,7 +589,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
                 load_staged<2>(q, st + bst::PR, 64, 16, r.g, r.t);
                 load_staged<2>(pp, st + bst::PR, 64, 48, r.g, r.t);
                 __syncwarp();  // every lane is done with DF / PR: refill them for the next (earlier) step
-                bstage_dfp(st, p, row0, t - 1, lane);
+                bstage_dfp(st, p, sl, -1, t > 0);
             } else {
                 load_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r.t);
                 load_c<2>(pp, p.prior_probs_l + iA * 16, p.prior_probs_l + iB * 16, r.t);
@@ -571,7 +599,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
             add_global<2>(dpp, p.d_prior_probs_l, iA * 16, iB * 16, r.t);
             add_global<2>(dpp, p.d_prior_stoch_l, iA * 16, iB * 16, r.t);
             if (p.d_kl_l != nullptr) {
-                const float dkl[2] = {p.d_kl_l[iA], p.d_kl_l[iB]};
+                const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 2), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 3)};
                 kl_rows_bwd<NS == 1>(q, pp, dkl, p.kl_wq, p.kl_wp, dzl, dpp);
             }
             float dla[2][4], dlv[2][4];
@@ -617,7 +645,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
             load_hid(mts::LP_HID);
             if constexpr (STAGED) {
                 __syncwarp();  // last read of the staged saved record: refill it
-                bstage_sv(st, reinterpret_cast<const __nv_bfloat16*>(p.saved), row0, p.B, T, t - 1, lane);
+                bstage_sv(st, reinterpret_cast<const __nv_bfloat16*>(p.saved), sl, -1, t > 0);
             }
             head_bwd<NS>(dlg, wblk<NS>(W, mt::T_LP2), hid, dpA, dpB, mtd::LPL, mtd::LP1, f1, r, lane);
             gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_LP1), lane);
@@ -631,7 +659,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
                 load_staged<4>(dh, st + bst::FT, 64, 0, r.g, r.t);
                 load_staged<4>(dl, st + bst::FT, 64, 32, r.g, r.t);
                 __syncwarp();
-                bstage_ft(st, p.feature, row0, p.B, T, t - 1, lane);
+                bstage_ft(st, p.feature, sl, -1, t > 0);
             } else {
                 load_c<4>(dh, p.feature + iA * F, p.feature + iB * F, r.t);
                 load_c<4>(dl, p.feature + iA * F + 48, p.feature + iB * F + 48, r.t);
@@ -665,6 +693,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
                 store_c_partial(da, p.d_actions + iA * A, p.d_actions + iB * A, r, A);
             }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sl.idx[j] -= 1;
     }
     store_c<4>(ddh, p.d_deter_h0 + (size_t)r.rA * 32, p.d_deter_h0 + (size_t)r.rB * 32, r);
     store_c<4>(ddl, p.d_deter_l0 + (size_t)r.rA * 32, p.d_deter_l0 + (size_t)r.rB * 32, r);
