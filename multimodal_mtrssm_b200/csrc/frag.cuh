@@ -443,9 +443,34 @@ struct Math {
 template <bool FAST>
 struct MathUnused {
 #endif
-    static __device__ __forceinline__ float exp(float x) { return FAST ? __expf(x) : expf(x); }
-    static __device__ __forceinline__ float log(float x) { return FAST ? __logf(x) : logf(x); }
-    static __device__ __forceinline__ float div(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+    // FAST: single MUFU ops with flush-to-zero (no denormal guard code around them)
+    static __device__ __forceinline__ float exp(float x) {
+        if constexpr (FAST) {
+            float y;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+            return y;
+        } else {
+            return expf(x);
+        }
+    }
+    static __device__ __forceinline__ float log(float x) {
+        if constexpr (FAST) {
+            float y;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+            return y * 0.6931471805599453f;
+        } else {
+            return logf(x);
+        }
+    }
+    static __device__ __forceinline__ float div(float a, float b) {
+        if constexpr (FAST) {
+            float y;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(b));
+            return a * y;
+        } else {
+            return a / b;
+        }
+    }
     static __device__ __forceinline__ float tanh(float x) {
         if constexpr (FAST) {
             float y;
@@ -456,10 +481,10 @@ struct MathUnused {
         }
     }
     static __device__ __forceinline__ float sigmoid(float x) { return div(1.f, 1.f + exp(-x)); }
-    static __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : (FAST ? __expf(x) - 1.f : expm1f(x)); }
+    static __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : (FAST ? exp(x) - 1.f : expm1f(x)); }
 };
 // d ELU / d pre, from the POST-activation value y: y > 0 -> 1, else exp(x) = y + 1
-__device__ __forceinline__ float elu_grad_from_out(float y) { return y > 0.f ? 1.f : y + 1.f; }
+__device__ __forceinline__ float elu_grad_from_out(float y) { return fminf(y, 0.f) + 1.f; }
 
 template <bool FAST>
 struct EluOp {
