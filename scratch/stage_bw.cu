@@ -1,0 +1,123 @@
+// Which staging path sustains more HBM read bandwidth at the rollout kernels' occupancy (4-8 warps per SM, one
+// 16-row tile per warp, one `seg`-byte segment per row per step)?
+//   mode 0: cp.async (LDGSTS) 16 B per lane      mode 1: cp.async.bulk, one bulk copy per row segment (TMA 1-D), mbarrier
+// Both double-buffered: step t+1 is in flight while step t is consumed.  Prints GB/s.
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scratch/stage_bw scratch/stage_bw.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+template <int MODE, int DEPTH>
+__global__ void __launch_bounds__(128) stage_kernel(const char* __restrict__ in, int B, int T, int seg, int nt, size_t tensor_bytes,
+                                                     float* sink, int compute_iters) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bars[4][DEPTH];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_stage = 16 * seg * nt;
+    unsigned char* mine = smem + (size_t)warp * DEPTH * per_stage;
+    if (lane == 0)
+        for (int d = 0; d < DEPTH; ++d) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[warp][d])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const int nwarps_total = gridDim.x * 4;
+    float acc = 0.f;
+    uint32_t phase[DEPTH];
+    for (int d = 0; d < DEPTH; ++d) phase[d] = 0;
+    for (int tile = blockIdx.x * 4 + warp; tile * 16 < B; tile += nwarps_total) {
+        const int row0 = tile * 16;
+        auto issue = [&](int t, int d) {
+            unsigned char* dst = mine + (size_t)d * per_stage;
+            if (MODE == 0) {
+                const int c16 = seg / 16;
+                for (int k = 0; k < nt; ++k)
+                    for (int i = lane; i < 16 * c16; i += 32) {
+                        const int r = i / c16, c = i - r * c16;
+                        const char* src = in + k * tensor_bytes + ((size_t)(row0 + r) * T + t) * seg + c * 16;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + (k * 16 + r) * seg + c * 16)), "l"(src)
+                                     : "memory");
+                    }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            } else {
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bars[warp][d])), "r"(per_stage)
+                                 : "memory");
+                __syncwarp();
+                for (int i = lane; i < 16 * nt; i += 32) {
+                    const int k = i >> 4, r = i & 15;
+                    const char* src = in + k * tensor_bytes + ((size_t)(row0 + r) * T + t) * seg;
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     smem_u32(dst + (k * 16 + r) * seg)),
+                                 "l"(src), "r"(seg), "r"(smem_u32(&bars[warp][d]))
+                                 : "memory");
+                }
+            }
+        };
+        for (int d = 0; d < DEPTH - 1 && d < T; ++d) issue(d, d);
+        for (int t = 0; t < T; ++t) {
+            const int d = t % DEPTH;
+            if (t + DEPTH - 1 < T) issue(t + DEPTH - 1, (t + DEPTH - 1) % DEPTH);
+            else if (MODE == 0) asm volatile("cp.async.commit_group;" ::: "memory");
+            if (MODE == 0) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+                __syncwarp();
+            } else {
+                uint32_t done = 0;
+                while (!done)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done)
+                                 : "r"(smem_u32(&bars[warp][d])), "r"(phase[d])
+                                 : "memory");
+                phase[d] ^= 1;
+            }
+            const float* s = reinterpret_cast<const float*>(mine + (size_t)d * per_stage);
+            acc += s[lane] + s[per_stage / 4 - 32 + lane];
+            for (int it = 0; it < compute_iters; ++it) acc = acc * 1.0001f + 0.5f;  // stand-in for the step's math
+            __syncwarp();
+        }
+    }
+    if (acc == 1.2345e-30f) *sink = acc;
+}
+
+template <int MODE, int DEPTH>
+static void run(const char* in, int B, int T, int seg, int nt, size_t tensor_bytes, float* sink, int ctas_per_sm, int compute_iters) {
+    const size_t smem = (size_t)4 * DEPTH * 16 * seg * nt;
+    if (smem * ctas_per_sm > 220 * 1024) return;
+    cudaFuncSetAttribute(stage_kernel<MODE, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        stage_kernel<MODE, DEPTH><<<148 * ctas_per_sm, 128, smem>>>(in, B, T, seg, nt, tensor_bytes, sink, compute_iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    printf("%s depth=%d seg=%d nt=%d ctas/sm=%d compute=%d: %7.1f GB/s  (%s)\n", MODE == 0 ? "cp.async   " : "bulk (TMA) ", DEPTH, seg, nt,
+           ctas_per_sm, compute_iters, (double)B * T * seg * nt / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+    const int B = 37888, T = 30, nt = 3;
+    const size_t tensor_bytes = (size_t)B * T * 512;
+    char* in;
+    float* sink;
+    cudaMalloc(&in, tensor_bytes * nt), cudaMalloc(&sink, 4);
+    cudaMemset(in, 0, tensor_bytes * nt);
+    for (int seg : {128, 384, 512})
+        for (int cps : {1, 2, 4})
+            for (int ci : {0, 2000}) {
+                run<0, 2>(in, B, T, seg, nt, tensor_bytes, sink, cps, ci);
+                run<1, 2>(in, B, T, seg, nt, tensor_bytes, sink, cps, ci);
+                if (cps <= 2) {
+                    run<0, 3>(in, B, T, seg, nt, tensor_bytes, sink, cps, ci);
+                    run<1, 3>(in, B, T, seg, nt, tensor_bytes, sink, cps, ci);
+                }
+            }
+    printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+    return 0;
+}
