@@ -10,8 +10,9 @@ and noise.  default.yaml's batch of 8 cannot occupy a GPU, so the per-GPU batch 
 two full waves of the kernels' 16-sequence warp tiles; weak scaling: every rank processes its own 37888).  The B=8
 latency (`default_batch8`) and B = 256 / 4096 / 16384 and cfg4 (`other_workloads`) are reported beside it.
 
-A step = one pass of the hot path over one batch: forward rollout kernel, backward (BPTT) kernel, weight-gradient
-kernel (+ one NCCL allreduce of the flat weight-gradient bucket when N > 1).  `value` has the inputs resident in
+A step = one pass of the hot path over one batch: forward rollout kernel + fused backward kernel (BPTT and the weight
+gradients on tcgen05 / TMEM in one launch; the fp32-parity path runs a BPTT kernel + a weight-gradient kernel instead)
+(+ one NCCL allreduce of the flat weight-gradient bucket when N > 1).  `value` has the inputs resident in
 HBM; `e2e` goes through the public API (`rollout_ops.mtrssm_rollout` + autograd) with pinned-host inputs copied
 in and the loss + weight gradients copied out every step.  One JSON line on stdout (rank 0).
 """
@@ -49,7 +50,7 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=37888, help="sequences per GPU (default 148 SMs x 256 = two full waves of 16-sequence warp tiles)")
     ap.add_argument("--seq-len", type=int, default=30)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16_fused", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp32-path / B=8 side measurements")
@@ -112,6 +113,7 @@ class DirectMtrssm:
         from multimodal_mtrssm_b200.params import mtrssm_weight_list
 
         self.lib, self.B, self.T = _lib, B, T
+        self.fused = precision == _lib.PRECISION_BF16_FUSED
         self.params = {k: v.to(device) for k, v in synthetic.mtrssm_params().items()}
         self.weights = mtrssm_weight_list(self.params)
         self.inp = {k: v.to(device) for k, v in synthetic.mtrssm_batch(B, T).items()}
@@ -123,7 +125,7 @@ class DirectMtrssm:
             "feature": e(B, T, 96), "hidden_h": e(B, T, 32), "hidden_l": e(B, T, 32),
             "prior_probs_h": e(B, T, 8, 2), "prior_probs_l": e(B, T, 4, 4), "post_probs_h": e(B, T, 8, 2), "post_probs_l": e(B, T, 4, 4),
             "kl_l": e(B, T), "kl_h": e(B, T),
-            "saved": torch.empty(B, T, _lib.MTRSSM_SAVED_FLOATS, device=device, dtype=_lib.record_dtype(precision)),
+            "saved": torch.empty(B, T, _lib.mtrssm_saved_elems(precision), device=device, dtype=_lib.record_dtype(precision)),
         }
         self.gin = {
             "d_actions": e(B, T, 6), "d_embed_a": e(B, T, 64), "d_embed_v": e(B, T, 64), "d_deter_h0": e(B, 32), "d_deter_l0": e(B, 32),
@@ -151,6 +153,11 @@ class DirectMtrssm:
     def bwd_data(self) -> None:
         self.lib.call("rssm_mtrssm_rollout_bwd", self.c_dims, self.c_w, self.c_in, self.c_out, self.c_up, self.c_gin, None)
 
+    def bwd_fused(self) -> None:
+        """bf16 path: BPTT + weight gradients in one kernel (no dpre round trip)."""
+        self.flat_grad.zero_()
+        self.lib.call("rssm_mtrssm_rollout_bwd", self.c_dims, self.c_w, self.c_in, self.c_out, self.c_up, self.c_gin, self.c_gw)
+
     def wgrad(self) -> None:
         self.flat_grad.zero_()
         self.lib.call("rssm_mtrssm_wgrad", self.c_dims, self.c_in, self.c_out, self.gin["dpre"].data_ptr(), self.c_gw)
@@ -168,10 +175,14 @@ def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
         run.fwd()
         if evs:
             evs[1].record()
-        run.bwd_data()
+        if run.fused:
+            run.bwd_fused()
+        else:
+            run.bwd_data()
         if evs:
             evs[2].record()
-        run.wgrad()
+        if not run.fused:
+            run.wgrad()
         if world > 1:
             dist.all_reduce(run.flat_grad)
         if evs:
@@ -332,7 +343,7 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=device)
     from multimodal_mtrssm_b200 import _lib
 
-    precision = _lib.PRECISION_BF16 if args.precision == "bf16" else _lib.PRECISION_FP32
+    precision = {"bf16": _lib.PRECISION_BF16, "bf16_fused": _lib.PRECISION_BF16_FUSED, "fp32": _lib.PRECISION_FP32}[args.precision]
     B, T = args.batch, args.seq_len
     launches0 = _lib.launch_count()
     run = DirectMtrssm(B, T, precision, device)
@@ -344,13 +355,16 @@ def main() -> None:
 
     extras = {}
     if rank == 0 and not args.no_extras:
-        other = DirectMtrssm(B, T, _lib.PRECISION_FP32 if precision == _lib.PRECISION_BF16 else _lib.PRECISION_BF16, device)
-        r2 = time_direct(other, max(3, args.steps // 2), 3, 1)
         n2 = max(3, args.steps // 2)
-        extras["fp32_path" if precision == _lib.PRECISION_BF16 else "bf16_path"] = {
-            "value": B * T * n2 / (r2["total_ms"] * 1e-3), "ms_per_step": r2["total_ms"] / n2,
-            "fwd_ms": r2["fwd_ms"], "bwd_ms": r2["bwd_ms"], "wgrad_ms": r2["wgrad_ms"]}
-        del other
+        for name, prec in (("fp32_path", _lib.PRECISION_FP32), ("bf16_path", _lib.PRECISION_BF16),
+                           ("bf16_fused_backward_path", _lib.PRECISION_BF16_FUSED)):
+            if prec == precision:
+                continue
+            other = DirectMtrssm(B, T, prec, device)
+            r2 = time_direct(other, n2, 3, 1)
+            extras[name] = {"value": B * T * n2 / (r2["total_ms"] * 1e-3), "ms_per_step": r2["total_ms"] / n2,
+                            "fwd_ms": r2["fwd_ms"], "bwd_ms": r2["bwd_ms"], "wgrad_ms": r2["wgrad_ms"]}
+            del other
         small = DirectMtrssm(8, T, precision, device)
         r3 = time_direct(small, 50, 10, 1)
         extras["default_batch8"] = {"B": 8, "T": T, "value": 8 * T * 50 / (r3["total_ms"] * 1e-3), "us_per_step": r3["total_ms"] / 50 * 1e3}
@@ -379,24 +393,27 @@ def main() -> None:
     ms_step = res["total_ms"] / args.steps
     value = world * B * T / (ms_step * 1e-3)
     seg = {"mtrssm_fwd_kernel": res["fwd_ms"], "mtrssm_bwd_kernel": res["bwd_ms"], "wgrad_kernel": res["wgrad_ms"]}
+    if run.fused:
+        seg = {"mtrssm_fwd_kernel": res["fwd_ms"], "mtrssm_bwd_fused_kernel": res["bwd_ms"] + res["wgrad_ms"]}
     dominant = max(seg, key=seg.get)
     # algorithmic bytes of the dominant launch: forward = fwd I/O; backward (bwd kernel + its wgrad pass) = fwd I/O again
     if dominant == "mtrssm_fwd_kernel":
         alg_bytes, dur_ms, what = FWD_BYTES_PER_BT * B * T, seg[dominant], "forward rollout kernel"
     else:
         alg_bytes, dur_ms = FWD_BYTES_PER_BT * B * T, res["bwd_ms"] + res["wgrad_ms"]
-        what = "backward = BPTT kernel + weight-gradient kernel (dominant: %s)" % dominant
+        what = ("fused backward kernel (BPTT + weight gradients)" if run.fused
+                else "backward = BPTT kernel + weight-gradient kernel (dominant: %s)" % dominant)
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if precision == _lib.PRECISION_BF16 else "f32", "data": "synthetic",
+        "dtype": "f32" if precision == _lib.PRECISION_FP32 else "bf16", "data": "synthetic",
         "config": {
             "workload": "cfg2: MoPoE-MMTRSSM default.yaml sizes (hd=ld=32, hs=ls=16, E=64, A=6), rollout fwd+bwd on synthetic "
                         "vision+audio embeddings/actions", "batch_per_gpu": B, "seq_len": T, "global_batch": world * B,
             "parallelism": f"dp{world} (batch-sharded, one flat-bucket NCCL allreduce of the weight gradients)" if world > 1 else "single GPU",
             "l2": f"inputs {run.input_bytes() / 1e6:.0f} MB + outputs/records per step exceed the 126 MB L2 (no flush needed)",
-            "precision": "bf16 operands / fp32 accumulate+state (tensor-core path)" if precision == _lib.PRECISION_BF16
+            "precision": "bf16 operands / fp32 accumulate+state (tensor-core path)" if precision != _lib.PRECISION_FP32
                          else "3-way bf16 split, fp32-level accuracy",
         },
         "kernel_ms": seg,

@@ -43,6 +43,9 @@ extern "C" {
 #define RSSM_ABI_VERSION 1
 #define RSSM_PRECISION_FP32 0
 #define RSSM_PRECISION_BF16 1
+/* bf16 tensor-core path whose backward is ONE kernel: BPTT + weight-gradient contractions on tcgen05 with TMEM accumulators
+   (MMTRSSM only; the forward then writes the extended saved record MTRSSM_SAVED_BF16).  Same numerics as RSSM_PRECISION_BF16. */
+#define RSSM_PRECISION_BF16_FUSED 2
 
 /* ELEMENTS per (b,t) of the opaque records exchanged between fwd, bwd and wgrad.  Element type: fp32 with
    RSSM_PRECISION_FP32, bf16 with RSSM_PRECISION_BF16 (so bytes = elements * 4 or * 2). */
@@ -50,6 +53,10 @@ extern "C" {
 #define MRSSM_DPRE_FLOATS 336
 #define MTRSSM_SAVED_FLOATS 192
 #define MTRSSM_DPRE_FLOATS 304
+/* With RSSM_PRECISION_BF16_FUSED the MMTRSSM saved record is [B,T,MTRSSM_SAVED_BF16] bf16: the 192 elements above followed by
+   bf16 copies of the step's inputs (both embeddings, the previous deter / stoch of both levels, the action, a ones column)
+   -- the operands of the weight-gradient contractions that the fused backward runs on the tcgen05 tensor cores. */
+#define MTRSSM_SAVED_BF16 448
 
 /* ---- MoPoE-MRSSM -------------------------------------------------------------------------------------- */
 typedef struct {
@@ -173,7 +180,7 @@ typedef struct {
     float *post_probs_h, *post_probs_l;
     float *prior_stoch_h, *prior_stoch_l;   /* [B,T,HS] [B,T,LS]; may be NULL */
     float *kl_l, *kl_h;                     /* [B,T] each */
-    void *saved;                            /* [B,T,MTRSSM_SAVED_FLOATS] record elements; NULL = inference */
+    void *saved;                            /* [B,T,MTRSSM_SAVED_FLOATS] record elements ([B,T,MTRSSM_SAVED_BF16] bf16 with _BF16_FUSED); NULL = inference */
 } RssmMtrssmOutputs;
 
 typedef struct {
@@ -189,11 +196,15 @@ typedef struct {
     float *d_actions;                       /* may be NULL */
     float *d_embed_a, *d_embed_v;
     float *d_deter_h0, *d_deter_l0, *d_hidden_h0, *d_hidden_l0, *d_stoch_h0, *d_stoch_l0;
-    void *dpre;                             /* [B,T,MTRSSM_DPRE_FLOATS] record elements, workspace */
+    void *dpre;                             /* [B,T,MTRSSM_DPRE_FLOATS] record elements, workspace; may be NULL when
+                                               rssm_mtrssm_rollout_bwd runs fused (RSSM_PRECISION_BF16_FUSED and gw != NULL) */
 } RssmMtrssmInputGrads;
 
 int rssm_mtrssm_rollout_fwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights *w, const RssmMtrssmInputs *in,
                             const RssmMtrssmOutputs *out, void *stream);
+/* gw == NULL: data gradients only (fills `dpre` for a later rssm_mtrssm_wgrad).  gw != NULL: also ADDS the weight gradients
+   into gw -- with RSSM_PRECISION_BF16_FUSED in ONE kernel (BPTT + weight-gradient contractions on tcgen05 / TMEM, no dpre
+   round trip), otherwise as backward kernel + rssm_mtrssm_wgrad. */
 int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights *w, const RssmMtrssmInputs *in,
                             const RssmMtrssmOutputs *fwd_out, const RssmMtrssmUpstream *up, const RssmMtrssmInputGrads *gin,
                             const RssmMtrssmWeightGrads *gw, void *stream);

@@ -16,9 +16,11 @@ from .build import LIB, build_library
 
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+PRECISION_BF16_FUSED = 2  # bf16 path with the one-kernel backward (tcgen05 weight gradients); MMTRSSM only
 ABI_VERSION = 1
 MRSSM_SAVED_FLOATS, MRSSM_DPRE_FLOATS = 320, 336
 MTRSSM_SAVED_FLOATS, MTRSSM_DPRE_FLOATS = 192, 304
+MTRSSM_SAVED_BF16 = 448
 
 _fp = C.c_void_p  # device pointers travel as integers
 
@@ -143,7 +145,12 @@ def ptr(t: torch.Tensor | None) -> int | None:
 
 def record_dtype(precision: int) -> torch.dtype:
     """Element type of the opaque saved / dpre records (include/rssm_rollout.h)."""
-    return torch.bfloat16 if precision == PRECISION_BF16 else torch.float32
+    return torch.float32 if precision == PRECISION_FP32 else torch.bfloat16
+
+
+def mtrssm_saved_elems(precision: int) -> int:
+    """Elements per (b,t) of the MMTRSSM saved record (include/rssm_rollout.h)."""
+    return MTRSSM_SAVED_BF16 if precision == PRECISION_BF16_FUSED else MTRSSM_SAVED_FLOATS
 
 
 def launch_count() -> int:

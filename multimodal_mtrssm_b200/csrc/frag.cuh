@@ -245,7 +245,7 @@ __device__ __forceinline__ void store_rec(const float (&c)[NT][4], float* __rest
 template <int NT>
 __device__ __forceinline__ void store_rec(const float (&c)[NT][4], __nv_bfloat16* __restrict__ pA, __nv_bfloat16* __restrict__ pB,
                                           const Rows& r) {
-#ifdef RSSM_EXP_NO_STORES
+#if defined(RSSM_EXP_NO_STORES) || defined(RSSM_EXP_NO_REC_STORES)
     if (c[0][0] == 1.2345e-30f) *pA = __float2bfloat16(c[0][1]);
     return;
 #endif
@@ -274,6 +274,18 @@ __device__ __forceinline__ void load_rec(float (&c)[NT][4], const __nv_bfloat16*
         const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&b.x), b1 = *reinterpret_cast<const __nv_bfloat162*>(&b.y);
         c[2 * j][0] = __low2float(a0), c[2 * j][1] = __high2float(a0), c[2 * j + 1][0] = __low2float(a1), c[2 * j + 1][1] = __high2float(a1);
         c[2 * j][2] = __low2float(b0), c[2 * j][3] = __high2float(b0), c[2 * j + 1][2] = __low2float(b1), c[2 * j + 1][3] = __high2float(b1);
+    }
+}
+
+// bf16 A operand (KT k-tiles = 16*KT logical columns) -> bf16 record columns: lane (g,t) owns the four consecutive columns
+// 16kt + 4t .. + 3 of rows g (registers 0, 2) and g + 8 (registers 1, 3)
+template <int KT>
+__device__ __forceinline__ void store_afrag(const AFrag<1, KT>& a, __nv_bfloat16* __restrict__ pA, __nv_bfloat16* __restrict__ pB,
+                                            const Rows& r) {
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        if (r.vA) *reinterpret_cast<uint2*>(pA + 16 * kt + 4 * r.t) = make_uint2(a.r[0][kt][0], a.r[0][kt][2]);
+        if (r.vB) *reinterpret_cast<uint2*>(pB + 16 * kt + 4 * r.t) = make_uint2(a.r[0][kt][1], a.r[0][kt][3]);
     }
 }
 
@@ -396,6 +408,41 @@ __device__ __forceinline__ void stage_inputs(float* stage, const float* __restri
         }
     }
     cp_async_commit();
+}
+
+// ---- mbarrier + bulk-copy (TMA 1-D) helpers ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// asynchronous bulk store shared -> global (TMA 1-D); completion tracked per issuing thread in bulk groups
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// until the sources of all of this thread's bulk stores have been read (the shared-memory buffer may be rewritten)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// bounded wait: a lost transaction traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
 }
 
 // A operand (KT = 4, 64 columns) from a swizzled staged embedding tile

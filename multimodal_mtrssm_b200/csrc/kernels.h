@@ -41,6 +41,8 @@ struct MtrssmFwdArgs {
     float *prior_probs_h, *prior_probs_l, *post_probs_h, *post_probs_l, *prior_stoch_h, *prior_stoch_l;
     float *kl_l, *kl_h;
     void* saved;
+    int saved_ld;    // elements per (b,t) row of `saved`
+    int saved_ext;   // bf16 path: also write the bf16 copies of the step's inputs (MTRSSM_SAVED_BF16 record, fused backward)
 };
 
 struct MtrssmBwdArgs {
@@ -49,6 +51,7 @@ struct MtrssmBwdArgs {
     RssmMtrssmWeights w;
     const float *feature, *prior_probs_h, *prior_probs_l, *post_probs_h, *post_probs_l;
     const void* saved;
+    int saved_ld;  // elements per (b,t) row of `saved`
     const float *d_feature, *d_prior_probs_h, *d_prior_probs_l, *d_post_probs_h, *d_post_probs_l;
     const float *d_prior_stoch_h, *d_prior_stoch_l, *d_kl_l, *d_kl_h;
     void* dpre;
@@ -58,6 +61,8 @@ struct MtrssmBwdArgs {
 
 cudaError_t launch_mtrssm_fwd(const MtrssmFwdArgs& a, int precision, bool imagine, cudaStream_t s);
 cudaError_t launch_mtrssm_bwd(const MtrssmBwdArgs& a, int precision, cudaStream_t s);
+// bf16 path: BPTT + weight gradients in one kernel (tcgen05 / TMEM accumulators); ADDS into g (mtrssm_fused_bwd.cu)
+cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeightGrads& g, cudaStream_t s);
 
 // ---- batched weight gradients on the tensor cores (wgrad_kernel.cu) -----------------------------------------------
 // A staged shared-memory row holds, per (b,t), the dpre record followed by every layer's input, as bf16 columns.

@@ -18,48 +18,13 @@
 //
 // Fixed sizes of this instantiation: hd = ld = 32, hs = ls = 16, head hidden 32, E = 64, A <= 8.
 // feature layout (state.py:51): [deter_h 0:32 | stoch_h 32:48 | deter_l 48:80 | stoch_l 80:96].
+#include <stdlib.h>
+
 #include "frag.cuh"
 #include "kernels.h"
+#include "mtrssm_common.cuh"
 
 namespace rssm {
-
-namespace mt {
-// ---- forward weight blocks (tile offsets) ----------------------------------------------------------
-constexpr int L_D2H = 0;              // d_l_prev (32) -> l pre (32)       KT2 NT4
-constexpr int L_IN_ZL = L_D2H + 8;    // z_l_prev (16) -> l pre            KT1 NT4
-constexpr int L_IN_ZH = L_IN_ZL + 4;  // z_h_prev (16) -> l pre            KT1 NT4
-constexpr int L_IN_A = L_IN_ZH + 4;   // action        -> l pre            KT1 NT4
-constexpr int H_D2H = L_IN_A + 4;     // d_h_prev      -> h pre            KT2 NT4
-constexpr int H_IN = H_D2H + 8;       // z_h_prev      -> h pre            KT1 NT4
-constexpr int LP1 = H_IN + 4, LP2 = LP1 + 8;
-constexpr int HP1 = LP2 + 4, HP2 = HP1 + 8;
-constexpr int HQ1L = HP2 + 4, HQ1H = HQ1L + 8, HQ2 = HQ1H + 8;
-constexpr int A1H = HQ2 + 4, A1E = A1H + 8, A2 = A1E + 16;
-constexpr int V1H = A2 + 4, V1E = V1H + 8, V2 = V1E + 16;
-constexpr int FWD_TILES = V2 + 4;  // 132
-constexpr int B_L = 0, B_H = 32, B_LP1 = 64, B_LP2 = 96, B_HP1 = 112, B_HP2 = 144, B_HQ1 = 160, B_HQ2 = 192, B_A1 = 208,
-              B_A2 = 240, B_V1 = 256, B_V2 = 288, FWD_BIAS = 304;
-// ---- backward (transposed) weight blocks -----------------------------------------------------------
-constexpr int T_A2 = 0, T_V2 = 4, T_LP2 = 8, T_HP2 = 12, T_HQ2 = 16;                       // KT1 NT4
-constexpr int T_A1H = 20, T_V1H = 28, T_LP1 = 36, T_HP1 = 44, T_HQ1L = 52, T_HQ1H = 60;   // KT2 NT4
-constexpr int T_A1E = 68, T_V1E = 84;                                                       // KT2 NT8
-constexpr int T_L_D2H = 100, T_H_D2H = 108;                                                 // KT2 NT4
-constexpr int T_L_IN_ZL = 116, T_L_IN_ZH = 120, T_H_IN = 124;                               // KT2 NT2
-constexpr int T_L_IN_A = 128;                                                               // KT2 NT2 (one 16-block)
-constexpr int BWD_TILES = 132;
-}  // namespace mt
-
-namespace mts {  // saved record (MTRSSM_SAVED_FLOATS = 192)
-constexpr int LP_HID = 0, HP_HID = 32, HQ_HID = 64, A_HID = 96, V_HID = 128, LA = 160, LV = 176;
-}
-namespace mtd {  // dpre record (MTRSSM_DPRE_FLOATS = 304)
-constexpr int L = 0, H = 32, LP1 = 64, LPL = 96, HP1 = 112, HPL = 144, HQ1 = 160, HQL = 192, A1 = 208, LA = 240, V1 = 256, LV = 288;
-}
-
-template <int NS>
-__device__ __forceinline__ uint2* wblk(uint2* W, int tile_off) {
-    return W + (size_t)NS * tile_off * 32;
-}
 
 // hidden -> ELU -> logits for a 32-wide hidden layer whose pre-activation is already accumulated
 template <int NS>
@@ -170,8 +135,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
 
     for (int t = 0; t < T; ++t) {
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
-        RT* svA = saved ? saved + iA * MTRSSM_SAVED_FLOATS : nullptr;
-        RT* svB = saved ? saved + iB * MTRSSM_SAVED_FLOATS : nullptr;
+        RT* svA = saved ? saved + iA * p.saved_ld : nullptr;
+        RT* svB = saved ? saved + iB * p.saved_ld : nullptr;
         const float* stage = stage_base + (t & 1) * stg::FLOATS;
         if (STAGED) {
             cp_async_wait_all();  // this step's inputs have landed ...
@@ -188,6 +153,17 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
             AFrag<NS, 1> fa;
             if (STAGED) load_a_staged_act<NS>(fa, stage + stg::ACT, r.g, r.t);
             else load_a_global<NS, 1>(fa, p.actions + iA * A, p.actions + iB * A, r.t, A);
+            if constexpr (NS == 1 && !IMAGINE) {
+                if (svA && p.saved_ext) {  // bf16 copies of the step's inputs: the X operands of the fused backward's weight-gradient MMAs
+                    store_afrag<2>(dlf, svA + mts::DL_PREV, svB + mts::DL_PREV, r);
+                    store_afrag<2>(dhf, svA + mts::DH_PREV, svB + mts::DH_PREV, r);
+                    store_afrag<1>(zlf, svA + mts::ZL_PREV, svB + mts::ZL_PREV, r);
+                    store_afrag<1>(zhf, svA + mts::ZH_PREV, svB + mts::ZH_PREV, r);
+                    AFrag<1, 1> ao = fa;  // [action (8 columns, zero padded) | ones column + 7 zeros]
+                    if (r.t == 2) ao.r[0][0][0] = ao.r[0][0][1] = 0x00003f80u;
+                    store_afrag<1>(ao, svA + mts::ACT, svB + mts::ACT, r);
+                }
+            }
             gemm<NS, 2, 4>(pl, dlf, wblk<NS>(W, mt::L_D2H), lane);
             gemm<NS, 1, 4>(pl, zlf, wblk<NS>(W, mt::L_IN_ZL), lane);
             gemm<NS, 1, 4>(pl, zhf, wblk<NS>(W, mt::L_IN_ZH), lane);
@@ -257,6 +233,9 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
             AFrag<NS, 4> fe;
             if (STAGED) load_a_staged64<NS>(fe, stage + (m == 0 ? stg::EA : stg::EV), r.g, r.t);
             else load_a_global<NS, 4>(fe, (m == 0 ? p.embed_a : p.embed_v) + iA * 64, (m == 0 ? p.embed_a : p.embed_v) + iB * 64, r.t, 64);
+            if constexpr (NS == 1) {
+                if (svA && p.saved_ext) store_afrag<4>(fe, svA + (m == 0 ? mts::EMB_A : mts::EMB_V), svB + (m == 0 ? mts::EMB_A : mts::EMB_V), r);
+            }
             gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, m == 0 ? mt::A1H : mt::V1H), lane);
             gemm<NS, 4, 4>(acc, fe, wblk<NS>(W, m == 0 ? mt::A1E : mt::V1E), lane);
             float (&lg)[2][4] = m == 0 ? la : lv;
@@ -309,146 +288,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
 // ================================================================================================
 // backward
 // ================================================================================================
-// ---- per-warp staging of the backward kernel's per-step inputs (bf16 path) ---------------------------------------
-// Single-buffered "consume early, refill at once": each buffer is read by step t and, right after its last read,
-// re-filled with cp.async for step t-1, which then has most of a step to land.  Rows are swizzled at 16-byte chunk
-// granularity so the fragment-pattern reads are bank-conflict free.  Layout (32-bit words per warp):
-//   DF [16][96]  d_feature            | PR [16][64] post_h | post_l | prior_h | prior_l
-//   SV [16][96]  saved record (bf16)  | FT [16][64] deter_h | deter_l
-namespace bst {
-constexpr int DF = 0, PR = 1536, SV = 2560, FT = 4096, WORDS = 5120;  // 20480 bytes per warp
-}
-
-__device__ __forceinline__ int sw32(int chunk, int row) { return chunk ^ (4 * (row & 1)); }   // fp32 rows, float4 reads
-__device__ __forceinline__ int sw16(int chunk, int row) { return chunk ^ (2 * (row & 3)); }   // bf16 rows, 8-byte reads
-
-// Lane -> piece mapping of the staging copies.  A lane always copies the SAME 16-byte chunk column c8 = lane & 7 (plus
-// 8-chunk groups) of the FOUR rows rq + 4j (rq = lane >> 3, j = 0..3): every shared-memory destination is one per-lane
-// base plus a compile-time offset (the swizzle term depends only on rq, since 4j does not change row & 1 / row & 3), and
-// every source is one of four (row, t) element indices times the tensor's row stride -- nothing loop-invariant is left
-// for the compiler to hoist into (and spill from) registers.
-struct StageLane {
-    int idx[4];          // (clamped row rq + 4j) * T + t, decremented once per step
-    int c8, rq;
-};
-__device__ __forceinline__ StageLane make_stage_lane(int row0, int B, int T, int t, int lane) {
-    StageLane s;
-    s.c8 = lane & 7, s.rq = lane >> 3;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s.idx[j] = min(row0 + s.rq + 4 * j, B - 1) * T + t;
-    return s;
-}
-
-// d_feature + the four probability tensors of the step the lane indices point at (one cp.async group)
-__device__ __forceinline__ void bstage_dfp(float* st, const MtrssmBwdArgs& p, const StageLane& s, int dt, bool live) {
-    if (live) {
-        float* d = st + bst::DF + s.rq * 96 + 4 * (s.c8 ^ (4 * (s.rq & 1)));
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int cg = 0; cg < 3; ++cg)  // 16 rows x 24 chunks
-                cp_async16(d + j * 384 + cg * 32, p.d_feature + (size_t)(s.idx[j] + dt) * 96 + 32 * cg + 4 * s.c8);
-        // 16 rows x (4 tensors x 4 chunks): chunk 8*cgrp + c8  ->  tensor 2*cgrp + (c8 >> 2), its chunk c8 & 3
-        float* d2 = st + bst::PR + s.rq * 64 + 4 * (s.c8 ^ (4 * (s.rq & 1)));
-        const bool hi = (s.c8 >> 2) != 0;
-        const float* src0 = hi ? p.post_probs_l : p.post_probs_h;
-        const float* src1 = hi ? p.prior_probs_l : p.prior_probs_h;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cp_async16(d2 + j * 256, src0 + (size_t)(s.idx[j] + dt) * 16 + 4 * (s.c8 & 3));
-            cp_async16(d2 + j * 256 + 32, src1 + (size_t)(s.idx[j] + dt) * 16 + 4 * (s.c8 & 3));
-        }
-    }
-    cp_async_commit();
-}
-
-// the saved record (bf16, 384 bytes per row)
-__device__ __forceinline__ void bstage_sv(float* st, const __nv_bfloat16* saved, const StageLane& s, int dt, bool live) {
-    if (live) {
-        float* d = st + bst::SV + s.rq * 96 + 4 * (s.c8 ^ (2 * (s.rq & 3)));
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-            for (int cg = 0; cg < 3; ++cg)  // 16 rows x 24 chunks
-                cp_async16(d + j * 384 + cg * 32, saved + (size_t)(s.idx[j] + dt) * MTRSSM_SAVED_FLOATS + 64 * cg + 8 * s.c8);
-    }
-    cp_async_commit();
-}
-
-// deter_h (feature[0:32]) and deter_l (feature[48:80])
-__device__ __forceinline__ void bstage_ft(float* st, const float* feature, const StageLane& s, int dt, bool live) {
-    if (live) {
-        float* d = st + bst::FT + s.rq * 64 + 4 * (s.c8 ^ (4 * (s.rq & 1)));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            cp_async16(d + j * 256, feature + (size_t)(s.idx[j] + dt) * 96 + 4 * s.c8);
-            cp_async16(d + j * 256 + 32, feature + (size_t)(s.idx[j] + dt) * 96 + 48 + 4 * s.c8);
-        }
-    }
-    cp_async_commit();
-}
-
-// NT tiles starting at logical column col0 of a staged fp32 buffer with `stride` words per row
-template <int NT>
-__device__ __forceinline__ void load_staged(float (&c)[NT][4], const float* buf, int stride, int col0, int g, int t) {
-#pragma unroll
-    for (int j = 0; j < NT / 2; ++j) {
-        const int ch = sw32(col0 / 4 + 4 * j + t, g);
-        const float4 a = *reinterpret_cast<const float4*>(buf + g * stride + 4 * ch);
-        const float4 b = *reinterpret_cast<const float4*>(buf + (g + 8) * stride + 4 * ch);
-        c[2 * j][0] = a.x, c[2 * j][1] = a.y, c[2 * j + 1][0] = a.z, c[2 * j + 1][1] = a.w;
-        c[2 * j][2] = b.x, c[2 * j][3] = b.y, c[2 * j + 1][2] = b.z, c[2 * j + 1][3] = b.w;
-    }
-}
-
-// NT tiles starting at record element `off` of the staged bf16 saved rows
-template <int NT>
-__device__ __forceinline__ void load_staged_rec(float (&c)[NT][4], const float* buf, int off, int g, int t) {
-#pragma unroll
-    for (int j = 0; j < NT / 2; ++j) {
-        const int e = off + 16 * j + 4 * t;                 // bf16 element index in the row
-        const int w = 4 * sw16(e >> 3, g) + ((e >> 1) & 3);  // 32-bit word: swizzled 16-byte chunk + offset inside it
-        const uint2 a = *reinterpret_cast<const uint2*>(buf + g * 96 + w), b = *reinterpret_cast<const uint2*>(buf + (g + 8) * 96 + w);
-        const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162*>(&a.x), a1 = *reinterpret_cast<const __nv_bfloat162*>(&a.y);
-        const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&b.x), b1 = *reinterpret_cast<const __nv_bfloat162*>(&b.y);
-        c[2 * j][0] = __low2float(a0), c[2 * j][1] = __high2float(a0), c[2 * j + 1][0] = __low2float(a1), c[2 * j + 1][1] = __high2float(a1);
-        c[2 * j][2] = __low2float(b0), c[2 * j][3] = __high2float(b0), c[2 * j + 1][2] = __low2float(b1), c[2 * j + 1][3] = __high2float(b1);
-    }
-}
-
-// d logits (16) -> through W2^T -> * ELU'(hidden) -> dpre1 (stored) ; returns dpre1 as A operand.
-// `hid` = the head's saved post-ELU hidden.
-template <int NS>
-__device__ __forceinline__ void head_bwd(const float (&dlogit)[2][4], const uint2* w2t, const float (&hid)[4][4], typename Rec<NS>::T* dpA,
-                                         typename Rec<NS>::T* dpB, int dp_logit_off, int dp1_off, AFrag<NS, 2>& f1, const Rows& r,
-                                         int lane) {
-    store_rec<2>(dlogit, dpA + dp_logit_off, dpB + dp_logit_off, r);
-    AFrag<NS, 1> fl;
-    to_afrag<NS, 1>(fl, dlogit);
-    float dhid[4][4];
-    zero_c<4>(dhid);
-    gemm<NS, 1, 4>(dhid, fl, w2t, lane);
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dhid[nt][j] *= elu_grad_from_out(hid[nt][j]);
-    store_rec<4>(dhid, dpA + dp1_off, dpB + dp1_off, r);
-    to_afrag<NS, 2>(f1, dhid);
-}
-
-template <int NT>
-__device__ __forceinline__ void add_global(float (&acc)[NT][4], const float* base, size_t offA, size_t offB, int t) {
-    if (base == nullptr) return;
-    float g[NT][4];
-    load_c<NT>(g, base + offA, base + offB, t);
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[nt][j] += g[nt][j];
-}
-
 template <int NS, int KL, int KH>
-__global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_kernel(const MtrssmBwdArgs p) {
+__global__ void __launch_bounds__(NS == 1 ? 256 : 128, 1) mtrssm_bwd_kernel(const MtrssmBwdArgs p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* W = reinterpret_cast<uint2*>(smem_raw);
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -491,11 +332,21 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
     // per-warp staging of this kernel's per-step inputs (bf16 path; see namespace bst)
     constexpr bool STAGED = NS == 1;
     float* st = reinterpret_cast<float*>(W + (size_t)NS * mt::BWD_TILES * 32) + warp * bst::WORDS;
-    StageLane sl = make_stage_lane(row0, p.B, T, T - 1, lane);
-    if constexpr (STAGED) {  // cp.async groups in flight, oldest first: DFP(t), SV(t), FT(t)
-        bstage_dfp(st, p, sl, 0, true);
-        bstage_sv(st, reinterpret_cast<const __nv_bfloat16*>(p.saved), sl, 0, true);
-        bstage_ft(st, p.feature, sl, 0, true);
+    __shared__ __align__(8) uint64_t bars_all[8][bst::NBAR];
+    uint64_t* bars = bars_all[warp];
+    uint32_t ph_df = 0, ph_sv = 0, ph_ft = 0;  // mbarrier phase parities
+    const char* sv_bytes = reinterpret_cast<const char*>(p.saved);
+    if constexpr (STAGED) {
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < bst::NBAR; ++i) mbar_init(&bars[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        bulk_rows(st + bst::DF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, T - 1, &bars[bst::BAR_DF], lane);
+        bulk_rows(st + bst::SV, bst::SV_LD, sv_bytes, (size_t)p.saved_ld * 2, bst::SV_BYTES, row0, p.B, T, T - 1, &bars[bst::BAR_SV], lane);
+        bulk_rows(st + bst::FT, bst::FT_LD, reinterpret_cast<const char*>(p.feature), 384, bst::FT_BYTES, row0, p.B, T, T - 1, &bars[bst::BAR_FT], lane);
+        bstage_pr(st, p, row0, T - 1, lane);
     }
 
     // upstream KL gradients: lane t of a quad fetches ONE of the quad's four values (0: kl_h row A, 1: kl_h row B,
@@ -509,8 +360,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
 
     for (int t = T - 1; t >= 0; --t) {
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
-        const RT* svA = saved + iA * MTRSSM_SAVED_FLOATS;
-        const RT* svB = saved + iB * MTRSSM_SAVED_FLOATS;
+        const RT* svA = saved + iA * p.saved_ld;
+        const RT* svB = saved + iB * p.saved_ld;
         RT* dpA = dpre + iA * MTRSSM_DPRE_FLOATS;
         RT* dpB = dpre + iB * MTRSSM_DPRE_FLOATS;
 
@@ -522,29 +373,35 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
             else load_rec<4>(hid, svA + off, svB + off, r.t);
         };
         if constexpr (STAGED) {
-            cp_async_wait<1>();  // DFP(t) and SV(t) have landed (FT(t) may still be in flight)
-            __syncwarp();
+            mbar_wait(&bars[bst::BAR_DF], ph_df), ph_df ^= 1;  // d_feature(t) has landed
             float g4[4][4], g2[2][4];
-            load_staged<4>(g4, st + bst::DF, 96, 0, r.g, r.t);
+            load_staged<4, false>(g4, st + bst::DF, bst::DF_LD, 0, r.g, r.t);
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) ddh[nt][j] += g4[nt][j];
-            load_staged<2>(g2, st + bst::DF, 96, 32, r.g, r.t);  // straight-through: d stoch -> d probs
+            load_staged<2, false>(g2, st + bst::DF, bst::DF_LD, 32, r.g, r.t);  // straight-through: d stoch -> d probs
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dzh[nt][j] += g2[nt][j];
-            load_staged<4>(g4, st + bst::DF, 96, 48, r.g, r.t);
+            load_staged<4, false>(g4, st + bst::DF, bst::DF_LD, 48, r.g, r.t);
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) ddl[nt][j] += g4[nt][j];
-            load_staged<2>(g2, st + bst::DF, 96, 80, r.g, r.t);
+            load_staged<2, false>(g2, st + bst::DF, bst::DF_LD, 80, r.g, r.t);
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dzl[nt][j] += g2[nt][j];
+            __syncwarp();  // every lane is done with DF: refill it for the next (earlier) step
+            if (t > 0)
+                bulk_rows(st + bst::DF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, t - 1,
+                          &bars[bst::BAR_DF], lane);
+            cp_async_wait_all();  // the probability rows of step t ...
+            __syncwarp();
+            mbar_wait(&bars[bst::BAR_SV], ph_sv), ph_sv ^= 1;  // ... and its saved record have landed
         } else {
             add_global<4>(ddh, p.d_feature, iA * F, iB * F, r.t);
             add_global<2>(dzh, p.d_feature, iA * F + 32, iB * F + 32, r.t);  // straight-through: d stoch -> d probs
@@ -556,8 +413,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
         {
             float q[2][4], pp[2][4], dpp[2][4];
             if constexpr (STAGED) {
-                load_staged<2>(q, st + bst::PR, 64, 0, r.g, r.t);
-                load_staged<2>(pp, st + bst::PR, 64, 32, r.g, r.t);
+                load_staged<2, true>(q, st + bst::PR, 64, 0, r.g, r.t);
+                load_staged<2, true>(pp, st + bst::PR, 64, 32, r.g, r.t);
             } else {
                 load_c<2>(q, p.post_probs_h + iA * 16, p.post_probs_h + iB * 16, r.t);
                 load_c<2>(pp, p.prior_probs_h + iA * 16, p.prior_probs_h + iB * 16, r.t);
@@ -586,10 +443,10 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
         {
             float q[2][4], pp[2][4], dpp[2][4];
             if constexpr (STAGED) {
-                load_staged<2>(q, st + bst::PR, 64, 16, r.g, r.t);
-                load_staged<2>(pp, st + bst::PR, 64, 48, r.g, r.t);
-                __syncwarp();  // every lane is done with DF / PR: refill them for the next (earlier) step
-                bstage_dfp(st, p, sl, -1, t > 0);
+                load_staged<2, true>(q, st + bst::PR, 64, 16, r.g, r.t);
+                load_staged<2, true>(pp, st + bst::PR, 64, 48, r.g, r.t);
+                __syncwarp();  // every lane is done with PR: refill it for the next (earlier) step
+                bstage_pr(st, p, row0, t - 1, lane);
             } else {
                 load_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r.t);
                 load_c<2>(pp, p.prior_probs_l + iA * 16, p.prior_probs_l + iB * 16, r.t);
@@ -645,7 +502,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
             load_hid(mts::LP_HID);
             if constexpr (STAGED) {
                 __syncwarp();  // last read of the staged saved record: refill it
-                bstage_sv(st, reinterpret_cast<const __nv_bfloat16*>(p.saved), sl, -1, t > 0);
+                if (t > 0)
+                    bulk_rows(st + bst::SV, bst::SV_LD, sv_bytes, (size_t)p.saved_ld * 2, bst::SV_BYTES, row0, p.B, T, t - 1, &bars[bst::BAR_SV], lane);
             }
             head_bwd<NS>(dlg, wblk<NS>(W, mt::T_LP2), hid, dpA, dpB, mtd::LPL, mtd::LP1, f1, r, lane);
             gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_LP1), lane);
@@ -654,12 +512,13 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
         {
             float dh[4][4], dl[4][4], ph[4][4], pl[4][4];
             if constexpr (STAGED) {
-                cp_async_wait<2>();  // FT(t) has landed (DFP(t-1), SV(t-1) may still be in flight)
+                mbar_wait(&bars[bst::BAR_FT], ph_ft), ph_ft ^= 1;  // feature[0:80](t) has landed
+                load_staged<4, false>(dh, st + bst::FT, bst::FT_LD, 0, r.g, r.t);
+                load_staged<4, false>(dl, st + bst::FT, bst::FT_LD, 48, r.g, r.t);
                 __syncwarp();
-                load_staged<4>(dh, st + bst::FT, 64, 0, r.g, r.t);
-                load_staged<4>(dl, st + bst::FT, 64, 32, r.g, r.t);
-                __syncwarp();
-                bstage_ft(st, p.feature, sl, -1, t > 0);
+                if (t > 0)
+                    bulk_rows(st + bst::FT, bst::FT_LD, reinterpret_cast<const char*>(p.feature), 384, bst::FT_BYTES, row0, p.B, T, t - 1,
+                              &bars[bst::BAR_FT], lane);
             } else {
                 load_c<4>(dh, p.feature + iA * F, p.feature + iB * F, r.t);
                 load_c<4>(dl, p.feature + iA * F + 48, p.feature + iB * F + 48, r.t);
@@ -693,8 +552,6 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
                 store_c_partial(da, p.d_actions + iA * A, p.d_actions + iB * A, r, A);
             }
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sl.idx[j] -= 1;
     }
     store_c<4>(ddh, p.d_deter_h0 + (size_t)r.rA * 32, p.d_deter_h0 + (size_t)r.rB * 32, r);
     store_c<4>(ddl, p.d_deter_l0 + (size_t)r.rA * 32, p.d_deter_l0 + (size_t)r.rB * 32, r);
@@ -707,18 +564,22 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_bwd_k
 // ================================================================================================
 // launchers
 // ================================================================================================
-static int pick_warps_per_cta(int B) {
+// warps (= 16-sequence tiles) per CTA: spread small batches over all SMs, share one weight copy per SM for large ones
+static int pick_warps_per_cta(int B, int max_wpc) {
     const int warps = (B + 15) / 16;
-    if (warps <= 2 * 148) return 1;
-    if (warps <= 4 * 148) return 2;
-    return 4;
+    int wpc = 1;
+    while (wpc < max_wpc && warps > 2 * wpc * 148) wpc *= 2;
+    return wpc;
 }
 
+// smem = smem_cta (weights, biases) + warps per CTA * smem_warp (per-warp staging)
 template <typename KernelT, typename ArgsT>
-static cudaError_t launch(KernelT kernel, const ArgsT& args, int B, size_t smem, cudaStream_t stream) {
+static cudaError_t launch(KernelT kernel, const ArgsT& args, int B, size_t smem_cta, size_t smem_warp, int max_wpc, cudaStream_t stream) {
+    const int wpc = pick_warps_per_cta(B, max_wpc);
+    size_t smem = smem_cta + wpc * smem_warp;
+    if (const char* pad = getenv("RSSM_EXP_SMEM_PAD")) smem += (size_t)atoi(pad);  // occupancy experiment only
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    const int wpc = pick_warps_per_cta(B);
     const int ctas = ((B + 15) / 16 + wpc - 1) / wpc;
     kernel<<<ctas, wpc * 32, smem, stream>>>(args);
     return cudaGetLastError();
@@ -727,23 +588,24 @@ static cudaError_t launch(KernelT kernel, const ArgsT& args, int B, size_t smem,
 // supported (class_size_l, class_size_h) pairs; default.yaml is (4, 2)
 #ifdef RSSM_EXP_ONLY_DEFAULT
 #define MT_DISPATCH(KERNEL, ...)                                                              \
-    if (a.KL == 4 && a.KH == 2) return launch(KERNEL<NS, 4, 2 __VA_ARGS__>, a, a.B, smem, s); \
+    if (a.KL == 4 && a.KH == 2) return launch(KERNEL<NS, 4, 2 __VA_ARGS__>, a, a.B, smem_cta, smem_warp, max_wpc, s); \
     return cudaErrorInvalidValue;
 #else
 #define MT_DISPATCH(KERNEL, ...)                                                              \
-    if (a.KL == 4 && a.KH == 2) return launch(KERNEL<NS, 4, 2 __VA_ARGS__>, a, a.B, smem, s); \
-    if (a.KL == 4 && a.KH == 4) return launch(KERNEL<NS, 4, 4 __VA_ARGS__>, a, a.B, smem, s); \
-    if (a.KL == 2 && a.KH == 2) return launch(KERNEL<NS, 2, 2 __VA_ARGS__>, a, a.B, smem, s); \
-    if (a.KL == 8 && a.KH == 8) return launch(KERNEL<NS, 8, 8 __VA_ARGS__>, a, a.B, smem, s); \
-    if (a.KL == 16 && a.KH == 16) return launch(KERNEL<NS, 16, 16 __VA_ARGS__>, a, a.B, smem, s); \
+    if (a.KL == 4 && a.KH == 2) return launch(KERNEL<NS, 4, 2 __VA_ARGS__>, a, a.B, smem_cta, smem_warp, max_wpc, s); \
+    if (a.KL == 4 && a.KH == 4) return launch(KERNEL<NS, 4, 4 __VA_ARGS__>, a, a.B, smem_cta, smem_warp, max_wpc, s); \
+    if (a.KL == 2 && a.KH == 2) return launch(KERNEL<NS, 2, 2 __VA_ARGS__>, a, a.B, smem_cta, smem_warp, max_wpc, s); \
+    if (a.KL == 8 && a.KH == 8) return launch(KERNEL<NS, 8, 8 __VA_ARGS__>, a, a.B, smem_cta, smem_warp, max_wpc, s); \
+    if (a.KL == 16 && a.KH == 16) return launch(KERNEL<NS, 16, 16 __VA_ARGS__>, a, a.B, smem_cta, smem_warp, max_wpc, s); \
     return cudaErrorInvalidValue;
 #endif
 
 template <int NS, bool IMAGINE>
 static cudaError_t launch_mtrssm_fwd_k(const MtrssmFwdArgs& a, cudaStream_t s) {
-    // weights + biases (+ per-warp input staging, sized for the largest CTA of 4 warps)
-    const size_t smem = (size_t)NS * mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float) +
-                        (IMAGINE || NS != 1 ? 0 : 4 * 2 * stg::FLOATS * sizeof(float));
+    // weights + biases (+ per-warp double-buffered input staging)
+    const size_t smem_cta = (size_t)NS * mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float);
+    const size_t smem_warp = IMAGINE || NS != 1 ? 0 : 2 * stg::FLOATS * sizeof(float);
+    const int max_wpc = 4;
 #define COMMA_IMAGINE , IMAGINE
     MT_DISPATCH(mtrssm_fwd_kernel, COMMA_IMAGINE)
 #undef COMMA_IMAGINE
@@ -757,7 +619,9 @@ cudaError_t launch_mtrssm_fwd(const MtrssmFwdArgs& a, int precision, bool imagin
 
 template <int NS>
 static cudaError_t launch_mtrssm_bwd_k(const MtrssmBwdArgs& a, cudaStream_t s) {
-    const size_t smem = (size_t)NS * mt::BWD_TILES * 32 * sizeof(uint2) + (NS == 1 ? 4 * bst::WORDS * sizeof(float) : 0);
+    const size_t smem_cta = (size_t)NS * mt::BWD_TILES * 32 * sizeof(uint2);
+    const size_t smem_warp = NS == 1 ? bst::WORDS * sizeof(float) : 0;
+    const int max_wpc = NS == 1 ? 8 : 4;  // bf16 path: one CTA of 8 warps per SM (255 registers, 218 KB of shared memory)
     MT_DISPATCH(mtrssm_bwd_kernel, )
 }
 

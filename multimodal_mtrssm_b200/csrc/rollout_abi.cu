@@ -52,9 +52,14 @@ int check_mtrssm(const RssmMtrssmDims* d) {
                     d->CH);
     if (d->A < 2 || d->A > 8 || (d->A & 1)) return fail("unsupported action_size %d: need an even size in 2..8", d->A);
     if (!(d->l_tau > 1.f) || !(d->h_tau > 1.f)) return fail("tau must be greater than 1.0 (l_tau=%g h_tau=%g)", d->l_tau, d->h_tau);
-    if (d->precision != RSSM_PRECISION_FP32 && d->precision != RSSM_PRECISION_BF16) return fail("bad precision %d", d->precision);
+    if (d->precision != RSSM_PRECISION_FP32 && d->precision != RSSM_PRECISION_BF16 && d->precision != RSSM_PRECISION_BF16_FUSED)
+        return fail("bad precision %d", d->precision);
     return 0;
 }
+
+// kernel precision policy (fp32-parity / bf16) and saved-record row length of an MMTRSSM precision value
+int mt_kernel_precision(int precision) { return precision == RSSM_PRECISION_FP32 ? RSSM_PRECISION_FP32 : RSSM_PRECISION_BF16; }
+int mt_saved_ld(int precision) { return precision == RSSM_PRECISION_BF16_FUSED ? MTRSSM_SAVED_BF16 : MTRSSM_SAVED_FLOATS; }
 
 #define REQUIRE(ptr)                                                           \
     do {                                                                       \
@@ -238,8 +243,9 @@ static int mtrssm_fwd_common(const RssmMtrssmDims* d, const RssmMtrssmWeights* w
     a.post_probs_h = out->post_probs_h, a.post_probs_l = out->post_probs_l;
     a.prior_stoch_h = out->prior_stoch_h, a.prior_stoch_l = out->prior_stoch_l;
     a.kl_l = out->kl_l, a.kl_h = out->kl_h, a.saved = imagine ? nullptr : out->saved;
+    a.saved_ld = mt_saved_ld(d->precision), a.saved_ext = d->precision == RSSM_PRECISION_BF16_FUSED;
     g_launches.fetch_add(1);
-    return check_cuda(rssm::launch_mtrssm_fwd(a, d->precision, imagine, static_cast<cudaStream_t>(stream)),
+    return check_cuda(rssm::launch_mtrssm_fwd(a, mt_kernel_precision(d->precision), imagine, static_cast<cudaStream_t>(stream)),
                       imagine ? "mtrssm imagine launch" : "mtrssm forward launch");
 }
 
@@ -261,7 +267,9 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
     REQUIRE(in->actions); REQUIRE(in->embed_a); REQUIRE(in->embed_v); REQUIRE(in->deter_h0); REQUIRE(in->deter_l0);
     REQUIRE(in->stoch_h0); REQUIRE(in->stoch_l0);
     REQUIRE(fo->feature); REQUIRE(fo->prior_probs_h); REQUIRE(fo->prior_probs_l); REQUIRE(fo->post_probs_h); REQUIRE(fo->post_probs_l);
-    REQUIRE(fo->saved); REQUIRE(up->d_feature); REQUIRE(gin->d_embed_a); REQUIRE(gin->d_embed_v); REQUIRE(gin->dpre);
+    REQUIRE(fo->saved); REQUIRE(up->d_feature); REQUIRE(gin->d_embed_a); REQUIRE(gin->d_embed_v);
+    const bool fused = gw != nullptr && d->precision == RSSM_PRECISION_BF16_FUSED;
+    if (!fused) REQUIRE(gin->dpre);
     REQUIRE(gin->d_deter_h0); REQUIRE(gin->d_deter_l0); REQUIRE(gin->d_hidden_h0); REQUIRE(gin->d_hidden_l0);
     REQUIRE(gin->d_stoch_h0); REQUIRE(gin->d_stoch_l0);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -269,15 +277,22 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
     a.B = d->B, a.T = d->T, a.A = d->A, a.KL = d->KL, a.KH = d->KH;
     a.inv_tau_l = 1.f / d->l_tau, a.inv_tau_h = 1.f / d->h_tau, a.kl_wq = up->kl_wq, a.kl_wp = up->kl_wp, a.w = *w;
     a.feature = fo->feature, a.prior_probs_h = fo->prior_probs_h, a.prior_probs_l = fo->prior_probs_l;
-    a.post_probs_h = fo->post_probs_h, a.post_probs_l = fo->post_probs_l, a.saved = fo->saved;
+    a.post_probs_h = fo->post_probs_h, a.post_probs_l = fo->post_probs_l, a.saved = fo->saved, a.saved_ld = mt_saved_ld(d->precision);
     a.d_feature = up->d_feature, a.d_prior_probs_h = up->d_prior_probs_h, a.d_prior_probs_l = up->d_prior_probs_l;
     a.d_post_probs_h = up->d_post_probs_h, a.d_post_probs_l = up->d_post_probs_l;
     a.d_prior_stoch_h = up->d_prior_stoch_h, a.d_prior_stoch_l = up->d_prior_stoch_l, a.d_kl_l = up->d_kl_l, a.d_kl_h = up->d_kl_h;
     a.dpre = gin->dpre, a.d_actions = gin->d_actions, a.d_embed_a = gin->d_embed_a, a.d_embed_v = gin->d_embed_v;
     a.d_deter_h0 = gin->d_deter_h0, a.d_deter_l0 = gin->d_deter_l0, a.d_hidden_h0 = gin->d_hidden_h0;
     a.d_hidden_l0 = gin->d_hidden_l0, a.d_stoch_h0 = gin->d_stoch_h0, a.d_stoch_l0 = gin->d_stoch_l0;
+    if (fused) {
+        const float* const* gp = reinterpret_cast<const float* const*>(gw);
+        for (size_t i = 0; i < sizeof(RssmMtrssmWeightGrads) / sizeof(float*); ++i)
+            if (gp[i] == nullptr) return fail("weight-gradient pointer %d is NULL", (int)i);
+        g_launches.fetch_add(1);
+        return check_cuda(rssm::launch_mtrssm_bwd_fused(a, *gw, s), "mtrssm fused backward launch");
+    }
     g_launches.fetch_add(1);
-    if (check_cuda(rssm::launch_mtrssm_bwd(a, d->precision, s), "mtrssm backward launch")) return 1;
+    if (check_cuda(rssm::launch_mtrssm_bwd(a, mt_kernel_precision(d->precision), s), "mtrssm backward launch")) return 1;
     if (gw == nullptr) return 0;
     return rssm_mtrssm_wgrad(d, in, fo, gin->dpre, gw, stream);
 }
@@ -291,8 +306,9 @@ int rssm_mtrssm_wgrad(const RssmMtrssmDims* d, const RssmMtrssmInputs* in, const
     // staged-row layout and part ids: kernels.h (wgl_mt); record offsets: mtrssm_kernels.cu (mts / mtd);
     // feature = [d_h 0 | z_h 32 | d_l 48 | z_l 80]
     using namespace rssm::wgl_mt;
-    const int A = d->A, F = 96, SV = MTRSSM_SAVED_FLOATS, DPF = MTRSSM_DPRE_FLOATS, LDIN = A + 32;
-    const int RE = d->precision == RSSM_PRECISION_BF16 ? 2 : 4;  // record element size
+    const int A = d->A, F = 96, DPF = MTRSSM_DPRE_FLOATS, LDIN = A + 32;
+    const int SV = mt_saved_ld(d->precision);
+    const int RE = d->precision == RSSM_PRECISION_FP32 ? 4 : 2;  // record element size
     const void* sv = fo->saved;
     const float* feat = fo->feature;
     rssm::WgradMmaArgs j{};
@@ -333,7 +349,7 @@ int rssm_mtrssm_wgrad(const RssmMtrssmDims* d, const RssmMtrssmInputs* in, const
     for (int i = 0; i < N_OUT; ++i)
         if (j.out[i].dW == nullptr) return fail("weight-gradient pointer of part %d is NULL", i);
     g_launches.fetch_add(1);
-    return check_cuda(rssm::launch_wgrad_mma(j, 0, d->precision, static_cast<cudaStream_t>(stream)), "mtrssm wgrad launch");
+    return check_cuda(rssm::launch_wgrad_mma(j, 0, mt_kernel_precision(d->precision), static_cast<cudaStream_t>(stream)), "mtrssm wgrad launch");
 }
 
 }  // extern "C"

@@ -370,6 +370,54 @@ def test_mtrssm_bf16_teacher_forced(ops):
     rep.finish()
 
 
+@pytest.mark.parametrize("B,T", [(37, 9), (200, 12), (16, 1)])
+def test_mtrssm_bf16_fused_backward_matches_two_kernel_backward(ops, B, T):
+    """RSSM_PRECISION_BF16_FUSED (BPTT + weight gradients in one kernel, tcgen05 / TMEM accumulators) against
+    RSSM_PRECISION_BF16 (BPTT kernel + mma.sync weight-gradient kernel): the forward and the data gradients run the same
+    arithmetic (bit-identical); the weight gradients multiply the same bf16 operands and differ only in the fp32 summation
+    order (tolerance 2e-4 of the tensor's scale)."""
+    R, P = ops
+    dims = H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    inp = H.mtrssm_inputs(B, T, dims)
+    up = mtrssm_upstream(B, T, dims)
+    o1, w1, x1 = run_mtrssm(R, P, params, inp, dims, precision=1, grad=True, upstream=up)
+    o2, w2, x2 = run_mtrssm(R, P, params, inp, dims, precision=2, grad=True, upstream=up)
+    for k in ("feature", *MT_FWD_KEYS):
+        assert torch.equal(o1[k], o2[k]), k
+    for k in MT_GRAD_IN:
+        assert torch.equal(x1[k].grad, x2[k].grad), k
+    rep = H.Report(f"mtrssm bf16 fused vs two-kernel backward B={B} T={T}")
+    for k in w1:
+        scale = float(w1[k].grad.abs().max())
+        rep.check("d " + k.replace("rnn_to_post_projector", "post"), w2[k].grad, w1[k].grad, rtol=0, atol=2e-4 * max(scale, 1e-3))
+    rep.finish()
+
+
+@pytest.mark.parametrize("precision", [1, 2])
+def test_mtrssm_bf16_backward_vs_oracle(ops, precision):
+    """Gradients of the bf16 tensor-core paths against the fp32 oracle, teacher-forced on the kernel's own draws (as in
+    test_mtrssm_bf16_teacher_forced).  Stated bf16 tolerance for gradients: 2e-2 of each tensor's scale."""
+    R, P = ops
+    B, T, dims = 48, 8, H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    inp = H.mtrssm_inputs(B, T, dims)
+    inp["u_prior_l"] = inp["u_prior_h"] = None  # the prior samples are not part of the training loss
+    up = {k: v for k, v in mtrssm_upstream(B, T, dims).items() if not k.startswith("prior_stoch")}
+    got, w, x = run_mtrssm(R, P, params, inp, dims, precision=precision, grad=True, upstream=up)
+    f = got["feature"].detach().cpu()
+    idx_h = f[..., 32:48].reshape(B, T, dims["CH"], dims["KH"]).argmax(-1)
+    idx_l = f[..., 80:].reshape(B, T, dims["CL"], dims["KL"]).argmax(-1)
+    _, w_ref, x_ref = oracle_mtrssm(params, inp, dims, grad=True, upstream=up, forced=(idx_l, idx_h))
+    rep = H.Report(f"mtrssm bwd bf16 (precision {precision}) vs teacher-forced oracle")
+    for k in MT_GRAD_IN:
+        rep.check("d " + k, x[k].grad, x_ref[k].grad, rtol=0, atol=2e-2 * float(x_ref[k].grad.abs().max()))
+    for k in w:
+        rep.check("d " + k.replace("rnn_to_post_projector", "post"), w[k].grad, w_ref[k].grad, rtol=0,
+                  atol=2e-2 * float(w_ref[k].grad.abs().max()))
+    rep.finish()
+
+
 # ---------------------------------------------------------------------------------------------------
 # size-independent properties at benchmark scale, error behaviour
 # ---------------------------------------------------------------------------------------------------
