@@ -51,8 +51,8 @@ extern "C" {
    RSSM_PRECISION_FP32, bf16 with RSSM_PRECISION_BF16 (so bytes = elements * 4 or * 2). */
 #define MRSSM_SAVED_FLOATS 320
 #define MRSSM_DPRE_FLOATS 336
-#define MTRSSM_SAVED_FLOATS 192
-#define MTRSSM_DPRE_FLOATS 304
+#define MTRSSM_SAVED_FLOATS 208 /* 192 used; bf16 rows of 416 bytes: whole 32-byte sectors, and a row pitch that lets the  */
+#define MTRSSM_DPRE_FLOATS 304  /* weight-gradient kernel read bulk-copied 32-row slabs with ldmatrix in place              */
 /* With RSSM_PRECISION_BF16_FUSED the MMTRSSM saved record is [B,T,MTRSSM_SAVED_BF16] bf16: the 192 elements above followed by
    bf16 copies of the step's inputs (both embeddings, the previous deter / stoch of both levels, the action, a ones column)
    -- the operands of the weight-gradient contractions that the fused backward runs on the tcgen05 tensor cores. */

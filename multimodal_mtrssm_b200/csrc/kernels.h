@@ -1,5 +1,6 @@
 // Internal launch interface between the C-ABI layer (rollout_abi.cu) and the kernels.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/rssm_rollout.h"
@@ -89,6 +90,17 @@ struct WgradMmaArgs {
 };
 // model: 0 = MMTRSSM, 1 = MRSSM
 cudaError_t launch_wgrad_mma(const WgradMmaArgs& a, int model, int precision, cudaStream_t s);
+
+// MMTRSSM, bf16 records of MTRSSM_DPRE_FLOATS / MTRSSM_SAVED_FLOATS elements per row: slab-staged variant (one bulk copy per
+// source tensor and 32-row block); same outputs (`out`, indexed by wgl_mt part ids) as the generic kernel
+struct WgradMtSlabArgs {
+    int B, T, A;
+    const __nv_bfloat16 *dpre, *saved;
+    const float *feature, *embed_a, *embed_v, *actions;
+    const float *deter_l0, *deter_h0, *stoch_l0, *stoch_h0;
+    WgradOut out[MAX_WGRAD_OUTS];
+};
+cudaError_t launch_wgrad_mt_slab(const WgradMtSlabArgs& a, cudaStream_t s);
 
 // staged-row column layouts (bf16 elements) and part ids
 namespace wgl_mt {

@@ -32,13 +32,13 @@ constexpr int T_L_IN_A = 128;                                                   
 constexpr int BWD_TILES = 132;
 }  // namespace mt
 
-namespace mts {  // saved record (MTRSSM_SAVED_FLOATS = 192)
+namespace mts {  // saved record (192 used of MTRSSM_SAVED_FLOATS)
 constexpr int LP_HID = 0, HP_HID = 32, HQ_HID = 64, A_HID = 96, V_HID = 128, LA = 160, LV = 176;
 // RSSM_PRECISION_BF16_FUSED only (MTRSSM_SAVED_BF16 = 448): bf16 copies of the step's INPUTS, i.e. the X operands of the weight gradients
 constexpr int EMB_A = 192, EMB_V = 256, DL_PREV = 320, DH_PREV = 352, ZL_PREV = 384, ZH_PREV = 400, ACT = 416, ONES = 424;  // 432..447: pad
 }
 
-namespace mtd {  // dpre record (MTRSSM_DPRE_FLOATS = 304)
+namespace mtd {  // dpre record (304 used of MTRSSM_DPRE_FLOATS)
 constexpr int L = 0, H = 32, LP1 = 64, LPL = 96, HP1 = 112, HPL = 144, HQ1 = 160, HQL = 192, A1 = 208, LA = 240, V1 = 256, LV = 288;
 }
 

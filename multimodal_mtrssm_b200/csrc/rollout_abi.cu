@@ -1,6 +1,7 @@
 // C-ABI entry points of librssm_rollout.so (declared in include/rssm_rollout.h).
 // Validates sizes, builds kernel arguments and the weight-gradient job lists, launches on the
 // caller's stream.  No hidden state; errors are reported through a thread-local message.
+#include <stdlib.h>
 #include <atomic>
 #include <cstdarg>
 #include <cstdint>
@@ -313,7 +314,7 @@ int rssm_mtrssm_wgrad(const RssmMtrssmDims* d, const RssmMtrssmInputs* in, const
     const float* feat = fo->feature;
     rssm::WgradMmaArgs j{};
     j.B = d->B, j.T = d->T;
-    add_seg(j, DP, dpre, DPF, DPF, RE);
+    add_seg(j, DP, dpre, DPF, 304, RE);
     add_seg(j, XLD, feat + 48, F, 32, 4, 1, in->deter_l0, 32);       // d_l_prev
     add_seg(j, XLZ, feat + 80, F, 16, 4, 1, in->stoch_l0, 16);       // z_l_prev
     add_seg(j, XLZ + 16, feat + 32, F, 16, 4, 1, in->stoch_h0, 16);  // z_h_prev
@@ -349,6 +350,19 @@ int rssm_mtrssm_wgrad(const RssmMtrssmDims* d, const RssmMtrssmInputs* in, const
     for (int i = 0; i < N_OUT; ++i)
         if (j.out[i].dW == nullptr) return fail("weight-gradient pointer of part %d is NULL", i);
     g_launches.fetch_add(1);
+    // bf16 records with the padded row lengths: slab-staged kernel (one bulk copy per source tensor and 32-row block)
+    const bool slab_ok = d->precision == RSSM_PRECISION_BF16 && aligned16(dpre) && aligned16(sv) && aligned16(feat) &&
+                         aligned16(in->embed_a) && aligned16(in->embed_v) && aligned16(in->deter_l0) && aligned16(in->deter_h0) &&
+                         aligned16(in->stoch_l0) && aligned16(in->stoch_h0) && getenv("RSSM_WGRAD_GENERIC") == nullptr;
+    if (slab_ok) {
+        rssm::WgradMtSlabArgs k{};
+        k.B = d->B, k.T = d->T, k.A = A;
+        k.dpre = static_cast<const __nv_bfloat16*>(dpre), k.saved = static_cast<const __nv_bfloat16*>(sv);
+        k.feature = feat, k.embed_a = in->embed_a, k.embed_v = in->embed_v, k.actions = in->actions;
+        k.deter_l0 = in->deter_l0, k.deter_h0 = in->deter_h0, k.stoch_l0 = in->stoch_l0, k.stoch_h0 = in->stoch_h0;
+        for (int i = 0; i < N_OUT; ++i) k.out[i] = j.out[i];
+        return check_cuda(rssm::launch_wgrad_mt_slab(k, static_cast<cudaStream_t>(stream)), "mtrssm wgrad (slab) launch");
+    }
     return check_cuda(rssm::launch_wgrad_mma(j, 0, mt_kernel_precision(d->precision), static_cast<cudaStream_t>(stream)), "mtrssm wgrad launch");
 }
 

@@ -42,8 +42,8 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t (&r)[2], const void* 
 // each, starting at staged column colX), accumulators acc[OFF .. OFF + MT*NT), bias accumulators (if BIAS) at
 // acc[OFF + MT*NT .. + MT).
 template <int NS, int MT, int NT, int OFF, bool BIAS>
-__device__ __forceinline__ void part(float (&acc)[MAX_TILES][4], const __nv_bfloat16* __restrict__ sm, int stride, int plane,
-                                     int colY, int colX, int lane) {
+__device__ __forceinline__ void part(float (&acc)[MAX_TILES][4], const __nv_bfloat16* __restrict__ smY, int strideY,
+                                     const __nv_bfloat16* __restrict__ smX, int strideX, int plane, int colY, int colX, int lane) {
     constexpr int ROWS = rows_of(NS);
     static_assert(OFF + MT * NT + (BIAS ? MT : 0) <= MAX_TILES, "too many tiles for one warp");
     const int lr = lane & 7, m8 = (lane >> 3) & 1, m16 = (lane >> 4) & 1;
@@ -56,7 +56,7 @@ __device__ __forceinline__ void part(float (&acc)[MAX_TILES][4], const __nv_bflo
         for (int s = 0; s < NS; ++s)
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
-                ldmatrix_x4_trans(a[s][mt], sm + (size_t)s * plane + (size_t)(r0 + lr + m16 * 8) * stride + colY + 16 * mt + m8 * 8);
+                ldmatrix_x4_trans(a[s][mt], smY + (size_t)s * plane + (size_t)(r0 + lr + m16 * 8) * strideY + colY + 16 * mt + m8 * 8);
         if constexpr (BIAS) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -73,7 +73,7 @@ __device__ __forceinline__ void part(float (&acc)[MAX_TILES][4], const __nv_bflo
             uint32_t b[NS][4];
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                const __nv_bfloat16* base = sm + (size_t)s * plane + (size_t)(r0 + lr + m8 * 8) * stride + colX + 16 * np;
+                const __nv_bfloat16* base = smX + (size_t)s * plane + (size_t)(r0 + lr + m8 * 8) * strideX + colX + 16 * np;
                 if (pair) {
                     ldmatrix_x4_trans(b[s], base + m16 * 8);
                 } else {
@@ -133,7 +133,7 @@ __device__ __forceinline__ void flush(const float (&acc)[MAX_TILES][4], const Wg
 // ---- per-model programs: which warp owns which parts (see the layout tables in rollout_abi.cu) ---------------------
 // MODE 0: accumulate one staged block; MODE 1: flush to global
 #define PART(MT, NT, OFF, BIAS, COLY, COLX, OUT)                                  \
-    if (MODE == 0) part<NS, MT, NT, OFF, BIAS>(acc, sm, stride, plane, COLY, COLX, lane); \
+    if (MODE == 0) part<NS, MT, NT, OFF, BIAS>(acc, sm, stride, sm, stride, plane, COLY, COLX, lane); \
     else flush<MT, NT, OFF, BIAS>(acc, outs[OUT], lane);
 
 template <int NS, int MODE>
@@ -259,7 +259,7 @@ __device__ __forceinline__ void stage_convert(__nv_bfloat16* sm, const float* ra
 template <int NS, int MODEL>
 __global__ void __launch_bounds__(THREADS, NS == 1 ? 2 : 1) wgrad_mma_kernel(const WgradMmaArgs a) {
     constexpr int ROWS = rows_of(NS);
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(smem_raw);
     const int stride = a.stride, plane = ROWS * a.stride;
     float* raw = reinterpret_cast<float*>(sm + (size_t)NS * plane);
@@ -312,7 +312,207 @@ __global__ void __launch_bounds__(THREADS, NS == 1 ? 2 : 1) wgrad_mma_kernel(con
     else program_mrssm<NS, 1>(acc, sm, stride, plane, a.out, warp, lane);
 }
 
+// =====================================================================================================================
+// MMTRSSM, bf16 path: SLAB-staged variant.
+// A block's 32 (b,t) rows are consecutive rows of every [B*T, C] tensor, so each source is ONE contiguous slab and one bulk
+// copy (5 per block instead of ~450 per-row pieces).  The slabs are DOUBLE-BUFFERED: block n+1 streams in while block n is
+// converted and multiplied, so the kernel runs at the speed of its HBM reads.  The bf16 records (dpre 608 B, saved 416 B
+// per row: whole 32-byte sectors for the kernels that write them, and 2 mod 4 sixteen-byte chunks so that ldmatrix reads
+// them in place with at most 2-way bank conflicts) are used as they land; the fp32 sources (feature rows r0-1 .. r0+31,
+// both embeddings) land in a raw area and one pass writes their bf16 operand columns (X plane); previous-step inputs of
+// rows with t == 0 come from the initial state.
+// =====================================================================================================================
+namespace slab {
+constexpr int ROWS = 32;
+constexpr int DP_LD = MTRSSM_DPRE_FLOATS, SV_LD = MTRSSM_SAVED_FLOATS, X_LD = 392;  // row pitches (bf16 elements)
+static_assert((DP_LD * 2 / 16) % 4 == 2 && (SV_LD * 2 / 16) % 4 == 2 && (X_LD * 2 / 16) % 2 == 1, "ldmatrix-friendly row pitches");
+static_assert((DP_LD * 2) % 32 == 0 && (SV_LD * 2) % 32 == 0, "record rows are whole 32-byte sectors");
+// X plane columns: ordered so that a thread converting the 4-column chunks sub, sub + 8, sub + 16, ... of one row meets one
+// source per step of its (unrolled) loop; [d_l | d_h] and [z_l_prev | z_h_prev] stay adjacent (they are one K range each)
+constexpr int XDLP = 0, XDHP = 32, XDL = 64, XDH = 96, XEA = 128, XEV = 192, XZLP = 256, XZHP = 272, XACT = 288;  // 296 columns
+// shared-memory map (bytes): X plane, then two stages of slabs
+constexpr int XP = 0, STAGE0 = ROWS * X_LD * 2;
+constexpr int DP = 0, SV = DP + ROWS * DP_LD * 2, FEAT = SV + ROWS * SV_LD * 2, EA = FEAT + (ROWS + 1) * 384, EV = EA + ROWS * 256,
+              STAGE_BYTES = EV + ROWS * 256;                 // offsets inside a stage; 61,824 bytes per stage
+#ifndef RSSM_WGRAD_STAGES
+#define RSSM_WGRAD_STAGES 2  // 2: double-buffered slabs, one CTA per SM;  1: single stage, two CTAs per SM
+#endif
+constexpr int NSTAGE = RSSM_WGRAD_STAGES;
+constexpr int BYTES = STAGE0 + NSTAGE * STAGE_BYTES;        // 148,736 with two stages
+}  // namespace slab
+
+template <int MODE>
+__device__ __forceinline__ void program_mt_slab(float (&acc)[MAX_TILES][4], const __nv_bfloat16* dp, const __nv_bfloat16* sv,
+                                                const __nv_bfloat16* xp, const WgradOut* outs, int warp, int lane) {
+    using namespace slab;
+    using namespace wgl_mt;
+    // dY columns of the dpre record (mtrssm_common.cuh, namespace mtd) and hidden columns of the saved record (mts)
+    constexpr int L = 0, H = 32, LP1 = 64, LPL = 96, HP1 = 112, HPL = 144, HQ1 = 160, HQL = 192, A1 = 208, LA = 240, V1 = 256, LV = 288;
+    constexpr int LP_HID = 0, HP_HID = 32, HQ_HID = 64, A_HID = 96, V_HID = 128;
+#define PX(MT, NT, OFF, BIAS, COLY, COLX) part<1, MT, NT, OFF, BIAS>(acc, dp, DP_LD, xp, X_LD, 0, COLY, COLX, lane)
+#define PS(MT, NT, OFF, BIAS, COLY, COLX) part<1, MT, NT, OFF, BIAS>(acc, dp, DP_LD, sv, SV_LD, 0, COLY, COLX, lane)
+#define FL(MT, NT, OFF, BIAS, OUT) flush<MT, NT, OFF, BIAS>(acc, outs[OUT], lane)
+    switch (warp) {
+        case 0:
+            if (MODE == 0) { PX(2, 4, 0, true, L, XDLP); PX(2, 4, 10, false, L, XZLP); PX(2, 1, 18, false, L, XACT); }
+            else { FL(2, 4, 0, true, O_LD); FL(2, 4, 10, false, O_LIZ); FL(2, 1, 18, false, O_LIA); }
+            break;
+        case 1:
+            if (MODE == 0) { PX(2, 4, 0, true, H, XDHP); PX(2, 2, 10, false, H, XZHP); PS(1, 4, 14, true, LPL, LP_HID); }
+            else { FL(2, 4, 0, true, O_HD); FL(2, 2, 10, false, O_HI); FL(1, 4, 14, true, O_LP2); }
+            break;
+        case 2:
+            if (MODE == 0) { PX(2, 4, 0, true, LP1, XDL); PX(2, 4, 10, true, HP1, XDH); }
+            else { FL(2, 4, 0, true, O_LP1); FL(2, 4, 10, true, O_HP1); }
+            break;
+        case 3:
+            if (MODE == 0) { PX(2, 8, 0, true, HQ1, XDL); }  // [d_l | d_h] are adjacent
+            else { FL(2, 8, 0, true, O_HQ1); }
+            break;
+        case 4:  // first layer of a modality head: tiles 0..3 = d_l half, 4..11 = embedding half, 12 = bias
+            if (MODE == 0) { PX(1, 4, 0, false, A1, XDL); PX(1, 8, 4, true, A1, XEA); PS(1, 4, 13, true, LA, A_HID); }
+            else { FL(1, 12, 0, true, O_A1A); FL(1, 4, 13, true, O_A2); }
+            break;
+        case 5:
+            if (MODE == 0) { PX(1, 4, 0, false, A1 + 16, XDL); PX(1, 8, 4, true, A1 + 16, XEA); PS(1, 4, 13, true, HPL, HP_HID); }
+            else { FL(1, 12, 0, true, O_A1B); FL(1, 4, 13, true, O_HP2); }
+            break;
+        case 6:
+            if (MODE == 0) { PX(1, 4, 0, false, V1, XDL); PX(1, 8, 4, true, V1, XEV); PS(1, 4, 13, true, LV, V_HID); }
+            else { FL(1, 12, 0, true, O_V1A); FL(1, 4, 13, true, O_V2); }
+            break;
+        default:
+            if (MODE == 0) { PX(1, 4, 0, false, V1 + 16, XDL); PX(1, 8, 4, true, V1 + 16, XEV); PS(1, 4, 13, true, HQL, HQ_HID); }
+            else { FL(1, 12, 0, true, O_V1B); FL(1, 4, 13, true, O_HQ2); }
+            break;
+    }
+#undef PX
+#undef PS
+#undef FL
+}
+
+__global__ void __launch_bounds__(THREADS, slab::NSTAGE == 2 ? 1 : 2) wgrad_mt_slab_kernel(const WgradMtSlabArgs a) {
+    using namespace slab;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(smem_raw + XP);
+    __shared__ __align__(8) uint64_t bars[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1), mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    float acc[MAX_TILES][4];
+#pragma unroll
+    for (int i = 0; i < MAX_TILES; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+    const int R = a.B * a.T, A = a.A, T = a.T;
+    const int nblocks = (R + ROWS - 1) / ROWS;
+    // one thread streams a block's five slabs into a stage
+    auto issue = [&](int blk, int stage) {
+        unsigned char* st = smem_raw + STAGE0 + stage * STAGE_BYTES;
+        const int r0 = blk * ROWS, nlive = min(ROWS, R - r0);
+        const int fslot = r0 > 0 ? 0 : 1, frow = r0 > 0 ? r0 - 1 : 0, fn = nlive + 1 - fslot;  // feature rows r0-1 .. r0+nlive-1
+        mbar_expect_tx(&bars[stage], (uint32_t)nlive * (DP_LD * 2 + SV_LD * 2 + 512) + (uint32_t)fn * 384);
+        bulk_g2s(st + DP, a.dpre + (size_t)r0 * DP_LD, nlive * DP_LD * 2, &bars[stage]);
+        bulk_g2s(st + SV, a.saved + (size_t)r0 * SV_LD, nlive * SV_LD * 2, &bars[stage]);
+        bulk_g2s(st + FEAT + fslot * 384, a.feature + (size_t)frow * 96, fn * 384, &bars[stage]);
+        bulk_g2s(st + EA, a.embed_a + (size_t)r0 * 64, nlive * 256, &bars[stage]);
+        bulk_g2s(st + EV, a.embed_v + (size_t)r0 * 64, nlive * 256, &bars[stage]);
+    };
+    if (NSTAGE == 2 && tid == 0 && (int)blockIdx.x < nblocks) issue(blockIdx.x, 0);
+    uint32_t phase0 = 0u, phase1 = 0u;
+    int stage = 0;
+    // conversion: thread -> row crow, four-column chunks csub + 8k of that row
+    const int crow = tid >> 3, csub = tid & 7;
+    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        unsigned char* st = smem_raw + STAGE0 + stage * STAGE_BYTES;
+        const __nv_bfloat16* dp = reinterpret_cast<const __nv_bfloat16*>(st + DP);
+        const __nv_bfloat16* sv = reinterpret_cast<const __nv_bfloat16*>(st + SV);
+        const float* feat = reinterpret_cast<const float*>(st + FEAT);  // slot s = row r0 - 1 + s
+        const float* ea = reinterpret_cast<const float*>(st + EA);
+        const float* ev = reinterpret_cast<const float*>(st + EV);
+        const int r0 = blk * ROWS, nlive = min(ROWS, R - r0);
+        if (NSTAGE == 2) {  // prefetch the next block into the other stage (its readers finished before the last __syncthreads)
+            if (tid == 0 && blk + (int)gridDim.x < nblocks) issue(blk + gridDim.x, stage ^ 1);
+        } else if (tid == 0) {
+            issue(blk, 0);
+        }
+        // the action columns come straight from global memory (24-byte rows): fetch before waiting on the slabs
+        float2 av0 = make_float2(0.f, 0.f), av1 = av0;
+        if (csub < 2 && crow < nlive) {
+            const float* ap = a.actions + (size_t)(r0 + crow) * A;
+            if (4 * csub < A) av0 = *reinterpret_cast<const float2*>(ap + 4 * csub);
+            if (4 * csub + 2 < A) av1 = *reinterpret_cast<const float2*>(ap + 4 * csub + 2);
+        }
+        const int r = r0 + crow, b = r / T;
+        const bool first_step = r - b * T == 0;  // t == 0: the previous state is the initial state
+        if (stage == 0) mbar_wait(&bars[0], phase0), phase0 ^= 1;
+        else mbar_wait(&bars[1], phase1), phase1 ^= 1;
+        if (nlive < ROWS)  // tail block: stale dY rows of an earlier block must not contribute
+            for (int i = tid; i < (ROWS - nlive) * DP_LD / 8; i += THREADS)
+                reinterpret_cast<uint4*>(st + DP + nlive * DP_LD * 2)[i] = make_uint4(0u, 0u, 0u, 0u);
+        // ---- fp32 -> bf16 operand columns of row crow ----------------------------------------------------------------
+        {
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 v[9];
+            const bool live = crow < nlive;
+            const float* fp = feat + crow * 96;        // row r - 1
+            const float* fc = feat + (crow + 1) * 96;  // row r
+            const int zoff = csub < 4 ? 80 + 4 * csub : 32 + 4 * (csub - 4);  // z_l_prev <- feature[80:96], z_h_prev <- feature[32:48]
+            if (live && !first_step) {
+                v[0] = *reinterpret_cast<const float4*>(fp + 48 + 4 * csub);  // d_l_prev
+                v[1] = *reinterpret_cast<const float4*>(fp + 4 * csub);       // d_h_prev
+                v[8] = *reinterpret_cast<const float4*>(fp + zoff);
+            } else if (live) {
+                v[0] = *reinterpret_cast<const float4*>(a.deter_l0 + (size_t)b * 32 + 4 * csub);
+                v[1] = *reinterpret_cast<const float4*>(a.deter_h0 + (size_t)b * 32 + 4 * csub);
+                v[8] = *reinterpret_cast<const float4*>(csub < 4 ? a.stoch_l0 + (size_t)b * 16 + 4 * csub : a.stoch_h0 + (size_t)b * 16 + 4 * (csub - 4));
+            } else {
+                v[0] = v[1] = v[8] = zero4;
+            }
+            v[2] = live ? *reinterpret_cast<const float4*>(fc + 48 + 4 * csub) : zero4;  // d_l
+            v[3] = live ? *reinterpret_cast<const float4*>(fc + 4 * csub) : zero4;       // d_h
+            v[4] = live ? *reinterpret_cast<const float4*>(ea + crow * 64 + 4 * csub) : zero4;
+            v[5] = live ? *reinterpret_cast<const float4*>(ea + crow * 64 + 32 + 4 * csub) : zero4;
+            v[6] = live ? *reinterpret_cast<const float4*>(ev + crow * 64 + 4 * csub) : zero4;
+            v[7] = live ? *reinterpret_cast<const float4*>(ev + crow * 64 + 32 + 4 * csub) : zero4;
+            __nv_bfloat16* xr = xp + crow * X_LD + 4 * csub;
+#pragma unroll
+            for (int k = 0; k < 9; ++k)
+                *reinterpret_cast<uint2*>(xr + 32 * k) = make_uint2(pack_bf16(v[k].x, v[k].y), pack_bf16(v[k].z, v[k].w));
+            if (csub < 2) *reinterpret_cast<uint2*>(xr + XACT) = make_uint2(pack_bf16(av0.x, av0.y), pack_bf16(av1.x, av1.y));
+        }
+        __syncthreads();
+        program_mt_slab<0>(acc, dp, sv, xp, a.out, warp, lane);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order our smem reads before the next bulk writes
+        __syncthreads();
+        if (NSTAGE == 2) stage ^= 1;
+    }
+    program_mt_slab<1>(acc, nullptr, nullptr, xp, a.out, warp, lane);
+}
+
 }  // namespace wg
+
+cudaError_t launch_wgrad_mt_slab(const WgradMtSlabArgs& a, cudaStream_t s) {
+    auto kernel = wg::wgrad_mt_slab_kernel;
+    const size_t smem = wg::slab::BYTES;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int per_sm = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, wg::THREADS, smem);
+    if (err != cudaSuccess) return err;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int nblocks = (a.B * a.T + wg::slab::ROWS - 1) / wg::slab::ROWS;
+    int grid = sms * (per_sm > 0 ? per_sm : 1);
+    if (grid > nblocks) grid = nblocks;
+    kernel<<<grid, wg::THREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
 
 template <int NS, int MODEL>
 static cudaError_t launch_wgrad_k(const WgradMmaArgs& a, cudaStream_t s) {
