@@ -134,7 +134,11 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
     }
 
     for (int t = 0; t < T; ++t) {
+#ifdef RSSM_EXP_STORE_L2  // timing experiment only (wrong results): all per-step stores land in an L2-resident 40 MB window
+        const size_t iA = (size_t)(r.rA & 1023) * T + t, iB = (size_t)(r.rB & 1023) * T + t;
+#else
         const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
+#endif
         RT* svA = saved ? saved + iA * p.saved_ld : nullptr;
         RT* svB = saved ? saved + iB * p.saved_ld : nullptr;
         const float* stage = stage_base + (t & 1) * stg::FLOATS;
