@@ -418,6 +418,13 @@ def main() -> None:
         what = ("fused backward kernel (BPTT + weight gradients)" if run.fused
                 else "backward = BPTT kernel + weight-gradient kernel (dominant: %s)" % dominant)
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of exactly this workload
+    # (profiles/r1_e_ncu_summary.txt); None for any other size
+    traffic = None
+    if (B, T) == (37888, 30) and precision == _lib.PRECISION_BF16:
+        traffic = 2.156e9 if dominant == "mtrssm_fwd_kernel" else 3.014e9 + 2.230e9
+    elif (B, T) == (37888, 30) and precision == _lib.PRECISION_BF16_FUSED:
+        traffic = 2.6e9 if dominant == "mtrssm_fwd_kernel" else 2.806e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -431,7 +438,7 @@ def main() -> None:
                          else "3-way bf16 split, fp32-level accuracy",
         },
         "kernel_ms": seg,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": what, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes},
         "roofline_step": {"algorithmic_bytes": STEP_BYTES_PER_BT * B * T, "achieved_gbs": STEP_BYTES_PER_BT * B * T / (ms_step * 1e-3) / 1e9,
