@@ -335,10 +335,11 @@ constexpr int XP = 0, STAGE0 = ROWS * X_LD * 2;
 constexpr int DP = 0, SV = DP + ROWS * DP_LD * 2, FEAT = SV + ROWS * SV_LD * 2, EA = FEAT + (ROWS + 1) * 384, EV = EA + ROWS * 256,
               STAGE_BYTES = EV + ROWS * 256;                 // offsets inside a stage; 61,824 bytes per stage
 #ifndef RSSM_WGRAD_STAGES
-#define RSSM_WGRAD_STAGES 2  // 2: double-buffered slabs, one CTA per SM;  1: single stage, two CTAs per SM
-#endif
+#define RSSM_WGRAD_STAGES 3  // slab stages per CTA (one CTA per SM): NSTAGE - 1 blocks (62 KB each) are in flight while one is
+#endif                       // multiplied; two stages leave the kernel latency x concurrency bound at ~4.4 TB/s
 constexpr int NSTAGE = RSSM_WGRAD_STAGES;
-constexpr int BYTES = STAGE0 + NSTAGE * STAGE_BYTES;        // 148,736 with two stages
+static_assert(NSTAGE >= 2 && NSTAGE <= 3, "2 or 3 slab stages");
+constexpr int BYTES = STAGE0 + NSTAGE * STAGE_BYTES;        // 210,560 with three stages
 }  // namespace slab
 
 template <int MODE>
@@ -391,14 +392,14 @@ __device__ __forceinline__ void program_mt_slab(float (&acc)[MAX_TILES][4], cons
 #undef FL
 }
 
-__global__ void __launch_bounds__(THREADS, slab::NSTAGE == 2 ? 1 : 2) wgrad_mt_slab_kernel(const WgradMtSlabArgs a) {
+__global__ void __launch_bounds__(THREADS, 1) wgrad_mt_slab_kernel(const WgradMtSlabArgs a) {
     using namespace slab;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(smem_raw + XP);
-    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ __align__(8) uint64_t bars[3];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        mbar_init(&bars[0], 1), mbar_init(&bars[1], 1);
+        mbar_init(&bars[0], 1), mbar_init(&bars[1], 1), mbar_init(&bars[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -422,8 +423,10 @@ __global__ void __launch_bounds__(THREADS, slab::NSTAGE == 2 ? 1 : 2) wgrad_mt_s
         bulk_g2s(st + EA, a.embed_a + (size_t)r0 * 64, nlive * 256, &bars[stage]);
         bulk_g2s(st + EV, a.embed_v + (size_t)r0 * 64, nlive * 256, &bars[stage]);
     };
-    if (NSTAGE == 2 && tid == 0 && (int)blockIdx.x < nblocks) issue(blockIdx.x, 0);
-    uint32_t phase0 = 0u, phase1 = 0u;
+    if (tid == 0)  // prologue: the first NSTAGE - 1 blocks of this CTA
+        for (int k = 0; k < NSTAGE - 1; ++k)
+            if ((int)(blockIdx.x + k * gridDim.x) < nblocks) issue(blockIdx.x + k * gridDim.x, k);
+    uint32_t phases = 0u;  // bit s = parity of stage s
     int stage = 0;
     // conversion: thread -> row crow, four-column chunks csub + 8k of that row
     const int crow = tid >> 3, csub = tid & 7;
@@ -435,10 +438,9 @@ __global__ void __launch_bounds__(THREADS, slab::NSTAGE == 2 ? 1 : 2) wgrad_mt_s
         const float* ea = reinterpret_cast<const float*>(st + EA);
         const float* ev = reinterpret_cast<const float*>(st + EV);
         const int r0 = blk * ROWS, nlive = min(ROWS, R - r0);
-        if (NSTAGE == 2) {  // prefetch the next block into the other stage (its readers finished before the last __syncthreads)
-            if (tid == 0 && blk + (int)gridDim.x < nblocks) issue(blk + gridDim.x, stage ^ 1);
-        } else if (tid == 0) {
-            issue(blk, 0);
+        {  // prefetch block n + NSTAGE - 1 into the stage block n - 1 used (its readers finished before the last __syncthreads)
+            const int nxt = blk + (NSTAGE - 1) * (int)gridDim.x, ns = stage == 0 ? NSTAGE - 1 : stage - 1;
+            if (tid == 0 && nxt < nblocks) issue(nxt, ns);
         }
         // the action columns come straight from global memory (24-byte rows): fetch before waiting on the slabs
         float2 av0 = make_float2(0.f, 0.f), av1 = av0;
@@ -449,8 +451,8 @@ __global__ void __launch_bounds__(THREADS, slab::NSTAGE == 2 ? 1 : 2) wgrad_mt_s
         }
         const int r = r0 + crow, b = r / T;
         const bool first_step = r - b * T == 0;  // t == 0: the previous state is the initial state
-        if (stage == 0) mbar_wait(&bars[0], phase0), phase0 ^= 1;
-        else mbar_wait(&bars[1], phase1), phase1 ^= 1;
+        mbar_wait(&bars[stage], (phases >> stage) & 1u);
+        phases ^= 1u << stage;
         if (nlive < ROWS)  // tail block: stale dY rows of an earlier block must not contribute
             for (int i = tid; i < (ROWS - nlive) * DP_LD / 8; i += THREADS)
                 reinterpret_cast<uint4*>(st + DP + nlive * DP_LD * 2)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(THREADS, slab::NSTAGE == 2 ? 1 : 2) wgrad_mt_s
         program_mt_slab<0>(acc, dp, sv, xp, a.out, warp, lane);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // order our smem reads before the next bulk writes
         __syncthreads();
-        if (NSTAGE == 2) stage ^= 1;
+        stage = stage + 1 == NSTAGE ? 0 : stage + 1;
     }
     program_mt_slab<1>(acc, nullptr, nullptr, xp, a.out, warp, lane);
 }
