@@ -501,6 +501,492 @@ __global__ void __launch_bounds__(128, 1) mtrssm_bwd_fused_kernel(const MtrssmBw
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
+// =====================================================================================================================
+// Version 2: TWO warps per 16-sequence tile.
+// The single-warp kernel above needs ~46 KB of shared memory per tile, i.e. four tiles = four warps per SM = one warp per
+// scheduler, and every dependent-instruction latency is exposed.  A backward step has two branches that are independent
+// given the carried gradients and join only at the two cells:
+//     "core" warp: lower prior head, higher posterior + prior heads, the two leaky-integrator cells (owns ddl ddh dul duh dzh)
+//     "mod"  warp: MoPoE-fusion backward, audio and vision heads (receives dzl, returns its contribution to ddl)
+// They share the tile's staged inputs and operand images and exchange 3 KB per step through shared memory, ordered by two
+// named barriers (X: mod -> core "my heads are done", Y: core -> mod "dzl of the next step is ready").  Same footprint per
+// tile, twice the warps per SM, and a per-step critical path of (MoPoE + two modality heads) + cells.
+// MMAs are issued by the warp that owns the operands: mod issues {[a|v hid] x [LA|LV], [embed_a|embed_v] x [A1|V1]},
+// core issues {[lp|hp|hq hid] x [LPL|HPL|HQL]} after its heads and {deter x all first layers, cells, biases} at the cells.
+// =====================================================================================================================
+namespace fz2 {
+constexpr int CH = fz::CH;
+// ---- per-TILE shared-memory map (bytes) ---------------------------------------------------------------------------------
+constexpr int DOP = 0;                      // [d_l 4][d_h 4] chunks
+constexpr int SVOP = DOP + 8 * CH;          // saved-record chunks 0..39 (core: 0..11 = lp, hp, hq hid; mod: 12..39)
+constexpr int PVOP = SVOP + 40 * CH;        // record chunks 40..55 (previous-state inputs), single buffer
+constexpr int DYOP = PVOP + 16 * CH;        // 38 chunks of dY (fz::Y_* column order)
+constexpr int DF = DYOP + 38 * CH;          // d_feature [16][112 words] (bulk, core)
+constexpr int FT = DF + 16 * bst::DF_LD * 4;   // feature[0:80] [16][80 words] (bulk, core)
+constexpr int PR = FT + 16 * bst::FT_LD * 4;   // 4 probability tensors [16][64 words] (cp.async, core)
+constexpr int PRL = PR + 16 * 64 * 4;          // post_l | prior_l [16][32 words] (cp.async, mod's own copy)
+constexpr int XDDL = PRL + 16 * 32 * 4;        // mod -> core: contribution to d deter_l   [4][32 lanes][4] fp32
+constexpr int XDZL = XDDL + 2048;              // core -> mod: d stoch_l of the next step  [2][32 lanes][4] fp32
+constexpr int BYTES = XDZL + 1024;             // 47,616
+// ---- TMEM accumulator columns ---------------------------------------------------------------------------------------
+constexpr int T_E = 0;      // [lp|hp|hq|a hid]  x [LPL|HPL|HQL]                    48 columns
+constexpr int T_M = 48;     // [a|v hid|..]      x [LA|LV]                          32
+constexpr int T_EMB = 80;   // [embed_a|embed_v] x [A1|V1]                          64
+constexpr int T_D1 = 144;   // [d_l|d_h|..]      x [HQ1|LP1|A1|V1|HP1]             160
+constexpr int T_C = 304;    // previous-state window x [L|H]                        64
+constexpr int T_B = 368;    // 3 x (dY window x [ones|..])                      3 x 16
+constexpr int T_COLS = 416;
+enum { BAR_DF, BAR_FT, BAR_E, BAR_END, BAR_M, NBAR };  // per tile
+}  // namespace fz2
+
+__device__ __forceinline__ void nbar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id) {
+    __threadfence_block();
+    asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+}
+// C tiles <-> the lane-linear fp32 exchange buffers ([tile][32 lanes][4 floats]: conflict-free 16-byte accesses)
+template <int NT>
+__device__ __forceinline__ void xch_store(const float (&c)[NT][4], float* buf, int lane) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) *reinterpret_cast<float4*>(buf + (nt * 32 + lane) * 4) = make_float4(c[nt][0], c[nt][1], c[nt][2], c[nt][3]);
+}
+template <int NT>
+__device__ __forceinline__ void xch_load(float (&c)[NT][4], const float* buf, int lane) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const float4 v = *reinterpret_cast<const float4*>(buf + (nt * 32 + lane) * 4);
+        c[nt][0] = v.x, c[nt][1] = v.y, c[nt][2] = v.z, c[nt][3] = v.w;
+    }
+}
+
+template <int KL, int KH>
+__global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmBwdArgs p, const FusedFlushTable ft) {
+    constexpr int NS = 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars_all[4][fz2::NBAR];
+    __shared__ uint32_t tmem_base_s;
+    uint2* W = reinterpret_cast<uint2*>(smem_raw);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int A = p.A;
+    {
+        using namespace mt;
+        const int ldin = A + 32;
+        pack_weight<NS, true>(wblk<NS>(W, T_A2), p.w.au_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_V2), p.w.vi_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_LP2), p.w.lp_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_HP2), p.w.hp_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_HQ2), p.w.hq_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_A1E), p.w.au_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_V1E), p.w.vi_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZL), p.w.l_in_w, ldin, 0, A, 32, 16, 2, 2, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 32, 16, 2, 2, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_H_IN), p.w.h_in_w, 16, 0, 0, 32, 16, 2, 2, tid, nthr);
+        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_A), p.w.l_in_w, ldin, 0, 0, 32, A, 2, 2, tid, nthr);
+    }
+    const int lane = tid & 31, warp = tid >> 5, tile = warp >> 1, role = warp & 1;  // role 0 = core, 1 = mod
+    unsigned char* my = smem_raw + (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + (size_t)tile * fz2::BYTES;
+    // zero the tile's images and exchange buffers once (the two warps of the tile split the range)
+    for (int i = lane + 32 * role; i < fz2::BYTES / 16; i += 64) reinterpret_cast<uint4*>(my)[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint64_t* bars = bars_all[tile];
+    if (role == 0 && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < fz2::NBAR; ++i) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    if (warp < 4) {
+        const uint32_t z = 0u;
+        for (int c = 0; c < fz2::T_COLS; c += 16)
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
+                    tmem + ((uint32_t)(32 * warp) << 16) + c),
+                "r"(z)
+                : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const int row0 = (blockIdx.x * 4 + tile) * 16;
+    if (row0 < p.B) {
+        const Rows r = make_rows(row0, p.B, lane);
+        const int T = p.T;
+        const __nv_bfloat16* saved = reinterpret_cast<const __nv_bfloat16*>(p.saved);
+        unsigned char* dop = my + fz2::DOP;
+        unsigned char* svop = my + fz2::SVOP;
+        unsigned char* pvop = my + fz2::PVOP;
+        unsigned char* dy = my + fz2::DYOP;
+        float* xddl = reinterpret_cast<float*>(my + fz2::XDDL);
+        float* xdzl = reinterpret_cast<float*>(my + fz2::XDZL);
+        const uint32_t s_dop = smem_u32(dop), s_sv = smem_u32(svop), s_dy = smem_u32(dy), s_pv = smem_u32(pvop);
+        const int bar_x = 1 + 2 * tile, bar_y = 2 + 2 * tile;
+
+        if (role == 1) {
+            // ============================== mod warp: MoPoE backward + audio / vision heads ===============================
+            float* stPRL = reinterpret_cast<float*>(my + fz2::PRL);  // [16][32]: post_l | prior_l, swizzled like PR
+            auto stage_prl = [&](int t) {
+                if (t >= 0) {
+                    const int c8 = lane & 7, rq = lane >> 3;
+                    float* d2 = stPRL + rq * 32 + 4 * (c8 ^ (4 * (rq & 1)));
+                    const float* src = (c8 >> 2) ? p.prior_probs_l : p.post_probs_l;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const size_t idx = (size_t)min(row0 + rq + 4 * j, p.B - 1) * T + t;
+                        cp_async16(d2 + j * 128, src + idx * 16 + 4 * (c8 & 3));
+                    }
+                }
+            };
+            auto stage_logits = [&](int t) {  // LA, LV: read by registers only, refilled right after the MoPoE math
+                if (t >= 0) stage_chunks(svop + 20 * fz2::CH, saved, 20, 4, row0, p.B, T, t, lane);
+                stage_prl(t);
+                cp_async_commit();
+            };
+            auto stage_rest = [&](int t) {  // a / v hiddens and both embeddings: free once this warp's MMAs have completed
+                if (t >= 0) {
+                    stage_chunks(svop + 12 * fz2::CH, saved, 12, 8, row0, p.B, T, t, lane);
+                    stage_chunks(svop + 24 * fz2::CH, saved, 24, 8, row0, p.B, T, t, lane);
+                    stage_chunks(svop + 32 * fz2::CH, saved, 32, 8, row0, p.B, T, t, lane);
+                }
+                cp_async_commit();
+            };
+            stage_logits(T - 1);
+            stage_rest(T - 1);
+            const float* dkl_src = p.d_kl_l;  // lanes t = 0 / 1 of a quad fetch rows A / B one step ahead
+            const size_t dkl_row = (size_t)((r.t & 1) ? r.rB : r.rA) * T;
+            float dkl_next = dkl_src != nullptr ? dkl_src[dkl_row + T - 1] : 0.f;
+            uint32_t ph_m = 0, ph_end = 0;
+            for (int t = T - 1; t >= 0; --t) {
+                const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
+                const float dkl_cur = dkl_next;
+                if (t > 0 && dkl_src != nullptr) dkl_next = dkl_src[dkl_row + t - 1];
+                cp_async_wait<1>();  // LA, LV, post_l, prior_l of step t have landed (the rest may still be in flight)
+                __syncwarp();
+                nbar_sync(bar_y);    // d stoch_l of step t is in XDZL
+                float dzl[2][4], q[2][4], pp[2][4], dpp[2][4];
+                xch_load<2>(dzl, xdzl, lane);
+                load_staged<2, true>(q, stPRL, 32, 0, r.g, r.t);
+                load_staged<2, true>(pp, stPRL, 32, 16, r.g, r.t);
+                add_global<2>(dzl, p.d_post_probs_l, iA * 16, iB * 16, r.t);
+                zero_c<2>(dpp);
+                if (p.d_kl_l != nullptr) {
+                    const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 0), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 1)};
+                    kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dzl, dpp);  // the prior half (dpp) belongs to the core warp
+                }
+                float dla[2][4], dlv[2][4];
+                {
+                    float dm[2][4], la[2][4], lv[2][4], lsa[2][4], lsv[2][4], mixed[2][4], ra[2][4], rv[2][4];
+                    softmax_groups_bwd<KL>(q, dzl, dm);
+                    load_op<2>(la, svop, mts::LA, r.g, r.t);
+                    load_op<2>(lv, svop, mts::LV, r.g, r.t);
+                    log_softmax_flat<true>(la, lsa);
+                    log_softmax_flat<true>(lv, lsv);
+                    mopoe_mix<true>(lsa, lsv, mixed, ra, rv);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            ra[nt][j] *= dm[nt][j];
+                            rv[nt][j] *= dm[nt][j];
+                        }
+                    log_softmax_flat_bwd<true>(lsa, ra, dla);
+                    log_softmax_flat_bwd<true>(lsv, rv, dlv);
+                }
+                __syncwarp();
+                stage_logits(t - 1);
+                // this warp's dY columns (LA, A1, LV, V1) were last read by the core warp's end-of-step MMAs of step t+1
+                if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
+                cp_async_wait<1>();  // hiddens and embeddings of step t have landed
+                __syncwarp();
+                float ddl[4][4], hid[4][4];
+                zero_c<4>(ddl);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    AFrag<NS, 2> f1;
+                    load_op<4>(hid, svop, m == 0 ? mts::A_HID : mts::V_HID, r.g, r.t);
+                    head_bwd_op(m == 0 ? dla : dlv, wblk<NS>(W, m == 0 ? mt::T_A2 : mt::T_V2), hid, dy, m == 0 ? fz::Y_LA : fz::Y_LV,
+                                m == 0 ? fz::Y_A1 : fz::Y_V1, f1, r, lane);
+                    gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, m == 0 ? mt::T_A1H : mt::T_V1H), lane);
+                    float de[8][4];
+                    zero_c<8>(de);
+                    gemm<NS, 2, 8>(de, f1, wblk<NS>(W, m == 0 ? mt::T_A1E : mt::T_V1E), lane);
+                    float* dE = m == 0 ? p.d_embed_a : p.d_embed_v;
+                    store_c<8>(de, dE + iA * 64, dE + iB * 64, r);
+                }
+                xch_store<4>(ddl, xddl, lane);
+                FZ_FENCE();
+                __syncwarp();
+                if (FZ_MMA && lane == 0) {
+                    umma_acc(tmem + fz2::T_M, s_sv + 12 * fz2::CH, s_dy + (fz::Y_LA / 8) * fz2::CH, 32);
+                    umma_acc(tmem + fz2::T_EMB, s_sv + 24 * fz2::CH, s_dy + (fz::Y_A1 / 8) * fz2::CH, 64);
+                    umma_commit(&bars[fz2::BAR_M]);
+                }
+                nbar_arrive(bar_x);  // XDDL and this warp's dY columns are complete
+                FZ_WAIT(&bars[fz2::BAR_M], ph_m), ph_m ^= 1;  // own MMAs done: hiddens / embeddings may be refilled
+                stage_rest(t - 1);
+            }
+            cp_async_wait_all();
+        } else {
+            // ============================== core warp: prior / higher heads + the two cells ===============================
+            const float keep_l = 1.f - p.inv_tau_l, keep_h = 1.f - p.inv_tau_h;
+            float* stDF = reinterpret_cast<float*>(my + fz2::DF);
+            float* stFT = reinterpret_cast<float*>(my + fz2::FT);
+            float* stPR = reinterpret_cast<float*>(my + fz2::PR) - bst::PR;  // bstage_pr adds bst::PR itself
+            uint32_t ph_df = 0, ph_ft = 0, ph_e = 0, ph_end = 0;
+            auto stage_hid = [&](int t) {  // lp, hp, hq hiddens: free once the E-group MMA has completed
+                if (t >= 0) {
+                    stage_chunks(svop, saved, 0, 8, row0, p.B, T, t, lane);
+                    stage_chunks(svop + 8 * fz2::CH, saved, 8, 4, row0, p.B, T, t, lane);
+                }
+                cp_async_commit();
+            };
+            auto stage_pv = [&](int t) {  // previous-state operand chunks: free once the end-of-step MMAs have completed
+                if (t >= 0) {
+                    stage_chunks(pvop, saved, 40, 8, row0, p.B, T, t, lane);
+                    stage_chunks(pvop + 8 * fz2::CH, saved, 48, 6, row0, p.B, T, t, lane);
+                }
+                cp_async_commit();
+            };
+            bulk_rows(stDF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, T - 1, &bars[fz2::BAR_DF], lane);
+            bulk_rows(stFT, bst::FT_LD, reinterpret_cast<const char*>(p.feature), 384, bst::FT_BYTES, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
+            bstage_pr(stPR, p, row0, T - 1, lane);  // cp.async groups per step, in issue order: PV(t) | PR(t-1) | HID(t-1)
+            stage_hid(T - 1);
+            const float* dkl_src = (r.t < 2) ? p.d_kl_h : p.d_kl_l;  // quad lanes: 0 kl_h row A, 1 kl_h row B, 2 kl_l row A, 3 kl_l row B
+            const size_t dkl_row = (size_t)((r.t & 1) ? r.rB : r.rA) * T;
+            float dkl_next = dkl_src != nullptr ? dkl_src[dkl_row + T - 1] : 0.f;
+            float ddl[4][4], ddh[4][4], dul[4][4], duh[4][4], dzh[2][4];
+            zero_c<4>(dul), zero_c<4>(duh);
+            // upstream d_feature of step T-1: d stoch_l goes to the mod warp, the rest seeds the carried gradients
+            {
+                float dzl0[2][4];
+                mbar_wait(&bars[fz2::BAR_DF], ph_df), ph_df ^= 1;
+                load_staged<4, false>(ddh, stDF, bst::DF_LD, 0, r.g, r.t);
+                load_staged<2, false>(dzh, stDF, bst::DF_LD, 32, r.g, r.t);
+                load_staged<4, false>(ddl, stDF, bst::DF_LD, 48, r.g, r.t);
+                load_staged<2, false>(dzl0, stDF, bst::DF_LD, 80, r.g, r.t);
+                xch_store<2>(dzl0, xdzl, lane);
+                nbar_arrive(bar_y);
+                __syncwarp();
+                if (T > 1)
+                    bulk_rows(stDF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, T - 2,
+                              &bars[fz2::BAR_DF], lane);
+            }
+            for (int t = T - 1; t >= 0; --t) {
+                const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
+                const float dkl_cur = dkl_next;
+                if (t > 0 && dkl_src != nullptr) dkl_next = dkl_src[dkl_row + t - 1];
+                float hid[4][4];
+                cp_async_wait_all();  // PR(t) and the hiddens of step t have landed
+                __syncwarp();
+                // the end-of-step MMAs of step t+1 are done with dY, Dop and the previous-state chunks
+                if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
+                stage_pv(t);  // needed at this step's cells
+                // ---- lower prior head -------------------------------------------------------------------------------------
+                {
+                    float q[2][4], pp[2][4], dq[2][4], dpp[2][4], dlg[2][4];
+                    load_staged<2, true>(q, stPR + bst::PR, 64, 16, r.g, r.t);
+                    load_staged<2, true>(pp, stPR + bst::PR, 64, 48, r.g, r.t);
+                    zero_c<2>(dpp), zero_c<2>(dq);
+                    add_global<2>(dpp, p.d_prior_probs_l, iA * 16, iB * 16, r.t);
+                    add_global<2>(dpp, p.d_prior_stoch_l, iA * 16, iB * 16, r.t);
+                    if (p.d_kl_l != nullptr) {
+                        const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 2), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 3)};
+                        kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dq, dpp);  // the posterior half (dq) belongs to the mod warp
+                    }
+                    AFrag<NS, 2> f1;
+                    softmax_groups_bwd<KL>(pp, dpp, dlg);
+                    load_op<4>(hid, svop, mts::LP_HID, r.g, r.t);
+                    head_bwd_op(dlg, wblk<NS>(W, mt::T_LP2), hid, dy, fz::Y_LPL, fz::Y_LP1, f1, r, lane);
+                    gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_LP1), lane);
+                }
+                // ---- higher layer: posterior + prior heads ----------------------------------------------------------------
+                {
+                    float q[2][4], pp[2][4], dpp[2][4];
+                    load_staged<2, true>(q, stPR + bst::PR, 64, 0, r.g, r.t);
+                    load_staged<2, true>(pp, stPR + bst::PR, 64, 32, r.g, r.t);
+                    __syncwarp();  // every lane is done with PR: refill it for the next (earlier) step
+                    bstage_pr(stPR, p, row0, t - 1, lane);
+                    add_global<2>(dzh, p.d_post_probs_h, iA * 16, iB * 16, r.t);
+                    zero_c<2>(dpp);
+                    add_global<2>(dpp, p.d_prior_probs_h, iA * 16, iB * 16, r.t);
+                    add_global<2>(dpp, p.d_prior_stoch_h, iA * 16, iB * 16, r.t);
+                    if (p.d_kl_h != nullptr) {
+                        const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 0), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 1)};
+                        kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dzh, dpp);
+                    }
+                    float dlg[2][4];
+                    AFrag<NS, 2> f1;
+                    softmax_groups_bwd<KH>(q, dzh, dlg);
+                    load_op<4>(hid, svop, mts::HQ_HID, r.g, r.t);
+                    head_bwd_op(dlg, wblk<NS>(W, mt::T_HQ2), hid, dy, fz::Y_HQL, fz::Y_HQ1, f1, r, lane);
+                    gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_HQ1L), lane);
+                    gemm<NS, 2, 4>(ddh, f1, wblk<NS>(W, mt::T_HQ1H), lane);
+                    softmax_groups_bwd<KH>(pp, dpp, dlg);
+                    load_op<4>(hid, svop, mts::HP_HID, r.g, r.t);
+                    head_bwd_op(dlg, wblk<NS>(W, mt::T_HP2), hid, dy, fz::Y_HPL, fz::Y_HP1, f1, r, lane);
+                    gemm<NS, 2, 4>(ddh, f1, wblk<NS>(W, mt::T_HP1), lane);
+                }
+                // second-layer weight gradients of this warp's three heads
+                FZ_FENCE();
+                __syncwarp();
+                if (FZ_MMA && lane == 0) {
+                    umma_acc(tmem + fz2::T_E, s_sv, s_dy + (fz::Y_LPL / 8) * fz2::CH, 48);
+                    umma_commit(&bars[fz2::BAR_E]);
+                }
+                // ---- the two leaky integrators --------------------------------------------------------------------------
+                float dh[4][4], dl[4][4], ph[4][4], pl[4][4];
+                mbar_wait(&bars[fz2::BAR_FT], ph_ft), ph_ft ^= 1;  // feature[0:80](t) has landed
+                load_staged<4, false>(dh, stFT, bst::FT_LD, 0, r.g, r.t);
+                load_staged<4, false>(dl, stFT, bst::FT_LD, 48, r.g, r.t);
+                __syncwarp();
+                if (t > 0)
+                    bulk_rows(stFT, bst::FT_LD, reinterpret_cast<const char*>(p.feature), 384, bst::FT_BYTES, row0, p.B, T, t - 1,
+                              &bars[fz2::BAR_FT], lane);
+                store_op<4>(dl, dop, 0, r);  // bf16 [d_l | d_h](t)
+                store_op<4>(dh, dop, 32, r);
+                FZ_WAIT(&bars[fz2::BAR_E], ph_e), ph_e ^= 1;  // the hiddens may be refilled
+                cp_async_wait<1>();                            // PV(t) has landed (PR(t-1) may still be in flight)
+                __syncwarp();
+                stage_hid(t - 1);
+                nbar_sync(bar_x);  // the mod warp's dY columns and its contribution to d deter_l are complete
+                {
+                    float c[4][4];
+                    xch_load<4>(c, xddl, lane);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ddl[nt][j] += c[nt][j];
+                }
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float gh = duh[nt][j] + ddh[nt][j] * (1.f - dh[nt][j] * dh[nt][j]);
+                        const float gl = dul[nt][j] + ddl[nt][j] * (1.f - dl[nt][j] * dl[nt][j]);
+                        ph[nt][j] = gh * p.inv_tau_h;
+                        pl[nt][j] = gl * p.inv_tau_l;
+                        duh[nt][j] = gh * keep_h;
+                        dul[nt][j] = gl * keep_l;
+                    }
+                store_op<4>(pl, dy, fz::Y_L, r);
+                store_op<4>(ph, dy, fz::Y_H, r);
+                FZ_FENCE();
+                __syncwarp();
+                if (FZ_MMA && lane == 0) {
+                    umma_acc(tmem + fz2::T_D1, s_dop, s_dy + (fz::Y_HQ1 / 8) * fz2::CH, 160);
+                    umma_acc(tmem + fz2::T_C, s_pv, s_dy + (fz::Y_L / 8) * fz2::CH, 64);
+                    umma_acc(tmem + fz2::T_B, s_dy, s_pv + 13 * fz2::CH, 16);                     // dY columns   0..127
+                    umma_acc(tmem + fz2::T_B + 16, s_dy + 16 * fz2::CH, s_pv + 13 * fz2::CH, 16);  // dY columns 128..255
+                    umma_acc(tmem + fz2::T_B + 32, s_dy + 22 * fz2::CH, s_pv + 13 * fz2::CH, 16);  // dY columns 176..303
+                    umma_commit(&bars[fz2::BAR_END]);
+                }
+                AFrag<NS, 2> fl, fh;
+                to_afrag<NS, 2>(fl, pl);
+                to_afrag<NS, 2>(fh, ph);
+                float dzl[2][4];
+                zero_c<4>(ddl), zero_c<4>(ddh), zero_c<2>(dzl), zero_c<2>(dzh);
+                gemm<NS, 2, 2>(dzl, fl, wblk<NS>(W, mt::T_L_IN_ZL), lane);
+                if (t > 0) {  // hand d stoch_l of step t-1 (+ its upstream part) to the mod warp as early as possible
+                    float g2[2][4];
+                    mbar_wait(&bars[fz2::BAR_DF], ph_df), ph_df ^= 1;  // d_feature(t-1) has landed
+                    load_staged<2, false>(g2, stDF, bst::DF_LD, 80, r.g, r.t);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dzl[nt][j] += g2[nt][j];
+                    xch_store<2>(dzl, xdzl, lane);
+                    nbar_arrive(bar_y);
+                }
+                gemm<NS, 2, 4>(ddl, fl, wblk<NS>(W, mt::T_L_D2H), lane);
+                gemm<NS, 2, 4>(ddh, fh, wblk<NS>(W, mt::T_H_D2H), lane);
+                gemm<NS, 2, 2>(dzh, fl, wblk<NS>(W, mt::T_L_IN_ZH), lane);
+                gemm<NS, 2, 2>(dzh, fh, wblk<NS>(W, mt::T_H_IN), lane);
+                if (p.d_actions != nullptr) {
+                    float da[2][4];
+                    zero_c<2>(da);
+                    gemm<NS, 2, 2>(da, fl, wblk<NS>(W, mt::T_L_IN_A), lane);
+                    store_c_partial(da, p.d_actions + iA * A, p.d_actions + iB * A, r, A);
+                }
+                if (t > 0) {  // the rest of d_feature(t-1) seeds the carried gradients of the next step
+                    float g4[4][4], g2[2][4];
+                    load_staged<4, false>(g4, stDF, bst::DF_LD, 0, r.g, r.t);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ddh[nt][j] += g4[nt][j];
+                    load_staged<2, false>(g2, stDF, bst::DF_LD, 32, r.g, r.t);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dzh[nt][j] += g2[nt][j];
+                    load_staged<4, false>(g4, stDF, bst::DF_LD, 48, r.g, r.t);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ddl[nt][j] += g4[nt][j];
+                    __syncwarp();
+                    if (t > 1)
+                        bulk_rows(stDF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, t - 2,
+                                  &bars[fz2::BAR_DF], lane);
+                } else {  // t == 0: the gradients w.r.t. the initial state
+                    store_c<4>(ddh, p.d_deter_h0 + (size_t)r.rA * 32, p.d_deter_h0 + (size_t)r.rB * 32, r);
+                    store_c<4>(ddl, p.d_deter_l0 + (size_t)r.rA * 32, p.d_deter_l0 + (size_t)r.rB * 32, r);
+                    store_c<4>(duh, p.d_hidden_h0 + (size_t)r.rA * 32, p.d_hidden_h0 + (size_t)r.rB * 32, r);
+                    store_c<4>(dul, p.d_hidden_l0 + (size_t)r.rA * 32, p.d_hidden_l0 + (size_t)r.rB * 32, r);
+                    store_c<2>(dzh, p.d_stoch_h0 + (size_t)r.rA * 16, p.d_stoch_h0 + (size_t)r.rB * 16, r);
+                    store_c<2>(dzl, p.d_stoch_l0 + (size_t)r.rA * 16, p.d_stoch_l0 + (size_t)r.rB * 16, r);
+                }
+            }
+            FZ_WAIT(&bars[fz2::BAR_END], ph_end);
+            cp_async_wait_all();
+        }
+    }
+    // ---- epilogue: TMEM accumulators -> global weight gradients (one atomicAdd per element per CTA) -----------------------
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp < 4) {
+        const int L = 32 * warp + lane;  // TMEM lane read by this thread
+        for (int i = 0; i < ft.n; ++i) {
+            const FusedFlush f = ft.e[i];
+            if (f.lane0 + f.nlanes <= 32 * warp || f.lane0 >= 32 * warp + 32) continue;  // warp-uniform
+            for (int c0 = 0; c0 < f.ncols; c0 += 16) {
+                uint32_t v[16];
+                const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16) + f.tcol + c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (L >= f.lane0 && L < f.lane0 + f.nlanes) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < f.ncols) atomicAdd(f.dst + (size_t)(c0 + j) * f.ld + (L - f.lane0) + f.koff, __uint_as_float(v[j]));
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
 // ---- host side: which TMEM block goes where ------------------------------------------------------------------------------
 static void add_flush(FusedFlushTable& t, float* dst, int tcol, int ncols, int lane0, int nlanes, int ld, int koff) {
     if (dst == nullptr || nlanes <= 0) return;
@@ -550,21 +1036,63 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
     add_flush(t, g.h_d2h_b, T_B + 32, 1, Y_H - 176, 32, 0, 0);
     add_flush(t, g.h_in_b, T_B + 32, 1, Y_H - 176, 32, 0, 0);
 
-    const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + 4 * (size_t)fz::BYTES;
-    auto launch = [&](auto kernel) -> cudaError_t {
+    // ---- version 2 (two warps per tile): same blocks, its own TMEM column map ---------------------------------------------------
+    FusedFlushTable u{};
+    {
+        namespace z = fz2;
+        add_flush(u, g.lp_w2, z::T_E + 0, 16, 0, 32, 32, 0);
+        add_flush(u, g.hp_w2, z::T_E + 16, 16, 32, 32, 32, 0);
+        add_flush(u, g.hq_w2, z::T_E + 32, 16, 64, 32, 32, 0);
+        add_flush(u, g.au_w2, z::T_M + 0, 16, 0, 32, 32, 0);
+        add_flush(u, g.vi_w2, z::T_M + 16, 16, 32, 32, 32, 0);
+        add_flush(u, g.au_w1, z::T_EMB + 0, 32, 0, 64, 96, 32);
+        add_flush(u, g.vi_w1, z::T_EMB + 32, 32, 64, 64, 96, 32);
+        add_flush(u, g.hq_w1, z::T_D1 + 0, 32, 0, 64, 64, 0);
+        add_flush(u, g.lp_w1, z::T_D1 + 32, 32, 0, 32, 32, 0);
+        add_flush(u, g.au_w1, z::T_D1 + 64, 32, 0, 32, 96, 0);
+        add_flush(u, g.vi_w1, z::T_D1 + 96, 32, 0, 32, 96, 0);
+        add_flush(u, g.hp_w1, z::T_D1 + 128, 32, 32, 32, 32, 0);
+        add_flush(u, g.l_d2h_w, z::T_C + 0, 32, 0, 32, 32, 0);
+        add_flush(u, g.h_d2h_w, z::T_C + 32, 32, 32, 32, 32, 0);
+        add_flush(u, g.l_in_w, z::T_C + 0, 32, 64, 32, LDIN, A);
+        add_flush(u, g.h_in_w, z::T_C + 32, 32, 80, 16, 16, 0);
+        add_flush(u, g.l_in_w, z::T_C + 0, 32, 96, A, LDIN, 0);
+        add_flush(u, g.lp_b2, z::T_B, 1, Y_LPL, 16, 0, 0);
+        add_flush(u, g.hp_b2, z::T_B, 1, Y_HPL, 16, 0, 0);
+        add_flush(u, g.hq_b2, z::T_B, 1, Y_HQL, 16, 0, 0);
+        add_flush(u, g.au_b2, z::T_B, 1, Y_LA, 16, 0, 0);
+        add_flush(u, g.vi_b2, z::T_B, 1, Y_LV, 16, 0, 0);
+        add_flush(u, g.hq_b1, z::T_B, 1, Y_HQ1, 32, 0, 0);
+        add_flush(u, g.lp_b1, z::T_B, 1, Y_LP1, 16, 0, 0);
+        add_flush(u, g.lp_b1, z::T_B + 16, 1, 0, 16, 0, 16);
+        add_flush(u, g.au_b1, z::T_B + 16, 1, Y_A1 - 128, 32, 0, 0);
+        add_flush(u, g.vi_b1, z::T_B + 16, 1, Y_V1 - 128, 32, 0, 0);
+        add_flush(u, g.hp_b1, z::T_B + 16, 1, Y_HP1 - 128, 32, 0, 0);
+        add_flush(u, g.l_d2h_b, z::T_B + 32, 1, Y_L - 176, 32, 0, 0);
+        add_flush(u, g.l_in_b, z::T_B + 32, 1, Y_L - 176, 32, 0, 0);
+        add_flush(u, g.h_d2h_b, z::T_B + 32, 1, Y_H - 176, 32, 0, 0);
+        add_flush(u, g.h_in_b, z::T_B + 32, 1, Y_H - 176, 32, 0, 0);
+    }
+    const bool v1 = getenv("RSSM_FUSED_V1") != nullptr;  // the single-warp-per-tile kernel, kept for comparison
+    const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + 4 * (size_t)(v1 ? fz::BYTES : fz2::BYTES);
+    auto launch = [&](auto kernel, const FusedFlushTable& tab, int threads) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        const int warps = (a.B + 15) / 16, ctas = (warps + 3) / 4;
-        kernel<<<ctas, 128, smem, s>>>(a, t);
+        const int tiles = (a.B + 15) / 16, ctas = (tiles + 3) / 4;
+        kernel<<<ctas, threads, smem, s>>>(a, tab);
         return cudaGetLastError();
     };
-    if (a.KL == 4 && a.KH == 2) return launch(mtrssm_bwd_fused_kernel<4, 2>);
+#define FUSED_DISPATCH(KLv, KHv)                                                           \
+    if (a.KL == KLv && a.KH == KHv)                                                        \
+        return v1 ? launch(mtrssm_bwd_fused_kernel<KLv, KHv>, t, 128) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv>, u, 256);
+    FUSED_DISPATCH(4, 2)
 #ifndef RSSM_EXP_ONLY_DEFAULT
-    if (a.KL == 4 && a.KH == 4) return launch(mtrssm_bwd_fused_kernel<4, 4>);
-    if (a.KL == 2 && a.KH == 2) return launch(mtrssm_bwd_fused_kernel<2, 2>);
-    if (a.KL == 8 && a.KH == 8) return launch(mtrssm_bwd_fused_kernel<8, 8>);
-    if (a.KL == 16 && a.KH == 16) return launch(mtrssm_bwd_fused_kernel<16, 16>);
+    FUSED_DISPATCH(4, 4)
+    FUSED_DISPATCH(2, 2)
+    FUSED_DISPATCH(8, 8)
+    FUSED_DISPATCH(16, 16)
 #endif
+#undef FUSED_DISPATCH
     return cudaErrorInvalidValue;
 }
 
