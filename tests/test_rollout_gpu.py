@@ -370,14 +370,17 @@ def test_mtrssm_bf16_teacher_forced(ops):
     rep.finish()
 
 
-@pytest.mark.parametrize("B,T", [(37, 9), (200, 12), (16, 1)])
-def test_mtrssm_bf16_fused_backward_matches_two_kernel_backward(ops, B, T):
+@pytest.mark.parametrize("B,T,dims", [
+    (37, 9, H.MT_DIMS), (200, 12, H.MT_DIMS), (16, 1, H.MT_DIMS), (1, 3, H.MT_DIMS),
+    (70, 5, dict(CL=4, KL=4, CH=4, KH=4, l_tau=1.5, h_tau=8.0)),
+    (33, 4, dict(CL=8, KL=2, CH=8, KH=2, l_tau=2.0, h_tau=3.0)),
+])
+def test_mtrssm_bf16_fused_backward_matches_two_kernel_backward(ops, B, T, dims):
     """RSSM_PRECISION_BF16_FUSED (BPTT + weight gradients in one kernel, tcgen05 / TMEM accumulators) against
     RSSM_PRECISION_BF16 (BPTT kernel + mma.sync weight-gradient kernel): the forward is bit-identical, the data gradients run
     the same arithmetic up to the fp32 summation order and the bf16 operand roundings that order can flip (4e-3 of scale, data
     gradients; 2e-3 of scale, weight gradients)."""
     R, P = ops
-    dims = H.MT_DIMS
     params = H.make_params(H.MT_SHAPES)
     inp = H.mtrssm_inputs(B, T, dims)
     up = mtrssm_upstream(B, T, dims)
@@ -385,7 +388,7 @@ def test_mtrssm_bf16_fused_backward_matches_two_kernel_backward(ops, B, T):
     o2, w2, x2 = run_mtrssm(R, P, params, inp, dims, precision=2, grad=True, upstream=up)
     for k in ("feature", *MT_FWD_KEYS):
         assert torch.equal(o1[k], o2[k]), k
-    rep = H.Report(f"mtrssm bf16 fused vs two-kernel backward B={B} T={T}")
+    rep = H.Report(f"mtrssm bf16 fused vs two-kernel backward B={B} T={T} {dims}")
     # same arithmetic, but the two-warp fused kernel sums the d deter_l contributions in another order: an fp32 ulp can flip
     # the bf16 rounding (2^-9) of an MMA operand downstream, so the paths agree to a few bf16 ulps, not bit for bit
     for k in MT_GRAD_IN:
