@@ -371,7 +371,7 @@ def test_mtrssm_bf16_teacher_forced(ops):
 
 
 @pytest.mark.parametrize("B,T,dims", [
-    (37, 9, H.MT_DIMS), (200, 12, H.MT_DIMS), (16, 1, H.MT_DIMS), (1, 3, H.MT_DIMS),
+    (37, 9, H.MT_DIMS), (200, 12, H.MT_DIMS), (16, 1, H.MT_DIMS), (1, 3, H.MT_DIMS), (20, 131, H.MT_DIMS),
     (70, 5, dict(CL=4, KL=4, CH=4, KH=4, l_tau=1.5, h_tau=8.0)),
     (33, 4, dict(CL=8, KL=2, CH=8, KH=2, l_tau=2.0, h_tau=3.0)),
 ])
