@@ -270,6 +270,46 @@ def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int
                     "PCIe-bound"}
 
 
+def time_train_step(B: int, T: int, world: int, device: torch.device, autocast: bool, iters: int = 10) -> dict:
+    """BASELINE.json's second metric, train sequences/s: one full training step of MoPoE-MMTRSSM built from the reference's
+    default.yaml through this package's drop-in classes -- CNN encoders (stand-ins for the absent `cnn` package), initial
+    state, fused rollout, decoders, Gaussian likelihood + KL, backward, flat-bucket gradient allreduce (N > 1), clip, AdamW.
+    B sequences per GPU of synthetic audio / vision frames [B,T,1,32,32] ~ U(-1,1)."""
+    from multimodal_mtrssm_b200 import compat, dp, standins, synthetic
+
+    model = compat.load_model(ROOT / "multimodal_mtrssm_b200" / "configs" / "mopoe_mmtrssm_default.yaml")
+    standins.materialize(model, model.feature_dim)
+    model.to(device).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    bucket = dp.FlatGradBucket(model.parameters())
+    g = torch.Generator().manual_seed(1234)
+    frames = lambda: (torch.rand(B, T, 1, 32, 32, generator=g) * 2 - 1).to(device)  # noqa: E731
+    act = synthetic.actions(B, T, g).to(device)
+    batch = (act, frames(), frames(), act.clone(), frames(), frames())
+
+    def step() -> None:
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            dp.train_step(model, batch, opt, bucket)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(iters):
+        step()
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / iters
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    return {"B_per_gpu": B, "T": T, "autocast_bf16": autocast, "ms_per_step": ms, "train_seq_per_sec": world * B / (ms * 1e-3)}
+
+
 # ---------------------------------------------------------------------------------------------------
 # CPU legs (the ONLY place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------------
@@ -368,6 +408,11 @@ def main() -> None:
     clocks = sampler.stop() if sampler else None
 
     extras = {}
+    if not args.no_extras:  # every rank takes part (gradient allreduce inside)
+        train = [time_train_step(b_, T, world, device, ac) for b_, ac in ((8, True), (256, True), (256, False))]
+        if rank == 0:
+            extras["train_step"] = {"metric": "train sequences/s (full MoPoE-MMTRSSM training step, default.yaml model)",
+                                    "runs": train}
     if rank == 0 and not args.no_extras:
         n2 = max(3, args.steps // 2)
         for name, prec in (("fp32_path", _lib.PRECISION_FP32), ("bf16_path", _lib.PRECISION_BF16),
