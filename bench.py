@@ -10,9 +10,9 @@ and noise.  default.yaml's batch of 8 cannot occupy a GPU, so the per-GPU batch 
 two full waves of the kernels' 16-sequence warp tiles; weak scaling: every rank processes its own 37888).  The B=8
 latency (`default_batch8`) and B = 256 / 4096 / 16384 and cfg4 (`other_workloads`) are reported beside it.
 
-A step = one pass of the hot path over one batch: forward rollout kernel + fused backward kernel (BPTT and the weight
-gradients on tcgen05 / TMEM in one launch; the fp32-parity path runs a BPTT kernel + a weight-gradient kernel instead)
-(+ one NCCL allreduce of the flat weight-gradient bucket when N > 1).  `value` has the inputs resident in
+A step = one pass of the hot path over one batch: the forward rollout kernel + the fused backward kernel (BPTT and the weight
+gradients -- tcgen05 MMAs with TMEM accumulators -- in one launch; `--precision bf16` runs the two-kernel backward, `--precision
+fp32` the fp32-parity path) (+ one NCCL allreduce of the flat weight-gradient bucket when N > 1).  `value` has the inputs resident in
 HBM; `e2e` goes through the public API (`rollout_ops.mtrssm_rollout` + autograd) with pinned-host inputs copied
 in and the loss + weight gradients copied out every step.  One JSON line on stdout (rank 0).
 """
@@ -50,7 +50,8 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=37888, help="sequences per GPU (default 148 SMs x 256 = two full waves of 16-sequence warp tiles)")
     ap.add_argument("--seq-len", type=int, default=30)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16_fused", "fp32"])
+    ap.add_argument("--precision", default="bf16_fused", choices=["bf16", "bf16_fused", "fp32"],
+                    help="bf16_fused: bf16 path, one-kernel backward (default); bf16: bf16 path, BPTT kernel + weight-gradient kernel")
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp32-path / B=8 side measurements")
@@ -415,7 +416,7 @@ def main() -> None:
                                     "runs": train}
     if rank == 0 and not args.no_extras:
         n2 = max(3, args.steps // 2)
-        for name, prec in (("fp32_path", _lib.PRECISION_FP32), ("bf16_path", _lib.PRECISION_BF16),
+        for name, prec in (("fp32_path", _lib.PRECISION_FP32), ("bf16_two_kernel_backward_path", _lib.PRECISION_BF16),
                            ("bf16_fused_backward_path", _lib.PRECISION_BF16_FUSED)):
             if prec == precision:
                 continue

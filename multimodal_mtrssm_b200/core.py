@@ -80,9 +80,11 @@ class BaseRSSM(_Base):
     def _precision(self) -> int:
         from . import _lib
 
+        # the bf16 tensor-core path of this model family (MoPoE-MMTRSSM overrides it with the fused-backward policy)
+        bf16 = getattr(self, "_BF16_POLICY", _lib.PRECISION_BF16)
         if self.rollout_precision is not None:
-            return {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[self.rollout_precision]
-        return _lib.PRECISION_BF16 if torch.is_autocast_enabled() else _lib.PRECISION_FP32
+            return {"fp32": _lib.PRECISION_FP32, "bf16": bf16, "bf16_two_kernel": _lib.PRECISION_BF16}[self.rollout_precision]
+        return bf16 if torch.is_autocast_enabled() else _lib.PRECISION_FP32
 
     # ---- reference API ----------------------------------------------------------------------------------------------
     def initial_state(self, observation) -> State:  # noqa: ANN001

@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    const int row0 = (blockIdx.x * 4 + tile) * 16;
+    const int row0 = (blockIdx.x * (nthr >> 6) + tile) * 16;  // 2 or 4 tiles (4 or 8 warps) per CTA
     if (row0 < p.B) {
         const Rows r = make_rows(row0, p.B, lane);
         const int T = p.T;
@@ -1074,17 +1074,19 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
         add_flush(u, g.h_in_b, z::T_B + 32, 1, Y_H - 176, 32, 0, 0);
     }
     const bool v1 = getenv("RSSM_FUSED_V1") != nullptr;  // the single-warp-per-tile kernel, kept for comparison
-    const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + 4 * (size_t)(v1 ? fz::BYTES : fz2::BYTES);
+    // tiles per CTA: 4 fill an SM's shared memory; small batches use 2 (the TMEM read-back needs four warps) to reach more SMs
+    const int tiles = (a.B + 15) / 16, tpc = (v1 || tiles > 2 * 148) ? 4 : 2;
+    const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + tpc * (size_t)(v1 ? fz::BYTES : fz2::BYTES);
     auto launch = [&](auto kernel, const FusedFlushTable& tab, int threads) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        const int tiles = (a.B + 15) / 16, ctas = (tiles + 3) / 4;
+        const int ctas = (tiles + tpc - 1) / tpc;
         kernel<<<ctas, threads, smem, s>>>(a, tab);
         return cudaGetLastError();
     };
 #define FUSED_DISPATCH(KLv, KHv)                                                           \
     if (a.KL == KLv && a.KH == KHv)                                                        \
-        return v1 ? launch(mtrssm_bwd_fused_kernel<KLv, KHv>, t, 128) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv>, u, 256);
+        return v1 ? launch(mtrssm_bwd_fused_kernel<KLv, KHv>, t, 128) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv>, u, 64 * tpc);
     FUSED_DISPATCH(4, 2)
 #ifndef RSSM_EXP_ONLY_DEFAULT
     FUSED_DISPATCH(4, 4)

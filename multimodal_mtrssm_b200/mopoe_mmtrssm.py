@@ -40,6 +40,10 @@ class MTRNN(nn.Module):
 class MoPoE_MMTRSSM(MoPoE_MRSSM):  # noqa: N801
     """MoPoE-MRSSM with a two-level (fast lower / slow higher) multi-timescale latent hierarchy."""
 
+    # bf16 path of this model: one-kernel backward (BPTT + weight gradients on tcgen05 / TMEM), never slower than the
+    # two-kernel backward at any batch size measured (DESIGN.md section 5); "bf16_two_kernel" selects the latter
+    _BF16_POLICY = 2  # _lib.PRECISION_BF16_FUSED
+
     def __init__(  # noqa: PLR0913
         self,
         *,

@@ -142,7 +142,11 @@ def test_autocast_selects_the_bf16_path_and_training_reduces_the_loss():
     model = H.build_mtrssm_model().cuda()
     assert model._precision() == _lib.PRECISION_FP32
     with torch.autocast("cuda", dtype=torch.bfloat16):
-        assert model._precision() == _lib.PRECISION_BF16
+        assert model._precision() == _lib.PRECISION_BF16_FUSED  # MMTRSSM: bf16 path with the fused (tcgen05) backward
+    model.rollout_precision = "bf16_two_kernel"
+    assert model._precision() == _lib.PRECISION_BF16
+    model.rollout_precision = "bf16"
+    assert model._precision() == _lib.PRECISION_BF16_FUSED
     B, T = 32, 12
     g = torch.Generator().manual_seed(1)
     obs = torch.rand(B, T, 1, 32, 32, generator=g).cuda() * 2 - 1
