@@ -271,6 +271,37 @@ def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int
                     "PCIe-bound"}
 
 
+def time_mrssm(B: int, T: int, precision: int, device: torch.device, iters: int = 10) -> dict:
+    """MoPoE-MRSSM (GRU transition; default.yaml sizes: the cfg1 model) rollout fwd+bwd through the public op API
+    (`rollout_ops.mrssm_rollout` + autograd: forward kernel, BPTT kernel, weight-gradient kernel, torch allocations)."""
+    from multimodal_mtrssm_b200 import rollout_ops as R
+    from multimodal_mtrssm_b200 import synthetic
+    from multimodal_mtrssm_b200.params import mrssm_weight_list
+
+    weights = mrssm_weight_list({k: v.to(device).requires_grad_(True) for k, v in synthetic.mrssm_params().items()})
+    inp = {k: v.to(device) for k, v in synthetic.mrssm_batch(B, T).items()}
+    g = torch.Generator().manual_seed(7)
+    readout = torch.randn(48, generator=g).to(device)
+
+    def step() -> None:
+        out = R.mrssm_rollout(weights, precision=precision, **inp)
+        loss = (out["feature"] @ readout).sum() + out["kl"].mean()
+        torch.autograd.grad(loss, weights)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(iters):
+        step()
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / iters
+    return {"workload": f"cfg1 model (MoPoE-MRSSM default.yaml sizes) B={B}", "B": B, "T": T, "ms_per_step": ms,
+            "value": B * T / (ms * 1e-3), "via": "public op API (incl. torch allocations and the loss)"}
+
+
 def time_train_step(B: int, T: int, world: int, device: torch.device, autocast: bool, iters: int = 10) -> dict:
     """BASELINE.json's second metric, train sequences/s: one full training step of MoPoE-MMTRSSM built from the reference's
     default.yaml through this package's drop-in classes -- CNN encoders (stand-ins for the absent `cnn` package), initial
@@ -438,6 +469,8 @@ def main() -> None:
                                               "ms_per_step": rr["total_ms"] / 10,
                                               "frac_of_hbm": STEP_BYTES_PER_BT * b_ * t_ / (rr["total_ms"] / 10 * 1e-3) / 1e9 / 6464.9})
             del w
+        mr_prec = _lib.PRECISION_FP32 if precision == _lib.PRECISION_FP32 else _lib.PRECISION_BF16
+        extras["mrssm_workloads"] = [time_mrssm(8, T, mr_prec, device), time_mrssm(16384, T, mr_prec, device)]
     if world > 1:
         import torch.distributed as dist
 
