@@ -53,10 +53,10 @@ extern "C" {
 #define MRSSM_DPRE_FLOATS 336
 #define MTRSSM_SAVED_FLOATS 208 /* 192 used; bf16 rows of 416 bytes: whole 32-byte sectors, and a row pitch that lets the  */
 #define MTRSSM_DPRE_FLOATS 304  /* weight-gradient kernel read bulk-copied 32-row slabs with ldmatrix in place              */
-/* With RSSM_PRECISION_BF16_FUSED the MMTRSSM saved record is [B,T,MTRSSM_SAVED_BF16] bf16: the 192 elements above followed by
-   bf16 copies of the step's inputs (both embeddings, the previous deter / stoch of both levels, the action, a ones column)
-   -- the operands of the weight-gradient contractions that the fused backward runs on the tcgen05 tensor cores. */
-#define MTRSSM_SAVED_BF16 448
+/* With RSSM_PRECISION_BF16_FUSED the MMTRSSM saved record is [B,T,MTRSSM_SAVED_BF16] bf16: the MTRSSM_SAVED_FLOATS elements
+   above followed by bf16 copies of the step's recurrent inputs (previous deter / stoch of both levels, the action, a ones
+   column) -- X operands of the weight-gradient contractions that the fused backward runs on the tcgen05 tensor cores. */
+#define MTRSSM_SAVED_BF16 336
 
 /* ---- MoPoE-MRSSM -------------------------------------------------------------------------------------- */
 typedef struct {

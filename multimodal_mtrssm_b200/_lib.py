@@ -20,7 +20,7 @@ PRECISION_BF16_FUSED = 2  # bf16 path with the one-kernel backward (tcgen05 weig
 ABI_VERSION = 1
 MRSSM_SAVED_FLOATS, MRSSM_DPRE_FLOATS = 320, 336
 MTRSSM_SAVED_FLOATS, MTRSSM_DPRE_FLOATS = 208, 304
-MTRSSM_SAVED_BF16 = 448
+MTRSSM_SAVED_BF16 = 336
 
 _fp = C.c_void_p  # device pointers travel as integers
 

@@ -51,6 +51,7 @@ struct MtrssmBwdArgs {
     float inv_tau_l, inv_tau_h, kl_wq, kl_wp;
     RssmMtrssmWeights w;
     const float *feature, *prior_probs_h, *prior_probs_l, *post_probs_h, *post_probs_l;
+    const float *embed_a, *embed_v;  // forward inputs (read by the fused backward only: X operands of the modality heads)
     const void* saved;
     int saved_ld;  // elements per (b,t) row of `saved`
     const float *d_feature, *d_prior_probs_h, *d_prior_probs_l, *d_post_probs_h, *d_post_probs_l;

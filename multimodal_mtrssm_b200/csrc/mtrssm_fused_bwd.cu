@@ -42,29 +42,10 @@ namespace rssm {
 
 namespace fz {
 constexpr int CH = 256;  // bytes of one operand chunk (8 columns x 16 rows, bf16)
-// ---- per-warp shared-memory map (bytes) ---------------------------------------------------------------------------
-constexpr int DOP = 0;                     // [d_l 4][d_h 4] chunks: bf16 copies of this step's deter (converted from FT)
-constexpr int SVOP = DOP + 8 * CH;         // saved-record chunks 0..39: hids 20 | LA, LV 4 | embed_a 8 | embed_v 8
-constexpr int PVOP = SVOP + 40 * CH;       // 2 x record chunks 40..55: d_l_prev 4 | d_h_prev 4 | z_l_prev 2 | z_h_prev 2 | act 1 | ones 1 | pad 2
-constexpr int DYOP = PVOP + 2 * 16 * CH;   // 38 chunks of dY (column order below)
-constexpr int DF = DYOP + 38 * CH;         // fp32 staging: d_feature [16][112 words] (bulk)
-constexpr int FT = DF + 16 * bst::DF_LD * 4;  // feature[0:80] [16][80 words] (bulk)
-constexpr int PR = FT + 16 * bst::FT_LD * 4;  // 4 probability tensors [16][64 words] (cp.async, swizzled)
-constexpr int BYTES = PR + 16 * 64 * 4;       // 46592
 // ---- dY column order (elements); every MMA's N window is one contiguous run ----------------------------------------
 constexpr int Y_LPL = 0, Y_HPL = 16, Y_HQL = 32, Y_LA = 48, Y_LV = 64;            // second-layer (logit) gradients
 constexpr int Y_HQ1 = 80, Y_LP1 = 112, Y_A1 = 144, Y_V1 = 176, Y_HP1 = 208;       // first-layer pre-activation gradients
 constexpr int Y_L = 240, Y_H = 272;                                                // the two MTRNN cells
-// ---- TMEM accumulator columns ---------------------------------------------------------------------------------------
-constexpr int T_E1 = 0;      // [lp|hp|hq|a hid] x [HPL|HQL]                         32 columns
-constexpr int T_L2 = 32;     // [lp|hp|hq|a hid] x [LPL|HPL|HQL|LA]                  64
-constexpr int T_L2V = 96;    // [v hid|..]       x [LV]                              16
-constexpr int T_EMB = 112;   // [embed_a|embed_v] x [A1|V1]                          64
-constexpr int T_D1 = 176;    // [d_l|d_h|..]     x [HQ1|LP1|A1|V1|HP1]              160
-constexpr int T_C = 336;     // [d_l_prev|d_h_prev|z_l_prev|z_h_prev|act|ones|..] x [L|H]   64
-constexpr int T_B = 400;     // 3 x (dY window x [ones|..]) : column 0 = bias gradients      3 x 16
-constexpr int T_COLS = 448;
-enum { BAR_DF, BAR_FT, BAR_E, BAR_L, BAR_END, NBAR };
 }  // namespace fz
 
 // one (lane range, column range) block of a TMEM accumulator tile -> global weight gradient
@@ -155,352 +136,6 @@ __device__ __forceinline__ void head_bwd_op(const float (&dlogit)[2][4], const u
     to_afrag<1, 2>(f1, dhid);
 }
 
-template <int KL, int KH>
-__global__ void __launch_bounds__(128, 1) mtrssm_bwd_fused_kernel(const MtrssmBwdArgs p, const FusedFlushTable ft) {
-    constexpr int NS = 1;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bars_all[4][fz::NBAR];
-    __shared__ uint32_t tmem_base_s;
-    uint2* W = reinterpret_cast<uint2*>(smem_raw);
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int A = p.A;
-    {
-        using namespace mt;
-        const int ldin = A + 32;
-        pack_weight<NS, true>(wblk<NS>(W, T_A2), p.w.au_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_V2), p.w.vi_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_LP2), p.w.lp_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HP2), p.w.hp_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HQ2), p.w.hq_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_A1E), p.w.au_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_V1E), p.w.vi_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZL), p.w.l_in_w, ldin, 0, A, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_H_IN), p.w.h_in_w, 16, 0, 0, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_A), p.w.l_in_w, ldin, 0, 0, 32, A, 2, 2, tid, nthr);
-    }
-    const int lane = tid & 31, warp = tid >> 5;
-    unsigned char* my = smem_raw + (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + (size_t)warp * fz::BYTES;
-    // zero this warp's operand images once: pad chunks / junk rows of the MMA windows then hold finite values
-    for (int i = lane; i < fz::DF / 16; i += 32) reinterpret_cast<uint4*>(my)[i] = make_uint4(0u, 0u, 0u, 0u);
-    uint64_t* bars = bars_all[warp];
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < fz::NBAR; ++i) mbar_init(&bars[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // ---- TMEM: warp 0 allocates all 512 columns (one CTA per SM by shared-memory footprint); everybody zeroes its lanes ----
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmem_base_s;
-    {
-        const uint32_t z = 0u;
-        for (int c = 0; c < fz::T_COLS; c += 16)
-            asm volatile(
-                "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(
-                    tmem + ((uint32_t)(32 * warp) << 16) + c),
-                "r"(z)
-                : "memory");
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    const int row0 = (blockIdx.x * (nthr >> 5) + warp) * 16;
-    if (row0 < p.B) {
-        const Rows r = make_rows(row0, p.B, lane);
-        const int T = p.T;
-        const float keep_l = 1.f - p.inv_tau_l, keep_h = 1.f - p.inv_tau_h;
-        const __nv_bfloat16* saved = reinterpret_cast<const __nv_bfloat16*>(p.saved);
-        unsigned char* dop = my + fz::DOP;
-        unsigned char* svop = my + fz::SVOP;
-        unsigned char* dy = my + fz::DYOP;
-        float* stDF = reinterpret_cast<float*>(my + fz::DF);
-        float* stFT = reinterpret_cast<float*>(my + fz::FT);
-        float* stPR = reinterpret_cast<float*>(my + fz::PR) - bst::PR;  // bstage_pr / load_staged add bst::PR themselves
-        const uint32_t s_dop = smem_u32(dop), s_sv = smem_u32(svop), s_dy = smem_u32(dy), s_pv = smem_u32(my + fz::PVOP);
-        uint32_t ph_df = 0, ph_ft = 0, ph_e = 0, ph_l = 0, ph_end = 0;
-
-        // cp.async groups, in issue order per step: PR(t-1) | EARLY(t-1) = hp, hq hid + LA, LV + previous-state chunks | LATE(t-1)
-        auto stage_early = [&](int t) {
-            if (t >= 0) {
-                stage_chunks(svop + 4 * fz::CH, saved, 4, 8, row0, p.B, T, t, lane);    // hp_hid, hq_hid
-                stage_chunks(svop + 20 * fz::CH, saved, 20, 4, row0, p.B, T, t, lane);  // LA, LV
-                unsigned char* pv = my + fz::PVOP + (t & 1) * 16 * fz::CH;
-                stage_chunks(pv, saved, 40, 8, row0, p.B, T, t, lane);                  // d_l_prev, d_h_prev
-                stage_chunks(pv + 8 * fz::CH, saved, 48, 6, row0, p.B, T, t, lane);     // z_l_prev, z_h_prev, act, ones
-            }
-            cp_async_commit();
-        };
-        auto stage_late = [&](int t) {
-            if (t >= 0) {
-                stage_chunks(svop, saved, 0, 4, row0, p.B, T, t, lane);                  // lp_hid
-                stage_chunks(svop + 12 * fz::CH, saved, 12, 8, row0, p.B, T, t, lane);  // a_hid, v_hid
-                stage_chunks(svop + 24 * fz::CH, saved, 24, 8, row0, p.B, T, t, lane);  // embed_a
-                stage_chunks(svop + 32 * fz::CH, saved, 32, 8, row0, p.B, T, t, lane);  // embed_v
-            }
-            cp_async_commit();
-        };
-        __syncwarp();
-        bulk_rows(stDF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, T - 1, &bars[fz::BAR_DF], lane);
-        bulk_rows(stFT, bst::FT_LD, reinterpret_cast<const char*>(p.feature), 384, bst::FT_BYTES, row0, p.B, T, T - 1, &bars[fz::BAR_FT], lane);
-        bstage_pr(stPR, p, row0, T - 1, lane);
-        stage_early(T - 1);
-        stage_late(T - 1);
-
-        const float* dkl_src = (r.t < 2) ? p.d_kl_h : p.d_kl_l;
-        const size_t dkl_row = (size_t)((r.t & 1) ? r.rB : r.rA) * T;
-        float dkl_next = dkl_src != nullptr ? dkl_src[dkl_row + T - 1] : 0.f;
-        float ddl[4][4], ddh[4][4], dul[4][4], duh[4][4], dzl[2][4], dzh[2][4];
-        zero_c<4>(ddl), zero_c<4>(ddh), zero_c<4>(dul), zero_c<4>(duh), zero_c<2>(dzl), zero_c<2>(dzh);
-
-        for (int t = T - 1; t >= 0; --t) {
-            const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
-            const float dkl_cur = dkl_next;
-            if (t > 0 && dkl_src != nullptr) dkl_next = dkl_src[dkl_row + t - 1];
-            float hid[4][4];
-            {
-                mbar_wait(&bars[fz::BAR_DF], ph_df), ph_df ^= 1;  // d_feature(t) has landed
-                float g4[4][4], g2[2][4];
-                load_staged<4, false>(g4, stDF, bst::DF_LD, 0, r.g, r.t);
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) ddh[nt][j] += g4[nt][j];
-                load_staged<2, false>(g2, stDF, bst::DF_LD, 32, r.g, r.t);  // straight-through: d stoch -> d probs
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dzh[nt][j] += g2[nt][j];
-                load_staged<4, false>(g4, stDF, bst::DF_LD, 48, r.g, r.t);
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) ddl[nt][j] += g4[nt][j];
-                load_staged<2, false>(g2, stDF, bst::DF_LD, 80, r.g, r.t);
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) dzl[nt][j] += g2[nt][j];
-                __syncwarp();
-                if (t > 0)
-                    bulk_rows(stDF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, t - 1,
-                              &bars[fz::BAR_DF], lane);
-                cp_async_wait<1>();  // PR(t) and EARLY(t) have landed (LATE(t) may still be in flight)
-                __syncwarp();
-                if (t < T - 1) FZ_WAIT(&bars[fz::BAR_END], ph_end), ph_end ^= 1;  // step t+1's last MMAs are done with dY / Dop
-            }
-            // ---- higher layer: posterior + prior heads ----------------------------------------------------------------
-            {
-                float q[2][4], pp[2][4], dpp[2][4];
-                load_staged<2, true>(q, stPR + bst::PR, 64, 0, r.g, r.t);
-                load_staged<2, true>(pp, stPR + bst::PR, 64, 32, r.g, r.t);
-                add_global<2>(dzh, p.d_post_probs_h, iA * 16, iB * 16, r.t);
-                zero_c<2>(dpp);
-                add_global<2>(dpp, p.d_prior_probs_h, iA * 16, iB * 16, r.t);
-                add_global<2>(dpp, p.d_prior_stoch_h, iA * 16, iB * 16, r.t);
-                if (p.d_kl_h != nullptr) {
-                    const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 0), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 1)};
-                    kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dzh, dpp);
-                }
-                float dlg[2][4];
-                AFrag<NS, 2> f1;
-                softmax_groups_bwd<KH>(q, dzh, dlg);
-                load_op<4>(hid, svop, mts::HQ_HID, r.g, r.t);
-                head_bwd_op(dlg, wblk<NS>(W, mt::T_HQ2), hid, dy, fz::Y_HQL, fz::Y_HQ1, f1, r, lane);
-                gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_HQ1L), lane);
-                gemm<NS, 2, 4>(ddh, f1, wblk<NS>(W, mt::T_HQ1H), lane);
-                softmax_groups_bwd<KH>(pp, dpp, dlg);
-                load_op<4>(hid, svop, mts::HP_HID, r.g, r.t);
-                head_bwd_op(dlg, wblk<NS>(W, mt::T_HP2), hid, dy, fz::Y_HPL, fz::Y_HP1, f1, r, lane);
-                gemm<NS, 2, 4>(ddh, f1, wblk<NS>(W, mt::T_HP1), lane);
-                // second-layer weight gradients of the two higher heads: their hiddens can then be refilled early
-                FZ_FENCE();
-                __syncwarp();
-                if (FZ_MMA && lane == 0) {
-                    umma_acc(tmem + fz::T_E1, s_sv, s_dy + (fz::Y_HPL / 8) * fz::CH, 32);
-                    umma_commit(&bars[fz::BAR_E]);
-                }
-            }
-            // ---- lower layer: MoPoE posterior + prior head -----------------------------------------------------------
-            {
-                float q[2][4], pp[2][4], dpp[2][4];
-                load_staged<2, true>(q, stPR + bst::PR, 64, 16, r.g, r.t);
-                load_staged<2, true>(pp, stPR + bst::PR, 64, 48, r.g, r.t);
-                __syncwarp();  // every lane is done with PR: refill it for the next (earlier) step
-                bstage_pr(stPR, p, row0, t - 1, lane);
-                add_global<2>(dzl, p.d_post_probs_l, iA * 16, iB * 16, r.t);
-                zero_c<2>(dpp);
-                add_global<2>(dpp, p.d_prior_probs_l, iA * 16, iB * 16, r.t);
-                add_global<2>(dpp, p.d_prior_stoch_l, iA * 16, iB * 16, r.t);
-                if (p.d_kl_l != nullptr) {
-                    const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 2), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 3)};
-                    kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dzl, dpp);
-                }
-                float dla[2][4], dlv[2][4];
-                {
-                    float dm[2][4], la[2][4], lv[2][4], lsa[2][4], lsv[2][4], mixed[2][4], ra[2][4], rv[2][4];
-                    softmax_groups_bwd<KL>(q, dzl, dm);
-                    load_op<2>(la, svop, mts::LA, r.g, r.t);
-                    load_op<2>(lv, svop, mts::LV, r.g, r.t);
-                    log_softmax_flat<true>(la, lsa);
-                    log_softmax_flat<true>(lv, lsv);
-                    mopoe_mix<true>(lsa, lsv, mixed, ra, rv);
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            ra[nt][j] *= dm[nt][j];
-                            rv[nt][j] *= dm[nt][j];
-                        }
-                    log_softmax_flat_bwd<true>(lsa, ra, dla);
-                    log_softmax_flat_bwd<true>(lsv, rv, dlv);
-                }
-                // the early chunks (hp / hq hiddens, LA / LV) and the previous-state image of step t-1 can be refilled now:
-                // every lane has read LA / LV, and the MMA that read the hiddens has completed
-                FZ_WAIT(&bars[fz::BAR_E], ph_e), ph_e ^= 1;
-                cp_async_wait<1>();  // LATE(t) has landed (PR(t-1) may still be in flight)
-                __syncwarp();
-                stage_early(t - 1);
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    AFrag<NS, 2> f1;
-                    load_op<4>(hid, svop, m == 0 ? mts::A_HID : mts::V_HID, r.g, r.t);
-                    head_bwd_op(m == 0 ? dla : dlv, wblk<NS>(W, m == 0 ? mt::T_A2 : mt::T_V2), hid, dy, m == 0 ? fz::Y_LA : fz::Y_LV,
-                                m == 0 ? fz::Y_A1 : fz::Y_V1, f1, r, lane);
-                    gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, m == 0 ? mt::T_A1H : mt::T_V1H), lane);
-                    float de[8][4];
-                    zero_c<8>(de);
-                    gemm<NS, 2, 8>(de, f1, wblk<NS>(W, m == 0 ? mt::T_A1E : mt::T_V1E), lane);
-                    float* dE = m == 0 ? p.d_embed_a : p.d_embed_v;
-                    store_c<8>(de, dE + iA * 64, dE + iB * 64, r);
-                }
-                float dlg[2][4];
-                AFrag<NS, 2> f1;
-                softmax_groups_bwd<KL>(pp, dpp, dlg);
-                load_op<4>(hid, svop, mts::LP_HID, r.g, r.t);
-                head_bwd_op(dlg, wblk<NS>(W, mt::T_LP2), hid, dy, fz::Y_LPL, fz::Y_LP1, f1, r, lane);
-                gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_LP1), lane);
-                // second-layer weight gradients of the lower heads + the embedding halves of the modality heads' first layers
-                FZ_FENCE();
-                __syncwarp();
-                if (FZ_MMA && lane == 0) {
-                    umma_acc(tmem + fz::T_L2, s_sv, s_dy + (fz::Y_LPL / 8) * fz::CH, 64);
-                    umma_acc(tmem + fz::T_L2V, s_sv + 16 * fz::CH, s_dy + (fz::Y_LV / 8) * fz::CH, 16);
-                    umma_acc(tmem + fz::T_EMB, s_sv + 24 * fz::CH, s_dy + (fz::Y_A1 / 8) * fz::CH, 64);
-                    umma_commit(&bars[fz::BAR_L]);
-                }
-            }
-            // ---- the two leaky integrators: u = keep*u_prev + pre/tau, d = tanh(u) -------------------------------------
-            {
-                float dh[4][4], dl[4][4], ph[4][4], pl[4][4];
-                mbar_wait(&bars[fz::BAR_FT], ph_ft), ph_ft ^= 1;  // feature[0:80](t) has landed
-                load_staged<4, false>(dh, stFT, bst::FT_LD, 0, r.g, r.t);
-                load_staged<4, false>(dl, stFT, bst::FT_LD, 48, r.g, r.t);
-                __syncwarp();
-                if (t > 0)
-                    bulk_rows(stFT, bst::FT_LD, reinterpret_cast<const char*>(p.feature), 384, bst::FT_BYTES, row0, p.B, T, t - 1,
-                              &bars[fz::BAR_FT], lane);
-                store_op<4>(dl, dop, 0, r);   // bf16 [d_l | d_h](t): the X operand of every first layer that reads the deters
-                store_op<4>(dh, dop, 32, r);
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float gh = duh[nt][j] + ddh[nt][j] * (1.f - dh[nt][j] * dh[nt][j]);
-                        const float gl = dul[nt][j] + ddl[nt][j] * (1.f - dl[nt][j] * dl[nt][j]);
-                        ph[nt][j] = gh * p.inv_tau_h;
-                        pl[nt][j] = gl * p.inv_tau_l;
-                        duh[nt][j] = gh * keep_h;
-                        dul[nt][j] = gl * keep_l;
-                    }
-                store_op<4>(pl, dy, fz::Y_L, r);
-                store_op<4>(ph, dy, fz::Y_H, r);
-                FZ_FENCE();
-                __syncwarp();
-                if (FZ_MMA && lane == 0) {
-                    const uint32_t pv = s_pv + (t & 1) * 16 * fz::CH;
-                    umma_acc(tmem + fz::T_D1, s_dop, s_dy + (fz::Y_HQ1 / 8) * fz::CH, 160);
-                    umma_acc(tmem + fz::T_C, pv, s_dy + (fz::Y_L / 8) * fz::CH, 64);
-                    umma_acc(tmem + fz::T_B, s_dy, pv + 13 * fz::CH, 16);                     // dY columns   0..127
-                    umma_acc(tmem + fz::T_B + 16, s_dy + 16 * fz::CH, pv + 13 * fz::CH, 16);  // dY columns 128..255
-                    umma_acc(tmem + fz::T_B + 32, s_dy + 22 * fz::CH, pv + 13 * fz::CH, 16);  // dY columns 176..303
-                    umma_commit(&bars[fz::BAR_END]);
-                }
-                AFrag<NS, 2> fl, fh;
-                to_afrag<NS, 2>(fl, pl);
-                to_afrag<NS, 2>(fh, ph);
-                zero_c<4>(ddl), zero_c<4>(ddh), zero_c<2>(dzl), zero_c<2>(dzh);
-                gemm<NS, 2, 4>(ddl, fl, wblk<NS>(W, mt::T_L_D2H), lane);
-                gemm<NS, 2, 4>(ddh, fh, wblk<NS>(W, mt::T_H_D2H), lane);
-                gemm<NS, 2, 2>(dzl, fl, wblk<NS>(W, mt::T_L_IN_ZL), lane);
-                gemm<NS, 2, 2>(dzh, fl, wblk<NS>(W, mt::T_L_IN_ZH), lane);
-                gemm<NS, 2, 2>(dzh, fh, wblk<NS>(W, mt::T_H_IN), lane);
-                if (p.d_actions != nullptr) {
-                    float da[2][4];
-                    zero_c<2>(da);
-                    gemm<NS, 2, 2>(da, fl, wblk<NS>(W, mt::T_L_IN_A), lane);
-                    store_c_partial(da, p.d_actions + iA * A, p.d_actions + iB * A, r, A);
-                }
-                // the late chunks (lp / a / v hiddens, embeddings) are free once the lower heads' MMAs have completed
-                FZ_WAIT(&bars[fz::BAR_L], ph_l), ph_l ^= 1;
-                stage_late(t - 1);
-            }
-        }
-        store_c<4>(ddh, p.d_deter_h0 + (size_t)r.rA * 32, p.d_deter_h0 + (size_t)r.rB * 32, r);
-        store_c<4>(ddl, p.d_deter_l0 + (size_t)r.rA * 32, p.d_deter_l0 + (size_t)r.rB * 32, r);
-        store_c<4>(duh, p.d_hidden_h0 + (size_t)r.rA * 32, p.d_hidden_h0 + (size_t)r.rB * 32, r);
-        store_c<4>(dul, p.d_hidden_l0 + (size_t)r.rA * 32, p.d_hidden_l0 + (size_t)r.rB * 32, r);
-        store_c<2>(dzh, p.d_stoch_h0 + (size_t)r.rA * 16, p.d_stoch_h0 + (size_t)r.rB * 16, r);
-        store_c<2>(dzl, p.d_stoch_l0 + (size_t)r.rA * 16, p.d_stoch_l0 + (size_t)r.rB * 16, r);
-        FZ_WAIT(&bars[fz::BAR_END], ph_end);  // this warp's last MMAs have completed
-        cp_async_wait_all();
-    }
-    // ---- epilogue: TMEM accumulators -> global weight gradients (one atomicAdd per element per CTA) -----------------------
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    {
-        const int L = 32 * warp + lane;  // TMEM lane read by this thread
-        for (int i = 0; i < ft.n; ++i) {
-            const FusedFlush f = ft.e[i];
-            if (f.lane0 + f.nlanes <= 32 * warp || f.lane0 >= 32 * warp + 32) continue;  // warp-uniform
-            for (int c0 = 0; c0 < f.ncols; c0 += 16) {
-                uint32_t v[16];
-                const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16) + f.tcol + c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (L >= f.lane0 && L < f.lane0 + f.nlanes) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < f.ncols) atomicAdd(f.dst + (size_t)(c0 + j) * f.ld + (L - f.lane0) + f.koff, __uint_as_float(v[j]));
-                }
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
-}
-
 // =====================================================================================================================
 // Version 2: TWO warps per 16-sequence tile.
 // The single-warp kernel above needs ~46 KB of shared memory per tile, i.e. four tiles = four warps per SM = one warp per
@@ -518,8 +153,8 @@ namespace fz2 {
 constexpr int CH = fz::CH;
 // ---- per-TILE shared-memory map (bytes) ---------------------------------------------------------------------------------
 constexpr int DOP = 0;                      // [d_l 4][d_h 4] chunks
-constexpr int SVOP = DOP + 8 * CH;          // saved-record chunks 0..39 (core: 0..11 = lp, hp, hq hid; mod: 12..39)
-constexpr int PVOP = SVOP + 40 * CH;        // record chunks 40..55 (previous-state inputs), single buffer
+constexpr int SVOP = DOP + 8 * CH;          // record chunks 0..23 (core: lp, hp, hq hid; mod: a, v hid, LA, LV) + embedding images 24..39 (mod)
+constexpr int PVOP = SVOP + 40 * CH;        // record chunks 26..41 (previous-state inputs), single buffer
 constexpr int DYOP = PVOP + 16 * CH;        // 38 chunks of dY (fz::Y_* column order)
 constexpr int DF = DYOP + 38 * CH;          // d_feature [16][112 words] (bulk, core)
 constexpr int FT = DF + 16 * bst::DF_LD * 4;   // feature[0:80] [16][80 words] (bulk, core)
@@ -657,14 +292,29 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 stage_prl(t);
                 cp_async_commit();
             };
-            auto stage_rest = [&](int t) {  // a / v hiddens and both embeddings: free once this warp's MMAs have completed
-                if (t >= 0) {
-                    stage_chunks(svop + 12 * fz2::CH, saved, 12, 8, row0, p.B, T, t, lane);
-                    stage_chunks(svop + 24 * fz2::CH, saved, 24, 8, row0, p.B, T, t, lane);
-                    stage_chunks(svop + 32 * fz2::CH, saved, 32, 8, row0, p.B, T, t, lane);
-                }
+            auto stage_rest = [&](int t) {  // a / v hiddens: free once this warp's MMAs have completed
+                if (t >= 0) stage_chunks(svop + 12 * fz2::CH, saved, 12, 8, row0, p.B, T, t, lane);
                 cp_async_commit();
             };
+            // the embedding operand images (chunks 24..39) are converted from the fp32 inputs by this warp itself, in the window
+            // where it would otherwise wait for the core warp's cells (the rows were pulled into L2 one step earlier)
+            auto embed_images = [&](int t) {
+                const size_t jA = ((size_t)r.rA * T + t) * 64, jB = ((size_t)r.rB * T + t) * 64;
+                float e[8][4];
+                load_c<8>(e, p.embed_a + jA, p.embed_a + jB, r.t);
+                store_op<8>(e, svop, 24 * 8, r);
+                load_c<8>(e, p.embed_v + jA, p.embed_v + jB, r.t);
+                store_op<8>(e, svop, 32 * 8, r);
+            };
+            auto embed_prefetch = [&](int t) {  // lanes 0..15: one 256-byte row of each embedding
+                if (t >= 0 && lane < 16) {
+                    const size_t j = ((size_t)min(row0 + lane, p.B - 1) * T + t) * 64;
+                    prefetch_bulk_l2(p.embed_a + j, 256);
+                    prefetch_bulk_l2(p.embed_v + j, 256);
+                }
+            };
+            embed_prefetch(T - 2);
+            embed_images(T - 1);
             stage_logits(T - 1);
             stage_rest(T - 1);
             const float* dkl_src = p.d_kl_l;  // lanes t = 0 / 1 of a quad fetch rows A / B one step ahead
@@ -737,8 +387,10 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     umma_commit(&bars[fz2::BAR_M]);
                 }
                 nbar_arrive(bar_x);  // XDDL and this warp's dY columns are complete
-                FZ_WAIT(&bars[fz2::BAR_M], ph_m), ph_m ^= 1;  // own MMAs done: hiddens / embeddings may be refilled
+                FZ_WAIT(&bars[fz2::BAR_M], ph_m), ph_m ^= 1;  // own MMAs done: hiddens / embedding images may be rewritten
                 stage_rest(t - 1);
+                embed_prefetch(t - 2);
+                if (t > 0) embed_images(t - 1);
             }
             cp_async_wait_all();
         } else {
@@ -757,8 +409,8 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
             };
             auto stage_pv = [&](int t) {  // previous-state operand chunks: free once the end-of-step MMAs have completed
                 if (t >= 0) {
-                    stage_chunks(pvop, saved, 40, 8, row0, p.B, T, t, lane);
-                    stage_chunks(pvop + 8 * fz2::CH, saved, 48, 6, row0, p.B, T, t, lane);
+                    stage_chunks(pvop, saved, 26, 8, row0, p.B, T, t, lane);
+                    stage_chunks(pvop + 8 * fz2::CH, saved, 34, 6, row0, p.B, T, t, lane);
                 }
                 cp_async_commit();
             };
@@ -997,46 +649,7 @@ static void add_flush(FusedFlushTable& t, float* dst, int tcol, int ncols, int l
 cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeightGrads& g, cudaStream_t s) {
     using namespace fz;
     const int A = a.A, LDIN = A + 32;
-    FusedFlushTable t{};
-    // second layers (hidden 32 -> logits 16): rows = hidden index k, columns = logit n
-    add_flush(t, g.hp_w2, T_E1 + 0, 16, 32, 32, 32, 0);
-    add_flush(t, g.hq_w2, T_E1 + 16, 16, 64, 32, 32, 0);
-    add_flush(t, g.lp_w2, T_L2 + 0, 16, 0, 32, 32, 0);
-    add_flush(t, g.au_w2, T_L2 + 48, 16, 96, 32, 32, 0);
-    add_flush(t, g.vi_w2, T_L2V, 16, 0, 32, 32, 0);
-    // embedding halves of the modality heads' first layers: [d_l 32 | embed 64] -> 32
-    add_flush(t, g.au_w1, T_EMB + 0, 32, 0, 64, 96, 32);
-    add_flush(t, g.vi_w1, T_EMB + 32, 32, 64, 64, 96, 32);
-    // deter halves: rows 0..31 = d_l, rows 32..63 = d_h; columns [HQ1|LP1|A1|V1|HP1]
-    add_flush(t, g.hq_w1, T_D1 + 0, 32, 0, 64, 64, 0);  // hq_w1 input = [d_l | d_h]
-    add_flush(t, g.lp_w1, T_D1 + 32, 32, 0, 32, 32, 0);
-    add_flush(t, g.au_w1, T_D1 + 64, 32, 0, 32, 96, 0);
-    add_flush(t, g.vi_w1, T_D1 + 96, 32, 0, 32, 96, 0);
-    add_flush(t, g.hp_w1, T_D1 + 128, 32, 32, 32, 32, 0);
-    // cells: rows [d_l_prev 0..31 | d_h_prev 32..63 | z_l_prev 64..79 | z_h_prev 80..95 | act 96..103 | ones 104]; columns [L | H]
-    add_flush(t, g.l_d2h_w, T_C + 0, 32, 0, 32, 32, 0);
-    add_flush(t, g.h_d2h_w, T_C + 32, 32, 32, 32, 32, 0);
-    add_flush(t, g.l_in_w, T_C + 0, 32, 64, 32, LDIN, A);  // [z_l_prev | z_h_prev] -> l_in_w[:, A : A+32]
-    add_flush(t, g.h_in_w, T_C + 32, 32, 80, 16, 16, 0);
-    add_flush(t, g.l_in_w, T_C + 0, 32, 96, A, LDIN, 0);
-    // biases: column 0 of the three (dY window x ones) tiles; lane = dY column - window start (windows at 0, 128, 176)
-    add_flush(t, g.lp_b2, T_B, 1, Y_LPL, 16, 0, 0);
-    add_flush(t, g.hp_b2, T_B, 1, Y_HPL, 16, 0, 0);
-    add_flush(t, g.hq_b2, T_B, 1, Y_HQL, 16, 0, 0);
-    add_flush(t, g.au_b2, T_B, 1, Y_LA, 16, 0, 0);
-    add_flush(t, g.vi_b2, T_B, 1, Y_LV, 16, 0, 0);
-    add_flush(t, g.hq_b1, T_B, 1, Y_HQ1, 32, 0, 0);
-    add_flush(t, g.lp_b1, T_B, 1, Y_LP1, 16, 0, 0);            // LP1 columns 112..127 (first half) ...
-    add_flush(t, g.lp_b1, T_B + 16, 1, 0, 16, 0, 16);          // ... and 128..143 (second half, window 1)
-    add_flush(t, g.au_b1, T_B + 16, 1, Y_A1 - 128, 32, 0, 0);
-    add_flush(t, g.vi_b1, T_B + 16, 1, Y_V1 - 128, 32, 0, 0);
-    add_flush(t, g.hp_b1, T_B + 16, 1, Y_HP1 - 128, 32, 0, 0);
-    add_flush(t, g.l_d2h_b, T_B + 32, 1, Y_L - 176, 32, 0, 0);
-    add_flush(t, g.l_in_b, T_B + 32, 1, Y_L - 176, 32, 0, 0);
-    add_flush(t, g.h_d2h_b, T_B + 32, 1, Y_H - 176, 32, 0, 0);
-    add_flush(t, g.h_in_b, T_B + 32, 1, Y_H - 176, 32, 0, 0);
-
-    // ---- version 2 (two warps per tile): same blocks, its own TMEM column map ---------------------------------------------------
+    // which (lane range, column range) block of a TMEM tile is which weight gradient
     FusedFlushTable u{};
     {
         namespace z = fz2;
@@ -1073,20 +686,17 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
         add_flush(u, g.h_d2h_b, z::T_B + 32, 1, Y_H - 176, 32, 0, 0);
         add_flush(u, g.h_in_b, z::T_B + 32, 1, Y_H - 176, 32, 0, 0);
     }
-    const bool v1 = getenv("RSSM_FUSED_V1") != nullptr;  // the single-warp-per-tile kernel, kept for comparison
     // tiles per CTA: 4 fill an SM's shared memory; small batches use 2 (the TMEM read-back needs four warps) to reach more SMs
-    const int tiles = (a.B + 15) / 16, tpc = (v1 || tiles > 2 * 148) ? 4 : 2;
-    const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + tpc * (size_t)(v1 ? fz::BYTES : fz2::BYTES);
-    auto launch = [&](auto kernel, const FusedFlushTable& tab, int threads) -> cudaError_t {
+    const int tiles = (a.B + 15) / 16, tpc = tiles > 2 * 148 ? 4 : 2;
+    const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + tpc * (size_t)fz2::BYTES;
+    auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        const int ctas = (tiles + tpc - 1) / tpc;
-        kernel<<<ctas, threads, smem, s>>>(a, tab);
+        kernel<<<(tiles + tpc - 1) / tpc, 64 * tpc, smem, s>>>(a, u);
         return cudaGetLastError();
     };
-#define FUSED_DISPATCH(KLv, KHv)                                                           \
-    if (a.KL == KLv && a.KH == KHv)                                                        \
-        return v1 ? launch(mtrssm_bwd_fused_kernel<KLv, KHv>, t, 128) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv>, u, 64 * tpc);
+#define FUSED_DISPATCH(KLv, KHv) \
+    if (a.KL == KLv && a.KH == KHv) return launch(mtrssm_bwd_fused2_kernel<KLv, KHv>);
     FUSED_DISPATCH(4, 2)
 #ifndef RSSM_EXP_ONLY_DEFAULT
     FUSED_DISPATCH(4, 4)

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
             if (STAGED) load_a_staged_act<NS>(fa, stage + stg::ACT, r.g, r.t);
             else load_a_global<NS, 1>(fa, p.actions + iA * A, p.actions + iB * A, r.t, A);
             if constexpr (NS == 1 && !IMAGINE) {
-                if (svA && p.saved_ext) {  // bf16 copies of the step's inputs: the X operands of the fused backward's weight-gradient MMAs
+                if (svA && p.saved_ext) {  // bf16 copies of the step's recurrent inputs: X operands of the fused backward's cell MMAs
                     store_afrag<2>(dlf, svA + mts::DL_PREV, svB + mts::DL_PREV, r);
                     store_afrag<2>(dhf, svA + mts::DH_PREV, svB + mts::DH_PREV, r);
                     store_afrag<1>(zlf, svA + mts::ZL_PREV, svB + mts::ZL_PREV, r);
@@ -237,9 +237,6 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
             AFrag<NS, 4> fe;
             if (STAGED) load_a_staged64<NS>(fe, stage + (m == 0 ? stg::EA : stg::EV), r.g, r.t);
             else load_a_global<NS, 4>(fe, (m == 0 ? p.embed_a : p.embed_v) + iA * 64, (m == 0 ? p.embed_a : p.embed_v) + iB * 64, r.t, 64);
-            if constexpr (NS == 1) {
-                if (svA && p.saved_ext) store_afrag<4>(fe, svA + (m == 0 ? mts::EMB_A : mts::EMB_V), svB + (m == 0 ? mts::EMB_A : mts::EMB_V), r);
-            }
             gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, m == 0 ? mt::A1H : mt::V1H), lane);
             gemm<NS, 4, 4>(acc, fe, wblk<NS>(W, m == 0 ? mt::A1E : mt::V1E), lane);
             float (&lg)[2][4] = m == 0 ? la : lv;

@@ -279,6 +279,7 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
     a.inv_tau_l = 1.f / d->l_tau, a.inv_tau_h = 1.f / d->h_tau, a.kl_wq = up->kl_wq, a.kl_wp = up->kl_wp, a.w = *w;
     a.feature = fo->feature, a.prior_probs_h = fo->prior_probs_h, a.prior_probs_l = fo->prior_probs_l;
     a.post_probs_h = fo->post_probs_h, a.post_probs_l = fo->post_probs_l, a.saved = fo->saved, a.saved_ld = mt_saved_ld(d->precision);
+    a.embed_a = in->embed_a, a.embed_v = in->embed_v;
     a.d_feature = up->d_feature, a.d_prior_probs_h = up->d_prior_probs_h, a.d_prior_probs_l = up->d_prior_probs_l;
     a.d_post_probs_h = up->d_post_probs_h, a.d_post_probs_l = up->d_post_probs_l;
     a.d_prior_stoch_h = up->d_prior_stoch_h, a.d_prior_stoch_l = up->d_prior_stoch_l, a.d_kl_l = up->d_kl_l, a.d_kl_h = up->d_kl_h;
