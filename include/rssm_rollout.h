@@ -44,7 +44,7 @@ extern "C" {
 #define RSSM_PRECISION_FP32 0
 #define RSSM_PRECISION_BF16 1
 /* bf16 tensor-core path whose backward is ONE kernel: BPTT + weight-gradient contractions on tcgen05 with TMEM accumulators
-   (MMTRSSM only; the forward then writes the extended saved record MTRSSM_SAVED_BF16).  Same numerics as RSSM_PRECISION_BF16. */
+   (MMTRSSM only).  Same forward, same records, same numerics as RSSM_PRECISION_BF16. */
 #define RSSM_PRECISION_BF16_FUSED 2
 
 /* ELEMENTS per (b,t) of the opaque records exchanged between fwd, bwd and wgrad.  Element type: fp32 with
@@ -53,10 +53,8 @@ extern "C" {
 #define MRSSM_DPRE_FLOATS 336
 #define MTRSSM_SAVED_FLOATS 208 /* 192 used; bf16 rows of 416 bytes: whole 32-byte sectors, and a row pitch that lets the  */
 #define MTRSSM_DPRE_FLOATS 304  /* weight-gradient kernel read bulk-copied 32-row slabs with ldmatrix in place              */
-/* With RSSM_PRECISION_BF16_FUSED the MMTRSSM saved record is [B,T,MTRSSM_SAVED_BF16] bf16: the MTRSSM_SAVED_FLOATS elements
-   above followed by bf16 copies of the step's recurrent inputs (previous deter / stoch of both levels, the action, a ones
-   column) -- X operands of the weight-gradient contractions that the fused backward runs on the tcgen05 tensor cores. */
-#define MTRSSM_SAVED_BF16 336
+/* (the fused backward reads the same saved record as the two-kernel backward) */
+#define MTRSSM_SAVED_BF16 MTRSSM_SAVED_FLOATS
 
 /* ---- MoPoE-MRSSM -------------------------------------------------------------------------------------- */
 typedef struct {
@@ -180,7 +178,7 @@ typedef struct {
     float *post_probs_h, *post_probs_l;
     float *prior_stoch_h, *prior_stoch_l;   /* [B,T,HS] [B,T,LS]; may be NULL */
     float *kl_l, *kl_h;                     /* [B,T] each */
-    void *saved;                            /* [B,T,MTRSSM_SAVED_FLOATS] record elements ([B,T,MTRSSM_SAVED_BF16] bf16 with _BF16_FUSED); NULL = inference */
+    void *saved;                            /* [B,T,MTRSSM_SAVED_FLOATS] record elements; NULL = inference */
 } RssmMtrssmOutputs;
 
 typedef struct {

@@ -20,7 +20,7 @@ PRECISION_BF16_FUSED = 2  # bf16 path with the one-kernel backward (tcgen05 weig
 ABI_VERSION = 1
 MRSSM_SAVED_FLOATS, MRSSM_DPRE_FLOATS = 320, 336
 MTRSSM_SAVED_FLOATS, MTRSSM_DPRE_FLOATS = 208, 304
-MTRSSM_SAVED_BF16 = 336
+MTRSSM_SAVED_BF16 = MTRSSM_SAVED_FLOATS
 
 _fp = C.c_void_p  # device pointers travel as integers
 
@@ -150,7 +150,7 @@ def record_dtype(precision: int) -> torch.dtype:
 
 def mtrssm_saved_elems(precision: int) -> int:
     """Elements per (b,t) of the MMTRSSM saved record (include/rssm_rollout.h)."""
-    return MTRSSM_SAVED_BF16 if precision == PRECISION_BF16_FUSED else MTRSSM_SAVED_FLOATS
+    return MTRSSM_SAVED_FLOATS
 
 
 def launch_count() -> int:

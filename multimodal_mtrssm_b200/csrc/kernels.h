@@ -43,7 +43,6 @@ struct MtrssmFwdArgs {
     float *kl_l, *kl_h;
     void* saved;
     int saved_ld;    // elements per (b,t) row of `saved`
-    int saved_ext;   // bf16 path: also write the bf16 copies of the step's inputs (MTRSSM_SAVED_BF16 record, fused backward)
 };
 
 struct MtrssmBwdArgs {
@@ -51,7 +50,8 @@ struct MtrssmBwdArgs {
     float inv_tau_l, inv_tau_h, kl_wq, kl_wp;
     RssmMtrssmWeights w;
     const float *feature, *prior_probs_h, *prior_probs_l, *post_probs_h, *post_probs_l;
-    const float *embed_a, *embed_v;  // forward inputs (read by the fused backward only: X operands of the modality heads)
+    // forward inputs read by the fused backward only (X operands of the weight-gradient MMAs)
+    const float *embed_a, *embed_v, *actions, *deter_h0, *deter_l0, *stoch_h0, *stoch_l0;
     const void* saved;
     int saved_ld;  // elements per (b,t) row of `saved`
     const float *d_feature, *d_prior_probs_h, *d_prior_probs_l, *d_post_probs_h, *d_post_probs_l;

@@ -34,9 +34,6 @@ constexpr int BWD_TILES = 132;
 
 namespace mts {  // saved record (192 used of MTRSSM_SAVED_FLOATS)
 constexpr int LP_HID = 0, HP_HID = 32, HQ_HID = 64, A_HID = 96, V_HID = 128, LA = 160, LV = 176;
-// RSSM_PRECISION_BF16_FUSED only (MTRSSM_SAVED_BF16 = 336): bf16 copies of the step's recurrent INPUTS (X operands of the cells'
-// weight gradients), record chunks 26..41
-constexpr int DL_PREV = 208, DH_PREV = 240, ZL_PREV = 272, ZH_PREV = 288, ACT = 304, ONES = 312;  // 320..335: pad
 }
 
 namespace mtd {  // dpre record (304 used of MTRSSM_DPRE_FLOATS)

@@ -152,25 +152,25 @@ __device__ __forceinline__ void head_bwd_op(const float (&dlogit)[2][4], const u
 namespace fz2 {
 constexpr int CH = fz::CH;
 // ---- per-TILE shared-memory map (bytes) ---------------------------------------------------------------------------------
-constexpr int DOP = 0;                      // [d_l 4][d_h 4] chunks
-constexpr int SVOP = DOP + 8 * CH;          // record chunks 0..23 (core: lp, hp, hq hid; mod: a, v hid, LA, LV) + embedding images 24..39 (mod)
-constexpr int PVOP = SVOP + 40 * CH;        // record chunks 26..41 (previous-state inputs), single buffer
-constexpr int DYOP = PVOP + 16 * CH;        // 38 chunks of dY (fz::Y_* column order)
-constexpr int DF = DYOP + 38 * CH;          // d_feature [16][112 words] (bulk, core)
-constexpr int FT = DF + 16 * bst::DF_LD * 4;   // feature[0:80] [16][80 words] (bulk, core)
-constexpr int PR = FT + 16 * bst::FT_LD * 4;   // 4 probability tensors [16][64 words] (cp.async, core)
+constexpr int DOP = 0;                      // [d_l 4][d_h 4] chunks: bf16 deter of this step (core, from the staged feature row)
+constexpr int ZOP = DOP + 8 * CH;           // [z_l 2][z_h 2][act 1][ones 1] chunks: this step's stoch, the NEXT step's action, ones column
+constexpr int SVOP = ZOP + 6 * CH;          // record chunks 0..23 (core: lp, hp, hq hid; mod: a, v hid, LA, LV) + embedding images 24..39 (mod)
+constexpr int DYOP = SVOP + 40 * CH;        // dY: 30 chunks (columns 0..239, fz::Y_* order) + 2 x 8 chunks [L | H], double buffered
+constexpr int DF = DYOP + 46 * CH;          // d_feature [16][112 words] (bulk, core)
+constexpr int FT = DF + 16 * bst::DF_LD * 4;   // feature row [16][112 words] (bulk, core)
+constexpr int PR = FT + 16 * bst::DF_LD * 4;   // 4 probability tensors [16][64 words] (cp.async, core)
 constexpr int PRL = PR + 16 * 64 * 4;          // post_l | prior_l [16][32 words] (cp.async, mod's own copy)
 constexpr int XDDL = PRL + 16 * 32 * 4;        // mod -> core: contribution to d deter_l   [4][32 lanes][4] fp32
 constexpr int XDZL = XDDL + 2048;              // core -> mod: d stoch_l of the next step  [2][32 lanes][4] fp32
-constexpr int BYTES = XDZL + 1024;             // 47,616
+constexpr int BYTES = XDZL + 1024;             // 49,152
 // ---- TMEM accumulator columns ---------------------------------------------------------------------------------------
 constexpr int T_E = 0;      // [lp|hp|hq|a hid]  x [LPL|HPL|HQL]                    48 columns
 constexpr int T_M = 48;     // [a|v hid|..]      x [LA|LV]                          32
 constexpr int T_EMB = 80;   // [embed_a|embed_v] x [A1|V1]                          64
 constexpr int T_D1 = 144;   // [d_l|d_h|..]      x [HQ1|LP1|A1|V1|HP1]             160
-constexpr int T_C = 304;    // previous-state window x [L|H]                        64
-constexpr int T_B = 368;    // 3 x (dY window x [ones|..])                      3 x 16
-constexpr int T_COLS = 416;
+constexpr int T_C = 304;    // [d_l|d_h|z_l|z_h|act|ones|..] of step t x [L|H] of step t+1   64 (the ones row carries the cells' biases)
+constexpr int T_B = 368;    // 2 x (dY window x [ones|..])                      2 x 16
+constexpr int T_COLS = 400;
 enum { BAR_DF, BAR_FT, BAR_E, BAR_END, BAR_M, NBAR };  // per tile
 }  // namespace fz2
 
@@ -265,11 +265,11 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
         const __nv_bfloat16* saved = reinterpret_cast<const __nv_bfloat16*>(p.saved);
         unsigned char* dop = my + fz2::DOP;
         unsigned char* svop = my + fz2::SVOP;
-        unsigned char* pvop = my + fz2::PVOP;
+        unsigned char* zop = my + fz2::ZOP;
         unsigned char* dy = my + fz2::DYOP;
         float* xddl = reinterpret_cast<float*>(my + fz2::XDDL);
         float* xdzl = reinterpret_cast<float*>(my + fz2::XDZL);
-        const uint32_t s_dop = smem_u32(dop), s_sv = smem_u32(svop), s_dy = smem_u32(dy), s_pv = smem_u32(pvop);
+        const uint32_t s_dop = smem_u32(dop), s_sv = smem_u32(svop), s_dy = smem_u32(dy), s_ones = smem_u32(zop) + 5 * fz2::CH;
         const int bar_x = 1 + 2 * tile, bar_y = 2 + 2 * tile;
 
         if (role == 1) {
@@ -407,16 +407,9 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 }
                 cp_async_commit();
             };
-            auto stage_pv = [&](int t) {  // previous-state operand chunks: free once the end-of-step MMAs have completed
-                if (t >= 0) {
-                    stage_chunks(pvop, saved, 26, 8, row0, p.B, T, t, lane);
-                    stage_chunks(pvop + 8 * fz2::CH, saved, 34, 6, row0, p.B, T, t, lane);
-                }
-                cp_async_commit();
-            };
             bulk_rows(stDF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, T - 1, &bars[fz2::BAR_DF], lane);
-            bulk_rows(stFT, bst::FT_LD, reinterpret_cast<const char*>(p.feature), 384, bst::FT_BYTES, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
-            bstage_pr(stPR, p, row0, T - 1, lane);  // cp.async groups per step, in issue order: PV(t) | PR(t-1) | HID(t-1)
+            bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
+            bstage_pr(stPR, p, row0, T - 1, lane);  // cp.async groups per step, in issue order: PR(t-1) | HID(t-1)
             stage_hid(T - 1);
             const float* dkl_src = (r.t < 2) ? p.d_kl_h : p.d_kl_l;  // quad lanes: 0 kl_h row A, 1 kl_h row B, 2 kl_l row A, 3 kl_l row B
             const size_t dkl_row = (size_t)((r.t & 1) ? r.rB : r.rA) * T;
@@ -445,9 +438,25 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 float hid[4][4];
                 cp_async_wait_all();  // PR(t) and the hiddens of step t have landed
                 __syncwarp();
-                // the end-of-step MMAs of step t+1 are done with dY, Dop and the previous-state chunks
+                // the end-of-step MMAs of step t+1 are done with dY, Dop and Zop
                 if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
-                stage_pv(t);  // needed at this step's cells
+                // the action of step t+1 (X operand of the l cell's weight gradient, paired below with dY of step t+1): lanes with
+                // t < 2 own its columns 4t .. 4t+3; column 8 of the 16-column block is the ones column
+                float actc[2][4];
+                zero_c<2>(actc);
+                if (t + 1 < T && r.t < 2) {
+                    const float* aA = p.actions + (iA + 1) * A + 4 * r.t;
+                    const float* aB = p.actions + (iB + 1) * A + 4 * r.t;
+                    if (4 * r.t < A) {
+                        const float2 x = *reinterpret_cast<const float2*>(aA), y = *reinterpret_cast<const float2*>(aB);
+                        actc[0][0] = x.x, actc[0][1] = x.y, actc[0][2] = y.x, actc[0][3] = y.y;
+                    }
+                    if (4 * r.t + 2 < A) {
+                        const float2 x = *reinterpret_cast<const float2*>(aA + 2), y = *reinterpret_cast<const float2*>(aB + 2);
+                        actc[1][0] = x.x, actc[1][1] = x.y, actc[1][2] = y.x, actc[1][3] = y.y;
+                    }
+                }
+                if (r.t == 2) actc[0][0] = actc[0][2] = 1.f;
                 // ---- lower prior head -------------------------------------------------------------------------------------
                 {
                     float q[2][4], pp[2][4], dq[2][4], dpp[2][4], dlg[2][4];
@@ -502,18 +511,24 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 }
                 // ---- the two leaky integrators --------------------------------------------------------------------------
                 float dh[4][4], dl[4][4], ph[4][4], pl[4][4];
-                mbar_wait(&bars[fz2::BAR_FT], ph_ft), ph_ft ^= 1;  // feature[0:80](t) has landed
-                load_staged<4, false>(dh, stFT, bst::FT_LD, 0, r.g, r.t);
-                load_staged<4, false>(dl, stFT, bst::FT_LD, 48, r.g, r.t);
-                __syncwarp();
-                if (t > 0)
-                    bulk_rows(stFT, bst::FT_LD, reinterpret_cast<const char*>(p.feature), 384, bst::FT_BYTES, row0, p.B, T, t - 1,
-                              &bars[fz2::BAR_FT], lane);
-                store_op<4>(dl, dop, 0, r);  // bf16 [d_l | d_h](t)
-                store_op<4>(dh, dop, 32, r);
+                mbar_wait(&bars[fz2::BAR_FT], ph_ft), ph_ft ^= 1;  // the feature row of step t has landed
+                load_staged<4, false>(dh, stFT, bst::DF_LD, 0, r.g, r.t);
+                load_staged<4, false>(dl, stFT, bst::DF_LD, 48, r.g, r.t);
+                {
+                    float zh[2][4], zl[2][4];
+                    load_staged<2, false>(zh, stFT, bst::DF_LD, 32, r.g, r.t);
+                    load_staged<2, false>(zl, stFT, bst::DF_LD, 80, r.g, r.t);
+                    __syncwarp();
+                    if (t > 0)
+                        bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, t - 1, &bars[fz2::BAR_FT], lane);
+                    // X operands: bf16 [d_l | d_h | z_l | z_h](t) and [action(t+1) | ones]
+                    store_op<4>(dl, dop, 0, r);
+                    store_op<4>(dh, dop, 32, r);
+                    store_op<2>(zl, zop, 0, r);
+                    store_op<2>(zh, zop, 16, r);
+                    store_op<2>(actc, zop, 32, r);
+                }
                 FZ_WAIT(&bars[fz2::BAR_E], ph_e), ph_e ^= 1;  // the hiddens may be refilled
-                cp_async_wait<1>();                            // PV(t) has landed (PR(t-1) may still be in flight)
-                __syncwarp();
                 stage_hid(t - 1);
                 nbar_sync(bar_x);  // the mod warp's dY columns and its contribution to d deter_l are complete
                 {
@@ -535,16 +550,17 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                         duh[nt][j] = gh * keep_h;
                         dul[nt][j] = gl * keep_l;
                     }
-                store_op<4>(pl, dy, fz::Y_L, r);
-                store_op<4>(ph, dy, fz::Y_H, r);
+                // the cells' dY is double buffered: step t's lands in buffer t & 1 and is multiplied at step t-1 with that step's
+                // state (= this step's INPUT state), so no copies of the previous state are needed anywhere
+                store_op<4>(pl, dy, fz::Y_L + 64 * (t & 1), r);
+                store_op<4>(ph, dy, fz::Y_H + 64 * (t & 1), r);
                 FZ_FENCE();
                 __syncwarp();
                 if (FZ_MMA && lane == 0) {
                     umma_acc(tmem + fz2::T_D1, s_dop, s_dy + (fz::Y_HQ1 / 8) * fz2::CH, 160);
-                    umma_acc(tmem + fz2::T_C, s_pv, s_dy + (fz::Y_L / 8) * fz2::CH, 64);
-                    umma_acc(tmem + fz2::T_B, s_dy, s_pv + 13 * fz2::CH, 16);                     // dY columns   0..127
-                    umma_acc(tmem + fz2::T_B + 16, s_dy + 16 * fz2::CH, s_pv + 13 * fz2::CH, 16);  // dY columns 128..255
-                    umma_acc(tmem + fz2::T_B + 32, s_dy + 22 * fz2::CH, s_pv + 13 * fz2::CH, 16);  // dY columns 176..303
+                    if (t < T - 1) umma_acc(tmem + fz2::T_C, s_dop, s_dy + ((fz::Y_L + 64 * ((t + 1) & 1)) / 8) * fz2::CH, 64);
+                    umma_acc(tmem + fz2::T_B, s_dy, s_ones, 16);                     // dY columns   0..127
+                    umma_acc(tmem + fz2::T_B + 16, s_dy + 16 * fz2::CH, s_ones, 16);  // dY columns 128..239 (+ junk)
                     umma_commit(&bars[fz2::BAR_END]);
                 }
                 AFrag<NS, 2> fl, fh;
@@ -604,7 +620,41 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     store_c<2>(dzl, p.d_stoch_l0 + (size_t)r.rA * 16, p.d_stoch_l0 + (size_t)r.rB * 16, r);
                 }
             }
-            FZ_WAIT(&bars[fz2::BAR_END], ph_end);
+            // step 0's cell gradients pair with the INITIAL state
+            FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
+            {
+                float c4[4][4], c2[2][4], actc[2][4];
+                load_c<4>(c4, p.deter_l0 + (size_t)r.rA * 32, p.deter_l0 + (size_t)r.rB * 32, r.t);
+                store_op<4>(c4, dop, 0, r);
+                load_c<4>(c4, p.deter_h0 + (size_t)r.rA * 32, p.deter_h0 + (size_t)r.rB * 32, r.t);
+                store_op<4>(c4, dop, 32, r);
+                load_c<2>(c2, p.stoch_l0 + (size_t)r.rA * 16, p.stoch_l0 + (size_t)r.rB * 16, r.t);
+                store_op<2>(c2, zop, 0, r);
+                load_c<2>(c2, p.stoch_h0 + (size_t)r.rA * 16, p.stoch_h0 + (size_t)r.rB * 16, r.t);
+                store_op<2>(c2, zop, 16, r);
+                zero_c<2>(actc);
+                if (r.t < 2) {
+                    const float* aA = p.actions + (size_t)r.rA * T * A + 4 * r.t;
+                    const float* aB = p.actions + (size_t)r.rB * T * A + 4 * r.t;
+                    if (4 * r.t < A) {
+                        const float2 x = *reinterpret_cast<const float2*>(aA), y = *reinterpret_cast<const float2*>(aB);
+                        actc[0][0] = x.x, actc[0][1] = x.y, actc[0][2] = y.x, actc[0][3] = y.y;
+                    }
+                    if (4 * r.t + 2 < A) {
+                        const float2 x = *reinterpret_cast<const float2*>(aA + 2), y = *reinterpret_cast<const float2*>(aB + 2);
+                        actc[1][0] = x.x, actc[1][1] = x.y, actc[1][2] = y.x, actc[1][3] = y.y;
+                    }
+                }
+                if (r.t == 2) actc[0][0] = actc[0][2] = 1.f;
+                store_op<2>(actc, zop, 32, r);
+                FZ_FENCE();
+                __syncwarp();
+                if (FZ_MMA && lane == 0) {
+                    umma_acc(tmem + fz2::T_C, s_dop, s_dy + (fz::Y_L / 8) * fz2::CH, 64);  // buffer 0 holds step 0's [L | H]
+                    umma_commit(&bars[fz2::BAR_END]);
+                }
+                FZ_WAIT(&bars[fz2::BAR_END], ph_end);
+            }
             cp_async_wait_all();
         }
     }
@@ -681,10 +731,10 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
         add_flush(u, g.au_b1, z::T_B + 16, 1, Y_A1 - 128, 32, 0, 0);
         add_flush(u, g.vi_b1, z::T_B + 16, 1, Y_V1 - 128, 32, 0, 0);
         add_flush(u, g.hp_b1, z::T_B + 16, 1, Y_HP1 - 128, 32, 0, 0);
-        add_flush(u, g.l_d2h_b, z::T_B + 32, 1, Y_L - 176, 32, 0, 0);
-        add_flush(u, g.l_in_b, z::T_B + 32, 1, Y_L - 176, 32, 0, 0);
-        add_flush(u, g.h_d2h_b, z::T_B + 32, 1, Y_H - 176, 32, 0, 0);
-        add_flush(u, g.h_in_b, z::T_B + 32, 1, Y_H - 176, 32, 0, 0);
+        add_flush(u, g.l_d2h_b, z::T_C + 0, 32, 104, 1, 1, 0);  // ones row (lane 104) of the cells' tile: column n -> bias n
+        add_flush(u, g.l_in_b, z::T_C + 0, 32, 104, 1, 1, 0);
+        add_flush(u, g.h_d2h_b, z::T_C + 32, 32, 104, 1, 1, 0);
+        add_flush(u, g.h_in_b, z::T_C + 32, 32, 104, 1, 1, 0);
     }
     // tiles per CTA: 4 fill an SM's shared memory; small batches use 2 (the TMEM read-back needs four warps) to reach more SMs
     const int tiles = (a.B + 15) / 16, tpc = tiles > 2 * 148 ? 4 : 2;

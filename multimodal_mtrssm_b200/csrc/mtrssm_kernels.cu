@@ -157,17 +157,6 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
             AFrag<NS, 1> fa;
             if (STAGED) load_a_staged_act<NS>(fa, stage + stg::ACT, r.g, r.t);
             else load_a_global<NS, 1>(fa, p.actions + iA * A, p.actions + iB * A, r.t, A);
-            if constexpr (NS == 1 && !IMAGINE) {
-                if (svA && p.saved_ext) {  // bf16 copies of the step's recurrent inputs: X operands of the fused backward's cell MMAs
-                    store_afrag<2>(dlf, svA + mts::DL_PREV, svB + mts::DL_PREV, r);
-                    store_afrag<2>(dhf, svA + mts::DH_PREV, svB + mts::DH_PREV, r);
-                    store_afrag<1>(zlf, svA + mts::ZL_PREV, svB + mts::ZL_PREV, r);
-                    store_afrag<1>(zhf, svA + mts::ZH_PREV, svB + mts::ZH_PREV, r);
-                    AFrag<1, 1> ao = fa;  // [action (8 columns, zero padded) | ones column + 7 zeros]
-                    if (r.t == 2) ao.r[0][0][0] = ao.r[0][0][1] = 0x00003f80u;
-                    store_afrag<1>(ao, svA + mts::ACT, svB + mts::ACT, r);
-                }
-            }
             gemm<NS, 2, 4>(pl, dlf, wblk<NS>(W, mt::L_D2H), lane);
             gemm<NS, 1, 4>(pl, zlf, wblk<NS>(W, mt::L_IN_ZL), lane);
             gemm<NS, 1, 4>(pl, zhf, wblk<NS>(W, mt::L_IN_ZH), lane);

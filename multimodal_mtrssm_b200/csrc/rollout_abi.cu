@@ -60,7 +60,7 @@ int check_mtrssm(const RssmMtrssmDims* d) {
 
 // kernel precision policy (fp32-parity / bf16) and saved-record row length of an MMTRSSM precision value
 int mt_kernel_precision(int precision) { return precision == RSSM_PRECISION_FP32 ? RSSM_PRECISION_FP32 : RSSM_PRECISION_BF16; }
-int mt_saved_ld(int precision) { return precision == RSSM_PRECISION_BF16_FUSED ? MTRSSM_SAVED_BF16 : MTRSSM_SAVED_FLOATS; }
+int mt_saved_ld(int) { return MTRSSM_SAVED_FLOATS; }
 
 #define REQUIRE(ptr)                                                           \
     do {                                                                       \
@@ -244,7 +244,7 @@ static int mtrssm_fwd_common(const RssmMtrssmDims* d, const RssmMtrssmWeights* w
     a.post_probs_h = out->post_probs_h, a.post_probs_l = out->post_probs_l;
     a.prior_stoch_h = out->prior_stoch_h, a.prior_stoch_l = out->prior_stoch_l;
     a.kl_l = out->kl_l, a.kl_h = out->kl_h, a.saved = imagine ? nullptr : out->saved;
-    a.saved_ld = mt_saved_ld(d->precision), a.saved_ext = d->precision == RSSM_PRECISION_BF16_FUSED;
+    a.saved_ld = mt_saved_ld(d->precision);
     g_launches.fetch_add(1);
     return check_cuda(rssm::launch_mtrssm_fwd(a, mt_kernel_precision(d->precision), imagine, static_cast<cudaStream_t>(stream)),
                       imagine ? "mtrssm imagine launch" : "mtrssm forward launch");
@@ -279,7 +279,8 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
     a.inv_tau_l = 1.f / d->l_tau, a.inv_tau_h = 1.f / d->h_tau, a.kl_wq = up->kl_wq, a.kl_wp = up->kl_wp, a.w = *w;
     a.feature = fo->feature, a.prior_probs_h = fo->prior_probs_h, a.prior_probs_l = fo->prior_probs_l;
     a.post_probs_h = fo->post_probs_h, a.post_probs_l = fo->post_probs_l, a.saved = fo->saved, a.saved_ld = mt_saved_ld(d->precision);
-    a.embed_a = in->embed_a, a.embed_v = in->embed_v;
+    a.embed_a = in->embed_a, a.embed_v = in->embed_v, a.actions = in->actions;
+    a.deter_h0 = in->deter_h0, a.deter_l0 = in->deter_l0, a.stoch_h0 = in->stoch_h0, a.stoch_l0 = in->stoch_l0;
     a.d_feature = up->d_feature, a.d_prior_probs_h = up->d_prior_probs_h, a.d_prior_probs_l = up->d_prior_probs_l;
     a.d_post_probs_h = up->d_post_probs_h, a.d_post_probs_l = up->d_post_probs_l;
     a.d_prior_stoch_h = up->d_prior_stoch_h, a.d_prior_stoch_l = up->d_prior_stoch_l, a.d_kl_l = up->d_kl_l, a.d_kl_h = up->d_kl_h;
