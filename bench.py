@@ -498,12 +498,12 @@ def main() -> None:
                 else "backward = BPTT kernel + weight-gradient kernel (dominant: %s)" % dominant)
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of exactly this workload
-    # (profiles/r1_e_ncu_summary.txt, r1_f_ncu_summary.txt); None for any other size
+    # (profiles/r1_e_ncu_summary.txt, r1_g_ncu_summary.txt); None for any other size
     traffic = None
     if (B, T) == (37888, 30) and precision == _lib.PRECISION_BF16:
         traffic = 2.156e9 if dominant == "mtrssm_fwd_kernel" else 3.014e9 + 2.230e9
     elif (B, T) == (37888, 30) and precision == _lib.PRECISION_BF16_FUSED:
-        traffic = 2.727e9 if dominant == "mtrssm_fwd_kernel" else 2.801e9  # profiles/r1_f_ncu_summary.txt
+        traffic = 2.155e9 if dominant == "mtrssm_fwd_kernel" else 2.888e9  # profiles/r1_g_ncu_summary.txt
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
