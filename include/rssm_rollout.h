@@ -26,7 +26,10 @@
  *     idx = min(K-1, #{k : cdf_k <= u}).
  *   - return value: 0 = ok, non-zero = error; rssm_last_error() returns a thread-local message.
  *   - supported sizes (anything else returns an error, never a fallback):
- *       deter = hidden = 32, stochastic size C*K = 16 with K in {2,4,8,16}, embed = 64, action even, 2..8.
+ *       default family: deter = hidden = 32, stochastic size C*K = 16 with K in {2,4,8,16}, embed = 64, action even, 2..8.
+ *       wide family (MoPoE-MRSSM only, RSSM_PRECISION_BF16 only): deter = hidden = D, D % 64 == 0, 64 <= D <= 512
+ *       (BASELINE.json cfg3 "hidden 512"), same stochastic / embed sizes, action 1..8.  The wide family needs a caller-
+ *       provided workspace and a larger saved record: size them with rssm_mrssm_workspace_bytes / rssm_mrssm_saved_bytes.
  *   - precision: RSSM_PRECISION_FP32 = every contraction as a 3-way bf16 split on the tensor cores with fp32
  *     accumulation (fp32-level accuracy); RSSM_PRECISION_BF16 = single bf16 operands, fp32 accumulation,
  *     fp32 state/epilogues.
@@ -40,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RSSM_ABI_VERSION 1
+#define RSSM_ABI_VERSION 2
 #define RSSM_PRECISION_FP32 0
 #define RSSM_PRECISION_BF16 1
 /* bf16 tensor-core path whose backward is ONE kernel: BPTT + weight-gradient contractions on tcgen05 with TMEM accumulators
@@ -97,7 +100,10 @@ typedef struct {
     float *post_probs;   /* [B,T,C,K] posterior.distribution                                      */
     float *prior_stoch;  /* [B,T,S]   prior.stoch (one-hot); may be NULL                          */
     float *kl;           /* [B,T]     sum_c KL(post_c || prior_c), before mean / balancing / coeff */
-    void *saved;         /* [B,T,MRSSM_SAVED_FLOATS] record elements for the backward; NULL = inference */
+    void *saved;         /* [B,T,MRSSM_SAVED_FLOATS] record elements for the backward; NULL = inference
+                            (wide family: rssm_mrssm_saved_bytes(dims) bytes, opaque) */
+    void *workspace;     /* wide family only: rssm_mrssm_workspace_bytes(dims, 0) bytes of scratch, 256-byte aligned */
+    size_t workspace_bytes;
 } RssmMrssmOutputs;
 
 typedef struct {           /* upstream gradients; any pointer may be NULL (= zero) except d_feature */
@@ -116,9 +122,16 @@ typedef struct {
     float *d_embed_v; /* [B,T,E] */
     float *d_h0;      /* [B,D]   */
     float *d_z0;      /* [B,S]   */
-    void *dpre;       /* [B,T,MRSSM_DPRE_FLOATS] record elements, workspace */
+    void *dpre;       /* [B,T,MRSSM_DPRE_FLOATS] record elements, workspace (wide family: unused, may be NULL) */
+    void *workspace;  /* wide family only: rssm_mrssm_workspace_bytes(dims, 1) bytes of scratch, 256-byte aligned */
+    size_t workspace_bytes;
 } RssmMrssmInputGrads;
 
+/* bytes of the opaque saved record (default family: B*T*MRSSM_SAVED_FLOATS elements) and of the scratch workspace a call
+   needs (pass 0 = forward / imagination, 1 = backward; 0 bytes for the default family).  0 is also returned for unsupported
+   dims (the launch entry points report the error). */
+size_t rssm_mrssm_saved_bytes(const RssmMrssmDims *dims);
+size_t rssm_mrssm_workspace_bytes(const RssmMrssmDims *dims, int pass);
 int rssm_mrssm_rollout_fwd(const RssmMrssmDims *dims, const RssmMrssmWeights *w, const RssmMrssmInputs *in,
                            const RssmMrssmOutputs *out, void *stream);
 int rssm_mrssm_rollout_bwd(const RssmMrssmDims *dims, const RssmMrssmWeights *w, const RssmMrssmInputs *in,

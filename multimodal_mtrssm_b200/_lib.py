@@ -17,7 +17,7 @@ from .build import LIB, build_library
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 PRECISION_BF16_FUSED = 2  # bf16 path with the one-kernel backward (tcgen05 weight gradients); MMTRSSM only
-ABI_VERSION = 1
+ABI_VERSION = 2
 MRSSM_SAVED_FLOATS, MRSSM_DPRE_FLOATS = 320, 336
 MTRSSM_SAVED_FLOATS, MTRSSM_DPRE_FLOATS = 208, 304
 MTRSSM_SAVED_BF16 = MTRSSM_SAVED_FLOATS
@@ -45,12 +45,16 @@ MrssmDims = _struct("RssmMrssmDims", [(n, C.c_int) for n in "B T A E D H C K pre
 MrssmWeights = _struct("RssmMrssmWeights", _ptrs(_MR_W))
 MrssmWeightGrads = _struct("RssmMrssmWeightGrads", _ptrs(_MR_W))
 MrssmInputs = _struct("RssmMrssmInputs", _ptrs("actions embed_a embed_v h0 z0 u_post u_prior"))
-MrssmOutputs = _struct("RssmMrssmOutputs", _ptrs("feature prior_probs post_probs prior_stoch kl saved"))
+MrssmOutputs = _struct(
+    "RssmMrssmOutputs", _ptrs("feature prior_probs post_probs prior_stoch kl saved workspace") + [("workspace_bytes", C.c_size_t)]
+)
 MrssmUpstream = _struct(
     "RssmMrssmUpstream",
     _ptrs("d_feature d_prior_probs d_post_probs d_prior_stoch d_kl") + [("kl_wq", C.c_float), ("kl_wp", C.c_float)],
 )
-MrssmInputGrads = _struct("RssmMrssmInputGrads", _ptrs("d_actions d_embed_a d_embed_v d_h0 d_z0 dpre"))
+MrssmInputGrads = _struct(
+    "RssmMrssmInputGrads", _ptrs("d_actions d_embed_a d_embed_v d_h0 d_z0 dpre workspace") + [("workspace_bytes", C.c_size_t)]
+)
 
 MtrssmDims = _struct(
     "RssmMtrssmDims",
@@ -91,6 +95,7 @@ EXPORTS = (
     "rssm_mtrssm_rollout_fwd", "rssm_mtrssm_rollout_bwd", "rssm_mtrssm_imagine_fwd",
     "rssm_mrssm_wgrad", "rssm_mtrssm_wgrad",
     "rssm_abi_version", "rssm_last_error", "rssm_kernel_launch_count",
+    "rssm_mrssm_saved_bytes", "rssm_mrssm_workspace_bytes",
 )
 
 
@@ -108,6 +113,10 @@ def lib() -> C.CDLL:
     P = C.c_void_p
     for name in EXPORTS[:8]:
         getattr(handle, name).restype = C.c_int
+    handle.rssm_mrssm_saved_bytes.restype = C.c_size_t
+    handle.rssm_mrssm_saved_bytes.argtypes = [P]
+    handle.rssm_mrssm_workspace_bytes.restype = C.c_size_t
+    handle.rssm_mrssm_workspace_bytes.argtypes = [P, C.c_int]
     handle.rssm_mrssm_wgrad.argtypes = [P] * 6
     handle.rssm_mtrssm_wgrad.argtypes = [P] * 6
     handle.rssm_mrssm_rollout_fwd.argtypes = [P] * 5
@@ -151,6 +160,16 @@ def record_dtype(precision: int) -> torch.dtype:
 def mtrssm_saved_elems(precision: int) -> int:
     """Elements per (b,t) of the MMTRSSM saved record (include/rssm_rollout.h)."""
     return MTRSSM_SAVED_FLOATS
+
+
+def mrssm_saved_bytes(dims) -> int:  # noqa: ANN001
+    """Bytes of the opaque MRSSM saved record for `dims` (0 = unsupported sizes; the launch reports the error)."""
+    return int(lib().rssm_mrssm_saved_bytes(C.byref(dims)))
+
+
+def mrssm_workspace_bytes(dims, backward: bool) -> int:  # noqa: ANN001
+    """Bytes of scratch a wide-family MRSSM call needs (0 for the default family)."""
+    return int(lib().rssm_mrssm_workspace_bytes(C.byref(dims), 1 if backward else 0))
 
 
 def launch_count() -> int:

@@ -30,6 +30,87 @@ struct MrssmBwdArgs {
 cudaError_t launch_mrssm_fwd(const MrssmFwdArgs& a, int precision, bool imagine, cudaStream_t s);
 cudaError_t launch_mrssm_bwd(const MrssmBwdArgs& a, int precision, cudaStream_t s);
 
+
+// ---- wide MoPoE-MRSSM (deter = hidden = D, D % 64 == 0; persistent tcgen05 kernels: wide_common.cuh) --------------------
+struct MrssmWideFwdArgs {
+    int B, T, A, K, D;  // B = sequences of this launch group (<= NBB * 128)
+    int NBB, NSL;       // batch blocks of the group, slices (D / 32); grid = NBB * NSL
+    int imagine, desc_swap;
+    long long plane_stride, t_stride, emb_t_stride;  // record / packed-embedding strides in elements (t_stride 0: keep one step)
+    RssmMrssmWeights w;                               // fp32 originals (biases, first projector layer, logit layers)
+    const __nv_bfloat16 *pW2, *pWhh, *pWih, *pWhd, *pWae, *pWve;  // packed bf16 weight slices
+    const float *actions, *h0, *z0, *u_post, *u_prior;           // first row of the group
+    const __nv_bfloat16 *emb_a, *emb_v;                          // packed [T][blocks][8][128][8], first block of the group
+    float *feature, *prior_probs, *post_probs, *prior_stoch, *kl;
+    __nv_bfloat16 *rec, *h0p;  // record planes [t][plane][blocks][D/8][128][8]; packed h0 [NBB][D/8][128][8]
+    float* part;               // partial logits [NBB*128][NSL][48]
+    float* logits;             // [rows][T][32] audio / vision logits for the backward (NULL when not saving)
+    unsigned* bar;
+    int* status;
+};
+cudaError_t launch_mrssm_wide_fwd(const MrssmWideFwdArgs& a, cudaStream_t s);
+size_t mrssm_wide_fwd_smem(int D);
+
+
+struct MrssmWideBwdArgs {
+    int B, T, A, K, D, NBB, NSL;
+    float kl_wq, kl_wp;
+    long long plane_stride, t_stride, dt_stride;  // elements: one plane, forward record step, gradient-plane step
+    long long dlg_off, xin_off;                   // element offsets of the narrow planes inside a gradient-plane step (group-relative)
+    RssmMrssmWeights w;
+    const __nv_bfloat16 *pW1x, *pWhdT, *pWgT, *pWihTn, *pWhhTn, *pW2T;  // transposed packed weight images
+    const __nv_bfloat16* rec;  // forward record planes (first block of the group)
+    __nv_bfloat16* drec;       // gradient planes (first block of the group)
+    const float* logits;       // [rows][T][32] audio / vision logits saved by the forward
+    const float *feature, *prior_probs, *post_probs, *h0, *z0, *actions;
+    const float *d_feature, *d_prior_probs, *d_post_probs, *d_prior_stoch, *d_kl;
+    float *d_actions, *d_h0, *d_z0;
+    float* carry;  // [NBB*128][D]
+    unsigned* bar;
+    int* status;
+};
+cudaError_t launch_mrssm_wide_bwd(const MrssmWideBwdArgs& a, cudaStream_t s);
+cudaError_t launch_wide_pack_bwd_weights(const MrssmWideBwdArgs& a, cudaStream_t s);
+
+// one output tile of the weight-gradient contraction over (b,t) rows: dW[m * sm + n * sn] += sum_rows Y[row][m] X[row][n]
+struct WideWgradTile {
+    const __nv_bfloat16 *y, *x, *x0;  // first element of the tile's 128 Y features / N X features in block 0 of step 0
+    long long y_tstride, y_bstride, x_tstride, x_bstride;
+    int x_shift;                      // 1: X of step t-1 (x0 for t = 0)
+    int N, mvalid, nvalid;
+    float *dW, *db;                   // db (optional): += sum_rows Y[row][m]
+    long long sm, sn;
+};
+cudaError_t launch_wide_wgrad(const WideWgradTile* tiles_dev, int ntiles, int nsplit, int T, int NBBT, const __nv_bfloat16* ones, cudaStream_t s);
+
+struct WideDembedArgs {
+    int B, T, D, NBBT;
+    long long dt_stride;
+    const __nv_bfloat16 *dah, *dvh, *pWaeT, *pWveT;
+    float *d_embed_a, *d_embed_v;
+};
+cudaError_t launch_wide_dembed(const WideDembedArgs& a, cudaStream_t s);
+cudaError_t launch_wide_pack_dembed(const float* au_w1, const float* vi_w1, int D, __nv_bfloat16* dstA, __nv_bfloat16* dstV, __nv_bfloat16* ones,
+                                    cudaStream_t s);
+
+// packs fp32 [out,in] weights into per-slice bf16 operand images [slice][K/64][8][32*nparts][8]:
+// row (part p, unit u) of slice s = src[p] + (s*32+u) * ld[p] + coloff + k
+struct WidePackJob {
+    const float* src[3];
+    int ld[3];
+    int coloff, nparts, K;
+    __nv_bfloat16* dst;
+};
+constexpr int MAX_WIDE_PACK_JOBS = 8;
+struct WidePackJobs {
+    WidePackJob job[MAX_WIDE_PACK_JOBS];
+    int njobs, NSL;
+};
+cudaError_t launch_wide_pack_weights(const WidePackJobs& jobs, cudaStream_t s);
+// fp32 rows src[(b*T + t) * ld + coloff + f], f < F (F % 8 == 0)  ->  packed bf16 dst[t][blocks][F/8][128][8]
+cudaError_t launch_wide_pack_rows(const float* src, int B, int T, int F, int ld, int coloff, __nv_bfloat16* dst, int blocks,
+                                  cudaStream_t s);
+
 // ---- MoPoE-MMTRSSM ---------------------------------------------------------------------------------
 struct MtrssmFwdArgs {
     int B, T, A, KL, KH;

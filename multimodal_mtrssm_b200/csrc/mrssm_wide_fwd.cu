@@ -1,0 +1,486 @@
+// Wide MoPoE-MRSSM rollout, forward (and imagination): one persistent cooperative kernel for all T steps.
+// Replaces the T loop of MoPoE_MRSSM.rollout_representation (mrssm/mopoe_mrssm/core.py:221-256) / BaseRSSM.rollout_transition
+// (core.py:170-185) for deterministic_size = hidden_size = D in {64, 128, ..., 512}.  Design notes: wide_common.cuh.
+//
+// CTA (bb, s) = batch block bb (128 sequences) x slice s (hidden units / head features 32 s .. 32 s + 31).  One step = four
+// phases separated by grid barriers (each phase consumes what ALL slices of the block produced in the previous one):
+//   A  x2[:, slice]  = W2[slice] . hid1_t + b2                 (action_state_projector.2, networks.py:169)      N = 32, K = D
+//      gh[:, slice]  = W_hh[r|z|n of slice] . h_{t-1}           (GRUCell, networks.py:170)                       N = 96, K = D
+//   B  gi[:, slice]  = W_ih[r|z|n of slice] . x2 ; gates ; h_t  (GRUCell)                                        N = 96, K = D
+//   C  hid[:, slice] = ELU([W_prior | W_audio | W_vision][slice] . h_t (+ W_e . embed_t) + b1)                   N = 96, K = D (+64)
+//      partial logits of the slice (CUDA cores; 32 features x 16 outputs per head)  -> part[row][s][48]
+//   D  rows are dealt out evenly over ALL CTAs: sum the partial logits, MoPoE fusion (mopoe_mrssm/core.py:241-251,135-154),
+//      per-group softmax, inverse-CDF draw, KL, per-step outputs; hid1_{t+1} = ELU(W1 . [a_{t+1} ; z_t] + b1) (networks.py:164-169)
+// Accumulators live in TMEM (x2 @0, gh @32, gi @128, heads @224); gh is issued in phase A and consumed in phase B.
+#include "kernels.h"
+#include "wide_common.cuh"
+
+namespace rssm {
+namespace wide {
+
+constexpr int STAGES = 5;
+constexpr int B_MAX_BYTES = 96 * 64 * 2;
+constexpr int STAGE_BYTES = A_BYTES + B_MAX_BYTES;
+constexpr int TM_X2 = 0, TM_GH = 32, TM_GI = 128, TM_HD = 224;
+constexpr int MAX_RPC = 64;  // rows per CTA in phase D (NSL >= 2)
+
+struct FwdSmem {
+    unsigned char* ring;
+    float *w1t, *b2s, *bih, *bhh, *bhd, *w2l, *b2l, *zval;
+    uint64_t *full, *empty, *accbar;
+    uint32_t* tmem_base;
+};
+
+__host__ __device__ inline size_t fwd_smem_bytes(int D, int A) {
+    size_t n = 128;  // alignment slack
+    n += (size_t)STAGES * STAGE_BYTES;
+    n += (size_t)(A + 17) * D * 4;
+    n += (32 + 96 * 3) * 4 + 3 * 32 * 16 * 4 + 48 * 4 + MAX_RPC * 16 * 4;
+    n += (2 * STAGES + 1) * 8 + 16;
+    return n;
+}
+
+__device__ __forceinline__ FwdSmem carve(unsigned char* dyn, int D, int A) {
+    FwdSmem s;
+    unsigned char* p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(dyn) + 127) & ~(uintptr_t)127);
+    s.ring = p, p += (size_t)STAGES * STAGE_BYTES;
+    s.w1t = reinterpret_cast<float*>(p), p += (size_t)(A + 17) * D * 4;
+    s.b2s = reinterpret_cast<float*>(p), p += 32 * 4;
+    s.bih = reinterpret_cast<float*>(p), p += 96 * 4;
+    s.bhh = reinterpret_cast<float*>(p), p += 96 * 4;
+    s.bhd = reinterpret_cast<float*>(p), p += 96 * 4;
+    s.w2l = reinterpret_cast<float*>(p), p += 3 * 32 * 16 * 4;
+    s.b2l = reinterpret_cast<float*>(p), p += 48 * 4;
+    s.zval = reinterpret_cast<float*>(p), p += MAX_RPC * 16 * 4;
+    s.full = reinterpret_cast<uint64_t*>(p), p += STAGES * 8;
+    s.empty = reinterpret_cast<uint64_t*>(p), p += STAGES * 8;
+    s.accbar = reinterpret_cast<uint64_t*>(p), p += 8;
+    s.tmem_base = reinterpret_cast<uint32_t*>(p);
+    return s;
+}
+
+using M = Math<true>;
+
+__device__ __forceinline__ float half_sum(float v) {
+#pragma unroll
+    for (int m = 8; m >= 1; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
+    return v;
+}
+__device__ __forceinline__ float half_max(float v) {
+#pragma unroll
+    for (int m = 8; m >= 1; m >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL, v, m));
+    return v;
+}
+// softmax over the K lanes of this lane's group (K = 2, 4, 8, 16 consecutive lanes)
+__device__ __forceinline__ float group_softmax(float x, int K) {
+    float mx = x;
+    for (int m = K >> 1; m >= 1; m >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, m));
+    const float e = M::exp(x - mx);
+    float sum = e;
+    for (int m = K >> 1; m >= 1; m >>= 1) sum += __shfl_xor_sync(FULL, sum, m);
+    return M::div(e, sum);
+}
+// inverse-CDF draw (A2): idx = min(K-1, #{k : cdf_k <= u}), cdf accumulated in class order; returns 1 if this lane's class is drawn
+__device__ __forceinline__ float draw_onehot(float prob, float u, int K, int lane) {
+    const int k = lane & (K - 1), g0 = lane & ~(K - 1);
+    float cdf = 0.f;
+    for (int i = 0; i < K; ++i) {
+        const float pi = __shfl_sync(FULL, prob, g0 + i);
+        if (i <= k) cdf += pi;
+    }
+    const unsigned hits = __ballot_sync(FULL, (k < K - 1) && (cdf <= u));
+    const unsigned gmask = (K == 32 ? 0xffffffffu : ((1u << K) - 1u)) << g0;
+    const int idx = __popc(hits & gmask);
+    return k == idx ? 1.f : 0.f;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const MrssmWideFwdArgs p) {
+    extern __shared__ unsigned char smem_dyn[];
+    const int D = p.D, KC = D >> 6, NSL = p.NSL, A = p.A, T = p.T, K = p.K, C = 16 / p.K, F = D + 16;
+    const FwdSmem sm = carve(smem_dyn, D, A);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bb = blockIdx.x / NSL, s = blockIdx.x - bb * NSL;
+    const bool imagine = p.imagine != 0;
+
+    // ---- one-time setup ---------------------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) mbar_init(&sm.full[i], 1), mbar_init(&sm.empty[i], 1);
+        mbar_init(sm.accbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    // first projector layer, transposed: w1t[a][j] = asp_w1[j][a]; row A+16 = bias
+    for (int i = tid; i < (A + 16) * D; i += NTHREADS) {
+        const int j = i / (A + 16), a = i - j * (A + 16);
+        sm.w1t[a * D + j] = p.w.asp_w1[i];
+    }
+    for (int j = tid; j < D; j += NTHREADS) sm.w1t[(A + 16) * D + j] = p.w.asp_b1[j];
+    if (tid < 32) sm.b2s[tid] = p.w.asp_b2[s * 32 + tid];
+    if (tid < 96) {
+        const int part = tid >> 5, u = tid & 31;
+        sm.bih[tid] = p.w.b_ih[part * D + s * 32 + u];
+        sm.bhh[tid] = p.w.b_hh[part * D + s * 32 + u];
+        const float* b1 = part == 0 ? p.w.pr_b1 : (part == 1 ? p.w.au_b1 : p.w.vi_b1);
+        sm.bhd[tid] = (b1 != nullptr) ? b1[s * 32 + u] : 0.f;
+    }
+    for (int i = tid; i < 3 * 32 * 16; i += NTHREADS) {  // w2l[h][j][o] = W2_h[o][32 s + j]
+        const int h = i / 512, j = (i >> 4) & 31, o = i & 15;
+        const float* w2 = h == 0 ? p.w.pr_w2 : (h == 1 ? p.w.au_w2 : p.w.vi_w2);
+        sm.w2l[i] = (w2 != nullptr) ? w2[o * D + s * 32 + j] : 0.f;
+    }
+    if (tid < 48) {
+        const int h = tid >> 4, o = tid & 15;
+        const float* b2 = h == 0 ? p.w.pr_b2 : (h == 1 ? p.w.au_b2 : p.w.vi_b2);
+        sm.b2l[tid] = (b2 != nullptr) ? b2[o] : 0.f;
+    }
+    proxy_fence();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *sm.tmem_base;
+
+    // phase-D rows of this CTA
+    const int rpc = (p.B + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int row0 = blockIdx.x * rpc;
+    const int nrows = max(0, min(rpc, p.B - row0));
+    const int FG = D >> 3;
+
+    // hid1 of step tn from zval (the previous step's stochastic state) and the action of step tn
+    auto compute_hid1 = [&](int tn) {
+        __nv_bfloat16* dst = p.rec + (long long)tn * p.t_stride + (long long)P_HID1 * p.plane_stride;
+        for (int item = tid; item < nrows * FG; item += NTHREADS) {
+            const int fg = item / nrows, rl = item - fg * nrows, row = row0 + rl;
+            float acc[8];
+            const float* wb = sm.w1t + fg * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = wb[(A + 16) * D + i];
+            const float* act = p.actions + ((long long)row * T + tn) * A;
+            for (int a = 0; a < A; ++a) {
+                const float x = act[a];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(x, wb[a * D + i], acc[i]);
+            }
+#pragma unroll 4
+            for (int c = 0; c < 16; ++c) {
+                const float z = sm.zval[rl * 16 + c];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(z, wb[(A + c) * D + i], acc[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = M::elu(acc[i]);
+            *reinterpret_cast<uint4*>(dst + pk_off(row >> 7, row & 127, fg * 8, D)) = pack8(acc);
+        }
+    };
+
+    // ---- prologue: z0 -> zval, hid1_0, packed h0 ---------------------------------------------------------------------------
+    for (int i = tid; i < nrows * 16; i += NTHREADS) sm.zval[i] = p.z0[(long long)(row0 + (i >> 4)) * 16 + (i & 15)];
+    for (int item = tid; item < nrows * FG; item += NTHREADS) {
+        const int fg = item / nrows, rl = item - fg * nrows, row = row0 + rl;
+        float v[8];
+        const float4 a = *reinterpret_cast<const float4*>(p.h0 + (long long)row * D + fg * 8);
+        const float4 b = *reinterpret_cast<const float4*>(p.h0 + (long long)row * D + fg * 8 + 4);
+        v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+        *reinterpret_cast<uint4*>(p.h0p + pk_off(row >> 7, row & 127, fg * 8, D)) = pack8(v);
+    }
+    __syncthreads();
+    compute_hid1(0);
+    unsigned epoch = 0;
+    grid_sync(p.bar, epoch, p.status);
+
+    Ring ring;            // producer and MMA issuer walk the same chunk sequence
+    uint32_t accph = 0;   // epilogue warps: parity of the accumulator barrier
+    const uint32_t lboA = BM * 16, sbo = 128;
+    const long long blk = (long long)bb * D * BM;  // element offset of block bb inside a plane
+
+    auto load = [&](const __nv_bfloat16* a_src, const __nv_bfloat16* b_src, uint32_t b_bytes) {
+        mbar_wait(&sm.empty[ring.slot], ring.phase ^ 1);
+        mbar_expect_tx(&sm.full[ring.slot], A_BYTES + b_bytes);
+        unsigned char* st = sm.ring + (size_t)ring.slot * STAGE_BYTES;
+        bulk_g2s(st, a_src, A_BYTES, &sm.full[ring.slot]);
+        bulk_g2s(st + A_BYTES, b_src, b_bytes, &sm.full[ring.slot]);
+        ring.advance(STAGES);
+    };
+    auto mma_chunk = [&](uint32_t tcol, int N, bool first) {
+        mbar_wait(&sm.full[ring.slot], ring.phase);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sm.ring + (size_t)ring.slot * STAGE_BYTES), b0 = a0 + A_BYTES;
+        const uint32_t lboB = N * 16;
+        const uint32_t idesc = idesc_bf16(N, 0, 0);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t da = p.desc_swap ? smem_desc(a0 + kk * 2 * lboA, sbo, lboA) : smem_desc(a0 + kk * 2 * lboA, lboA, sbo);
+            const uint64_t db = p.desc_swap ? smem_desc(b0 + kk * 2 * lboB, sbo, lboB) : smem_desc(b0 + kk * 2 * lboB, lboB, sbo);
+            umma(tmem + tcol, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+        }
+        umma_commit(&sm.empty[ring.slot]);
+        ring.advance(STAGES);
+    };
+    const int row = warp * 32 + lane;                     // epilogue: batch row inside the block (warps 0-3)
+    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int grow = bb * BM + row;                        // row inside the launch group
+    const bool rvalid = grow < p.B;
+
+    for (int t = 0; t < T; ++t) {
+        __nv_bfloat16* rec_t = p.rec + (long long)t * p.t_stride;
+        const __nv_bfloat16* hb_prev = (t == 0) ? p.h0p + blk : (p.rec + (long long)(t - 1) * p.t_stride + (long long)P_HB * p.plane_stride + blk);
+        // =================================== phase A ===================================
+        if (warp == 4) {
+            if (lane == 0) {
+                const __nv_bfloat16* a_src = rec_t + (long long)P_HID1 * p.plane_stride + blk;
+                for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pW2 + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
+                for (int c = 0; c < KC; ++c) load(hb_prev + (long long)c * (BM * 64), p.pWhh + ((long long)s * KC + c) * (96 * 64), 96 * 64 * 2);
+            }
+        } else if (warp == 5) {
+            if (lane == 0) {
+                for (int c = 0; c < KC; ++c) mma_chunk(TM_X2, 32, c == 0);
+                umma_commit(sm.accbar);
+                for (int c = 0; c < KC; ++c) mma_chunk(TM_GH, 96, c == 0);
+            }
+        } else {
+            mbar_wait(sm.accbar, accph), accph ^= 1;
+            tc_fence_after();
+            __nv_bfloat16* x2 = rec_t + (long long)P_X2 * p.plane_stride;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float v[8];
+                tmem_ld8(tlane + TM_X2 + q * 8, v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += sm.b2s[q * 8 + i];
+                *reinterpret_cast<uint4*>(x2 + pk_off(bb, row, s * 32 + q * 8, D)) = pack8(v);
+            }
+        }
+        grid_sync(p.bar, epoch, p.status);
+        // =================================== phase B ===================================
+        if (warp == 4) {
+            if (lane == 0) {
+                const __nv_bfloat16* a_src = rec_t + (long long)P_X2 * p.plane_stride + blk;
+                for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pWih + ((long long)s * KC + c) * (96 * 64), 96 * 64 * 2);
+            }
+        } else if (warp == 5) {
+            if (lane == 0) {
+                for (int c = 0; c < KC; ++c) mma_chunk(TM_GI, 96, c == 0);
+                umma_commit(sm.accbar);  // covers the gh MMAs of phase A as well
+            }
+        } else {
+            mbar_wait(sm.accbar, accph), accph ^= 1;
+            tc_fence_after();
+            const float* hprev = (t == 0) ? p.h0 + (long long)grow * D : p.feature + ((long long)grow * T + (t - 1)) * F;
+            float* hout = p.feature + ((long long)grow * T + t) * F;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                float gi[8], gh[8], r[8], z[8], n[8], hn[8], h[8];
+                tmem_ld8(tlane + TM_GI + q * 8, gi);
+                tmem_ld8(tlane + TM_GH + q * 8, gh);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = M::sigmoid(gi[i] + gh[i] + sm.bih[q * 8 + i] + sm.bhh[q * 8 + i]);
+                tmem_ld8(tlane + TM_GI + 32 + q * 8, gi);
+                tmem_ld8(tlane + TM_GH + 32 + q * 8, gh);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) z[i] = M::sigmoid(gi[i] + gh[i] + sm.bih[32 + q * 8 + i] + sm.bhh[32 + q * 8 + i]);
+                tmem_ld8(tlane + TM_GI + 64 + q * 8, gi);
+                tmem_ld8(tlane + TM_GH + 64 + q * 8, gh);
+                float hp[8];
+                if (rvalid) {
+                    const float4 a = *reinterpret_cast<const float4*>(hprev + s * 32 + q * 8);
+                    const float4 b = *reinterpret_cast<const float4*>(hprev + s * 32 + q * 8 + 4);
+                    hp[0] = a.x, hp[1] = a.y, hp[2] = a.z, hp[3] = a.w, hp[4] = b.x, hp[5] = b.y, hp[6] = b.z, hp[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) hp[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    hn[i] = gh[i] + sm.bhh[64 + q * 8 + i];
+                    n[i] = M::tanh(gi[i] + sm.bih[64 + q * 8 + i] + r[i] * hn[i]);
+                    h[i] = (1.f - z[i]) * n[i] + z[i] * hp[i];
+                }
+                if (rvalid) {
+                    *reinterpret_cast<float4*>(hout + s * 32 + q * 8) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4*>(hout + s * 32 + q * 8 + 4) = make_float4(h[4], h[5], h[6], h[7]);
+                }
+                const long long o = pk_off(bb, row, s * 32 + q * 8, D);
+                *reinterpret_cast<uint4*>(rec_t + (long long)P_HB * p.plane_stride + o) = pack8(h);
+                if (p.t_stride != 0) {  // gate record for the backward
+                    *reinterpret_cast<uint4*>(rec_t + (long long)P_R * p.plane_stride + o) = pack8(r);
+                    *reinterpret_cast<uint4*>(rec_t + (long long)P_Z * p.plane_stride + o) = pack8(z);
+                    *reinterpret_cast<uint4*>(rec_t + (long long)P_N * p.plane_stride + o) = pack8(n);
+                    *reinterpret_cast<uint4*>(rec_t + (long long)P_HN * p.plane_stride + o) = pack8(hn);
+                }
+            }
+        }
+        grid_sync(p.bar, epoch, p.status);
+        // =================================== phase C ===================================
+        if (warp == 4) {
+            if (lane == 0) {
+                const __nv_bfloat16* a_src = rec_t + (long long)P_HB * p.plane_stride + blk;
+                for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pWhd + ((long long)s * KC + c) * (96 * 64), 96 * 64 * 2);
+                if (!imagine) {
+                    load(p.emb_a + (long long)t * p.emb_t_stride + (long long)bb * (BM * 64), p.pWae + (long long)s * (32 * 64), 32 * 64 * 2);
+                    load(p.emb_v + (long long)t * p.emb_t_stride + (long long)bb * (BM * 64), p.pWve + (long long)s * (32 * 64), 32 * 64 * 2);
+                }
+            }
+        } else if (warp == 5) {
+            if (lane == 0) {
+                for (int c = 0; c < KC; ++c) mma_chunk(TM_HD, 96, c == 0);
+                if (!imagine) {
+                    mma_chunk(TM_HD + 32, 32, false);
+                    mma_chunk(TM_HD + 64, 32, false);
+                }
+                umma_commit(sm.accbar);
+            }
+        } else {
+            mbar_wait(sm.accbar, accph), accph ^= 1;
+            tc_fence_after();
+            float* part = p.part + ((long long)grow * NSL + s) * 48;
+            const int nheads = imagine ? 1 : 3;
+#pragma unroll 1
+            for (int h = 0; h < nheads; ++h) {
+                float acc[16];
+#pragma unroll
+                for (int o = 0; o < 16; ++o) acc[o] = 0.f;
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    float v[8];
+                    tmem_ld8(tlane + TM_HD + h * 32 + q * 8, v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = M::elu(v[i] + sm.bhd[h * 32 + q * 8 + i]);
+                    if (p.t_stride != 0)
+                        *reinterpret_cast<uint4*>(rec_t + (long long)(P_PH + h) * p.plane_stride + pk_off(bb, row, s * 32 + q * 8, D)) = pack8(v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float4* w = reinterpret_cast<const float4*>(sm.w2l + (h * 32 + q * 8 + i) * 16);
+#pragma unroll
+                        for (int o4 = 0; o4 < 4; ++o4) {
+                            const float4 ww = w[o4];
+                            acc[4 * o4] = fmaf(v[i], ww.x, acc[4 * o4]), acc[4 * o4 + 1] = fmaf(v[i], ww.y, acc[4 * o4 + 1]);
+                            acc[4 * o4 + 2] = fmaf(v[i], ww.z, acc[4 * o4 + 2]), acc[4 * o4 + 3] = fmaf(v[i], ww.w, acc[4 * o4 + 3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o4 = 0; o4 < 4; ++o4)
+                    *reinterpret_cast<float4*>(part + h * 16 + o4 * 4) = make_float4(acc[4 * o4], acc[4 * o4 + 1], acc[4 * o4 + 2], acc[4 * o4 + 3]);
+            }
+        }
+        grid_sync(p.bar, epoch, p.status);
+        // =================================== phase D ===================================
+        {
+            const int j = lane & 15, g = j / K;
+            for (int base = warp * 2; base < nrows; base += (NTHREADS / 32) * 2) {
+                const int rl = base + (lane >> 4);
+                const bool valid = rl < nrows;
+                const int rw = row0 + (valid ? rl : nrows - 1);
+                const float* part = p.part + (long long)rw * NSL * 48;
+                float lp = sm.b2l[j], la = sm.b2l[16 + j], lv = sm.b2l[32 + j];
+                for (int sl = 0; sl < NSL; ++sl) {
+                    lp += __ldcg(part + sl * 48 + j);  // written by other CTAs this step: L2, not a stale L1 line
+                    if (!imagine) la += __ldcg(part + sl * 48 + 16 + j), lv += __ldcg(part + sl * 48 + 32 + j);
+                }
+                const long long bt = (long long)rw * T + t;
+                const float pp = group_softmax(lp, K);
+                float zs;  // the sample fed back
+                if (!imagine) {
+                    // flat log-softmaxes, PoE = sum, MoE = logsumexp of the three experts (1/3 each)
+                    const float ma = half_max(la), mv = half_max(lv);
+                    const float lsa = la - ma - M::log(half_sum(M::exp(la - ma)));
+                    const float lsv = lv - mv - M::log(half_sum(M::exp(lv - mv)));
+                    const float f = lsa + lsv, mx = fmaxf(lsa, fmaxf(lsv, f));
+                    const float mixed = -1.0986122886681098f + mx + M::log(M::exp(lsa - mx) + M::exp(lsv - mx) + M::exp(f - mx));
+                    const float q = group_softmax(mixed, K);
+                    const float u = p.u_post[bt * C + g];
+                    zs = draw_onehot(q, u, K, lane);
+                    const float klt = half_sum(q * (clamp_log<true>(q) - clamp_log<true>(pp)));
+                    if (valid) {
+                        if (p.logits != nullptr) p.logits[bt * 32 + j] = la, p.logits[bt * 32 + 16 + j] = lv;
+                        p.post_probs[bt * 16 + j] = q;
+                        if (j == 0) p.kl[bt] = klt;
+                    }
+                    if (p.u_prior != nullptr) {
+                        const float zp = draw_onehot(pp, p.u_prior[bt * C + g], K, lane);
+                        if (valid && p.prior_stoch != nullptr) p.prior_stoch[bt * 16 + j] = zp;
+                    }
+                } else {
+                    zs = draw_onehot(pp, p.u_prior[bt * C + g], K, lane);
+                }
+                if (valid) {
+                    p.prior_probs[bt * 16 + j] = pp;
+                    p.feature[bt * F + D + j] = zs;
+                    sm.zval[rl * 16 + j] = zs;
+                }
+            }
+            __syncthreads();
+            if (t + 1 < T) compute_hid1(t + 1);
+        }
+        grid_sync(p.bar, epoch, p.status);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    __syncwarp();
+    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// ---- packing kernels ---------------------------------------------------------------------------------------------------
+__global__ void wide_pack_weights_kernel(const WidePackJobs jobs) {
+    const WidePackJob& j = jobs.job[blockIdx.y];
+    const int N = 32 * j.nparts, KC = j.K >> 6;
+    const long long total = (long long)jobs.NSL * KC * 8 * N;  // 16-byte groups
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % N);
+        const int kg = (int)((i / N) % 8);
+        const int c = (int)((i / (8LL * N)) % KC);
+        const int s = (int)(i / (8LL * N * KC));
+        const int part = n >> 5, u = n & 31;
+        const float* src = j.src[part] + (long long)(s * 32 + u) * j.ld[part] + j.coloff + c * 64 + kg * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = src[e];
+        *reinterpret_cast<uint4*>(j.dst + i * 8) = pack8(v);
+    }
+}
+
+__global__ void wide_pack_rows_kernel(const float* __restrict__ src, int B, int T, int Fc, int ld, int coloff, __nv_bfloat16* __restrict__ dst,
+                                      int blocks) {
+    const int FG = Fc >> 3;
+    const long long total = (long long)B * T * FG;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int fg = (int)(i % FG);
+        const int t = (int)((i / FG) % T);
+        const int b = (int)(i / ((long long)FG * T));
+        const float* s = src + ((long long)b * T + t) * ld + coloff + fg * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = s[e];
+        *reinterpret_cast<uint4*>(dst + ((((long long)t * blocks + (b >> 7)) * FG + fg) * BM + (b & 127)) * 8) = pack8(v);
+    }
+}
+
+}  // namespace wide
+
+size_t mrssm_wide_fwd_smem(int D) { return wide::fwd_smem_bytes(D, 8); }
+
+cudaError_t launch_mrssm_wide_fwd(const MrssmWideFwdArgs& a, cudaStream_t s) {
+    const size_t smem = wide::fwd_smem_bytes(a.D, a.A);
+    cudaError_t e = cudaFuncSetAttribute(wide::mrssm_wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    MrssmWideFwdArgs args = a;
+    void* params[] = {&args};
+    return cudaLaunchCooperativeKernel((const void*)wide::mrssm_wide_fwd_kernel, dim3(a.NBB * a.NSL), dim3(wide::NTHREADS), params, smem, s);
+}
+
+cudaError_t launch_wide_pack_weights(const WidePackJobs& jobs, cudaStream_t s) {
+    wide::wide_pack_weights_kernel<<<dim3(64, jobs.njobs), 256, 0, s>>>(jobs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wide_pack_rows(const float* src, int B, int T, int F, int ld, int coloff, __nv_bfloat16* dst, int blocks, cudaStream_t s) {
+    const long long total = (long long)B * T * (F >> 3);
+    const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    wide::wide_pack_rows_kernel<<<grid > 0 ? grid : 1, 256, 0, s>>>(src, B, T, F, ld, coloff, dst, blocks);
+    return cudaGetLastError();
+}
+
+}  // namespace rssm

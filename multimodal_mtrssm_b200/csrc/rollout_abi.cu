@@ -8,6 +8,7 @@
 #include <cstdio>
 
 #include "kernels.h"
+#include "wide_common.cuh"
 
 namespace {
 
@@ -95,6 +96,308 @@ void set_out(rssm::WgradMmaArgs& a, int id, float* dW, int ldw, int kvalid, floa
     o.dW = dW, o.ldw = ldw, o.kvalid = kvalid, o.db0 = db0, o.db1 = db1;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// wide MoPoE-MRSSM family (D = H in 64..512): workspace layout + launch sequence (kernels: mrssm_wide_*.cu)
+// ---------------------------------------------------------------------------------------------------
+bool is_wide(const RssmMrssmDims* d) { return d && d->D != 32; }
+
+int check_mrssm_wide(const RssmMrssmDims* d) {
+    if (!d) return fail("dims is NULL");
+    if (d->B < 1 || d->T < 1) return fail("B and T must be >= 1 (got B=%d T=%d)", d->B, d->T);
+    if (d->D != d->H || d->D % 128 != 0 || d->D < 128 || d->D > 512 || d->E != 64)
+        return fail("unsupported sizes D=%d H=%d E=%d: this build instantiates deter=hidden=32 (default family) or "
+                    "deter=hidden in {128,256,384,512} (wide family), embed=64", d->D, d->H, d->E);
+    if (d->C * d->K != 16 || !class_size_ok(d->K))
+        return fail("unsupported distribution_config (class=%d, category=%d): need class*category = 16, class in {2,4,8,16}", d->K,
+                    d->C);
+    if (d->A < 1 || d->A > 8) return fail("unsupported action_size %d: need 1..8", d->A);
+    if (d->precision != RSSM_PRECISION_BF16)
+        return fail("the wide family (deter=%d) is built for RSSM_PRECISION_BF16 only (got precision %d)", d->D, d->precision);
+    return 0;
+}
+
+size_t wide_saved_planes_bytes(const RssmMrssmDims* d) {
+    return (size_t)d->T * rssm::wide::NPLANES * ((size_t)((d->B + 127) / 128) * d->D * 128) * 2;
+}
+
+struct WideLayout {
+    int D, KC, NSL, NBBT, NBBG, ngroups;
+    long long plane;  // elements of one record plane = NBBT * D * 128
+    size_t pW2, pWhh, pWih, pWhd, pWae, pWve, emb_a, emb_v, h0p, part, rec1, bar, total_fwd;
+};
+
+int wide_layout(const RssmMrssmDims* d, bool need_rec1, WideLayout* L) {
+    int dev = 0, nsm = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+    if (check_cuda(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev), "cudaDeviceGetAttribute")) return 1;
+    L->D = d->D, L->KC = d->D / 64, L->NSL = d->D / 32;
+    L->NBBT = (d->B + 127) / 128;
+    L->NBBG = nsm / L->NSL;
+    if (L->NBBG < 1) return fail("device has %d SMs, the wide kernels need at least %d", nsm, L->NSL);
+    if (L->NBBG > L->NBBT) L->NBBG = L->NBBT;
+    L->ngroups = (L->NBBT + L->NBBG - 1) / L->NBBG;
+    L->plane = (long long)L->NBBT * d->D * 128;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = rssm::wide::align_up(o + bytes, 256); return at; };
+    const size_t DD = (size_t)d->D * d->D * 2;
+    L->pW2 = take(DD), L->pWhh = take(3 * DD), L->pWih = take(3 * DD), L->pWhd = take(3 * DD);
+    L->pWae = take((size_t)d->D * 64 * 2), L->pWve = take((size_t)d->D * 64 * 2);
+    const size_t emb = (size_t)d->T * L->NBBT * 64 * 128 * 2;
+    L->emb_a = take(emb), L->emb_v = take(emb);
+    L->h0p = take((size_t)L->plane * 2);
+    L->part = take((size_t)L->NBBT * 128 * L->NSL * 48 * 4);
+    L->rec1 = take(need_rec1 ? (size_t)rssm::wide::NPLANES * L->plane * 2 : 0);
+    L->bar = take(256 * (size_t)(L->ngroups + 1));
+    L->total_fwd = o;
+    return 0;
+}
+
+struct WideBwdLayout {
+    size_t pW1x, pWhdT, pWgT, pWihTn, pWhhTn, pW2T, pWaeT, pWveT, ones, drec, carry, h0p, emb_a, emb_v, tiles, bar, total;
+    long long dt_stride, dlg, xin;  // elements: gradient-plane step, narrow planes inside a step
+};
+constexpr int MAX_WIDE_TILES = 256;
+
+void wide_bwd_layout(const RssmMrssmDims* d, const WideLayout& L, WideBwdLayout* W) {
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = rssm::wide::align_up(o + bytes, 256); return at; };
+    const size_t D = d->D, DD = D * D * 2;
+    W->pW1x = take(32 * D * 2), W->pWhdT = take(3 * DD), W->pWgT = take(4 * DD), W->pWihTn = take(DD), W->pWhhTn = take(DD);
+    W->pW2T = take(DD), W->pWaeT = take(64 * D * 2), W->pWveT = take(64 * D * 2), W->ones = take(16 * 128 * 8 * 2);
+    W->dlg = (long long)rssm::wide::NDPLANES * L.plane;
+    W->xin = W->dlg + (long long)L.NBBT * 48 * 128;
+    W->dt_stride = W->xin + (long long)L.NBBT * 32 * 128;
+    W->drec = take((size_t)d->T * W->dt_stride * 2);
+    W->carry = take((size_t)L.NBBT * 128 * D * 4);
+    W->h0p = take((size_t)L.plane * 2);
+    const size_t emb = (size_t)d->T * L.NBBT * 64 * 128 * 2;
+    W->emb_a = take(emb), W->emb_v = take(emb);
+    W->tiles = take(sizeof(rssm::WideWgradTile) * MAX_WIDE_TILES);
+    W->bar = take(256 * (size_t)(L.ngroups + 1));
+    W->total = o;
+}
+
+size_t wide_bwd_workspace(const RssmMrssmDims* d, const WideLayout& L) {
+    WideBwdLayout W;
+    wide_bwd_layout(d, L, &W);
+    return W.total;
+}
+
+
+int wide_pack_weights(const RssmMrssmDims* d, const RssmMrssmWeights* w, char* ws, const WideLayout& L, bool imagine, cudaStream_t s) {
+    const int D = d->D;
+    rssm::WidePackJobs J{};
+    J.NSL = L.NSL;
+    auto job = [&](const float* a, int lda, const float* b, int ldb, const float* c, int ldc, int nparts, int coloff, int K, size_t off) {
+        rssm::WidePackJob& j = J.job[J.njobs++];
+        j.src[0] = a, j.src[1] = b, j.src[2] = c, j.ld[0] = lda, j.ld[1] = ldb, j.ld[2] = ldc;
+        j.nparts = nparts, j.coloff = coloff, j.K = K, j.dst = reinterpret_cast<__nv_bfloat16*>(ws + off);
+    };
+    job(w->asp_w2, D, nullptr, 0, nullptr, 0, 1, 0, D, L.pW2);
+    job(w->w_hh, D, w->w_hh + (size_t)D * D, D, w->w_hh + 2 * (size_t)D * D, D, 3, 0, D, L.pWhh);
+    job(w->w_ih, D, w->w_ih + (size_t)D * D, D, w->w_ih + 2 * (size_t)D * D, D, 3, 0, D, L.pWih);
+    if (imagine) {
+        job(w->pr_w1, D, w->pr_w1, D, w->pr_w1, D, 3, 0, D, L.pWhd);
+    } else {
+        job(w->pr_w1, D, w->au_w1, D + 64, w->vi_w1, D + 64, 3, 0, D, L.pWhd);
+        job(w->au_w1, D + 64, nullptr, 0, nullptr, 0, 1, D, 64, L.pWae);
+        job(w->vi_w1, D + 64, nullptr, 0, nullptr, 0, 1, D, 64, L.pWve);
+    }
+    g_launches.fetch_add(1);
+    return check_cuda(rssm::launch_wide_pack_weights(J, s), "wide weight packing launch");
+}
+
+int wide_mrssm_fwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const RssmMrssmInputs* in, const RssmMrssmOutputs* out,
+                   cudaStream_t s, bool imagine) {
+    if (check_mrssm_wide(d)) return 1;
+    const bool save = !imagine && out->saved != nullptr;
+    WideLayout L;
+    if (wide_layout(d, !save, &L)) return 1;
+    if (out->workspace == nullptr || out->workspace_bytes < L.total_fwd)
+        return fail("wide family: workspace of %zu bytes required (rssm_mrssm_workspace_bytes), got %zu", L.total_fwd,
+                    out->workspace ? out->workspace_bytes : (size_t)0);
+    if ((reinterpret_cast<uintptr_t>(out->workspace) & 255) != 0) return fail("workspace must be 256-byte aligned");
+    char* ws = static_cast<char*>(out->workspace);
+    const int D = d->D, T = d->T, A = d->A, F = D + 16, C = d->C;
+    // pad rows of the last batch block take part in the contractions: keep them finite
+    if (d->B % 128 != 0) {
+        if (check_cuda(cudaMemsetAsync(ws + L.emb_a, 0, L.bar - L.emb_a, s), "workspace memset")) return 1;
+        if (save && check_cuda(cudaMemsetAsync(out->saved, 0, (size_t)T * rssm::wide::NPLANES * L.plane * 2, s), "record memset")) return 1;
+    }
+    if (check_cuda(cudaMemsetAsync(ws + L.bar, 0, 256 * (size_t)(L.ngroups + 1), s), "barrier memset")) return 1;
+    if (wide_pack_weights(d, w, ws, L, imagine, s)) return 1;
+    if (!imagine) {
+        g_launches.fetch_add(2);
+        if (check_cuda(rssm::launch_wide_pack_rows(in->embed_a, d->B, T, 64, 64, 0, reinterpret_cast<__nv_bfloat16*>(ws + L.emb_a), L.NBBT, s),
+                       "embedding packing launch"))
+            return 1;
+        if (check_cuda(rssm::launch_wide_pack_rows(in->embed_v, d->B, T, 64, 64, 0, reinterpret_cast<__nv_bfloat16*>(ws + L.emb_v), L.NBBT, s),
+                       "embedding packing launch"))
+            return 1;
+    }
+    const char* swap_env = getenv("RSSM_WIDE_DESC_SWAP");
+    for (int g = 0; g < L.ngroups; ++g) {
+        const int bb0 = g * L.NBBG, nbb = (L.NBBT - bb0 < L.NBBG) ? L.NBBT - bb0 : L.NBBG;
+        const long long r0 = (long long)bb0 * 128;
+        rssm::MrssmWideFwdArgs a{};
+        a.B = (int)((d->B - r0 < (long long)nbb * 128) ? d->B - r0 : (long long)nbb * 128);
+        a.T = T, a.A = A, a.K = d->K, a.D = D, a.NBB = nbb, a.NSL = L.NSL, a.imagine = imagine ? 1 : 0;
+        a.desc_swap = (swap_env && swap_env[0] == '1') ? 1 : 0;
+        a.plane_stride = L.plane, a.t_stride = save ? (long long)rssm::wide::NPLANES * L.plane : 0;
+        a.emb_t_stride = (long long)L.NBBT * 64 * 128;
+        a.w = *w;
+        auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+        a.pW2 = bf(L.pW2), a.pWhh = bf(L.pWhh), a.pWih = bf(L.pWih), a.pWhd = bf(L.pWhd), a.pWae = bf(L.pWae), a.pWve = bf(L.pWve);
+        a.actions = in->actions + r0 * T * A, a.h0 = in->h0 + r0 * D, a.z0 = in->z0 + r0 * 16;
+        a.u_post = in->u_post ? in->u_post + r0 * T * C : nullptr, a.u_prior = in->u_prior ? in->u_prior + r0 * T * C : nullptr;
+        a.emb_a = bf(L.emb_a) + (long long)bb0 * 64 * 128, a.emb_v = bf(L.emb_v) + (long long)bb0 * 64 * 128;
+        a.feature = out->feature + r0 * T * F, a.prior_probs = out->prior_probs + r0 * T * 16;
+        a.post_probs = out->post_probs ? out->post_probs + r0 * T * 16 : nullptr;
+        a.prior_stoch = out->prior_stoch ? out->prior_stoch + r0 * T * 16 : nullptr;
+        a.kl = out->kl ? out->kl + r0 * T : nullptr;
+        a.rec = (save ? static_cast<__nv_bfloat16*>(out->saved) : bf(L.rec1)) + (long long)bb0 * D * 128;
+        a.h0p = bf(L.h0p) + (long long)bb0 * D * 128;
+        a.part = reinterpret_cast<float*>(ws + L.part) + r0 * L.NSL * 48;
+        a.logits = save ? reinterpret_cast<float*>(static_cast<char*>(out->saved) + wide_saved_planes_bytes(d)) + r0 * T * 32 : nullptr;
+        a.bar = reinterpret_cast<unsigned*>(ws + L.bar + 256 * (size_t)g);
+        a.status = reinterpret_cast<int*>(ws + L.bar + 256 * (size_t)L.ngroups);
+        g_launches.fetch_add(1);
+        if (check_cuda(rssm::launch_mrssm_wide_fwd(a, s), imagine ? "wide mrssm imagine launch" : "wide mrssm forward launch")) return 1;
+    }
+    return 0;
+}
+
+int wide_mrssm_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const RssmMrssmInputs* in, const RssmMrssmOutputs* fo,
+                   const RssmMrssmUpstream* up, const RssmMrssmInputGrads* gin, const RssmMrssmWeightGrads* gw, cudaStream_t s) {
+    if (check_mrssm_wide(d)) return 1;
+    WideLayout L;
+    if (wide_layout(d, false, &L)) return 1;
+    WideBwdLayout W;
+    wide_bwd_layout(d, L, &W);
+    if (gin->workspace == nullptr || gin->workspace_bytes < W.total)
+        return fail("wide family: backward workspace of %zu bytes required (rssm_mrssm_workspace_bytes(dims, 1)), got %zu", W.total,
+                    gin->workspace ? gin->workspace_bytes : (size_t)0);
+    if ((reinterpret_cast<uintptr_t>(gin->workspace) & 255) != 0) return fail("workspace must be 256-byte aligned");
+    char* ws = static_cast<char*>(gin->workspace);
+    auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+    const int D = d->D, T = d->T, A = d->A, F = D + 16;
+    const long long plane = L.plane, tstride = (long long)rssm::wide::NPLANES * plane;
+    if (d->B % 128 != 0 && check_cuda(cudaMemsetAsync(ws + W.drec, 0, W.tiles - W.drec, s), "workspace memset")) return 1;
+    if (check_cuda(cudaMemsetAsync(ws + W.bar, 0, 256 * (size_t)(L.ngroups + 1), s), "barrier memset")) return 1;
+    const __nv_bfloat16* rec = static_cast<const __nv_bfloat16*>(fo->saved);
+    const float* logits = reinterpret_cast<const float*>(static_cast<const char*>(fo->saved) + wide_saved_planes_bytes(d));
+
+    rssm::MrssmWideBwdArgs a{};
+    a.T = T, a.A = A, a.K = d->K, a.D = D, a.NSL = L.NSL, a.kl_wq = up->kl_wq, a.kl_wp = up->kl_wp;
+    a.plane_stride = plane, a.t_stride = tstride, a.dt_stride = W.dt_stride;
+    a.w = *w;
+    a.pW1x = bf(W.pW1x), a.pWhdT = bf(W.pWhdT), a.pWgT = bf(W.pWgT), a.pWihTn = bf(W.pWihTn), a.pWhhTn = bf(W.pWhhTn), a.pW2T = bf(W.pW2T);
+    g_launches.fetch_add(2);
+    if (check_cuda(rssm::launch_wide_pack_bwd_weights(a, s), "wide backward weight packing launch")) return 1;
+    if (check_cuda(rssm::launch_wide_pack_dembed(w->au_w1, w->vi_w1, D, bf(W.pWaeT), bf(W.pWveT), bf(W.ones), s), "wide embed-weight packing launch"))
+        return 1;
+    for (int g = 0; g < L.ngroups; ++g) {
+        const int bb0 = g * L.NBBG, nbb = (L.NBBT - bb0 < L.NBBG) ? L.NBBT - bb0 : L.NBBG;
+        const long long r0 = (long long)bb0 * 128, boff = (long long)bb0 * D * 128;
+        a.B = (int)((d->B - r0 < (long long)nbb * 128) ? d->B - r0 : (long long)nbb * 128);
+        a.NBB = nbb;
+        a.rec = rec + boff, a.drec = bf(W.drec) + boff;
+        a.dlg_off = W.dlg - boff + (long long)bb0 * 48 * 128, a.xin_off = W.xin - boff + (long long)bb0 * 32 * 128;
+        a.logits = logits + r0 * T * 32;
+        a.feature = fo->feature + r0 * T * F, a.prior_probs = fo->prior_probs + r0 * T * 16, a.post_probs = fo->post_probs + r0 * T * 16;
+        a.h0 = in->h0 + r0 * D, a.z0 = in->z0 + r0 * 16, a.actions = in->actions + r0 * T * A;
+        a.d_feature = up->d_feature + r0 * T * F;
+        a.d_prior_probs = up->d_prior_probs ? up->d_prior_probs + r0 * T * 16 : nullptr;
+        a.d_post_probs = up->d_post_probs ? up->d_post_probs + r0 * T * 16 : nullptr;
+        a.d_prior_stoch = up->d_prior_stoch ? up->d_prior_stoch + r0 * T * 16 : nullptr;
+        a.d_kl = up->d_kl ? up->d_kl + r0 * T : nullptr;
+        a.d_actions = gin->d_actions ? gin->d_actions + r0 * T * A : nullptr;
+        a.d_h0 = gin->d_h0 + r0 * D, a.d_z0 = gin->d_z0 + r0 * 16;
+        a.carry = reinterpret_cast<float*>(ws + W.carry) + r0 * D;
+        a.bar = reinterpret_cast<unsigned*>(ws + W.bar + 256 * (size_t)g);
+        a.status = reinterpret_cast<int*>(ws + W.bar + 256 * (size_t)L.ngroups);
+        g_launches.fetch_add(1);
+        if (check_cuda(rssm::launch_mrssm_wide_bwd(a, s), "wide mrssm backward launch")) return 1;
+    }
+    // ---- embedding gradients ------------------------------------------------------------------------------------------------
+    {
+        rssm::WideDembedArgs e{};
+        e.B = d->B, e.T = T, e.D = D, e.NBBT = L.NBBT, e.dt_stride = W.dt_stride;
+        e.dah = bf(W.drec) + (long long)rssm::wide::DP_AH * plane, e.dvh = bf(W.drec) + (long long)rssm::wide::DP_VH * plane;
+        e.pWaeT = bf(W.pWaeT), e.pWveT = bf(W.pWveT), e.d_embed_a = gin->d_embed_a, e.d_embed_v = gin->d_embed_v;
+        g_launches.fetch_add(1);
+        if (check_cuda(rssm::launch_wide_dembed(e, s), "wide embedding-gradient launch")) return 1;
+    }
+    if (gw == nullptr) return 0;
+    // ---- weight gradients: tile table ------------------------------------------------------------------------------------------
+    g_launches.fetch_add(3);
+    if (check_cuda(rssm::launch_wide_pack_rows(in->h0, d->B, 1, D, D, 0, bf(W.h0p), L.NBBT, s), "h0 packing launch")) return 1;
+    if (check_cuda(rssm::launch_wide_pack_rows(in->embed_a, d->B, T, 64, 64, 0, bf(W.emb_a), L.NBBT, s), "embedding packing launch")) return 1;
+    if (check_cuda(rssm::launch_wide_pack_rows(in->embed_v, d->B, T, 64, 64, 0, bf(W.emb_v), L.NBBT, s), "embedding packing launch")) return 1;
+    static thread_local rssm::WideWgradTile tiles[MAX_WIDE_TILES];
+    int nt = 0;
+    const long long bstrideD = (long long)D * 128;
+    const __nv_bfloat16* dr = bf(W.drec);
+    auto dplane = [&](int pl, int f0) { return dr + (long long)pl * plane + (long long)(f0 / 8) * 1024; };
+    auto fplane = [&](int pl, int f0) { return rec + (long long)pl * plane + (long long)(f0 / 8) * 1024; };
+    auto add = [&](const __nv_bfloat16* y, long long yt, long long yb, const __nv_bfloat16* x, const __nv_bfloat16* x0, long long xt, long long xb,
+                   int shift, int N, int mvalid, int nvalid, float* dW, float* db, long long sm, long long sn) {
+        rssm::WideWgradTile& t = tiles[nt++];
+        t.y = y, t.x = x, t.x0 = x0, t.y_tstride = yt, t.y_bstride = yb, t.x_tstride = xt, t.x_bstride = xb, t.x_shift = shift;
+        t.N = N, t.mvalid = mvalid, t.nvalid = nvalid, t.dW = dW, t.db = db, t.sm = sm, t.sn = sn;
+    };
+    const int MT = D / 128;
+    // Y = gradient plane `ypl`, X = record plane `xpl` (all D input features, in N tiles of <= 256)
+    auto dense = [&](int ypl, int xpl, int shift, float* dW, long long ldw, float* db) {
+        for (int mt = 0; mt < MT; ++mt)
+            for (int n0 = 0; n0 < D; n0 += 256) {
+                const int N = D - n0 < 256 ? D - n0 : 256;
+                add(dplane(ypl, mt * 128), W.dt_stride, bstrideD, fplane(xpl, n0), shift ? bf(W.h0p) + (long long)(n0 / 8) * 1024 : nullptr, tstride,
+                    bstrideD, shift, N, 128, N, dW + (long long)mt * 128 * ldw + n0, (n0 == 0 && db) ? db + mt * 128 : nullptr, ldw, 1);
+            }
+    };
+    using namespace rssm::wide;
+    const int ih_pl[3] = {DP_GR, DP_GZ, DP_GIN}, hh_pl[3] = {DP_GR, DP_GZ, DP_GHN};
+    for (int g = 0; g < 3; ++g) {
+        dense(ih_pl[g], P_X2, 0, gw->w_ih + (size_t)g * D * D, D, gw->b_ih + g * D);
+        dense(hh_pl[g], P_HB, 1, gw->w_hh + (size_t)g * D * D, D, gw->b_hh + g * D);
+    }
+    dense(DP_X2, P_HID1, 0, gw->asp_w2, D, gw->asp_b2);
+    dense(DP_PH, P_HB, 0, gw->pr_w1, D, gw->pr_b1);
+    dense(DP_AH, P_HB, 0, gw->au_w1, D + 64, gw->au_b1);
+    dense(DP_VH, P_HB, 0, gw->vi_w1, D + 64, gw->vi_b1);
+    const long long embt = (long long)L.NBBT * 64 * 128;
+    for (int mt = 0; mt < MT; ++mt) {
+        add(dplane(DP_AH, mt * 128), W.dt_stride, bstrideD, bf(W.emb_a), nullptr, embt, 64 * 128, 0, 64, 128, 64,
+            gw->au_w1 + (size_t)mt * 128 * (D + 64) + D, nullptr, D + 64, 1);
+        add(dplane(DP_VH, mt * 128), W.dt_stride, bstrideD, bf(W.emb_v), nullptr, embt, 64 * 128, 0, 64, 128, 64,
+            gw->vi_w1 + (size_t)mt * 128 * (D + 64) + D, nullptr, D + 64, 1);
+        add(dplane(DP_H1, mt * 128), W.dt_stride, bstrideD, dr + W.xin, nullptr, W.dt_stride, 32 * 128, 0, 32, 128, A + 16,
+            gw->asp_w1 + (size_t)mt * 128 * (A + 16), gw->asp_b1 + mt * 128, A + 16, 1);
+    }
+    float* w2g[3] = {gw->pr_w2, gw->au_w2, gw->vi_w2};
+    float* b2g[3] = {gw->pr_b2, gw->au_b2, gw->vi_b2};
+    for (int h = 0; h < 3; ++h) {
+        const __nv_bfloat16* dl = dr + W.dlg + (long long)h * 2048;
+        for (int mt = 0; mt < MT; ++mt)  // dW2_h[n][m] = sum_rows hid_h[row][m] * dlogit_h[row][n]
+            add(fplane(P_PH + h, mt * 128), tstride, bstrideD, dl, nullptr, W.dt_stride, 48 * 128, 0, 16, 128, 16, w2g[h] + mt * 128, nullptr, 1, D);
+        add(bf(W.ones), 0, 0, dl, nullptr, W.dt_stride, 48 * 128, 0, 16, 1, 16, b2g[h], nullptr, 0, 1);  // column sums
+    }
+    if (nt > MAX_WIDE_TILES) return fail("internal: %d weight-gradient tiles", nt);
+    if (check_cuda(cudaMemcpyAsync(ws + W.tiles, tiles, sizeof(rssm::WideWgradTile) * nt, cudaMemcpyHostToDevice, s), "tile table copy")) return 1;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int nblocks = T * L.NBBT;
+    int nsplit = (3 * nsm) / nt;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > nblocks) nsplit = nblocks;
+    g_launches.fetch_add(1);
+    return check_cuda(rssm::launch_wide_wgrad(reinterpret_cast<const rssm::WideWgradTile*>(ws + W.tiles), nt, nsplit, T, L.NBBT, bf(W.ones), s),
+                      "wide weight-gradient launch");
+}
+
 }  // namespace
 
 extern "C" {
@@ -103,12 +406,25 @@ int rssm_abi_version(void) { return RSSM_ABI_VERSION; }
 const char* rssm_last_error(void) { return g_err; }
 long long rssm_kernel_launch_count(void) { return g_launches.load(); }
 
+size_t rssm_mrssm_saved_bytes(const RssmMrssmDims* d) {
+    if (!d) return 0;
+    if (!is_wide(d)) return (size_t)d->B * d->T * MRSSM_SAVED_FLOATS * (d->precision == RSSM_PRECISION_FP32 ? 4 : 2);
+    if (check_mrssm_wide(d)) return 0;
+    return wide_saved_planes_bytes(d) + (size_t)((d->B + 127) / 128) * 128 * d->T * 32 * 4;
+}
+size_t rssm_mrssm_workspace_bytes(const RssmMrssmDims* d, int pass) {
+    if (!d || !is_wide(d) || check_mrssm_wide(d)) return 0;
+    WideLayout L;
+    if (wide_layout(d, true, &L)) return 0;
+    return pass == 0 ? L.total_fwd : wide_bwd_workspace(d, L);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // MoPoE-MRSSM
 // ---------------------------------------------------------------------------------------------------
 static int mrssm_fwd_common(const RssmMrssmDims* d, const RssmMrssmWeights* w, const RssmMrssmInputs* in,
                             const RssmMrssmOutputs* out, void* stream, bool imagine) {
-    if (check_mrssm(d)) return 1;
+    if (!is_wide(d) && check_mrssm(d)) return 1;
     REQUIRE(w); REQUIRE(in); REQUIRE(out);
     REQUIRE(in->actions); REQUIRE(in->h0); REQUIRE(in->z0); REQUIRE(out->feature); REQUIRE(out->prior_probs);
     REQUIRE(w->asp_w1); REQUIRE(w->w_ih); REQUIRE(w->w_hh); REQUIRE(w->pr_w1); REQUIRE(w->pr_w2);
@@ -118,6 +434,7 @@ static int mrssm_fwd_common(const RssmMrssmDims* d, const RssmMrssmWeights* w, c
         REQUIRE(in->embed_a); REQUIRE(in->embed_v); REQUIRE(in->u_post); REQUIRE(out->post_probs); REQUIRE(out->kl);
         REQUIRE(w->au_w1); REQUIRE(w->au_w2); REQUIRE(w->vi_w1); REQUIRE(w->vi_w2);
     }
+    if (is_wide(d)) return wide_mrssm_fwd(d, w, in, out, static_cast<cudaStream_t>(stream), imagine);
     rssm::MrssmFwdArgs a{};
     a.B = d->B, a.T = d->T, a.A = d->A, a.K = d->K, a.w = *w;
     a.actions = in->actions, a.embed_a = in->embed_a, a.embed_v = in->embed_v, a.h0 = in->h0, a.z0 = in->z0;
@@ -141,11 +458,12 @@ int rssm_mrssm_imagine_fwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, co
 
 int rssm_mrssm_rollout_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const RssmMrssmInputs* in, const RssmMrssmOutputs* fo,
                            const RssmMrssmUpstream* up, const RssmMrssmInputGrads* gin, const RssmMrssmWeightGrads* gw, void* stream) {
-    if (check_mrssm(d)) return 1;
+    if (!is_wide(d) && check_mrssm(d)) return 1;
     REQUIRE(w); REQUIRE(in); REQUIRE(fo); REQUIRE(up); REQUIRE(gin);
     REQUIRE(in->actions); REQUIRE(in->embed_a); REQUIRE(in->embed_v); REQUIRE(in->h0); REQUIRE(in->z0);
     REQUIRE(fo->feature); REQUIRE(fo->prior_probs); REQUIRE(fo->post_probs); REQUIRE(fo->saved);
     REQUIRE(up->d_feature); REQUIRE(gin->d_embed_a); REQUIRE(gin->d_embed_v); REQUIRE(gin->d_h0); REQUIRE(gin->d_z0);
+    if (is_wide(d)) return wide_mrssm_bwd(d, w, in, fo, up, gin, gw, static_cast<cudaStream_t>(stream));
     REQUIRE(gin->dpre);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rssm::MrssmBwdArgs a{};
@@ -163,6 +481,7 @@ int rssm_mrssm_rollout_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, co
 
 int rssm_mrssm_wgrad(const RssmMrssmDims* d, const RssmMrssmInputs* in, const RssmMrssmOutputs* fo, const void* dpre,
                      const RssmMrssmWeightGrads* gw, void* stream) {
+    if (is_wide(d)) return fail("rssm_mrssm_wgrad: the wide family computes its weight gradients inside rssm_mrssm_rollout_bwd (gw != NULL)");
     if (check_mrssm(d)) return 1;
     REQUIRE(in); REQUIRE(fo); REQUIRE(dpre); REQUIRE(gw);
     REQUIRE(in->actions); REQUIRE(in->embed_a); REQUIRE(in->embed_v); REQUIRE(in->h0); REQUIRE(in->z0);

@@ -44,20 +44,46 @@ def _fill(struct, names: Sequence[str], tensors: Sequence[Optional[Tensor]]):  #
 # =================================================================================================
 # MoPoE-MRSSM
 # =================================================================================================
-def _mr_dims(actions: Tensor, K: int, precision: int) -> _lib.MrssmDims:
+def _mr_dims(actions: Tensor, K: int, precision: int, D: int = 32) -> _lib.MrssmDims:
     B, T, A = actions.shape
-    return _lib.MrssmDims(B=B, T=T, A=A, E=64, D=32, H=32, C=16 // K, K=K, precision=precision)
+    return _lib.MrssmDims(B=B, T=T, A=A, E=64, D=D, H=D, C=16 // K, K=K, precision=precision)
 
 
-def _mr_check(weights: Sequence[Tensor], embed_a: Tensor, h0: Tensor, z0: Tensor) -> None:
+def _mr_wide(D: int) -> bool:
+    """deterministic_size of the wide family (persistent tcgen05 kernels; include/rssm_rollout.h)"""
+    return D != 32
+
+
+def _mr_check(weights: Sequence[Tensor], embed_a: Tensor, h0: Tensor, z0: Tensor) -> int:
+    """Validates the size family; returns deterministic_size."""
     if len(weights) != len(_lib.MR_WEIGHT_FIELDS):
         raise RuntimeError(f"expected {len(_lib.MR_WEIGHT_FIELDS)} weight tensors, got {len(weights)}")
-    if embed_a.shape[-1] != 64 or h0.shape[-1] != 32 or z0.shape[-1] != 16 or tuple(weights[4].shape) != (96, 32):
+    D = h0.shape[-1]
+    ok_d = D == 32 or (D % 128 == 0 and 128 <= D <= 512)
+    if embed_a.shape[-1] != 64 or not ok_d or z0.shape[-1] != 16 or tuple(weights[4].shape) != (3 * D, D):
         raise RuntimeError(
-            "fused MRSSM rollout supports deterministic_size = hidden_size = 32, obs_embed_size = 64, "
-            f"class_size*category_size = 16 (got embed {embed_a.shape[-1]}, deter {h0.shape[-1]}, stoch {z0.shape[-1]}, "
-            f"weight_ih {tuple(weights[4].shape)})"
+            "fused MRSSM rollout supports deterministic_size = hidden_size = 32 or a multiple of 128 up to 512, "
+            f"obs_embed_size = 64, class_size*category_size = 16 (got embed {embed_a.shape[-1]}, deter {h0.shape[-1]}, "
+            f"stoch {z0.shape[-1]}, weight_ih {tuple(weights[4].shape)})"
         )
+    return D
+
+
+_WIDE_PLANES = 10  # record planes per step of the wide family (csrc/wide_common.cuh)
+
+
+def _mr_saved_shape(B: int, T: int, D: int) -> tuple[int, ...]:
+    """Shape of the opaque saved record.  Wide family: bf16 elements covering the planes [T][plane][block][D/8][128][8] followed
+    by the fp32 audio / vision logits [blocks*128][T][32] (rssm_mrssm_saved_bytes)."""
+    if not _mr_wide(D):
+        return (B, T, _lib.MRSSM_SAVED_FLOATS)
+    blocks = (B + 127) // 128
+    return (T * _WIDE_PLANES * blocks * D * 128 + blocks * 128 * T * 32 * 2,)
+
+
+def _mr_workspace(dims: _lib.MrssmDims, backward: bool, dev: torch.device) -> Optional[Tensor]:
+    n = _lib.mrssm_workspace_bytes(dims, backward)
+    return torch.empty((n + 1) // 2, device=dev, dtype=torch.bfloat16) if n else None
 
 
 @torch.library.custom_op("mtrssm_b200::mrssm_rollout", mutates_args=())
@@ -65,30 +91,38 @@ def mrssm_rollout_op(
     weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, h0: Tensor, z0: Tensor,
     u_post: Tensor, u_prior: Optional[Tensor], K: int, precision: int, kl_wq: float, kl_wp: float, save: bool,
 ) -> List[Tensor]:
-    _mr_check(weights, embed_a, h0, z0)
+    D = _mr_check(weights, embed_a, h0, z0)
     B, T, _ = actions.shape
     dev = actions.device
-    feature = torch.empty(B, T, 48, device=dev)
+    dims = _mr_dims(actions, K, precision, D)
+    feature = torch.empty(B, T, D + 16, device=dev)
     prior_probs = torch.empty(B, T, 16 // K, K, device=dev)
     post_probs = torch.empty_like(prior_probs)
     prior_stoch = torch.empty(B, T, 16, device=dev) if u_prior is not None else torch.empty(0, device=dev)
     kl = torch.empty(B, T, device=dev)
-    saved = torch.empty(B, T, _lib.MRSSM_SAVED_FLOATS, device=dev, dtype=_lib.record_dtype(precision)) if save else torch.empty(0, device=dev)
+    saved = torch.empty(_mr_saved_shape(B, T, D), device=dev, dtype=_lib.record_dtype(precision)) if save else torch.empty(0, device=dev)
+    if save and saved.numel() * saved.element_size() != _lib.mrssm_saved_bytes(dims):
+        raise RuntimeError(f"saved record size mismatch with the library: {saved.numel() * saved.element_size()} vs "
+                           f"{_lib.mrssm_saved_bytes(dims)} bytes")
+    workspace = _mr_workspace(dims, False, dev)
     w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
     inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0 u_post u_prior".split(),
                 (actions, embed_a, embed_v, h0, z0, u_post, u_prior))
-    out = _fill(_lib.MrssmOutputs(), "feature prior_probs post_probs prior_stoch kl saved".split(),
-                (feature, prior_probs, post_probs, prior_stoch if u_prior is not None else None, kl, saved if save else None))
-    _lib.call("rssm_mrssm_rollout_fwd", _mr_dims(actions, K, precision), w, inp, out)
+    out = _fill(_lib.MrssmOutputs(), "feature prior_probs post_probs prior_stoch kl saved workspace".split(),
+                (feature, prior_probs, post_probs, prior_stoch if u_prior is not None else None, kl, saved if save else None,
+                 workspace))
+    out.workspace_bytes = 0 if workspace is None else workspace.numel() * 2
+    _lib.call("rssm_mrssm_rollout_fwd", dims, w, inp, out)
     return [feature, prior_probs, post_probs, prior_stoch, kl, saved]
 
 
 @mrssm_rollout_op.register_fake
 def _(weights, actions, embed_a, embed_v, h0, z0, u_post, u_prior, K, precision, kl_wq, kl_wp, save):  # noqa: ANN001
     B, T, _ = actions.shape
+    D = h0.shape[-1]
     e = actions.new_empty
-    return [e(B, T, 48), e(B, T, 16 // K, K), e(B, T, 16 // K, K), e(B, T, 16) if u_prior is not None else e(0), e(B, T),
-            e(B, T, _lib.MRSSM_SAVED_FLOATS, dtype=_lib.record_dtype(precision)) if save else e(0)]
+    return [e(B, T, D + 16), e(B, T, 16 // K, K), e(B, T, 16 // K, K), e(B, T, 16) if u_prior is not None else e(0), e(B, T),
+            e(_mr_saved_shape(B, T, D), dtype=_lib.record_dtype(precision)) if save else e(0)]
 
 
 @torch.library.custom_op("mtrssm_b200::mrssm_rollout_bwd", mutates_args=())
@@ -100,6 +134,8 @@ def mrssm_rollout_bwd_op(
 ) -> List[Tensor]:
     B, T, A = actions.shape
     dev = actions.device
+    D = h0.shape[-1]
+    dims = _mr_dims(actions, K, precision, D)
     if d_feature is None:
         d_feature = torch.zeros_like(feature)
     sizes = [t.numel() for t in weights]
@@ -108,9 +144,11 @@ def mrssm_rollout_bwd_op(
     d_actions = torch.empty(B, T, A, device=dev)
     d_embed_a = torch.empty(B, T, 64, device=dev)
     d_embed_v = torch.empty(B, T, 64, device=dev)
-    d_h0 = torch.empty(B, 32, device=dev)
+    d_h0 = torch.empty(B, D, device=dev)
     d_z0 = torch.empty(B, 16, device=dev)
-    dpre = torch.empty(B, T, _lib.MRSSM_DPRE_FLOATS, device=dev, dtype=_lib.record_dtype(precision))
+    # default family: pre-activation gradient record; wide family: the library keeps its gradient planes in the workspace
+    dpre = None if _mr_wide(D) else torch.empty(B, T, _lib.MRSSM_DPRE_FLOATS, device=dev, dtype=_lib.record_dtype(precision))
+    workspace = _mr_workspace(dims, True, dev)
     w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
     gw = _fill(_lib.MrssmWeightGrads(), _lib.MR_WEIGHT_FIELDS, gws)
     inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0".split(), (actions, embed_a, embed_v, h0, z0))
@@ -118,9 +156,10 @@ def mrssm_rollout_bwd_op(
     up = _fill(_lib.MrssmUpstream(), "d_feature d_prior_probs d_post_probs d_prior_stoch d_kl".split(),
                (_c(d_feature), _c(d_prior_probs), _c(d_post_probs), _c(d_prior_stoch), _c(d_kl)))
     up.kl_wq, up.kl_wp = kl_wq, kl_wp
-    gin = _fill(_lib.MrssmInputGrads(), "d_actions d_embed_a d_embed_v d_h0 d_z0 dpre".split(),
-                (d_actions, d_embed_a, d_embed_v, d_h0, d_z0, dpre))
-    _lib.call("rssm_mrssm_rollout_bwd", _mr_dims(actions, K, precision), w, inp, out, up, gin, gw)
+    gin = _fill(_lib.MrssmInputGrads(), "d_actions d_embed_a d_embed_v d_h0 d_z0 dpre workspace".split(),
+                (d_actions, d_embed_a, d_embed_v, d_h0, d_z0, dpre, workspace))
+    gin.workspace_bytes = 0 if workspace is None else workspace.numel() * 2
+    _lib.call("rssm_mrssm_rollout_bwd", dims, w, inp, out, up, gin, gw)
     return [flat, d_actions, d_embed_a, d_embed_v, d_h0, d_z0]  # flat = all weight grads, split by the caller
 
 
@@ -187,19 +226,23 @@ def mrssm_imagine_op(weights: Sequence[Tensor], actions: Tensor, h0: Tensor, z0:
                      precision: int) -> List[Tensor]:
     B, T, _ = actions.shape
     dev = actions.device
-    feature = torch.empty(B, T, 48, device=dev)
+    D = h0.shape[-1]
+    dims = _mr_dims(actions, K, precision, D)
+    feature = torch.empty(B, T, D + 16, device=dev)
     probs = torch.empty(B, T, 16 // K, K, device=dev)
+    workspace = _mr_workspace(dims, False, dev)
     w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
     inp = _fill(_lib.MrssmInputs(), "actions h0 z0 u_prior".split(), (actions, h0, z0, u))
-    out = _fill(_lib.MrssmOutputs(), "feature prior_probs".split(), (feature, probs))
-    _lib.call("rssm_mrssm_imagine_fwd", _mr_dims(actions, K, precision), w, inp, out)
+    out = _fill(_lib.MrssmOutputs(), "feature prior_probs workspace".split(), (feature, probs, workspace))
+    out.workspace_bytes = 0 if workspace is None else workspace.numel() * 2
+    _lib.call("rssm_mrssm_imagine_fwd", dims, w, inp, out)
     return [feature, probs]
 
 
 @mrssm_imagine_op.register_fake
 def _(weights, actions, h0, z0, u, K, precision):  # noqa: ANN001
     B, T, _ = actions.shape
-    return [actions.new_empty(B, T, 48), actions.new_empty(B, T, 16 // K, K)]
+    return [actions.new_empty(B, T, h0.shape[-1] + 16), actions.new_empty(B, T, 16 // K, K)]
 
 
 def mrssm_imagine(weights: Sequence[Tensor], *, actions: Tensor, h0: Tensor, z0: Tensor, u: Tensor, class_size: int = 4,

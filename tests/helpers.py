@@ -19,6 +19,23 @@ MR_SHAPES = {
     "vision_representation.rnn_to_post_projector.2.weight": (16, 32), "vision_representation.rnn_to_post_projector.2.bias": (16,),
 }
 
+
+
+def mr_shapes(D: int, A: int = 6) -> dict:
+    """MoPoE-MRSSM parameter shapes for deterministic_size = hidden_size = D (BASELINE.json cfg3: D = 512)."""
+    t, a, v = "transition.", "audio_representation.rnn_to_post_projector.", "vision_representation.rnn_to_post_projector."
+    return {
+        t + "action_state_projector.0.weight": (D, A + 16), t + "action_state_projector.0.bias": (D,),
+        t + "action_state_projector.2.weight": (D, D), t + "action_state_projector.2.bias": (D,),
+        t + "rnn_cell.weight_ih": (3 * D, D), t + "rnn_cell.weight_hh": (3 * D, D),
+        t + "rnn_cell.bias_ih": (3 * D,), t + "rnn_cell.bias_hh": (3 * D,),
+        t + "rnn_to_prior_projector.0.weight": (D, D), t + "rnn_to_prior_projector.0.bias": (D,),
+        t + "rnn_to_prior_projector.2.weight": (16, D), t + "rnn_to_prior_projector.2.bias": (16,),
+        a + "0.weight": (D, D + 64), a + "0.bias": (D,), a + "2.weight": (16, D), a + "2.bias": (16,),
+        v + "0.weight": (D, D + 64), v + "0.bias": (D,), v + "2.weight": (16, D), v + "2.bias": (16,),
+    }
+
+
 MT_SHAPES = {
     "l_rnn._d2h.weight": (32, 32), "l_rnn._d2h.bias": (32,), "l_rnn._input2h.weight": (32, 38), "l_rnn._input2h.bias": (32,),
     "h_rnn._d2h.weight": (32, 32), "h_rnn._d2h.bias": (32,), "h_rnn._input2h.weight": (32, 16), "h_rnn._input2h.bias": (32,),
@@ -55,12 +72,12 @@ def synth_actions(B: int, T: int, g: torch.Generator, A: int = 6) -> torch.Tenso
     return (act + 0.1 * torch.randn(B, T, A, generator=g)).contiguous()
 
 
-def mrssm_inputs(B: int, T: int, C: int = 4, K: int = 4, seed: int = 1234) -> dict[str, torch.Tensor]:
+def mrssm_inputs(B: int, T: int, C: int = 4, K: int = 4, seed: int = 1234, D: int = 32) -> dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)
     n = torch.Generator().manual_seed(4321)
     return {
         "actions": synth_actions(B, T, g), "embed_a": torch.randn(B, T, 64, generator=g), "embed_v": torch.randn(B, T, 64, generator=g),
-        "h0": torch.randn(B, 32, generator=g), "z0": onehot_draw(B, C, K, g),
+        "h0": torch.randn(B, D, generator=g), "z0": onehot_draw(B, C, K, g),
         "u_post": torch.rand(B, T, C, generator=n), "u_prior": torch.rand(B, T, C, generator=n),
     }
 

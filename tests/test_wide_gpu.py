@@ -1,0 +1,91 @@
+"""GPU parity of the WIDE MoPoE-MRSSM rollout (deterministic_size = hidden_size = D up to 512: BASELINE.json cfg3) against
+the CPU oracle, through the torch custom ops -> C ABI -> persistent tcgen05 kernels.
+
+The wide family computes on the bf16 tensor-core path only.  Stated tolerances (written at each check): 3e-2 absolute on the
+O(1) states / probabilities of a rollout that is teacher-forced on the kernel's own categorical draws (bf16 operands with
+fp32 accumulation over K = D <= 512, error compounding over the recurrence), 3e-2 of each gradient tensor's scale.
+"""
+
+from __future__ import annotations
+
+import pytest
+import torch
+
+from oracle import rssm_oracle as O
+from tests import helpers as H
+from tests.test_rollout_gpu import cuda, oracle_mrssm, run_mrssm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from multimodal_mtrssm_b200 import params as P
+    from multimodal_mtrssm_b200 import rollout_ops as R
+
+    return R, P
+
+
+def wide_case(D, B, T, K, gain=2.0):
+    C = 16 // K
+    params = H.make_params(H.mr_shapes(D), gain=gain)
+    inp = H.mrssm_inputs(B, T, C, K, D=D)
+    return params, inp, C
+
+
+@pytest.mark.parametrize("D,B,T,K", [(512, 200, 6, 4), (128, 128, 5, 2), (384, 33, 4, 16), (512, 1, 1, 4), (256, 300, 3, 8)])
+def test_wide_forward_bf16_teacher_forced(ops, D, B, T, K):
+    R, P = ops
+    params, inp, C = wide_case(D, B, T, K)
+    got, _, _ = run_mrssm(R, P, params, inp, K, precision=1)
+    onehot = got["feature"][..., D:].cpu().reshape(B, T, C, K)
+    assert bool(((onehot == 0) | (onehot == 1)).all()) and bool((onehot.sum(-1) == 1).all())
+    idx = onehot.argmax(-1)
+    want, _, _ = oracle_mrssm(params, inp, C, K, forced=idx)
+    rep = H.Report(f"wide mrssm fwd bf16 D={D} B={B} T={T} K={K} (teacher-forced on the kernel's draws)")
+    rep.check("deter", got["feature"][..., :D], want["deter"], rtol=0, atol=3e-2)
+    rep.check("prior_probs", got["prior_probs"], want["prior_probs"], rtol=0, atol=3e-2)
+    rep.check("post_probs", got["post_probs"], want["post_probs"], rtol=0, atol=3e-2)
+    rep.check("kl", got["kl"], want["kl"], rtol=5e-2, atol=5e-2)
+    rep.finish()
+    # the kernel's draws are the inverse-CDF draws of ITS OWN probabilities (posterior and prior)
+    self_idx = O.inverse_cdf_index(got["post_probs"].cpu(), inp["u_post"])
+    margin = O.cdf_margin(got["post_probs"].cpu(), inp["u_post"])
+    assert bool(((self_idx == idx) | (margin < 1e-5)).all())
+    pidx = got["prior_stoch"].cpu().reshape(B, T, C, K).argmax(-1)
+    self_p = O.inverse_cdf_index(got["prior_probs"].cpu(), inp["u_prior"])
+    margin_p = O.cdf_margin(got["prior_probs"].cpu(), inp["u_prior"])
+    assert bool(((self_p == pidx) | (margin_p < 1e-5)).all())
+    for k in ("prior_probs", "post_probs"):
+        s = got[k].sum(-1)
+        assert torch.allclose(s, torch.ones_like(s), atol=1e-3), k
+
+
+def wide_upstream(B, T, C, K, D, seed=7):
+    g = torch.Generator().manual_seed(seed)
+    return {
+        "feature": torch.randn(B, T, D + 16, generator=g), "kl": torch.randn(B, T, generator=g),
+        "post_probs": torch.randn(B, T, C, K, generator=g), "prior_probs": torch.randn(B, T, C, K, generator=g),
+    }
+
+
+@pytest.mark.parametrize("D,B,T,K,balancing", [(512, 200, 5, 4, True), (128, 96, 6, 2, False), (256, 130, 1, 8, True)])
+def test_wide_backward_bf16_vs_oracle(ops, D, B, T, K, balancing):
+    """All gradients (inputs, initial state, every weight) of the wide bf16 path against the fp32 oracle, teacher-forced on the
+    kernel's own draws.  Stated bf16 tolerance: 3e-2 of each gradient tensor's scale (max |grad|)."""
+    R, P = ops
+    params, inp, C = wide_case(D, B, T, K)
+    inp["u_prior"] = None  # the prior sample is not part of the training loss
+    up = wide_upstream(B, T, C, K, D)
+    got, w, x = run_mrssm(R, P, params, inp, K, precision=1, grad=True, upstream=up, use_balancing=balancing)
+    idx = got["feature"][..., D:].detach().cpu().reshape(B, T, C, K).argmax(-1)
+    _, w_ref, x_ref = oracle_mrssm(params, inp, C, K, grad=True, upstream=up, use_balancing=balancing, forced=idx)
+    rep = H.Report(f"wide mrssm bwd bf16 D={D} B={B} T={T} K={K} vs teacher-forced oracle")
+    for k in ("actions", "embed_a", "embed_v", "h0", "z0"):
+        rep.check("d " + k, x[k].grad, x_ref[k].grad, rtol=0, atol=3e-2 * float(x_ref[k].grad.abs().max()))
+    for k in w:
+        rep.check("d " + k.replace("rnn_to_post_projector", "post"), w[k].grad, w_ref[k].grad, rtol=0,
+                  atol=3e-2 * float(w_ref[k].grad.abs().max()))
+    rep.finish()
