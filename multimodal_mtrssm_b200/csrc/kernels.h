@@ -45,6 +45,7 @@ struct MrssmWideFwdArgs {
     __nv_bfloat16 *rec, *h0p;  // record planes [t][plane][blocks][D/8][128][8]; packed h0 [NBB][D/8][128][8]
     float* part;               // partial logits [NBB*128][NSL][48]
     float* logits;             // [rows][T][32] audio / vision logits for the backward (NULL when not saving)
+    unsigned long long* timing;  // debug: globaltimer at the end of each phase of the first steps (CTA 0), or NULL
     unsigned* bar;
     int* status;
 };

@@ -223,6 +223,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
     const int grow = bb * BM + row;                        // row inside the launch group
     const bool rvalid = grow < p.B;
 
+    int tidx = 0;
+    auto stamp = [&]() {
+        if (p.timing != nullptr && blockIdx.x == 0 && tid == 0 && tidx < 500) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            p.timing[tidx++] = now;
+        }
+    };
+    stamp();
     for (int t = 0; t < T; ++t) {
         __nv_bfloat16* rec_t = p.rec + (long long)t * p.t_stride;
         const __nv_bfloat16* hb_prev = (t == 0) ? p.h0p + blk : (p.rec + (long long)(t - 1) * p.t_stride + (long long)P_HB * p.plane_stride + blk);
@@ -252,7 +261,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                 *reinterpret_cast<uint4*>(x2 + pk_off(bb, row, s * 32 + q * 8, D)) = pack8(v);
             }
         }
+        stamp();
         grid_sync(p.bar, epoch, p.status);
+        stamp();
         // =================================== phase B ===================================
         if (warp == 4) {
             if (lane == 0) {
@@ -311,7 +322,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                 }
             }
         }
+        stamp();
         grid_sync(p.bar, epoch, p.status);
+        stamp();
         // =================================== phase C ===================================
         if (warp == 4) {
             if (lane == 0) {
@@ -365,7 +378,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                     *reinterpret_cast<float4*>(part + h * 16 + o4 * 4) = make_float4(acc[4 * o4], acc[4 * o4 + 1], acc[4 * o4 + 2], acc[4 * o4 + 3]);
             }
         }
+        stamp();
         grid_sync(p.bar, epoch, p.status);
+        stamp();
         // =================================== phase D ===================================
         {
             const int j = lane & 15, g = j / K;
@@ -414,7 +429,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             __syncthreads();
             if (t + 1 < T) compute_hid1(t + 1);
         }
+        stamp();
         grid_sync(p.bar, epoch, p.status);
+        stamp();
     }
 
     tc_fence_before();

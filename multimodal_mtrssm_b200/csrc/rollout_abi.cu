@@ -148,7 +148,7 @@ int wide_layout(const RssmMrssmDims* d, bool need_rec1, WideLayout* L) {
     L->h0p = take((size_t)L->plane * 2);
     L->part = take((size_t)L->NBBT * 128 * L->NSL * 48 * 4);
     L->rec1 = take(need_rec1 ? (size_t)rssm::wide::NPLANES * L->plane * 2 : 0);
-    L->bar = take(256 * (size_t)(L->ngroups + 1));
+    L->bar = take(256 * (size_t)(L->ngroups + 1) + 4096);  // barrier counters, status word, 4 KB of phase timestamps (debug)
     L->total_fwd = o;
     return 0;
 }
@@ -225,7 +225,7 @@ int wide_mrssm_fwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
         if (check_cuda(cudaMemsetAsync(ws + L.emb_a, 0, L.bar - L.emb_a, s), "workspace memset")) return 1;
         if (save && check_cuda(cudaMemsetAsync(out->saved, 0, (size_t)T * rssm::wide::NPLANES * L.plane * 2, s), "record memset")) return 1;
     }
-    if (check_cuda(cudaMemsetAsync(ws + L.bar, 0, 256 * (size_t)(L.ngroups + 1), s), "barrier memset")) return 1;
+    if (check_cuda(cudaMemsetAsync(ws + L.bar, 0, 256 * (size_t)(L.ngroups + 1) + 4096, s), "barrier memset")) return 1;
     if (wide_pack_weights(d, w, ws, L, imagine, s)) return 1;
     if (!imagine) {
         g_launches.fetch_add(2);
@@ -262,6 +262,7 @@ int wide_mrssm_fwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
         a.logits = save ? reinterpret_cast<float*>(static_cast<char*>(out->saved) + wide_saved_planes_bytes(d)) + r0 * T * 32 : nullptr;
         a.bar = reinterpret_cast<unsigned*>(ws + L.bar + 256 * (size_t)g);
         a.status = reinterpret_cast<int*>(ws + L.bar + 256 * (size_t)L.ngroups);
+        a.timing = (g == 0 && getenv("RSSM_WIDE_TIMING")) ? reinterpret_cast<unsigned long long*>(ws + L.bar + 256 * (size_t)(L.ngroups + 1)) : nullptr;
         g_launches.fetch_add(1);
         if (check_cuda(rssm::launch_mrssm_wide_fwd(a, s), imagine ? "wide mrssm imagine launch" : "wide mrssm forward launch")) return 1;
     }
