@@ -46,6 +46,7 @@ struct MrssmWideFwdArgs {
     float* part;               // partial logits [NBB*128][NSL][48]
     float* logits;             // [rows][T][32] audio / vision logits for the backward (NULL when not saving)
     unsigned long long* timing;  // debug: globaltimer at the end of each phase of the first steps (CTA 0), or NULL
+    int exp;                     // debug (RSSM_WIDE_EXP): 1 = skip the operand copies, 2 = skip the MMAs (timing experiments, wrong results)
     unsigned* bar;
     int* status;
 };
@@ -62,15 +63,30 @@ struct MrssmWideBwdArgs {
     const __nv_bfloat16 *pW1x, *pWhdT, *pWgT, *pWihTn, *pWhhTn, *pW2T;  // transposed packed weight images
     const __nv_bfloat16* rec;  // forward record planes (first block of the group)
     __nv_bfloat16* drec;       // gradient planes (first block of the group)
-    const float* logits;       // [rows][T][32] audio / vision logits saved by the forward
-    const float *feature, *prior_probs, *post_probs, *h0, *z0, *actions;
-    const float *d_feature, *d_prior_probs, *d_post_probs, *d_prior_stoch, *d_kl;
+    const float* stat;         // per-row statistics of the pre-pass [t][blocks][32][128][4], first block of the group
+    long long stat_t_stride;   // floats
+    const float *feature, *h0;
+    const float* d_feature;
     float *d_actions, *d_h0, *d_z0;
-    float* carry;  // [NBB*128][D]
     unsigned* bar;
     int* status;
+    unsigned long long* timing;  // debug, as in the forward
+    int exp;
 };
 cudaError_t launch_mrssm_wide_bwd(const MrssmWideBwdArgs& a, cudaStream_t s);
+
+// pre-pass of the backward over all (b,t) rows (padded to whole 128-row blocks): the part of the row-wise distribution
+// backward that does not depend on the carried gradient, and the [z_{t-1} | a_t] operand plane
+struct WideRowstatArgs {
+    int B, T, A, K, D, NBBT;
+    float kl_wq, kl_wp;
+    long long dt_stride;  // elements between steps of the xin plane
+    const float *logits, *feature, *prior_probs, *post_probs, *z0, *actions;
+    const float *d_feature, *d_prior_probs, *d_post_probs, *d_prior_stoch, *d_kl;
+    float* stat;
+    __nv_bfloat16* xin;   // step 0, block 0 of the narrow [32]-feature plane
+};
+cudaError_t launch_wide_bwd_rowstat(const WideRowstatArgs& a, cudaStream_t s);
 cudaError_t launch_wide_pack_bwd_weights(const MrssmWideBwdArgs& a, cudaStream_t s);
 
 // one output tile of the weight-gradient contraction over (b,t) rows: dW[m * sm + n * sn] += sum_rows Y[row][m] X[row][n]

@@ -23,10 +23,12 @@ constexpr int B_MAX_BYTES = 96 * 64 * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_MAX_BYTES;
 constexpr int TM_X2 = 0, TM_GH = 32, TM_GI = 128, TM_HD = 224;
 constexpr int MAX_RPC = 64;  // rows per CTA in phase D (NSL >= 2)
+constexpr int HROW = 36;     // padded fp32 row of the CTA's own h slice (conflict-free float4 access)
 
 struct FwdSmem {
     unsigned char* ring;
-    float *w1t, *b2s, *bih, *bhh, *bhd, *w2l, *b2l, *zval;
+    float *w1t, *b2s, *bih, *bhh, *bhd, *w2l, *b2l, *zval, *hs, *acts;
+    int* zidx;
     uint64_t *full, *empty, *accbar;
     uint32_t* tmem_base;
 };
@@ -36,6 +38,7 @@ __host__ __device__ inline size_t fwd_smem_bytes(int D, int A) {
     n += (size_t)STAGES * STAGE_BYTES;
     n += (size_t)(A + 17) * D * 4;
     n += (32 + 96 * 3) * 4 + 3 * 32 * 16 * 4 + 48 * 4 + MAX_RPC * 16 * 4;
+    n += BM * HROW * 4 + MAX_RPC * 8 * 4 + MAX_RPC * 8 * 4;
     n += (2 * STAGES + 1) * 8 + 16;
     return n;
 }
@@ -52,6 +55,9 @@ __device__ __forceinline__ FwdSmem carve(unsigned char* dyn, int D, int A) {
     s.w2l = reinterpret_cast<float*>(p), p += 3 * 32 * 16 * 4;
     s.b2l = reinterpret_cast<float*>(p), p += 48 * 4;
     s.zval = reinterpret_cast<float*>(p), p += MAX_RPC * 16 * 4;
+    s.hs = reinterpret_cast<float*>(p), p += BM * HROW * 4;
+    s.acts = reinterpret_cast<float*>(p), p += MAX_RPC * 8 * 4;
+    s.zidx = reinterpret_cast<int*>(p), p += MAX_RPC * 8 * 4;
     s.full = reinterpret_cast<uint64_t*>(p), p += STAGES * 8;
     s.empty = reinterpret_cast<uint64_t*>(p), p += STAGES * 8;
     s.accbar = reinterpret_cast<uint64_t*>(p), p += 8;
@@ -148,8 +154,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
     const int nrows = max(0, min(rpc, p.B - row0));
     const int FG = D >> 3;
 
-    // hid1 of step tn from zval (the previous step's stochastic state) and the action of step tn
-    auto compute_hid1 = [&](int tn) {
+    // hid1 of step tn from the previous step's stochastic state and the action of step tn (staged in sm.acts).
+    // onehot: the state is a drawn sample (one index per group in sm.zidx) -> C gathered columns; else generic values in sm.zval.
+    auto compute_hid1 = [&](int tn, bool onehot) {
         __nv_bfloat16* dst = p.rec + (long long)tn * p.t_stride + (long long)P_HID1 * p.plane_stride;
         for (int item = tid; item < nrows * FG; item += NTHREADS) {
             const int fg = item / nrows, rl = item - fg * nrows, row = row0 + rl;
@@ -157,21 +164,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             const float* wb = sm.w1t + fg * 8;
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = wb[(A + 16) * D + i];
-            const float* act = p.actions + ((long long)row * T + tn) * A;
             for (int a = 0; a < A; ++a) {
-                const float x = act[a];
+                const float x = sm.acts[rl * 8 + a];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = fmaf(x, wb[a * D + i], acc[i]);
             }
-#pragma unroll 4
-            for (int c = 0; c < 16; ++c) {
-                const float z = sm.zval[rl * 16 + c];
+            if (onehot) {
+                for (int g = 0; g < C; ++g) {
+                    const float* wz = wb + (A + g * K + sm.zidx[rl * 8 + g]) * D;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(z, wb[(A + c) * D + i], acc[i]);
+                    for (int i = 0; i < 8; ++i) acc[i] += wz[i];
+                }
+            } else {
+#pragma unroll 4
+                for (int c = 0; c < 16; ++c) {
+                    const float z = sm.zval[rl * 16 + c];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = fmaf(z, wb[(A + c) * D + i], acc[i]);
+                }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[i] = M::elu(acc[i]);
             *reinterpret_cast<uint4*>(dst + pk_off(row >> 7, row & 127, fg * 8, D)) = pack8(acc);
+        }
+    };
+    auto stage_actions = [&](int tn) {
+        for (int i = tid; i < nrows * A; i += NTHREADS) {
+            const int rl = i / A, a = i - rl * A;
+            sm.acts[rl * 8 + a] = p.actions[((long long)(row0 + rl) * T + tn) * A + a];
         }
     };
 
@@ -185,8 +205,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
         *reinterpret_cast<uint4*>(p.h0p + pk_off(row >> 7, row & 127, fg * 8, D)) = pack8(v);
     }
+    stage_actions(0);
+    {   // this CTA's own slice of h_{t-1} stays in shared memory for the whole rollout
+        const int r = tid;
+        if (r < BM) {
+            const int gr = bb * BM + r;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gr < p.B) x = *reinterpret_cast<const float4*>(p.h0 + (long long)gr * D + s * 32 + i);
+                *reinterpret_cast<float4*>(sm.hs + r * HROW + i) = x;
+            }
+        }
+    }
     __syncthreads();
-    compute_hid1(0);
+    compute_hid1(0, false);
     unsigned epoch = 0;
     grid_sync(p.bar, epoch, p.status);
 
@@ -197,10 +230,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
 
     auto load = [&](const __nv_bfloat16* a_src, const __nv_bfloat16* b_src, uint32_t b_bytes) {
         mbar_wait(&sm.empty[ring.slot], ring.phase ^ 1);
-        mbar_expect_tx(&sm.full[ring.slot], A_BYTES + b_bytes);
         unsigned char* st = sm.ring + (size_t)ring.slot * STAGE_BYTES;
-        bulk_g2s(st, a_src, A_BYTES, &sm.full[ring.slot]);
-        bulk_g2s(st + A_BYTES, b_src, b_bytes, &sm.full[ring.slot]);
+        if (p.exp == 1) {
+            mbar_expect_tx(&sm.full[ring.slot], 0);
+        } else {
+            mbar_expect_tx(&sm.full[ring.slot], A_BYTES + b_bytes);
+            bulk_g2s(st, a_src, A_BYTES, &sm.full[ring.slot]);
+            bulk_g2s(st + A_BYTES, b_src, b_bytes, &sm.full[ring.slot]);
+        }
         ring.advance(STAGES);
     };
     auto mma_chunk = [&](uint32_t tcol, int N, bool first) {
@@ -213,7 +250,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         for (int kk = 0; kk < 4; ++kk) {
             const uint64_t da = p.desc_swap ? smem_desc(a0 + kk * 2 * lboA, sbo, lboA) : smem_desc(a0 + kk * 2 * lboA, lboA, sbo);
             const uint64_t db = p.desc_swap ? smem_desc(b0 + kk * 2 * lboB, sbo, lboB) : smem_desc(b0 + kk * 2 * lboB, lboB, sbo);
-            umma(tmem + tcol, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+            if (p.exp != 2) umma(tmem + tcol, da, db, idesc, (first && kk == 0) ? 0u : 1u);
         }
         umma_commit(&sm.empty[ring.slot]);
         ring.advance(STAGES);
@@ -278,7 +315,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         } else {
             mbar_wait(sm.accbar, accph), accph ^= 1;
             tc_fence_after();
-            const float* hprev = (t == 0) ? p.h0 + (long long)grow * D : p.feature + ((long long)grow * T + (t - 1)) * F;
+            float* hsr = sm.hs + row * HROW;
             float* hout = p.feature + ((long long)grow * T + t) * F;
 #pragma unroll 1
             for (int q = 0; q < 4; ++q) {
@@ -294,13 +331,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                 tmem_ld8(tlane + TM_GI + 64 + q * 8, gi);
                 tmem_ld8(tlane + TM_GH + 64 + q * 8, gh);
                 float hp[8];
-                if (rvalid) {
-                    const float4 a = *reinterpret_cast<const float4*>(hprev + s * 32 + q * 8);
-                    const float4 b = *reinterpret_cast<const float4*>(hprev + s * 32 + q * 8 + 4);
+                {
+                    const float4 a = *reinterpret_cast<const float4*>(hsr + q * 8), b = *reinterpret_cast<const float4*>(hsr + q * 8 + 4);
                     hp[0] = a.x, hp[1] = a.y, hp[2] = a.z, hp[3] = a.w, hp[4] = b.x, hp[5] = b.y, hp[6] = b.z, hp[7] = b.w;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) hp[i] = 0.f;
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -308,6 +341,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                     n[i] = M::tanh(gi[i] + sm.bih[64 + q * 8 + i] + r[i] * hn[i]);
                     h[i] = (1.f - z[i]) * n[i] + z[i] * hp[i];
                 }
+                *reinterpret_cast<float4*>(hsr + q * 8) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(hsr + q * 8 + 4) = make_float4(h[4], h[5], h[6], h[7]);
                 if (rvalid) {
                     *reinterpret_cast<float4*>(hout + s * 32 + q * 8) = make_float4(h[0], h[1], h[2], h[3]);
                     *reinterpret_cast<float4*>(hout + s * 32 + q * 8 + 4) = make_float4(h[4], h[5], h[6], h[7]);
@@ -383,6 +418,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         stamp();
         // =================================== phase D ===================================
         {
+            if (t + 1 < T) stage_actions(t + 1);
             const int j = lane & 15, g = j / K;
             for (int base = warp * 2; base < nrows; base += (NTHREADS / 32) * 2) {
                 const int rl = base + (lane >> 4);
@@ -390,9 +426,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                 const int rw = row0 + (valid ? rl : nrows - 1);
                 const float* part = p.part + (long long)rw * NSL * 48;
                 float lp = sm.b2l[j], la = sm.b2l[16 + j], lv = sm.b2l[32 + j];
-                for (int sl = 0; sl < NSL; ++sl) {
-                    lp += __ldcg(part + sl * 48 + j);  // written by other CTAs this step: L2, not a stale L1 line
-                    if (!imagine) la += __ldcg(part + sl * 48 + 16 + j), lv += __ldcg(part + sl * 48 + 32 + j);
+#pragma unroll
+                for (int sl = 0; sl < 16; ++sl) {  // all loads in flight at once (NSL <= 16); L2 loads: written by other CTAs this step
+                    if (sl < NSL) {
+                        lp += __ldcg(part + sl * 48 + j);
+                        if (!imagine) la += __ldcg(part + sl * 48 + 16 + j), lv += __ldcg(part + sl * 48 + 32 + j);
+                    }
                 }
                 const long long bt = (long long)rw * T + t;
                 const float pp = group_softmax(lp, K);
@@ -423,11 +462,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                 if (valid) {
                     p.prior_probs[bt * 16 + j] = pp;
                     p.feature[bt * F + D + j] = zs;
-                    sm.zval[rl * 16 + j] = zs;
+                    if (zs != 0.f) sm.zidx[rl * 8 + g] = j - g * K;
                 }
             }
             __syncthreads();
-            if (t + 1 < T) compute_hid1(t + 1);
+            if (t + 1 < T) compute_hid1(t + 1, true);
         }
         stamp();
         grid_sync(p.bar, epoch, p.status);

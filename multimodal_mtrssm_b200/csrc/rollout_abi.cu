@@ -154,7 +154,7 @@ int wide_layout(const RssmMrssmDims* d, bool need_rec1, WideLayout* L) {
 }
 
 struct WideBwdLayout {
-    size_t pW1x, pWhdT, pWgT, pWihTn, pWhhTn, pW2T, pWaeT, pWveT, ones, drec, carry, h0p, emb_a, emb_v, tiles, bar, total;
+    size_t pW1x, pWhdT, pWgT, pWihTn, pWhhTn, pW2T, pWaeT, pWveT, ones, drec, stat, h0p, emb_a, emb_v, tiles, bar, total;
     long long dt_stride, dlg, xin;  // elements: gradient-plane step, narrow planes inside a step
 };
 constexpr int MAX_WIDE_TILES = 256;
@@ -169,12 +169,12 @@ void wide_bwd_layout(const RssmMrssmDims* d, const WideLayout& L, WideBwdLayout*
     W->xin = W->dlg + (long long)L.NBBT * 48 * 128;
     W->dt_stride = W->xin + (long long)L.NBBT * 32 * 128;
     W->drec = take((size_t)d->T * W->dt_stride * 2);
-    W->carry = take((size_t)L.NBBT * 128 * D * 4);
+    W->stat = take((size_t)d->T * L.NBBT * 32 * 128 * 16);  // per-row statistics of the pre-pass
     W->h0p = take((size_t)L.plane * 2);
     const size_t emb = (size_t)d->T * L.NBBT * 64 * 128 * 2;
     W->emb_a = take(emb), W->emb_v = take(emb);
     W->tiles = take(sizeof(rssm::WideWgradTile) * MAX_WIDE_TILES);
-    W->bar = take(256 * (size_t)(L.ngroups + 1));
+    W->bar = take(256 * (size_t)(L.ngroups + 1) + 4096);  // + phase timestamps (debug)
     W->total = o;
 }
 
@@ -263,6 +263,7 @@ int wide_mrssm_fwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
         a.bar = reinterpret_cast<unsigned*>(ws + L.bar + 256 * (size_t)g);
         a.status = reinterpret_cast<int*>(ws + L.bar + 256 * (size_t)L.ngroups);
         a.timing = (g == 0 && getenv("RSSM_WIDE_TIMING")) ? reinterpret_cast<unsigned long long*>(ws + L.bar + 256 * (size_t)(L.ngroups + 1)) : nullptr;
+        a.exp = getenv("RSSM_WIDE_EXP") ? atoi(getenv("RSSM_WIDE_EXP")) : 0;
         g_launches.fetch_add(1);
         if (check_cuda(rssm::launch_mrssm_wide_fwd(a, s), imagine ? "wide mrssm imagine launch" : "wide mrssm forward launch")) return 1;
     }
@@ -285,7 +286,7 @@ int wide_mrssm_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
     const int D = d->D, T = d->T, A = d->A, F = D + 16;
     const long long plane = L.plane, tstride = (long long)rssm::wide::NPLANES * plane;
     if (d->B % 128 != 0 && check_cuda(cudaMemsetAsync(ws + W.drec, 0, W.tiles - W.drec, s), "workspace memset")) return 1;
-    if (check_cuda(cudaMemsetAsync(ws + W.bar, 0, 256 * (size_t)(L.ngroups + 1), s), "barrier memset")) return 1;
+    if (check_cuda(cudaMemsetAsync(ws + W.bar, 0, 256 * (size_t)(L.ngroups + 1) + 4096, s), "barrier memset")) return 1;
     const __nv_bfloat16* rec = static_cast<const __nv_bfloat16*>(fo->saved);
     const float* logits = reinterpret_cast<const float*>(static_cast<const char*>(fo->saved) + wide_saved_planes_bytes(d));
 
@@ -298,6 +299,16 @@ int wide_mrssm_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
     if (check_cuda(rssm::launch_wide_pack_bwd_weights(a, s), "wide backward weight packing launch")) return 1;
     if (check_cuda(rssm::launch_wide_pack_dembed(w->au_w1, w->vi_w1, D, bf(W.pWaeT), bf(W.pWveT), bf(W.ones), s), "wide embed-weight packing launch"))
         return 1;
+    {
+        rssm::WideRowstatArgs r{};
+        r.B = d->B, r.T = T, r.A = A, r.K = d->K, r.D = D, r.NBBT = L.NBBT, r.kl_wq = up->kl_wq, r.kl_wp = up->kl_wp, r.dt_stride = W.dt_stride;
+        r.logits = logits, r.feature = fo->feature, r.prior_probs = fo->prior_probs, r.post_probs = fo->post_probs, r.z0 = in->z0;
+        r.actions = in->actions, r.d_feature = up->d_feature, r.d_prior_probs = up->d_prior_probs, r.d_post_probs = up->d_post_probs;
+        r.d_prior_stoch = up->d_prior_stoch, r.d_kl = up->d_kl;
+        r.stat = reinterpret_cast<float*>(ws + W.stat), r.xin = bf(W.drec) + W.xin;
+        g_launches.fetch_add(1);
+        if (check_cuda(rssm::launch_wide_bwd_rowstat(r, s), "wide backward pre-pass launch")) return 1;
+    }
     for (int g = 0; g < L.ngroups; ++g) {
         const int bb0 = g * L.NBBG, nbb = (L.NBBT - bb0 < L.NBBG) ? L.NBBT - bb0 : L.NBBG;
         const long long r0 = (long long)bb0 * 128, boff = (long long)bb0 * D * 128;
@@ -305,19 +316,16 @@ int wide_mrssm_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
         a.NBB = nbb;
         a.rec = rec + boff, a.drec = bf(W.drec) + boff;
         a.dlg_off = W.dlg - boff + (long long)bb0 * 48 * 128, a.xin_off = W.xin - boff + (long long)bb0 * 32 * 128;
-        a.logits = logits + r0 * T * 32;
-        a.feature = fo->feature + r0 * T * F, a.prior_probs = fo->prior_probs + r0 * T * 16, a.post_probs = fo->post_probs + r0 * T * 16;
-        a.h0 = in->h0 + r0 * D, a.z0 = in->z0 + r0 * 16, a.actions = in->actions + r0 * T * A;
+        a.stat = reinterpret_cast<const float*>(ws + W.stat) + (long long)bb0 * (32 * 128 * 4);
+        a.stat_t_stride = (long long)L.NBBT * (32 * 128 * 4);
+        a.feature = fo->feature + r0 * T * F, a.h0 = in->h0 + r0 * D;
         a.d_feature = up->d_feature + r0 * T * F;
-        a.d_prior_probs = up->d_prior_probs ? up->d_prior_probs + r0 * T * 16 : nullptr;
-        a.d_post_probs = up->d_post_probs ? up->d_post_probs + r0 * T * 16 : nullptr;
-        a.d_prior_stoch = up->d_prior_stoch ? up->d_prior_stoch + r0 * T * 16 : nullptr;
-        a.d_kl = up->d_kl ? up->d_kl + r0 * T : nullptr;
         a.d_actions = gin->d_actions ? gin->d_actions + r0 * T * A : nullptr;
         a.d_h0 = gin->d_h0 + r0 * D, a.d_z0 = gin->d_z0 + r0 * 16;
-        a.carry = reinterpret_cast<float*>(ws + W.carry) + r0 * D;
         a.bar = reinterpret_cast<unsigned*>(ws + W.bar + 256 * (size_t)g);
         a.status = reinterpret_cast<int*>(ws + W.bar + 256 * (size_t)L.ngroups);
+        a.timing = (g == 0 && getenv("RSSM_WIDE_TIMING")) ? reinterpret_cast<unsigned long long*>(ws + W.bar + 256 * (size_t)(L.ngroups + 1)) : nullptr;
+        a.exp = getenv("RSSM_WIDE_EXP") ? atoi(getenv("RSSM_WIDE_EXP")) : 0;
         g_launches.fetch_add(1);
         if (check_cuda(rssm::launch_mrssm_wide_bwd(a, s), "wide mrssm backward launch")) return 1;
     }
@@ -374,8 +382,11 @@ int wide_mrssm_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
             gw->au_w1 + (size_t)mt * 128 * (D + 64) + D, nullptr, D + 64, 1);
         add(dplane(DP_VH, mt * 128), W.dt_stride, bstrideD, bf(W.emb_v), nullptr, embt, 64 * 128, 0, 64, 128, 64,
             gw->vi_w1 + (size_t)mt * 128 * (D + 64) + D, nullptr, D + 64, 1);
-        add(dplane(DP_H1, mt * 128), W.dt_stride, bstrideD, dr + W.xin, nullptr, W.dt_stride, 32 * 128, 0, 32, 128, A + 16,
-            gw->asp_w1 + (size_t)mt * 128 * (A + 16), gw->asp_b1 + mt * 128, A + 16, 1);
+        // first projector layer: the operand plane is [z_{t-1} (16) | a_t (A) | 0]
+        add(dplane(DP_H1, mt * 128), W.dt_stride, bstrideD, dr + W.xin, nullptr, W.dt_stride, 32 * 128, 0, 16, 128, 16,
+            gw->asp_w1 + (size_t)mt * 128 * (A + 16) + A, gw->asp_b1 + mt * 128, A + 16, 1);
+        add(dplane(DP_H1, mt * 128), W.dt_stride, bstrideD, dr + W.xin + 2048, nullptr, W.dt_stride, 32 * 128, 0, 16, 128, A,
+            gw->asp_w1 + (size_t)mt * 128 * (A + 16), nullptr, A + 16, 1);
     }
     float* w2g[3] = {gw->pr_w2, gw->au_w2, gw->vi_w2};
     float* b2g[3] = {gw->pr_b2, gw->au_b2, gw->vi_b2};

@@ -12,6 +12,7 @@ Weight order of the `weights` list follows `_lib.MR_WEIGHT_FIELDS` / `_lib.MT_WE
 
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -81,9 +82,15 @@ def _mr_saved_shape(B: int, T: int, D: int) -> tuple[int, ...]:
     return (T * _WIDE_PLANES * blocks * D * 128 + blocks * 128 * T * 32 * 2,)
 
 
+_DEBUG_LAST_WORKSPACE: dict[bool, Tensor] = {}  # RSSM_WIDE_TIMING only: lets a profiling script read the phase timestamps
+
+
 def _mr_workspace(dims: _lib.MrssmDims, backward: bool, dev: torch.device) -> Optional[Tensor]:
     n = _lib.mrssm_workspace_bytes(dims, backward)
-    return torch.empty((n + 1) // 2, device=dev, dtype=torch.bfloat16) if n else None
+    ws = torch.empty((n + 1) // 2, device=dev, dtype=torch.bfloat16) if n else None
+    if ws is not None and os.environ.get("RSSM_WIDE_TIMING"):
+        _DEBUG_LAST_WORKSPACE[backward] = ws
+    return ws
 
 
 @torch.library.custom_op("mtrssm_b200::mrssm_rollout", mutates_args=())
