@@ -343,6 +343,80 @@ def time_train_step(B: int, T: int, world: int, device: torch.device, autocast: 
 
 
 # ---------------------------------------------------------------------------------------------------
+def time_wide_cfg3(device: torch.device, iters: int = 10, B: int = 1024, T: int = 64, D: int = 512) -> dict:
+    """BASELINE.json cfg3: MoPoE-MRSSM rollout-only microbench, batch 1024, T = 64, hidden 512 -- fwd+bwd through the public op API
+    (`rollout_ops.mrssm_rollout` + autograd: weight packing, persistent tcgen05 forward kernel, pre-pass, persistent BPTT kernel,
+    embedding- and weight-gradient kernels, torch allocations).  Tensor-pipe bound: SURVEY.md 8(d) counts 5 445 632 forward
+    GEMM FLOPs per (b,t), x3 for fwd+bwd; the fraction is against the measured sustained bf16 peak."""
+    from multimodal_mtrssm_b200 import _lib
+    from multimodal_mtrssm_b200 import rollout_ops as R
+    from multimodal_mtrssm_b200 import synthetic
+    from multimodal_mtrssm_b200.params import mrssm_weight_list
+
+    weights = mrssm_weight_list({k: v.to(device).requires_grad_(True) for k, v in synthetic.mrssm_params(D=D).items()})
+    inp = {k: v.to(device) for k, v in synthetic.mrssm_batch(B, T, D=D).items()}
+    g = torch.Generator().manual_seed(7)
+    readout = torch.randn(D + 16, generator=g).to(device)
+
+    def run(grad: bool) -> float:
+        def step() -> None:
+            if grad:
+                out = R.mrssm_rollout(weights, precision=_lib.PRECISION_BF16, **inp)
+                torch.autograd.grad((out["feature"] @ readout).sum() + out["kl"].mean(), weights)
+            else:
+                with torch.no_grad():
+                    R.mrssm_rollout(weights, precision=_lib.PRECISION_BF16, **inp)
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(iters):
+            step()
+        end.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(end) / iters
+
+    ms, ms_fwd = run(True), run(False)
+    flops_fwd = 2 * ((6 + 16) * D + D * D + 3 * D * D + 3 * D * D + D * D + D * 16 + 2 * ((D + 64) * D + D * 16)) * B * T
+    peaks_file = ROOT / "MEASURED_PEAKS.json"  # sustained bf16 figure: the kernels run inside a long step
+    peak = json.loads(peaks_file.read_text()).get("bf16_tflops_sustained", 1384.6) if peaks_file.exists() else 1384.6
+    return {"workload": f"cfg3 MoPoE-MRSSM rollout-only B={B} T={T} hidden={D}", "B": B, "T": T, "ms_per_step": ms, "fwd_only_ms": ms_fwd,
+            "value": B * T / (ms * 1e-3), "unit": UNIT, "dtype": "bf16 operands, fp32 accumulate/state",
+            "roofline": {"bound": "tensor", "achieved": 3 * flops_fwd / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": 3 * flops_fwd / (ms * 1e-3) / 1e12 / peak,
+                         "serial_chain_note": f"{T} steps x 8 dependent contraction phases; {ms / T * 1e3:.1f} us per step"},
+            "via": "public op API (incl. packing kernels, torch allocations and the loss)"}
+
+
+def reference_eager_gpu_cfg3(device: torch.device, B: int = 1024, T: int = 64, D: int = 512) -> dict:
+    """The "vs reference" number of cfg3: the fp32 oracle (= the reference's PyTorch rollout with explicit noise)
+    run EAGER on this GPU, fwd + autograd bwd, CUDA events.  Baseline leg: touches oracle/."""
+    from multimodal_mtrssm_b200 import synthetic
+    from oracle import rssm_oracle as O
+
+    params = {k: v.to(device).requires_grad_(True) for k, v in synthetic.mrssm_params(D=D).items()}
+    inp = {k: v.to(device) for k, v in synthetic.mrssm_batch(B, T, D=D).items()}
+    up = torch.randn(B, T, D + 16, generator=torch.Generator().manual_seed(7)).to(device)
+
+    def step() -> None:
+        res = O.mrssm_rollout(params, C=4, K=4, u_prior=None, **inp)
+        loss = (res["post_feature"] * up).sum() + O.kl_per_sample(res["post_probs"], res["prior_probs"], True).mean()
+        torch.autograd.grad(loss, list(params.values()))
+
+    step()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(3):
+        step()
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / 3
+    return {"ms_per_step": ms, "value": B * T / (ms * 1e-3), "unit": UNIT, "what": "fp32 PyTorch oracle, eager on this GPU (cuBLAS fp32 / TF32 off)"}
+
+
 # CPU legs (the ONLY place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------------
 def cpu_oracle_rate(B: int, T: int, literal: bool, budget_s: float) -> dict:
@@ -471,6 +545,11 @@ def main() -> None:
             del w
         mr_prec = _lib.PRECISION_FP32 if precision == _lib.PRECISION_FP32 else _lib.PRECISION_BF16
         extras["mrssm_workloads"] = [time_mrssm(8, T, mr_prec, device), time_mrssm(16384, T, mr_prec, device)]
+        if precision != _lib.PRECISION_FP32:  # the wide family is the bf16 tensor-core path
+            extras["cfg3_wide_mrssm"] = time_wide_cfg3(device)
+            extras["cfg3_wide_mrssm"]["reference_eager_on_this_gpu"] = reference_eager_gpu_cfg3(device)
+            r = extras["cfg3_wide_mrssm"]
+            r["speedup_vs_reference_eager_gpu"] = r["reference_eager_on_this_gpu"]["ms_per_step"] / r["ms_per_step"]
     if world > 1:
         import torch.distributed as dist
 

@@ -465,7 +465,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                     if (zs != 0.f) sm.zidx[rl * 8 + g] = j - g * K;
                 }
             }
+            stamp();
             __syncthreads();
+            stamp();
             if (t + 1 < T) compute_hid1(t + 1, true);
         }
         stamp();

@@ -213,7 +213,7 @@ int wide_mrssm_fwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
     if (check_mrssm_wide(d)) return 1;
     const bool save = !imagine && out->saved != nullptr;
     WideLayout L;
-    if (wide_layout(d, !save, &L)) return 1;
+    if (wide_layout(d, true, &L)) return 1;  // same layout as rssm_mrssm_workspace_bytes reports (the one-step record is unused when saving)
     if (out->workspace == nullptr || out->workspace_bytes < L.total_fwd)
         return fail("wide family: workspace of %zu bytes required (rssm_mrssm_workspace_bytes), got %zu", L.total_fwd,
                     out->workspace ? out->workspace_bytes : (size_t)0);

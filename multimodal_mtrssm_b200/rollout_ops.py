@@ -108,9 +108,9 @@ def mrssm_rollout_op(
     prior_stoch = torch.empty(B, T, 16, device=dev) if u_prior is not None else torch.empty(0, device=dev)
     kl = torch.empty(B, T, device=dev)
     saved = torch.empty(_mr_saved_shape(B, T, D), device=dev, dtype=_lib.record_dtype(precision)) if save else torch.empty(0, device=dev)
-    if save and saved.numel() * saved.element_size() != _lib.mrssm_saved_bytes(dims):
-        raise RuntimeError(f"saved record size mismatch with the library: {saved.numel() * saved.element_size()} vs "
-                           f"{_lib.mrssm_saved_bytes(dims)} bytes")
+    lib_bytes = _lib.mrssm_saved_bytes(dims)  # 0: unsupported sizes / precision -- the launch below reports why
+    if save and lib_bytes and saved.numel() * saved.element_size() != lib_bytes:
+        raise RuntimeError(f"saved record size mismatch with the library: {saved.numel() * saved.element_size()} vs {lib_bytes} bytes")
     workspace = _mr_workspace(dims, False, dev)
     w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
     inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0 u_post u_prior".split(),

@@ -33,11 +33,21 @@ def _linear_init(shapes: dict, g: torch.Generator, gain: float) -> dict[str, Ten
     return out
 
 
-def mrssm_params(seed: int = 42, gain: float = 1.0) -> dict[str, Tensor]:
+def mrssm_shapes(D: int, A: int = 6) -> dict:
+    """Linear shapes of MoPoE-MRSSM for deterministic_size = hidden_size = D (D = 32: default.yaml; D = 512: BASELINE cfg3)."""
+    t, a, v = "transition.", "audio_representation.rnn_to_post_projector.", "vision_representation.rnn_to_post_projector."
+    return {
+        t + "action_state_projector.0": (D, A + 16), t + "action_state_projector.2": (D, D),
+        t + "rnn_to_prior_projector.0": (D, D), t + "rnn_to_prior_projector.2": (16, D),
+        a + "0": (D, D + 64), a + "2": (16, D), v + "0": (D, D + 64), v + "2": (16, D),
+    }
+
+
+def mrssm_params(seed: int = 42, gain: float = 1.0, D: int = 32) -> dict[str, Tensor]:
     g = torch.Generator().manual_seed(seed)
-    p = _linear_init(MR_SHAPES, g, gain)
-    b = gain / 32**0.5  # nn.GRUCell default: U(-1/sqrt(hidden), 1/sqrt(hidden))
-    for k, s in (("weight_ih", (96, 32)), ("weight_hh", (96, 32)), ("bias_ih", (96,)), ("bias_hh", (96,))):
+    p = _linear_init(MR_SHAPES if D == 32 else mrssm_shapes(D), g, gain)
+    b = gain / D**0.5  # nn.GRUCell default: U(-1/sqrt(hidden), 1/sqrt(hidden))
+    for k, s in (("weight_ih", (3 * D, D)), ("weight_hh", (3 * D, D)), ("bias_ih", (3 * D,)), ("bias_hh", (3 * D,))):
         p[f"transition.rnn_cell.{k}"] = (torch.rand(*s, generator=g) * 2 - 1) * b
     assert set(p) == set(MR_STATE_KEYS)
     return p
@@ -72,9 +82,9 @@ def mtrssm_batch(B: int, T: int, seed: int = 1234, noise_seed: int = 4321) -> di
     }
 
 
-def mrssm_batch(B: int, T: int, seed: int = 1234, noise_seed: int = 4321) -> dict[str, Tensor]:
+def mrssm_batch(B: int, T: int, seed: int = 1234, noise_seed: int = 4321, D: int = 32) -> dict[str, Tensor]:
     g, n = torch.Generator().manual_seed(seed), torch.Generator().manual_seed(noise_seed)
     return {
         "actions": actions(B, T, g), "embed_a": torch.randn(B, T, 64, generator=g), "embed_v": torch.randn(B, T, 64, generator=g),
-        "h0": torch.randn(B, 32, generator=g), "z0": onehot(B, 4, 4, g), "u_post": torch.rand(B, T, 4, generator=n),
+        "h0": torch.randn(B, D, generator=g), "z0": onehot(B, 4, 4, g), "u_post": torch.rand(B, T, 4, generator=n),
     }

@@ -27,5 +27,5 @@ def report(ws, names, label):
         print(f"  {nm:12s} median {np.median(dd[2:, i]) / 1e3:7.2f} us")
     print(f"  step total median {np.median(dd[2:].sum(1)) / 1e3:.2f} us")
 
-report(R._DEBUG_LAST_WORKSPACE[False], ["A compute", "A barrier", "B compute", "B barrier", "C compute", "C barrier", "D compute", "D barrier"], "forward")
+report(R._DEBUG_LAST_WORKSPACE[False], ["A compute", "A barrier", "B compute", "B barrier", "C compute", "C barrier", "D sample", "D sync", "D hid1", "D barrier"], "forward")
 report(R._DEBUG_LAST_WORKSPACE[True], ["P1 compute", "P1 barrier", "P2 compute", "P2 barrier", "P3 compute", "P3 barrier", "P4 compute", "P4 barrier"], "backward")

@@ -200,18 +200,19 @@ class RandQueue:
         return False
 
 
-def build_mrssm_model():
-    """Product MoPoE_MRSSM at the default.yaml sizes with LinEncoder/LinDecoder (golden-compatible state_dict)."""
+def build_mrssm_model(D: int = 32):
+    """Product MoPoE_MRSSM at the default.yaml sizes (D = 32; D = 512 is BASELINE.json cfg3) with LinEncoder/LinDecoder
+    (golden-compatible state_dict)."""
     from multimodal_mtrssm_b200.mlp import MLP
     from multimodal_mtrssm_b200.mopoe_mrssm import MoPoE_MRSSM
     from multimodal_mtrssm_b200.networks import Representation, Transition
 
-    rep = dict(deterministic_size=32, hidden_size=32, obs_embed_size=64, distribution_config=[4, 4], activation_name="ELU")
+    rep = dict(deterministic_size=D, hidden_size=D, obs_embed_size=64, distribution_config=[4, 4], activation_name="ELU")
     return MoPoE_MRSSM(
         audio_representation=Representation(**rep), vision_representation=Representation(**rep),
-        transition=Transition(deterministic_size=32, hidden_size=32, action_size=6, distribution_config=[4, 4], activation_name="ELU"),
-        audio_encoder=LinEncoder(), vision_encoder=LinEncoder(), audio_decoder=LinDecoder(48), vision_decoder=LinDecoder(48),
-        init_proj=MLP(in_features=64, out_features=32, num_cells=200, depth=1), kl_coeff=1, use_kl_balancing=True,
+        transition=Transition(deterministic_size=D, hidden_size=D, action_size=6, distribution_config=[4, 4], activation_name="ELU"),
+        audio_encoder=LinEncoder(), vision_encoder=LinEncoder(), audio_decoder=LinDecoder(D + 16), vision_decoder=LinDecoder(D + 16),
+        init_proj=MLP(in_features=64, out_features=D, num_cells=200, depth=1), kl_coeff=1, use_kl_balancing=True,
     )
 
 

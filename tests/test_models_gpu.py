@@ -162,3 +162,35 @@ def test_autocast_selects_the_bf16_path_and_training_reduces_the_loss():
         losses.append(float(out["loss"]))
     assert losses[-1] < losses[0] and all(map(lambda v: v == v, losses)), losses
     assert set(out) == {"loss", "train/loss", "train/recon", "train/recon/audio", "train/recon/vision", "train/kl", "train/kl_h"}
+
+
+def test_wide_mrssm_model_trains_under_autocast_and_fails_loudly_in_fp32():
+    """MoPoE_MRSSM with deterministic_size = hidden_size = 512 (BASELINE.json cfg3) behind the reference's class interface: the
+    fused wide kernels are the bf16 tensor-core path, selected under autocast (the reference trains with 16-mixed); the
+    fp32-parity policy is not built for this size and must raise, not fall back."""
+    torch.manual_seed(0)
+    model = H.build_mrssm_model(512).cuda()
+    B, T = 24, 6
+    g = torch.Generator().manual_seed(1)
+    obs = torch.rand(B, T, 1, 32, 32, generator=g).cuda() * 2 - 1
+    batch = (torch.randn(B, T, 6, generator=g).cuda(), obs, obs.flip(-1), None, obs, obs.flip(-1))
+    with pytest.raises(RuntimeError, match="RSSM_PRECISION_BF16 only"):
+        model.training_step(batch, 0)
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4)
+    losses = []
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        for _ in range(15):
+            opt.zero_grad(set_to_none=True)
+            out = model.training_step(batch, 0)
+            out["loss"].backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 10.0)
+            opt.step()
+            losses.append(float(out["loss"].detach()))
+        with torch.no_grad():
+            post, _ = model.rollout_representation(actions=batch[0], observations=(obs, obs.flip(-1)),
+                                                   prev_state=model.initial_state((obs[:, 0], obs.flip(-1)[:, 0])))
+            imag = model.rollout_transition(actions=batch[0][:, :3], prev_state=post[:, -1])
+    assert post.feature.shape == (B, T, 528) and imag.feature.shape == (B, 3, 528)
+    assert losses[-1] < losses[0] and all(map(lambda v: v == v, losses)), losses
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for n, p in model.named_parameters()
+               if not n.startswith("representation."))
