@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
         }
         if (t < 0) break;
         stamp();
-        grid_sync(p.bar, epoch, p.status);
+        grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== P2 ===================================
         if (warp == 4) {
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
             }
         }
         stamp();
-        grid_sync(p.bar, epoch, p.status);
+        grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== P3 ===================================
         if (warp == 4) {
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
             }
         }
         stamp();
-        grid_sync(p.bar, epoch, p.status);
+        grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== P4 ===================================
         if (warp == 4) {
@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
             }
         }
         stamp();
-        grid_sync(p.bar, epoch, p.status);
+        grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
     }
 

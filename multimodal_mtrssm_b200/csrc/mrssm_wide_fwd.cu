@@ -3,13 +3,13 @@
 // (core.py:170-185) for deterministic_size = hidden_size = D in {64, 128, ..., 512}.  Design notes: wide_common.cuh.
 //
 // CTA (bb, s) = batch block bb (128 sequences) x slice s (hidden units / head features 32 s .. 32 s + 31).  One step = four
-// phases separated by grid barriers (each phase consumes what ALL slices of the block produced in the previous one):
+// phases separated by barriers among the slice CTAs of a batch block (each phase consumes what ALL slices of the block produced in the previous one):
 //   A  x2[:, slice]  = W2[slice] . hid1_t + b2                 (action_state_projector.2, networks.py:169)      N = 32, K = D
 //      gh[:, slice]  = W_hh[r|z|n of slice] . h_{t-1}           (GRUCell, networks.py:170)                       N = 96, K = D
 //   B  gi[:, slice]  = W_ih[r|z|n of slice] . x2 ; gates ; h_t  (GRUCell)                                        N = 96, K = D
 //   C  hid[:, slice] = ELU([W_prior | W_audio | W_vision][slice] . h_t (+ W_e . embed_t) + b1)                   N = 96, K = D (+64)
 //      partial logits of the slice (CUDA cores; 32 features x 16 outputs per head)  -> part[row][s][48]
-//   D  rows are dealt out evenly over ALL CTAs: sum the partial logits, MoPoE fusion (mopoe_mrssm/core.py:241-251,135-154),
+//   D  the block's rows are dealt out evenly over its slice CTAs: sum the partial logits, MoPoE fusion (mopoe_mrssm/core.py:241-251,135-154),
 //      per-group softmax, inverse-CDF draw, KL, per-step outputs; hid1_{t+1} = ELU(W1 . [a_{t+1} ; z_t] + b1) (networks.py:164-169)
 // Accumulators live in TMEM (x2 @0, gh @32, gi @128, heads @224); gh is issued in phase A and consumed in phase B.
 #include "kernels.h"
@@ -148,10 +148,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
     tc_fence_after();
     const uint32_t tmem = *sm.tmem_base;
 
-    // phase-D rows of this CTA
-    const int rpc = (p.B + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int row0 = blockIdx.x * rpc;
-    const int nrows = max(0, min(rpc, p.B - row0));
+    // phase-D rows of this CTA: the rows of its own batch block are dealt out over the block's slice CTAs
+    const int rpc = (BM + NSL - 1) / NSL;
+    const int row0 = bb * BM + s * rpc;
+    const int nrows = max(0, min(min(rpc, BM - s * rpc), p.B - row0));
     const int FG = D >> 3;
 
     // hid1 of step tn from the previous step's stochastic state and the action of step tn (staged in sm.acts).
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
     __syncthreads();
     compute_hid1(0, false);
     unsigned epoch = 0;
-    grid_sync(p.bar, epoch, p.status);
+    grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
 
     Ring ring;            // producer and MMA issuer walk the same chunk sequence
     uint32_t accph = 0;   // epilogue warps: parity of the accumulator barrier
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             }
         }
         stamp();
-        grid_sync(p.bar, epoch, p.status);
+        grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== phase B ===================================
         if (warp == 4) {
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             }
         }
         stamp();
-        grid_sync(p.bar, epoch, p.status);
+        grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== phase C ===================================
         if (warp == 4) {
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             }
         }
         stamp();
-        grid_sync(p.bar, epoch, p.status);
+        grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== phase D ===================================
         {
@@ -425,13 +425,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                 const bool valid = rl < nrows;
                 const int rw = row0 + (valid ? rl : nrows - 1);
                 const float* part = p.part + (long long)rw * NSL * 48;
+                // all partial-logit loads in flight at once (NSL <= 16; clamped index, masked value); L2 loads: other CTAs wrote them
+                float pv[16][3];
+#pragma unroll
+                for (int sl = 0; sl < 16; ++sl) {
+                    const float* ps = part + (sl < NSL ? sl : NSL - 1) * 48 + j;
+                    pv[sl][0] = __ldcg(ps);
+                    pv[sl][1] = imagine ? 0.f : __ldcg(ps + 16);
+                    pv[sl][2] = imagine ? 0.f : __ldcg(ps + 32);
+                }
                 float lp = sm.b2l[j], la = sm.b2l[16 + j], lv = sm.b2l[32 + j];
 #pragma unroll
-                for (int sl = 0; sl < 16; ++sl) {  // all loads in flight at once (NSL <= 16); L2 loads: written by other CTAs this step
-                    if (sl < NSL) {
-                        lp += __ldcg(part + sl * 48 + j);
-                        if (!imagine) la += __ldcg(part + sl * 48 + 16 + j), lv += __ldcg(part + sl * 48 + 32 + j);
-                    }
+                for (int sl = 0; sl < 16; ++sl) {
+                    const float m = sl < NSL ? 1.f : 0.f;
+                    lp = fmaf(m, pv[sl][0], lp), la = fmaf(m, pv[sl][1], la), lv = fmaf(m, pv[sl][2], lv);
                 }
                 const long long bt = (long long)rw * T + t;
                 const float pp = group_softmax(lp, K);
@@ -471,7 +478,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             if (t + 1 < T) compute_hid1(t + 1, true);
         }
         stamp();
-        grid_sync(p.bar, epoch, p.status);
+        grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
     }
 

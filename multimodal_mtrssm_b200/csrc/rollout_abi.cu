@@ -148,7 +148,7 @@ int wide_layout(const RssmMrssmDims* d, bool need_rec1, WideLayout* L) {
     L->h0p = take((size_t)L->plane * 2);
     L->part = take((size_t)L->NBBT * 128 * L->NSL * 48 * 4);
     L->rec1 = take(need_rec1 ? (size_t)rssm::wide::NPLANES * L->plane * 2 : 0);
-    L->bar = take(256 * (size_t)(L->ngroups + 1) + 4096);  // barrier counters, status word, 4 KB of phase timestamps (debug)
+    L->bar = take(256 * (size_t)(L->NBBT + 1) + 4096);  // one barrier counter line per batch block, status word, 4 KB of phase timestamps (debug)
     L->total_fwd = o;
     return 0;
 }
@@ -174,7 +174,7 @@ void wide_bwd_layout(const RssmMrssmDims* d, const WideLayout& L, WideBwdLayout*
     const size_t emb = (size_t)d->T * L.NBBT * 64 * 128 * 2;
     W->emb_a = take(emb), W->emb_v = take(emb);
     W->tiles = take(sizeof(rssm::WideWgradTile) * MAX_WIDE_TILES);
-    W->bar = take(256 * (size_t)(L.ngroups + 1) + 4096);  // + phase timestamps (debug)
+    W->bar = take(256 * (size_t)(L.NBBT + 1) + 4096);  // counter line per batch block, status, phase timestamps (debug)
     W->total = o;
 }
 
@@ -225,7 +225,7 @@ int wide_mrssm_fwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
         if (check_cuda(cudaMemsetAsync(ws + L.emb_a, 0, L.bar - L.emb_a, s), "workspace memset")) return 1;
         if (save && check_cuda(cudaMemsetAsync(out->saved, 0, (size_t)T * rssm::wide::NPLANES * L.plane * 2, s), "record memset")) return 1;
     }
-    if (check_cuda(cudaMemsetAsync(ws + L.bar, 0, 256 * (size_t)(L.ngroups + 1) + 4096, s), "barrier memset")) return 1;
+    if (check_cuda(cudaMemsetAsync(ws + L.bar, 0, 256 * (size_t)(L.NBBT + 1) + 4096, s), "barrier memset")) return 1;
     if (wide_pack_weights(d, w, ws, L, imagine, s)) return 1;
     if (!imagine) {
         g_launches.fetch_add(2);
@@ -260,9 +260,9 @@ int wide_mrssm_fwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
         a.h0p = bf(L.h0p) + (long long)bb0 * D * 128;
         a.part = reinterpret_cast<float*>(ws + L.part) + r0 * L.NSL * 48;
         a.logits = save ? reinterpret_cast<float*>(static_cast<char*>(out->saved) + wide_saved_planes_bytes(d)) + r0 * T * 32 : nullptr;
-        a.bar = reinterpret_cast<unsigned*>(ws + L.bar + 256 * (size_t)g);
-        a.status = reinterpret_cast<int*>(ws + L.bar + 256 * (size_t)L.ngroups);
-        a.timing = (g == 0 && getenv("RSSM_WIDE_TIMING")) ? reinterpret_cast<unsigned long long*>(ws + L.bar + 256 * (size_t)(L.ngroups + 1)) : nullptr;
+        a.bar = reinterpret_cast<unsigned*>(ws + L.bar + 256 * (size_t)bb0);
+        a.status = reinterpret_cast<int*>(ws + L.bar + 256 * (size_t)L.NBBT);
+        a.timing = (g == 0 && getenv("RSSM_WIDE_TIMING")) ? reinterpret_cast<unsigned long long*>(ws + L.bar + 256 * (size_t)(L.NBBT + 1)) : nullptr;
         a.exp = getenv("RSSM_WIDE_EXP") ? atoi(getenv("RSSM_WIDE_EXP")) : 0;
         g_launches.fetch_add(1);
         if (check_cuda(rssm::launch_mrssm_wide_fwd(a, s), imagine ? "wide mrssm imagine launch" : "wide mrssm forward launch")) return 1;
@@ -286,7 +286,7 @@ int wide_mrssm_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
     const int D = d->D, T = d->T, A = d->A, F = D + 16;
     const long long plane = L.plane, tstride = (long long)rssm::wide::NPLANES * plane;
     if (d->B % 128 != 0 && check_cuda(cudaMemsetAsync(ws + W.drec, 0, W.tiles - W.drec, s), "workspace memset")) return 1;
-    if (check_cuda(cudaMemsetAsync(ws + W.bar, 0, 256 * (size_t)(L.ngroups + 1) + 4096, s), "barrier memset")) return 1;
+    if (check_cuda(cudaMemsetAsync(ws + W.bar, 0, 256 * (size_t)(L.NBBT + 1) + 4096, s), "barrier memset")) return 1;
     const __nv_bfloat16* rec = static_cast<const __nv_bfloat16*>(fo->saved);
     const float* logits = reinterpret_cast<const float*>(static_cast<const char*>(fo->saved) + wide_saved_planes_bytes(d));
 
@@ -322,9 +322,9 @@ int wide_mrssm_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
         a.d_feature = up->d_feature + r0 * T * F;
         a.d_actions = gin->d_actions ? gin->d_actions + r0 * T * A : nullptr;
         a.d_h0 = gin->d_h0 + r0 * D, a.d_z0 = gin->d_z0 + r0 * 16;
-        a.bar = reinterpret_cast<unsigned*>(ws + W.bar + 256 * (size_t)g);
-        a.status = reinterpret_cast<int*>(ws + W.bar + 256 * (size_t)L.ngroups);
-        a.timing = (g == 0 && getenv("RSSM_WIDE_TIMING")) ? reinterpret_cast<unsigned long long*>(ws + W.bar + 256 * (size_t)(L.ngroups + 1)) : nullptr;
+        a.bar = reinterpret_cast<unsigned*>(ws + W.bar + 256 * (size_t)bb0);
+        a.status = reinterpret_cast<int*>(ws + W.bar + 256 * (size_t)L.NBBT);
+        a.timing = (g == 0 && getenv("RSSM_WIDE_TIMING")) ? reinterpret_cast<unsigned long long*>(ws + W.bar + 256 * (size_t)(L.NBBT + 1)) : nullptr;
         a.exp = getenv("RSSM_WIDE_EXP") ? atoi(getenv("RSSM_WIDE_EXP")) : 0;
         g_launches.fetch_add(1);
         if (check_cuda(rssm::launch_mrssm_wide_bwd(a, s), "wide mrssm backward launch")) return 1;
