@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
         mbar_init(sm.accbar, 1), mbar_init(sm.stgbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_base)), "r"(256));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
 
     const int row = (warp & 3) * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int half = (warp >> 2) & 1;  // epilogue warps 0-3: column groups 0-1 of the slice, warps 4-7: groups 2-3
     const int grow = bb * BM + row;
     const bool rvalid = grow < p.B;
     float* carry = sm.carry + row * ROWF;  // d h carried to the previous step, this thread's 32 units (shared memory, CTA-private)
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
     for (int t = T - 1; t >= -1; --t) {
         // =================================== P1 ===================================
         const bool have_next = t < T - 1;  // dhid1_{t+1} exists
-        if (warp == 4) {
+        if (warp == PRODUCER_WARP) {
             if (lane == 0) {
                 if (t >= 0) {  // epilogue inputs: per-row statistics and this slice's head hiddens
                     mbar_expect_tx(sm.stgbar, STAT_BYTES + 12 * PIECE_BYTES);
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                     for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pW1x + (long long)c * (32 * 64), 32 * 64 * 2);
                 }
             }
-        } else if (warp == 5) {
+        } else if (warp == MMA_WARP) {
             if (lane == 0 && have_next) {
                 for (int c = 0; c < KC; ++c) mma_chunk(TB_DX, 32, c == 0);
                 umma_commit(sm.accbar);
@@ -253,20 +254,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                 float da[16];
                 tmem_ld16(tlane + TB_DX, dz);
                 tmem_ld16(tlane + TB_DX + 16, da);
-                if (s == 0 && rvalid && p.d_actions != nullptr) {
+                if (s == 0 && half == 0 && rvalid && p.d_actions != nullptr) {
 #pragma unroll
                     for (int a = 0; a < 8; ++a)
                         if (a < A) p.d_actions[((long long)grow * T + (t + 1)) * A + a] = da[a];
                 }
             }
             if (t < 0) {
-                if (s == 0 && rvalid) {
+                if (s == 0 && half == 0 && rvalid) {
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(p.d_z0 + (long long)grow * 16 + i) = make_float4(dz[i], dz[i + 1], dz[i + 2], dz[i + 3]);
                 }
                 if (rvalid) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(p.d_h0 + (long long)grow * D + s * 32 + i) = *reinterpret_cast<const float4*>(carry + i);
+                    for (int i = 16 * half; i < 16 * half + 16; i += 4) *reinterpret_cast<float4*>(p.d_h0 + (long long)grow * D + s * 32 + i) = *reinterpret_cast<const float4*>(carry + i);
                 }
             } else {
                 mbar_wait(sm.stgbar, stgph), stgph ^= 1;
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
 #pragma unroll
                     for (int i = 0; i < 16; ++i) dl[16 + 16 * e + i] = st[i] + rr[i] - sx[i] * sum;
                 }
-                if (s == 0) {  // d logits operand of the logit layers' weight gradients
+                if (s == 0 && half == 0) {  // d logits operand of the logit layers' weight gradients
                     __nv_bfloat16* dlg = drec(t, 0) + p.dlg_off;
 #pragma unroll
                     for (int g = 0; g < 6; ++g) {
@@ -313,7 +314,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
 #pragma unroll
                 for (int h = 0; h < 3; ++h) {
 #pragma unroll 1
-                    for (int qd = 0; qd < 4; ++qd) {
+                    for (int qd = 2 * half; qd < 2 * half + 2; ++qd) {
                         float y[8], g[8];
                         unpack8(stage16[(STAT_BYTES / 16) + (h * 4 + qd) * BM + row], y);
 #pragma unroll
@@ -338,14 +339,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
         grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== P2 ===================================
-        if (warp == 4) {
+        if (warp == PRODUCER_WARP) {
             if (lane == 0) {
                 mbar_expect_tx(sm.stgbar, 16 * PIECE_BYTES);  // gate record of this slice: r, z, n, hn
                 for (int i = 0; i < 16; ++i) bulk_g2s(sm.stage + i * PIECE_BYTES, rec(t, P_R + (i >> 2)) + piece(i & 3), PIECE_BYTES, sm.stgbar);
                 for (int c = 0; c < 3 * KC; ++c)
                     load(drec(t, DP_PH + c / KC) + blk + (long long)(c % KC) * (BM * 64), p.pWhdT + ((long long)s * 3 * KC + c) * (32 * 64), 32 * 64 * 2);
             }
-        } else if (warp == 5) {
+        } else if (warp == MMA_WARP) {
             if (lane == 0) {
                 for (int c = 0; c < 3 * KC; ++c) mma_chunk(TB_DH, 32, c == 0);
                 umma_commit(sm.accbar);
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                 const float* hprev = ((t == 0) ? p.h0 + (long long)grow * D : p.feature + ((long long)grow * T + (t - 1)) * F) + s * 32;
                 const float* dfe = p.d_feature + ((long long)grow * T + t) * F + s * 32;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) cp_async16(hps + 4 * i, hprev + 4 * i), cp_async16(dfs + 4 * i, dfe + 4 * i);
+                for (int i = 4 * half; i < 4 * half + 4; ++i) cp_async16(hps + 4 * i, hprev + 4 * i), cp_async16(dfs + 4 * i, dfe + 4 * i);
             }
             cp_async_commit();
             mbar_wait(sm.accbar, accph), accph ^= 1;
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
             mbar_wait(sm.stgbar, stgph), stgph ^= 1;
             cp_async_wait_all();
 #pragma unroll 1
-            for (int qd = 0; qd < 4; ++qd) {
+            for (int qd = 2 * half; qd < 2 * half + 2; ++qd) {
                 float dh[8], r[8], z[8], n[8], hn[8], hp[8], g0[8], g1[8], g2[8], g3[8];
                 tmem_ld8(tlane + TB_DH + qd * 8, dh);
                 unpack8(stage16[(0 * 4 + qd) * BM + row], r);
@@ -405,14 +406,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
         grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== P3 ===================================
-        if (warp == 4) {
+        if (warp == PRODUCER_WARP) {
             if (lane == 0) {
                 for (int c = 0; c < 2 * KC; ++c)
                     load(drec(t, DP_GR + c / KC) + blk + (long long)(c % KC) * (BM * 64), p.pWgT + ((long long)s * 2 * KC + c) * (64 * 64), 64 * 64 * 2);
                 for (int c = 0; c < KC; ++c) load(drec(t, DP_GIN) + blk + (long long)c * (BM * 64), p.pWihTn + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
                 for (int c = 0; c < KC; ++c) load(drec(t, DP_GHN) + blk + (long long)c * (BM * 64), p.pWhhTn + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
             }
-        } else if (warp == 5) {
+        } else if (warp == MMA_WARP) {
             if (lane == 0) {
                 for (int c = 0; c < 2 * KC; ++c) mma_chunk(TB_P3, 64, c == 0);
                 for (int c = 0; c < KC; ++c) mma_chunk(TB_P3, 32, false);
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
             mbar_wait(sm.accbar, accph), accph ^= 1;
             tc_fence_after();
 #pragma unroll 1
-            for (int qd = 0; qd < 4; ++qd) {
+            for (int qd = 2 * half; qd < 2 * half + 2; ++qd) {
                 float v[8], c[8];
                 tmem_ld8(tlane + TB_P3 + qd * 8, v);
                 *reinterpret_cast<uint4*>(drec(t, DP_X2) + piece(qd) + row * 8) = pack8(v);
@@ -437,13 +438,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
         grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== P4 ===================================
-        if (warp == 4) {
+        if (warp == PRODUCER_WARP) {
             if (lane == 0) {
                 mbar_expect_tx(sm.stgbar, 4 * PIECE_BYTES);  // hid1_t of this slice (ELU')
                 for (int i = 0; i < 4; ++i) bulk_g2s(sm.stage + i * PIECE_BYTES, rec(t, P_HID1) + piece(i), PIECE_BYTES, sm.stgbar);
                 for (int c = 0; c < KC; ++c) load(drec(t, DP_X2) + blk + (long long)c * (BM * 64), p.pW2T + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
             }
-        } else if (warp == 5) {
+        } else if (warp == MMA_WARP) {
             if (lane == 0) {
                 for (int c = 0; c < KC; ++c) mma_chunk(TB_H1, 32, c == 0);
                 umma_commit(sm.accbar);
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
             tc_fence_after();
             mbar_wait(sm.stgbar, stgph), stgph ^= 1;
 #pragma unroll 1
-            for (int qd = 0; qd < 4; ++qd) {
+            for (int qd = 2 * half; qd < 2 * half + 2; ++qd) {
                 float v[8], y[8];
                 tmem_ld8(tlane + TB_H1 + qd * 8, v);
                 unpack8(stage16[qd * BM + row], y);
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
     tc_fence_before();
     __syncthreads();
     __syncwarp();
-    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
 }
 
 // ---- transposed weight images for the backward contractions -----------------------------------------------------------------

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         mbar_init(sm.accbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -255,8 +255,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         umma_commit(&sm.empty[ring.slot]);
         ring.advance(STAGES);
     };
-    const int row = warp * 32 + lane;                     // epilogue: batch row inside the block (warps 0-3)
-    const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int row = (warp & 3) * 32 + lane;               // epilogue: batch row inside the block (TMEM lane quadrant = warp & 3)
+    const int half = (warp >> 2) & 1;                      // epilogue: warps 0-3 take column groups 0-1 of the slice, warps 4-7 groups 2-3
+    const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int grow = bb * BM + row;                        // row inside the launch group
     const bool rvalid = grow < p.B;
 
@@ -273,13 +274,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         __nv_bfloat16* rec_t = p.rec + (long long)t * p.t_stride;
         const __nv_bfloat16* hb_prev = (t == 0) ? p.h0p + blk : (p.rec + (long long)(t - 1) * p.t_stride + (long long)P_HB * p.plane_stride + blk);
         // =================================== phase A ===================================
-        if (warp == 4) {
+        if (warp == PRODUCER_WARP) {
             if (lane == 0) {
                 const __nv_bfloat16* a_src = rec_t + (long long)P_HID1 * p.plane_stride + blk;
                 for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pW2 + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
                 for (int c = 0; c < KC; ++c) load(hb_prev + (long long)c * (BM * 64), p.pWhh + ((long long)s * KC + c) * (96 * 64), 96 * 64 * 2);
             }
-        } else if (warp == 5) {
+        } else if (warp == MMA_WARP) {
             if (lane == 0) {
                 for (int c = 0; c < KC; ++c) mma_chunk(TM_X2, 32, c == 0);
                 umma_commit(sm.accbar);
@@ -289,8 +290,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             mbar_wait(sm.accbar, accph), accph ^= 1;
             tc_fence_after();
             __nv_bfloat16* x2 = rec_t + (long long)P_X2 * p.plane_stride;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
+#pragma unroll 1
+            for (int q = 2 * half; q < 2 * half + 2; ++q) {
                 float v[8];
                 tmem_ld8(tlane + TM_X2 + q * 8, v);
 #pragma unroll
@@ -302,12 +303,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== phase B ===================================
-        if (warp == 4) {
+        if (warp == PRODUCER_WARP) {
             if (lane == 0) {
                 const __nv_bfloat16* a_src = rec_t + (long long)P_X2 * p.plane_stride + blk;
                 for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pWih + ((long long)s * KC + c) * (96 * 64), 96 * 64 * 2);
             }
-        } else if (warp == 5) {
+        } else if (warp == MMA_WARP) {
             if (lane == 0) {
                 for (int c = 0; c < KC; ++c) mma_chunk(TM_GI, 96, c == 0);
                 umma_commit(sm.accbar);  // covers the gh MMAs of phase A as well
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             float* hsr = sm.hs + row * HROW;
             float* hout = p.feature + ((long long)grow * T + t) * F;
 #pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 2 * half; q < 2 * half + 2; ++q) {
                 float gi[8], gh[8], r[8], z[8], n[8], hn[8], h[8];
                 tmem_ld8(tlane + TM_GI + q * 8, gi);
                 tmem_ld8(tlane + TM_GH + q * 8, gh);
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         grid_sync(p.bar + bb * 64, epoch, p.status, NSL);
         stamp();
         // =================================== phase C ===================================
-        if (warp == 4) {
+        if (warp == PRODUCER_WARP) {
             if (lane == 0) {
                 const __nv_bfloat16* a_src = rec_t + (long long)P_HB * p.plane_stride + blk;
                 for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pWhd + ((long long)s * KC + c) * (96 * 64), 96 * 64 * 2);
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                     load(p.emb_v + (long long)t * p.emb_t_stride + (long long)bb * (BM * 64), p.pWve + (long long)s * (32 * 64), 32 * 64 * 2);
                 }
             }
-        } else if (warp == 5) {
+        } else if (warp == MMA_WARP) {
             if (lane == 0) {
                 for (int c = 0; c < KC; ++c) mma_chunk(TM_HD, 96, c == 0);
                 if (!imagine) {
@@ -382,35 +383,54 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         } else {
             mbar_wait(sm.accbar, accph), accph ^= 1;
             tc_fence_after();
-            float* part = p.part + ((long long)grow * NSL + s) * 48;
             const int nheads = imagine ? 1 : 3;
+            float accs[3][16];
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+#pragma unroll
+                for (int o = 0; o < 16; ++o) accs[h][o] = 0.f;
+                if (h < nheads) {
 #pragma unroll 1
-            for (int h = 0; h < nheads; ++h) {
-                float acc[16];
+                    for (int q = 2 * half; q < 2 * half + 2; ++q) {
+                        float v[8];
+                        tmem_ld8(tlane + TM_HD + h * 32 + q * 8, v);
 #pragma unroll
-                for (int o = 0; o < 16; ++o) acc[o] = 0.f;
-#pragma unroll 1
-                for (int q = 0; q < 4; ++q) {
-                    float v[8];
-                    tmem_ld8(tlane + TM_HD + h * 32 + q * 8, v);
+                        for (int i = 0; i < 8; ++i) v[i] = M::elu(v[i] + sm.bhd[h * 32 + q * 8 + i]);
+                        if (p.t_stride != 0)
+                            *reinterpret_cast<uint4*>(rec_t + (long long)(P_PH + h) * p.plane_stride + pk_off(bb, row, s * 32 + q * 8, D)) = pack8(v);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = M::elu(v[i] + sm.bhd[h * 32 + q * 8 + i]);
-                    if (p.t_stride != 0)
-                        *reinterpret_cast<uint4*>(rec_t + (long long)(P_PH + h) * p.plane_stride + pk_off(bb, row, s * 32 + q * 8, D)) = pack8(v);
+                        for (int i = 0; i < 8; ++i) {
+                            const float4* w = reinterpret_cast<const float4*>(sm.w2l + (h * 32 + q * 8 + i) * 16);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4* w = reinterpret_cast<const float4*>(sm.w2l + (h * 32 + q * 8 + i) * 16);
-#pragma unroll
-                        for (int o4 = 0; o4 < 4; ++o4) {
-                            const float4 ww = w[o4];
-                            acc[4 * o4] = fmaf(v[i], ww.x, acc[4 * o4]), acc[4 * o4 + 1] = fmaf(v[i], ww.y, acc[4 * o4 + 1]);
-                            acc[4 * o4 + 2] = fmaf(v[i], ww.z, acc[4 * o4 + 2]), acc[4 * o4 + 3] = fmaf(v[i], ww.w, acc[4 * o4 + 3]);
+                            for (int o4 = 0; o4 < 4; ++o4) {
+                                const float4 ww = w[o4];
+                                accs[h][4 * o4] = fmaf(v[i], ww.x, accs[h][4 * o4]), accs[h][4 * o4 + 1] = fmaf(v[i], ww.y, accs[h][4 * o4 + 1]);
+                                accs[h][4 * o4 + 2] = fmaf(v[i], ww.z, accs[h][4 * o4 + 2]), accs[h][4 * o4 + 3] = fmaf(v[i], ww.w, accs[h][4 * o4 + 3]);
+                            }
                         }
                     }
                 }
+            }
+            // the two column halves of a row meet in shared memory (the operand ring is idle here: every MMA of the phase is done)
+            float* ex = reinterpret_cast<float*>(sm.ring) + row * 52;
+            if (half == 1) {
 #pragma unroll
-                for (int o4 = 0; o4 < 4; ++o4)
-                    *reinterpret_cast<float4*>(part + h * 16 + o4 * 4) = make_float4(acc[4 * o4], acc[4 * o4 + 1], acc[4 * o4 + 2], acc[4 * o4 + 3]);
+                for (int h = 0; h < 3; ++h)
+#pragma unroll
+                    for (int o4 = 0; o4 < 4; ++o4)
+                        *reinterpret_cast<float4*>(ex + h * 16 + o4 * 4) = make_float4(accs[h][4 * o4], accs[h][4 * o4 + 1], accs[h][4 * o4 + 2], accs[h][4 * o4 + 3]);
+            }
+            epi_sync();
+            if (half == 0) {
+                float* part = p.part + ((long long)grow * NSL + s) * 48;
+#pragma unroll
+                for (int h = 0; h < 3; ++h)
+#pragma unroll
+                    for (int o4 = 0; o4 < 4; ++o4) {
+                        const float4 x = *reinterpret_cast<const float4*>(ex + h * 16 + o4 * 4);
+                        *reinterpret_cast<float4*>(part + h * 16 + o4 * 4) =
+                            make_float4(accs[h][4 * o4] + x.x, accs[h][4 * o4 + 1] + x.y, accs[h][4 * o4 + 2] + x.z, accs[h][4 * o4 + 3] + x.w);
+                    }
             }
         }
         stamp();
@@ -485,7 +505,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
     tc_fence_before();
     __syncthreads();
     __syncwarp();
-    if (warp == 5) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 // ---- packing kernels ---------------------------------------------------------------------------------------------------

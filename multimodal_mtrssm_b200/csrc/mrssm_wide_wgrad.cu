@@ -21,7 +21,7 @@ constexpr int WG_ONES_BYTES = 2 * 128 * 8 * 2;  // two 8-feature groups of the o
 
 __host__ __device__ inline size_t wg_smem_bytes() { return 128 + (size_t)WG_STAGES * WG_STAGE_BYTES + WG_ONES_BYTES + 64; }
 
-__global__ void __launch_bounds__(NTHREADS, 1) wide_wgrad_kernel(const WideWgradTile* __restrict__ tiles, int nsplit, int T, int NBBT,
+__global__ void __launch_bounds__(AUX_THREADS, 1) wide_wgrad_kernel(const WideWgradTile* __restrict__ tiles, int nsplit, int T, int NBBT,
                                                                   const __nv_bfloat16* __restrict__ ones) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
@@ -126,7 +126,7 @@ constexpr int DE_STAGES = 4;
 constexpr int DE_STAGE_BYTES = A_BYTES + 64 * 64 * 2;
 __host__ __device__ inline size_t de_smem_bytes() { return 128 + (size_t)DE_STAGES * DE_STAGE_BYTES + 128; }
 
-__global__ void __launch_bounds__(NTHREADS, 1) wide_dembed_kernel(const WideDembedArgs p) {
+__global__ void __launch_bounds__(AUX_THREADS, 1) wide_dembed_kernel(const WideDembedArgs p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~(uintptr_t)127);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)DE_STAGES * DE_STAGE_BYTES);
@@ -225,7 +225,7 @@ cudaError_t launch_wide_wgrad(const WideWgradTile* tiles_dev, int ntiles, int ns
     const size_t smem = wide::wg_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(wide::wide_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    wide::wide_wgrad_kernel<<<ntiles * nsplit, wide::NTHREADS, smem, s>>>(tiles_dev, nsplit, T, NBBT, ones);
+    wide::wide_wgrad_kernel<<<ntiles * nsplit, wide::AUX_THREADS, smem, s>>>(tiles_dev, nsplit, T, NBBT, ones);
     return cudaGetLastError();
 }
 
@@ -233,7 +233,7 @@ cudaError_t launch_wide_dembed(const WideDembedArgs& a, cudaStream_t s) {
     const size_t smem = wide::de_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(wide::wide_dembed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    wide::wide_dembed_kernel<<<dim3(a.T * a.NBBT, 2), wide::NTHREADS, smem, s>>>(a);
+    wide::wide_dembed_kernel<<<dim3(a.T * a.NBBT, 2), wide::AUX_THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
 

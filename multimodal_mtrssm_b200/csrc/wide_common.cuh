@@ -29,7 +29,9 @@ namespace rssm {
 namespace wide {
 
 constexpr int BM = 128;                // batch rows per block = MMA M
-constexpr int NTHREADS = 192;          // warps 0-3: epilogue (TMEM lane quadrant = warp), warp 4: producer, warp 5: MMA issuer
+constexpr int NTHREADS = 320;          // warps 0-7: epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2), warp 8: producer, warp 9: MMA issuer
+constexpr int PRODUCER_WARP = 8, MMA_WARP = 9, EPI_THREADS = 256;
+constexpr int AUX_THREADS = 192;       // non-recurrent kernels: warps 0-3 epilogue, warp 4 producer, warp 5 MMA issuer
 constexpr int A_BYTES = BM * 64 * 2;   // one K chunk (64 columns) of an activation block
 constexpr int NPLANES = 10;            // record planes per step
 enum Plane { P_HID1 = 0, P_X2, P_R, P_Z, P_N, P_HN, P_HB, P_PH, P_AH, P_VH };
@@ -68,6 +70,9 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// named barrier of the 8 epilogue warps
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // 8 consecutive accumulator columns of this thread's TMEM lane (32 * (warp & 3) + lane)
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
