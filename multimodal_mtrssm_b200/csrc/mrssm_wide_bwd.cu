@@ -34,11 +34,11 @@ static_assert(P2_DFE_OFF + BM * ROWF * 4 <= STAGE_REGION, "staging region too sm
 struct BwdSmem {
     unsigned char *ring, *stage;
     float *carry, *w2l;
-    uint64_t *full, *empty, *accbar, *stgbar;
+    uint64_t *full, *empty, *accbar, *stgbar, *firstbar;
     uint32_t* tmem_base;
 };
 __host__ __device__ inline size_t bwd_smem_bytes() {
-    return 128 + (size_t)BSTAGES * BSTAGE_BYTES + STAGE_REGION + BM * ROWF * 4 + 3 * 32 * 16 * 4 + (2 * BSTAGES + 2) * 8 + 16;
+    return 128 + (size_t)BSTAGES * BSTAGE_BYTES + STAGE_REGION + BM * ROWF * 4 + 3 * 32 * 16 * 4 + (2 * BSTAGES + 3) * 8 + 16;
 }
 __device__ __forceinline__ BwdSmem carve_bwd(unsigned char* dyn) {
     BwdSmem s;
@@ -51,6 +51,7 @@ __device__ __forceinline__ BwdSmem carve_bwd(unsigned char* dyn) {
     s.empty = reinterpret_cast<uint64_t*>(p), p += BSTAGES * 8;
     s.accbar = reinterpret_cast<uint64_t*>(p), p += 8;
     s.stgbar = reinterpret_cast<uint64_t*>(p), p += 8;
+    s.firstbar = reinterpret_cast<uint64_t*>(p), p += 8;
     s.tmem_base = reinterpret_cast<uint32_t*>(p);
     return s;
 }
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
 
     if (tid == 0) {
         for (int i = 0; i < BSTAGES; ++i) mbar_init(&sm.full[i], 1), mbar_init(&sm.empty[i], 1);
-        mbar_init(sm.accbar, 1), mbar_init(sm.stgbar, 1);
+        mbar_init(sm.accbar, 2), mbar_init(sm.stgbar, 1), mbar_init(sm.firstbar, 1);  // both issuers commit the accumulator barrier
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -183,7 +184,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
         }
         ring.advance(BSTAGES);
     };
+    const int issuer = warp == MMA_WARP ? 0 : 1;  // (meaningful in the two issuer warps only)
+    uint32_t chunk_ctr = 0, firstph = 0;
     auto mma_chunk = [&](uint32_t tcol, int N, bool first) {
+        const bool mine = (int)(chunk_ctr++ & 1u) == issuer;
+        if (!mine) {
+            if (first) {  // the other issuer zero-initialises this accumulator: order my later accumulating MMAs after that MMA
+                mbar_wait(sm.firstbar, firstph), firstph ^= 1;
+                tc_fence_after();
+            }
+            ring.advance(BSTAGES);
+            return;
+        }
         mbar_wait(&sm.full[ring.slot], ring.phase);
         tc_fence_after();
         const uint32_t a0 = smem_u32(sm.ring + (size_t)ring.slot * BSTAGE_BYTES), b0 = a0 + A_BYTES;
@@ -195,6 +207,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                 umma(tmem + tcol, smem_desc(a0 + kk * 2 * lboA, lboA, sbo), smem_desc(b0 + kk * 2 * lboB, lboB, sbo), idesc,
                      (first && kk == 0) ? 0u : 1u);
         umma_commit(&sm.empty[ring.slot]);
+        if (first) {
+            tc_fence_before();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sm.firstbar)) : "memory");
+            firstph ^= 1;
+        }
         ring.advance(BSTAGES);
     };
 
@@ -238,7 +255,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                     for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pW1x + (long long)c * (32 * 64), 32 * 64 * 2);
                 }
             }
-        } else if (warp == MMA_WARP) {
+        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
             if (lane == 0 && have_next) {
                 for (int c = 0; c < KC; ++c) mma_chunk(TB_DX, 32, c == 0);
                 umma_commit(sm.accbar);
@@ -346,7 +363,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                 for (int c = 0; c < 3 * KC; ++c)
                     load(drec(t, DP_PH + c / KC) + blk + (long long)(c % KC) * (BM * 64), p.pWhdT + ((long long)s * 3 * KC + c) * (32 * 64), 32 * 64 * 2);
             }
-        } else if (warp == MMA_WARP) {
+        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
             if (lane == 0) {
                 for (int c = 0; c < 3 * KC; ++c) mma_chunk(TB_DH, 32, c == 0);
                 umma_commit(sm.accbar);
@@ -413,7 +430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                 for (int c = 0; c < KC; ++c) load(drec(t, DP_GIN) + blk + (long long)c * (BM * 64), p.pWihTn + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
                 for (int c = 0; c < KC; ++c) load(drec(t, DP_GHN) + blk + (long long)c * (BM * 64), p.pWhhTn + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
             }
-        } else if (warp == MMA_WARP) {
+        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
             if (lane == 0) {
                 for (int c = 0; c < 2 * KC; ++c) mma_chunk(TB_P3, 64, c == 0);
                 for (int c = 0; c < KC; ++c) mma_chunk(TB_P3, 32, false);
@@ -444,7 +461,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                 for (int i = 0; i < 4; ++i) bulk_g2s(sm.stage + i * PIECE_BYTES, rec(t, P_HID1) + piece(i), PIECE_BYTES, sm.stgbar);
                 for (int c = 0; c < KC; ++c) load(drec(t, DP_X2) + blk + (long long)c * (BM * 64), p.pW2T + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
             }
-        } else if (warp == MMA_WARP) {
+        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
             if (lane == 0) {
                 for (int c = 0; c < KC; ++c) mma_chunk(TB_H1, 32, c == 0);
                 umma_commit(sm.accbar);

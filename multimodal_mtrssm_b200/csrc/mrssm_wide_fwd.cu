@@ -29,7 +29,7 @@ struct FwdSmem {
     unsigned char* ring;
     float *w1t, *b2s, *bih, *bhh, *bhd, *w2l, *b2l, *zval, *hs, *acts;
     int* zidx;
-    uint64_t *full, *empty, *accbar;
+    uint64_t *full, *empty, *accbar, *firstbar;
     uint32_t* tmem_base;
 };
 
@@ -39,7 +39,7 @@ __host__ __device__ inline size_t fwd_smem_bytes(int D, int A) {
     n += (size_t)(A + 17) * D * 4;
     n += (32 + 96 * 3) * 4 + 3 * 32 * 16 * 4 + 48 * 4 + MAX_RPC * 16 * 4;
     n += BM * HROW * 4 + MAX_RPC * 8 * 4 + MAX_RPC * 8 * 4;
-    n += (2 * STAGES + 1) * 8 + 16;
+    n += (2 * STAGES + 2) * 8 + 16;
     return n;
 }
 
@@ -61,6 +61,7 @@ __device__ __forceinline__ FwdSmem carve(unsigned char* dyn, int D, int A) {
     s.full = reinterpret_cast<uint64_t*>(p), p += STAGES * 8;
     s.empty = reinterpret_cast<uint64_t*>(p), p += STAGES * 8;
     s.accbar = reinterpret_cast<uint64_t*>(p), p += 8;
+    s.firstbar = reinterpret_cast<uint64_t*>(p), p += 8;
     s.tmem_base = reinterpret_cast<uint32_t*>(p);
     return s;
 }
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
     // ---- one-time setup ---------------------------------------------------------------------------------------------
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) mbar_init(&sm.full[i], 1), mbar_init(&sm.empty[i], 1);
-        mbar_init(sm.accbar, 1);
+        mbar_init(sm.accbar, 2), mbar_init(sm.firstbar, 1);  // both issuers commit the accumulator barrier
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -240,7 +241,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         }
         ring.advance(STAGES);
     };
+    const int issuer = warp == MMA_WARP ? 0 : 1;  // (meaningful in the two issuer warps only)
+    uint32_t chunk_ctr = 0, firstph = 0;
     auto mma_chunk = [&](uint32_t tcol, int N, bool first) {
+        const bool mine = (int)(chunk_ctr++ & 1u) == issuer;
+        if (!mine) {
+            if (first) {  // the other issuer zero-initialises this accumulator: order my later accumulating MMAs after that MMA
+                mbar_wait(sm.firstbar, firstph), firstph ^= 1;
+                tc_fence_after();
+            }
+            ring.advance(STAGES);
+            return;
+        }
         mbar_wait(&sm.full[ring.slot], ring.phase);
         tc_fence_after();
         const uint32_t a0 = smem_u32(sm.ring + (size_t)ring.slot * STAGE_BYTES), b0 = a0 + A_BYTES;
@@ -253,6 +265,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             if (p.exp != 2) umma(tmem + tcol, da, db, idesc, (first && kk == 0) ? 0u : 1u);
         }
         umma_commit(&sm.empty[ring.slot]);
+        if (first) {
+            tc_fence_before();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sm.firstbar)) : "memory");
+            firstph ^= 1;
+        }
         ring.advance(STAGES);
     };
     const int row = (warp & 3) * 32 + lane;               // epilogue: batch row inside the block (TMEM lane quadrant = warp & 3)
@@ -280,7 +297,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                 for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pW2 + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
                 for (int c = 0; c < KC; ++c) load(hb_prev + (long long)c * (BM * 64), p.pWhh + ((long long)s * KC + c) * (96 * 64), 96 * 64 * 2);
             }
-        } else if (warp == MMA_WARP) {
+        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
             if (lane == 0) {
                 for (int c = 0; c < KC; ++c) mma_chunk(TM_X2, 32, c == 0);
                 umma_commit(sm.accbar);
@@ -308,7 +325,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                 const __nv_bfloat16* a_src = rec_t + (long long)P_X2 * p.plane_stride + blk;
                 for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pWih + ((long long)s * KC + c) * (96 * 64), 96 * 64 * 2);
             }
-        } else if (warp == MMA_WARP) {
+        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
             if (lane == 0) {
                 for (int c = 0; c < KC; ++c) mma_chunk(TM_GI, 96, c == 0);
                 umma_commit(sm.accbar);  // covers the gh MMAs of phase A as well
@@ -371,7 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                     load(p.emb_v + (long long)t * p.emb_t_stride + (long long)bb * (BM * 64), p.pWve + (long long)s * (32 * 64), 32 * 64 * 2);
                 }
             }
-        } else if (warp == MMA_WARP) {
+        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
             if (lane == 0) {
                 for (int c = 0; c < KC; ++c) mma_chunk(TM_HD, 96, c == 0);
                 if (!imagine) {

@@ -29,8 +29,11 @@ namespace rssm {
 namespace wide {
 
 constexpr int BM = 128;                // batch rows per block = MMA M
-constexpr int NTHREADS = 320;          // warps 0-7: epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2), warp 8: producer, warp 9: MMA issuer
-constexpr int PRODUCER_WARP = 8, MMA_WARP = 9, EPI_THREADS = 256;
+constexpr int NTHREADS = 352;          // warps 0-7: epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2), warp 8: producer, warps 9-10: MMA issuers
+constexpr int PRODUCER_WARP = 8, MMA_WARP = 9, MMA_WARP2 = 10, EPI_THREADS = 256;
+// Two issuer threads take alternate operand chunks: one thread's wait -> 4 MMAs -> commit loop costs ~470 cycles per chunk
+// (mbarrier ops ~130 cycles each and ~47 cycles per tcgen05.mma issue, all serial in the thread: scratch/umma_ring*.cu) against
+// 268 cycles of tensor-pipe time, so a single issuer leaves the pipe idle 40 % of the time.
 constexpr int AUX_THREADS = 192;       // non-recurrent kernels: warps 0-3 epilogue, warp 4 producer, warp 5 MMA issuer
 constexpr int A_BYTES = BM * 64 * 2;   // one K chunk (64 columns) of an activation block
 constexpr int NPLANES = 10;            // record planes per step
