@@ -47,10 +47,12 @@ struct MrssmWideFwdArgs {
     float* logits;             // [rows][T][32] audio / vision logits for the backward (NULL when not saving)
     unsigned long long* timing;  // debug: globaltimer at the end of each phase of the first steps (CTA 0), or NULL
     int exp;                     // debug (RSSM_WIDE_EXP): 1 = skip the operand copies, 2 = skip the MMAs (timing experiments, wrong results)
+    int cs;                      // CTAs per cluster along the slice index (1, 2 or 4): activation chunks are multicast inside a cluster
     unsigned* bar;
     int* status;
 };
 cudaError_t launch_mrssm_wide_fwd(const MrssmWideFwdArgs& a, cudaStream_t s);
+cudaError_t launch_wide_persistent(const void* kernel, void* args, int grid, int cs, size_t smem, cudaStream_t s);
 size_t mrssm_wide_fwd_smem(int D);
 
 
@@ -72,6 +74,7 @@ struct MrssmWideBwdArgs {
     int* status;
     unsigned long long* timing;  // debug, as in the forward
     int exp;
+    int cs;  // as in the forward
 };
 cudaError_t launch_mrssm_wide_bwd(const MrssmWideBwdArgs& a, cudaStream_t s);
 

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
     const int bb = blockIdx.x / NSL, s = blockIdx.x - bb * NSL;
 
     if (tid == 0) {
-        for (int i = 0; i < BSTAGES; ++i) mbar_init(&sm.full[i], 1), mbar_init(&sm.empty[i], 1);
+        for (int i = 0; i < BSTAGES; ++i) mbar_init(&sm.full[i], 1), mbar_init(&sm.empty[i], p.cs);  // every CTA of the cluster releases a slot
         mbar_init(sm.accbar, 2), mbar_init(sm.stgbar, 1), mbar_init(sm.firstbar, 1);  // both issuers commit the accumulator barrier
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -165,6 +165,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *sm.tmem_base;
+    const uint32_t crank = p.cs > 1 ? cluster_rank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
+    if (p.cs > 1) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive / multicast copy
 
     Ring ring;
     uint32_t accph = 0, stgph = 0;
@@ -179,7 +182,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
             mbar_expect_tx(&sm.full[ring.slot], 0);
         } else {
             mbar_expect_tx(&sm.full[ring.slot], A_BYTES + b_bytes);
-            bulk_g2s(st, a_src, A_BYTES, &sm.full[ring.slot]);
+            if (p.cs == 1) {
+                bulk_g2s(st, a_src, A_BYTES, &sm.full[ring.slot]);
+            } else {  // my 1/CS of the activation chunk, delivered to every CTA of the cluster
+                const uint32_t piece = A_BYTES / p.cs;
+                bulk_g2s_mc(st + crank * piece, reinterpret_cast<const unsigned char*>(a_src) + crank * piece, piece, &sm.full[ring.slot], cmask);
+            }
             bulk_g2s(st + A_BYTES, b_src, b_bytes, &sm.full[ring.slot]);
         }
         ring.advance(BSTAGES);
@@ -206,7 +214,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
             if (p.exp != 2)
                 umma(tmem + tcol, smem_desc(a0 + kk * 2 * lboA, lboA, sbo), smem_desc(b0 + kk * 2 * lboB, lboB, sbo), idesc,
                      (first && kk == 0) ? 0u : 1u);
-        umma_commit(&sm.empty[ring.slot]);
+        if (p.cs == 1) umma_commit(&sm.empty[ring.slot]);
+        else umma_commit_mc(&sm.empty[ring.slot], cmask);
         if (first) {
             tc_fence_before();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sm.firstbar)) : "memory");
@@ -485,6 +494,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
         stamp();
     }
 
+    if (p.cs > 1) {
+        // no CTA may leave while a peer can still multicast into its shared memory or arrive on its barriers: take every ring
+        // slot once more (= all peers' last commits have arrived here), then meet the cluster
+        if (warp == PRODUCER_WARP && lane == 0)
+            for (int i = 0; i < BSTAGES; ++i) mbar_wait(&sm.empty[ring.slot], ring.phase ^ 1), ring.advance(BSTAGES);
+        __syncthreads();
+        cluster_sync_all();
+    }
     tc_fence_before();
     __syncthreads();
     __syncwarp();
@@ -544,12 +561,8 @@ cudaError_t launch_wide_pack_bwd_weights(const MrssmWideBwdArgs& a, cudaStream_t
 }
 
 cudaError_t launch_mrssm_wide_bwd(const MrssmWideBwdArgs& a, cudaStream_t s) {
-    const size_t smem = wide::bwd_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(wide::mrssm_wide_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     MrssmWideBwdArgs args = a;
-    void* params[] = {&args};
-    return cudaLaunchCooperativeKernel((const void*)wide::mrssm_wide_bwd_kernel, dim3(a.NBB * a.NSL), dim3(wide::NTHREADS), params, smem, s);
+    return launch_wide_persistent((const void*)wide::mrssm_wide_bwd_kernel, &args, a.NBB * a.NSL, a.cs, wide::bwd_smem_bytes(), s);
 }
 
 }  // namespace rssm

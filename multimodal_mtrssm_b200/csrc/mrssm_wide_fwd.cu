@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
 
     // ---- one-time setup ---------------------------------------------------------------------------------------------
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) mbar_init(&sm.full[i], 1), mbar_init(&sm.empty[i], 1);
+        for (int i = 0; i < STAGES; ++i) mbar_init(&sm.full[i], 1), mbar_init(&sm.empty[i], p.cs);  // every CTA of the cluster releases a slot
         mbar_init(sm.accbar, 2), mbar_init(sm.firstbar, 1);  // both issuers commit the accumulator barrier
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -148,6 +148,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *sm.tmem_base;
+    const uint32_t crank = p.cs > 1 ? cluster_rank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
+    if (p.cs > 1) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive / multicast copy
 
     // phase-D rows of this CTA: the rows of its own batch block are dealt out over the block's slice CTAs
     const int rpc = (BM + NSL - 1) / NSL;
@@ -236,7 +239,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             mbar_expect_tx(&sm.full[ring.slot], 0);
         } else {
             mbar_expect_tx(&sm.full[ring.slot], A_BYTES + b_bytes);
-            bulk_g2s(st, a_src, A_BYTES, &sm.full[ring.slot]);
+            if (p.cs == 1) {
+                bulk_g2s(st, a_src, A_BYTES, &sm.full[ring.slot]);
+            } else {  // my 1/CS of the activation chunk, delivered to every CTA of the cluster
+                const uint32_t piece = A_BYTES / p.cs;
+                bulk_g2s_mc(st + crank * piece, reinterpret_cast<const unsigned char*>(a_src) + crank * piece, piece, &sm.full[ring.slot], cmask);
+            }
             bulk_g2s(st + A_BYTES, b_src, b_bytes, &sm.full[ring.slot]);
         }
         ring.advance(STAGES);
@@ -264,7 +272,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
             const uint64_t db = p.desc_swap ? smem_desc(b0 + kk * 2 * lboB, sbo, lboB) : smem_desc(b0 + kk * 2 * lboB, lboB, sbo);
             if (p.exp != 2) umma(tmem + tcol, da, db, idesc, (first && kk == 0) ? 0u : 1u);
         }
-        umma_commit(&sm.empty[ring.slot]);
+        if (p.cs == 1) umma_commit(&sm.empty[ring.slot]);
+        else umma_commit_mc(&sm.empty[ring.slot], cmask);
         if (first) {
             tc_fence_before();
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sm.firstbar)) : "memory");
@@ -519,6 +528,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         stamp();
     }
 
+    if (p.cs > 1) {
+        // no CTA may leave while a peer can still multicast into its shared memory or arrive on its barriers: take every ring
+        // slot once more (= all peers' last commits have arrived here), then meet the cluster
+        if (warp == PRODUCER_WARP && lane == 0)
+            for (int i = 0; i < STAGES; ++i) mbar_wait(&sm.empty[ring.slot], ring.phase ^ 1), ring.advance(STAGES);
+        __syncthreads();
+        cluster_sync_all();
+    }
     tc_fence_before();
     __syncthreads();
     __syncwarp();
@@ -564,13 +581,24 @@ __global__ void wide_pack_rows_kernel(const float* __restrict__ src, int B, int 
 
 size_t mrssm_wide_fwd_smem(int D) { return wide::fwd_smem_bytes(D, 8); }
 
-cudaError_t launch_mrssm_wide_fwd(const MrssmWideFwdArgs& a, cudaStream_t s) {
-    const size_t smem = wide::fwd_smem_bytes(a.D, a.A);
-    cudaError_t e = cudaFuncSetAttribute(wide::mrssm_wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// cooperative launch (co-residency for the barriers) of clusters of a.cs CTAs along the slice index
+cudaError_t launch_wide_persistent(const void* kernel, void* args, int grid, int cs, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(wide::NTHREADS), cfg.dynamicSmemBytes = smem, cfg.stream = s;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative, attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cs, attr[1].val.clusterDim.y = 1, attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = cs > 1 ? 2 : 1;
+    void* params[] = {args};
+    return cudaLaunchKernelExC(&cfg, kernel, params);
+}
+
+cudaError_t launch_mrssm_wide_fwd(const MrssmWideFwdArgs& a, cudaStream_t s) {
     MrssmWideFwdArgs args = a;
-    void* params[] = {&args};
-    return cudaLaunchCooperativeKernel((const void*)wide::mrssm_wide_fwd_kernel, dim3(a.NBB * a.NSL), dim3(wide::NTHREADS), params, smem, s);
+    return launch_wide_persistent((const void*)wide::mrssm_wide_fwd_kernel, &args, a.NBB * a.NSL, a.cs, wide::fwd_smem_bytes(a.D, a.A), s);
 }
 
 cudaError_t launch_wide_pack_weights(const WidePackJobs& jobs, cudaStream_t s) {

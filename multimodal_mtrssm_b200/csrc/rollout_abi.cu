@@ -185,6 +185,18 @@ size_t wide_bwd_workspace(const RssmMrssmDims* d, const WideLayout& L) {
 }
 
 
+// CTAs per cluster along the slice index (the activation chunks are multicast inside a cluster).  Default 1: measured on B200
+// at cfg3, clusters of 2 / 4 are correct but SLOWER (6.7 ms against 6.2-6.3 ms): the operand ring is 4-5 stages deep and every slot
+// release then waits for the slowest of the cluster's CTAs, which costs more than the L2 reads it saves.  RSSM_WIDE_CLUSTER=2|4
+// selects them for experiments.
+int wide_cluster_size(int NSL) {
+    int cs = 1;
+    if (const char* e = getenv("RSSM_WIDE_CLUSTER")) cs = atoi(e);
+    if (cs != 1 && cs != 2 && cs != 4) cs = 1;
+    while (cs > 1 && NSL % cs != 0) cs >>= 1;
+    return cs;
+}
+
 int wide_pack_weights(const RssmMrssmDims* d, const RssmMrssmWeights* w, char* ws, const WideLayout& L, bool imagine, cudaStream_t s) {
     const int D = d->D;
     rssm::WidePackJobs J{};
@@ -264,6 +276,7 @@ int wide_mrssm_fwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
         a.status = reinterpret_cast<int*>(ws + L.bar + 256 * (size_t)L.NBBT);
         a.timing = (g == 0 && getenv("RSSM_WIDE_TIMING")) ? reinterpret_cast<unsigned long long*>(ws + L.bar + 256 * (size_t)(L.NBBT + 1)) : nullptr;
         a.exp = getenv("RSSM_WIDE_EXP") ? atoi(getenv("RSSM_WIDE_EXP")) : 0;
+        a.cs = wide_cluster_size(L.NSL);
         g_launches.fetch_add(1);
         if (check_cuda(rssm::launch_mrssm_wide_fwd(a, s), imagine ? "wide mrssm imagine launch" : "wide mrssm forward launch")) return 1;
     }
@@ -326,6 +339,7 @@ int wide_mrssm_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
         a.status = reinterpret_cast<int*>(ws + W.bar + 256 * (size_t)L.NBBT);
         a.timing = (g == 0 && getenv("RSSM_WIDE_TIMING")) ? reinterpret_cast<unsigned long long*>(ws + W.bar + 256 * (size_t)(L.NBBT + 1)) : nullptr;
         a.exp = getenv("RSSM_WIDE_EXP") ? atoi(getenv("RSSM_WIDE_EXP")) : 0;
+        a.cs = wide_cluster_size(L.NSL);
         g_launches.fetch_add(1);
         if (check_cuda(rssm::launch_mrssm_wide_bwd(a, s), "wide mrssm backward launch")) return 1;
     }

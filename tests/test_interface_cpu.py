@@ -213,6 +213,49 @@ def test_library_exports_every_declared_symbol():
     assert C.sizeof(_lib.MrssmWeights) == 20 * 8 and C.sizeof(_lib.MtrssmWeights) == 28 * 8
 
 
+def test_wide_family_abi_size_queries_and_struct_layout():
+    """ABI v2 (wide MoPoE-MRSSM sizes): record / workspace sizes are host computations that must work without a GPU for the
+    record, reject unsupported dims with 0 (the launch reports the error), and the ctypes structs carry the workspace fields."""
+    import ctypes as C
+
+    from multimodal_mtrssm_b200 import _lib, rollout_ops
+
+    assert C.sizeof(_lib.MrssmOutputs) == 8 * 8 and C.sizeof(_lib.MrssmInputGrads) == 8 * 8  # 7 pointers + size_t
+    d512 = _lib.MrssmDims(B=1024, T=64, A=6, E=64, D=512, H=512, C=4, K=4, precision=_lib.PRECISION_BF16)
+    planes = 64 * 10 * 8 * 512 * 128 * 2          # [T][plane][block][D/8][128][8] bf16
+    logits = 8 * 128 * 64 * 32 * 4                # [blocks*128][T][32] fp32
+    assert _lib.mrssm_saved_bytes(d512) == planes + logits
+    assert rollout_ops._mr_saved_shape(1024, 64, 512)[0] * 2 == planes + logits
+    ragged = _lib.MrssmDims(B=200, T=6, A=6, E=64, D=384, H=384, C=8, K=2, precision=_lib.PRECISION_BF16)
+    assert _lib.mrssm_saved_bytes(ragged) == rollout_ops._mr_saved_shape(200, 6, 384)[0] * 2  # padded to 2 blocks of 128
+    small = _lib.MrssmDims(B=8, T=30, A=6, E=64, D=32, H=32, C=4, K=4, precision=_lib.PRECISION_FP32)
+    assert _lib.mrssm_saved_bytes(small) == 8 * 30 * _lib.MRSSM_SAVED_FLOATS * 4 and _lib.mrssm_workspace_bytes(small, False) == 0
+    for bad in (dict(D=96, H=96), dict(D=512, H=256), dict(D=1024, H=1024), dict(D=512, H=512, precision=_lib.PRECISION_FP32),
+                dict(D=512, H=512, A=9), dict(D=512, H=512, C=4, K=8)):
+        kw = dict(B=8, T=4, A=6, E=64, D=512, H=512, C=4, K=4, precision=_lib.PRECISION_BF16)
+        kw.update(bad)
+        assert _lib.mrssm_saved_bytes(_lib.MrssmDims(**kw)) == 0, bad
+
+
+def test_wide_family_fake_shapes_and_size_check():
+    """Shape inference of the custom ops (meta tensors, no kernel) follows deterministic_size, and unsupported sizes are
+    rejected by the host wrapper before any launch."""
+    from multimodal_mtrssm_b200 import rollout_ops
+
+    D, B, T, K = 512, 5, 3, 4
+    meta = lambda *s: torch.empty(*s, device="meta")  # noqa: E731
+    shapes = H.mr_shapes(D)
+    from multimodal_mtrssm_b200.params import MR_STATE_KEYS
+
+    weights = [meta(*shapes[k]) for k in MR_STATE_KEYS]
+    out = torch.ops.mtrssm_b200.mrssm_rollout(weights, meta(B, T, 6), meta(B, T, 64), meta(B, T, 64), meta(B, D), meta(B, 16),
+                                              meta(B, T, 4), None, K, 1, 0.2, 0.8, True)
+    assert out[0].shape == (B, T, D + 16) and out[1].shape == (B, T, 4, 4) and out[5].dtype == torch.bfloat16
+    assert out[5].numel() * 2 == 3 * 10 * 1 * D * 128 * 2 + 128 * 3 * 32 * 4
+    with pytest.raises(RuntimeError, match="supports"):
+        rollout_ops._mr_check([torch.empty(s) for s in H.mr_shapes(96).values()], torch.empty(2, 3, 64), torch.empty(2, 96), torch.empty(2, 16))
+
+
 # ---- data parallel plumbing (gloo, world size 2) ------------------------------------------------------------------------
 DP_WORKER = r'''
 import os, sys, torch, torch.distributed as dist
