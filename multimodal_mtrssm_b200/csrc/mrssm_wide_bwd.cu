@@ -23,7 +23,7 @@ namespace wide {
 constexpr int BSTAGES = 4;
 constexpr int BB_MAX_BYTES = 64 * 64 * 2;
 constexpr int BSTAGE_BYTES = A_BYTES + BB_MAX_BYTES;
-constexpr int TB_DX = 0, TB_DH = 32, TB_P3 = 64, TB_H1 = 128;
+constexpr int TB_DX = 0, TB_DH = 32, TB_P3 = 64, TB_H1 = 128, BWD_ACC_OFF = 160;  // second issuer's accumulator copies: + BWD_ACC_OFF
 constexpr int STAT_BYTES = 32 * BM * 16;            // per-row statistics of one (t, block): [32 float4 columns][128 rows]
 constexpr int PIECE_BYTES = BM * 16;                // 8 features x 128 rows of a packed plane
 constexpr int STAGE_REGION = STAT_BYTES + 12 * PIECE_BYTES;  // P1: stat + 12 head-hidden pieces; P2: 16 gate pieces + hprev + dfe
@@ -147,11 +147,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
 
     if (tid == 0) {
         for (int i = 0; i < BSTAGES; ++i) mbar_init(&sm.full[i], 1), mbar_init(&sm.empty[i], p.cs);  // every CTA of the cluster releases a slot
-        mbar_init(sm.accbar, 2), mbar_init(sm.stgbar, 1), mbar_init(sm.firstbar, 1);  // both issuers commit the accumulator barrier
+        mbar_init(sm.accbar, N_ISSUERS), mbar_init(sm.stgbar, 1), mbar_init(sm.firstbar, 1);  // both issuers commit the accumulator barrier
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_base)), "r"(256));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sm.tmem_base)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     for (int i = tid; i < 3 * 32 * 16; i += NTHREADS) {  // w2l[h][j][o] = W2_h[o][32 s + j]
@@ -192,15 +192,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
         }
         ring.advance(BSTAGES);
     };
-    const int issuer = warp == MMA_WARP ? 0 : 1;  // (meaningful in the two issuer warps only)
-    uint32_t chunk_ctr = 0, firstph = 0;
-    auto mma_chunk = [&](uint32_t tcol, int N, bool first) {
-        const bool mine = (int)(chunk_ctr++ & 1u) == issuer;
-        if (!mine) {
-            if (first) {  // the other issuer zero-initialises this accumulator: order my later accumulating MMAs after that MMA
-                mbar_wait(sm.firstbar, firstph), firstph ^= 1;
-                tc_fence_after();
-            }
+    const int issuer = warp == MMA_WARP ? 0 : 1;  // (meaningful in the issuer warps only)
+    // chunk c of an accumulation group: issuer c % N_ISSUERS accumulates it into its own copy of the accumulator
+    auto mma_chunk = [&](uint32_t tcol, int N, int c) {
+        if (N_ISSUERS > 1 && (c & 1) != issuer) {
             ring.advance(BSTAGES);
             return;
         }
@@ -209,18 +204,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
         const uint32_t a0 = smem_u32(sm.ring + (size_t)ring.slot * BSTAGE_BYTES), b0 = a0 + A_BYTES;
         const uint32_t lboB = N * 16;
         const uint32_t idesc = idesc_bf16(N, 0, 0);
+        const uint32_t dcol = tmem + tcol + (N_ISSUERS > 1 ? issuer * BWD_ACC_OFF : 0);
+        const bool first = c < N_ISSUERS;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
             if (p.exp != 2)
-                umma(tmem + tcol, smem_desc(a0 + kk * 2 * lboA, lboA, sbo), smem_desc(b0 + kk * 2 * lboB, lboB, sbo), idesc,
+                umma(dcol, smem_desc(a0 + kk * 2 * lboA, lboA, sbo), smem_desc(b0 + kk * 2 * lboB, lboB, sbo), idesc,
                      (first && kk == 0) ? 0u : 1u);
         if (p.cs == 1) umma_commit(&sm.empty[ring.slot]);
         else umma_commit_mc(&sm.empty[ring.slot], cmask);
-        if (first) {
-            tc_fence_before();
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sm.firstbar)) : "memory");
-            firstph ^= 1;
-        }
         ring.advance(BSTAGES);
     };
 
@@ -264,9 +256,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                     for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pW1x + (long long)c * (32 * 64), 32 * 64 * 2);
                 }
             }
-        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+        } else if (warp == MMA_WARP || (N_ISSUERS > 1 && warp == MMA_WARP2)) {
             if (lane == 0 && have_next) {
-                for (int c = 0; c < KC; ++c) mma_chunk(TB_DX, 32, c == 0);
+                for (int c = 0; c < KC; ++c) mma_chunk(TB_DX, 32, c);
                 umma_commit(sm.accbar);
             }
         } else {
@@ -278,8 +270,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                 mbar_wait(sm.accbar, accph), accph ^= 1;
                 tc_fence_after();
                 float da[16];
-                tmem_ld16(tlane + TB_DX, dz);
-                tmem_ld16(tlane + TB_DX + 16, da);
+                acc_ld16(tlane + TB_DX, BWD_ACC_OFF, dz);
+                acc_ld16(tlane + TB_DX + 16, BWD_ACC_OFF, da);
                 if (s == 0 && half == 0 && rvalid && p.d_actions != nullptr) {
 #pragma unroll
                     for (int a = 0; a < 8; ++a)
@@ -372,9 +364,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                 for (int c = 0; c < 3 * KC; ++c)
                     load(drec(t, DP_PH + c / KC) + blk + (long long)(c % KC) * (BM * 64), p.pWhdT + ((long long)s * 3 * KC + c) * (32 * 64), 32 * 64 * 2);
             }
-        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+        } else if (warp == MMA_WARP || (N_ISSUERS > 1 && warp == MMA_WARP2)) {
             if (lane == 0) {
-                for (int c = 0; c < 3 * KC; ++c) mma_chunk(TB_DH, 32, c == 0);
+                for (int c = 0; c < 3 * KC; ++c) mma_chunk(TB_DH, 32, c);
                 umma_commit(sm.accbar);
             }
         } else {
@@ -394,7 +386,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
 #pragma unroll 1
             for (int qd = 2 * half; qd < 2 * half + 2; ++qd) {
                 float dh[8], r[8], z[8], n[8], hn[8], hp[8], g0[8], g1[8], g2[8], g3[8];
-                tmem_ld8(tlane + TB_DH + qd * 8, dh);
+                acc_ld8(tlane + TB_DH + qd * 8, BWD_ACC_OFF, dh);
                 unpack8(stage16[(0 * 4 + qd) * BM + row], r);
                 unpack8(stage16[(1 * 4 + qd) * BM + row], z);
                 unpack8(stage16[(2 * 4 + qd) * BM + row], n);
@@ -439,11 +431,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                 for (int c = 0; c < KC; ++c) load(drec(t, DP_GIN) + blk + (long long)c * (BM * 64), p.pWihTn + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
                 for (int c = 0; c < KC; ++c) load(drec(t, DP_GHN) + blk + (long long)c * (BM * 64), p.pWhhTn + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
             }
-        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+        } else if (warp == MMA_WARP || (N_ISSUERS > 1 && warp == MMA_WARP2)) {
             if (lane == 0) {
-                for (int c = 0; c < 2 * KC; ++c) mma_chunk(TB_P3, 64, c == 0);
-                for (int c = 0; c < KC; ++c) mma_chunk(TB_P3, 32, false);
-                for (int c = 0; c < KC; ++c) mma_chunk(TB_P3 + 32, 32, false);
+                for (int c = 0; c < 2 * KC; ++c) mma_chunk(TB_P3, 64, c);
+                for (int c = 0; c < KC; ++c) mma_chunk(TB_P3, 32, 2 * KC + c);
+                for (int c = 0; c < KC; ++c) mma_chunk(TB_P3 + 32, 32, 3 * KC + c);
                 umma_commit(sm.accbar);
             }
         } else {
@@ -452,9 +444,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
 #pragma unroll 1
             for (int qd = 2 * half; qd < 2 * half + 2; ++qd) {
                 float v[8], c[8];
-                tmem_ld8(tlane + TB_P3 + qd * 8, v);
+                acc_ld8(tlane + TB_P3 + qd * 8, BWD_ACC_OFF, v);
                 *reinterpret_cast<uint4*>(drec(t, DP_X2) + piece(qd) + row * 8) = pack8(v);
-                tmem_ld8(tlane + TB_P3 + 32 + qd * 8, c);
+                acc_ld8(tlane + TB_P3 + 32 + qd * 8, BWD_ACC_OFF, c);
                 float4 e = *reinterpret_cast<const float4*>(carry + qd * 8), f = *reinterpret_cast<const float4*>(carry + qd * 8 + 4);
                 e.x += c[0], e.y += c[1], e.z += c[2], e.w += c[3], f.x += c[4], f.y += c[5], f.z += c[6], f.w += c[7];
                 *reinterpret_cast<float4*>(carry + qd * 8) = e, *reinterpret_cast<float4*>(carry + qd * 8 + 4) = f;
@@ -470,9 +462,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
                 for (int i = 0; i < 4; ++i) bulk_g2s(sm.stage + i * PIECE_BYTES, rec(t, P_HID1) + piece(i), PIECE_BYTES, sm.stgbar);
                 for (int c = 0; c < KC; ++c) load(drec(t, DP_X2) + blk + (long long)c * (BM * 64), p.pW2T + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
             }
-        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+        } else if (warp == MMA_WARP || (N_ISSUERS > 1 && warp == MMA_WARP2)) {
             if (lane == 0) {
-                for (int c = 0; c < KC; ++c) mma_chunk(TB_H1, 32, c == 0);
+                for (int c = 0; c < KC; ++c) mma_chunk(TB_H1, 32, c);
                 umma_commit(sm.accbar);
             }
         } else {
@@ -482,7 +474,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
 #pragma unroll 1
             for (int qd = 2 * half; qd < 2 * half + 2; ++qd) {
                 float v[8], y[8];
-                tmem_ld8(tlane + TB_H1 + qd * 8, v);
+                acc_ld8(tlane + TB_H1 + qd * 8, BWD_ACC_OFF, v);
                 unpack8(stage16[qd * BM + row], y);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] *= elu_grad_from_out(y[i]);
@@ -505,7 +497,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_bwd_kernel(const Mrssm
     tc_fence_before();
     __syncthreads();
     __syncwarp();
-    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256));
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
 // ---- transposed weight images for the backward contractions -----------------------------------------------------------------

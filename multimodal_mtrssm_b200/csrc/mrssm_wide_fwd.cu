@@ -11,7 +11,7 @@
 //      partial logits of the slice (CUDA cores; 32 features x 16 outputs per head)  -> part[row][s][48]
 //   D  the block's rows are dealt out evenly over its slice CTAs: sum the partial logits, MoPoE fusion (mopoe_mrssm/core.py:241-251,135-154),
 //      per-group softmax, inverse-CDF draw, KL, per-step outputs; hid1_{t+1} = ELU(W1 . [a_{t+1} ; z_t] + b1) (networks.py:164-169)
-// Accumulators live in TMEM (x2 @0, gh @32, gi @128, heads @224); gh is issued in phase A and consumed in phase B.
+// Accumulators live in TMEM; gh is issued in phase A and consumed in phase B.
 #include "kernels.h"
 #include "wide_common.cuh"
 
@@ -21,7 +21,9 @@ namespace wide {
 constexpr int STAGES = 5;
 constexpr int B_MAX_BYTES = 96 * 64 * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_MAX_BYTES;
-constexpr int TM_X2 = 0, TM_GH = 32, TM_GI = 128, TM_HD = 224;
+// TMEM columns: gh lives from phase A to phase B; x2 (phase A), gi (B) and the heads (C) take turns in one region.  With two
+// issuers every accumulator has a second copy FWD_ACC_OFF columns further on.
+constexpr int TM_GH = 0, TM_R = 96 * N_ISSUERS, TM_X2 = TM_R, TM_GI = TM_R, TM_HD = TM_R, FWD_ACC_OFF = 96;
 constexpr int MAX_RPC = 64;  // rows per CTA in phase D (NSL >= 2)
 constexpr int HROW = 36;     // padded fp32 row of the CTA's own h slice (conflict-free float4 access)
 
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
     // ---- one-time setup ---------------------------------------------------------------------------------------------
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) mbar_init(&sm.full[i], 1), mbar_init(&sm.empty[i], p.cs);  // every CTA of the cluster releases a slot
-        mbar_init(sm.accbar, 2), mbar_init(sm.firstbar, 1);  // both issuers commit the accumulator barrier
+        mbar_init(sm.accbar, N_ISSUERS), mbar_init(sm.firstbar, 1);  // every issuer commits the accumulator barrier
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -249,15 +251,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         }
         ring.advance(STAGES);
     };
-    const int issuer = warp == MMA_WARP ? 0 : 1;  // (meaningful in the two issuer warps only)
-    uint32_t chunk_ctr = 0, firstph = 0;
-    auto mma_chunk = [&](uint32_t tcol, int N, bool first) {
-        const bool mine = (int)(chunk_ctr++ & 1u) == issuer;
-        if (!mine) {
-            if (first) {  // the other issuer zero-initialises this accumulator: order my later accumulating MMAs after that MMA
-                mbar_wait(sm.firstbar, firstph), firstph ^= 1;
-                tc_fence_after();
-            }
+    const int issuer = warp == MMA_WARP ? 0 : 1;  // (meaningful in the issuer warps only)
+    // chunk c of an accumulation group: issuer c % N_ISSUERS accumulates it into its own copy of the accumulator
+    auto mma_chunk = [&](uint32_t tcol, int N, int c) {
+        if (N_ISSUERS > 1 && (c & 1) != issuer) {
             ring.advance(STAGES);
             return;
         }
@@ -266,19 +263,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
         const uint32_t a0 = smem_u32(sm.ring + (size_t)ring.slot * STAGE_BYTES), b0 = a0 + A_BYTES;
         const uint32_t lboB = N * 16;
         const uint32_t idesc = idesc_bf16(N, 0, 0);
+        const uint32_t dcol = tmem + tcol + (N_ISSUERS > 1 ? issuer * FWD_ACC_OFF : 0);
+        const bool first = c < N_ISSUERS;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             const uint64_t da = p.desc_swap ? smem_desc(a0 + kk * 2 * lboA, sbo, lboA) : smem_desc(a0 + kk * 2 * lboA, lboA, sbo);
             const uint64_t db = p.desc_swap ? smem_desc(b0 + kk * 2 * lboB, sbo, lboB) : smem_desc(b0 + kk * 2 * lboB, lboB, sbo);
-            if (p.exp != 2) umma(tmem + tcol, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+            if (p.exp != 2) umma(dcol, da, db, idesc, (first && kk == 0) ? 0u : 1u);
         }
         if (p.cs == 1) umma_commit(&sm.empty[ring.slot]);
         else umma_commit_mc(&sm.empty[ring.slot], cmask);
-        if (first) {
-            tc_fence_before();
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(sm.firstbar)) : "memory");
-            firstph ^= 1;
-        }
         ring.advance(STAGES);
     };
     const int row = (warp & 3) * 32 + lane;               // epilogue: batch row inside the block (TMEM lane quadrant = warp & 3)
@@ -306,11 +300,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                 for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pW2 + ((long long)s * KC + c) * (32 * 64), 32 * 64 * 2);
                 for (int c = 0; c < KC; ++c) load(hb_prev + (long long)c * (BM * 64), p.pWhh + ((long long)s * KC + c) * (96 * 64), 96 * 64 * 2);
             }
-        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+        } else if (warp == MMA_WARP || (N_ISSUERS > 1 && warp == MMA_WARP2)) {
             if (lane == 0) {
-                for (int c = 0; c < KC; ++c) mma_chunk(TM_X2, 32, c == 0);
+                for (int c = 0; c < KC; ++c) mma_chunk(TM_X2, 32, c);
                 umma_commit(sm.accbar);
-                for (int c = 0; c < KC; ++c) mma_chunk(TM_GH, 96, c == 0);
+                for (int c = 0; c < KC; ++c) mma_chunk(TM_GH, 96, c);
             }
         } else {
             mbar_wait(sm.accbar, accph), accph ^= 1;
@@ -319,7 +313,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
 #pragma unroll 1
             for (int q = 2 * half; q < 2 * half + 2; ++q) {
                 float v[8];
-                tmem_ld8(tlane + TM_X2 + q * 8, v);
+                acc_ld8(tlane + TM_X2 + q * 8, FWD_ACC_OFF, v);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] += sm.b2s[q * 8 + i];
                 *reinterpret_cast<uint4*>(x2 + pk_off(bb, row, s * 32 + q * 8, D)) = pack8(v);
@@ -334,9 +328,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                 const __nv_bfloat16* a_src = rec_t + (long long)P_X2 * p.plane_stride + blk;
                 for (int c = 0; c < KC; ++c) load(a_src + (long long)c * (BM * 64), p.pWih + ((long long)s * KC + c) * (96 * 64), 96 * 64 * 2);
             }
-        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+        } else if (warp == MMA_WARP || (N_ISSUERS > 1 && warp == MMA_WARP2)) {
             if (lane == 0) {
-                for (int c = 0; c < KC; ++c) mma_chunk(TM_GI, 96, c == 0);
+                for (int c = 0; c < KC; ++c) mma_chunk(TM_GI, 96, c);
                 umma_commit(sm.accbar);  // covers the gh MMAs of phase A as well
             }
         } else {
@@ -347,16 +341,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
 #pragma unroll 1
             for (int q = 2 * half; q < 2 * half + 2; ++q) {
                 float gi[8], gh[8], r[8], z[8], n[8], hn[8], h[8];
-                tmem_ld8(tlane + TM_GI + q * 8, gi);
-                tmem_ld8(tlane + TM_GH + q * 8, gh);
+                acc_ld8(tlane + TM_GI + q * 8, FWD_ACC_OFF, gi);
+                acc_ld8(tlane + TM_GH + q * 8, FWD_ACC_OFF, gh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) r[i] = M::sigmoid(gi[i] + gh[i] + sm.bih[q * 8 + i] + sm.bhh[q * 8 + i]);
-                tmem_ld8(tlane + TM_GI + 32 + q * 8, gi);
-                tmem_ld8(tlane + TM_GH + 32 + q * 8, gh);
+                acc_ld8(tlane + TM_GI + 32 + q * 8, FWD_ACC_OFF, gi);
+                acc_ld8(tlane + TM_GH + 32 + q * 8, FWD_ACC_OFF, gh);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) z[i] = M::sigmoid(gi[i] + gh[i] + sm.bih[32 + q * 8 + i] + sm.bhh[32 + q * 8 + i]);
-                tmem_ld8(tlane + TM_GI + 64 + q * 8, gi);
-                tmem_ld8(tlane + TM_GH + 64 + q * 8, gh);
+                acc_ld8(tlane + TM_GI + 64 + q * 8, FWD_ACC_OFF, gi);
+                acc_ld8(tlane + TM_GH + 64 + q * 8, FWD_ACC_OFF, gh);
                 float hp[8];
                 {
                     const float4 a = *reinterpret_cast<const float4*>(hsr + q * 8), b = *reinterpret_cast<const float4*>(hsr + q * 8 + 4);
@@ -397,12 +391,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
                     load(p.emb_v + (long long)t * p.emb_t_stride + (long long)bb * (BM * 64), p.pWve + (long long)s * (32 * 64), 32 * 64 * 2);
                 }
             }
-        } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+        } else if (warp == MMA_WARP || (N_ISSUERS > 1 && warp == MMA_WARP2)) {
             if (lane == 0) {
-                for (int c = 0; c < KC; ++c) mma_chunk(TM_HD, 96, c == 0);
+                for (int c = 0; c < KC; ++c) mma_chunk(TM_HD, 96, c);
                 if (!imagine) {
-                    mma_chunk(TM_HD + 32, 32, false);
-                    mma_chunk(TM_HD + 64, 32, false);
+                    mma_chunk(TM_HD + 32, 32, KC);
+                    mma_chunk(TM_HD + 64, 32, KC + 1);
                 }
                 umma_commit(sm.accbar);
             }
@@ -419,7 +413,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mrssm_wide_fwd_kernel(const Mrssm
 #pragma unroll 1
                     for (int q = 2 * half; q < 2 * half + 2; ++q) {
                         float v[8];
-                        tmem_ld8(tlane + TM_HD + h * 32 + q * 8, v);
+                        acc_ld8(tlane + TM_HD + h * 32 + q * 8, FWD_ACC_OFF, v);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = M::elu(v[i] + sm.bhd[h * 32 + q * 8 + i]);
                         if (p.t_stride != 0)

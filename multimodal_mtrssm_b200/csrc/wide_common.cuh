@@ -29,11 +29,18 @@ namespace rssm {
 namespace wide {
 
 constexpr int BM = 128;                // batch rows per block = MMA M
-constexpr int NTHREADS = 352;          // warps 0-7: epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2), warp 8: producer, warps 9-10: MMA issuers
+#ifndef RSSM_WIDE_ISSUERS
+#define RSSM_WIDE_ISSUERS 2
+#endif
+constexpr int N_ISSUERS = RSSM_WIDE_ISSUERS;  // MMA issuer threads (1 or 2; build-time switch -DRSSM_WIDE_ISSUERS=2), see below
+constexpr int NTHREADS = 320 + 32 * (N_ISSUERS - 1);  // warps 0-7: epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2), warp 8: producer, warps 9(-10): MMA issuer(s)
 constexpr int PRODUCER_WARP = 8, MMA_WARP = 9, MMA_WARP2 = 10, EPI_THREADS = 256;
 // Two issuer threads take alternate operand chunks: one thread's wait -> 4 MMAs -> commit loop costs ~470 cycles per chunk
 // (mbarrier ops ~130 cycles each and ~47 cycles per tcgen05.mma issue, all serial in the thread: scratch/umma_ring*.cu) against
-// 268 cycles of tensor-pipe time, so a single issuer leaves the pipe idle 40 % of the time.
+// 268 cycles of tensor-pipe time, so a single issuer leaves the pipe idle 40 % of the time (cfg3, same box: 6.70 -> 6.29 ms).
+// Each issuer accumulates its chunks (even / odd) into ITS OWN copy of the accumulator (TMEM columns + acc_off); the epilogue
+// adds the two copies.  So every accumulator is written by one thread in a fixed order and the results stay bit-reproducible
+// (two threads accumulating into one tile would make the summation order a race).
 constexpr int AUX_THREADS = 192;       // non-recurrent kernels: warps 0-3 epilogue, warp 4 producer, warp 5 MMA issuer
 constexpr int A_BYTES = BM * 64 * 2;   // one K chunk (64 columns) of an activation block
 constexpr int NPLANES = 10;            // record planes per step
@@ -129,6 +136,26 @@ __device__ __forceinline__ void unpack8(const uint4 q, float (&v)[8]) {
     for (int i = 0; i < 4; ++i) {
         v[2 * i] = __uint_as_float(w[i] << 16);
         v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+// this thread's 8 / 16 accumulator columns, summed over the issuers' copies
+__device__ __forceinline__ void acc_ld8(uint32_t taddr, uint32_t acc_off, float (&v)[8]) {
+    tmem_ld8(taddr, v);
+    if (N_ISSUERS > 1) {
+        float w[8];
+        tmem_ld8(taddr + acc_off, w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += w[i];
+    }
+}
+__device__ __forceinline__ void acc_ld16(uint32_t taddr, uint32_t acc_off, float (&v)[16]) {
+    tmem_ld16(taddr, v);
+    if (N_ISSUERS > 1) {
+        float w[16];
+        tmem_ld16(taddr + acc_off, w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += w[i];
     }
 }
 

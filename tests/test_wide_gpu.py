@@ -89,3 +89,70 @@ def test_wide_backward_bf16_vs_oracle(ops, D, B, T, K, balancing):
         rep.check("d " + k.replace("rnn_to_post_projector", "post"), w[k].grad, w_ref[k].grad, rtol=0,
                   atol=3e-2 * float(w_ref[k].grad.abs().max()))
     rep.finish()
+
+
+def test_wide_multiple_launch_groups_match_oracle(ops):
+    """B = 1300 at hidden 512 is 11 batch blocks = two launch groups (9 + 2 blocks on 148 SMs): the group offsets of every
+    buffer (records, gradient planes, narrow planes, statistics) are exercised; forward and all gradients against the oracle."""
+    R, P = ops
+    D, B, T, K = 512, 1300, 2, 4
+    params, inp, C = wide_case(D, B, T, K)
+    inp["u_prior"] = None
+    up = wide_upstream(B, T, C, K, D)
+    got, w, x = run_mrssm(R, P, params, inp, K, precision=1, grad=True, upstream=up)
+    idx = got["feature"][..., D:].detach().cpu().reshape(B, T, C, K).argmax(-1)
+    want, w_ref, x_ref = oracle_mrssm(params, inp, C, K, grad=True, upstream=up, forced=idx)
+    rep = H.Report("wide mrssm, two launch groups (B=1300, hidden 512)")
+    rep.check("deter", got["feature"][..., :D], want["deter"], rtol=0, atol=3e-2)
+    rep.check("post_probs", got["post_probs"], want["post_probs"], rtol=0, atol=3e-2)
+    for k in ("actions", "embed_a", "embed_v", "h0", "z0"):
+        rep.check("d " + k, x[k].grad, x_ref[k].grad, rtol=0, atol=3e-2 * float(x_ref[k].grad.abs().max()))
+    for k in w:
+        rep.check("d " + k.replace("rnn_to_post_projector", "post"), w[k].grad, w_ref[k].grad, rtol=0,
+                  atol=3e-2 * float(w_ref[k].grad.abs().max()))
+    rep.finish()
+
+
+def test_wide_cfg3_full_size_properties(ops):
+    """BASELINE.json cfg3 at full size (B = 1024, T = 64, hidden 512), where the CPU oracle is too slow: size-independent
+    properties.  Distributions normalise; samples are exact one-hots and equal the inverse-CDF draw of the kernel's own
+    probabilities; the KL output equals the KL of the returned probabilities; rolling out in two chained chunks equals one
+    rollout BIT FOR BIT (state hand-over, deterministic summation orders); gradients are finite and linear in the upstream."""
+    R, P = ops
+    D, B, T, K, C = 512, 1024, 64, 4, 4
+    params = {k: v.cuda() for k, v in H.make_params(H.mr_shapes(D), gain=1.0).items()}
+    inp = cuda(H.mrssm_inputs(B, T, C, K, D=D))
+    inp["u_prior"] = None
+    w = P.mrssm_weight_list(params)
+    with torch.no_grad():
+        full = R.mrssm_rollout(w, class_size=K, precision=1, **inp)
+    for k in ("prior_probs", "post_probs"):
+        s = full[k].sum(-1)
+        assert torch.allclose(s, torch.ones_like(s), atol=1e-3), k
+    z = full["feature"][..., D:].reshape(B, T, C, K)
+    assert bool(((z == 0) | (z == 1)).all()) and bool((z.sum(-1) == 1).all())
+    idx = O.inverse_cdf_index(full["post_probs"].cpu(), inp["u_post"].cpu())
+    margin = O.cdf_margin(full["post_probs"].cpu(), inp["u_post"].cpu())
+    assert bool(((idx == z.argmax(-1).cpu()) | (margin < 1e-5)).all())
+    kl = O.kl_per_sample(full["post_probs"].cpu(), full["prior_probs"].cpu(), False)
+    torch.testing.assert_close(full["kl"].cpu(), kl, rtol=2e-3, atol=2e-3)
+    assert bool(torch.isfinite(full["feature"]).all()) and float(full["feature"][..., :D].abs().max()) <= 1.0 + 1e-3 + float(inp["h0"].abs().max())
+    # chained chunks
+    t0 = 23
+    cut = lambda d, a, b: {k: (v[:, a:b].contiguous() if v is not None and v.dim() == 3 and v.shape[1] == T else v) for k, v in d.items()}  # noqa: E731
+    with torch.no_grad():
+        first = R.mrssm_rollout(w, class_size=K, precision=1, **cut(inp, 0, t0))
+        nxt = cut(inp, t0, T)
+        nxt.update(h0=first["feature"][:, -1, :D].contiguous(), z0=first["feature"][:, -1, D:].contiguous())
+        second = R.mrssm_rollout(w, class_size=K, precision=1, **nxt)
+    assert torch.equal(torch.cat([first["feature"], second["feature"]], 1), full["feature"])
+    assert torch.equal(torch.cat([first["kl"], second["kl"]], 1), full["kl"])
+    # gradients: finite, and linear in the upstream gradient (2x upstream -> 2x gradients up to bf16 rounding of the planes)
+    wg = [t.clone().requires_grad_(True) for t in w]
+    up = torch.randn(B, T, D + 16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
+    out = R.mrssm_rollout(wg, class_size=K, precision=1, **inp)
+    g1 = torch.autograd.grad((out["feature"] * up).sum(), wg, retain_graph=True)
+    g2 = torch.autograd.grad((out["feature"] * (2 * up)).sum(), wg)
+    for a, b in zip(g1, g2):
+        assert bool(torch.isfinite(a).all())
+        torch.testing.assert_close(b, 2 * a, rtol=0, atol=2e-2 * max(float(a.abs().max()), 1e-6))
