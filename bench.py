@@ -390,6 +390,55 @@ def time_wide_cfg3(device: torch.device, iters: int = 10, B: int = 1024, T: int 
             "via": "public op API (incl. packing kernels, torch allocations and the loss)"}
 
 
+def time_likelihood(device: torch.device, peak_gbs: float, B: int = 4096, T: int = 30, iters: int = 20) -> dict:
+    """the fused Gaussian reconstruction likelihood of both modalities (objective.py:7-23 as
+    mopoe_mrssm/core.py:294-303 calls it) on decoder-shaped tensors [B,T,1,32,32]; one launch forward, one backward.
+    Algorithmic bytes: forward reads prediction + target (8 B per element), backward reads both and writes d prediction (12 B).
+    4 x 503 MB of inputs exceed the 126 MB L2.  Beside it: the reference's own formulation (torch.distributions) eager on this GPU."""
+    import torch.distributions as td
+
+    from multimodal_mtrssm_b200 import objective
+
+    g = torch.Generator(device=device).manual_seed(1234)
+    mk = lambda: torch.rand(B, T, 1, 32, 32, device=device, generator=g) * 2 - 1  # noqa: E731
+    preds, tgts = [mk().requires_grad_(True), mk().requires_grad_(True)], [mk(), mk()]
+    n = 2 * B * T * 1024
+    ones = torch.ones(2, device=device)
+
+    def timed(fn) -> float:  # noqa: ANN001
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(iters):
+            fn()
+        end.record()
+        torch.cuda.synchronize()
+        return start.elapsed_time(end) / iters
+
+    det = [p.detach() for p in preds]
+    nb = [B * T, B * T]
+    fwd_ms = timed(lambda: objective.gaussian_nll_op(det, tgts, nb, 1.0))
+    bwd_ms = timed(lambda: objective.gaussian_nll_bwd_op(det, tgts, nb, 1.0, ones, False))
+
+    def ours() -> None:
+        torch.autograd.grad(objective.likelihood_pairs(preds, tgts, 3).sum(), preds)
+
+    def ref() -> None:
+        loss = sum(-td.Independent(td.Normal(p, 1.0), 3).log_prob(t).mean() for p, t in zip(preds, tgts))
+        torch.autograd.grad(loss, preds)
+
+    ours_ms, ref_ms = timed(ours), timed(ref)
+    return {"workload": f"both modalities [B={B},T={T},1,32,32] fp32, fwd+bwd", "elements": n,
+            "fwd_kernel_ms": fwd_ms, "bwd_kernel_ms": bwd_ms, "fwd_bwd_via_api_ms": ours_ms,
+            "roofline_fwd": {"bound": "hbm", "achieved": 8 * n / (fwd_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                             "frac": 8 * n / (fwd_ms * 1e-3) / 1e9 / peak_gbs, "algorithmic_bytes_per_launch": 8 * n},
+            "roofline_bwd": {"bound": "hbm", "achieved": 12 * n / (bwd_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                             "frac": 12 * n / (bwd_ms * 1e-3) / 1e9 / peak_gbs, "algorithmic_bytes_per_launch": 12 * n},
+            "reference_formulation_eager_on_this_gpu_ms": ref_ms, "speedup_vs_reference_eager_gpu": ref_ms / ours_ms}
+
+
 def reference_eager_gpu_cfg3(device: torch.device, B: int = 1024, T: int = 64, D: int = 512) -> dict:
     """The "vs reference" number of cfg3: the fp32 oracle (= the reference's PyTorch rollout with explicit noise)
     run EAGER on this GPU, fwd + autograd bwd, CUDA events.  Baseline leg: touches oracle/."""
@@ -550,6 +599,8 @@ def main() -> None:
             extras["cfg3_wide_mrssm"]["reference_eager_on_this_gpu"] = reference_eager_gpu_cfg3(device)
             r = extras["cfg3_wide_mrssm"]
             r["speedup_vs_reference_eager_gpu"] = r["reference_eager_on_this_gpu"]["ms_per_step"] / r["ms_per_step"]
+        pk = ROOT / "MEASURED_PEAKS.json"
+        extras["likelihood_f3"] = time_likelihood(device, json.loads(pk.read_text())["hbm_gbs"] if pk.exists() else 6650.0)
     if world > 1:
         import torch.distributed as dist
 

@@ -16,6 +16,8 @@
  *                             KL terms of :589-600)
  *   rssm_mtrssm_rollout_bwd  autograd (BPTT) of the above
  *   rssm_mtrssm_imagine_fwd  MoPoE_MMTRSSM.rollout_transition      mmtrssm/mopoe_mmtrssm/core.py:496-544
+ *   rssm_gaussian_nll_fwd    likelihood (objective.py:7-23) for all modalities of compute_reconstruction_loss
+ *                            (mrssm/mopoe_mrssm/core.py:294-303) in one launch; rssm_gaussian_nll_bwd = its autograd
  *
  * Conventions
  *   - every pointer is a DEVICE pointer to contiguous fp32 (8-byte aligned); the library borrows it for the
@@ -43,7 +45,7 @@
 extern "C" {
 #endif
 
-#define RSSM_ABI_VERSION 2
+#define RSSM_ABI_VERSION 3
 #define RSSM_PRECISION_FP32 0
 #define RSSM_PRECISION_BF16 1
 /* bf16 tensor-core path whose backward is ONE kernel: BPTT + weight-gradient contractions on tcgen05 with TMEM accumulators
@@ -225,6 +227,34 @@ int rssm_mtrssm_wgrad(const RssmMtrssmDims *dims, const RssmMtrssmInputs *in, co
    u_prior_* required */
 int rssm_mtrssm_imagine_fwd(const RssmMtrssmDims *dims, const RssmMtrssmWeights *w, const RssmMtrssmInputs *in,
                             const RssmMtrssmOutputs *out, void *stream);
+
+/* ---- reconstruction likelihood ------------------------------------------------------------------------- */
+/* Replaces the body of `likelihood` (objective.py:7-23) as `compute_reconstruction_loss` calls it once per modality
+   (mrssm/mopoe_mrssm/core.py:294-303):
+     loss = -mean over the batch dims of Independent(Normal(prediction, scale), event_ndims).log_prob(target)
+          = 0.5 / (scale^2 * n_batch) * sum_i (target_i - prediction_i)^2 + n_event * (log(scale) + 0.5 log(2 pi)),
+   n_event = n_elems / n_batch.  Up to RSSM_NLL_MAX_SEGMENTS (prediction, target) pairs -- the modalities -- per launch.
+   prediction may be fp32 / bf16 / fp16 (decoder output under autocast), target and loss are fp32.  Pointers must be 16-byte
+   aligned.  The result is bit-reproducible (fixed summation order for a given size). */
+#define RSSM_NLL_MAX_SEGMENTS 4
+#define RSSM_DTYPE_F32 0
+#define RSSM_DTYPE_BF16 1
+#define RSSM_DTYPE_F16 2
+typedef struct {
+    const void *prediction;  /* [n_elems] of pred_dtype */
+    const float *target;     /* [n_elems] */
+    size_t n_elems, n_batch; /* n_batch = product of the batch dims (the mean's denominator) */
+    float scale;
+    float *loss;             /* fwd out: device scalar */
+    const float *d_loss;     /* bwd in: device scalar upstream gradient; NULL = 1 */
+    void *d_prediction;      /* bwd out: [n_elems] of pred_dtype */
+    float *d_target;         /* bwd out: [n_elems]; may be NULL */
+} RssmNllPair;
+/* bytes of zero-filled scratch rssm_gaussian_nll_fwd needs; a call leaves it zero-filled where it must be (reusable without
+   a memset by later calls on the SAME stream; concurrent streams need their own) */
+size_t rssm_gaussian_nll_workspace_bytes(void);
+int rssm_gaussian_nll_fwd(const RssmNllPair *pairs, int n_pairs, int pred_dtype, void *workspace, size_t workspace_bytes, void *stream);
+int rssm_gaussian_nll_bwd(const RssmNllPair *pairs, int n_pairs, int pred_dtype, void *stream);
 
 /* ---- misc ------------------------------------------------------------------------------------------------ */
 int rssm_abi_version(void);

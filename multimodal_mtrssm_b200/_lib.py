@@ -17,7 +17,7 @@ from .build import LIB, build_library
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 PRECISION_BF16_FUSED = 2  # bf16 path with the one-kernel backward (tcgen05 weight gradients); MMTRSSM only
-ABI_VERSION = 2
+ABI_VERSION = 3
 MRSSM_SAVED_FLOATS, MRSSM_DPRE_FLOATS = 320, 336
 MTRSSM_SAVED_FLOATS, MTRSSM_DPRE_FLOATS = 208, 304
 MTRSSM_SAVED_BF16 = MTRSSM_SAVED_FLOATS
@@ -90,12 +90,21 @@ MtrssmInputGrads = _struct(
     _ptrs("d_actions d_embed_a d_embed_v d_deter_h0 d_deter_l0 d_hidden_h0 d_hidden_l0 d_stoch_h0 d_stoch_l0 dpre"),
 )
 
+NLL_MAX_SEGMENTS = 4
+DTYPE_CODES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+NllPair = _struct(
+    "RssmNllPair",
+    [("prediction", _fp), ("target", _fp), ("n_elems", C.c_size_t), ("n_batch", C.c_size_t), ("scale", C.c_float),
+     ("loss", _fp), ("d_loss", _fp), ("d_prediction", _fp), ("d_target", _fp)],
+)
+
 EXPORTS = (
     "rssm_mrssm_rollout_fwd", "rssm_mrssm_rollout_bwd", "rssm_mrssm_imagine_fwd",
     "rssm_mtrssm_rollout_fwd", "rssm_mtrssm_rollout_bwd", "rssm_mtrssm_imagine_fwd",
     "rssm_mrssm_wgrad", "rssm_mtrssm_wgrad",
     "rssm_abi_version", "rssm_last_error", "rssm_kernel_launch_count",
     "rssm_mrssm_saved_bytes", "rssm_mrssm_workspace_bytes",
+    "rssm_gaussian_nll_fwd", "rssm_gaussian_nll_bwd", "rssm_gaussian_nll_workspace_bytes",
 )
 
 
@@ -125,6 +134,12 @@ def lib() -> C.CDLL:
     handle.rssm_mtrssm_rollout_fwd.argtypes = [P] * 5
     handle.rssm_mtrssm_imagine_fwd.argtypes = [P] * 5
     handle.rssm_mtrssm_rollout_bwd.argtypes = [P] * 8
+    handle.rssm_gaussian_nll_workspace_bytes.restype = C.c_size_t
+    handle.rssm_gaussian_nll_workspace_bytes.argtypes = []
+    handle.rssm_gaussian_nll_fwd.restype = C.c_int
+    handle.rssm_gaussian_nll_fwd.argtypes = [P, C.c_int, C.c_int, P, C.c_size_t, P]
+    handle.rssm_gaussian_nll_bwd.restype = C.c_int
+    handle.rssm_gaussian_nll_bwd.argtypes = [P, C.c_int, C.c_int, P]
     if handle.rssm_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{LIB.name}: ABI version {handle.rssm_abi_version()} != {ABI_VERSION}")
     return handle

@@ -215,4 +215,26 @@ enum { O_ASP1Z, O_ASP1A, O_ASP2, O_IHR, O_IHZ, O_IHN, O_HHR, O_HHZ, O_HHN, O_P1,
 }  // namespace wgl_mr
 static_assert((wgl_mt::STRIDE * 2 / 16) % 2 == 1 && (wgl_mr::STRIDE * 2 / 16) % 2 == 1, "row stride must be an odd number of 16B chunks (ldmatrix bank-conflict free)");
 
+// ---- Gaussian reconstruction likelihood (likelihood_kernel.cu) ---------------------------------------
+struct NllSeg {
+    const void* prediction;  // pred_dtype elements
+    const float* target;
+    size_t n;                // elements
+    double sq_coeff;         // 0.5 / (scale^2 * n_batch)
+    double constant;         // n_event * (log(scale) + 0.5 log(2 pi))
+    float* loss;             // forward: device scalar out
+    const float* d_loss;     // backward: device scalar in (NULL = 1)
+    void* d_prediction;      // backward out, pred_dtype elements
+    float* d_target;         // backward out, may be NULL
+};
+struct NllArgs {
+    NllSeg seg[RSSM_NLL_MAX_SEGMENTS];
+    int nseg;
+    int pred_dtype;  // RSSM_DTYPE_*
+    double* partials;    // [nseg][ctas]
+    unsigned* tickets;   // [RSSM_NLL_MAX_SEGMENTS], zero between launches
+};
+int nll_ctas_per_segment(int nseg);
+cudaError_t launch_gaussian_nll(const NllArgs& a, bool backward, cudaStream_t s);
+
 }  // namespace rssm

@@ -3,6 +3,7 @@
 // caller's stream.  No hidden state; errors are reported through a thread-local message.
 #include <stdlib.h>
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -711,6 +712,59 @@ int rssm_mtrssm_wgrad(const RssmMtrssmDims* d, const RssmMtrssmInputs* in, const
         return check_cuda(rssm::launch_wgrad_mt_slab(k, static_cast<cudaStream_t>(stream)), "mtrssm wgrad (slab) launch");
     }
     return check_cuda(rssm::launch_wgrad_mma(j, 0, mt_kernel_precision(d->precision), static_cast<cudaStream_t>(stream)), "mtrssm wgrad launch");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reconstruction likelihood (objective.py:7-23)
+// ---------------------------------------------------------------------------------------------------
+size_t rssm_gaussian_nll_workspace_bytes(void) {
+    return 64 + sizeof(double) * RSSM_NLL_MAX_SEGMENTS * (size_t)rssm::nll_ctas_per_segment(1);
+}
+
+static int nll_args(const RssmNllPair* pairs, int n_pairs, int pred_dtype, bool backward, rssm::NllArgs* a) {
+    REQUIRE(pairs);
+    if (n_pairs < 1 || n_pairs > RSSM_NLL_MAX_SEGMENTS) return fail("n_pairs must be 1..%d (got %d)", RSSM_NLL_MAX_SEGMENTS, n_pairs);
+    if (pred_dtype != RSSM_DTYPE_F32 && pred_dtype != RSSM_DTYPE_BF16 && pred_dtype != RSSM_DTYPE_F16) return fail("bad pred_dtype %d", pred_dtype);
+    a->nseg = n_pairs, a->pred_dtype = pred_dtype;
+    for (int i = 0; i < n_pairs; ++i) {
+        const RssmNllPair& p = pairs[i];
+        REQUIRE(p.prediction); REQUIRE(p.target);
+        if (p.n_elems < 1 || p.n_batch < 1 || p.n_elems % p.n_batch) return fail("pair %d: n_elems=%zu must be a positive multiple of n_batch=%zu", i, p.n_elems, p.n_batch);
+        if (!(p.scale > 0.f)) return fail("pair %d: scale must be positive (got %g)", i, (double)p.scale);
+        if (!aligned16(p.prediction) || !aligned16(p.target)) return fail("pair %d: prediction / target must be 16-byte aligned", i);
+        rssm::NllSeg& s = a->seg[i];
+        s.prediction = p.prediction, s.target = p.target, s.n = p.n_elems;
+        s.sq_coeff = 0.5 / ((double)p.scale * (double)p.scale * (double)p.n_batch);
+        s.constant = (double)(p.n_elems / p.n_batch) * (log((double)p.scale) + 0.9189385332046727418 /* 0.5 log(2 pi) */);
+        if (backward) {
+            REQUIRE(p.d_prediction);
+            if (!aligned16(p.d_prediction) || !aligned16(p.d_target)) return fail("pair %d: gradient outputs must be 16-byte aligned", i);
+            s.d_loss = p.d_loss, s.d_prediction = p.d_prediction, s.d_target = p.d_target;
+        } else {
+            REQUIRE(p.loss);
+            s.loss = p.loss;
+        }
+    }
+    return 0;
+}
+
+int rssm_gaussian_nll_fwd(const RssmNllPair* pairs, int n_pairs, int pred_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+    rssm::NllArgs a{};
+    if (nll_args(pairs, n_pairs, pred_dtype, false, &a)) return 1;
+    REQUIRE(workspace);
+    if (workspace_bytes < rssm_gaussian_nll_workspace_bytes() || !aligned16(workspace))
+        return fail("workspace: need %zu zero-filled, 16-byte aligned bytes (got %zu)", rssm_gaussian_nll_workspace_bytes(), workspace_bytes);
+    a.tickets = static_cast<unsigned*>(workspace);
+    a.partials = reinterpret_cast<double*>(static_cast<char*>(workspace) + 64);
+    g_launches.fetch_add(1);
+    return check_cuda(rssm::launch_gaussian_nll(a, false, static_cast<cudaStream_t>(stream)), "gaussian nll forward launch");
+}
+
+int rssm_gaussian_nll_bwd(const RssmNllPair* pairs, int n_pairs, int pred_dtype, void* stream) {
+    rssm::NllArgs a{};
+    if (nll_args(pairs, n_pairs, pred_dtype, true, &a)) return 1;
+    g_launches.fetch_add(1);
+    return check_cuda(rssm::launch_gaussian_nll(a, true, static_cast<cudaStream_t>(stream)), "gaussian nll backward launch");
 }
 
 }  // extern "C"

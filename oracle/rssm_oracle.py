@@ -403,3 +403,14 @@ def mtrssm_rollout_literal(params: Params, *, actions, embed_a, embed_v, deter_h
         pl.append(prior_l), ph.append(prior_h), ql.append(post_l), qh.append(post_h)
     st = lambda xs: torch.stack(xs, 1)  # noqa: E731
     return {"post_feature": st(feats), "prior_probs_l": st(pl), "prior_probs_h": st(ph), "post_probs_l": st(ql), "post_probs_h": st(qh)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reconstruction likelihood
+# ---------------------------------------------------------------------------------------------------------------------
+def likelihood(prediction: Tensor, target: Tensor, event_ndims: int, scale: float = 1.0) -> Tensor:
+    """objective.py:21-23, literally: -Independent(Normal(prediction, scale), event_ndims).log_prob(target).mean()
+    (torch.distributions is the arithmetic the reference itself calls, so this row of the oracle is pinned by torch)."""
+    import torch.distributions as td
+
+    return -td.Independent(td.Normal(prediction, scale), event_ndims).log_prob(target).mean()

@@ -211,6 +211,39 @@ def test_library_exports_every_declared_symbol():
     import ctypes as C
 
     assert C.sizeof(_lib.MrssmWeights) == 20 * 8 and C.sizeof(_lib.MtrssmWeights) == 28 * 8
+    assert C.sizeof(_lib.NllPair) == 9 * 8  # 2 pointers, 2 size_t, float (+pad), 4 pointers
+    assert handle.rssm_gaussian_nll_workspace_bytes() >= 64 + 8 * 148 * 4
+
+
+def test_gaussian_nll_abi_rejects_bad_arguments_without_a_gpu():
+    """Argument checks of the likelihood entry points run on the host before any launch (include/rssm_rollout.h)."""
+    import ctypes as C
+
+    from multimodal_mtrssm_b200 import _lib
+
+    handle = _lib.lib()
+    pair = (_lib.NllPair * 1)()
+    pair[0].prediction, pair[0].target, pair[0].n_elems, pair[0].n_batch, pair[0].scale, pair[0].loss = 256, 512, 10, 3, 1.0, 1024
+    assert handle.rssm_gaussian_nll_fwd(pair, 1, 0, C.c_void_p(4096), 1 << 20, None) != 0
+    assert b"multiple of n_batch" in handle.rssm_last_error()
+    pair[0].n_batch = 5
+    assert handle.rssm_gaussian_nll_fwd(pair, 1, 7, C.c_void_p(4096), 1 << 20, None) != 0 and b"pred_dtype" in handle.rssm_last_error()
+    assert handle.rssm_gaussian_nll_fwd(pair, 1, 0, C.c_void_p(4096), 8, None) != 0 and b"workspace" in handle.rssm_last_error()
+    assert handle.rssm_gaussian_nll_fwd(pair, 9, 0, C.c_void_p(4096), 1 << 20, None) != 0 and b"n_pairs" in handle.rssm_last_error()
+    pair[0].prediction = 260
+    assert handle.rssm_gaussian_nll_fwd(pair, 1, 0, C.c_void_p(4096), 1 << 20, None) != 0 and b"aligned" in handle.rssm_last_error()
+    pair[0].prediction, pair[0].d_prediction = 256, None
+    assert handle.rssm_gaussian_nll_bwd(pair, 1, 0, None) != 0 and b"d_prediction" in handle.rssm_last_error()
+
+
+def test_oracle_likelihood_is_the_closed_form_the_kernel_computes():
+    from multimodal_mtrssm_b200.objective import likelihood
+    from oracle import rssm_oracle as O
+
+    g = torch.Generator().manual_seed(0)
+    pred, tgt = torch.randn(3, 4, 1, 8, 8, generator=g), torch.randn(3, 4, 1, 8, 8, generator=g)
+    for scale in (1.0, 0.3):
+        torch.testing.assert_close(likelihood(pred, tgt, 3, scale), O.likelihood(pred, tgt, 3, scale), rtol=1e-6, atol=0)
 
 
 def test_wide_family_abi_size_queries_and_struct_layout():
