@@ -237,27 +237,38 @@ def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int
     host_out = torch.empty(n_w + 1).pin_memory()
     h2d = sum(v.numel() * 4 for v in host.values())
 
-    def step() -> None:
-        dev = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+    from multimodal_mtrssm_b200 import dp
+
+    pre = dp.PinnedPrefetcher(host, device)  # step i+1's H2D copy runs on a side stream under step i's kernels
+
+    def step(more: bool) -> None:
+        slot, dev = pre.next()
+        if more:
+            pre.submit(host)
+        dev = dict(dev)
         dev.update({k: torch.rand(s, device=device) for k, s in noise_shapes.items()})
         out = R.mtrssm_rollout(weights, precision=precision, **dev)
         loss = (out["feature"] @ readout).sum() + out["kl_l"].mean() + out["kl_h"].mean()
         grads = torch.autograd.grad(loss, weights)
+        pre.release(slot)
         flat = torch.cat([loss.detach().reshape(1), *[g_.reshape(-1) for g_ in grads]])
         if world > 1:
             dist.all_reduce(flat)
         host_out.copy_(flat, non_blocking=True)
 
-    for _ in range(max(1, warmup // 2)):
-        step()
+    def run(k: int) -> None:  # k steps, k H2D copies of the inputs (the first one is exposed), k D2H read-backs
+        pre.submit(host)
+        for i in range(k):
+            step(i + 1 < k)
+
+    run(max(1, warmup // 2))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = max(3, steps // 2)
     start.record()
-    for _ in range(n):
-        step()
+    run(n)
     end.record()
     torch.cuda.synchronize()
     ms = start.elapsed_time(end)
@@ -267,8 +278,8 @@ def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int
         ms = float(t)
     return {"value": world * B * T * n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (n_w + 1) * 4,
             "ms_per_step": ms / n, "steps": n,
-            "note": "inputs (actions, both embeddings, initial state) from pinned host memory; noise drawn on the device; "
-                    "PCIe-bound"}
+            "note": "inputs (actions, both embeddings, initial state) copied from pinned host memory EVERY step (double-buffered: "
+                    "step i+1's copy overlaps step i's kernels); noise drawn on the device; PCIe-bound"}
 
 
 def time_mrssm(B: int, T: int, precision: int, device: torch.device, iters: int = 10) -> dict:
@@ -302,7 +313,7 @@ def time_mrssm(B: int, T: int, precision: int, device: torch.device, iters: int 
             "value": B * T / (ms * 1e-3), "via": "public op API (incl. torch allocations and the loss)"}
 
 
-def time_train_step(B: int, T: int, world: int, device: torch.device, autocast: bool, iters: int = 10) -> dict:
+def time_train_step(B: int, T: int, world: int, device: torch.device, autocast: bool, iters: int = 10, graphed: bool = False) -> dict:
     """BASELINE.json's second metric, train sequences/s: one full training step of MoPoE-MMTRSSM built from the reference's
     default.yaml through this package's drop-in classes -- CNN encoders (stand-ins for the absent `cnn` package), initial
     state, fused rollout, decoders, Gaussian likelihood + KL, backward, flat-bucket gradient allreduce (N > 1), clip, AdamW.
@@ -312,16 +323,23 @@ def time_train_step(B: int, T: int, world: int, device: torch.device, autocast: 
     model = compat.load_model(ROOT / "multimodal_mtrssm_b200" / "configs" / "mopoe_mmtrssm_default.yaml")
     standins.materialize(model, model.feature_dim)
     model.to(device).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=graphed)
     bucket = dp.FlatGradBucket(model.parameters())
     g = torch.Generator().manual_seed(1234)
     frames = lambda: (torch.rand(B, T, 1, 32, 32, generator=g) * 2 - 1).to(device)  # noqa: E731
     act = synthetic.actions(B, T, g).to(device)
     batch = (act, frames(), frames(), act.clone(), frames(), frames())
 
-    def step() -> None:
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-            dp.train_step(model, batch, opt, bucket)
+    if graphed:  # the whole step (enc, rollout, dec, likelihood, backward, allreduce, clip, AdamW) as ONE CUDA graph replay
+        gstep = dp.GraphedTrainStep(model, batch, opt, bucket, autocast_dtype=torch.bfloat16 if autocast else None)
+        fresh = tuple(t.clone() for t in batch)  # a new batch every step: the copy into the graph's inputs is part of the step
+
+        def step() -> None:
+            gstep(fresh)
+    else:
+        def step() -> None:
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                dp.train_step(model, batch, opt, bucket)
 
     for _ in range(3):
         step()
@@ -339,7 +357,8 @@ def time_train_step(B: int, T: int, world: int, device: torch.device, autocast: 
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
-    return {"B_per_gpu": B, "T": T, "autocast_bf16": autocast, "ms_per_step": ms, "train_seq_per_sec": world * B / (ms * 1e-3)}
+    return {"B_per_gpu": B, "T": T, "autocast_bf16": autocast, "cuda_graph": graphed, "ms_per_step": ms,
+            "train_seq_per_sec": world * B / (ms * 1e-3)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -564,7 +583,8 @@ def main() -> None:
 
     extras = {}
     if not args.no_extras:  # every rank takes part (gradient allreduce inside)
-        train = [time_train_step(b_, T, world, device, ac) for b_, ac in ((8, True), (256, True), (256, False))]
+        train = [time_train_step(b_, T, world, device, ac, graphed=gr)
+                 for b_, ac, gr in ((8, True, False), (8, True, True), (256, True, False), (256, True, True), (256, False, False))]
         if rank == 0:
             extras["train_step"] = {"metric": "train sequences/s (full MoPoE-MMTRSSM training step, default.yaml model)",
                                     "runs": train}
