@@ -43,7 +43,15 @@ class Distribution:
 
     # A4
     def independent(self, dim: int) -> td.Independent:
-        ind = td.Independent(td.OneHotCategoricalStraightThrough(probs=self.probs, validate_args=False), dim, validate_args=False)
+        # OneHotCategorical builds its inner Categorical WITHOUT forwarding validate_args, and that validation reads a device
+        # flag on the host (`torch._is_all_true`): a sync per call and illegal under CUDA-graph capture -> switch the default off
+        # around the construction (the probabilities come from the kernels' / factory's softmax)
+        default = td.Distribution._validate_args  # noqa: SLF001
+        td.Distribution.set_default_validate_args(False)
+        try:
+            ind = td.Independent(td.OneHotCategoricalStraightThrough(probs=self.probs, validate_args=False), dim, validate_args=False)
+        finally:
+            td.Distribution.set_default_validate_args(default)
         ind._rssm_fused, ind._rssm_role = self._fused, self._role  # type: ignore[attr-defined]
         return ind
 

@@ -194,3 +194,71 @@ def test_wide_mrssm_model_trains_under_autocast_and_fails_loudly_in_fp32():
     assert losses[-1] < losses[0] and all(map(lambda v: v == v, losses)), losses
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for n, p in model.named_parameters()
                if not n.startswith("representation."))
+
+
+def test_cuda_graph_training_step_tracks_the_eager_step():
+    """dp.GraphedTrainStep: the whole training step (encoders, initial state, fused rollout, decoders, fused likelihood, backward,
+    clip, AdamW) replayed as ONE CUDA graph.  With the noise-free parts equal, graph and eager runs from the same initial weights
+    on the same batch follow the same loss curve (they draw different categorical noise: Philox offsets differ under capture), the
+    graph's inputs are really inputs (a different batch changes the loss), and wrong shapes / non-capturable optimisers raise."""
+    import copy
+
+    from multimodal_mtrssm_b200 import dp
+
+    torch.manual_seed(0)
+    eager = H.build_mtrssm_model().cuda()
+    graphed = copy.deepcopy(eager)
+    B, T = 16, 10
+    g = torch.Generator().manual_seed(1)
+    obs = torch.rand(B, T, 1, 32, 32, generator=g).cuda() * 2 - 1
+    act = torch.randn(B, T, 6, generator=g).cuda()
+    batch = (act, obs, obs.flip(-1), act.clone(), obs, obs.flip(-1))
+    opt_e = torch.optim.AdamW(eager.parameters(), lr=1e-3)
+    opt_g = torch.optim.AdamW(graphed.parameters(), lr=1e-3, capturable=True)
+    with pytest.raises(RuntimeError, match="capturable"):
+        dp.GraphedTrainStep(graphed, batch, torch.optim.AdamW(graphed.parameters(), lr=1e-3), dp.FlatGradBucket(graphed.parameters()))
+    w0 = copy.deepcopy(graphed.state_dict())
+    step = dp.GraphedTrainStep(graphed, batch, opt_g, dp.FlatGradBucket(graphed.parameters()), warmup=2)
+    # the warm-up and the capture trained `graphed` for 2 steps (capture itself executes nothing): restart both from w0
+    graphed.load_state_dict(w0)
+    eager.load_state_dict(w0)
+    bucket_e = dp.FlatGradBucket(eager.parameters())
+    le, lg = [], []
+    for _ in range(30):
+        le.append(float(dp.train_step(eager, batch, opt_e, bucket_e)["loss"]))
+        lg.append(float(step(batch)["loss"]))
+    assert all(v == v for v in lg) and lg[-1] < lg[0] - 1.0, lg
+    assert abs(lg[0] - le[0]) < 0.02 * abs(le[0]), (lg[0], le[0])       # same weights, same batch; only the draws differ
+    assert abs(lg[-1] - le[-1]) < 0.05 * abs(le[0] - le[-1]) + 0.02 * abs(le[-1]), (lg[-1], le[-1])
+    other = tuple(t.clone() for t in batch)
+    other[1].mul_(-1.0)
+    other[4].mul_(-1.0)
+    assert abs(float(step(other)["train/recon/audio"]) - float(step(batch)["train/recon/audio"])) > 1e-3
+    with pytest.raises(ValueError, match="shape"):
+        step(tuple(t[:, :5] for t in batch))
+
+
+def test_pinned_prefetcher_delivers_every_batch_in_order():
+    from multimodal_mtrssm_b200 import dp
+
+    dev = torch.device("cuda", 0)
+    hosts = [{"x": torch.full((1 << 20,), float(i)).pin_memory(), "y": torch.arange(8, dtype=torch.float32).add_(i).pin_memory()} for i in range(5)]
+    pre = dp.PinnedPrefetcher(hosts[0], dev)
+    pre.submit(hosts[0])
+    sums = []
+    for i in range(5):
+        slot, d = pre.next()
+        if i + 1 < 5:
+            pre.submit(hosts[i + 1])
+        sums.append((d["x"].mean() + d["y"][0]).reshape(1))     # consumer work on the compute stream
+        pre.release(slot)
+    assert torch.cat(sums).cpu().tolist() == [2.0 * i for i in range(5)]
+    with pytest.raises(RuntimeError, match="nothing submitted"):
+        pre.next()
+    with pytest.raises(RuntimeError, match="not pinned"):
+        pre.submit({"x": torch.zeros(1 << 20), "y": torch.zeros(8)})
+    pre2 = dp.PinnedPrefetcher(hosts[0], dev)
+    pre2.submit(hosts[0])
+    pre2.submit(hosts[1])
+    with pytest.raises(RuntimeError, match="in flight"):
+        pre2.submit(hosts[2])
