@@ -8,6 +8,8 @@ from torch.profiler import profile, ProfilerActivity
 from multimodal_mtrssm_b200 import compat, dp, standins, synthetic
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+if len(sys.argv) > 2 and sys.argv[2] == "bench":
+    torch.backends.cudnn.benchmark = True
 T = 30
 device = torch.device("cuda", 0)
 model = compat.load_model(ROOT / "multimodal_mtrssm_b200" / "configs" / "mopoe_mmtrssm_default.yaml")
@@ -27,4 +29,10 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3): step()
     torch.cuda.synchronize()
+torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record()
+for _ in range(10): step()
+ev1.record(); torch.cuda.synchronize()
+print("ms_per_step", ev0.elapsed_time(ev1) / 10)
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
