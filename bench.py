@@ -214,7 +214,7 @@ def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
             "wgrad_ms": statistics.mean(seg[2])}
 
 
-def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int, device: torch.device) -> dict:
+def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int, device: torch.device, host_bf16: bool = False) -> dict:
     """Same metric through the public API with HOST buffers, as a training step sees it: the step's encoder outputs,
     actions and initial state are copied from pinned host memory (H2D), the noise is drawn on the device (as
     MoPoE_MMTRSSM.rollout_representation does), the rollout + autograd run through `rollout_ops.mtrssm_rollout`, the
@@ -229,13 +229,16 @@ def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int
     params = {k: v.to(device).requires_grad_(True) for k, v in synthetic.mtrssm_params().items()}
     weights = mtrssm_weight_list(params)
     batch = synthetic.mtrssm_batch(B, T)
-    host = {k: v.pin_memory() for k, v in batch.items() if not k.startswith("u_")}
+    # host_bf16 (side measurement only): the two embedding tensors wait on the host in bf16 -- what an autocast encoder emits and
+    # what the bf16 policy's contractions consume anyway (the op widens them on the device) -- halving the PCIe bytes
+    half = lambda k, v: v.bfloat16() if host_bf16 and k.startswith("embed_") else v  # noqa: E731
+    host = {k: half(k, v).pin_memory() for k, v in batch.items() if not k.startswith("u_")}
     noise_shapes = {k: tuple(v.shape) for k, v in batch.items() if k.startswith("u_")}
     g = torch.Generator().manual_seed(7)
     readout = torch.randn(96, generator=g).to(device)  # device-resident "decoder": loss = <feature, readout> + KL terms
     n_w = sum(w.numel() for w in weights)
     host_out = torch.empty(n_w + 1).pin_memory()
-    h2d = sum(v.numel() * 4 for v in host.values())
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
 
     from multimodal_mtrssm_b200 import dp
 
@@ -277,7 +280,7 @@ def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
     return {"value": world * B * T * n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": (n_w + 1) * 4,
-            "ms_per_step": ms / n, "steps": n,
+            "ms_per_step": ms / n, "steps": n, "gbs_per_rank": h2d * n / (ms * 1e-3) / 1e9,
             "note": "inputs (actions, both embeddings, initial state) copied from pinned host memory EVERY step (double-buffered: "
                     "step i+1's copy overlaps step i's kernels); noise drawn on the device; PCIe-bound"}
 
@@ -561,6 +564,9 @@ def main() -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    from multimodal_mtrssm_b200 import dp as _dp
+
+    numa_bound = os.environ.get("RSSM_NO_NUMA_BIND") is None and _dp.bind_to_gpu_numa_node(local)  # before any pinned allocation: the e2e leg copies 633 MB per step and rank
     if world > 1:
         import torch.distributed as dist
 
@@ -622,6 +628,7 @@ def main() -> None:
             extras["cfg3_wide_mrssm"]["reference_eager_on_this_gpu"] = reference_eager_gpu_cfg3(device)
             r = extras["cfg3_wide_mrssm"]
             r["speedup_vs_reference_eager_gpu"] = r["reference_eager_on_this_gpu"]["ms_per_step"] / r["ms_per_step"]
+        extras["e2e_bf16_host_embeddings"] = time_e2e(B, T, precision, 10, 4, 1, device, host_bf16=True)
         pk = ROOT / "MEASURED_PEAKS.json"
         extras["likelihood_f3"] = time_likelihood(device, json.loads(pk.read_text())["hbm_gbs"] if pk.exists() else 6650.0)
     if world > 1:
@@ -676,7 +683,7 @@ def main() -> None:
         "roofline_step": {"algorithmic_bytes": STEP_BYTES_PER_BT * B * T, "achieved_gbs": STEP_BYTES_PER_BT * B * T / (ms_step * 1e-3) / 1e9,
                           "frac_of_hbm": STEP_BYTES_PER_BT * B * T / (ms_step * 1e-3) / 1e9 / peak,
                           "tensor_tflops": 3 * FWD_FLOPS_PER_BT * B * T / (ms_step * 1e-3) / 1e12},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, **extras,
+        "e2e": e2e | {"host_numa_bound": numa_bound}, "gpu_launches": int(launches), "clocks": clocks, **extras,
     }
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_oracle_rate(args.cpu_batch, T, literal=False, budget_s=12.0)

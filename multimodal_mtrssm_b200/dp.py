@@ -15,6 +15,32 @@ import torch.distributed as dist
 from torch import Tensor, nn
 
 
+def bind_to_gpu_numa_node(device_index: int) -> bool:
+    """Pins the calling process to the CPU cores NVML reports as local to GPU `device_index` (one process per GPU), so that
+    pinned host buffers allocated afterwards are first-touched on that GPU's NUMA node and the per-step H2D copies of all ranks
+    do not funnel through one socket's memory controllers / inter-socket link.  Returns False (and changes nothing) when NVML or
+    the affinity call is unavailable; the data path never depends on it."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = device_index
+        if visible:  # NVML enumerates physical devices
+            entry = visible.split(",")[device_index].strip()
+            if entry.isdigit():
+                index = int(entry)
+            else:
+                pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByUUID(entry.encode()))
+                return True
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:  # noqa: BLE001  (no NVML, no permission, restricted cpuset: keep the default placement)
+        return False
+    return True
+
+
 def shard_batch(batch: Sequence[Tensor], rank: int, world: int) -> tuple[Tensor, ...]:
     """Equal contiguous shards along dim 0 (B must divide by world: loss means then average exactly)."""
     B = batch[0].shape[0]
