@@ -491,6 +491,38 @@ def reference_eager_gpu_cfg3(device: torch.device, B: int = 1024, T: int = 64, D
     return {"ms_per_step": ms, "value": B * T / (ms * 1e-3), "unit": UNIT, "what": "fp32 PyTorch oracle, eager on this GPU (cuBLAS fp32 / TF32 off)"}
 
 
+def reference_eager_gpu_cfg2(device: torch.device, B: int, T: int) -> dict:
+    """The same comparison for the headline workload (cfg2 sizes): the fp32 oracle (= the reference's MoPoE-MMTRSSM rollout with
+    explicit noise: the Python T loop of ~100 small launches per step and direction) EAGER on this GPU, fwd + autograd bwd, on the
+    SAME batch, CUDA events.  This is what a reference user gets from a B200 today.  Baseline leg: touches oracle/."""
+    from multimodal_mtrssm_b200 import synthetic
+    from oracle import rssm_oracle as O
+
+    dims = dict(CL=4, KL=4, CH=8, KH=2, l_tau=2.0, h_tau=4.0)
+    params = {k: v.to(device).requires_grad_(True) for k, v in synthetic.mtrssm_params().items()}
+    inp = {k: v.to(device) for k, v in synthetic.mtrssm_batch(B, T).items()}
+    up = torch.randn(B, T, 96, generator=torch.Generator().manual_seed(7)).to(device)
+
+    def step() -> None:
+        res = O.mtrssm_rollout(params, dims=dims, u_prior_l=None, u_prior_h=None, **inp)
+        kl_l = O.kl_per_sample(res["post_probs_l"], res["prior_probs_l"], True).mean()
+        kl_h = O.kl_per_sample(res["post_probs_h"], res["prior_probs_h"], True).mean()
+        loss = (res["post_feature"] * up).sum() + kl_l + kl_h
+        torch.autograd.grad(loss, list(params.values()), allow_unused=True)
+
+    step()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(3):
+        step()
+    end.record()
+    torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / 3
+    return {"B": B, "T": T, "ms_per_step": ms, "value": B * T / (ms * 1e-3), "unit": UNIT,
+            "what": "fp32 PyTorch oracle of the same workload, eager on this GPU"}
+
+
 # CPU legs (the ONLY place bench.py touches oracle/)
 # ---------------------------------------------------------------------------------------------------
 def cpu_oracle_rate(B: int, T: int, literal: bool, budget_s: float) -> dict:
@@ -628,6 +660,8 @@ def main() -> None:
             extras["cfg3_wide_mrssm"]["reference_eager_on_this_gpu"] = reference_eager_gpu_cfg3(device)
             r = extras["cfg3_wide_mrssm"]
             r["speedup_vs_reference_eager_gpu"] = r["reference_eager_on_this_gpu"]["ms_per_step"] / r["ms_per_step"]
+        extras["reference_eager_on_this_gpu"] = reference_eager_gpu_cfg2(device, B, T)
+        extras["reference_eager_on_this_gpu"]["speedup_of_value"] = (B * T / (res["total_ms"] / args.steps * 1e-3)) / extras["reference_eager_on_this_gpu"]["value"]
         extras["e2e_bf16_host_embeddings"] = time_e2e(B, T, precision, 10, 4, 1, device, host_bf16=True)
         pk = ROOT / "MEASURED_PEAKS.json"
         extras["likelihood_f3"] = time_likelihood(device, json.loads(pk.read_text())["hbm_gbs"] if pk.exists() else 6650.0)

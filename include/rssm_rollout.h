@@ -8,6 +8,8 @@
  *                            (after the encoders, :215-216; includes Transition.forward networks.py:151-173,
  *                             the posterior heads :62-84, the MoPoE fusion :112-163,241-251, the samples
  *                             state.py:17 and the per-(b,t) KL terms of core.py:212-216)
+ *                            with dims.unimodal = 1: BaseRSSM.rollout_representation  core.py:137-168 (single
+ *                             Representation.forward networks.py:70-84, no fusion)
  *   rssm_mrssm_rollout_bwd   autograd (BPTT) of the above; rssm_mrssm_wgrad = its weight-gradient half
  *   rssm_mrssm_imagine_fwd   BaseRSSM.rollout_transition           core.py:170-185
  *   rssm_mtrssm_rollout_fwd  MoPoE_MMTRSSM.rollout_representation  mmtrssm/mopoe_mmtrssm/core.py:364-494
@@ -45,7 +47,7 @@
 extern "C" {
 #endif
 
-#define RSSM_ABI_VERSION 3
+#define RSSM_ABI_VERSION 4
 #define RSSM_PRECISION_FP32 0
 #define RSSM_PRECISION_BF16 1
 /* bf16 tensor-core path whose backward is ONE kernel: BPTT + weight-gradient contractions on tcgen05 with TMEM accumulators
@@ -67,6 +69,10 @@ typedef struct {
     int A, E, D, H; /* action, obs-embed, deterministic, MLP hidden sizes */
     int C, K;       /* category_size (groups) x class_size (classes per group) */
     int precision;  /* RSSM_PRECISION_* */
+    int unimodal;   /* 0 = MoPoE_MRSSM.rollout_representation.  1 = BaseRSSM.rollout_representation (core.py:137-168): the posterior
+                       is Representation.forward (networks.py:70-84) of ONE head -- the au_* weights on embed_a -- with no fusion;
+                       embed_v / vi_* are not used by the result (pass any valid buffers, e.g. the audio ones; their gradients
+                       come back zero).  Default-size family only. */
 } RssmMrssmDims;
 
 /* state_dict names in comments */

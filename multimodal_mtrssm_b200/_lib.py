@@ -17,7 +17,7 @@ from .build import LIB, build_library
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 PRECISION_BF16_FUSED = 2  # bf16 path with the one-kernel backward (tcgen05 weight gradients); MMTRSSM only
-ABI_VERSION = 3
+ABI_VERSION = 4
 MRSSM_SAVED_FLOATS, MRSSM_DPRE_FLOATS = 320, 336
 MTRSSM_SAVED_FLOATS, MTRSSM_DPRE_FLOATS = 208, 304
 MTRSSM_SAVED_BF16 = MTRSSM_SAVED_FLOATS
@@ -41,7 +41,7 @@ _MT_W = (
 MR_WEIGHT_FIELDS = tuple(_MR_W.split())
 MT_WEIGHT_FIELDS = tuple(_MT_W.split())
 
-MrssmDims = _struct("RssmMrssmDims", [(n, C.c_int) for n in "B T A E D H C K precision".split()])
+MrssmDims = _struct("RssmMrssmDims", [(n, C.c_int) for n in "B T A E D H C K precision unimodal".split()])
 MrssmWeights = _struct("RssmMrssmWeights", _ptrs(_MR_W))
 MrssmWeightGrads = _struct("RssmMrssmWeightGrads", _ptrs(_MR_W))
 MrssmInputs = _struct("RssmMrssmInputs", _ptrs("actions embed_a embed_v h0 z0 u_post u_prior"))

@@ -94,8 +94,13 @@ class BaseRSSM(_Base):
         return State(deter=deter, distribution=self.representation.distribution_factory(logits)).to(self.device)
 
     def rollout_representation(self, *, actions: Tensor, observations, prev_state: State) -> tuple[State, State]:  # noqa: ANN001
-        """core.py:137-168: the unimodal per-step loop (kept for API parity; both shipped models override it)."""
+        """core.py:137-168, the unimodal rollout (both shipped models override it).  On CUDA, at the sizes the kernels are built
+        for, the T loop is ONE fused kernel (`rollout_ops.mrssm_rollout(..., unimodal=True)`: Transition.forward + ONE
+        Representation.forward per step, no fusion); otherwise (CPU tensors, as the reference also allows) the reference's own
+        per-step structure runs."""
         obs_embed = self.encode_observation(observations)
+        if obs_embed.is_cuda and self._fused_unimodal_ok(obs_embed, prev_state):
+            return self._rollout_representation_fused(actions, obs_embed, prev_state)
         priors, posteriors = [], []
         for t in range(obs_embed.shape[1]):
             prior = self.transition(actions[:, t], prev_state)
@@ -104,6 +109,47 @@ class BaseRSSM(_Base):
             posteriors.append(posterior)
             prev_state = posterior
         return stack_states(posteriors, dim=1), stack_states(priors, dim=1)
+
+    def _fused_unimodal_ok(self, obs_embed: Tensor, prev_state: State) -> bool:
+        from .mopoe_mrssm import mlp_params
+
+        f = self.representation.distribution_factory
+        if not (prev_state.deter.shape[-1] == 32 and obs_embed.shape[-1] == 64 and int(f.class_size) * int(f.category_size) == 16
+                and all(hasattr(self.transition, n) for n in ("action_state_projector", "rnn_cell", "rnn_to_prior_projector"))):
+            return False
+        try:  # Linear-ELU-Linear heads only (the kernels' epilogues)
+            for m in (self.transition.action_state_projector, self.transition.rnn_to_prior_projector, self.representation.rnn_to_post_projector):
+                mlp_params(m, "head")
+        except (RuntimeError, TypeError, ValueError):
+            return False
+        return True
+
+    def _rollout_representation_fused(self, actions: Tensor, obs_embed: Tensor, prev_state: State) -> tuple[State, State]:
+        from . import rollout_ops
+        from .distribution import Distribution, FusedKL
+        from .mopoe_mrssm import flat_stoch, mlp_params
+
+        tr, head = self.transition, mlp_params(self.representation.rnn_to_post_projector, "representation.rnn_to_post_projector")
+        weights = [
+            *mlp_params(tr.action_state_projector, "transition.action_state_projector"),
+            tr.rnn_cell.weight_ih, tr.rnn_cell.weight_hh, tr.rnn_cell.bias_ih, tr.rnn_cell.bias_hh,
+            *mlp_params(tr.rnn_to_prior_projector, "transition.rnn_to_prior_projector"), *head, *head,  # second copy: unused slot
+        ]
+        f = self.representation.distribution_factory
+        B, T = obs_embed.shape[:2]
+        C, dev = int(f.category_size), obs_embed.device
+        out = rollout_ops.mrssm_rollout(
+            weights, actions=actions, embed_a=obs_embed, embed_v=obs_embed, h0=prev_state.deter, z0=flat_stoch(prev_state.stoch),
+            u_post=torch.rand(B, T, C, device=dev), u_prior=torch.rand(B, T, C, device=dev), class_size=int(f.class_size),
+            precision=self._precision(), use_kl_balancing=bool(self.use_kl_balancing), unimodal=True,
+        )
+        feature = out["feature"]
+        D = prev_state.deter.shape[-1]
+        link = FusedKL(kl=out["kl"], use_balancing=bool(self.use_kl_balancing), token=object())
+        posterior = State(deter=feature[..., :D], stoch=feature[..., D:], feature=feature,
+                          distribution=Distribution(out["post_probs"], _fused=link, _role="post"))
+        prior = State(deter=feature[..., :D], stoch=out["prior_stoch"], distribution=Distribution(out["prior_probs"], _fused=link, _role="prior"))
+        return posterior, prior
 
     def rollout_transition(self, *, actions: Tensor, prev_state: State) -> State:
         """core.py:170-185: imagination, the prior's own sample is fed back."""

@@ -10,6 +10,7 @@ namespace rssm {
 // ---- MoPoE-MRSSM ----------------------------------------------------------------------------------
 struct MrssmFwdArgs {
     int B, T, A, K;
+    int unimodal;  // posterior = the audio head alone, no fusion (BaseRSSM.rollout_representation)
     RssmMrssmWeights w;
     const float *actions, *embed_a, *embed_v, *h0, *z0, *u_post, *u_prior;
     float *feature, *prior_probs, *post_probs, *prior_stoch, *kl;
@@ -18,6 +19,7 @@ struct MrssmFwdArgs {
 
 struct MrssmBwdArgs {
     int B, T, A, K;
+    int unimodal;
     float kl_wq, kl_wp;
     RssmMrssmWeights w;
     const float *h0, *feature, *prior_probs, *post_probs;

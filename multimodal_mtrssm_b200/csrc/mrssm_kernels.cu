@@ -269,9 +269,16 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
         // ---- MoPoE fusion, factory, sample, KL (mopoe_mrssm/core.py:241-251,135-163) --------------
         {
             float lsa[2][4], lsv[2][4], mixed[2][4], q[2][4], zs[2][4];
-            log_softmax_flat<NS == 1>(la, lsa);
-            log_softmax_flat<NS == 1>(lv, lsv);
-            mopoe_mix<NS == 1>(lsa, lsv, mixed, nullptr, nullptr);
+            if (p.unimodal) {  // Representation.forward: factory(logits of the one head), networks.py:83
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mixed[nt][j] = la[nt][j];
+            } else {
+                log_softmax_flat<NS == 1>(la, lsa);
+                log_softmax_flat<NS == 1>(lv, lsv);
+                mopoe_mix<NS == 1>(lsa, lsv, mixed, nullptr, nullptr);
+            }
             softmax_groups<K, NS == 1>(mixed, q);
             store_c<2>(q, p.post_probs + iA * 16, p.post_probs + iB * 16, r);
             if (STAGED) sample_onehot<K>(q, stage + stg::U0 + r.g * 8, stage + stg::U0 + (r.g + 8) * 8, zs, lane);
@@ -393,18 +400,25 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
             float la[2][4], lv[2][4], lsa[2][4], lsv[2][4], mixed[2][4], ra[2][4], rv[2][4];
             load_rec<2>(la, svA + mrs::LA, svB + mrs::LA, r.t);
             load_rec<2>(lv, svA + mrs::LV, svB + mrs::LV, r.t);
-            log_softmax_flat<NS == 1>(la, lsa);
-            log_softmax_flat<NS == 1>(lv, lsv);
-            mopoe_mix<NS == 1>(lsa, lsv, mixed, ra, rv);
+            if (p.unimodal) {  // posterior logits ARE the one head's logits: the vision head gets no gradient
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
+                for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    ra[nt][j] *= dm[nt][j];
-                    rv[nt][j] *= dm[nt][j];
-                }
-            log_softmax_flat_bwd<NS == 1>(lsa, ra, dla);
-            log_softmax_flat_bwd<NS == 1>(lsv, rv, dlv);
+                    for (int j = 0; j < 4; ++j) dla[nt][j] = dm[nt][j], dlv[nt][j] = 0.f;
+            } else {
+                log_softmax_flat<NS == 1>(la, lsa);
+                log_softmax_flat<NS == 1>(lv, lsv);
+                mopoe_mix<NS == 1>(lsa, lsv, mixed, ra, rv);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        ra[nt][j] *= dm[nt][j];
+                        rv[nt][j] *= dm[nt][j];
+                    }
+                log_softmax_flat_bwd<NS == 1>(lsa, ra, dla);
+                log_softmax_flat_bwd<NS == 1>(lsv, rv, dlv);
+            }
         }
         store_rec<2>(dla, dpA + mrd::LA, dpB + mrd::LA, r);
         store_rec<2>(dlv, dpA + mrd::LV, dpB + mrd::LV, r);

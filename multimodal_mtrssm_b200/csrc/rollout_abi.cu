@@ -115,6 +115,7 @@ int check_mrssm_wide(const RssmMrssmDims* d) {
     if (d->A < 1 || d->A > 8) return fail("unsupported action_size %d: need 1..8", d->A);
     if (d->precision != RSSM_PRECISION_BF16)
         return fail("the wide family (deter=%d) is built for RSSM_PRECISION_BF16 only (got precision %d)", d->D, d->precision);
+    if (d->unimodal) return fail("the unimodal rollout (BaseRSSM.rollout_representation) is built for the default sizes only (deter=%d)", d->D);
     return 0;
 }
 
@@ -463,7 +464,7 @@ static int mrssm_fwd_common(const RssmMrssmDims* d, const RssmMrssmWeights* w, c
     }
     if (is_wide(d)) return wide_mrssm_fwd(d, w, in, out, static_cast<cudaStream_t>(stream), imagine);
     rssm::MrssmFwdArgs a{};
-    a.B = d->B, a.T = d->T, a.A = d->A, a.K = d->K, a.w = *w;
+    a.B = d->B, a.T = d->T, a.A = d->A, a.K = d->K, a.unimodal = d->unimodal ? 1 : 0, a.w = *w;
     a.actions = in->actions, a.embed_a = in->embed_a, a.embed_v = in->embed_v, a.h0 = in->h0, a.z0 = in->z0;
     a.u_post = in->u_post, a.u_prior = in->u_prior;
     a.feature = out->feature, a.prior_probs = out->prior_probs, a.post_probs = out->post_probs;
@@ -494,7 +495,7 @@ int rssm_mrssm_rollout_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, co
     REQUIRE(gin->dpre);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     rssm::MrssmBwdArgs a{};
-    a.B = d->B, a.T = d->T, a.A = d->A, a.K = d->K, a.kl_wq = up->kl_wq, a.kl_wp = up->kl_wp, a.w = *w;
+    a.B = d->B, a.T = d->T, a.A = d->A, a.K = d->K, a.unimodal = d->unimodal ? 1 : 0, a.kl_wq = up->kl_wq, a.kl_wp = up->kl_wp, a.w = *w;
     a.h0 = in->h0, a.feature = fo->feature, a.prior_probs = fo->prior_probs, a.post_probs = fo->post_probs, a.saved = fo->saved;
     a.d_feature = up->d_feature, a.d_prior_probs = up->d_prior_probs, a.d_post_probs = up->d_post_probs;
     a.d_prior_stoch = up->d_prior_stoch, a.d_kl = up->d_kl;

@@ -45,9 +45,9 @@ def _fill(struct, names: Sequence[str], tensors: Sequence[Optional[Tensor]]):  #
 # =================================================================================================
 # MoPoE-MRSSM
 # =================================================================================================
-def _mr_dims(actions: Tensor, K: int, precision: int, D: int = 32) -> _lib.MrssmDims:
+def _mr_dims(actions: Tensor, K: int, precision: int, D: int = 32, unimodal: bool = False) -> _lib.MrssmDims:
     B, T, A = actions.shape
-    return _lib.MrssmDims(B=B, T=T, A=A, E=64, D=D, H=D, C=16 // K, K=K, precision=precision)
+    return _lib.MrssmDims(B=B, T=T, A=A, E=64, D=D, H=D, C=16 // K, K=K, precision=precision, unimodal=int(unimodal))
 
 
 def _mr_wide(D: int) -> bool:
@@ -97,11 +97,12 @@ def _mr_workspace(dims: _lib.MrssmDims, backward: bool, dev: torch.device) -> Op
 def mrssm_rollout_op(
     weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, h0: Tensor, z0: Tensor,
     u_post: Tensor, u_prior: Optional[Tensor], K: int, precision: int, kl_wq: float, kl_wp: float, save: bool,
+    unimodal: bool,
 ) -> List[Tensor]:
     D = _mr_check(weights, embed_a, h0, z0)
     B, T, _ = actions.shape
     dev = actions.device
-    dims = _mr_dims(actions, K, precision, D)
+    dims = _mr_dims(actions, K, precision, D, unimodal)
     feature = torch.empty(B, T, D + 16, device=dev)
     prior_probs = torch.empty(B, T, 16 // K, K, device=dev)
     post_probs = torch.empty_like(prior_probs)
@@ -124,7 +125,7 @@ def mrssm_rollout_op(
 
 
 @mrssm_rollout_op.register_fake
-def _(weights, actions, embed_a, embed_v, h0, z0, u_post, u_prior, K, precision, kl_wq, kl_wp, save):  # noqa: ANN001
+def _(weights, actions, embed_a, embed_v, h0, z0, u_post, u_prior, K, precision, kl_wq, kl_wp, save, unimodal):  # noqa: ANN001
     B, T, _ = actions.shape
     D = h0.shape[-1]
     e = actions.new_empty
@@ -138,11 +139,12 @@ def mrssm_rollout_bwd_op(
     feature: Tensor, prior_probs: Tensor, post_probs: Tensor, saved: Tensor,
     d_feature: Optional[Tensor], d_prior_probs: Optional[Tensor], d_post_probs: Optional[Tensor],
     d_prior_stoch: Optional[Tensor], d_kl: Optional[Tensor], K: int, precision: int, kl_wq: float, kl_wp: float,
+    unimodal: bool,
 ) -> List[Tensor]:
     B, T, A = actions.shape
     dev = actions.device
     D = h0.shape[-1]
-    dims = _mr_dims(actions, K, precision, D)
+    dims = _mr_dims(actions, K, precision, D, unimodal)
     if d_feature is None:
         d_feature = torch.zeros_like(feature)
     sizes = [t.numel() for t in weights]
@@ -172,20 +174,20 @@ def mrssm_rollout_bwd_op(
 
 @mrssm_rollout_bwd_op.register_fake
 def _(weights, actions, embed_a, embed_v, h0, z0, feature, prior_probs, post_probs, saved, d_feature, d_prior_probs,  # noqa: ANN001
-      d_post_probs, d_prior_stoch, d_kl, K, precision, kl_wq, kl_wp):
+      d_post_probs, d_prior_stoch, d_kl, K, precision, kl_wq, kl_wp, unimodal):
     return [actions.new_empty(sum(t.numel() for t in weights)), torch.empty_like(actions), torch.empty_like(embed_a),
             torch.empty_like(embed_v), torch.empty_like(h0), torch.empty_like(z0)]
 
 
 def _mr_setup(ctx, inputs, output) -> None:  # noqa: ANN001
-    weights, actions, embed_a, embed_v, h0, z0, u_post, u_prior, K, precision, kl_wq, kl_wp, save = inputs
+    weights, actions, embed_a, embed_v, h0, z0, u_post, u_prior, K, precision, kl_wq, kl_wp, save, unimodal = inputs
     feature, prior_probs, post_probs, prior_stoch, kl, saved = output
     if not save:
         raise RuntimeError("mrssm_rollout was called with save=False but a gradient is required")
     ctx.set_materialize_grads(False)
     ctx.nw = len(weights)
     ctx.has_prior_stoch = u_prior is not None
-    ctx.cfg = (K, precision, kl_wq, kl_wp)
+    ctx.cfg = (K, precision, kl_wq, kl_wp, unimodal)
     ctx.save_for_backward(*weights, actions, embed_a, embed_v, h0, z0, feature, prior_probs, post_probs, saved)
 
 
@@ -194,14 +196,14 @@ def _mr_backward(ctx, grads):  # noqa: ANN001
     saved_t = ctx.saved_tensors
     weights, rest = list(saved_t[: ctx.nw]), saved_t[ctx.nw:]
     actions, embed_a, embed_v, h0, z0, feature, prior_probs, post_probs, saved = rest
-    K, precision, kl_wq, kl_wp = ctx.cfg
+    K, precision, kl_wq, kl_wp, unimodal = ctx.cfg
     res = mrssm_rollout_bwd_op(
         weights, actions, embed_a, embed_v, h0, z0, feature, prior_probs, post_probs, saved, d_feature, d_prior_probs,
-        d_post_probs, d_prior_stoch if ctx.has_prior_stoch else None, d_kl, K, precision, kl_wq, kl_wp,
+        d_post_probs, d_prior_stoch if ctx.has_prior_stoch else None, d_kl, K, precision, kl_wq, kl_wp, unimodal,
     )
     flat, d_actions, d_ea, d_ev, d_h0, d_z0 = res
     gws = [g.view_as(w) for g, w in zip(flat.split([w.numel() for w in weights]), weights)]
-    return gws, d_actions, d_ea, d_ev, d_h0, d_z0, None, None, None, None, None, None, None
+    return gws, d_actions, d_ea, d_ev, d_h0, d_z0, None, None, None, None, None, None, None, None
 
 
 mrssm_rollout_op.register_autograd(_mr_backward, setup_context=_mr_setup)
@@ -210,9 +212,13 @@ mrssm_rollout_op.register_autograd(_mr_backward, setup_context=_mr_setup)
 def mrssm_rollout(
     weights: Sequence[Tensor], *, actions: Tensor, embed_a: Tensor, embed_v: Tensor, h0: Tensor, z0: Tensor,
     u_post: Tensor, u_prior: Optional[Tensor] = None, class_size: int = 4, precision: int = _lib.PRECISION_FP32,
-    use_kl_balancing: bool = True,
+    use_kl_balancing: bool = True, unimodal: bool = False,
 ) -> dict[str, Tensor]:
     """Fused MoPoE-MRSSM rollout_representation on encoder outputs (mrssm/mopoe_mrssm/core.py:184-260).
+
+    `unimodal=True` is BaseRSSM.rollout_representation (core.py:137-168): the posterior is the FIRST head (`au_*` weights on
+    `embed_a`, i.e. `representation.rnn_to_post_projector`) with no fusion; `embed_v` and the `vi_*` weights are not used by the
+    result (pass the audio ones) and get zero gradients.
 
     Returns feature [B,T,48] = [deter | post_stoch], prior_probs / post_probs [B,T,C,K], prior_stoch
     [B,T,16] (only when `u_prior` is given) and kl [B,T] = sum_c KL(post_c || prior_c) whose gradient is
@@ -222,7 +228,7 @@ def mrssm_rollout(
     wq, wp = kl_path_weights(use_kl_balancing)
     feature, prior_probs, post_probs, prior_stoch, kl, _ = mrssm_rollout_op(
         [_c(w) for w in weights], _c(actions), _c(embed_a), _c(embed_v), _c(h0), _c(z0), _c(u_post), _c(u_prior),
-        class_size, precision, wq, wp, save,
+        class_size, precision, wq, wp, save, unimodal,
     )
     return {"feature": feature, "prior_probs": prior_probs, "post_probs": post_probs,
             "prior_stoch": prior_stoch if u_prior is not None else None, "kl": kl}

@@ -159,8 +159,13 @@ def mrssm_rollout(
     C: int,
     K: int,
     forced_post_idx: Tensor | None = None,
+    unimodal: bool = False,
 ) -> dict[str, Tensor]:
     """MoPoE_MRSSM.rollout_representation, mrssm/mopoe_mrssm/core.py:184-260, on encoder outputs.
+
+    `unimodal=True` is BaseRSSM.rollout_representation, core.py:137-168: `posterior = representation(obs_embed[:, t], prior)`
+    = Representation.forward (networks.py:70-84): factory(MLP([deter ; embed])) of the ONE head stored under
+    `audio_representation.*` (the reference aliases `representation` to it), no fusion; embed_v is ignored.
 
     actions [B,T,A], embed_* [B,T,E], h0 [B,D], z0 [B,S], u_* [B,T,C].  The per-modality posterior
     samples the reference draws and discards (:83 -> state.py:17) are not drawn.  `forced_post_idx`
@@ -178,7 +183,7 @@ def mrssm_rollout(
         deter, prior_probs, inter = mrssm_transition(params, actions[:, t], deter, stoch, C, K)  # :222
         la, a_hid = mlp(params, "audio_representation.rnn_to_post_projector", torch.cat([deter, embed_a[:, t]], -1))  # :80-81
         lv, v_hid = mlp(params, "vision_representation.rnn_to_post_projector", torch.cat([deter, embed_v[:, t]], -1))
-        mixed = mopoe_fuse(la, lv)  # :241-251
+        mixed = la if unimodal else mopoe_fuse(la, lv)  # :241-251 / networks.py:82-83
         post_probs = group_probs(mixed, C, K)  # :161
         forced = None if forced_post_idx is None else forced_post_idx[:, t]
         stoch, post_idx = sample_st(post_probs, u_post[:, t], forced)  # :163 -> state.py:17

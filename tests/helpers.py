@@ -103,13 +103,13 @@ def _resample(u: torch.Tensor, bad: torch.Tensor, g: torch.Generator) -> int:
     return n
 
 
-def mrssm_safe_uniforms(params, inp, C: int, K: int, eps: float) -> None:
+def mrssm_safe_uniforms(params, inp, C: int, K: int, eps: float, unimodal: bool = False) -> None:
     """Resample (in place) uniforms that sit within `eps` of a CDF boundary of the ORACLE trajectory, so that
     rounding-level differences between two correct implementations cannot flip a categorical draw."""
     g = torch.Generator().manual_seed(99)
     for _ in range(50):
         with torch.no_grad():
-            res = O.mrssm_rollout(params, C=C, K=K, **inp)
+            res = O.mrssm_rollout(params, C=C, K=K, unimodal=unimodal, **inp)
             bad = res["post_margin"] < eps
             badp = O.cdf_margin(res["prior_probs"], inp["u_prior"]) < eps
         if _resample(inp["u_post"], bad, g) + _resample(inp["u_prior"], badp, g) == 0:

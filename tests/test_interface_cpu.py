@@ -282,7 +282,7 @@ def test_wide_family_fake_shapes_and_size_check():
 
     weights = [meta(*shapes[k]) for k in MR_STATE_KEYS]
     out = torch.ops.mtrssm_b200.mrssm_rollout(weights, meta(B, T, 6), meta(B, T, 64), meta(B, T, 64), meta(B, D), meta(B, 16),
-                                              meta(B, T, 4), None, K, 1, 0.2, 0.8, True)
+                                              meta(B, T, 4), None, K, 1, 0.2, 0.8, True, False)
     assert out[0].shape == (B, T, D + 16) and out[1].shape == (B, T, 4, 4) and out[5].dtype == torch.bfloat16
     assert out[5].numel() * 2 == 3 * 10 * 1 * D * 128 * 2 + 128 * 3 * 32 * 4
     with pytest.raises(RuntimeError, match="supports"):
@@ -339,3 +339,34 @@ def test_shard_batch_rejects_ragged():
 
     with pytest.raises(ValueError, match="divisible"):
         shard_batch((torch.zeros(5, 2),), 0, 2)
+
+
+def test_oracle_unimodal_switch_follows_the_reference_structured_module_loop():
+    """SURVEY 8 row a6 (core.py:137-168): the oracle's `unimodal=True` rollout against the per-step loop of the host modules
+    (Transition.forward networks.py:151-173, Representation.forward networks.py:70-84) with the oracle's draws forced."""
+    from multimodal_mtrssm_b200 import _lib
+    from multimodal_mtrssm_b200.state import State
+    from oracle import rssm_oracle as O
+    from tests import helpers as H
+
+    import ctypes as C
+
+    assert C.sizeof(_lib.MrssmDims) == 10 * 4  # ... precision, unimodal
+    torch.manual_seed(0)
+    m = H.build_mrssm_model()
+    B, T = 5, 6
+    inp = H.mrssm_inputs(B, T, 4, 4)
+    params = {k: v.detach() for k, v in m.state_dict().items()}
+    res = O.mrssm_rollout(params, C=4, K=4, unimodal=True, **inp)
+    with torch.no_grad():
+        state = State(deter=inp["h0"], distribution=m.representation.distribution_factory(torch.zeros(B, 16)), stoch=inp["z0"])
+        for t in range(T):
+            prior = m.transition(inp["actions"][:, t], state)
+            dist = m.representation.distribution_factory(
+                m.representation.rnn_to_post_projector(torch.cat([prior.deter, inp["embed_a"][:, t]], -1)))
+            torch.testing.assert_close(prior.deter, res["deter"][:, t], rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(dist.probs, res["post_probs"][:, t], rtol=1e-5, atol=1e-6)
+            state = State(deter=prior.deter, distribution=dist, stoch=res["post_stoch"][:, t])
+    # the vision inputs / head play no role
+    other = dict(inp, embed_v=torch.randn_like(inp["embed_v"]))
+    assert torch.equal(O.mrssm_rollout(params, C=4, K=4, unimodal=True, **other)["post_probs"], res["post_probs"])

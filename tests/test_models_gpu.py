@@ -262,3 +262,44 @@ def test_pinned_prefetcher_delivers_every_batch_in_order():
     pre2.submit(hosts[1])
     with pytest.raises(RuntimeError, match="in flight"):
         pre2.submit(hosts[2])
+
+
+def test_base_rssm_unimodal_rollout_uses_the_fused_kernel_and_matches_the_module_loop():
+    """BaseRSSM.rollout_representation (core.py:137-168).  On CUDA it is one fused launch (unimodal flag); its
+    deterministic outputs must match the reference-structured per-step loop of the same modules (Transition.forward /
+    Representation.forward) teacher-forced on the kernel's draws, and training through it must work."""
+    from multimodal_mtrssm_b200 import _lib
+    from multimodal_mtrssm_b200.core import BaseRSSM
+    from multimodal_mtrssm_b200.state import State
+
+    torch.manual_seed(0)
+    m = H.build_mrssm_model().cuda()
+    B, T = 24, 7
+    g = torch.Generator().manual_seed(3)
+    emb = torch.randn(B, T, 64, generator=g).cuda()
+    act = torch.randn(B, T, 6, generator=g).cuda()
+    m.encode_observation = lambda obs: obs          # unimodal: observations are already embeddings here
+    with torch.no_grad():
+        h0 = torch.randn(B, 32, generator=g).cuda()
+        prev = State(deter=h0, distribution=m.representation.distribution_factory(m.transition.rnn_to_prior_projector(h0)))
+    n0 = _lib.launch_count()
+    post, prior = BaseRSSM.rollout_representation(m, actions=act, observations=emb, prev_state=prev)
+    assert _lib.launch_count() == n0 + 1 and post.feature.shape == (B, T, 48) and prior.stoch.shape == (B, T, 16)
+    # per-step module loop, teacher-forced on the kernel's posterior draws
+    with torch.no_grad():
+        state, deters, probs = prev, [], []
+        for t in range(T):
+            pr = m.transition(act[:, t], state)
+            hid = m.representation.rnn_to_post_projector(torch.cat([pr.deter, emb[:, t]], -1))
+            dist = m.representation.distribution_factory(hid)
+            state = State(deter=pr.deter, distribution=dist, stoch=post.stoch[:, t])
+            deters.append(pr.deter)
+            probs.append(dist.probs)
+    torch.testing.assert_close(post.deter, torch.stack(deters, 1), rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(post.distribution.probs, torch.stack(probs, 1), rtol=1e-5, atol=2e-6)
+    loss = (post.feature ** 2).mean() + m.kl_coeff * __import__("multimodal_mtrssm_b200.distribution", fromlist=["kl_divergence"]).kl_divergence(
+        q=post.distribution.independent(1), p=prior.distribution.independent(1), use_balancing=True)
+    loss.backward()
+    head = m.representation.rnn_to_post_projector
+    assert head[0].weight.grad is not None and float(head[0].weight.grad.abs().max()) > 0
+    assert m.transition.rnn_cell.weight_hh.grad is not None

@@ -209,6 +209,62 @@ def test_mrssm_bf16_teacher_forced(ops):
 
 
 # ---------------------------------------------------------------------------------------------------
+# unimodal rollout (BaseRSSM.rollout_representation, core.py:137-168): dims.unimodal = 1
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,K,precision", [(37, 9, 4, 0), (8, 30, 2, 0), (20, 6, 4, 1)])
+def test_mrssm_unimodal_matches_oracle(ops, B, T, K, precision):
+    """One Representation.forward per step, no fusion: forward and every gradient against the oracle's unimodal switch.  The
+    vision slot (weights and embedding) must not influence the result and must get exactly zero gradients.  fp32 path: the
+    module tolerances; bf16 path: teacher-forced on the kernel's draws, 3e-2 / 2e-2 of scale as for the multimodal kernels."""
+    R, P = ops
+    C = 16 // K
+    params = H.make_params(H.MR_SHAPES)
+    inp = H.mrssm_inputs(B, T, C, K)
+    H.mrssm_safe_uniforms(params, inp, C, K, eps=2e-4, unimodal=True)
+    up = mrssm_upstream(B, T, C, K)
+    w = {k: v.cuda().requires_grad_(True) for k, v in params.items()}
+    x = cuda(inp)
+    for k in ("actions", "embed_a", "embed_v", "h0", "z0"):
+        x[k] = x[k].requires_grad_(True)
+    got = R.mrssm_rollout(P.mrssm_weight_list(w), class_size=K, precision=precision, unimodal=True, **x)
+    sum((got[k] * up[k].cuda()).sum() for k in up).backward()
+    forced = None if precision == 0 else got["feature"][..., 32:].detach().cpu().reshape(B, T, C, K).argmax(-1)
+    w_ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    x_ref = {k: (v.clone().requires_grad_(True) if k in ("actions", "embed_a", "embed_v", "h0", "z0") else v) for k, v in inp.items()}
+    want = O.mrssm_rollout(w_ref, C=C, K=K, forced_post_idx=forced, unimodal=True, **x_ref)
+    want["kl"] = O.kl_per_sample(want["post_probs"], want["prior_probs"], True)
+    want["feature"] = want["post_feature"]
+    if precision != 0:  # the prior's own draw is not teacher-forced: leave it out of the bf16 comparison
+        up = {k: v for k, v in up.items() if k != "prior_stoch"}
+        w2 = {k: v.cuda().requires_grad_(True) for k, v in params.items()}
+        x2 = cuda(inp)
+        for k in ("actions", "embed_a", "embed_v", "h0", "z0"):
+            x2[k] = x2[k].requires_grad_(True)
+        got = R.mrssm_rollout(P.mrssm_weight_list(w2), class_size=K, precision=precision, unimodal=True, **x2)
+        sum((got[k] * up[k].cuda()).sum() for k in up).backward()
+        w, x = w2, x2
+    sum((want[k] * up[k]).sum() for k in up).backward()
+    rep = H.Report(f"mrssm unimodal B={B} T={T} K={K} precision={precision}")
+    ftol = FWD_TOL if precision == 0 else dict(rtol=0, atol=3e-2)
+    rep.check("deter", got["feature"][..., :32], want["deter"], **ftol)
+    rep.check("post_probs", got["post_probs"], want["post_probs"], **ftol)
+    rep.check("prior_probs", got["prior_probs"], want["prior_probs"], **ftol)
+    rep.check("kl", got["kl"], want["kl"], **(dict(rtol=1e-5, atol=1e-6) if precision == 0 else dict(rtol=0, atol=3e-2)))
+    if precision == 0:
+        assert torch.equal(got["feature"][..., 32:].cpu().reshape(B, T, C, K).argmax(-1), want["post_idx"])
+    gt = grad_tol if precision == 0 else (lambda r: dict(rtol=0, atol=2e-2 * max(float(r.abs().max()), 1e-3)))
+    for k in ("embed_a", "actions", "h0", "z0"):
+        rep.check("d " + k, x[k].grad, x_ref[k].grad, **gt(x_ref[k].grad))
+    for k in w:
+        if k.startswith("vision_representation"):
+            continue
+        rep.check("d " + k, w[k].grad, w_ref[k].grad, **gt(w_ref[k].grad))
+    rep.finish()
+    assert float(x["embed_v"].grad.abs().max()) == 0.0
+    assert all(float(w[k].grad.abs().max()) == 0.0 for k in w if k.startswith("vision_representation"))
+
+
+# ---------------------------------------------------------------------------------------------------
 # MMTRSSM
 # ---------------------------------------------------------------------------------------------------
 MT_GRAD_IN = ("actions", "embed_a", "embed_v", "deter_h0", "deter_l0", "hidden_h0", "hidden_l0", "stoch_h0", "stoch_l0")
