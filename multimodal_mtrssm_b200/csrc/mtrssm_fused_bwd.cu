@@ -258,7 +258,12 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    const int row0 = (blockIdx.x * (nthr >> 6) + tile) * 16;  // 2 or 4 tiles (4 or 8 warps) per CTA
+    // Persistent over tile groups: a CTA (2 or 4 tiles = 4 or 8 warps) walks groups blockIdx.x, blockIdx.x + gridDim.x, ... and keeps
+    // accumulating the weight gradients in the SAME TMEM columns, so the weight packing above, the TMEM allocation and the
+    // read-back + atomics below happen once per SM instead of once per group (4 groups per SM at the bench size).
+    const int tpc = nthr >> 6, ngroups = ((p.B + 15) / 16 + tpc - 1) / tpc;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int row0 = (grp * tpc + tile) * 16;
     if (row0 < p.B) {
         const Rows r = make_rows(row0, p.B, lane);
         const int T = p.T;
@@ -658,6 +663,22 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
             cp_async_wait_all();
         }
     }
+    if (grp + (int)gridDim.x < ngroups) {
+        // another group follows: put the tile's shared memory and mbarriers back into their initial state (every MMA and bulk
+        // copy of this group has completed: both warps waited on BAR_END / their copies above)
+        nbar_sync(9 + tile);
+        for (int i = lane + 32 * role; i < fz2::BYTES / 16; i += 64) reinterpret_cast<uint4*>(my)[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (role == 0 && lane == 0) {
+#pragma unroll
+            for (int i = 0; i < fz2::NBAR; ++i) {
+                asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[i])) : "memory");
+                mbar_init(&bars[i], 1);
+            }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        nbar_sync(9 + tile);
+    }
+    }  // tile groups
     // ---- epilogue: TMEM accumulators -> global weight gradients (one atomicAdd per element per CTA) -----------------------
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -742,7 +763,11 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
     auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        kernel<<<(tiles + tpc - 1) / tpc, 64 * tpc, smem, s>>>(a, u);
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int groups = (tiles + tpc - 1) / tpc;  // one resident CTA per SM (shared memory): persistent over its groups
+        kernel<<<groups < sms ? groups : sms, 64 * tpc, smem, s>>>(a, u);
         return cudaGetLastError();
     };
 #define FUSED_DISPATCH(KLv, KHv) \
