@@ -697,7 +697,7 @@ def main() -> None:
     if (B, T) == (37888, 30) and precision == _lib.PRECISION_BF16:
         traffic = 2.156e9 if dominant == "mtrssm_fwd_kernel" else 3.014e9 + 2.230e9
     elif (B, T) == (37888, 30) and precision == _lib.PRECISION_BF16_FUSED:
-        traffic = 2.155e9 if dominant == "mtrssm_fwd_kernel" else 2.888e9  # profiles/r1_g_ncu_summary.txt
+        traffic = 2.156e9 if dominant == "mtrssm_fwd_kernel" else 2.888e9  # profiles/r1_n_ncu_summary.txt (2.2746 GB read + 0.6137 GB written)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
