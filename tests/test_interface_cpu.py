@@ -370,3 +370,15 @@ def test_oracle_unimodal_switch_follows_the_reference_structured_module_loop():
     # the vision inputs / head play no role
     other = dict(inp, embed_v=torch.randn_like(inp["embed_v"]))
     assert torch.equal(O.mrssm_rollout(params, C=4, K=4, unimodal=True, **other)["post_probs"], res["post_probs"])
+
+
+def test_unimodal_flag_is_rejected_for_the_wide_family_on_the_host():
+    """dims.unimodal (BaseRSSM.rollout_representation) is built for the default sizes; the wide family must refuse it before any
+    launch (size queries return 0, the launch would report why) rather than silently running the multimodal kernel."""
+    from multimodal_mtrssm_b200 import _lib
+
+    ok = _lib.MrssmDims(B=256, T=4, A=6, E=64, D=512, H=512, C=4, K=4, precision=_lib.PRECISION_BF16, unimodal=0)
+    bad = _lib.MrssmDims(B=256, T=4, A=6, E=64, D=512, H=512, C=4, K=4, precision=_lib.PRECISION_BF16, unimodal=1)
+    assert _lib.mrssm_saved_bytes(ok) > 0 and _lib.mrssm_saved_bytes(bad) == 0
+    small = _lib.MrssmDims(B=8, T=4, A=6, E=64, D=32, H=32, C=4, K=4, precision=_lib.PRECISION_FP32, unimodal=1)
+    assert _lib.mrssm_saved_bytes(small) == 8 * 4 * _lib.MRSSM_SAVED_FLOATS * 4
