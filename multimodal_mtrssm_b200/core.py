@@ -14,7 +14,7 @@ from torch import Tensor, nn
 
 from .distribution import kl_divergence
 from .networks import Representation, Transition
-from .state import State, stack_states
+from .state import State
 
 try:  # pragma: no cover - lightning is absent in the build image
     from lightning import LightningModule as _Base
@@ -94,54 +94,41 @@ class BaseRSSM(_Base):
         return State(deter=deter, distribution=self.representation.distribution_factory(logits)).to(self.device)
 
     def rollout_representation(self, *, actions: Tensor, observations, prev_state: State) -> tuple[State, State]:  # noqa: ANN001
-        """core.py:137-168, the unimodal rollout (both shipped models override it).  On CUDA, at the sizes the kernels are built
-        for, the T loop is ONE fused kernel (`rollout_ops.mrssm_rollout(..., unimodal=True)`: Transition.forward + ONE
-        Representation.forward per step, no fusion); otherwise (CPU tensors, as the reference also allows) the reference's own
-        per-step structure runs."""
+        """core.py:137-168, the unimodal rollout (both shipped models override it).  The T loop is ONE fused kernel
+        (`rollout_ops.mrssm_rollout(..., unimodal=True)`: Transition.forward + ONE Representation.forward per step, no fusion).
+        There is no per-step fallback: CPU tensors, sizes outside the built family (include/rssm_rollout.h) or heads that are
+        not Linear-ELU-Linear raise RuntimeError."""
         obs_embed = self.encode_observation(observations)
-        if obs_embed.is_cuda and self._fused_unimodal_ok(obs_embed, prev_state):
-            return self._rollout_representation_fused(actions, obs_embed, prev_state)
-        priors, posteriors = [], []
-        for t in range(obs_embed.shape[1]):
-            prior = self.transition(actions[:, t], prev_state)
-            posterior = self.representation(obs_embed[:, t], prior)
-            priors.append(prior)
-            posteriors.append(posterior)
-            prev_state = posterior
-        return stack_states(posteriors, dim=1), stack_states(priors, dim=1)
+        return self._rollout_representation_fused(actions, obs_embed, prev_state)
 
-    def _fused_unimodal_ok(self, obs_embed: Tensor, prev_state: State) -> bool:
+    def _unimodal_weights(self) -> list[Tensor]:
+        """Parameters in C-ABI order (`params.MR_STATE_KEYS`); the single head fills both posterior slots (the second is unused
+        by the unimodal kernels and gets zero gradients)."""
         from .mopoe_mrssm import mlp_params
 
-        f = self.representation.distribution_factory
-        if not (prev_state.deter.shape[-1] == 32 and obs_embed.shape[-1] == 64 and int(f.class_size) * int(f.category_size) == 16
-                and all(hasattr(self.transition, n) for n in ("action_state_projector", "rnn_cell", "rnn_to_prior_projector"))):
-            return False
-        try:  # Linear-ELU-Linear heads only (the kernels' epilogues)
-            for m in (self.transition.action_state_projector, self.transition.rnn_to_prior_projector, self.representation.rnn_to_post_projector):
-                mlp_params(m, "head")
-        except (RuntimeError, TypeError, ValueError):
-            return False
-        return True
+        tr = self.transition
+        for name in ("action_state_projector", "rnn_cell", "rnn_to_prior_projector"):
+            if not hasattr(tr, name):
+                raise RuntimeError(f"the fused rollout needs a `Transition` with `{name}` (networks.py:126-149), got {type(tr).__name__}")
+        head = mlp_params(self.representation.rnn_to_post_projector, "representation.rnn_to_post_projector")
+        return [
+            *mlp_params(tr.action_state_projector, "transition.action_state_projector"),
+            tr.rnn_cell.weight_ih, tr.rnn_cell.weight_hh, tr.rnn_cell.bias_ih, tr.rnn_cell.bias_hh,
+            *mlp_params(tr.rnn_to_prior_projector, "transition.rnn_to_prior_projector"), *head, *head,
+        ]
 
     def _rollout_representation_fused(self, actions: Tensor, obs_embed: Tensor, prev_state: State) -> tuple[State, State]:
         from . import rollout_ops
         from .distribution import Distribution, FusedKL
-        from .mopoe_mrssm import flat_stoch, mlp_params
+        from .mopoe_mrssm import flat_stoch
 
-        tr, head = self.transition, mlp_params(self.representation.rnn_to_post_projector, "representation.rnn_to_post_projector")
-        weights = [
-            *mlp_params(tr.action_state_projector, "transition.action_state_projector"),
-            tr.rnn_cell.weight_ih, tr.rnn_cell.weight_hh, tr.rnn_cell.bias_ih, tr.rnn_cell.bias_hh,
-            *mlp_params(tr.rnn_to_prior_projector, "transition.rnn_to_prior_projector"), *head, *head,  # second copy: unused slot
-        ]
         f = self.representation.distribution_factory
         B, T = obs_embed.shape[:2]
         C, dev = int(f.category_size), obs_embed.device
         out = rollout_ops.mrssm_rollout(
-            weights, actions=actions, embed_a=obs_embed, embed_v=obs_embed, h0=prev_state.deter, z0=flat_stoch(prev_state.stoch),
-            u_post=torch.rand(B, T, C, device=dev), u_prior=torch.rand(B, T, C, device=dev), class_size=int(f.class_size),
-            precision=self._precision(), use_kl_balancing=bool(self.use_kl_balancing), unimodal=True,
+            self._unimodal_weights(), actions=actions, embed_a=obs_embed, embed_v=obs_embed, h0=prev_state.deter,
+            z0=flat_stoch(prev_state.stoch), u_post=torch.rand(B, T, C, device=dev), u_prior=torch.rand(B, T, C, device=dev),
+            class_size=int(f.class_size), precision=self._precision(), use_kl_balancing=bool(self.use_kl_balancing), unimodal=True,
         )
         feature = out["feature"]
         D = prev_state.deter.shape[-1]
@@ -152,12 +139,25 @@ class BaseRSSM(_Base):
         return posterior, prior
 
     def rollout_transition(self, *, actions: Tensor, prev_state: State) -> State:
-        """core.py:170-185: imagination, the prior's own sample is fed back."""
-        priors = []
-        for t in range(actions.shape[1]):
-            prev_state = self.transition(actions[:, t], prev_state)
-            priors.append(prev_state)
-        return stack_states(priors, dim=1)
+        """core.py:170-185: imagination, the prior's own sample is fed back.  ONE fused forward-only kernel
+        (`rollout_ops.mrssm_imagine`; the reference calls this under no_grad); no per-step fallback."""
+        from . import rollout_ops
+        from .distribution import Distribution
+        from .mopoe_mrssm import flat_stoch
+
+        if torch.is_grad_enabled() and (actions.requires_grad or prev_state.deter.requires_grad):
+            msg = "the fused rollout_transition is forward-only; call it under torch.no_grad() (as the reference's callbacks do)"
+            raise RuntimeError(msg)
+        B, T = actions.shape[:2]
+        fac = self.transition.distribution_factory
+        u = torch.rand(B, T, int(fac.category_size), device=actions.device)
+        out = rollout_ops.mrssm_imagine(
+            [w.detach() for w in self._unimodal_weights()], actions=actions, h0=prev_state.deter, z0=flat_stoch(prev_state.stoch), u=u,
+            class_size=int(fac.class_size), precision=self._precision(),
+        )
+        feature = out["feature"]
+        D = prev_state.deter.shape[-1]
+        return State(deter=feature[..., :D], stoch=feature[..., D:], feature=feature, distribution=Distribution(out["probs"]))
 
     def shared_step(self, batch: tuple[Tensor, ...]) -> dict[str, Tensor]:
         """core.py:187-221: recon + kl_coeff * KL(posterior || prior)."""

@@ -36,6 +36,25 @@ def _c(t: Optional[Tensor]) -> Optional[Tensor]:
     return None if t is None else t.float().contiguous()
 
 
+def _on_device(*tensors):  # noqa: ANN002, ANN202
+    """Device guard of one op call: every tensor must live on ONE CUDA device (the first tensor's); the body then runs with that
+    device current, so `torch.empty(device=...)`, `torch.cuda.current_stream()` and the kernel launch all agree even when the
+    caller's current device is another GPU.  CPU tensors raise: there is no eager fallback."""
+    flat = []
+    for t in tensors:
+        if isinstance(t, Tensor):
+            flat.append(t)
+        elif isinstance(t, (list, tuple)):
+            flat.extend(x for x in t if isinstance(x, Tensor))
+    dev = flat[0].device
+    if dev.type != "cuda":
+        raise RuntimeError(f"the fused rollout ops are CUDA-only (there is no CPU fallback); got a tensor on {dev}")
+    for t in flat:
+        if t.device != dev:
+            raise RuntimeError(f"all tensors of a fused rollout call must be on one device: got {dev} and {t.device}")
+    return torch.cuda.device(dev)
+
+
 def _fill(struct, names: Sequence[str], tensors: Sequence[Optional[Tensor]]):  # noqa: ANN001
     for n, t in zip(names, tensors):
         setattr(struct, n, ptr(t))
@@ -99,29 +118,30 @@ def mrssm_rollout_op(
     u_post: Tensor, u_prior: Optional[Tensor], K: int, precision: int, kl_wq: float, kl_wp: float, save: bool,
     unimodal: bool,
 ) -> List[Tensor]:
-    D = _mr_check(weights, embed_a, h0, z0)
-    B, T, _ = actions.shape
-    dev = actions.device
-    dims = _mr_dims(actions, K, precision, D, unimodal)
-    feature = torch.empty(B, T, D + 16, device=dev)
-    prior_probs = torch.empty(B, T, 16 // K, K, device=dev)
-    post_probs = torch.empty_like(prior_probs)
-    prior_stoch = torch.empty(B, T, 16, device=dev) if u_prior is not None else torch.empty(0, device=dev)
-    kl = torch.empty(B, T, device=dev)
-    saved = torch.empty(_mr_saved_shape(B, T, D), device=dev, dtype=_lib.record_dtype(precision)) if save else torch.empty(0, device=dev)
-    lib_bytes = _lib.mrssm_saved_bytes(dims)  # 0: unsupported sizes / precision -- the launch below reports why
-    if save and lib_bytes and saved.numel() * saved.element_size() != lib_bytes:
-        raise RuntimeError(f"saved record size mismatch with the library: {saved.numel() * saved.element_size()} vs {lib_bytes} bytes")
-    workspace = _mr_workspace(dims, False, dev)
-    w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
-    inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0 u_post u_prior".split(),
-                (actions, embed_a, embed_v, h0, z0, u_post, u_prior))
-    out = _fill(_lib.MrssmOutputs(), "feature prior_probs post_probs prior_stoch kl saved workspace".split(),
-                (feature, prior_probs, post_probs, prior_stoch if u_prior is not None else None, kl, saved if save else None,
-                 workspace))
-    out.workspace_bytes = 0 if workspace is None else workspace.numel() * 2
-    _lib.call("rssm_mrssm_rollout_fwd", dims, w, inp, out)
-    return [feature, prior_probs, post_probs, prior_stoch, kl, saved]
+    with _on_device(actions, weights, embed_a, embed_v, h0, z0, u_post, u_prior):
+        D = _mr_check(weights, embed_a, h0, z0)
+        B, T, _ = actions.shape
+        dev = actions.device
+        dims = _mr_dims(actions, K, precision, D, unimodal)
+        feature = torch.empty(B, T, D + 16, device=dev)
+        prior_probs = torch.empty(B, T, 16 // K, K, device=dev)
+        post_probs = torch.empty_like(prior_probs)
+        prior_stoch = torch.empty(B, T, 16, device=dev) if u_prior is not None else torch.empty(0, device=dev)
+        kl = torch.empty(B, T, device=dev)
+        saved = torch.empty(_mr_saved_shape(B, T, D), device=dev, dtype=_lib.record_dtype(precision)) if save else torch.empty(0, device=dev)
+        lib_bytes = _lib.mrssm_saved_bytes(dims)  # 0: unsupported sizes / precision -- the launch below reports why
+        if save and lib_bytes and saved.numel() * saved.element_size() != lib_bytes:
+            raise RuntimeError(f"saved record size mismatch with the library: {saved.numel() * saved.element_size()} vs {lib_bytes} bytes")
+        workspace = _mr_workspace(dims, False, dev)
+        w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
+        inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0 u_post u_prior".split(),
+                    (actions, embed_a, embed_v, h0, z0, u_post, u_prior))
+        out = _fill(_lib.MrssmOutputs(), "feature prior_probs post_probs prior_stoch kl saved workspace".split(),
+                    (feature, prior_probs, post_probs, prior_stoch if u_prior is not None else None, kl, saved if save else None,
+                     workspace))
+        out.workspace_bytes = 0 if workspace is None else workspace.numel() * 2
+        _lib.call("rssm_mrssm_rollout_fwd", dims, w, inp, out)
+        return [feature, prior_probs, post_probs, prior_stoch, kl, saved]
 
 
 @mrssm_rollout_op.register_fake
@@ -141,35 +161,36 @@ def mrssm_rollout_bwd_op(
     d_prior_stoch: Optional[Tensor], d_kl: Optional[Tensor], K: int, precision: int, kl_wq: float, kl_wp: float,
     unimodal: bool,
 ) -> List[Tensor]:
-    B, T, A = actions.shape
-    dev = actions.device
-    D = h0.shape[-1]
-    dims = _mr_dims(actions, K, precision, D, unimodal)
-    if d_feature is None:
-        d_feature = torch.zeros_like(feature)
-    sizes = [t.numel() for t in weights]
-    flat = torch.zeros(sum(sizes), device=dev)
-    gws = [g.view_as(t) for g, t in zip(flat.split(sizes), weights)]
-    d_actions = torch.empty(B, T, A, device=dev)
-    d_embed_a = torch.empty(B, T, 64, device=dev)
-    d_embed_v = torch.empty(B, T, 64, device=dev)
-    d_h0 = torch.empty(B, D, device=dev)
-    d_z0 = torch.empty(B, 16, device=dev)
-    # default family: pre-activation gradient record; wide family: the library keeps its gradient planes in the workspace
-    dpre = None if _mr_wide(D) else torch.empty(B, T, _lib.MRSSM_DPRE_FLOATS, device=dev, dtype=_lib.record_dtype(precision))
-    workspace = _mr_workspace(dims, True, dev)
-    w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
-    gw = _fill(_lib.MrssmWeightGrads(), _lib.MR_WEIGHT_FIELDS, gws)
-    inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0".split(), (actions, embed_a, embed_v, h0, z0))
-    out = _fill(_lib.MrssmOutputs(), "feature prior_probs post_probs saved".split(), (feature, prior_probs, post_probs, saved))
-    up = _fill(_lib.MrssmUpstream(), "d_feature d_prior_probs d_post_probs d_prior_stoch d_kl".split(),
-               (_c(d_feature), _c(d_prior_probs), _c(d_post_probs), _c(d_prior_stoch), _c(d_kl)))
-    up.kl_wq, up.kl_wp = kl_wq, kl_wp
-    gin = _fill(_lib.MrssmInputGrads(), "d_actions d_embed_a d_embed_v d_h0 d_z0 dpre workspace".split(),
-                (d_actions, d_embed_a, d_embed_v, d_h0, d_z0, dpre, workspace))
-    gin.workspace_bytes = 0 if workspace is None else workspace.numel() * 2
-    _lib.call("rssm_mrssm_rollout_bwd", dims, w, inp, out, up, gin, gw)
-    return [flat, d_actions, d_embed_a, d_embed_v, d_h0, d_z0]  # flat = all weight grads, split by the caller
+    with _on_device(actions, weights, embed_a, embed_v, h0, z0, feature, prior_probs, post_probs, saved, d_feature, d_prior_probs, d_post_probs, d_prior_stoch, d_kl):
+        B, T, A = actions.shape
+        dev = actions.device
+        D = h0.shape[-1]
+        dims = _mr_dims(actions, K, precision, D, unimodal)
+        if d_feature is None:
+            d_feature = torch.zeros_like(feature)
+        sizes = [t.numel() for t in weights]
+        flat = torch.zeros(sum(sizes), device=dev)
+        gws = [g.view_as(t) for g, t in zip(flat.split(sizes), weights)]
+        d_actions = torch.empty(B, T, A, device=dev)
+        d_embed_a = torch.empty(B, T, 64, device=dev)
+        d_embed_v = torch.empty(B, T, 64, device=dev)
+        d_h0 = torch.empty(B, D, device=dev)
+        d_z0 = torch.empty(B, 16, device=dev)
+        # default family: pre-activation gradient record; wide family: the library keeps its gradient planes in the workspace
+        dpre = None if _mr_wide(D) else torch.empty(B, T, _lib.MRSSM_DPRE_FLOATS, device=dev, dtype=_lib.record_dtype(precision))
+        workspace = _mr_workspace(dims, True, dev)
+        w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
+        gw = _fill(_lib.MrssmWeightGrads(), _lib.MR_WEIGHT_FIELDS, gws)
+        inp = _fill(_lib.MrssmInputs(), "actions embed_a embed_v h0 z0".split(), (actions, embed_a, embed_v, h0, z0))
+        out = _fill(_lib.MrssmOutputs(), "feature prior_probs post_probs saved".split(), (feature, prior_probs, post_probs, saved))
+        up = _fill(_lib.MrssmUpstream(), "d_feature d_prior_probs d_post_probs d_prior_stoch d_kl".split(),
+                   (_c(d_feature), _c(d_prior_probs), _c(d_post_probs), _c(d_prior_stoch), _c(d_kl)))
+        up.kl_wq, up.kl_wp = kl_wq, kl_wp
+        gin = _fill(_lib.MrssmInputGrads(), "d_actions d_embed_a d_embed_v d_h0 d_z0 dpre workspace".split(),
+                    (d_actions, d_embed_a, d_embed_v, d_h0, d_z0, dpre, workspace))
+        gin.workspace_bytes = 0 if workspace is None else workspace.numel() * 2
+        _lib.call("rssm_mrssm_rollout_bwd", dims, w, inp, out, up, gin, gw)
+        return [flat, d_actions, d_embed_a, d_embed_v, d_h0, d_z0]  # flat = all weight grads, split by the caller
 
 
 @mrssm_rollout_bwd_op.register_fake
@@ -237,19 +258,20 @@ def mrssm_rollout(
 @torch.library.custom_op("mtrssm_b200::mrssm_imagine", mutates_args=())
 def mrssm_imagine_op(weights: Sequence[Tensor], actions: Tensor, h0: Tensor, z0: Tensor, u: Tensor, K: int,
                      precision: int) -> List[Tensor]:
-    B, T, _ = actions.shape
-    dev = actions.device
-    D = h0.shape[-1]
-    dims = _mr_dims(actions, K, precision, D)
-    feature = torch.empty(B, T, D + 16, device=dev)
-    probs = torch.empty(B, T, 16 // K, K, device=dev)
-    workspace = _mr_workspace(dims, False, dev)
-    w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
-    inp = _fill(_lib.MrssmInputs(), "actions h0 z0 u_prior".split(), (actions, h0, z0, u))
-    out = _fill(_lib.MrssmOutputs(), "feature prior_probs workspace".split(), (feature, probs, workspace))
-    out.workspace_bytes = 0 if workspace is None else workspace.numel() * 2
-    _lib.call("rssm_mrssm_imagine_fwd", dims, w, inp, out)
-    return [feature, probs]
+    with _on_device(actions, weights, h0, z0, u):
+        B, T, _ = actions.shape
+        dev = actions.device
+        D = h0.shape[-1]
+        dims = _mr_dims(actions, K, precision, D)
+        feature = torch.empty(B, T, D + 16, device=dev)
+        probs = torch.empty(B, T, 16 // K, K, device=dev)
+        workspace = _mr_workspace(dims, False, dev)
+        w = _fill(_lib.MrssmWeights(), _lib.MR_WEIGHT_FIELDS, weights)
+        inp = _fill(_lib.MrssmInputs(), "actions h0 z0 u_prior".split(), (actions, h0, z0, u))
+        out = _fill(_lib.MrssmOutputs(), "feature prior_probs workspace".split(), (feature, probs, workspace))
+        out.workspace_bytes = 0 if workspace is None else workspace.numel() * 2
+        _lib.call("rssm_mrssm_imagine_fwd", dims, w, inp, out)
+        return [feature, probs]
 
 
 @mrssm_imagine_op.register_fake
@@ -295,28 +317,29 @@ def mtrssm_rollout_op(
     u_post_l: Tensor, u_post_h: Tensor, u_prior_l: Optional[Tensor], u_prior_h: Optional[Tensor],
     KL: int, KH: int, l_tau: float, h_tau: float, precision: int, kl_wq: float, kl_wp: float, save: bool,
 ) -> List[Tensor]:
-    _mt_check(weights, embed_a, state)
-    B, T, _ = actions.shape
-    dev = actions.device
-    e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
-    feature, hidden_h, hidden_l = e(B, T, 96), e(B, T, 32), e(B, T, 32)
-    prior_h, post_h = e(B, T, 16 // KH, KH), e(B, T, 16 // KH, KH)
-    prior_l, post_l = e(B, T, 16 // KL, KL), e(B, T, 16 // KL, KL)
-    has_prior = u_prior_l is not None
-    pz_h, pz_l = (e(B, T, 16), e(B, T, 16)) if has_prior else (e(0), e(0))
-    kl_l, kl_h = e(B, T), e(B, T)
-    saved = torch.empty(B, T, _lib.mtrssm_saved_elems(precision), device=dev, dtype=_lib.record_dtype(precision)) if save else e(0)
-    w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
-    inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE, "u_post_l", "u_post_h", "u_prior_l", "u_prior_h"],
-                (actions, embed_a, embed_v, *state, u_post_l, u_post_h, u_prior_l, u_prior_h))
-    out = _fill(
-        _lib.MtrssmOutputs(),
-        "feature hidden_h hidden_l prior_probs_h prior_probs_l post_probs_h post_probs_l prior_stoch_h prior_stoch_l kl_l kl_h saved".split(),
-        (feature, hidden_h, hidden_l, prior_h, prior_l, post_h, post_l, pz_h if has_prior else None, pz_l if has_prior else None,
-         kl_l, kl_h, saved if save else None),
-    )
-    _lib.call("rssm_mtrssm_rollout_fwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out)
-    return [feature, hidden_h, hidden_l, prior_h, prior_l, post_h, post_l, pz_h, pz_l, kl_l, kl_h, saved]
+    with _on_device(actions, weights, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, u_prior_h):
+        _mt_check(weights, embed_a, state)
+        B, T, _ = actions.shape
+        dev = actions.device
+        e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
+        feature, hidden_h, hidden_l = e(B, T, 96), e(B, T, 32), e(B, T, 32)
+        prior_h, post_h = e(B, T, 16 // KH, KH), e(B, T, 16 // KH, KH)
+        prior_l, post_l = e(B, T, 16 // KL, KL), e(B, T, 16 // KL, KL)
+        has_prior = u_prior_l is not None
+        pz_h, pz_l = (e(B, T, 16), e(B, T, 16)) if has_prior else (e(0), e(0))
+        kl_l, kl_h = e(B, T), e(B, T)
+        saved = torch.empty(B, T, _lib.mtrssm_saved_elems(precision), device=dev, dtype=_lib.record_dtype(precision)) if save else e(0)
+        w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
+        inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE, "u_post_l", "u_post_h", "u_prior_l", "u_prior_h"],
+                    (actions, embed_a, embed_v, *state, u_post_l, u_post_h, u_prior_l, u_prior_h))
+        out = _fill(
+            _lib.MtrssmOutputs(),
+            "feature hidden_h hidden_l prior_probs_h prior_probs_l post_probs_h post_probs_l prior_stoch_h prior_stoch_l kl_l kl_h saved".split(),
+            (feature, hidden_h, hidden_l, prior_h, prior_l, post_h, post_l, pz_h if has_prior else None, pz_l if has_prior else None,
+             kl_l, kl_h, saved if save else None),
+        )
+        _lib.call("rssm_mtrssm_rollout_fwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out)
+        return [feature, hidden_h, hidden_l, prior_h, prior_l, post_h, post_l, pz_h, pz_l, kl_l, kl_h, saved]
 
 
 @mtrssm_rollout_op.register_fake
@@ -337,33 +360,34 @@ def mtrssm_rollout_bwd_op(
     d_post_l: Optional[Tensor], d_pz_h: Optional[Tensor], d_pz_l: Optional[Tensor], d_kl_l: Optional[Tensor],
     d_kl_h: Optional[Tensor], KL: int, KH: int, l_tau: float, h_tau: float, precision: int, kl_wq: float, kl_wp: float,
 ) -> List[Tensor]:
-    B, T, A = actions.shape
-    dev = actions.device
-    if d_feature is None:
-        d_feature = torch.zeros_like(feature)
-    sizes = [t.numel() for t in weights]
-    flat = torch.zeros(sum(sizes), device=dev)
-    gws = [g.view_as(t) for g, t in zip(flat.split(sizes), weights)]
-    e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
-    d_actions, d_ea, d_ev = e(B, T, A), e(B, T, 64), e(B, T, 64)
-    d_state = [e(B, 32), e(B, 32), e(B, 32), e(B, 32), e(B, 16), e(B, 16)]
-    dpre = torch.empty(B, T, _lib.MTRSSM_DPRE_FLOATS, device=dev, dtype=_lib.record_dtype(precision))
-    w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
-    gw = _fill(_lib.MtrssmWeightGrads(), _lib.MT_WEIGHT_FIELDS, gws)
-    inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE], (actions, embed_a, embed_v, *state))
-    out = _fill(_lib.MtrssmOutputs(), "feature prior_probs_h prior_probs_l post_probs_h post_probs_l saved".split(),
-                (feature, prior_h, prior_l, post_h, post_l, saved))
-    up = _fill(
-        _lib.MtrssmUpstream(),
-        "d_feature d_prior_probs_h d_prior_probs_l d_post_probs_h d_post_probs_l d_prior_stoch_h d_prior_stoch_l d_kl_l d_kl_h".split(),
-        tuple(_c(t) for t in (d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h)),
-    )
-    up.kl_wq, up.kl_wp = kl_wq, kl_wp
-    gin = _fill(_lib.MtrssmInputGrads(),
-                ["d_actions", "d_embed_a", "d_embed_v", *("d_" + n for n in _MT_STATE), "dpre"],
-                (d_actions, d_ea, d_ev, *d_state, dpre))
-    _lib.call("rssm_mtrssm_rollout_bwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out, up, gin, gw)
-    return [flat, d_actions, d_ea, d_ev, *d_state]  # flat = all weight grads, split by the caller
+    with _on_device(actions, weights, embed_a, embed_v, state, feature, prior_h, prior_l, post_h, post_l, saved, d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h):
+        B, T, A = actions.shape
+        dev = actions.device
+        if d_feature is None:
+            d_feature = torch.zeros_like(feature)
+        sizes = [t.numel() for t in weights]
+        flat = torch.zeros(sum(sizes), device=dev)
+        gws = [g.view_as(t) for g, t in zip(flat.split(sizes), weights)]
+        e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
+        d_actions, d_ea, d_ev = e(B, T, A), e(B, T, 64), e(B, T, 64)
+        d_state = [e(B, 32), e(B, 32), e(B, 32), e(B, 32), e(B, 16), e(B, 16)]
+        dpre = torch.empty(B, T, _lib.MTRSSM_DPRE_FLOATS, device=dev, dtype=_lib.record_dtype(precision))
+        w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
+        gw = _fill(_lib.MtrssmWeightGrads(), _lib.MT_WEIGHT_FIELDS, gws)
+        inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE], (actions, embed_a, embed_v, *state))
+        out = _fill(_lib.MtrssmOutputs(), "feature prior_probs_h prior_probs_l post_probs_h post_probs_l saved".split(),
+                    (feature, prior_h, prior_l, post_h, post_l, saved))
+        up = _fill(
+            _lib.MtrssmUpstream(),
+            "d_feature d_prior_probs_h d_prior_probs_l d_post_probs_h d_post_probs_l d_prior_stoch_h d_prior_stoch_l d_kl_l d_kl_h".split(),
+            tuple(_c(t) for t in (d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h)),
+        )
+        up.kl_wq, up.kl_wp = kl_wq, kl_wp
+        gin = _fill(_lib.MtrssmInputGrads(),
+                    ["d_actions", "d_embed_a", "d_embed_v", *("d_" + n for n in _MT_STATE), "dpre"],
+                    (d_actions, d_ea, d_ev, *d_state, dpre))
+        _lib.call("rssm_mtrssm_rollout_bwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out, up, gin, gw)
+        return [flat, d_actions, d_ea, d_ev, *d_state]  # flat = all weight grads, split by the caller
 
 
 @mtrssm_rollout_bwd_op.register_fake
@@ -441,17 +465,18 @@ def mtrssm_rollout(
 @torch.library.custom_op("mtrssm_b200::mtrssm_imagine", mutates_args=())
 def mtrssm_imagine_op(weights: Sequence[Tensor], actions: Tensor, state: Sequence[Tensor], u_l: Tensor, u_h: Tensor,
                       KL: int, KH: int, l_tau: float, h_tau: float, precision: int) -> List[Tensor]:
-    B, T, _ = actions.shape
-    dev = actions.device
-    e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
-    feature, hidden_h, hidden_l = e(B, T, 96), e(B, T, 32), e(B, T, 32)
-    probs_h, probs_l = e(B, T, 16 // KH, KH), e(B, T, 16 // KL, KL)
-    w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
-    inp = _fill(_lib.MtrssmInputs(), ["actions", *_MT_STATE, "u_prior_l", "u_prior_h"], (actions, *state, u_l, u_h))
-    out = _fill(_lib.MtrssmOutputs(), "feature hidden_h hidden_l prior_probs_h prior_probs_l".split(),
-                (feature, hidden_h, hidden_l, probs_h, probs_l))
-    _lib.call("rssm_mtrssm_imagine_fwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out)
-    return [feature, hidden_h, hidden_l, probs_h, probs_l]
+    with _on_device(actions, weights, state, u_l, u_h):
+        B, T, _ = actions.shape
+        dev = actions.device
+        e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
+        feature, hidden_h, hidden_l = e(B, T, 96), e(B, T, 32), e(B, T, 32)
+        probs_h, probs_l = e(B, T, 16 // KH, KH), e(B, T, 16 // KL, KL)
+        w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
+        inp = _fill(_lib.MtrssmInputs(), ["actions", *_MT_STATE, "u_prior_l", "u_prior_h"], (actions, *state, u_l, u_h))
+        out = _fill(_lib.MtrssmOutputs(), "feature hidden_h hidden_l prior_probs_h prior_probs_l".split(),
+                    (feature, hidden_h, hidden_l, probs_h, probs_l))
+        _lib.call("rssm_mtrssm_imagine_fwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out)
+        return [feature, hidden_h, hidden_l, probs_h, probs_l]
 
 
 @mtrssm_imagine_op.register_fake

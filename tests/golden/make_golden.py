@@ -20,7 +20,12 @@ of the third-party stand-ins in `ref_shims.py` (the only restated pieces: A1..A7
 Encoders/decoders: `cnn.Encoder/Decoder` are absent; shape-compatible stand-ins (A7) are used and
 their outputs are recorded, so the fixtures do not depend on them.
 
-Outputs: `tests/golden/mrssm_default.pt`, `tests/golden/mtrssm_default.pt` (a few hundred KB).
+Outputs: `tests/golden/mrssm_default.pt`, `tests/golden/mtrssm_default.pt` (B = 5, T = 7; a few hundred KB),
+`mrssm_cfg1.pt`, `mtrssm_cfg2.pt` (the batch and sequence length of the two `default.yaml`s, BASELINE.json configs[0] and [1]:
+B = 8, T = 30 -- `mopoe_mrssm/configs/default.yaml:162,180-182`, `mopoe_mmtrssm/configs/default.yaml:209,227-229`; the
+observation batch is regenerated from its seed by `tests/helpers.golden_batch` and checked against a stored checksum) and
+`rssm_unimodal.pt` (`BaseRSSM.rollout_representation`, `models/core.py:137-168`, reached through a minimal
+concrete subclass of the reference's own `BaseRSSM` -- neither shipped model calls it, both override it).
 """
 
 from __future__ import annotations
@@ -142,7 +147,14 @@ def build_mtrssm(ref) -> nn.Module:  # noqa: ANN001
     )
 
 
-def golden_mrssm(ref, B: int, T: int, Ti: int) -> dict:  # noqa: ANN001
+def pack_batch(batch: tuple[Tensor, ...], seed: int, compact: bool) -> dict:
+    """Small fixtures keep the batch; the default.yaml-sized ones keep its seed and a checksum (synth_batch is deterministic)."""
+    if not compact:
+        return {"batch": tuple(t.clone() for t in batch)}
+    return {"batch_seed": seed, "batch_checksum": [float(t.double().sum()) for t in batch]}
+
+
+def golden_mrssm(ref, B: int, T: int, Ti: int, compact: bool = False) -> dict:  # noqa: ANN001
     model = build_mrssm(ref)
     batch = synth_batch(B, T, seed=1234)
     obs = model.get_observations_from_batch(batch)
@@ -196,7 +208,7 @@ def golden_mrssm(ref, B: int, T: int, Ti: int) -> dict:  # noqa: ANN001
     return {
         "full_state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
         "full_grads": full_grads,
-        "batch": tuple(t.clone() for t in batch),
+        **pack_batch(batch, 1234, compact),
         "dims": dict(B=B, T=T, Ti=Ti, A=6, E=E, D=32, H=32, C=4, K=4, kl_coeff=1.0, use_kl_balancing=True),
         "params": {k: v.detach().clone() for k, v in params.items()},
         "inputs": {
@@ -237,7 +249,7 @@ def golden_mrssm(ref, B: int, T: int, Ti: int) -> dict:  # noqa: ANN001
     }
 
 
-def golden_mtrssm(ref, B: int, T: int, Ti: int) -> dict:  # noqa: ANN001
+def golden_mtrssm(ref, B: int, T: int, Ti: int, compact: bool = False) -> dict:  # noqa: ANN001
     model = build_mtrssm(ref)
     batch = synth_batch(B, T, seed=1234)
     obs = model.get_observations_from_batch(batch)
@@ -298,7 +310,7 @@ def golden_mtrssm(ref, B: int, T: int, Ti: int) -> dict:  # noqa: ANN001
     return {
         "full_state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
         "full_grads": full_grads,
-        "batch": tuple(t.clone() for t in batch),
+        **pack_batch(batch, 1234, compact),
         "dims": dict(
             B=B, T=T, Ti=Ti, A=6, E=E, HD=32, LD=32, HR=32, HH=32, CL=4, KL=4, CH=8, KH=2,
             l_tau=2.0, h_tau=4.0, kl_coeff=1.0, w_kl_h=1.0, use_kl_balancing=True,
@@ -364,6 +376,95 @@ def golden_mtrssm(ref, B: int, T: int, Ti: int) -> dict:  # noqa: ANN001
     }
 
 
+def golden_unimodal(ref, B: int, T: int, Ti: int) -> dict:  # noqa: ANN001
+    """the reference's OWN `BaseRSSM.rollout_representation` / `initial_state` / `shared_step` /
+    `rollout_transition` (models/core.py:121-221), reached through the smallest concrete subclass: one modality (the audio
+    tensors of the batch), the hooks filled in the way MoPoE_MRSSM fills them (mopoe_mrssm/core.py:165-182,262-355)."""
+    torch.manual_seed(42)
+
+    class Unimodal(ref.core.BaseRSSM):
+        def __init__(self, *, encoder: nn.Module, decoder: nn.Module, **kw) -> None:  # noqa: ANN003
+            super().__init__(**kw)
+            self.encoder, self.decoder = encoder, decoder
+
+        def encode_observation(self, observation: Tensor) -> Tensor:
+            return self.encoder(observation)
+
+        def decode_state(self, state) -> dict[str, Tensor]:  # noqa: ANN001
+            return {"recon": self.decoder(state.feature)}
+
+        def compute_reconstruction_loss(self, reconstructions, targets) -> dict[str, Tensor]:  # noqa: ANN001
+            return {"recon": ref.objective.likelihood(prediction=reconstructions["recon"], target=targets["recon"], event_ndims=3)}
+
+        def get_observations_from_batch(self, batch):  # noqa: ANN001, ANN201
+            return batch[1]
+
+        def get_initial_observation(self, observations):  # noqa: ANN001, ANN201
+            return observations[:, 0]
+
+        def get_targets_from_batch(self, batch):  # noqa: ANN001, ANN201
+            return {"recon": batch[4]}
+
+    dist = [4, 4]
+    model = Unimodal(
+        representation=ref.networks.Representation(deterministic_size=32, hidden_size=32, obs_embed_size=E, distribution_config=dist, activation_name="ELU"),
+        transition=ref.networks.Transition(deterministic_size=32, hidden_size=32, action_size=6, distribution_config=dist, activation_name="ELU"),
+        init_proj=MLP(in_features=E, out_features=32, num_cells=200, depth=1), kl_coeff=1, use_kl_balancing=True,
+        encoder=RecEncoder(), decoder=Decoder(48),
+    )
+    batch = synth_batch(B, T, seed=1234)
+    NOISE.reset(4321)
+    loss_ref = model.shared_step(batch)
+    noise_log = list(NOISE.log)
+
+    model.zero_grad()
+    model.encoder.outputs.clear()
+    NOISE.reset(0)
+    NOISE.forced.extend(noise_log)
+    obs = model.get_observations_from_batch(batch)
+    init = model.initial_state(model.get_initial_observation(obs))
+    init.deter.retain_grad()
+    init.stoch.retain_grad()
+    post, prior = model.rollout_representation(actions=batch[0], observations=obs, prev_state=init)  # core.py:137-168
+    post.feature.retain_grad()
+    loss = model.compute_reconstruction_loss(model.decode_state(post), model.get_targets_from_batch(batch))
+    from distribution_extension import kl_divergence
+
+    kl = kl_divergence(q=post.distribution.independent(1), p=prior.distribution.independent(1), use_balancing=True).mul(model.kl_coeff)
+    total = loss["recon"] + kl
+    assert torch.equal(total, loss_ref["loss"]), (total, loss_ref["loss"])
+    total.backward()
+    # noise order: initial z0, then per step the prior State (networks.py:173) and the posterior State (networks.py:84)
+    assert len(noise_log) == 1 + 2 * T
+    u_prior = torch.stack([noise_log[1 + 2 * t] for t in range(T)], 1)
+    u_post = torch.stack([noise_log[2 + 2 * t] for t in range(T)], 1)
+    embed = model.encoder.outputs[1]
+    params = rollout_params(model, ("transition.", "representation."))
+    with torch.no_grad():
+        NOISE.reset(777)
+        act_im = synth_batch(B, Ti, seed=99)[0]
+        imag = model.rollout_transition(actions=act_im, prev_state=post[:, -1])  # core.py:170-185
+        u_imag = torch.stack(list(NOISE.log), 1)
+    return {
+        "full_state_dict": {k: v.detach().clone() for k, v in model.state_dict().items()},
+        "full_grads": {k: (torch.zeros_like(v) if v.grad is None else v.grad.clone()) for k, v in model.named_parameters()},
+        "batch": tuple(t.clone() for t in batch),
+        "dims": dict(B=B, T=T, Ti=Ti, A=6, E=E, D=32, H=32, C=4, K=4, kl_coeff=1.0, use_kl_balancing=True),
+        "params": {k: v.detach().clone() for k, v in params.items()},
+        "inputs": {"actions": batch[0].clone(), "embed": embed.detach().clone(), "h0": init.deter.detach().clone(),
+                   "z0": init.stoch.detach().clone(), "u_z0": noise_log[0], "u_prior": u_prior, "u_post": u_post},
+        "outputs": {"deter": post.deter.detach().clone(), "post_probs": post.distribution.probs.detach().clone(),
+                    "post_stoch": post.stoch.detach().clone(), "post_feature": post.feature.detach().clone(),
+                    "prior_probs": prior.distribution.probs.detach().clone(), "prior_stoch": prior.stoch.detach().clone(),
+                    "prior_deter": prior.deter.detach().clone()},
+        "loss": {k: v.detach().clone() for k, v in loss_ref.items()},
+        "upstream": {"d_post_feature": post.feature.grad.clone()},
+        "grads": {"params": grads_of(params), "embed": embed.grad.clone(), "h0": init.deter.grad.clone(), "z0": init.stoch.grad.clone()},
+        "imagine": {"actions": act_im, "u": u_imag, "deter": imag.deter.clone(), "probs": imag.distribution.probs.clone(),
+                    "stoch": imag.stoch.clone()},
+    }
+
+
 def main() -> None:
     torch.set_num_threads(1)
     torch.use_deterministic_algorithms(True)
@@ -372,7 +473,14 @@ def main() -> None:
     torch.save(g1, HERE / "mrssm_default.pt")
     g2 = golden_mtrssm(ref, B=5, T=7, Ti=4)
     torch.save(g2, HERE / "mtrssm_default.pt")
-    for name, g in (("mrssm", g1), ("mtrssm", g2)):
+    # the two default.yaml configurations at their own batch size and sequence length (BASELINE.json configs[0], configs[1])
+    g3 = golden_mrssm(ref, B=8, T=30, Ti=10, compact=True)
+    torch.save(g3, HERE / "mrssm_cfg1.pt")
+    g4 = golden_mtrssm(ref, B=8, T=30, Ti=10, compact=True)
+    torch.save(g4, HERE / "mtrssm_cfg2.pt")
+    g5 = golden_unimodal(ref, B=6, T=9, Ti=4)
+    torch.save(g5, HERE / "rssm_unimodal.pt")
+    for name, g in (("mrssm", g1), ("mtrssm", g2), ("mrssm cfg1", g3), ("mtrssm cfg2", g4), ("unimodal", g5)):
         print(name, {k: float(v) for k, v in g["loss"].items()})
 
 

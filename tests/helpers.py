@@ -130,6 +130,28 @@ def mtrssm_safe_uniforms(params, inp, dims, eps: float) -> None:
     raise AssertionError("could not find knife-edge-free uniforms")
 
 
+def golden_batch(g: dict) -> tuple[torch.Tensor, ...]:
+    """The 6-tuple batch of a golden fixture.  The default.yaml-sized fixtures store the seed of make_golden.synth_batch (same
+    generator calls here) plus a checksum instead of 2 x 4 MB of observations."""
+    if "batch" in g:
+        return tuple(g["batch"])
+    B, T = g["dims"]["B"], g["dims"]["T"]
+    gen = torch.Generator().manual_seed(g["batch_seed"])
+    speaker = torch.randint(0, 6, (B,), generator=gen)
+    act = torch.nn.functional.one_hot(speaker, 6).float()[:, None, :].expand(B, T, 6)
+    act_in = act + 0.1 * torch.randn(B, T, 6, generator=gen)
+    audio = torch.rand(B, T, 1, 32, 32, generator=gen) * 2 - 1
+    vision = torch.rand(B, T, 1, 32, 32, generator=gen) * 2 - 1
+    batch = (act_in, audio, vision, act.clone(), audio.clone(), vision.clone())
+    assert [float(t.double().sum()) for t in batch] == g["batch_checksum"], "golden batch does not regenerate bit-exactly"
+    assert torch.equal(batch[0], g["inputs"]["actions"])
+    return batch
+
+
+MRSSM_GOLDEN = ("mrssm_default.pt", "mrssm_cfg1.pt")   # B=5,T=7 and default.yaml's own B=8,T=30 (BASELINE.json configs[0])
+MTRSSM_GOLDEN = ("mtrssm_default.pt", "mtrssm_cfg2.pt")  # B=5,T=7 and default.yaml's own B=8,T=30 (BASELINE.json configs[1])
+
+
 class Report:
     """Collects per-tensor errors so one GPU run shows every mismatch, then asserts."""
 

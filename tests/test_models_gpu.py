@@ -19,15 +19,16 @@ def _tol(ref):
     return dict(rtol=1e-4, atol=2e-5 * max(float(ref.abs().max()), 1e-3))
 
 
-def test_mrssm_shared_step_matches_reference_losses_and_all_gradients(golden_dir):
+@pytest.mark.parametrize("fixture", H.MRSSM_GOLDEN)
+def test_mrssm_shared_step_matches_reference_losses_and_all_gradients(golden_dir, fixture):
     """Drop-in check: same weights (state_dict), same batch, same noise -> same loss dict and the same gradient on
     EVERY parameter (encoders, decoders, init_proj and the rollout), including the initial_state paths."""
-    g = torch.load(golden_dir / "mrssm_default.pt")
+    g = torch.load(golden_dir / fixture)
     model = H.build_mrssm_model()
     model.load_state_dict(g["full_state_dict"], strict=True)
     model.cuda()
     inp = g["inputs"]
-    batch = tuple(t.cuda() for t in g["batch"])
+    batch = tuple(t.cuda() for t in H.golden_batch(g))
     # product noise order: initial_state draw, then the rollout's u_post, u_prior (mopoe_mrssm.py)
     with H.RandQueue([inp["u_z0"], inp["u_post"], inp["u_prior"]]) as q:
         loss = model.shared_step(batch)
@@ -41,13 +42,14 @@ def test_mrssm_shared_step_matches_reference_losses_and_all_gradients(golden_dir
     rep.finish()
 
 
-def test_mtrssm_shared_step_matches_reference_losses_and_all_gradients(golden_dir):
-    g = torch.load(golden_dir / "mtrssm_default.pt")
+@pytest.mark.parametrize("fixture", H.MTRSSM_GOLDEN)
+def test_mtrssm_shared_step_matches_reference_losses_and_all_gradients(golden_dir, fixture):
+    g = torch.load(golden_dir / fixture)
     model = H.build_mtrssm_model()
     model.load_state_dict(g["full_state_dict"], strict=True)
     model.cuda()
     inp = g["inputs"]
-    batch = tuple(t.cuda() for t in g["batch"])
+    batch = tuple(t.cuda() for t in H.golden_batch(g))
     # initial_state draws h then l (mmtrssm/state.py:48-49); the rollout draws post_l, post_h, prior_l, prior_h
     noise = [inp["u_h0"], inp["u_l0"], inp["u_post_l"], inp["u_post_h"], inp["u_prior_l"], inp["u_prior_h"]]
     with H.RandQueue(noise) as q:
@@ -71,7 +73,8 @@ def test_mtrssm_shared_step_matches_reference_losses_and_all_gradients(golden_di
 
 def test_rollout_transition_matches_reference_imagination(golden_dir):
     """callbacks' usage (mrssm/callback.py:184-188): imagination from posterior[:, -1]."""
-    for name, build in (("mrssm_default.pt", H.build_mrssm_model), ("mtrssm_default.pt", H.build_mtrssm_model)):
+    for name, build in (("mrssm_default.pt", H.build_mrssm_model), ("mtrssm_default.pt", H.build_mtrssm_model),
+                        ("mrssm_cfg1.pt", H.build_mrssm_model), ("mtrssm_cfg2.pt", H.build_mtrssm_model)):
         g = torch.load(golden_dir / name)
         model = build()
         model.load_state_dict(g["full_state_dict"], strict=True)
@@ -303,3 +306,73 @@ def test_base_rssm_unimodal_rollout_uses_the_fused_kernel_and_matches_the_module
     head = m.representation.rnn_to_post_projector
     assert head[0].weight.grad is not None and float(head[0].weight.grad.abs().max()) > 0
     assert m.transition.rnn_cell.weight_hh.grad is not None
+
+
+def test_base_rssm_shared_step_matches_the_reference_base_class(golden_dir):
+    """SURVEY §8 row a6, model level: a concrete subclass of the PRODUCT's BaseRSSM against the same subclass of the REFERENCE's
+    BaseRSSM (tests/golden/make_golden.golden_unimodal ran the reference's own initial_state / rollout_representation /
+    shared_step, models/core.py:121-221): same state_dict, batch and noise -> same loss dict and the same gradient on every
+    parameter; the rollout is ONE fused launch."""
+    from multimodal_mtrssm_b200 import _lib
+    from multimodal_mtrssm_b200.core import BaseRSSM
+    from multimodal_mtrssm_b200.mlp import MLP
+    from multimodal_mtrssm_b200.networks import Representation, Transition
+    from multimodal_mtrssm_b200.objective import likelihood
+
+    class Unimodal(BaseRSSM):
+        def __init__(self, *, encoder, decoder, **kw):
+            super().__init__(**kw)
+            self.encoder, self.decoder = encoder, decoder
+
+        def encode_observation(self, observation):
+            return self.encoder(observation)
+
+        def decode_state(self, state):
+            return {"recon": self.decoder(state.feature)}
+
+        def compute_reconstruction_loss(self, reconstructions, targets):
+            return {"recon": likelihood(prediction=reconstructions["recon"], target=targets["recon"], event_ndims=3)}
+
+        def get_observations_from_batch(self, batch):
+            return batch[1]
+
+        def get_initial_observation(self, observations):
+            return observations[:, 0]
+
+        def get_targets_from_batch(self, batch):
+            return {"recon": batch[4]}
+
+    g = torch.load(golden_dir / "rssm_unimodal.pt")
+    kw = dict(deterministic_size=32, hidden_size=32, distribution_config=[4, 4], activation_name="ELU")
+    model = Unimodal(representation=Representation(obs_embed_size=64, **kw), transition=Transition(action_size=6, **kw),
+                     init_proj=MLP(in_features=64, out_features=32, num_cells=200, depth=1), kl_coeff=1, use_kl_balancing=True,
+                     encoder=H.LinEncoder(), decoder=H.LinDecoder(48))
+    model.load_state_dict(g["full_state_dict"], strict=True)
+    model.cuda()
+    inp = g["inputs"]
+    batch = tuple(t.cuda() for t in g["batch"])
+    n0 = _lib.launch_count()
+    with H.RandQueue([inp["u_z0"], inp["u_post"], inp["u_prior"]]) as q:
+        loss = model.shared_step(batch)
+        assert not q.values
+    assert _lib.launch_count() == n0 + 2  # the fused rollout + the fused likelihood
+    rep = H.Report("BaseRSSM (unimodal) shared_step vs the reference's BaseRSSM.shared_step")
+    for k, v in g["loss"].items():
+        rep.check(k, loss[k], v, rtol=1e-5, atol=1e-6)
+    loss["loss"].backward()
+    for k, p in model.named_parameters():
+        rep.check("d " + k, p.grad if p.grad is not None else torch.zeros_like(p), g["full_grads"][k], **_tol(g["full_grads"][k]))
+    rep.finish()
+    # imagination through BaseRSSM.rollout_transition (core.py:170-185): one fused launch as well
+    from multimodal_mtrssm_b200.distribution import Distribution
+    from multimodal_mtrssm_b200.state import State
+
+    out, im = g["outputs"], g["imagine"]
+    prev = State(deter=out["deter"][:, -1].cuda(), stoch=out["post_stoch"][:, -1].cuda(), distribution=Distribution(out["post_probs"][:, -1].cuda()))
+    n0 = _lib.launch_count()
+    with torch.no_grad(), H.RandQueue([im["u"]]):
+        got = BaseRSSM.rollout_transition(model, actions=im["actions"].cuda(), prev_state=prev)
+    assert _lib.launch_count() == n0 + 1
+    torch.testing.assert_close(got.deter.cpu(), im["deter"], rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(got.stoch.cpu(), im["stoch"], rtol=1e-5, atol=2e-6)
+    torch.testing.assert_close(got.distribution.probs.cpu(), im["probs"], rtol=1e-5, atol=2e-6)

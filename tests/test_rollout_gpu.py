@@ -157,10 +157,12 @@ def test_mrssm_imagine_fp32(ops):
     rep.finish()
 
 
-def test_mrssm_golden_fixture(ops, golden_dir):
-    """The CUDA path against vectors produced by the reference's own code (tests/golden/make_golden.py)."""
+@pytest.mark.parametrize("fixture", H.MRSSM_GOLDEN)
+def test_mrssm_golden_fixture(ops, golden_dir, fixture):
+    """The CUDA path against vectors produced by the reference's own code (tests/golden/make_golden.py): B = 5, T = 7 and
+    default.yaml's own B = 8, T = 30 (BASELINE.json configs[0])."""
     R, P = ops
-    g = torch.load(golden_dir / "mrssm_default.pt")
+    g = torch.load(golden_dir / fixture)
     dims, inp, out = g["dims"], g["inputs"], g["outputs"]
     w = {k: v.cuda().requires_grad_(True) for k, v in g["params"].items() if not k.startswith("representation.")}
     x = {k: inp[k].cuda().requires_grad_(True) for k in ("embed_a", "embed_v", "h0", "z0")}
@@ -262,6 +264,44 @@ def test_mrssm_unimodal_matches_oracle(ops, B, T, K, precision):
     rep.finish()
     assert float(x["embed_v"].grad.abs().max()) == 0.0
     assert all(float(w[k].grad.abs().max()) == 0.0 for k in w if k.startswith("vision_representation"))
+
+
+def test_unimodal_golden_fixture(ops, golden_dir):
+    """SURVEY §8 row a6 against the reference's OWN BaseRSSM.rollout_representation / rollout_transition (models/core.py:137-185,
+    run through a concrete subclass by make_golden.golden_unimodal): states, KL, every gradient, imagination."""
+    R, P = ops
+    g = torch.load(golden_dir / "rssm_unimodal.pt")
+    dims, inp, out = g["dims"], g["inputs"], g["outputs"]
+    ren = lambda k: k.replace("representation.", "audio_representation.", 1) if k.startswith("representation.") else k  # noqa: E731
+    w = {ren(k): v.cuda().requires_grad_(True) for k, v in g["params"].items()}
+    for k in list(w):  # the unused vision slot
+        if k.startswith("audio_representation."):
+            w[k.replace("audio_", "vision_", 1)] = w[k].detach().clone().requires_grad_(True)
+    x = {"embed_a": inp["embed"].cuda().requires_grad_(True), "h0": inp["h0"].cuda().requires_grad_(True),
+         "z0": inp["z0"].cuda().requires_grad_(True)}
+    res = R.mrssm_rollout(P.mrssm_weight_list(w), actions=inp["actions"].cuda(), embed_v=inp["embed"].cuda(), u_post=inp["u_post"].cuda(),
+                          u_prior=inp["u_prior"].cuda(), class_size=dims["K"], unimodal=True, **x)
+    rep = H.Report("unimodal golden (reference BaseRSSM) vs CUDA")
+    rep.check("post_feature", res["feature"], out["post_feature"], **FWD_TOL)
+    rep.check("post_probs", res["post_probs"], out["post_probs"], **FWD_TOL)
+    rep.check("prior_probs", res["prior_probs"], out["prior_probs"], **FWD_TOL)
+    rep.check("prior_stoch", res["prior_stoch"], out["prior_stoch"], **FWD_TOL)
+    kl = res["kl"].mean() * dims["kl_coeff"]
+    rep.check("kl", kl, g["loss"]["kl"], rtol=1e-5, atol=1e-7)
+    ((res["feature"] * g["upstream"]["d_post_feature"].cuda()).sum() + kl).backward()
+    rep.check("d embed", x["embed_a"].grad, g["grads"]["embed"], **grad_tol(g["grads"]["embed"]))
+    rep.check("d z0", x["z0"].grad, g["grads"]["z0"], **grad_tol(g["grads"]["z0"]))
+    for k, ref in g["grads"]["params"].items():
+        if k.startswith("transition.rnn_to_prior_projector"):  # golden adds the initial_state path through z0 (core.py:133-135)
+            continue
+        rep.check("d " + k, w[ren(k)].grad, ref, **grad_tol(ref))
+    im = g["imagine"]
+    got = R.mrssm_imagine(P.mrssm_weight_list({k: v.detach() for k, v in w.items()}), actions=im["actions"].cuda(),
+                          h0=out["deter"][:, -1].cuda(), z0=out["post_stoch"][:, -1].round().cuda(), u=im["u"].cuda(), class_size=dims["K"])
+    rep.check("imagine deter", got["feature"][..., :32], im["deter"], **FWD_TOL)
+    rep.check("imagine stoch", got["feature"][..., 32:], im["stoch"], **FWD_TOL)
+    rep.check("imagine probs", got["probs"], im["probs"], **FWD_TOL)
+    rep.finish()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -379,9 +419,11 @@ def test_mtrssm_imagine_fp32(ops):
     rep.finish()
 
 
-def test_mtrssm_golden_fixture(ops, golden_dir):
+@pytest.mark.parametrize("fixture", H.MTRSSM_GOLDEN)
+def test_mtrssm_golden_fixture(ops, golden_dir, fixture):
+    """B = 5, T = 7 and default.yaml's own B = 8, T = 30 (BASELINE.json configs[1])."""
     R, P = ops
-    g = torch.load(golden_dir / "mtrssm_default.pt")
+    g = torch.load(golden_dir / fixture)
     dims, inp, out = g["dims"], g["inputs"], g["outputs"]
     w = {k: v.cuda().requires_grad_(True) for k, v in g["params"].items()}
     names = ("embed_a", "embed_v", "deter_h0", "deter_l0", "hidden_h0", "hidden_l0", "stoch_h0", "stoch_l0")
