@@ -87,26 +87,31 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
     float* bias = reinterpret_cast<float*>(W + (size_t)NS * mr::FWD_TILES * 32);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int A = p.A;
-    {
+    __shared__ PackTable tb;
+    if (tid == 0) {
         using namespace mr;
         const int ldasp = A + 16;
-        pack_weight<NS, false>(wblock<NS>(W, ASP1Z), p.w.asp_w1, ldasp, 0, A, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, false>(wblock<NS>(W, ASP1A), p.w.asp_w1, ldasp, 0, 0, A, 32, 1, 4, tid, nthr);
-        pack_weight<NS, false>(wblock<NS>(W, ASP2), p.w.asp_w2, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, false>(wblock<NS>(W, IH_RZ), p.w.w_ih, 32, 0, 0, 32, 64, 2, 8, tid, nthr);
-        pack_weight<NS, false>(wblock<NS>(W, HH_RZ), p.w.w_hh, 32, 0, 0, 32, 64, 2, 8, tid, nthr);
-        pack_weight<NS, false>(wblock<NS>(W, IH_N), p.w.w_ih, 32, 64, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, false>(wblock<NS>(W, HH_N), p.w.w_hh, 32, 64, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, false>(wblock<NS>(W, P1), p.w.pr_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, false>(wblock<NS>(W, P2), p.w.pr_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
+        tb.nblocks = tb.ntiles = 0;
+        pack_add(tb, false, wblock<NS>(W, ASP1Z), p.w.asp_w1, ldasp, 0, A, 16, 32, 1, 4);
+        pack_add(tb, false, wblock<NS>(W, ASP1A), p.w.asp_w1, ldasp, 0, 0, A, 32, 1, 4);
+        pack_add(tb, false, wblock<NS>(W, ASP2), p.w.asp_w2, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, false, wblock<NS>(W, IH_RZ), p.w.w_ih, 32, 0, 0, 32, 64, 2, 8);
+        pack_add(tb, false, wblock<NS>(W, HH_RZ), p.w.w_hh, 32, 0, 0, 32, 64, 2, 8);
+        pack_add(tb, false, wblock<NS>(W, IH_N), p.w.w_ih, 32, 64, 0, 32, 32, 2, 4);
+        pack_add(tb, false, wblock<NS>(W, HH_N), p.w.w_hh, 32, 64, 0, 32, 32, 2, 4);
+        pack_add(tb, false, wblock<NS>(W, P1), p.w.pr_w1, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, false, wblock<NS>(W, P2), p.w.pr_w2, 32, 0, 0, 32, 16, 2, 2);
         if (!IMAGINE) {
-            pack_weight<NS, false>(wblock<NS>(W, A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-            pack_weight<NS, false>(wblock<NS>(W, A1E), p.w.au_w1, 96, 0, 32, 64, 32, 4, 4, tid, nthr);
-            pack_weight<NS, false>(wblock<NS>(W, A2), p.w.au_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
-            pack_weight<NS, false>(wblock<NS>(W, V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-            pack_weight<NS, false>(wblock<NS>(W, V1E), p.w.vi_w1, 96, 0, 32, 64, 32, 4, 4, tid, nthr);
-            pack_weight<NS, false>(wblock<NS>(W, V2), p.w.vi_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
+            pack_add(tb, false, wblock<NS>(W, A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4);
+            pack_add(tb, false, wblock<NS>(W, A1E), p.w.au_w1, 96, 0, 32, 64, 32, 4, 4);
+            pack_add(tb, false, wblock<NS>(W, A2), p.w.au_w2, 32, 0, 0, 32, 16, 2, 2);
+            pack_add(tb, false, wblock<NS>(W, V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4);
+            pack_add(tb, false, wblock<NS>(W, V1E), p.w.vi_w1, 96, 0, 32, 64, 32, 4, 4);
+            pack_add(tb, false, wblock<NS>(W, V2), p.w.vi_w2, 32, 0, 0, 32, 16, 2, 2);
         }
+    }
+    {  // the biases, while thread 0 fills the table
+        using namespace mr;
         for (int i = tid; i < FWD_BIAS; i += nthr) {
             float v;
             if (i < B_ASP2) v = p.w.asp_b1[i - B_ASP1];
@@ -124,6 +129,8 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
             bias[i] = v;
         }
     }
+    __syncthreads();
+    pack_run<NS>(tb, tid, nthr);
     __syncthreads();
 
     const int lane = tid & 31, warp = tid >> 5;
@@ -305,27 +312,31 @@ __global__ void __launch_bounds__(128) mrssm_bwd_kernel(const MrssmBwdArgs p) {
     uint2* W = reinterpret_cast<uint2*>(smem_raw);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int A = p.A;
-    {
+    __shared__ PackTable tb;
+    if (tid == 0) {
         using namespace mr;
         const int ldasp = A + 16;
-        pack_weight<NS, true>(wblock<NS>(W, T_A2), p.w.au_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_V2), p.w.vi_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_P2), p.w.pr_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_P1), p.w.pr_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_A1E), p.w.au_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_V1E), p.w.vi_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_IH_R), p.w.w_ih, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_IH_Z), p.w.w_ih, 32, 32, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_IH_N), p.w.w_ih, 32, 64, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_HH_R), p.w.w_hh, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_HH_Z), p.w.w_hh, 32, 32, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_HH_N), p.w.w_hh, 32, 64, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_ASP2), p.w.asp_w2, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_ASP1Z), p.w.asp_w1, ldasp, 0, A, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblock<NS>(W, T_ASP1A), p.w.asp_w1, ldasp, 0, 0, 32, A, 2, 2, tid, nthr);
+        tb.nblocks = tb.ntiles = 0;
+        pack_add(tb, true, wblock<NS>(W, T_A2), p.w.au_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblock<NS>(W, T_V2), p.w.vi_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblock<NS>(W, T_P2), p.w.pr_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblock<NS>(W, T_A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblock<NS>(W, T_V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblock<NS>(W, T_P1), p.w.pr_w1, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblock<NS>(W, T_A1E), p.w.au_w1, 96, 0, 32, 32, 64, 2, 8);
+        pack_add(tb, true, wblock<NS>(W, T_V1E), p.w.vi_w1, 96, 0, 32, 32, 64, 2, 8);
+        pack_add(tb, true, wblock<NS>(W, T_IH_R), p.w.w_ih, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblock<NS>(W, T_IH_Z), p.w.w_ih, 32, 32, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblock<NS>(W, T_IH_N), p.w.w_ih, 32, 64, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblock<NS>(W, T_HH_R), p.w.w_hh, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblock<NS>(W, T_HH_Z), p.w.w_hh, 32, 32, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblock<NS>(W, T_HH_N), p.w.w_hh, 32, 64, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblock<NS>(W, T_ASP2), p.w.asp_w2, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblock<NS>(W, T_ASP1Z), p.w.asp_w1, ldasp, 0, A, 32, 16, 2, 2);
+        pack_add(tb, true, wblock<NS>(W, T_ASP1A), p.w.asp_w1, ldasp, 0, 0, 32, A, 2, 2);
     }
+    __syncthreads();
+    pack_run<NS>(tb, tid, nthr);
     __syncthreads();
 
     const int lane = tid & 31, warp = tid >> 5;

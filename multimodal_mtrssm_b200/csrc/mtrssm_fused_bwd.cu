@@ -12,7 +12,7 @@
 // with one atomicAdd per weight element per CTA.  The tensor work is ~1 % of the tcgen05 pipe; the point is that the
 // accumulators cost no registers and the operands no HBM round trip.
 //
-// Operand layout (validated by scratch/umma_probe.cu, profiles/r1_umma_probe.txt): MN-major, no swizzle,
+// Operand layout (validated by profiles/src/umma_probe.cu, profiles/r1_umma_probe.txt): MN-major, no swizzle,
 //     element (column c, row k) of a 16-row tile  ->  (c / 8) * 256 + (k / 8) * 128 + (k % 8) * 16 + (c % 8) * 2   bytes,
 // i.e. "chunks" of 8 columns (256 B); descriptor LBO = 128 (k-group stride), SBO = 256 (chunk stride).  An MMA's M (or
 // N) window is any run of consecutive chunks, so layers address sub-ranges of one staged row image directly.
@@ -136,6 +136,23 @@ __device__ __forceinline__ void head_bwd_op(const float (&dlogit)[2][4], const u
     to_afrag<1, 2>(f1, dhid);
 }
 
+// the same with ELU'(hidden) precomputed by the caller (mod warp: off the recurrence's critical section)
+__device__ __forceinline__ void head_bwd_elu(const float (&dlogit)[2][4], const uint2* w2t, const float (&elu_grad)[4][4], unsigned char* dy,
+                                             int y_logit, int y1, AFrag<1, 2>& f1, const Rows& r, int lane) {
+    store_op<2>(dlogit, dy, y_logit, r);
+    AFrag<1, 1> fl;
+    to_afrag<1, 1>(fl, dlogit);
+    float dhid[4][4];
+    zero_c<4>(dhid);
+    gemm<1, 1, 4>(dhid, fl, w2t, lane);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dhid[nt][j] *= elu_grad[nt][j];
+    store_op<4>(dhid, dy, y1, r);
+    to_afrag<1, 2>(f1, dhid);
+}
+
 // =====================================================================================================================
 // Version 2: TWO warps per 16-sequence tile.
 // The single-warp kernel above needs ~46 KB of shared memory per tile, i.e. four tiles = four warps per SM = one warp per
@@ -203,29 +220,33 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
     uint2* W = reinterpret_cast<uint2*>(smem_raw);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int A = p.A;
-    {
+    __shared__ PackTable tb;
+    if (tid == 0) {
         using namespace mt;
         const int ldin = A + 32;
-        pack_weight<NS, true>(wblk<NS>(W, T_A2), p.w.au_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_V2), p.w.vi_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_LP2), p.w.lp_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HP2), p.w.hp_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HQ2), p.w.hq_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_A1E), p.w.au_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_V1E), p.w.vi_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZL), p.w.l_in_w, ldin, 0, A, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_H_IN), p.w.h_in_w, 16, 0, 0, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_A), p.w.l_in_w, ldin, 0, 0, 32, A, 2, 2, tid, nthr);
+        tb.nblocks = tb.ntiles = 0;
+        pack_add(tb, true, wblk<NS>(W, T_A2), p.w.au_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblk<NS>(W, T_V2), p.w.vi_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblk<NS>(W, T_LP2), p.w.lp_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblk<NS>(W, T_HP2), p.w.hp_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblk<NS>(W, T_HQ2), p.w.hq_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblk<NS>(W, T_A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_A1E), p.w.au_w1, 96, 0, 32, 32, 64, 2, 8);
+        pack_add(tb, true, wblk<NS>(W, T_V1E), p.w.vi_w1, 96, 0, 32, 32, 64, 2, 8);
+        pack_add(tb, true, wblk<NS>(W, T_L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_L_IN_ZL), p.w.l_in_w, ldin, 0, A, 32, 16, 2, 2);
+        pack_add(tb, true, wblk<NS>(W, T_L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 32, 16, 2, 2);
+        pack_add(tb, true, wblk<NS>(W, T_H_IN), p.w.h_in_w, 16, 0, 0, 32, 16, 2, 2);
+        pack_add(tb, true, wblk<NS>(W, T_L_IN_A), p.w.l_in_w, ldin, 0, 0, 32, A, 2, 2);
     }
+    __syncthreads();
+    pack_run<NS>(tb, tid, nthr);
     const int lane = tid & 31, warp = tid >> 5, tile = warp >> 1, role = warp & 1;  // role 0 = core, 1 = mod
     unsigned char* my = smem_raw + (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + (size_t)tile * fz2::BYTES;
     // zero the tile's images and exchange buffers once (the two warps of the tile split the range)
@@ -330,23 +351,22 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
                 const float dkl_cur = dkl_next;
                 if (t > 0 && dkl_src != nullptr) dkl_next = dkl_src[dkl_row + t - 1];
+                // ---- everything that does NOT depend on the carried d stoch_l runs BEFORE the hand-over barrier, in the window
+                // where this warp used to idle: the two flat log-softmaxes, the mixture responsibilities, the KL / upstream part of
+                // d post_probs_l, exp(ls) for the log-softmax backward and ELU' of the two hiddens ----------------------------
                 cp_async_wait<1>();  // LA, LV, post_l, prior_l of step t have landed (the rest may still be in flight)
                 __syncwarp();
-                nbar_sync(bar_y);    // d stoch_l of step t is in XDZL
-                float dzl[2][4], q[2][4], pp[2][4], dpp[2][4];
-                xch_load<2>(dzl, xdzl, lane);
-                load_staged<2, true>(q, stPRL, 32, 0, r.g, r.t);
-                load_staged<2, true>(pp, stPRL, 32, 16, r.g, r.t);
-                add_global<2>(dzl, p.d_post_probs_l, iA * 16, iB * 16, r.t);
-                zero_c<2>(dpp);
-                if (p.d_kl_l != nullptr) {
-                    const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 0), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 1)};
-                    kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dzl, dpp);  // the prior half (dpp) belongs to the core warp
-                }
-                float dla[2][4], dlv[2][4];
+                float q[2][4], dzl_pre[2][4], lsa[2][4], lsv[2][4], ra[2][4], rv[2][4];
                 {
-                    float dm[2][4], la[2][4], lv[2][4], lsa[2][4], lsv[2][4], mixed[2][4], ra[2][4], rv[2][4];
-                    softmax_groups_bwd<KL>(q, dzl, dm);
+                    float pp[2][4], dpp[2][4], la[2][4], lv[2][4], mixed[2][4];
+                    load_staged<2, true>(q, stPRL, 32, 0, r.g, r.t);
+                    load_staged<2, true>(pp, stPRL, 32, 16, r.g, r.t);
+                    zero_c<2>(dzl_pre), zero_c<2>(dpp);
+                    add_global<2>(dzl_pre, p.d_post_probs_l, iA * 16, iB * 16, r.t);
+                    if (p.d_kl_l != nullptr) {
+                        const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 0), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 1)};
+                        kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dzl_pre, dpp);  // the prior half (dpp) belongs to the core warp
+                    }
                     load_op<2>(la, svop, mts::LA, r.g, r.t);
                     load_op<2>(lv, svop, mts::LV, r.g, r.t);
                     log_softmax_flat<true>(la, lsa);
@@ -356,42 +376,85 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
+                            lsa[nt][j] = Math<true>::exp(lsa[nt][j]);  // softmax(la), softmax(lv): all the log-softmax backward needs
+                            lsv[nt][j] = Math<true>::exp(lsv[nt][j]);
+                        }
+                }
+                __syncwarp();
+                stage_logits(t - 1);  // LA, LV and the probability rows are in registers: refill them
+                cp_async_wait<1>();   // hiddens of step t have landed (the embedding images were written by this warp itself)
+                __syncwarp();
+                float eluA[4][4], eluV[4][4];  // ELU'(hidden) of the two modality heads
+                load_op<4>(eluA, svop, mts::A_HID, r.g, r.t);
+                load_op<4>(eluV, svop, mts::V_HID, r.g, r.t);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        eluA[nt][j] = elu_grad_from_out(eluA[nt][j]);
+                        eluV[nt][j] = elu_grad_from_out(eluV[nt][j]);
+                    }
+                // ---- the recurrence's critical section: d stoch_l(t) -> ... -> contribution to d deter_l(t) --------------------
+                nbar_sync(bar_y);  // d stoch_l of step t is in XDZL
+                float dla[2][4], dlv[2][4];
+                {
+                    float dzl[2][4], dm[2][4];
+                    xch_load<2>(dzl, xdzl, lane);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) dzl[nt][j] += dzl_pre[nt][j];
+                    softmax_groups_bwd<KL>(q, dzl, dm);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
                             ra[nt][j] *= dm[nt][j];
                             rv[nt][j] *= dm[nt][j];
                         }
-                    log_softmax_flat_bwd<true>(lsa, ra, dla);
-                    log_softmax_flat_bwd<true>(lsv, rv, dlv);
+                    // backward of the flat log-softmax with softmax(x) at hand: dx = dls - softmax(x) * sum(dls)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float sa[2] = {ra[0][2 * h] + ra[0][2 * h + 1], ra[1][2 * h] + ra[1][2 * h + 1]};
+                        float sv[2] = {rv[0][2 * h] + rv[0][2 * h + 1], rv[1][2 * h] + rv[1][2 * h + 1]};
+                        group_reduce<16, false>(sa);
+                        group_reduce<16, false>(sv);
+#pragma unroll
+                        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                dla[nt][2 * h + e] = ra[nt][2 * h + e] - lsa[nt][2 * h + e] * sa[0];
+                                dlv[nt][2 * h + e] = rv[nt][2 * h + e] - lsv[nt][2 * h + e] * sv[0];
+                            }
+                    }
                 }
-                __syncwarp();
-                stage_logits(t - 1);
                 // this warp's dY columns (LA, A1, LV, V1) were last read by the core warp's end-of-step MMAs of step t+1
                 if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
-                cp_async_wait<1>();  // hiddens and embeddings of step t have landed
-                __syncwarp();
-                float ddl[4][4], hid[4][4];
+                float ddl[4][4];
                 zero_c<4>(ddl);
-#pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    AFrag<NS, 2> f1;
-                    load_op<4>(hid, svop, m == 0 ? mts::A_HID : mts::V_HID, r.g, r.t);
-                    head_bwd_op(m == 0 ? dla : dlv, wblk<NS>(W, m == 0 ? mt::T_A2 : mt::T_V2), hid, dy, m == 0 ? fz::Y_LA : fz::Y_LV,
-                                m == 0 ? fz::Y_A1 : fz::Y_V1, f1, r, lane);
-                    gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, m == 0 ? mt::T_A1H : mt::T_V1H), lane);
-                    float de[8][4];
-                    zero_c<8>(de);
-                    gemm<NS, 2, 8>(de, f1, wblk<NS>(W, m == 0 ? mt::T_A1E : mt::T_V1E), lane);
-                    float* dE = m == 0 ? p.d_embed_a : p.d_embed_v;
-                    store_c<8>(de, dE + iA * 64, dE + iB * 64, r);
-                }
+                AFrag<NS, 2> f1a, f1v;
+                head_bwd_elu(dla, wblk<NS>(W, mt::T_A2), eluA, dy, fz::Y_LA, fz::Y_A1, f1a, r, lane);
+                head_bwd_elu(dlv, wblk<NS>(W, mt::T_V2), eluV, dy, fz::Y_LV, fz::Y_V1, f1v, r, lane);
+                gemm<NS, 2, 4>(ddl, f1a, wblk<NS>(W, mt::T_A1H), lane);
+                gemm<NS, 2, 4>(ddl, f1v, wblk<NS>(W, mt::T_V1H), lane);
                 xch_store<4>(ddl, xddl, lane);
                 FZ_FENCE();
+                nbar_arrive(bar_x);  // XDDL and this warp's dY columns are complete (and visible to the async proxy)
+                // ---- off the critical path: this warp's weight-gradient MMAs, the embedding gradients, next step's staging -------
                 __syncwarp();
                 if (FZ_MMA && lane == 0) {
                     umma_acc(tmem + fz2::T_M, s_sv + 12 * fz2::CH, s_dy + (fz::Y_LA / 8) * fz2::CH, 32);
                     umma_acc(tmem + fz2::T_EMB, s_sv + 24 * fz2::CH, s_dy + (fz::Y_A1 / 8) * fz2::CH, 64);
                     umma_commit(&bars[fz2::BAR_M]);
                 }
-                nbar_arrive(bar_x);  // XDDL and this warp's dY columns are complete
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    float de[8][4];
+                    zero_c<8>(de);
+                    gemm<NS, 2, 8>(de, m == 0 ? f1a : f1v, wblk<NS>(W, m == 0 ? mt::T_A1E : mt::T_V1E), lane);
+                    float* dE = m == 0 ? p.d_embed_a : p.d_embed_v;
+                    store_c<8>(de, dE + iA * 64, dE + iB * 64, r);
+                }
                 FZ_WAIT(&bars[fz2::BAR_M], ph_m), ph_m ^= 1;  // own MMAs done: hiddens / embedding images may be rewritten
                 stage_rest(t - 1);
                 embed_prefetch(t - 2);
@@ -535,6 +598,32 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 }
                 FZ_WAIT(&bars[fz2::BAR_E], ph_e), ph_e ^= 1;  // the hiddens may be refilled
                 stage_hid(t - 1);
+                // ---- the higher cell depends on nothing the mod warp produces: all of it runs BEFORE the hand-over barrier ------
+                float dzh_n[2][4], ddh_n[4][4];
+                AFrag<NS, 2> fh;
+                zero_c<4>(ddh_n), zero_c<2>(dzh_n);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float gh = duh[nt][j] + ddh[nt][j] * (1.f - dh[nt][j] * dh[nt][j]);
+                        ph[nt][j] = gh * p.inv_tau_h;
+                        duh[nt][j] = gh * keep_h;
+                        dl[nt][j] = 1.f - dl[nt][j] * dl[nt][j];  // tanh' of the lower cell, ready for the critical section
+                    }
+                // the cells' dY is double buffered: step t's lands in buffer t & 1 and is multiplied at step t-1 with that step's
+                // state (= this step's INPUT state), so no copies of the previous state are needed anywhere
+                store_op<4>(ph, dy, fz::Y_H + 64 * (t & 1), r);
+                to_afrag<NS, 2>(fh, ph);
+                gemm<NS, 2, 4>(ddh_n, fh, wblk<NS>(W, mt::T_H_D2H), lane);
+                gemm<NS, 2, 2>(dzh_n, fh, wblk<NS>(W, mt::T_H_IN), lane);
+                float g2[2][4];  // upstream d stoch_l of step t-1
+                zero_c<2>(g2);
+                if (t > 0) {
+                    mbar_wait(&bars[fz2::BAR_DF], ph_df), ph_df ^= 1;  // d_feature(t-1) has landed
+                    load_staged<2, false>(g2, stDF, bst::DF_LD, 80, r.g, r.t);
+                }
+                // ---- the recurrence's critical section: mod's d deter_l(t) -> lower cell -> d stoch_l(t-1) back to the mod warp --
                 nbar_sync(bar_x);  // the mod warp's dY columns and its contribution to d deter_l are complete
                 {
                     float c[4][4];
@@ -542,23 +631,27 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
 #pragma unroll
                     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) ddl[nt][j] += c[nt][j];
+                        for (int j = 0; j < 4; ++j) {
+                            const float gl = dul[nt][j] + (ddl[nt][j] + c[nt][j]) * dl[nt][j];
+                            pl[nt][j] = gl * p.inv_tau_l;
+                            dul[nt][j] = gl * keep_l;
+                        }
                 }
+                AFrag<NS, 2> fl;
+                to_afrag<NS, 2>(fl, pl);
+                float dzl[2][4];
+                zero_c<2>(dzl);
+                gemm<NS, 2, 2>(dzl, fl, wblk<NS>(W, mt::T_L_IN_ZL), lane);
+                if (t > 0) {  // hand d stoch_l of step t-1 (+ its upstream part) to the mod warp
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt)
+                    for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float gh = duh[nt][j] + ddh[nt][j] * (1.f - dh[nt][j] * dh[nt][j]);
-                        const float gl = dul[nt][j] + ddl[nt][j] * (1.f - dl[nt][j] * dl[nt][j]);
-                        ph[nt][j] = gh * p.inv_tau_h;
-                        pl[nt][j] = gl * p.inv_tau_l;
-                        duh[nt][j] = gh * keep_h;
-                        dul[nt][j] = gl * keep_l;
-                    }
-                // the cells' dY is double buffered: step t's lands in buffer t & 1 and is multiplied at step t-1 with that step's
-                // state (= this step's INPUT state), so no copies of the previous state are needed anywhere
+                        for (int j = 0; j < 4; ++j) dzl[nt][j] += g2[nt][j];
+                    xch_store<2>(dzl, xdzl, lane);
+                    nbar_arrive(bar_y);
+                }
+                // ---- off the critical path: the end-of-step weight-gradient MMAs and the rest of the lower cell -------------------
                 store_op<4>(pl, dy, fz::Y_L + 64 * (t & 1), r);
-                store_op<4>(ph, dy, fz::Y_H + 64 * (t & 1), r);
                 FZ_FENCE();
                 __syncwarp();
                 if (FZ_MMA && lane == 0) {
@@ -568,27 +661,17 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     umma_acc(tmem + fz2::T_B + 16, s_dy + 16 * fz2::CH, s_ones, 16);  // dY columns 128..239 (+ junk)
                     umma_commit(&bars[fz2::BAR_END]);
                 }
-                AFrag<NS, 2> fl, fh;
-                to_afrag<NS, 2>(fl, pl);
-                to_afrag<NS, 2>(fh, ph);
-                float dzl[2][4];
-                zero_c<4>(ddl), zero_c<4>(ddh), zero_c<2>(dzl), zero_c<2>(dzh);
-                gemm<NS, 2, 2>(dzl, fl, wblk<NS>(W, mt::T_L_IN_ZL), lane);
-                if (t > 0) {  // hand d stoch_l of step t-1 (+ its upstream part) to the mod warp as early as possible
-                    float g2[2][4];
-                    mbar_wait(&bars[fz2::BAR_DF], ph_df), ph_df ^= 1;  // d_feature(t-1) has landed
-                    load_staged<2, false>(g2, stDF, bst::DF_LD, 80, r.g, r.t);
+                zero_c<4>(ddl);
 #pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
+                for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) dzl[nt][j] += g2[nt][j];
-                    xch_store<2>(dzl, xdzl, lane);
-                    nbar_arrive(bar_y);
-                }
+                    for (int j = 0; j < 4; ++j) ddh[nt][j] = ddh_n[nt][j];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dzh[nt][j] = dzh_n[nt][j];
                 gemm<NS, 2, 4>(ddl, fl, wblk<NS>(W, mt::T_L_D2H), lane);
-                gemm<NS, 2, 4>(ddh, fh, wblk<NS>(W, mt::T_H_D2H), lane);
                 gemm<NS, 2, 2>(dzh, fl, wblk<NS>(W, mt::T_L_IN_ZH), lane);
-                gemm<NS, 2, 2>(dzh, fh, wblk<NS>(W, mt::T_H_IN), lane);
                 if (p.d_actions != nullptr) {
                     float da[2][4];
                     zero_c<2>(da);
@@ -683,14 +766,18 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (warp < 4) {
-        const int L = 32 * warp + lane;  // TMEM lane read by this thread
+    {
+        // a warp may read the TMEM lane quarter (warp % 4); with 8 warps, warps w and w + 4 split a quarter's 16-column chunks
+        const int quarter = warp & 3, part = warp >> 2, nparts = nthr >> 7;
+        const int L = 32 * quarter + lane;  // TMEM lane read by this thread
+        int chunk = 0;
         for (int i = 0; i < ft.n; ++i) {
             const FusedFlush f = ft.e[i];
-            if (f.lane0 + f.nlanes <= 32 * warp || f.lane0 >= 32 * warp + 32) continue;  // warp-uniform
-            for (int c0 = 0; c0 < f.ncols; c0 += 16) {
+            if (f.lane0 + f.nlanes <= 32 * quarter || f.lane0 >= 32 * quarter + 32) continue;  // warp-uniform
+            for (int c0 = 0; c0 < f.ncols; c0 += 16, ++chunk) {
+                if (chunk % nparts != part) continue;  // warp-uniform
                 uint32_t v[16];
-                const uint32_t taddr = tmem + ((uint32_t)(32 * warp) << 16) + f.tcol + c0;
+                const uint32_t taddr = tmem + ((uint32_t)(32 * quarter) << 16) + f.tcol + c0;
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),

@@ -51,30 +51,35 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
     float* bias = reinterpret_cast<float*>(W + (size_t)NS * mt::FWD_TILES * 32);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int A = p.A;
-    {
+    __shared__ PackTable tb;
+    if (tid == 0) {
         using namespace mt;
         const int ldin = A + 32;
-        pack_weight<NS, false>(wblk<NS>(W, L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, false>(wblk<NS>(W, L_IN_ZL), p.w.l_in_w, ldin, 0, A, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, false>(wblk<NS>(W, L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, false>(wblk<NS>(W, L_IN_A), p.w.l_in_w, ldin, 0, 0, A, 32, 1, 4, tid, nthr);
-        pack_weight<NS, false>(wblk<NS>(W, H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, false>(wblk<NS>(W, H_IN), p.w.h_in_w, 16, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, false>(wblk<NS>(W, LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, false>(wblk<NS>(W, LP2), p.w.lp_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, false>(wblk<NS>(W, HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, false>(wblk<NS>(W, HP2), p.w.hp_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
+        tb.nblocks = tb.ntiles = 0;
+        pack_add(tb, false, wblk<NS>(W, L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, false, wblk<NS>(W, L_IN_ZL), p.w.l_in_w, ldin, 0, A, 16, 32, 1, 4);
+        pack_add(tb, false, wblk<NS>(W, L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 16, 32, 1, 4);
+        pack_add(tb, false, wblk<NS>(W, L_IN_A), p.w.l_in_w, ldin, 0, 0, A, 32, 1, 4);
+        pack_add(tb, false, wblk<NS>(W, H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, false, wblk<NS>(W, H_IN), p.w.h_in_w, 16, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, false, wblk<NS>(W, LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, false, wblk<NS>(W, LP2), p.w.lp_w2, 32, 0, 0, 32, 16, 2, 2);
+        pack_add(tb, false, wblk<NS>(W, HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, false, wblk<NS>(W, HP2), p.w.hp_w2, 32, 0, 0, 32, 16, 2, 2);
         if (!IMAGINE) {
-            pack_weight<NS, false>(wblk<NS>(W, HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4, tid, nthr);
-            pack_weight<NS, false>(wblk<NS>(W, HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4, tid, nthr);
-            pack_weight<NS, false>(wblk<NS>(W, HQ2), p.w.hq_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
-            pack_weight<NS, false>(wblk<NS>(W, A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-            pack_weight<NS, false>(wblk<NS>(W, A1E), p.w.au_w1, 96, 0, 32, 64, 32, 4, 4, tid, nthr);
-            pack_weight<NS, false>(wblk<NS>(W, A2), p.w.au_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
-            pack_weight<NS, false>(wblk<NS>(W, V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-            pack_weight<NS, false>(wblk<NS>(W, V1E), p.w.vi_w1, 96, 0, 32, 64, 32, 4, 4, tid, nthr);
-            pack_weight<NS, false>(wblk<NS>(W, V2), p.w.vi_w2, 32, 0, 0, 32, 16, 2, 2, tid, nthr);
+            pack_add(tb, false, wblk<NS>(W, HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4);
+            pack_add(tb, false, wblk<NS>(W, HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4);
+            pack_add(tb, false, wblk<NS>(W, HQ2), p.w.hq_w2, 32, 0, 0, 32, 16, 2, 2);
+            pack_add(tb, false, wblk<NS>(W, A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4);
+            pack_add(tb, false, wblk<NS>(W, A1E), p.w.au_w1, 96, 0, 32, 64, 32, 4, 4);
+            pack_add(tb, false, wblk<NS>(W, A2), p.w.au_w2, 32, 0, 0, 32, 16, 2, 2);
+            pack_add(tb, false, wblk<NS>(W, V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4);
+            pack_add(tb, false, wblk<NS>(W, V1E), p.w.vi_w1, 96, 0, 32, 64, 32, 4, 4);
+            pack_add(tb, false, wblk<NS>(W, V2), p.w.vi_w2, 32, 0, 0, 32, 16, 2, 2);
         }
+    }
+    {  // the biases, while thread 0 fills the table
+        using namespace mt;
         for (int i = tid; i < FWD_BIAS; i += nthr) {
             float v;
             if (i < B_H) v = p.w.l_d2h_b[i] + p.w.l_in_b[i];
@@ -93,6 +98,8 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
             bias[i] = v;
         }
     }
+    __syncthreads();
+    pack_run<NS>(tb, tid, nthr);
     __syncthreads();
 
     const int lane = tid & 31, warp = tid >> 5;
@@ -284,29 +291,33 @@ __global__ void __launch_bounds__(NS == 1 ? 256 : 128, 1) mtrssm_bwd_kernel(cons
     uint2* W = reinterpret_cast<uint2*>(smem_raw);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int A = p.A;
-    {
+    __shared__ PackTable tb;
+    if (tid == 0) {
         using namespace mt;
         const int ldin = A + 32;
-        pack_weight<NS, true>(wblk<NS>(W, T_A2), p.w.au_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_V2), p.w.vi_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_LP2), p.w.lp_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HP2), p.w.hp_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HQ2), p.w.hq_w2, 32, 0, 0, 16, 32, 1, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_A1E), p.w.au_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_V1E), p.w.vi_w1, 96, 0, 32, 32, 64, 2, 8, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZL), p.w.l_in_w, ldin, 0, A, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_H_IN), p.w.h_in_w, 16, 0, 0, 32, 16, 2, 2, tid, nthr);
-        pack_weight<NS, true>(wblk<NS>(W, T_L_IN_A), p.w.l_in_w, ldin, 0, 0, 32, A, 2, 2, tid, nthr);
+        tb.nblocks = tb.ntiles = 0;
+        pack_add(tb, true, wblk<NS>(W, T_A2), p.w.au_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblk<NS>(W, T_V2), p.w.vi_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblk<NS>(W, T_LP2), p.w.lp_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblk<NS>(W, T_HP2), p.w.hp_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblk<NS>(W, T_HQ2), p.w.hq_w2, 32, 0, 0, 16, 32, 1, 4);
+        pack_add(tb, true, wblk<NS>(W, T_A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_A1E), p.w.au_w1, 96, 0, 32, 32, 64, 2, 8);
+        pack_add(tb, true, wblk<NS>(W, T_V1E), p.w.vi_w1, 96, 0, 32, 32, 64, 2, 8);
+        pack_add(tb, true, wblk<NS>(W, T_L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4);
+        pack_add(tb, true, wblk<NS>(W, T_L_IN_ZL), p.w.l_in_w, ldin, 0, A, 32, 16, 2, 2);
+        pack_add(tb, true, wblk<NS>(W, T_L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 32, 16, 2, 2);
+        pack_add(tb, true, wblk<NS>(W, T_H_IN), p.w.h_in_w, 16, 0, 0, 32, 16, 2, 2);
+        pack_add(tb, true, wblk<NS>(W, T_L_IN_A), p.w.l_in_w, ldin, 0, 0, 32, A, 2, 2);
     }
+    __syncthreads();
+    pack_run<NS>(tb, tid, nthr);
     __syncthreads();
 
     const int lane = tid & 31, warp = tid >> 5;

@@ -16,7 +16,7 @@
 //   - the canonical no-swizzle K-MAJOR tcgen05 operand with K = feature (LBO = 128 rows * 16 B between 8-column groups,
 //     SBO = 128 B between 8-row groups): used by the forward / backward contractions over features, and
 //   - the canonical no-swizzle MN-MAJOR operand with K = row (LBO = 128 B between 8-row groups, SBO = 2048 B between
-//     8-feature groups): used by the weight-gradient contractions over (b,t) rows (layout validated by scratch/umma_probe.cu).
+//     8-feature groups): used by the weight-gradient contractions over (b,t) rows (layout validated by profiles/src/umma_probe.cu).
 // Weights are packed once per call the same way, per slice: [slice][K/64][8][N][8] (N = 32 or 96 rows).
 #pragma once
 #include <cuda_bf16.h>
@@ -36,7 +36,7 @@ constexpr int N_ISSUERS = RSSM_WIDE_ISSUERS;  // MMA issuer threads (1 or 2; bui
 constexpr int NTHREADS = 320 + 32 * (N_ISSUERS - 1);  // warps 0-7: epilogue (TMEM lane quadrant = warp & 3, column half = warp >> 2), warp 8: producer, warps 9(-10): MMA issuer(s)
 constexpr int PRODUCER_WARP = 8, MMA_WARP = 9, MMA_WARP2 = 10, EPI_THREADS = 256;
 // Two issuer threads take alternate operand chunks: one thread's wait -> 4 MMAs -> commit loop costs ~470 cycles per chunk
-// (mbarrier ops ~130 cycles each and ~47 cycles per tcgen05.mma issue, all serial in the thread: scratch/umma_ring*.cu) against
+// (mbarrier ops ~130 cycles each and ~47 cycles per tcgen05.mma issue, all serial in the thread: profiles/src/umma_ring*.cu) against
 // 268 cycles of tensor-pipe time, so a single issuer leaves the pipe idle 40 % of the time (cfg3, same box: 6.70 -> 6.29 ms).
 // Each issuer accumulates its chunks (even / odd) into ITS OWN copy of the accumulator (TMEM columns + acc_off); the epilogue
 // adds the two copies.  So every accumulator is written by one thread in a fixed order and the results stay bit-reproducible

@@ -1,4 +1,4 @@
-"""Times the likelihood kernels alone (scratch/nll_bench.py [B] [T]); used for the ncu capture of profiles/r1_j_*."""
+"""Times the likelihood kernels alone (profiles/src/nll_bench.py [B] [T]); used for the ncu capture of profiles/r1_j_*."""
 import json
 import sys
 from pathlib import Path

@@ -1,7 +1,7 @@
 // How much HBM bandwidth does the rollout's access pattern allow?  Each warp owns 16 rows of a [B, T, seg] tensor and marches
 // over t, touching one `seg`-byte segment per row per step (stride T*seg between rows), exactly like the rollout kernels.
 // Modes: copy (read + write), read-only, write-only; NT independent tensors are touched per step (the kernels touch ~10).
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scratch/seg_bw scratch/seg_bw.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o profiles/src/seg_bw profiles/src/seg_bw.cu
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

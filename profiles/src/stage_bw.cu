@@ -2,7 +2,7 @@
 // 16-row tile per warp, one `seg`-byte segment per row per step)?
 //   mode 0: cp.async (LDGSTS) 16 B per lane      mode 1: cp.async.bulk, one bulk copy per row segment (TMA 1-D), mbarrier
 // Both double-buffered: step t+1 is in flight while step t is consumed.  Prints GB/s.
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scratch/stage_bw scratch/stage_bw.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o profiles/src/stage_bw profiles/src/stage_bw.cu
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

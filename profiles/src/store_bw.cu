@@ -5,7 +5,7 @@
 //   mode 2: staged in shared memory; warp-coalesced 16-byte global stores (consecutive lanes -> consecutive addresses of a row)
 //   mode 3: no stores (compute stand-in only)
 // A dependent-FMA loop stands in for the step's math.  Prints ms per launch and written GB/s at 4 and 8 warps per SM.
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scratch/store_bw scratch/store_bw.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o profiles/src/store_bw profiles/src/store_bw.cu
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

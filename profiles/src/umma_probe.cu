@@ -2,7 +2,7 @@
 // Validates on a B200 the descriptor conventions the fused wgrad uses:
 //   operand element (mn, k) at  (mn/8)*SBO + (k/8)*LBO + (k%8)*16 + (mn%8)*2   bytes   [to be confirmed: which field is which]
 // and whether MMAs issued by different warps may accumulate into the same TMEM tile.
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scratch/umma_probe scratch/umma_probe.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o profiles/src/umma_probe profiles/src/umma_probe.cu
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -1,6 +1,6 @@
 // tcgen05.mma issue/execution rate by N and shared-memory operand layout (bf16, M = 128, K = 16 per instruction, cta_group::1).
 // Times R chunks of 4 back-to-back MMAs (one K = 64 operand chunk each), a commit per chunk, one wait at the end.
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scratch/umma_rate scratch/umma_rate.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o profiles/src/umma_rate profiles/src/umma_rate.cu
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>

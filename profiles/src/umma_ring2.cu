@@ -1,6 +1,6 @@
 // Per-chunk cost of the producer / MMA-issuer handshake used by the wide kernels, without any data movement:
 // warp 1 lane 0 = producer (wait empty -> arrive full), warp 2 lane 0 = MMA issuer (wait full -> 4 MMAs -> commit empty).
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scratch/umma_ring scratch/umma_ring.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o profiles/src/umma_ring profiles/src/umma_ring.cu
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,7 +25,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 template <int V>
-__global__ void __launch_bounds__(192, 1) ring(int N, int stages, int R, int do_mma, long long* out) {
+__global__ void __launch_bounds__(192, 1) ring(int N, int stages, int R, int do_mma, int plain_release, long long* out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t full[8], empty[8], fin;
     __shared__ uint32_t tmem_s;
@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(192, 1) ring(int N, int stages, int R, int do_
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) umma(tmem, make_desc(a0 + kk * 4096, 2048, 128), make_desc(b0 + kk * 2 * N * 16, N * 16, 128), idesc, 1);
             }
-            commit(&empty[slot]);
+            if (plain_release) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[slot])) : "memory");
+            else commit(&empty[slot]);
             if (++slot == (uint32_t)stages) slot = 0, ph ^= 1;
         }
         commit(&fin);
@@ -83,19 +84,20 @@ int main() {
     cudaFuncSetAttribute(ring<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(ring<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     const int R = 512;
-    for (int v = 0; v < 2; ++v)
+    for (int v = 0; v < 1; ++v)
+      for (int pr = 0; pr < 2; ++pr)
         for (int mma = 0; mma < 2; ++mma)
-            for (int stages : {1, 2, 4, 6})
-                for (int N : {32, 96}) {
+            for (int stages : {2, 4, 8})
+                for (int N : {96}) {
                     long long h = 0;
                     for (int rep = 0; rep < 2; ++rep) {
-                        if (v == 0) ring<0><<<1, 192, 64 * 1024>>>(N, stages, R, mma, d);
-                        else ring<1><<<1, 192, 64 * 1024>>>(N, stages, R, mma, d);
+                        if (v == 0) ring<0><<<1, 192, 64 * 1024>>>(N, stages, R, mma, pr, d);
+                        else ring<1><<<1, 192, 64 * 1024>>>(N, stages, R, mma, pr, d);
                         cudaError_t e = cudaDeviceSynchronize();
                         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
                         cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
                     }
-                    printf("wait=%s mma=%d stages=%d N=%2d: %7.1f cycles per chunk (4 MMAs; MMA floor 268)\n", v ? "test_wait" : "try_wait ", mma, stages, N, (double)h / R);
+                    printf("release=%s mma=%d stages=%d N=%2d: %7.1f cycles per chunk (4 MMAs; MMA floor 268)\n", pr ? "plain arrive  " : "tcgen05.commit", mma, stages, N, (double)h / R);
                 }
     return 0;
 }

@@ -1,6 +1,6 @@
 // Per-chunk cost of the producer / MMA-issuer handshake used by the wide kernels, without any data movement:
 // warp 1 lane 0 = producer (wait empty -> arrive full), warp 2 lane 0 = MMA issuer (wait full -> 4 MMAs -> commit empty).
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scratch/umma_ring scratch/umma_ring.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o profiles/src/umma_ring profiles/src/umma_ring.cu
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
