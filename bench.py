@@ -10,6 +10,10 @@ and noise.  default.yaml's batch of 8 cannot occupy a GPU, so the per-GPU batch 
 two full waves of the kernels' 16-sequence warp tiles; weak scaling: every rank processes its own 37888).  The B=8
 latency (`default_batch8`) and B = 256 / 4096 / 16384 and cfg4 (`other_workloads`) are reported beside it.
 
+The timed configuration is the one the model API launches (`MoPoE_MMTRSSM.rollout_representation`): the prior MTState's own
+draws are made and written (`u_prior_*` / `prior_stoch_*`; `--no-prior-sample` leaves them out and subtracts their 2 x 128
+algorithmic bytes per (b,t)).
+
 A step = one pass of the hot path over one batch: the forward rollout kernel + the fused backward kernel (BPTT and the weight
 gradients -- tcgen05 MMAs with TMEM accumulators -- in one launch; `--precision bf16` runs the two-kernel backward, `--precision
 fp32` the fp32-parity path) (+ one NCCL allreduce of the flat weight-gradient bucket when N > 1).  `value` has the inputs resident in
@@ -39,6 +43,13 @@ UNIT = "latent steps/s (B*T, rollout fwd+bwd)"
 # fp32 mandatory I/O per (b,t): inputs (A + 2E)*4 = 536 B, MMTRSSM outputs 1024 B; fwd+bwd = 2x
 FWD_BYTES_PER_BT = 536 + 1024
 STEP_BYTES_PER_BT = 2 * FWD_BYTES_PER_BT
+PRIOR_STOCH_BYTES_PER_BT = 128  # (hs + ls) * 4: part of the 1024 B of outputs; not moved under --no-prior-sample
+
+
+def bytes_per_bt(prior_sample: bool) -> tuple[int, int]:
+    """(forward, fwd+bwd) algorithmic HBM bytes per (b,t) of the timed configuration."""
+    f = FWD_BYTES_PER_BT - (0 if prior_sample else PRIOR_STOCH_BYTES_PER_BT)
+    return f, 2 * f
 FWD_FLOPS_PER_BT = 33152
 
 
@@ -55,6 +66,9 @@ def parse() -> argparse.Namespace:
     ap.add_argument("--cpu-batch", type=int, default=256, help="sequences in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp32-path / B=8 side measurements")
+    ap.add_argument("--no-prior-sample", action="store_true",
+                    help="do not draw / write the prior MTState's own samples (the model API always does); their bytes are subtracted")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="wall-clock budget of the whole reference-arm run")
     return ap.parse_args()
 
 
@@ -109,7 +123,7 @@ class ClockSampler:
 class DirectMtrssm:
     """Pre-allocated buffers + direct C-ABI calls: exactly the three kernels of the hot path, no allocator traffic."""
 
-    def __init__(self, B: int, T: int, precision: int, device: torch.device) -> None:
+    def __init__(self, B: int, T: int, precision: int, device: torch.device, prior_sample: bool = True) -> None:
         from multimodal_mtrssm_b200 import _lib, synthetic
         from multimodal_mtrssm_b200.params import mtrssm_weight_list
 
@@ -117,7 +131,7 @@ class DirectMtrssm:
         self.fused = precision == _lib.PRECISION_BF16_FUSED
         self.params = {k: v.to(device) for k, v in synthetic.mtrssm_params().items()}
         self.weights = mtrssm_weight_list(self.params)
-        self.inp = {k: v.to(device) for k, v in synthetic.mtrssm_batch(B, T).items()}
+        self.inp = {k: v.to(device) for k, v in synthetic.mtrssm_batch(B, T, prior_noise=prior_sample).items()}
         g = torch.Generator().manual_seed(7)
         self.d_feature = torch.randn(B, T, 96, generator=g).to(device)
         self.d_kl = torch.full((B, T), 1.0 / (B * T), device=device)
@@ -128,6 +142,8 @@ class DirectMtrssm:
             "kl_l": e(B, T), "kl_h": e(B, T),
             "saved": torch.empty(B, T, _lib.mtrssm_saved_elems(precision), device=device, dtype=_lib.record_dtype(precision)),
         }
+        if prior_sample:  # the prior MTState's own draws (mmtrssm/state.py:48-49): what the model API launches
+            self.out["prior_stoch_h"], self.out["prior_stoch_l"] = e(B, T, 16), e(B, T, 16)
         self.gin = {
             "d_actions": e(B, T, 6), "d_embed_a": e(B, T, 64), "d_embed_v": e(B, T, 64), "d_deter_h0": e(B, 32), "d_deter_l0": e(B, 32),
             "d_hidden_h0": e(B, 32), "d_hidden_l0": e(B, 32), "d_stoch_h0": e(B, 16), "d_stoch_l0": e(B, 16),

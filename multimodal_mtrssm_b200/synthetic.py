@@ -70,16 +70,20 @@ def onehot(B: int, C: int, K: int, g: torch.Generator) -> Tensor:
     return torch.nn.functional.one_hot(torch.randint(0, K, (B, C), generator=g), K).float().flatten(1)
 
 
-def mtrssm_batch(B: int, T: int, seed: int = 1234, noise_seed: int = 4321) -> dict[str, Tensor]:
-    """Rollout-only MMTRSSM inputs at the default.yaml sizes (l_dist 4x4, h_dist 8 groups x 2 classes)."""
+def mtrssm_batch(B: int, T: int, seed: int = 1234, noise_seed: int = 4321, prior_noise: bool = False) -> dict[str, Tensor]:
+    """Rollout-only MMTRSSM inputs at the default.yaml sizes (l_dist 4x4, h_dist 8 groups x 2 classes).  `prior_noise` adds the
+    uniforms of the prior MTState's own draws (mmtrssm/state.py:48-49), which `MoPoE_MMTRSSM.rollout_representation` always makes."""
     g, n = torch.Generator().manual_seed(seed), torch.Generator().manual_seed(noise_seed)
     d_h, d_l = torch.randn(B, 32, generator=g), torch.randn(B, 32, generator=g)
-    return {
+    out = {
         "actions": actions(B, T, g), "embed_a": torch.randn(B, T, 64, generator=g), "embed_v": torch.randn(B, T, 64, generator=g),
         "deter_h0": d_h, "deter_l0": d_l, "hidden_h0": d_h.clone(), "hidden_l0": d_l.clone(),
         "stoch_h0": onehot(B, 8, 2, g), "stoch_l0": onehot(B, 4, 4, g),
         "u_post_l": torch.rand(B, T, 4, generator=n), "u_post_h": torch.rand(B, T, 8, generator=n),
     }
+    if prior_noise:
+        out["u_prior_l"], out["u_prior_h"] = torch.rand(B, T, 4, generator=n), torch.rand(B, T, 8, generator=n)
+    return out
 
 
 def mrssm_batch(B: int, T: int, seed: int = 1234, noise_seed: int = 4321, D: int = 32) -> dict[str, Tensor]:
