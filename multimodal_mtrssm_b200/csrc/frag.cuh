@@ -466,7 +466,7 @@ __device__ __forceinline__ void stage_inputs(float* stage, const float* __restri
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const int piece = 2 * half + k;
-            if (2 * piece < A) cp_async8(stage + stg::ACT + rl * 8 + 2 * piece, act + idx * A + 2 * piece);
+            if (act != nullptr && 2 * piece < A) cp_async8(stage + stg::ACT + rl * 8 + 2 * piece, act + idx * A + 2 * piece);
         }
         const float* us[2] = {u0, u1};
         const int ns[2] = {n0, n1};

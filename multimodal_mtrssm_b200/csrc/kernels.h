@@ -165,6 +165,7 @@ struct MtrssmBwdArgs {
 };
 
 cudaError_t launch_mtrssm_fwd(const MtrssmFwdArgs& a, int precision, bool imagine, cudaStream_t s);
+cudaError_t launch_mtrssm_fwd2(const MtrssmFwdArgs& a, cudaStream_t s);  // bf16 policy, two warps per tile
 cudaError_t launch_mtrssm_bwd(const MtrssmBwdArgs& a, int precision, cudaStream_t s);
 // bf16 path: BPTT + weight gradients in one kernel (tcgen05 / TMEM accumulators); ADDS into g (mtrssm_fused_bwd.cu)
 cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeightGrads& g, cudaStream_t s);

@@ -38,6 +38,19 @@
 #define FZ_WAIT(bar, ph) mbar_wait(bar, ph)
 #endif
 
+// -DFZ_TIMING (profiles/src/build_variant.sh): tile 0 of CTA 0 stamps clock64() at fixed points of every step of its first group;
+// the launcher synchronises and prints the mean interval between consecutive stamps (cycles) for both warps of the tile.
+#ifdef FZ_TIMING
+#include <stdio.h>
+__device__ long long fz_dbg[2][1024][12];
+#define FZ_TS(i)                                                                                                  \
+    do {                                                                                                          \
+        if (lane == 0 && blockIdx.x == 0 && tile == 0 && grp == (int)blockIdx.x && t < 1024) fz_dbg[role][t][i] = clock64(); \
+    } while (0)
+#else
+#define FZ_TS(i) do {} while (0)
+#endif
+
 namespace rssm {
 
 namespace fz {
@@ -354,8 +367,10 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 // ---- everything that does NOT depend on the carried d stoch_l runs BEFORE the hand-over barrier, in the window
                 // where this warp used to idle: the two flat log-softmaxes, the mixture responsibilities, the KL / upstream part of
                 // d post_probs_l, exp(ls) for the log-softmax backward and ELU' of the two hiddens ----------------------------
+                FZ_TS(0);
                 cp_async_wait<1>();  // LA, LV, post_l, prior_l of step t have landed (the rest may still be in flight)
                 __syncwarp();
+                FZ_TS(1);
                 float q[2][4], dzl_pre[2][4], lsa[2][4], lsv[2][4], ra[2][4], rv[2][4];
                 {
                     float pp[2][4], dpp[2][4], la[2][4], lv[2][4], mixed[2][4];
@@ -381,6 +396,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                         }
                 }
                 __syncwarp();
+                FZ_TS(2);
                 stage_logits(t - 1);  // LA, LV and the probability rows are in registers: refill them
                 cp_async_wait<1>();   // hiddens of step t have landed (the embedding images were written by this warp itself)
                 __syncwarp();
@@ -395,7 +411,9 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                         eluV[nt][j] = elu_grad_from_out(eluV[nt][j]);
                     }
                 // ---- the recurrence's critical section: d stoch_l(t) -> ... -> contribution to d deter_l(t) --------------------
+                FZ_TS(3);
                 nbar_sync(bar_y);  // d stoch_l of step t is in XDZL
+                FZ_TS(4);
                 float dla[2][4], dlv[2][4];
                 {
                     float dzl[2][4], dm[2][4];
@@ -429,7 +447,9 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     }
                 }
                 // this warp's dY columns (LA, A1, LV, V1) were last read by the core warp's end-of-step MMAs of step t+1
+                FZ_TS(5);
                 if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
+                FZ_TS(6);
                 float ddl[4][4];
                 zero_c<4>(ddl);
                 AFrag<NS, 2> f1a, f1v;
@@ -440,6 +460,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 xch_store<4>(ddl, xddl, lane);
                 FZ_FENCE();
                 nbar_arrive(bar_x);  // XDDL and this warp's dY columns are complete (and visible to the async proxy)
+                FZ_TS(7);
                 // ---- off the critical path: this warp's weight-gradient MMAs, the embedding gradients, next step's staging -------
                 __syncwarp();
                 if (FZ_MMA && lane == 0) {
@@ -455,10 +476,15 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     float* dE = m == 0 ? p.d_embed_a : p.d_embed_v;
                     store_c<8>(de, dE + iA * 64, dE + iB * 64, r);
                 }
+                FZ_TS(8);
                 FZ_WAIT(&bars[fz2::BAR_M], ph_m), ph_m ^= 1;  // own MMAs done: hiddens / embedding images may be rewritten
+                FZ_TS(9);
                 stage_rest(t - 1);
                 embed_prefetch(t - 2);
+                // (requesting the fp32 embeddings before the embedding-gradient GEMMs and converting them here was measured: the
+                // stall moves into the GEMMs, 245 registers, 0.78 -> 0.815 ms at the bench size -- not kept)
                 if (t > 0) embed_images(t - 1);
+                FZ_TS(10);
             }
             cp_async_wait_all();
         } else {
@@ -504,10 +530,12 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 const float dkl_cur = dkl_next;
                 if (t > 0 && dkl_src != nullptr) dkl_next = dkl_src[dkl_row + t - 1];
                 float hid[4][4];
+                FZ_TS(0);
                 cp_async_wait_all();  // PR(t) and the hiddens of step t have landed
                 __syncwarp();
                 // the end-of-step MMAs of step t+1 are done with dY, Dop and Zop
                 if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
+                FZ_TS(1);
                 // the action of step t+1 (X operand of the l cell's weight gradient, paired below with dY of step t+1): lanes with
                 // t < 2 own its columns 4t .. 4t+3; column 8 of the 16-column block is the ones column
                 float actc[2][4];
@@ -543,6 +571,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     head_bwd_op(dlg, wblk<NS>(W, mt::T_LP2), hid, dy, fz::Y_LPL, fz::Y_LP1, f1, r, lane);
                     gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_LP1), lane);
                 }
+                FZ_TS(2);
                 // ---- higher layer: posterior + prior heads ----------------------------------------------------------------
                 {
                     float q[2][4], pp[2][4], dpp[2][4];
@@ -570,6 +599,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     head_bwd_op(dlg, wblk<NS>(W, mt::T_HP2), hid, dy, fz::Y_HPL, fz::Y_HP1, f1, r, lane);
                     gemm<NS, 2, 4>(ddh, f1, wblk<NS>(W, mt::T_HP1), lane);
                 }
+                FZ_TS(3);
                 // second-layer weight gradients of this warp's three heads
                 FZ_FENCE();
                 __syncwarp();
@@ -577,6 +607,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     umma_acc(tmem + fz2::T_E, s_sv, s_dy + (fz::Y_LPL / 8) * fz2::CH, 48);
                     umma_commit(&bars[fz2::BAR_E]);
                 }
+                FZ_TS(4);
                 // ---- the two leaky integrators --------------------------------------------------------------------------
                 float dh[4][4], dl[4][4], ph[4][4], pl[4][4];
                 mbar_wait(&bars[fz2::BAR_FT], ph_ft), ph_ft ^= 1;  // the feature row of step t has landed
@@ -596,8 +627,10 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     store_op<2>(zh, zop, 16, r);
                     store_op<2>(actc, zop, 32, r);
                 }
+                FZ_TS(5);
                 FZ_WAIT(&bars[fz2::BAR_E], ph_e), ph_e ^= 1;  // the hiddens may be refilled
                 stage_hid(t - 1);
+                FZ_TS(6);
                 // ---- the higher cell depends on nothing the mod warp produces: all of it runs BEFORE the hand-over barrier ------
                 float dzh_n[2][4], ddh_n[4][4];
                 AFrag<NS, 2> fh;
@@ -624,7 +657,9 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     load_staged<2, false>(g2, stDF, bst::DF_LD, 80, r.g, r.t);
                 }
                 // ---- the recurrence's critical section: mod's d deter_l(t) -> lower cell -> d stoch_l(t-1) back to the mod warp --
+                FZ_TS(7);
                 nbar_sync(bar_x);  // the mod warp's dY columns and its contribution to d deter_l are complete
+                FZ_TS(8);
                 {
                     float c[4][4];
                     xch_load<4>(c, xddl, lane);
@@ -650,6 +685,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     xch_store<2>(dzl, xdzl, lane);
                     nbar_arrive(bar_y);
                 }
+                FZ_TS(9);
                 // ---- off the critical path: the end-of-step weight-gradient MMAs and the rest of the lower cell -------------------
                 store_op<4>(pl, dy, fz::Y_L + 64 * (t & 1), r);
                 FZ_FENCE();
@@ -661,6 +697,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     umma_acc(tmem + fz2::T_B + 16, s_dy + 16 * fz2::CH, s_ones, 16);  // dY columns 128..239 (+ junk)
                     umma_commit(&bars[fz2::BAR_END]);
                 }
+                FZ_TS(10);
                 zero_c<4>(ddl);
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt)
@@ -707,6 +744,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     store_c<2>(dzh, p.d_stoch_h0 + (size_t)r.rA * 16, p.d_stoch_h0 + (size_t)r.rB * 16, r);
                     store_c<2>(dzl, p.d_stoch_l0 + (size_t)r.rA * 16, p.d_stoch_l0 + (size_t)r.rB * 16, r);
                 }
+                FZ_TS(11);
             }
             // step 0's cell gradients pair with the INITIAL state
             FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
@@ -855,6 +893,32 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int groups = (tiles + tpc - 1) / tpc;  // one resident CTA per SM (shared memory): persistent over its groups
         kernel<<<groups < sms ? groups : sms, 64 * tpc, smem, s>>>(a, u);
+#ifdef FZ_TIMING
+        if (getenv("RSSM_FZ_TIMING")) {
+            static long long h[2][1024][12];
+            cudaStreamSynchronize(s);
+            cudaMemcpyFromSymbol(h, fz_dbg, sizeof(h));
+            const int T = a.T < 1024 ? a.T : 1024, lo = T > 8 ? 2 : 0, hi = T > 8 ? T - 3 : T - 1;
+            const char* names[2][12] = {{"top", "cpwait+END", "lp head", "hq+hp heads", "fence+E mma", "FT wait+images", "E wait+stage_hid",
+                                         "h cell (pre-X)", "X SYNC wait", "l cell->Y arrive", "END mmas", "rest of step"},
+                                        {"top", "cpwait", "pre-Y math", "refill+ELU'", "Y SYNC wait", "post-Y math", "END wait", "heads->X arrive",
+                                         "mma+de gemms", "M wait", "refill+embed imgs", ""}};
+            for (int role = 0; role < 2; ++role) {
+                fprintf(stderr, "[fz timing B=%d T=%d] %s warp, mean cycles per interval over steps %d..%d:\n", a.B, a.T, role ? "mod" : "core", lo, hi);
+                const int n = role ? 11 : 12;
+                double tot = 0;
+                for (int i = 1; i < n; ++i) {
+                    double sum = 0;
+                    for (int t = lo; t <= hi; ++t) sum += (double)(h[role][t][i] - h[role][t][i - 1]);
+                    fprintf(stderr, "   %-20s %8.0f\n", names[role][i], sum / (hi - lo + 1));
+                    tot += sum / (hi - lo + 1);
+                }
+                double step = 0;  // top(t-1) - top(t): steps run t = T-1 .. 0
+                for (int t = lo + 1; t <= hi; ++t) step += (double)(h[role][t - 1][0] - h[role][t][0]);
+                fprintf(stderr, "   %-20s %8.0f   (sum of intervals %.0f)\n", "WHOLE STEP", step / (hi - lo), tot);
+            }
+        }
+#endif
         return cudaGetLastError();
     };
 #define FUSED_DISPATCH(KLv, KHv) \

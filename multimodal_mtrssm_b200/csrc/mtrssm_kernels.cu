@@ -20,9 +20,23 @@
 // feature layout (state.py:51): [deter_h 0:32 | stoch_h 32:48 | deter_l 48:80 | stoch_l 80:96].
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "frag.cuh"
 #include "kernels.h"
 #include "mtrssm_common.cuh"
+
+// -DFZ_TIMING: warp 0 of CTA 0 stamps clock64() at the phase boundaries of every forward step (see mtrssm_fused_bwd.cu)
+#ifdef FZ_TIMING
+#include <stdio.h>
+__device__ long long fw_dbg[1024][8];
+#define FW_TS(i)                                                                             \
+    do {                                                                                     \
+        if (lane == 0 && blockIdx.x == 0 && warp == 0 && t < 1024) fw_dbg[t][i] = clock64(); \
+    } while (0)
+#else
+#define FW_TS(i) do {} while (0)
+#endif
 
 namespace rssm {
 
@@ -149,6 +163,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
         RT* svA = saved ? saved + iA * p.saved_ld : nullptr;
         RT* svB = saved ? saved + iB * p.saved_ld : nullptr;
         const float* stage = stage_base + (t & 1) * stg::FLOATS;
+        FW_TS(0);
         if (STAGED) {
             cp_async_wait_all();  // this step's inputs have landed ...
             __syncwarp();         // ... for every lane, and every lane is done reading the other stage
@@ -157,6 +172,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
                              CH, row0, p.B, T, t + 1, lane);
         }
 
+        FW_TS(1);
         // ---- two leaky-integrator cells (mopoe_mmtrssm/core.py:59-60), both from the PREVIOUS state ----
         {
             float pl[4][4], ph[4][4];
@@ -188,6 +204,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
             to_afrag<NS, 2>(dlf, dl);
             to_afrag<NS, 2>(dhf, dh);
         }
+        FW_TS(2);
         // ---- priors (:285-286, :311-312) ------------------------------------------------------------------
         float ppl[2][4], pph[2][4];
         {
@@ -203,6 +220,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
             softmax_groups<KH, NS == 1>(lg, pph);
             store_c<2>(pph, p.prior_probs_h + iA * 16, p.prior_probs_h + iB * 16, r);
         }
+        FW_TS(3);
         if (p.u_prior_l != nullptr) {  // prior MTState ctor draws h then l (:467-474 -> state.py:48-49)
             float zh[2][4], zl[2][4];
             sample_onehot<KH>(pph, p.u_prior_h + iA * CH, p.u_prior_h + iB * CH, zh, lane);
@@ -217,6 +235,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
                 store_c<2>(zl, p.prior_stoch_l + iA * 16, p.prior_stoch_l + iB * 16, r);
             }
         }
+        FW_TS(4);
         if constexpr (!IMAGINE) {
         // ---- lower posterior: modality heads on d_l (:422-433), MoPoE fusion (:436-455), sample (:456) ----
         float la[2][4], lv[2][4];
@@ -240,6 +259,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
                         m == 0 ? mts::A_HID : mts::V_HID, r, lane);
             if (svA) store_rec<2>(lg, svA + (m == 0 ? mts::LA : mts::LV), svB + (m == 0 ? mts::LA : mts::LV), r);
         }
+        FW_TS(5);
         {
             float lsa[2][4], lsv[2][4], mixed[2][4], q[2][4], zs[2][4];
             log_softmax_flat<NS == 1>(la, lsa);
@@ -258,6 +278,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
                 if (r.vB) p.kl_l[iB] = kl[1];
             }
         }
+        FW_TS(6);
         // ---- higher posterior on [d_l ; d_h] (:315-317), sample (:464) -------------------------------------
         {
             float acc[4][4], lg[2][4], q[2][4], zs[2][4];
@@ -278,6 +299,7 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
                 if (r.vB) p.kl_h[iB] = kl[1];
             }
         }
+        FW_TS(7);
         }  // !IMAGINE
     }
 }
@@ -583,6 +605,25 @@ static cudaError_t launch(KernelT kernel, const ArgsT& args, int B, size_t smem_
     if (err != cudaSuccess) return err;
     const int ctas = ((B + 15) / 16 + wpc - 1) / wpc;
     kernel<<<ctas, wpc * 32, smem, stream>>>(args);
+#ifdef FZ_TIMING
+    if (getenv("RSSM_FZ_TIMING") && std::is_same<ArgsT, MtrssmFwdArgs>::value) {
+        static long long h[1024][8];
+        cudaStreamSynchronize(stream);
+        cudaMemcpyFromSymbol(h, fw_dbg, sizeof(h));
+        const int T = args.T < 1024 ? args.T : 1024, lo = T > 8 ? 2 : 0, hi = T > 8 ? T - 3 : T - 1;
+        const char* names[8] = {"top", "wait inputs+stage next", "two cells", "prior heads", "prior draws", "audio+vision heads", "fusion+draw+kl",
+                                "higher posterior"};
+        fprintf(stderr, "[fwd timing B=%d T=%d] warp 0, mean cycles per interval over steps %d..%d:\n", B, args.T, lo, hi);
+        for (int i = 1; i < 8; ++i) {
+            double sum = 0;
+            for (int t = lo; t <= hi; ++t) sum += (double)(h[t][i] - h[t][i - 1]);
+            fprintf(stderr, "   %-24s %8.0f\n", names[i], sum / (hi - lo + 1));
+        }
+        double step = 0;
+        for (int t = lo + 1; t <= hi; ++t) step += (double)(h[t][0] - h[t - 1][0]);
+        fprintf(stderr, "   %-24s %8.0f\n", "WHOLE STEP", step / (hi - lo));
+    }
+#endif
     return cudaGetLastError();
 }
 

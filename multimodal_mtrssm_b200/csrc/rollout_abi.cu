@@ -593,6 +593,9 @@ static int mtrssm_fwd_common(const RssmMtrssmDims* d, const RssmMtrssmWeights* w
     a.kl_l = out->kl_l, a.kl_h = out->kl_h, a.saved = imagine ? nullptr : out->saved;
     a.saved_ld = mt_saved_ld(d->precision);
     g_launches.fetch_add(1);
+    // bf16 policies, posterior rollout: two warps per tile (mtrssm_fwd2.cu); imagination and the fp32-parity policy: one warp per tile
+    if (!imagine && d->precision != RSSM_PRECISION_FP32 && getenv("RSSM_FWD_ONE_WARP") == nullptr)
+        return check_cuda(rssm::launch_mtrssm_fwd2(a, static_cast<cudaStream_t>(stream)), "mtrssm forward launch");
     return check_cuda(rssm::launch_mtrssm_fwd(a, mt_kernel_precision(d->precision), imagine, static_cast<cudaStream_t>(stream)),
                       imagine ? "mtrssm imagine launch" : "mtrssm forward launch");
 }

@@ -498,6 +498,37 @@ def test_mtrssm_bf16_fused_backward_matches_two_kernel_backward(ops, B, T, dims)
     rep.finish()
 
 
+def test_mtrssm_fwd2_matches_one_warp_kernel(ops, monkeypatch):
+    """The two-warps-per-tile forward (mtrssm_fwd2.cu, the bf16 default) against the one-warp kernel (RSSM_FWD_ONE_WARP=1): same
+    arithmetic and operand roundings, one fp32 summation order differs, so single steps agree to fp32 rounding of the bf16-operand
+    dot products (2e-6 absolute on O(1) values) and the draws coincide away from CDF knife edges; multi-step rollouts are covered
+    against the oracle (teacher-forced) by the tests above and in test_bench_configs_gpu.py.  Ragged batch, prior draws on."""
+    R, P = ops
+    B, T, dims = 333, 1, H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    inp = H.mtrssm_inputs(B, T, dims)
+    two, _, _ = run_mtrssm(R, P, params, inp, dims, precision=1)
+    monkeypatch.setenv("RSSM_FWD_ONE_WARP", "1")
+    one, _, _ = run_mtrssm(R, P, params, inp, dims, precision=1)
+    monkeypatch.delenv("RSSM_FWD_ONE_WARP")
+    rep = H.Report("mtrssm fwd2 (two warps per tile) vs one-warp kernel, one step")
+    for k in ("hidden_h", "hidden_l", "prior_probs_h", "prior_probs_l", "post_probs_h", "kl_l", "kl_h"):
+        rep.check(k, two[k], one[k], rtol=1e-5, atol=2e-6)
+    # the modality heads' first layer sums its two halves in the other order: an fp32 ulp there can flip the bf16 rounding of one
+    # hidden unit (2^-9 relative) in front of the second layer -> a few 1e-6 on the fused posterior (measured 7.8e-6)
+    rep.check("post_probs_l", two["post_probs_l"], one["post_probs_l"], rtol=0, atol=5e-5)
+    rep.check("deter_h", two["feature"][..., :32], one["feature"][..., :32], rtol=1e-5, atol=2e-6)
+    rep.check("deter_l", two["feature"][..., 48:80], one["feature"][..., 48:80], rtol=1e-5, atol=2e-6)
+    rep.finish()
+    for key, probs, u in (("feature", "post_probs_l", "u_post_l"), ("prior_stoch_l", "prior_probs_l", "u_prior_l"),
+                          ("prior_stoch_h", "prior_probs_h", "u_prior_h")):
+        a = two[key][..., 80:] if key == "feature" else two[key]
+        b = one[key][..., 80:] if key == "feature" else one[key]
+        same = (a == b).reshape(B, T, -1).all(-1).cpu()
+        margin = O.cdf_margin(one[probs].cpu(), inp[u]).amin(-1)
+        assert bool((same | (margin < 1e-5)).all()), key
+
+
 @pytest.mark.parametrize("precision", [1, 2])
 def test_mtrssm_bf16_backward_vs_oracle(ops, precision):
     """Gradients of the bf16 tensor-core paths against the fp32 oracle, teacher-forced on the kernel's own draws (as in
