@@ -103,6 +103,14 @@ struct WideWgradTile {
     float *dW, *db;                   // db (optional): += sum_rows Y[row][m]
     long long sm, sn;
 };
+// The tile table travels to the device as a KERNEL PARAMETER of a tiny upload kernel (captured by value under CUDA-graph capture;
+// no pageable host-to-device copy, no implicit stream synchronisation, nothing a later call could change behind a captured graph).
+constexpr int MAX_WIDE_WGRAD_TILES = 256;  // 256 x 104 B = 26.6 KB < the 32,764-byte kernel parameter limit
+struct WideWgradTileTable {
+    int n;
+    WideWgradTile t[MAX_WIDE_WGRAD_TILES];
+};
+cudaError_t launch_wide_wgrad_tiles_upload(const WideWgradTileTable& table, WideWgradTile* dst, cudaStream_t s);
 cudaError_t launch_wide_wgrad(const WideWgradTile* tiles_dev, int ntiles, int nsplit, int T, int NBBT, const __nv_bfloat16* ones, cudaStream_t s);
 
 struct WideDembedArgs {

@@ -219,7 +219,16 @@ __global__ void wide_pack_dembed_kernel(const float* __restrict__ au_w1, const f
     }
 }
 
+__global__ void wide_wgrad_tiles_upload_kernel(const __grid_constant__ WideWgradTileTable tb, WideWgradTile* __restrict__ dst) {
+    for (int i = threadIdx.x; i < tb.n; i += blockDim.x) dst[i] = tb.t[i];
+}
+
 }  // namespace wide
+
+cudaError_t launch_wide_wgrad_tiles_upload(const WideWgradTileTable& table, WideWgradTile* dst, cudaStream_t s) {
+    wide::wide_wgrad_tiles_upload_kernel<<<1, 128, 0, s>>>(table, dst);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_wide_wgrad(const WideWgradTile* tiles_dev, int ntiles, int nsplit, int T, int NBBT, const __nv_bfloat16* ones, cudaStream_t s) {
     const size_t smem = wide::wg_smem_bytes();

@@ -159,7 +159,7 @@ struct WideBwdLayout {
     size_t pW1x, pWhdT, pWgT, pWihTn, pWhhTn, pW2T, pWaeT, pWveT, ones, drec, stat, h0p, emb_a, emb_v, tiles, bar, total;
     long long dt_stride, dlg, xin;  // elements: gradient-plane step, narrow planes inside a step
 };
-constexpr int MAX_WIDE_TILES = 256;
+constexpr int MAX_WIDE_TILES = rssm::MAX_WIDE_WGRAD_TILES;
 
 void wide_bwd_layout(const RssmMrssmDims* d, const WideLayout& L, WideBwdLayout* W) {
     size_t o = 0;
@@ -360,7 +360,8 @@ int wide_mrssm_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
     if (check_cuda(rssm::launch_wide_pack_rows(in->h0, d->B, 1, D, D, 0, bf(W.h0p), L.NBBT, s), "h0 packing launch")) return 1;
     if (check_cuda(rssm::launch_wide_pack_rows(in->embed_a, d->B, T, 64, 64, 0, bf(W.emb_a), L.NBBT, s), "embedding packing launch")) return 1;
     if (check_cuda(rssm::launch_wide_pack_rows(in->embed_v, d->B, T, 64, 64, 0, bf(W.emb_v), L.NBBT, s), "embedding packing launch")) return 1;
-    static thread_local rssm::WideWgradTile tiles[MAX_WIDE_TILES];
+    static thread_local rssm::WideWgradTileTable table;  // host scratch only: passed BY VALUE to the upload kernel below
+    rssm::WideWgradTile* tiles = table.t;
     int nt = 0;
     const long long bstrideD = (long long)D * 128;
     const __nv_bfloat16* dr = bf(W.drec);
@@ -413,7 +414,10 @@ int wide_mrssm_bwd(const RssmMrssmDims* d, const RssmMrssmWeights* w, const Rssm
         add(bf(W.ones), 0, 0, dl, nullptr, W.dt_stride, 48 * 128, 0, 16, 1, 16, b2g[h], nullptr, 0, 1);  // column sums
     }
     if (nt > MAX_WIDE_TILES) return fail("internal: %d weight-gradient tiles", nt);
-    if (check_cuda(cudaMemcpyAsync(ws + W.tiles, tiles, sizeof(rssm::WideWgradTile) * nt, cudaMemcpyHostToDevice, s), "tile table copy")) return 1;
+    table.n = nt;
+    g_launches.fetch_add(1);
+    if (check_cuda(rssm::launch_wide_wgrad_tiles_upload(table, reinterpret_cast<rssm::WideWgradTile*>(ws + W.tiles), s), "tile table upload launch"))
+        return 1;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);

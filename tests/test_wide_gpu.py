@@ -156,3 +156,47 @@ def test_wide_cfg3_full_size_properties(ops):
     for a, b in zip(g1, g2):
         assert bool(torch.isfinite(a).all())
         torch.testing.assert_close(b, 2 * a, rtol=0, atol=2e-2 * max(float(a.abs().max()), 1e-6))
+
+
+def test_wide_family_forward_backward_replays_from_a_cuda_graph(ops):
+    """The wide family's forward + backward (weight packing, persistent kernels, pre-pass, weight-gradient tile table, all the
+    non-recurrent kernels) captured ONCE into a CUDA graph and replayed on new data: nothing in the path may be a pageable
+    host-to-device copy or depend on host state that a later call could change (the weight-gradient tile table is a by-value
+    kernel parameter).  Replays must match eager calls on the same data."""
+    R, P = ops
+    D, B, T, K, C = 128, 96, 3, 4, 4
+    params = {k: v.cuda() for k, v in H.make_params(H.mr_shapes(D)).items()}
+    w = [t.clone().requires_grad_(True) for t in P.mrssm_weight_list(params)]
+    static = cuda(H.mrssm_inputs(B, T, C, K, D=D))
+    static["u_prior"] = None
+    up = torch.randn(B, T, D + 16, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3))
+
+    def step(inp):
+        out = R.mrssm_rollout(w, class_size=K, precision=1, **inp)
+        grads = torch.autograd.grad((out["feature"] * up).sum() + out["kl"].mean(), w)
+        return out["feature"], grads
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step(static)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        g_feature, g_grads = step(static)
+    for seed in (11, 12):
+        fresh = cuda(H.mrssm_inputs(B, T, C, K, seed=seed, D=D))
+        for k, v in static.items():
+            if v is not None:
+                v.copy_(fresh[k])
+        # an unrelated wide call with OTHER sizes in between must not disturb the captured graph
+        other = cuda(H.mrssm_inputs(40, 2, C, K, D=D))
+        other["u_prior"] = None
+        step(other)
+        graph.replay()
+        torch.cuda.synchronize()
+        e_feature, e_grads = step(static)
+        assert torch.equal(g_feature, e_feature)
+        for a, b in zip(g_grads, e_grads):  # atomics: summation order differs between launches
+            torch.testing.assert_close(a, b, rtol=0, atol=2e-3 * max(float(b.abs().max()), 1e-6))
