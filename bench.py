@@ -150,14 +150,18 @@ class DirectMtrssm:
             "dpre": torch.empty(B, T, _lib.MTRSSM_DPRE_FLOATS, device=device, dtype=_lib.record_dtype(precision)),
         }
         sizes = [w.numel() for w in self.weights]
-        self.flat_grad = torch.zeros(sum(sizes), device=device)
-        self.gws = [g_.view_as(w) for g_, w in zip(self.flat_grad.split(sizes), self.weights)]
+        # two gradient buckets: with N > 1 the NCCL allreduce of step i's bucket runs on NCCL's stream under step i+1's kernels
+        self.flat_grads = [torch.zeros(sum(sizes), device=device) for _ in range(2)]
+        self.flat_grad = self.flat_grads[0]
+        gws2 = [[g_.view_as(w) for g_, w in zip(f.split(sizes), self.weights)] for f in self.flat_grads]
+        self.gws = gws2[0]
         L = _lib
         self.c_dims = L.MtrssmDims(B=B, T=T, A=6, E=64, HD=32, LD=32, HH=32, HR=32, CL=4, KL=4, CH=8, KH=2, l_tau=2.0, h_tau=4.0,
                                    precision=precision)
         fill = lambda st, d: [setattr(st, k, L.ptr(v)) for k, v in d.items()] and st  # noqa: E731
         self.c_w = fill(L.MtrssmWeights(), dict(zip(L.MT_WEIGHT_FIELDS, self.weights)))
-        self.c_gw = fill(L.MtrssmWeightGrads(), dict(zip(L.MT_WEIGHT_FIELDS, self.gws)))
+        self.c_gws = [fill(L.MtrssmWeightGrads(), dict(zip(L.MT_WEIGHT_FIELDS, g_))) for g_ in gws2]
+        self.c_gw = self.c_gws[0]
         self.c_in = fill(L.MtrssmInputs(), self.inp)
         self.c_out = fill(L.MtrssmOutputs(), self.out)
         self.c_up = fill(L.MtrssmUpstream(), {"d_feature": self.d_feature, "d_kl_l": self.d_kl, "d_kl_h": self.d_kl})
@@ -170,14 +174,14 @@ class DirectMtrssm:
     def bwd_data(self) -> None:
         self.lib.call("rssm_mtrssm_rollout_bwd", self.c_dims, self.c_w, self.c_in, self.c_out, self.c_up, self.c_gin, None)
 
-    def bwd_fused(self) -> None:
-        """bf16 path: BPTT + weight gradients in one kernel (no dpre round trip)."""
-        self.flat_grad.zero_()
-        self.lib.call("rssm_mtrssm_rollout_bwd", self.c_dims, self.c_w, self.c_in, self.c_out, self.c_up, self.c_gin, self.c_gw)
+    def bwd_fused(self, k: int = 0) -> None:
+        """bf16 path: BPTT + weight gradients in one kernel (no dpre round trip); gradients into bucket k."""
+        self.flat_grads[k].zero_()
+        self.lib.call("rssm_mtrssm_rollout_bwd", self.c_dims, self.c_w, self.c_in, self.c_out, self.c_up, self.c_gin, self.c_gws[k])
 
-    def wgrad(self) -> None:
-        self.flat_grad.zero_()
-        self.lib.call("rssm_mtrssm_wgrad", self.c_dims, self.c_in, self.c_out, self.gin["dpre"].data_ptr(), self.c_gw)
+    def wgrad(self, k: int = 0) -> None:
+        self.flat_grads[k].zero_()
+        self.lib.call("rssm_mtrssm_wgrad", self.c_dims, self.c_in, self.c_out, self.gin["dpre"].data_ptr(), self.c_gws[k])
 
     def input_bytes(self) -> int:
         return sum(v.numel() * 4 for v in self.inp.values())
@@ -186,27 +190,42 @@ class DirectMtrssm:
 def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
     import torch.distributed as dist
 
+    works = [None, None]  # the in-flight allreduce of each gradient bucket
+    count = [0]
+
     def step(evs=None):
+        k = count[0] & 1
+        count[0] += 1
+        if works[k] is not None:  # bucket k is about to be rewritten: its allreduce (two steps ago) must have finished
+            works[k].wait()
+            works[k] = None
         if evs:
             evs[0].record()
         run.fwd()
         if evs:
             evs[1].record()
         if run.fused:
-            run.bwd_fused()
+            run.bwd_fused(k)
         else:
             run.bwd_data()
         if evs:
             evs[2].record()
         if not run.fused:
-            run.wgrad()
-        if world > 1:
-            dist.all_reduce(run.flat_grad)
+            run.wgrad(k)
+        if world > 1:  # one NCCL allreduce of the 66 KB bucket per step, on NCCL's stream: it overlaps the NEXT step's kernels
+            works[k] = dist.all_reduce(run.flat_grads[k], async_op=True)
         if evs:
             evs[3].record()
 
+    def drain():
+        for k in range(2):
+            if works[k] is not None:
+                works[k].wait()
+                works[k] = None
+
     for _ in range(warmup):
         step()
+    drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -216,6 +235,7 @@ def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
     start.record()
     for i in range(steps):
         step(evs[i])
+    drain()  # every allreduce of the timed steps completes inside the timed region
     end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -230,7 +250,8 @@ def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
             "wgrad_ms": statistics.mean(seg[2])}
 
 
-def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int, device: torch.device, host_bf16: bool = False) -> dict:
+def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int, device: torch.device, host_bf16: bool = False,
+             prior_sample: bool = True) -> dict:
     """Same metric through the public API with HOST buffers, as a training step sees it: the step's encoder outputs,
     actions and initial state are copied from pinned host memory (H2D), the noise is drawn on the device (as
     MoPoE_MMTRSSM.rollout_representation does), the rollout + autograd run through `rollout_ops.mtrssm_rollout`, the
@@ -244,7 +265,7 @@ def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int
 
     params = {k: v.to(device).requires_grad_(True) for k, v in synthetic.mtrssm_params().items()}
     weights = mtrssm_weight_list(params)
-    batch = synthetic.mtrssm_batch(B, T)
+    batch = synthetic.mtrssm_batch(B, T, prior_noise=prior_sample)
     # host_bf16 (side measurement only): the two embedding tensors wait on the host in bf16 -- what an autocast encoder emits and
     # what the bf16 policy's contractions consume anyway (the op widens them on the device) -- halving the PCIe bytes
     half = lambda k, v: v.bfloat16() if host_bf16 and k.startswith("embed_") else v  # noqa: E731
@@ -548,7 +569,7 @@ def cpu_oracle_rate(B: int, T: int, literal: bool, budget_s: float) -> dict:
 
     dims = dict(CL=4, KL=4, CH=8, KH=2, l_tau=2.0, h_tau=4.0)
     params = {k: v.clone().requires_grad_(True) for k, v in synthetic.mtrssm_params().items()}
-    inp = synthetic.mtrssm_batch(B, T)
+    inp = synthetic.mtrssm_batch(B, T, prior_noise=True)
     g = torch.Generator().manual_seed(7)
     up = torch.randn(B, T, 96, generator=g)
 
@@ -557,7 +578,7 @@ def cpu_oracle_rate(B: int, T: int, literal: bool, budget_s: float) -> dict:
             x = {k: v for k, v in inp.items() if not k.startswith("u_")}
             res = O.mtrssm_rollout_literal(params, dims=dims, **x)
         else:
-            res = O.mtrssm_rollout(params, dims=dims, u_prior_l=None, u_prior_h=None, **inp)
+            res = O.mtrssm_rollout(params, dims=dims, **inp)
         kl_l = O.kl_per_sample(res["post_probs_l"], res["prior_probs_l"], True).mean()
         kl_h = O.kl_per_sample(res["post_probs_h"], res["prior_probs_h"], True).mean()
         loss = (res["post_feature"] * up).sum() + kl_l + kl_h
@@ -579,26 +600,92 @@ def cpu_oracle_rate(B: int, T: int, literal: bool, budget_s: float) -> dict:
                       f"B={B} T={T} of the same workload, median of {len(times)}"}
 
 
+def workload_config(B: int, T: int, world: int, prior_sample: bool) -> dict:
+    """`config` of the JSON line: identical in both arms (the reference arm times the same workload on a bounded sample)."""
+    input_mb = ((6 + 2 * 64 + 12 + (12 if prior_sample else 0)) * T + 160) * 4 * B / 1e6  # actions, embeddings, uniforms, initial state
+    cfg = {
+        "workload": "cfg2: MoPoE-MMTRSSM default.yaml sizes (hd=ld=32, hs=ls=16, E=64, A=6), rollout fwd+bwd on synthetic "
+                    "vision+audio embeddings/actions", "batch_per_gpu": B, "seq_len": T, "global_batch": world * B,
+        "parallelism": f"dp{world} (batch-sharded, one flat-bucket NCCL allreduce of the weight gradients)" if world > 1 else "single GPU",
+        "prior_samples": "drawn and written (what MoPoE_MMTRSSM.rollout_representation launches)" if prior_sample else "not drawn (bytes subtracted)",
+    }
+    cfg["l2"] = f"inputs {input_mb:.0f} MB + outputs/records per step exceed the 126 MB L2 (no flush needed)"
+    return cfg
+
+
 def run_reference(args: argparse.Namespace) -> None:
+    """Reference arm: the reference's own CPU formulation of the path (the oracle's LITERAL variant: Python T loop, State-style
+    per-step draws from the global RNG, per-step cats and T-way stacks) on ALL host cores.  `/root/reference` itself cannot be
+    imported or installed (lightning / torchrl / distribution_extension / cnn absent, hatchling missing: DESIGN.md), so `kind` is
+    "port".  Every step is a bounded sample of the SAME workload (same dims, same T, batch B_s <= B sized from a probe so that
+    W + K steps fit `--ref-budget-s`); the rate is also reported at B = 256 so the batch dependence is visible."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B = min(args.batch, max(args.cpu_batch, 256))
-    for _ in range(max(0, min(args.warmup, 1))):
-        pass
-    res = cpu_oracle_rate(B, args.seq_len, literal=True, budget_s=6.0 * max(1, min(args.steps, 5)))
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(ncpu)  # torchrun exports OMP_NUM_THREADS=1: undo it, this arm uses every host core
+    T, K, W = args.seq_len, max(1, args.steps), max(1, args.warmup)
+    probe = cpu_oracle_rate(256, T, literal=True, budget_s=2.0)
+    per_step_s = args.ref_budget_s * 0.85 / (K + W)
+    Bs = int(probe["value"] * per_step_s / T) // 256 * 256
+    Bs = max(256, min(args.batch, Bs))
+    from multimodal_mtrssm_b200 import synthetic
+    from oracle import rssm_oracle as O
+
+    dims = dict(CL=4, KL=4, CH=8, KH=2, l_tau=2.0, h_tau=4.0)
+    params = {k: v.clone().requires_grad_(True) for k, v in synthetic.mtrssm_params().items()}
+    inp = {k: v for k, v in synthetic.mtrssm_batch(Bs, T).items() if not k.startswith("u_")}
+    up = torch.randn(Bs, T, 96, generator=torch.Generator().manual_seed(7))
+
+    def step() -> None:
+        res = O.mtrssm_rollout_literal(params, dims=dims, **inp)
+        kl_l = O.kl_per_sample(res["post_probs_l"], res["prior_probs_l"], True).mean()
+        kl_h = O.kl_per_sample(res["post_probs_h"], res["prior_probs_h"], True).mean()
+        torch.autograd.grad((res["post_feature"] * up).sum() + kl_l + kl_h, list(params.values()), allow_unused=True)
+
+    t_start = time.perf_counter()
+    for _ in range(W):
+        step()
+    times = []
+    for _ in range(K):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > args.ref_budget_s * 1.5:  # a slower box than the probe suggested: stop early, say so
+            break
+    total = sum(times)
+    value = Bs * T * len(times) / total
+    sample = (f"oracle literal (reference structure, global RNG) fp32 fwd+autograd bwd on {ncpu} host threads; every step = B_s={Bs} "
+              f"sequences of the B={args.batch} workload, {W} warm-up + {len(times)} timed steps; at B=256: {probe['value']:.3e} steps/s")
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": W, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MoPoE-MMTRSSM default.yaml sizes, rollout fwd+bwd, T=%d, bounded CPU sample B=%d" % (args.seq_len, B)},
-        "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port", "sample": res["sample"]},
-        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(args.batch, T, args.gpus, not args.no_prior_sample),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncpu, "kind": "port", "sample": sample,
+                         "rate_at_B256": probe["value"], "sample_batch": Bs},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "the reference cannot be imported here (lightning/torchrl/distribution_extension absent, SURVEY.md §8(c)); "
                 "this is the oracle restatement with the reference's per-step structure on the host cores",
     }
     print(json.dumps(line))
+
+
+def measured_traffic(stamp: str, kernel: str, B: int, T: int, prior_sample: bool) -> float | None:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture of THIS build
+    (profiles/traffic.json: {"build_stamp", "batch", "seq_len", "prior_sample", "kernels": {name: bytes}}); None when the library
+    was rebuilt since (stamp mismatch) or the workload differs -- never a stale constant."""
+    f = ROOT / "profiles" / "traffic.json"
+    if not f.exists():
+        return None
+    try:
+        d = json.loads(f.read_text())
+    except ValueError:
+        return None
+    if d.get("build_stamp") != stamp or (d.get("batch"), d.get("seq_len"), d.get("prior_sample")) != (B, T, prior_sample):
+        return None
+    return d.get("kernels", {}).get(kernel)
 
 
 def main() -> None:
@@ -620,17 +707,26 @@ def main() -> None:
 
         dist.init_process_group("nccl", device_id=device)
     from multimodal_mtrssm_b200 import _lib
+    from multimodal_mtrssm_b200.build import build_stamp
 
     precision = {"bf16": _lib.PRECISION_BF16, "bf16_fused": _lib.PRECISION_BF16_FUSED, "fp32": _lib.PRECISION_FP32}[args.precision]
     B, T = args.batch, args.seq_len
+    prior_sample = not args.no_prior_sample
+    fwd_bytes_bt, step_bytes_bt = bytes_per_bt(prior_sample)
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peaks = json.loads(peaks_file.read_text())
+        peak, peak_src = peaks["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peaks, peak, peak_src = {}, 6650.0, "B200_PROFILING.md fallback (of fallback)"
     launches0 = _lib.launch_count()
-    run = DirectMtrssm(B, T, precision, device)
+    run = DirectMtrssm(B, T, precision, device, prior_sample)
     # nvidia-smi delivers its first sample after ~100 ms and a short timed region (K steps of ~2 ms) may end before that:
     # sample from before the warm-up until the end-to-end measurement is done (the GPU is under this load throughout)
     sampler = ClockSampler(local) if rank == 0 else None
     res = time_direct(run, args.steps, args.warmup, world)
     launches = (_lib.launch_count() - launches0) // (args.steps + args.warmup)
-    e2e = time_e2e(B, T, precision, args.steps, args.warmup, world, device)
+    e2e = time_e2e(B, T, precision, args.steps, args.warmup, world, device, prior_sample=prior_sample)
     if sampler and len(sampler.samples) < 3:  # still too short: keep the same kernels running for ~0.5 s
         t_end = time.perf_counter() + 0.5
         while time.perf_counter() < t_end:
@@ -638,49 +734,69 @@ def main() -> None:
             torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
 
-    extras = {}
+    def frac_of_hbm(b_: int, t_: int, ms: float) -> float:
+        return step_bytes_bt * b_ * t_ / (ms * 1e-3) / 1e9 / peak
+
+    extras, summary = {}, {}
     if not args.no_extras:  # every rank takes part (gradient allreduce inside)
         train = [time_train_step(b_, T, world, device, ac, graphed=gr)
                  for b_, ac, gr in ((8, True, False), (8, True, True), (256, True, False), (256, True, True), (256, False, False))]
         if rank == 0:
             extras["train_step"] = {"metric": "train sequences/s (full MoPoE-MMTRSSM training step, default.yaml model)",
                                     "runs": train}
+            best = max(train, key=lambda r_: r_["train_seq_per_sec"])
+            summary["train_seq_per_sec"] = {"value": round(best["train_seq_per_sec"], 1), "n_gpus": world, "B_per_gpu": best["B_per_gpu"],
+                                            "ms_per_step": round(best["ms_per_step"], 3), "cuda_graph": best["cuda_graph"]}
     if rank == 0 and not args.no_extras:
         n2 = max(3, args.steps // 2)
         for name, prec in (("fp32_path", _lib.PRECISION_FP32), ("bf16_two_kernel_backward_path", _lib.PRECISION_BF16),
                            ("bf16_fused_backward_path", _lib.PRECISION_BF16_FUSED)):
             if prec == precision:
                 continue
-            other = DirectMtrssm(B, T, prec, device)
+            other = DirectMtrssm(B, T, prec, device, prior_sample)
             r2 = time_direct(other, n2, 3, 1)
             extras[name] = {"value": B * T * n2 / (r2["total_ms"] * 1e-3), "ms_per_step": r2["total_ms"] / n2,
-                            "fwd_ms": r2["fwd_ms"], "bwd_ms": r2["bwd_ms"], "wgrad_ms": r2["wgrad_ms"]}
+                            "fwd_ms": r2["fwd_ms"], "bwd_ms": r2["bwd_ms"], "wgrad_ms": r2["wgrad_ms"],
+                            "frac_of_hbm": frac_of_hbm(B, T, r2["total_ms"] / n2)}
             del other
-        small = DirectMtrssm(8, T, precision, device)
+        if "fp32_path" in extras:
+            summary["fp32_path"] = {"ms_per_step": round(extras["fp32_path"]["ms_per_step"], 3), "frac_of_hbm": round(extras["fp32_path"]["frac_of_hbm"], 3),
+                                    "parity": "1e-5 vs oracle (tests)"}
+        small = DirectMtrssm(8, T, precision, device, prior_sample)
         r3 = time_direct(small, 50, 10, 1)
         extras["default_batch8"] = {"B": 8, "T": T, "value": 8 * T * 50 / (r3["total_ms"] * 1e-3), "us_per_step": r3["total_ms"] / 50 * 1e3}
+        summary["default_yaml_B8_fwd_bwd_us"] = round(extras["default_batch8"]["us_per_step"], 1)
         del small
         # the other batch sizes SURVEY.md 8(d) asks for, and cfg4 (long horizon); same dims, same kernels
         extras["other_workloads"] = []
-        for name, b_, t_ in (("cfg2 B=256", 256, T), ("cfg2 B=4096", 4096, T), ("cfg2 B=16384", 16384, T), ("cfg4 B=256 T=512", 256, 512)):
-            w = DirectMtrssm(b_, t_, precision, device)
+        for name, b_, t_ in (("cfg2 B=256", 256, T), ("cfg2 B=4096", 4096, T), ("cfg2 B=16384", 16384, T), ("cfg4 B=256 T=512", 256, 512),
+                             ("one tile B=16 T=512 (serial chain)", 16, 512)):
+            w = DirectMtrssm(b_, t_, precision, device, prior_sample)
             rr = time_direct(w, 10, 3, 1)
             extras["other_workloads"].append({"workload": name, "B": b_, "T": t_, "value": b_ * t_ * 10 / (rr["total_ms"] * 1e-3),
-                                              "ms_per_step": rr["total_ms"] / 10,
-                                              "frac_of_hbm": STEP_BYTES_PER_BT * b_ * t_ / (rr["total_ms"] / 10 * 1e-3) / 1e9 / 6464.9})
+                                              "ms_per_step": rr["total_ms"] / 10, "fwd_ms": rr["fwd_ms"], "bwd_ms": rr["bwd_ms"] + rr["wgrad_ms"],
+                                              "frac_of_hbm": frac_of_hbm(b_, t_, rr["total_ms"] / 10)})
             del w
+        cfg4, chain = extras["other_workloads"][3], extras["other_workloads"][4]
+        # serial-chain lower bound T x t_step_min: t_step_min = one 16-sequence tile alone on the GPU, fwd + bwd
+        summary["cfg4_T512_B256"] = {"ms": round(cfg4["ms_per_step"], 3), "steps_per_s": round(cfg4["value"]), "frac_of_hbm": round(cfg4["frac_of_hbm"], 4),
+                                     "serial_chain_bound_ms": round(chain["ms_per_step"], 3),
+                                     "t_step_min_us": round(chain["ms_per_step"] / 512 * 1e3, 2)}
         mr_prec = _lib.PRECISION_FP32 if precision == _lib.PRECISION_FP32 else _lib.PRECISION_BF16
         extras["mrssm_workloads"] = [time_mrssm(8, T, mr_prec, device), time_mrssm(16384, T, mr_prec, device)]
+        summary["cfg1_mrssm_B8_fwd_bwd_us"] = round(extras["mrssm_workloads"][0]["ms_per_step"] * 1e3, 1)
         if precision != _lib.PRECISION_FP32:  # the wide family is the bf16 tensor-core path
             extras["cfg3_wide_mrssm"] = time_wide_cfg3(device)
             extras["cfg3_wide_mrssm"]["reference_eager_on_this_gpu"] = reference_eager_gpu_cfg3(device)
             r = extras["cfg3_wide_mrssm"]
             r["speedup_vs_reference_eager_gpu"] = r["reference_eager_on_this_gpu"]["ms_per_step"] / r["ms_per_step"]
+            summary["cfg3_B1024_T64_D512"] = {"ms": round(r["ms_per_step"], 3), "tflops": round(r["roofline"]["achieved"], 1),
+                                              "frac_of_tensor": round(r["roofline"]["frac"], 3), "x_vs_eager_gpu": round(r["speedup_vs_reference_eager_gpu"], 1)}
         extras["reference_eager_on_this_gpu"] = reference_eager_gpu_cfg2(device, B, T)
         extras["reference_eager_on_this_gpu"]["speedup_of_value"] = (B * T / (res["total_ms"] / args.steps * 1e-3)) / extras["reference_eager_on_this_gpu"]["value"]
-        extras["e2e_bf16_host_embeddings"] = time_e2e(B, T, precision, 10, 4, 1, device, host_bf16=True)
-        pk = ROOT / "MEASURED_PEAKS.json"
-        extras["likelihood_f3"] = time_likelihood(device, json.loads(pk.read_text())["hbm_gbs"] if pk.exists() else 6650.0)
+        summary["x_vs_oracle_eager_same_gpu_same_batch"] = round(extras["reference_eager_on_this_gpu"]["speedup_of_value"], 1)
+        extras["e2e_bf16_host_embeddings"] = time_e2e(B, T, precision, 10, 4, 1, device, host_bf16=True, prior_sample=prior_sample)
+        extras["likelihood_f3"] = time_likelihood(device, peak)
     if world > 1:
         import torch.distributed as dist
 
@@ -688,56 +804,50 @@ def main() -> None:
     if rank != 0:
         return
 
-    peaks_file = ROOT / "MEASURED_PEAKS.json"
-    if peaks_file.exists():
-        peak, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
-    else:
-        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     ms_step = res["total_ms"] / args.steps
     value = world * B * T / (ms_step * 1e-3)
     seg = {"mtrssm_fwd_kernel": res["fwd_ms"], "mtrssm_bwd_kernel": res["bwd_ms"], "wgrad_kernel": res["wgrad_ms"]}
     if run.fused:
-        seg = {"mtrssm_fwd_kernel": res["fwd_ms"], "mtrssm_bwd_fused_kernel": res["bwd_ms"] + res["wgrad_ms"]}
+        seg = {"mtrssm_fwd2_kernel": res["fwd_ms"], "mtrssm_bwd_fused2_kernel": res["bwd_ms"] + res["wgrad_ms"]}
     dominant = max(seg, key=seg.get)
     # algorithmic bytes of the dominant launch: forward = fwd I/O; backward (bwd kernel + its wgrad pass) = fwd I/O again
-    if dominant == "mtrssm_fwd_kernel":
-        alg_bytes, dur_ms, what = FWD_BYTES_PER_BT * B * T, seg[dominant], "forward rollout kernel"
+    if dominant.startswith("mtrssm_fwd"):
+        alg_bytes, dur_ms, what = fwd_bytes_bt * B * T, seg[dominant], "forward rollout kernel"
     else:
-        alg_bytes, dur_ms = FWD_BYTES_PER_BT * B * T, res["bwd_ms"] + res["wgrad_ms"]
+        alg_bytes, dur_ms = fwd_bytes_bt * B * T, res["bwd_ms"] + res["wgrad_ms"]
         what = ("fused backward kernel (BPTT + weight gradients)" if run.fused
                 else "backward = BPTT kernel + weight-gradient kernel (dominant: %s)" % dominant)
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of exactly this workload
-    # (profiles/r1_e_ncu_summary.txt, r1_g_ncu_summary.txt); None for any other size
-    traffic = None
-    if (B, T) == (37888, 30) and precision == _lib.PRECISION_BF16:
-        traffic = 2.156e9 if dominant == "mtrssm_fwd_kernel" else 3.014e9 + 2.230e9
-    elif (B, T) == (37888, 30) and precision == _lib.PRECISION_BF16_FUSED:
-        traffic = 2.156e9 if dominant == "mtrssm_fwd_kernel" else 2.888e9  # profiles/r1_n_ncu_summary.txt (2.2746 GB read + 0.6137 GB written)
+    stamp = build_stamp()
+    traffic = measured_traffic(stamp, dominant, B, T, prior_sample) if run.fused else None
+    summary["kernel_ms"] = {k: round(v, 4) for k, v in seg.items()}
+    summary["step_frac_of_hbm"] = round(step_bytes_bt * B * T / (ms_step * 1e-3) / 1e9 / peak, 4)
+    summary["fwd_frac_of_hbm"] = round(fwd_bytes_bt * B * T / (res["fwd_ms"] * 1e-3) / 1e9 / peak, 4)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if precision == _lib.PRECISION_FP32 else "bf16", "data": "synthetic",
-        "config": {
-            "workload": "cfg2: MoPoE-MMTRSSM default.yaml sizes (hd=ld=32, hs=ls=16, E=64, A=6), rollout fwd+bwd on synthetic "
-                        "vision+audio embeddings/actions", "batch_per_gpu": B, "seq_len": T, "global_batch": world * B,
-            "parallelism": f"dp{world} (batch-sharded, one flat-bucket NCCL allreduce of the weight gradients)" if world > 1 else "single GPU",
-            "l2": f"inputs {run.input_bytes() / 1e6:.0f} MB + outputs/records per step exceed the 126 MB L2 (no flush needed)",
-            "precision": "bf16 operands / fp32 accumulate+state (tensor-core path)" if precision != _lib.PRECISION_FP32
-                         else "3-way bf16 split, fp32-level accuracy",
-        },
+        "config": workload_config(B, T, world, prior_sample),
         "kernel_ms": seg,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": what, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes},
-        "roofline_step": {"algorithmic_bytes": STEP_BYTES_PER_BT * B * T, "achieved_gbs": STEP_BYTES_PER_BT * B * T / (ms_step * 1e-3) / 1e9,
-                          "frac_of_hbm": STEP_BYTES_PER_BT * B * T / (ms_step * 1e-3) / 1e9 / peak,
+                     "kernel": what, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                     "algorithmic_bytes_per_bt": fwd_bytes_bt, "build_stamp": stamp[:16]},
+        "roofline_step": {"algorithmic_bytes": step_bytes_bt * B * T, "achieved_gbs": step_bytes_bt * B * T / (ms_step * 1e-3) / 1e9,
+                          "frac_of_hbm": step_bytes_bt * B * T / (ms_step * 1e-3) / 1e9 / peak,
                           "tensor_tflops": 3 * FWD_FLOPS_PER_BT * B * T / (ms_step * 1e-3) / 1e12},
+        "precision": "bf16 operands / fp32 accumulate+state (tensor-core path)" if precision != _lib.PRECISION_FP32 else "3-way bf16 split, fp32-level accuracy",
         "e2e": e2e | {"host_numa_bound": numa_bound}, "gpu_launches": int(launches), "clocks": clocks, **extras,
     }
     if not args.no_cpu_baseline and world == 1:
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        torch.set_num_threads(ncpu)
         cb = cpu_oracle_rate(args.cpu_batch, T, literal=False, budget_s=12.0)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "sample")} | {"kind": "port"}
+    # the compact summary goes LAST (the driver keeps the tail of stdout) and, abridged, into `roofline` (the driver keeps that dict
+    # whole; `config` stays identical to the reference arm's)
+    line["summary"] = summary
+    line["roofline"]["summary"] = {k: summary[k] for k in ("train_seq_per_sec", "cfg4_T512_B256", "cfg3_B1024_T64_D512", "fp32_path", "step_frac_of_hbm")
+                                   if k in summary}
     print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

@@ -31,7 +31,7 @@
  *   - return value: 0 = ok, non-zero = error; rssm_last_error() returns a thread-local message.
  *   - supported sizes (anything else returns an error, never a fallback):
  *       default family: deter = hidden = 32, stochastic size C*K = 16 with K in {2,4,8,16}, embed = 64, action even, 2..8.
- *       wide family (MoPoE-MRSSM only, RSSM_PRECISION_BF16 only): deter = hidden = D, D % 64 == 0, 64 <= D <= 512
+ *       wide family (MoPoE-MRSSM only, RSSM_PRECISION_BF16 only): deter = hidden = D in {128, 256, 384, 512}
  *       (BASELINE.json cfg3 "hidden 512"), same stochastic / embed sizes, action 1..8.  The wide family needs a caller-
  *       provided workspace and a larger saved record: size them with rssm_mrssm_workspace_bytes / rssm_mrssm_saved_bytes.
  *   - precision: RSSM_PRECISION_FP32 = every contraction as a 3-way bf16 split on the tensor cores with fp32

@@ -35,15 +35,36 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
+def build_stamp() -> str:
+    """Hash of the sources + flags the shipped library was built from (bench.py keys its ncu traffic figures by it)."""
+    return _stamp()
+
+
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the CUDA sources into `librssm_rollout.so` next to this file (skipped when up to date)."""
+    """Compile the CUDA sources into `librssm_rollout.so` next to this file (skipped when up to date).
+
+    One process per GPU means N ranks may get here at once: the stamp check and the build run under an exclusive `flock`, the
+    objects go to a per-process directory and the library is linked to a temporary name and `os.replace`d into place, so a rank
+    can never load a half-written file."""
+    import fcntl
+
+    obj_root = PKG / "build"
+    obj_root.mkdir(exist_ok=True)
+    with open(obj_root / "lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
     stamp_file = PKG / "build" / "stamp"
     stamp = _stamp()
     if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
         return LIB
     nvcc = _nvcc()
     obj_dir = PKG / "build"
-    obj_dir.mkdir(exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
 
     def compile_one(src: str) -> Path:
@@ -60,10 +81,13 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
         objs = list(pool.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs)]  # cudart linked statically (nvcc default)
+    tmp = LIB.with_suffix(f".so.tmp{os.getpid()}")
+    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs)]  # cudart linked statically (nvcc default)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    os.replace(tmp, LIB)
     stamp_file.write_text(stamp)
     return LIB
 
