@@ -42,7 +42,7 @@
 // the launcher synchronises and prints the mean interval between consecutive stamps (cycles) for both warps of the tile.
 #ifdef FZ_TIMING
 #include <stdio.h>
-__device__ long long fz_dbg[2][1024][12];
+__device__ long long fz_dbg[3][1024][12];
 #define FZ_TS(i)                                                                                                  \
     do {                                                                                                          \
         if (lane == 0 && blockIdx.x == 0 && tile == 0 && grp == (int)blockIdx.x && t < 1024) fz_dbg[role][t][i] = clock64(); \
@@ -166,6 +166,24 @@ __device__ __forceinline__ void head_bwd_elu(const float (&dlogit)[2][4], const 
     to_afrag<1, 2>(f1, dhid);
 }
 
+// [action | ones] X-operand columns of one step: lanes with t < 2 own action columns 4t .. 4t+3, column 8 is the ones column
+__device__ __forceinline__ void load_action_columns(float (&actc)[2][4], const float* actions, size_t iA, size_t iB, int A, bool valid,
+                                                    const Rows& r) {
+    if (valid && r.t < 2) {
+        const float* aA = actions + iA * A + 4 * r.t;
+        const float* aB = actions + iB * A + 4 * r.t;
+        if (4 * r.t < A) {
+            const float2 x = *reinterpret_cast<const float2*>(aA), y = *reinterpret_cast<const float2*>(aB);
+            actc[0][0] = x.x, actc[0][1] = x.y, actc[0][2] = y.x, actc[0][3] = y.y;
+        }
+        if (4 * r.t + 2 < A) {
+            const float2 x = *reinterpret_cast<const float2*>(aA + 2), y = *reinterpret_cast<const float2*>(aB + 2);
+            actc[1][0] = x.x, actc[1][1] = x.y, actc[1][2] = y.x, actc[1][3] = y.y;
+        }
+    }
+    if (r.t == 2) actc[0][0] = actc[0][2] = 1.f;
+}
+
 // =====================================================================================================================
 // Version 2: TWO warps per 16-sequence tile.
 // The single-warp kernel above needs ~46 KB of shared memory per tile, i.e. four tiles = four warps per SM = one warp per
@@ -204,10 +222,10 @@ constexpr int T_COLS = 400;
 enum { BAR_DF, BAR_FT, BAR_E, BAR_END, BAR_M, NBAR };  // per tile
 }  // namespace fz2
 
-__device__ __forceinline__ void nbar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void nbar_arrive(int id) {
+__device__ __forceinline__ void nbar_sync(int id, int count = 64) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int count = 64) {
     __threadfence_block();
-    asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory");
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 // C tiles <-> the lane-linear fp32 exchange buffers ([tile][32 lanes][4 floats]: conflict-free 16-byte accesses)
 template <int NT>
@@ -224,9 +242,16 @@ __device__ __forceinline__ void xch_load(float (&c)[NT][4], const float* buf, in
     }
 }
 
-template <int KL, int KH>
-__global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmBwdArgs p, const FusedFlushTable ft) {
+// WPT = warps per tile.  2: core + mod (above).  3: core + mod + AUX -- clock64 timelines (profiles/r2_b_timing.txt) show both
+// warps of the two-warp kernel busy ~8.7 k cycles per step with NO waiting on each other: each is a serial instruction stream at
+// ~0.1 instructions per cycle, and a third of it is "service" work with no place in the recurrence.  The aux warp takes that
+// work: it converts the feature row and the fp32 embeddings into the tcgen05 operand images, issues the end-of-step MMA group
+// (and the embedding MMA), computes the embedding / action gradients from the dY images (d_embed = dY1 . W1e, d_action = dY_l .
+// W_in) and stores them, and refills the feature-row stage.  12 warps per SM instead of 8, <= 168 registers each.
+template <int KL, int KH, int WPT>
+__global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const MtrssmBwdArgs p, const FusedFlushTable ft) {
     constexpr int NS = 1;
+    static_assert(WPT == 2 || WPT == 3, "two (core, mod) or three (core, mod, aux) warps per tile");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars_all[4][fz2::NBAR];
     __shared__ uint32_t tmem_base_s;
@@ -260,10 +285,10 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
     }
     __syncthreads();
     pack_run<NS>(tb, tid, nthr);
-    const int lane = tid & 31, warp = tid >> 5, tile = warp >> 1, role = warp & 1;  // role 0 = core, 1 = mod
+    const int lane = tid & 31, warp = tid >> 5, tile = warp / WPT, role = warp % WPT;  // role 0 = core, 1 = mod, 2 = aux
     unsigned char* my = smem_raw + (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + (size_t)tile * fz2::BYTES;
-    // zero the tile's images and exchange buffers once (the two warps of the tile split the range)
-    for (int i = lane + 32 * role; i < fz2::BYTES / 16; i += 64) reinterpret_cast<uint4*>(my)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // zero the tile's images and exchange buffers once (the warps of the tile split the range)
+    for (int i = lane + 32 * role; i < fz2::BYTES / 16; i += 32 * WPT) reinterpret_cast<uint4*>(my)[i] = make_uint4(0u, 0u, 0u, 0u);
     uint64_t* bars = bars_all[tile];
     if (role == 0 && lane == 0) {
 #pragma unroll
@@ -295,7 +320,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
     // Persistent over tile groups: a CTA (2 or 4 tiles = 4 or 8 warps) walks groups blockIdx.x, blockIdx.x + gridDim.x, ... and keeps
     // accumulating the weight gradients in the SAME TMEM columns, so the weight packing above, the TMEM allocation and the
     // read-back + atomics below happen once per SM instead of once per group (4 groups per SM at the bench size).
-    const int tpc = nthr >> 6, ngroups = ((p.B + 15) / 16 + tpc - 1) / tpc;
+    const int tpc = nthr / (32 * WPT), ngroups = ((p.B + 15) / 16 + tpc - 1) / tpc;
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int row0 = (grp * tpc + tile) * 16;
     if (row0 < p.B) {
@@ -309,7 +334,35 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
         float* xddl = reinterpret_cast<float*>(my + fz2::XDDL);
         float* xdzl = reinterpret_cast<float*>(my + fz2::XDZL);
         const uint32_t s_dop = smem_u32(dop), s_sv = smem_u32(svop), s_dy = smem_u32(dy), s_ones = smem_u32(zop) + 5 * fz2::CH;
-        const int bar_x = 1 + 2 * tile, bar_y = 2 + 2 * tile;
+        // named barriers of the tile.  X: mod -> core (+ aux) "my dY columns and XDDL are complete"; Y: core -> mod "d stoch_l is in
+        // XDZL"; Z (three warps): core -> aux "my dY columns are complete and I am done with the feature-row stage"
+        const int bar_x = 1 + WPT * tile, bar_y = 2 + WPT * tile, bar_z = 3 + WPT * tile;
+        constexpr int X_COUNT = 32 * WPT;
+        (void)bar_z;
+
+        // step 0's cell gradients pair with the INITIAL state (run by the warp that issues the end-of-step MMAs, after the loop)
+        auto pair_initial_state = [&](uint32_t& ph_end) {
+            FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
+            float c4[4][4], c2[2][4], actc[2][4];
+            load_c<4>(c4, p.deter_l0 + (size_t)r.rA * 32, p.deter_l0 + (size_t)r.rB * 32, r.t);
+            store_op<4>(c4, dop, 0, r);
+            load_c<4>(c4, p.deter_h0 + (size_t)r.rA * 32, p.deter_h0 + (size_t)r.rB * 32, r.t);
+            store_op<4>(c4, dop, 32, r);
+            load_c<2>(c2, p.stoch_l0 + (size_t)r.rA * 16, p.stoch_l0 + (size_t)r.rB * 16, r.t);
+            store_op<2>(c2, zop, 0, r);
+            load_c<2>(c2, p.stoch_h0 + (size_t)r.rA * 16, p.stoch_h0 + (size_t)r.rB * 16, r.t);
+            store_op<2>(c2, zop, 16, r);
+            zero_c<2>(actc);
+            load_action_columns(actc, p.actions, (size_t)r.rA * T, (size_t)r.rB * T, A, true, r);
+            store_op<2>(actc, zop, 32, r);
+            FZ_FENCE();
+            __syncwarp();
+            if (FZ_MMA && lane == 0) {
+                umma_acc(tmem + fz2::T_C, s_dop, s_dy + (fz::Y_L / 8) * fz2::CH, 64);  // buffer 0 holds step 0's [L | H]
+                umma_commit(&bars[fz2::BAR_END]);
+            }
+            FZ_WAIT(&bars[fz2::BAR_END], ph_end);
+        };
 
         if (role == 1) {
             // ============================== mod warp: MoPoE backward + audio / vision heads ===============================
@@ -352,8 +405,10 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     prefetch_bulk_l2(p.embed_v + j, 256);
                 }
             };
-            embed_prefetch(T - 2);
-            embed_images(T - 1);
+            if constexpr (WPT == 2) {
+                embed_prefetch(T - 2);
+                embed_images(T - 1);
+            }
             stage_logits(T - 1);
             stage_rest(T - 1);
             const float* dkl_src = p.d_kl_l;  // lanes t = 0 / 1 of a quad fetch rows A / B one step ahead
@@ -459,35 +514,39 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 gemm<NS, 2, 4>(ddl, f1v, wblk<NS>(W, mt::T_V1H), lane);
                 xch_store<4>(ddl, xddl, lane);
                 FZ_FENCE();
-                nbar_arrive(bar_x);  // XDDL and this warp's dY columns are complete (and visible to the async proxy)
+                nbar_arrive(bar_x, X_COUNT);  // XDDL and this warp's dY columns are complete (and visible to the async proxy)
                 FZ_TS(7);
                 // ---- off the critical path: this warp's weight-gradient MMAs, the embedding gradients, next step's staging -------
                 __syncwarp();
                 if (FZ_MMA && lane == 0) {
                     umma_acc(tmem + fz2::T_M, s_sv + 12 * fz2::CH, s_dy + (fz::Y_LA / 8) * fz2::CH, 32);
-                    umma_acc(tmem + fz2::T_EMB, s_sv + 24 * fz2::CH, s_dy + (fz::Y_A1 / 8) * fz2::CH, 64);
+                    if constexpr (WPT == 2) umma_acc(tmem + fz2::T_EMB, s_sv + 24 * fz2::CH, s_dy + (fz::Y_A1 / 8) * fz2::CH, 64);
                     umma_commit(&bars[fz2::BAR_M]);
                 }
+                if constexpr (WPT == 2) {  // three warps per tile: the aux warp computes the embedding gradients from the dY image
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    float de[8][4];
-                    zero_c<8>(de);
-                    gemm<NS, 2, 8>(de, m == 0 ? f1a : f1v, wblk<NS>(W, m == 0 ? mt::T_A1E : mt::T_V1E), lane);
-                    float* dE = m == 0 ? p.d_embed_a : p.d_embed_v;
-                    store_c<8>(de, dE + iA * 64, dE + iB * 64, r);
+                    for (int m = 0; m < 2; ++m) {
+                        float de[8][4];
+                        zero_c<8>(de);
+                        gemm<NS, 2, 8>(de, m == 0 ? f1a : f1v, wblk<NS>(W, m == 0 ? mt::T_A1E : mt::T_V1E), lane);
+                        float* dE = m == 0 ? p.d_embed_a : p.d_embed_v;
+                        store_c<8>(de, dE + iA * 64, dE + iB * 64, r);
+                    }
                 }
                 FZ_TS(8);
-                FZ_WAIT(&bars[fz2::BAR_M], ph_m), ph_m ^= 1;  // own MMAs done: hiddens / embedding images may be rewritten
+                FZ_WAIT(&bars[fz2::BAR_M], ph_m), ph_m ^= 1;  // own MMAs done: the hiddens may be rewritten
                 FZ_TS(9);
                 stage_rest(t - 1);
-                embed_prefetch(t - 2);
-                // (requesting the fp32 embeddings before the embedding-gradient GEMMs and converting them here was measured: the
-                // stall moves into the GEMMs, 245 registers, 0.78 -> 0.815 ms at the bench size -- not kept)
-                if (t > 0) embed_images(t - 1);
+                if constexpr (WPT == 2) {
+                    embed_prefetch(t - 2);
+                    // (requesting the fp32 embeddings before the embedding-gradient GEMMs and converting them here was measured: the
+                    // stall moves into the GEMMs, 245 registers, 0.78 -> 0.815 ms at the bench size -- not kept)
+                    if (t > 0) embed_images(t - 1);
+                }
                 FZ_TS(10);
             }
             cp_async_wait_all();
-        } else {
+        } else if (role == 0) {
             // ============================== core warp: prior / higher heads + the two cells ===============================
             const float keep_l = 1.f - p.inv_tau_l, keep_h = 1.f - p.inv_tau_h;
             float* stDF = reinterpret_cast<float*>(my + fz2::DF);
@@ -502,7 +561,8 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 cp_async_commit();
             };
             bulk_rows(stDF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, T - 1, &bars[fz2::BAR_DF], lane);
-            bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
+            if constexpr (WPT == 2)
+                bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
             bstage_pr(stPR, p, row0, T - 1, lane);  // cp.async groups per step, in issue order: PR(t-1) | HID(t-1)
             stage_hid(T - 1);
             const float* dkl_src = (r.t < 2) ? p.d_kl_h : p.d_kl_l;  // quad lanes: 0 kl_h row A, 1 kl_h row B, 2 kl_l row A, 3 kl_l row B
@@ -540,19 +600,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 // t < 2 own its columns 4t .. 4t+3; column 8 of the 16-column block is the ones column
                 float actc[2][4];
                 zero_c<2>(actc);
-                if (t + 1 < T && r.t < 2) {
-                    const float* aA = p.actions + (iA + 1) * A + 4 * r.t;
-                    const float* aB = p.actions + (iB + 1) * A + 4 * r.t;
-                    if (4 * r.t < A) {
-                        const float2 x = *reinterpret_cast<const float2*>(aA), y = *reinterpret_cast<const float2*>(aB);
-                        actc[0][0] = x.x, actc[0][1] = x.y, actc[0][2] = y.x, actc[0][3] = y.y;
-                    }
-                    if (4 * r.t + 2 < A) {
-                        const float2 x = *reinterpret_cast<const float2*>(aA + 2), y = *reinterpret_cast<const float2*>(aB + 2);
-                        actc[1][0] = x.x, actc[1][1] = x.y, actc[1][2] = y.x, actc[1][3] = y.y;
-                    }
-                }
-                if (r.t == 2) actc[0][0] = actc[0][2] = 1.f;
+                if constexpr (WPT == 2) load_action_columns(actc, p.actions, iA + 1, iB + 1, A, t + 1 < T, r);
                 // ---- lower prior head -------------------------------------------------------------------------------------
                 {
                     float q[2][4], pp[2][4], dq[2][4], dpp[2][4], dlg[2][4];
@@ -613,7 +661,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 mbar_wait(&bars[fz2::BAR_FT], ph_ft), ph_ft ^= 1;  // the feature row of step t has landed
                 load_staged<4, false>(dh, stFT, bst::DF_LD, 0, r.g, r.t);
                 load_staged<4, false>(dl, stFT, bst::DF_LD, 48, r.g, r.t);
-                {
+                if constexpr (WPT == 2) {  // three warps per tile: the aux warp builds the X-operand images and refills the stage
                     float zh[2][4], zl[2][4];
                     load_staged<2, false>(zh, stFT, bst::DF_LD, 32, r.g, r.t);
                     load_staged<2, false>(zl, stFT, bst::DF_LD, 80, r.g, r.t);
@@ -658,7 +706,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 }
                 // ---- the recurrence's critical section: mod's d deter_l(t) -> lower cell -> d stoch_l(t-1) back to the mod warp --
                 FZ_TS(7);
-                nbar_sync(bar_x);  // the mod warp's dY columns and its contribution to d deter_l are complete
+                nbar_sync(bar_x, X_COUNT);  // the mod warp's dY columns and its contribution to d deter_l are complete
                 FZ_TS(8);
                 {
                     float c[4][4];
@@ -689,13 +737,17 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 // ---- off the critical path: the end-of-step weight-gradient MMAs and the rest of the lower cell -------------------
                 store_op<4>(pl, dy, fz::Y_L + 64 * (t & 1), r);
                 FZ_FENCE();
-                __syncwarp();
-                if (FZ_MMA && lane == 0) {
-                    umma_acc(tmem + fz2::T_D1, s_dop, s_dy + (fz::Y_HQ1 / 8) * fz2::CH, 160);
-                    if (t < T - 1) umma_acc(tmem + fz2::T_C, s_dop, s_dy + ((fz::Y_L + 64 * ((t + 1) & 1)) / 8) * fz2::CH, 64);
-                    umma_acc(tmem + fz2::T_B, s_dy, s_ones, 16);                     // dY columns   0..127
-                    umma_acc(tmem + fz2::T_B + 16, s_dy + 16 * fz2::CH, s_ones, 16);  // dY columns 128..239 (+ junk)
-                    umma_commit(&bars[fz2::BAR_END]);
+                if constexpr (WPT == 3) {
+                    nbar_arrive(bar_z);  // every dY column of this warp is complete and it is done with the feature-row stage
+                } else {
+                    __syncwarp();
+                    if (FZ_MMA && lane == 0) {
+                        umma_acc(tmem + fz2::T_D1, s_dop, s_dy + (fz::Y_HQ1 / 8) * fz2::CH, 160);
+                        if (t < T - 1) umma_acc(tmem + fz2::T_C, s_dop, s_dy + ((fz::Y_L + 64 * ((t + 1) & 1)) / 8) * fz2::CH, 64);
+                        umma_acc(tmem + fz2::T_B, s_dy, s_ones, 16);                     // dY columns   0..127
+                        umma_acc(tmem + fz2::T_B + 16, s_dy + 16 * fz2::CH, s_ones, 16);  // dY columns 128..239 (+ junk)
+                        umma_commit(&bars[fz2::BAR_END]);
+                    }
                 }
                 FZ_TS(10);
                 zero_c<4>(ddl);
@@ -709,7 +761,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                     for (int j = 0; j < 4; ++j) dzh[nt][j] = dzh_n[nt][j];
                 gemm<NS, 2, 4>(ddl, fl, wblk<NS>(W, mt::T_L_D2H), lane);
                 gemm<NS, 2, 2>(dzh, fl, wblk<NS>(W, mt::T_L_IN_ZH), lane);
-                if (p.d_actions != nullptr) {
+                if (WPT == 2 && p.d_actions != nullptr) {  // three warps per tile: the aux warp, from the dY image
                     float da[2][4];
                     zero_c<2>(da);
                     gemm<NS, 2, 2>(da, fl, wblk<NS>(W, mt::T_L_IN_A), lane);
@@ -746,49 +798,111 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
                 }
                 FZ_TS(11);
             }
-            // step 0's cell gradients pair with the INITIAL state
-            FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
-            {
-                float c4[4][4], c2[2][4], actc[2][4];
-                load_c<4>(c4, p.deter_l0 + (size_t)r.rA * 32, p.deter_l0 + (size_t)r.rB * 32, r.t);
-                store_op<4>(c4, dop, 0, r);
-                load_c<4>(c4, p.deter_h0 + (size_t)r.rA * 32, p.deter_h0 + (size_t)r.rB * 32, r.t);
-                store_op<4>(c4, dop, 32, r);
-                load_c<2>(c2, p.stoch_l0 + (size_t)r.rA * 16, p.stoch_l0 + (size_t)r.rB * 16, r.t);
-                store_op<2>(c2, zop, 0, r);
-                load_c<2>(c2, p.stoch_h0 + (size_t)r.rA * 16, p.stoch_h0 + (size_t)r.rB * 16, r.t);
-                store_op<2>(c2, zop, 16, r);
-                zero_c<2>(actc);
-                if (r.t < 2) {
-                    const float* aA = p.actions + (size_t)r.rA * T * A + 4 * r.t;
-                    const float* aB = p.actions + (size_t)r.rB * T * A + 4 * r.t;
-                    if (4 * r.t < A) {
-                        const float2 x = *reinterpret_cast<const float2*>(aA), y = *reinterpret_cast<const float2*>(aB);
-                        actc[0][0] = x.x, actc[0][1] = x.y, actc[0][2] = y.x, actc[0][3] = y.y;
-                    }
-                    if (4 * r.t + 2 < A) {
-                        const float2 x = *reinterpret_cast<const float2*>(aA + 2), y = *reinterpret_cast<const float2*>(aB + 2);
-                        actc[1][0] = x.x, actc[1][1] = x.y, actc[1][2] = y.x, actc[1][3] = y.y;
-                    }
+            if constexpr (WPT == 2) pair_initial_state(ph_end);
+            cp_async_wait_all();
+        } else {
+            // ============================== aux warp (WPT == 3): operand images, MMAs, input gradients ======================
+            float* stFT = reinterpret_cast<float*>(my + fz2::FT);
+            uint32_t ph_ft = 0, ph_end = 0;
+            auto embed_prefetch = [&](int t) {  // lanes 0..15: one 256-byte row of each embedding into L2
+                if (t >= 0 && lane < 16) {
+                    const size_t j = ((size_t)min(row0 + lane, p.B - 1) * T + t) * 64;
+                    prefetch_bulk_l2(p.embed_a + j, 256);
+                    prefetch_bulk_l2(p.embed_v + j, 256);
                 }
-                if (r.t == 2) actc[0][0] = actc[0][2] = 1.f;
-                store_op<2>(actc, zop, 32, r);
+            };
+            bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
+            embed_prefetch(T - 2);
+            // the fp32 embeddings of a step are requested one step ahead (registers) and converted at the top of their step
+            float ea[8][4], ev[8][4];
+            {
+                const size_t jA = ((size_t)r.rA * T + T - 1) * 64, jB = ((size_t)r.rB * T + T - 1) * 64;
+                load_c<8>(ea, p.embed_a + jA, p.embed_a + jB, r.t);
+                load_c<8>(ev, p.embed_v + jA, p.embed_v + jB, r.t);
+            }
+            for (int t = T - 1; t >= 0; --t) {
+                const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
+                FZ_TS(0);
+                // the MMAs of step t+1 are done with the operand images
+                if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
+                FZ_TS(1);
+                store_op<8>(ea, svop, 24 * 8, r);
+                store_op<8>(ev, svop, 32 * 8, r);
+                if (t > 0) {
+                    const size_t jA = (iA - 1) * 64, jB = (iB - 1) * 64;
+                    load_c<8>(ea, p.embed_a + jA, p.embed_a + jB, r.t);
+                    load_c<8>(ev, p.embed_v + jA, p.embed_v + jB, r.t);
+                }
+                embed_prefetch(t - 2);
+                FZ_TS(2);
+                {   // X operands: bf16 [d_l | d_h | z_l | z_h](t) and [action(t+1) | ones]
+                    float actc[2][4], c4[4][4], c2[2][4];
+                    zero_c<2>(actc);
+                    load_action_columns(actc, p.actions, iA + 1, iB + 1, A, t + 1 < T, r);
+                    mbar_wait(&bars[fz2::BAR_FT], ph_ft), ph_ft ^= 1;  // the feature row of step t has landed
+                    load_staged<4, false>(c4, stFT, bst::DF_LD, 48, r.g, r.t);
+                    store_op<4>(c4, dop, 0, r);
+                    load_staged<4, false>(c4, stFT, bst::DF_LD, 0, r.g, r.t);
+                    store_op<4>(c4, dop, 32, r);
+                    load_staged<2, false>(c2, stFT, bst::DF_LD, 80, r.g, r.t);
+                    store_op<2>(c2, zop, 0, r);
+                    load_staged<2, false>(c2, stFT, bst::DF_LD, 32, r.g, r.t);
+                    store_op<2>(c2, zop, 16, r);
+                    store_op<2>(actc, zop, 32, r);
+                }
+                FZ_TS(3);
+                // ---- the mod warp's dY columns: embedding gradients d e = dY1 . W1[:, 32:] (mopoe_mmtrssm/core.py:259-260) ------
+                nbar_sync(bar_x, X_COUNT);
+                FZ_TS(4);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    float dhid[4][4], de[8][4];
+                    AFrag<NS, 2> f1;
+                    load_op<4>(dhid, dy, m == 0 ? fz::Y_A1 : fz::Y_V1, r.g, r.t);
+                    to_afrag<NS, 2>(f1, dhid);
+                    zero_c<8>(de);
+                    gemm<NS, 2, 8>(de, f1, wblk<NS>(W, m == 0 ? mt::T_A1E : mt::T_V1E), lane);
+                    float* dE = m == 0 ? p.d_embed_a : p.d_embed_v;
+                    store_c<8>(de, dE + iA * 64, dE + iB * 64, r);
+                }
+                FZ_TS(5);
+                // ---- the core warp's dY columns are complete and it is done with the feature-row stage ---------------------------
+                nbar_sync(bar_z);
+                FZ_TS(6);
+                float pl[4][4];
+                load_op<4>(pl, dy, fz::Y_L + 64 * (t & 1), r.g, r.t);
                 FZ_FENCE();
                 __syncwarp();
                 if (FZ_MMA && lane == 0) {
-                    umma_acc(tmem + fz2::T_C, s_dop, s_dy + (fz::Y_L / 8) * fz2::CH, 64);  // buffer 0 holds step 0's [L | H]
+                    umma_acc(tmem + fz2::T_EMB, s_sv + 24 * fz2::CH, s_dy + (fz::Y_A1 / 8) * fz2::CH, 64);
+                    umma_acc(tmem + fz2::T_D1, s_dop, s_dy + (fz::Y_HQ1 / 8) * fz2::CH, 160);
+                    if (t < T - 1) umma_acc(tmem + fz2::T_C, s_dop, s_dy + ((fz::Y_L + 64 * ((t + 1) & 1)) / 8) * fz2::CH, 64);
+                    umma_acc(tmem + fz2::T_B, s_dy, s_ones, 16);                     // dY columns   0..127
+                    umma_acc(tmem + fz2::T_B + 16, s_dy + 16 * fz2::CH, s_ones, 16);  // dY columns 128..239 (+ junk)
                     umma_commit(&bars[fz2::BAR_END]);
                 }
-                FZ_WAIT(&bars[fz2::BAR_END], ph_end);
+                FZ_TS(7);
+                if (t > 0)
+                    bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, t - 1, &bars[fz2::BAR_FT], lane);
+                if (p.d_actions != nullptr) {  // d a = dY_l . W_in[:, :A] (l_rnn._input2h, :283-284)
+                    AFrag<NS, 2> fl;
+                    to_afrag<NS, 2>(fl, pl);
+                    float da[2][4];
+                    zero_c<2>(da);
+                    gemm<NS, 2, 2>(da, fl, wblk<NS>(W, mt::T_L_IN_A), lane);
+                    store_c_partial(da, p.d_actions + iA * A, p.d_actions + iB * A, r, A);
+                }
+                FZ_TS(8);
             }
-            cp_async_wait_all();
+            pair_initial_state(ph_end);
         }
     }
     if (grp + (int)gridDim.x < ngroups) {
         // another group follows: put the tile's shared memory and mbarriers back into their initial state (every MMA and bulk
         // copy of this group has completed: both warps waited on BAR_END / their copies above)
-        nbar_sync(9 + tile);
-        for (int i = lane + 32 * role; i < fz2::BYTES / 16; i += 64) reinterpret_cast<uint4*>(my)[i] = make_uint4(0u, 0u, 0u, 0u);
+        const int bar_g = WPT == 2 ? 9 + tile : 2 + WPT * tile;  // three warps: the Y barrier's id is idle between groups
+        nbar_sync(bar_g, 32 * WPT);
+        for (int i = lane + 32 * role; i < fz2::BYTES / 16; i += 32 * WPT) reinterpret_cast<uint4*>(my)[i] = make_uint4(0u, 0u, 0u, 0u);
         if (role == 0 && lane == 0) {
 #pragma unroll
             for (int i = 0; i < fz2::NBAR; ++i) {
@@ -797,7 +911,7 @@ __global__ void __launch_bounds__(256, 1) mtrssm_bwd_fused2_kernel(const MtrssmB
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        nbar_sync(9 + tile);
+        nbar_sync(bar_g, 32 * WPT);
     }
     }  // tile groups
     // ---- epilogue: TMEM accumulators -> global weight gradients (one atomicAdd per element per CTA) -----------------------
@@ -885,6 +999,8 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
     // tiles per CTA: 4 fill an SM's shared memory; small batches use 2 (the TMEM read-back needs four warps) to reach more SMs
     const int tiles = (a.B + 15) / 16, tpc = tiles > 2 * 148 ? 4 : 2;
     const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + tpc * (size_t)fz2::BYTES;
+    // warps per tile: 3 (core, mod, aux) by default; RSSM_BWD_TWO_WARP=1 selects the two-warp kernel (A/B measurements)
+    const int wpt = getenv("RSSM_BWD_TWO_WARP") != nullptr ? 2 : 3;
     auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
@@ -892,20 +1008,23 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int groups = (tiles + tpc - 1) / tpc;  // one resident CTA per SM (shared memory): persistent over its groups
-        kernel<<<groups < sms ? groups : sms, 64 * tpc, smem, s>>>(a, u);
+        kernel<<<groups < sms ? groups : sms, 32 * wpt * tpc, smem, s>>>(a, u);
 #ifdef FZ_TIMING
         if (getenv("RSSM_FZ_TIMING")) {
-            static long long h[2][1024][12];
+            static long long h[3][1024][12];
             cudaStreamSynchronize(s);
             cudaMemcpyFromSymbol(h, fz_dbg, sizeof(h));
             const int T = a.T < 1024 ? a.T : 1024, lo = T > 8 ? 2 : 0, hi = T > 8 ? T - 3 : T - 1;
-            const char* names[2][12] = {{"top", "cpwait+END", "lp head", "hq+hp heads", "fence+E mma", "FT wait+images", "E wait+stage_hid",
-                                         "h cell (pre-X)", "X SYNC wait", "l cell->Y arrive", "END mmas", "rest of step"},
+            const char* names[3][12] = {{"top", "cpwait+END", "lp head", "hq+hp heads", "fence+E mma", "FT wait+images", "E wait+stage_hid",
+                                         "h cell (pre-X)", "X SYNC wait", "l cell->Y arrive", "END mmas / Z arrive", "rest of step"},
                                         {"top", "cpwait", "pre-Y math", "refill+ELU'", "Y SYNC wait", "post-Y math", "END wait", "heads->X arrive",
-                                         "mma+de gemms", "M wait", "refill+embed imgs", ""}};
-            for (int role = 0; role < 2; ++role) {
-                fprintf(stderr, "[fz timing B=%d T=%d] %s warp, mean cycles per interval over steps %d..%d:\n", a.B, a.T, role ? "mod" : "core", lo, hi);
-                const int n = role ? 11 : 12;
+                                         "mma+de gemms", "M wait", "refill+embed imgs", ""},
+                                        {"top", "END wait", "embed images+loads", "FT wait+images", "X SYNC wait", "de gemms+stores", "Z SYNC wait",
+                                         "MMA issue", "FT refill+d_actions", "", "", ""}};
+            const char* role_name[3] = {"core", "mod", "aux"};
+            for (int role = 0; role < wpt; ++role) {
+                fprintf(stderr, "[fz timing B=%d T=%d] %s warp, mean cycles per interval over steps %d..%d:\n", a.B, a.T, role_name[role], lo, hi);
+                const int n = role == 0 ? 12 : role == 1 ? 11 : 9;
                 double tot = 0;
                 for (int i = 1; i < n; ++i) {
                     double sum = 0;
@@ -922,7 +1041,7 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
         return cudaGetLastError();
     };
 #define FUSED_DISPATCH(KLv, KHv) \
-    if (a.KL == KLv && a.KH == KHv) return launch(mtrssm_bwd_fused2_kernel<KLv, KHv>);
+    if (a.KL == KLv && a.KH == KHv) return wpt == 2 ? launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 2>) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 3>);
     FUSED_DISPATCH(4, 2)
 #ifndef RSSM_EXP_ONLY_DEFAULT
     FUSED_DISPATCH(4, 4)

@@ -173,7 +173,8 @@ def test_wide_family_forward_backward_replays_from_a_cuda_graph(ops):
 
     def step(inp):
         out = R.mrssm_rollout(w, class_size=K, precision=1, **inp)
-        grads = torch.autograd.grad((out["feature"] * up).sum() + out["kl"].mean(), w)
+        b, t = out["feature"].shape[:2]
+        grads = torch.autograd.grad((out["feature"] * up[:b, :t]).sum() + out["kl"].mean(), w)
         return out["feature"], grads
 
     side = torch.cuda.Stream()
