@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define RSSM_ABI_VERSION 4
+#define RSSM_ABI_VERSION 5
 #define RSSM_PRECISION_FP32 0
 #define RSSM_PRECISION_BF16 1
 /* bf16 tensor-core path whose backward is ONE kernel: BPTT + weight-gradient contractions on tcgen05 with TMEM accumulators
@@ -161,6 +161,12 @@ typedef struct {
     int CL, KL, CH, KH;       /* l_dist / h_dist: category_size x class_size */
     float l_tau, h_tau;
     int precision;
+    int obs_projected; /* 0: embed_a / embed_v are the encoder outputs [B,T,E] and the modality heads' first layer multiplies them by
+                          W1[:, LD:] inside the step (mopoe_mmtrssm/core.py:259-260).  1 (ABI v5; RSSM_PRECISION_BF16_FUSED only):
+                          embed_a / embed_v hold the PRE-MULTIPLIED partials P = e . W1[:, LD:]^T, [B,T,HR] (no bias) -- SURVEY.md
+                          §8 f2: one big GEMM before the loop, or the encoder's last Linear with the merged weight; the kernels add
+                          them to the first-layer accumulators, d_embed_a / d_embed_v are then [B,T,HR] = d P, and the weight-
+                          gradient columns au_w1[:, LD:] / vi_w1[:, LD:] are NOT touched (they belong to the caller's GEMM). */
 } RssmMtrssmDims;
 
 typedef struct {

@@ -17,7 +17,7 @@ from .build import LIB, build_library
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 PRECISION_BF16_FUSED = 2  # bf16 path with the one-kernel backward (tcgen05 weight gradients); MMTRSSM only
-ABI_VERSION = 4
+ABI_VERSION = 5
 MRSSM_SAVED_FLOATS, MRSSM_DPRE_FLOATS = 320, 336
 MTRSSM_SAVED_FLOATS, MTRSSM_DPRE_FLOATS = 208, 304
 MTRSSM_SAVED_BF16 = MTRSSM_SAVED_FLOATS
@@ -59,7 +59,7 @@ MrssmInputGrads = _struct(
 MtrssmDims = _struct(
     "RssmMtrssmDims",
     [(n, C.c_int) for n in "B T A E HD LD HH HR CL KL CH KH".split()]
-    + [("l_tau", C.c_float), ("h_tau", C.c_float), ("precision", C.c_int)],
+    + [("l_tau", C.c_float), ("h_tau", C.c_float), ("precision", C.c_int), ("obs_projected", C.c_int)],
 )
 MtrssmWeights = _struct("RssmMtrssmWeights", _ptrs(_MT_W))
 MtrssmWeightGrads = _struct("RssmMtrssmWeightGrads", _ptrs(_MT_W))

@@ -154,6 +154,7 @@ struct MtrssmFwdArgs {
     float *kl_l, *kl_h;
     void* saved;
     int saved_ld;    // elements per (b,t) row of `saved`
+    int obs_projected;  // 1: embed_a / embed_v are the pre-multiplied first-layer partials [B,T,32] (include/rssm_rollout.h)
 };
 
 struct MtrssmBwdArgs {
@@ -170,6 +171,7 @@ struct MtrssmBwdArgs {
     void* dpre;
     float *d_actions, *d_embed_a, *d_embed_v;
     float *d_deter_h0, *d_deter_l0, *d_hidden_h0, *d_hidden_l0, *d_stoch_h0, *d_stoch_l0;
+    int obs_projected;  // 1: d_embed_a / d_embed_v are [B,T,32] = d of the pre-multiplied partials; no embedding operand images
 };
 
 cudaError_t launch_mtrssm_fwd(const MtrssmFwdArgs& a, int precision, bool imagine, cudaStream_t s);

@@ -151,7 +151,8 @@ __device__ __forceinline__ void head_bwd_op(const float (&dlogit)[2][4], const u
 
 // the same with ELU'(hidden) precomputed by the caller (mod warp: off the recurrence's critical section)
 __device__ __forceinline__ void head_bwd_elu(const float (&dlogit)[2][4], const uint2* w2t, const float (&elu_grad)[4][4], unsigned char* dy,
-                                             int y_logit, int y1, AFrag<1, 2>& f1, const Rows& r, int lane) {
+                                             int y_logit, int y1, AFrag<1, 2>& f1, const Rows& r, int lane, float* dpA = nullptr,
+                                             float* dpB = nullptr) {
     store_op<2>(dlogit, dy, y_logit, r);
     AFrag<1, 1> fl;
     to_afrag<1, 1>(fl, dlogit);
@@ -164,6 +165,7 @@ __device__ __forceinline__ void head_bwd_elu(const float (&dlogit)[2][4], const 
         for (int j = 0; j < 4; ++j) dhid[nt][j] *= elu_grad[nt][j];
     store_op<4>(dhid, dy, y1, r);
     to_afrag<1, 2>(f1, dhid);
+    if (dpA != nullptr) store_c<4>(dhid, dpA, dpB, r);  // obs_projected: dY1 IS the gradient of the pre-multiplied partial (fp32)
 }
 
 // [action | ones] X-operand columns of one step: lanes with t < 2 own action columns 4t .. 4t+3, column 8 is the ones column
@@ -508,8 +510,13 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 float ddl[4][4];
                 zero_c<4>(ddl);
                 AFrag<NS, 2> f1a, f1v;
-                head_bwd_elu(dla, wblk<NS>(W, mt::T_A2), eluA, dy, fz::Y_LA, fz::Y_A1, f1a, r, lane);
-                head_bwd_elu(dlv, wblk<NS>(W, mt::T_V2), eluV, dy, fz::Y_LV, fz::Y_V1, f1v, r, lane);
+                if (WPT == 3 && p.obs_projected) {
+                    head_bwd_elu(dla, wblk<NS>(W, mt::T_A2), eluA, dy, fz::Y_LA, fz::Y_A1, f1a, r, lane, p.d_embed_a + iA * 32, p.d_embed_a + iB * 32);
+                    head_bwd_elu(dlv, wblk<NS>(W, mt::T_V2), eluV, dy, fz::Y_LV, fz::Y_V1, f1v, r, lane, p.d_embed_v + iA * 32, p.d_embed_v + iB * 32);
+                } else {
+                    head_bwd_elu(dla, wblk<NS>(W, mt::T_A2), eluA, dy, fz::Y_LA, fz::Y_A1, f1a, r, lane);
+                    head_bwd_elu(dlv, wblk<NS>(W, mt::T_V2), eluV, dy, fz::Y_LV, fz::Y_V1, f1v, r, lane);
+                }
                 gemm<NS, 2, 4>(ddl, f1a, wblk<NS>(W, mt::T_A1H), lane);
                 gemm<NS, 2, 4>(ddl, f1v, wblk<NS>(W, mt::T_V1H), lane);
                 xch_store<4>(ddl, xddl, lane);
@@ -812,10 +819,12 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 }
             };
             bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
-            embed_prefetch(T - 2);
+            const bool emb = !p.obs_projected;  // obs_projected: no embedding operand images, no embedding MMA, no d_embed GEMMs here
+            if (emb) embed_prefetch(T - 2);
             // the fp32 embeddings of a step are requested one step ahead (registers) and converted at the top of their step
             float ea[8][4], ev[8][4];
-            {
+            zero_c<8>(ea), zero_c<8>(ev);
+            if (emb) {
                 const size_t jA = ((size_t)r.rA * T + T - 1) * 64, jB = ((size_t)r.rB * T + T - 1) * 64;
                 load_c<8>(ea, p.embed_a + jA, p.embed_a + jB, r.t);
                 load_c<8>(ev, p.embed_v + jA, p.embed_v + jB, r.t);
@@ -826,14 +835,16 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 // the MMAs of step t+1 are done with the operand images
                 if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
                 FZ_TS(1);
-                store_op<8>(ea, svop, 24 * 8, r);
-                store_op<8>(ev, svop, 32 * 8, r);
-                if (t > 0) {
-                    const size_t jA = (iA - 1) * 64, jB = (iB - 1) * 64;
-                    load_c<8>(ea, p.embed_a + jA, p.embed_a + jB, r.t);
-                    load_c<8>(ev, p.embed_v + jA, p.embed_v + jB, r.t);
+                if (emb) {
+                    store_op<8>(ea, svop, 24 * 8, r);
+                    store_op<8>(ev, svop, 32 * 8, r);
+                    if (t > 0) {
+                        const size_t jA = (iA - 1) * 64, jB = (iB - 1) * 64;
+                        load_c<8>(ea, p.embed_a + jA, p.embed_a + jB, r.t);
+                        load_c<8>(ev, p.embed_v + jA, p.embed_v + jB, r.t);
+                    }
+                    embed_prefetch(t - 2);
                 }
-                embed_prefetch(t - 2);
                 FZ_TS(2);
                 {   // X operands: bf16 [d_l | d_h | z_l | z_h](t) and [action(t+1) | ones]
                     float actc[2][4], c4[4][4], c2[2][4];
@@ -856,6 +867,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 FZ_TS(4);
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
+                    if (!emb) break;
                     float dhid[4][4], de[8][4];
                     AFrag<NS, 2> f1;
                     load_op<4>(dhid, dy, m == 0 ? fz::Y_A1 : fz::Y_V1, r.g, r.t);
@@ -874,7 +886,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 FZ_FENCE();
                 __syncwarp();
                 if (FZ_MMA && lane == 0) {
-                    umma_acc(tmem + fz2::T_EMB, s_sv + 24 * fz2::CH, s_dy + (fz::Y_A1 / 8) * fz2::CH, 64);
+                    if (emb) umma_acc(tmem + fz2::T_EMB, s_sv + 24 * fz2::CH, s_dy + (fz::Y_A1 / 8) * fz2::CH, 64);
                     umma_acc(tmem + fz2::T_D1, s_dop, s_dy + (fz::Y_HQ1 / 8) * fz2::CH, 160);
                     if (t < T - 1) umma_acc(tmem + fz2::T_C, s_dop, s_dy + ((fz::Y_L + 64 * ((t + 1) & 1)) / 8) * fz2::CH, 64);
                     umma_acc(tmem + fz2::T_B, s_dy, s_ones, 16);                     // dY columns   0..127
@@ -968,8 +980,10 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
         add_flush(u, g.hq_w2, z::T_E + 32, 16, 64, 32, 32, 0);
         add_flush(u, g.au_w2, z::T_M + 0, 16, 0, 32, 32, 0);
         add_flush(u, g.vi_w2, z::T_M + 16, 16, 32, 32, 32, 0);
-        add_flush(u, g.au_w1, z::T_EMB + 0, 32, 0, 64, 96, 32);
-        add_flush(u, g.vi_w1, z::T_EMB + 32, 32, 64, 64, 96, 32);
+        if (!a.obs_projected) {  // projected partials: the columns W1[:, 32:] belong to the caller's GEMM
+            add_flush(u, g.au_w1, z::T_EMB + 0, 32, 0, 64, 96, 32);
+            add_flush(u, g.vi_w1, z::T_EMB + 32, 32, 64, 64, 96, 32);
+        }
         add_flush(u, g.hq_w1, z::T_D1 + 0, 32, 0, 64, 64, 0);
         add_flush(u, g.lp_w1, z::T_D1 + 32, 32, 0, 32, 32, 0);
         add_flush(u, g.au_w1, z::T_D1 + 64, 32, 0, 32, 96, 0);
@@ -1001,6 +1015,7 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
     const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + tpc * (size_t)fz2::BYTES;
     // warps per tile: 3 (core, mod, aux) by default; RSSM_BWD_TWO_WARP=1 selects the two-warp kernel (A/B measurements)
     const int wpt = getenv("RSSM_BWD_TWO_WARP") != nullptr ? 2 : 3;
+    if (a.obs_projected && wpt != 3) return cudaErrorNotSupported;  // the pre-multiplied-partials mode lives in the three-warp kernel
     auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;

@@ -96,6 +96,32 @@ __device__ __forceinline__ void sample_onehot_regs(const float (&p)[2][4], const
     }
 }
 
+// obs_projected: the two modality partials P = e . W1[:, 32:]^T, [B,T,32] fp32, staged like the embeddings (regions EA / EV of the
+// stage, rows of 128 B, 16-byte chunks XOR-swizzled by (row & 7) so that the C-tile read pattern below is conflict-free) + u0
+__device__ __forceinline__ void stage_projected(float* stage, const float* __restrict__ pa, const float* __restrict__ pv,
+                                                const float* __restrict__ u0, int n0, int row0, int B, int T, int t, int lane) {
+    const int chunk = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int rl = (lane >> 3) + 4 * i;
+        const size_t src = ((size_t)min(row0 + rl, B - 1) * T + t) * 32 + chunk * 4;
+        const int dst = rl * 32 + ((chunk ^ (rl & 7)) << 2);
+        cp_async16(stage + stg::EA + dst, pa + src);
+        cp_async16(stage + stg::EV + dst, pv + src);
+    }
+    stage_inputs(stage, nullptr, nullptr, nullptr, 0, u0, n0, nullptr, 0, row0, B, T, t, lane);  // the uniforms (+ commit)
+}
+// acc (C tiles, 32 columns) += the staged partial rows of this lane
+__device__ __forceinline__ void add_staged_projected(float (&acc)[4][4], const float* tile, int g, int t) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int c = ((4 * j + t) ^ (g & 7)) << 2;
+        const float4 a = *reinterpret_cast<const float4*>(tile + g * 32 + c), b = *reinterpret_cast<const float4*>(tile + (g + 8) * 32 + c);
+        acc[2 * j][0] += a.x, acc[2 * j][1] += a.y, acc[2 * j + 1][0] += a.z, acc[2 * j + 1][1] += a.w;
+        acc[2 * j][2] += b.x, acc[2 * j][3] += b.y, acc[2 * j + 1][2] += b.z, acc[2 * j + 1][3] += b.w;
+    }
+}
+
 // hidden -> ELU -> (saved) -> logits, as head_l2 of mtrssm_kernels.cu (NS = 1)
 __device__ __forceinline__ void head2_l2(float (&acc)[4][4], float (&logits)[2][4], const float* bias2, const uint2* w2, __nv_bfloat16* svA,
                                          __nv_bfloat16* svB, int sv_off, const Rows& r, int lane) {
@@ -301,7 +327,8 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
             pair_sync(bar_z);  // consume the obs warp's last hand-over (keeps the barrier's phases paired across tiles)
         } else {
             // =========================== obs warp: modality heads, MoPoE, z_l, lower prior ===========================
-            stage_inputs(stage_base, p.embed_a, p.embed_v, nullptr, A, p.u_post_l, CL, nullptr, 0, row0, p.B, T, 0, lane);
+            if (p.obs_projected) stage_projected(stage_base, p.embed_a, p.embed_v, p.u_post_l, CL, row0, p.B, T, 0, lane);
+            else stage_inputs(stage_base, p.embed_a, p.embed_v, nullptr, A, p.u_post_l, CL, nullptr, 0, row0, p.B, T, 0, lane);
             float upA[2] = {0.f, 0.f}, upB[2] = {0.f, 0.f};  // uniforms of the prior's own z_l draw, one step ahead
             if (prior_draws) fetch_uniforms<KL>(p.u_prior_l, (size_t)r.rA * T, (size_t)r.rB * T, lane, upA, upB);
             for (int t = 0; t < T; ++t) {
@@ -311,17 +338,22 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                 const float* stage = stage_base + (t & 1) * stg::FLOATS;
                 cp_async_wait_all();
                 __syncwarp();
-                if (t + 1 < T)
-                    stage_inputs(stage_base + ((t + 1) & 1) * stg::FLOATS, p.embed_a, p.embed_v, nullptr, A, p.u_post_l, CL, nullptr, 0, row0,
-                                 p.B, T, t + 1, lane);
+                if (t + 1 < T) {
+                    float* nxt = stage_base + ((t + 1) & 1) * stg::FLOATS;
+                    if (p.obs_projected) stage_projected(nxt, p.embed_a, p.embed_v, p.u_post_l, CL, row0, p.B, T, t + 1, lane);
+                    else stage_inputs(nxt, p.embed_a, p.embed_v, nullptr, A, p.u_post_l, CL, nullptr, 0, row0, p.B, T, t + 1, lane);
+                }
                 // the embedding halves of the two first layers do not need d_l: they run before the hand-over
                 float acca[4][4], accv[4][4];
-                {
+                init_bias<4>(acca, bias + mt::B_A1, r.t);
+                init_bias<4>(accv, bias + mt::B_V1, r.t);
+                if (p.obs_projected) {  // the caller multiplied the embeddings by W1[:, 32:] in one GEMM before the loop
+                    add_staged_projected(acca, stage + stg::EA, r.g, r.t);
+                    add_staged_projected(accv, stage + stg::EV, r.g, r.t);
+                } else {
                     AFrag<NS, 4> fe;
-                    init_bias<4>(acca, bias + mt::B_A1, r.t);
                     load_a_staged64<NS>(fe, stage + stg::EA, r.g, r.t);
                     gemm<NS, 4, 4>(acca, fe, wblk<NS>(W, mt::A1E), lane);
-                    init_bias<4>(accv, bias + mt::B_V1, r.t);
                     load_a_staged64<NS>(fe, stage + stg::EV, r.g, r.t);
                     gemm<NS, 4, 4>(accv, fe, wblk<NS>(W, mt::V1E), lane);
                 }

@@ -57,6 +57,9 @@ int check_mtrssm(const RssmMtrssmDims* d) {
     if (!(d->l_tau > 1.f) || !(d->h_tau > 1.f)) return fail("tau must be greater than 1.0 (l_tau=%g h_tau=%g)", d->l_tau, d->h_tau);
     if (d->precision != RSSM_PRECISION_FP32 && d->precision != RSSM_PRECISION_BF16 && d->precision != RSSM_PRECISION_BF16_FUSED)
         return fail("bad precision %d", d->precision);
+    if (d->obs_projected != 0 && d->obs_projected != 1) return fail("obs_projected must be 0 or 1 (got %d)", d->obs_projected);
+    if (d->obs_projected && d->precision != RSSM_PRECISION_BF16_FUSED)
+        return fail("obs_projected (pre-multiplied first-layer partials) is built for RSSM_PRECISION_BF16_FUSED only (got precision %d)", d->precision);
     return 0;
 }
 
@@ -596,6 +599,7 @@ static int mtrssm_fwd_common(const RssmMtrssmDims* d, const RssmMtrssmWeights* w
     a.prior_stoch_h = out->prior_stoch_h, a.prior_stoch_l = out->prior_stoch_l;
     a.kl_l = out->kl_l, a.kl_h = out->kl_h, a.saved = imagine ? nullptr : out->saved;
     a.saved_ld = mt_saved_ld(d->precision);
+    a.obs_projected = imagine ? 0 : d->obs_projected;
     g_launches.fetch_add(1);
     // bf16 policies, posterior rollout: two warps per tile (mtrssm_fwd2.cu); imagination and the fp32-parity policy: one warp per tile
     if (!imagine && d->precision != RSSM_PRECISION_FP32 && getenv("RSSM_FWD_ONE_WARP") == nullptr)
@@ -641,6 +645,8 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
     a.dpre = gin->dpre, a.d_actions = gin->d_actions, a.d_embed_a = gin->d_embed_a, a.d_embed_v = gin->d_embed_v;
     a.d_deter_h0 = gin->d_deter_h0, a.d_deter_l0 = gin->d_deter_l0, a.d_hidden_h0 = gin->d_hidden_h0;
     a.d_hidden_l0 = gin->d_hidden_l0, a.d_stoch_h0 = gin->d_stoch_h0, a.d_stoch_l0 = gin->d_stoch_l0;
+    a.obs_projected = d->obs_projected;
+    if (d->obs_projected && !fused) return fail("obs_projected needs the fused backward (gw != NULL, RSSM_PRECISION_BF16_FUSED)");
     if (fused) {
         const float* const* gp = reinterpret_cast<const float* const*>(gw);
         for (size_t i = 0; i < sizeof(RssmMtrssmWeightGrads) / sizeof(float*); ++i)

@@ -10,7 +10,7 @@ from __future__ import annotations
 import torch
 from torch import Tensor, nn
 
-from . import rollout_ops
+from . import _lib, rollout_ops
 from .distribution import Distribution, FusedKL, MultiOneHotFactory, kl_divergence
 from .mopoe_mrssm import MoPoE_MRSSM, flat_stoch, mlp_params
 from .mtstate import MTState
@@ -43,6 +43,11 @@ class MoPoE_MMTRSSM(MoPoE_MRSSM):  # noqa: N801
     # bf16 path of this model: one-kernel backward (BPTT + weight gradients on tcgen05 / TMEM), never slower than the
     # two-kernel backward at any batch size measured; "bf16_two_kernel" selects the latter
     _BF16_POLICY = 2  # _lib.PRECISION_BF16_FUSED
+    #: SURVEY.md §8 f2 (off by default: results are the reference's up to the rounding of one reassociated sum).  True: under the
+    #: bf16 fused policy the embedding half of the modality heads' first layer runs as one fp32 GEMM per modality before the rollout
+    #: (`rollout_ops.obs_projection`) and the kernels take the pre-multiplied partials (`obs_projected=True`): half the embedding
+    #: bytes at the kernel boundary, no embedding work inside the recurrence.  Parameters and state_dict are unchanged.
+    hoist_obs_projection: bool = False
 
     def __init__(  # noqa: PLR0913
         self,
@@ -141,9 +146,19 @@ class MoPoE_MMTRSSM(MoPoE_MRSSM):  # noqa: N801
         dev = audio_embed.device
         CL, CH = int(self.l_dist.category_size), int(self.h_dist.category_size)
         u = {k: torch.rand(B, T, c, device=dev) for k, c in (("u_post_l", CL), ("u_post_h", CH), ("u_prior_l", CL), ("u_prior_h", CH))}
+        cfg = self._kernel_cfg()
+        projected = bool(self.hoist_obs_projection) and cfg["precision"] == _lib.PRECISION_BF16_FUSED
+        if projected:
+            # the embedding half of the two modality heads' first layer (:259-260, `cat([d_l, e]) @ W1.T` =
+            # `d_l @ W1[:, :ld].T + e @ W1[:, ld:].T`) as ONE GEMM per modality over all (b,t) before the loop; same parameters,
+            # same state_dict; autograd of this GEMM yields d embed and the W1[:, ld:] columns of d W1
+            w1a = self.audio_representation.rnn_to_post_projector[0].weight
+            w1v = self.vision_representation.rnn_to_post_projector[0].weight
+            audio_embed = rollout_ops.obs_projection(audio_embed, w1a, self.ld_dim)
+            vision_embed = rollout_ops.obs_projection(vision_embed, w1v, self.ld_dim)
         out = rollout_ops.mtrssm_rollout(
             self.rollout_weights(), actions=actions, embed_a=audio_embed, embed_v=vision_embed, **self._state_inputs(prev_state), **u,
-            use_kl_balancing=bool(self.use_kl_balancing), **self._kernel_cfg(),
+            use_kl_balancing=bool(self.use_kl_balancing), obs_projected=projected, **cfg,
         )
         feature = out["feature"]
         deter_h, stoch_h, deter_l, stoch_l = self._split(feature)

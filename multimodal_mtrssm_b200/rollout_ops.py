@@ -21,7 +21,7 @@ from torch import Tensor
 from . import _lib
 from ._lib import ptr
 
-__all__ = ["mrssm_rollout", "mrssm_imagine", "mtrssm_rollout", "mtrssm_imagine", "kl_path_weights"]
+__all__ = ["mrssm_rollout", "mrssm_imagine", "mtrssm_rollout", "mtrssm_imagine", "kl_path_weights", "obs_projection"]
 
 KL_BALANCE_ALPHA = 0.8
 
@@ -291,20 +291,22 @@ def mrssm_imagine(weights: Sequence[Tensor], *, actions: Tensor, h0: Tensor, z0:
 # =================================================================================================
 # MoPoE-MMTRSSM
 # =================================================================================================
-def _mt_dims(actions: Tensor, KL: int, KH: int, l_tau: float, h_tau: float, precision: int) -> _lib.MtrssmDims:
+def _mt_dims(actions: Tensor, KL: int, KH: int, l_tau: float, h_tau: float, precision: int, obs_projected: bool = False) -> _lib.MtrssmDims:
     B, T, A = actions.shape
     return _lib.MtrssmDims(B=B, T=T, A=A, E=64, HD=32, LD=32, HH=32, HR=32, CL=16 // KL, KL=KL, CH=16 // KH, KH=KH,
-                           l_tau=l_tau, h_tau=h_tau, precision=precision)
+                           l_tau=l_tau, h_tau=h_tau, precision=precision, obs_projected=int(obs_projected))
 
 
 _MT_STATE = "deter_h0 deter_l0 hidden_h0 hidden_l0 stoch_h0 stoch_l0".split()
 
 
-def _mt_check(weights: Sequence[Tensor], embed_a: Tensor, state: Sequence[Tensor]) -> None:
+def _mt_check(weights: Sequence[Tensor], embed_a: Tensor, state: Sequence[Tensor], obs_projected: bool = False) -> None:
     if len(weights) != len(_lib.MT_WEIGHT_FIELDS):
         raise RuntimeError(f"expected {len(_lib.MT_WEIGHT_FIELDS)} weight tensors, got {len(weights)}")
     shapes = [s.shape[-1] for s in state]
-    if embed_a.shape[-1] != 64 or shapes != [32, 32, 32, 32, 16, 16] or tuple(weights[8].shape) != (32, 32):
+    if obs_projected and embed_a.shape[-1] != 32:
+        raise RuntimeError(f"obs_projected=True takes the pre-multiplied partials e @ W1[:, 32:].T of width 32, got {embed_a.shape[-1]}")
+    if (not obs_projected and embed_a.shape[-1] != 64) or shapes != [32, 32, 32, 32, 16, 16] or tuple(weights[8].shape) != (32, 32):
         raise RuntimeError(
             "fused MMTRSSM rollout supports hd_dim = ld_dim = 32, hs_dim = ls_dim = 16, head hidden 32, obs_embed_size 64 "
             f"(got embed {embed_a.shape[-1]}, state widths {shapes}, l_prior.0 {tuple(weights[8].shape)})"
@@ -316,9 +318,10 @@ def mtrssm_rollout_op(
     weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, state: Sequence[Tensor],
     u_post_l: Tensor, u_post_h: Tensor, u_prior_l: Optional[Tensor], u_prior_h: Optional[Tensor],
     KL: int, KH: int, l_tau: float, h_tau: float, precision: int, kl_wq: float, kl_wp: float, save: bool,
+    obs_projected: bool,  # no default: the dispatcher strips trailing default-valued arguments, which changes the backward's arity
 ) -> List[Tensor]:
     with _on_device(actions, weights, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, u_prior_h):
-        _mt_check(weights, embed_a, state)
+        _mt_check(weights, embed_a, state, obs_projected)
         B, T, _ = actions.shape
         dev = actions.device
         e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
@@ -338,13 +341,13 @@ def mtrssm_rollout_op(
             (feature, hidden_h, hidden_l, prior_h, prior_l, post_h, post_l, pz_h if has_prior else None, pz_l if has_prior else None,
              kl_l, kl_h, saved if save else None),
         )
-        _lib.call("rssm_mtrssm_rollout_fwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out)
+        _lib.call("rssm_mtrssm_rollout_fwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision, obs_projected), w, inp, out)
         return [feature, hidden_h, hidden_l, prior_h, prior_l, post_h, post_l, pz_h, pz_l, kl_l, kl_h, saved]
 
 
 @mtrssm_rollout_op.register_fake
 def _(weights, actions, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, u_prior_h, KL, KH, l_tau, h_tau, precision,  # noqa: ANN001
-      kl_wq, kl_wp, save):
+      kl_wq, kl_wp, save, obs_projected):
     B, T, _ = actions.shape
     e = actions.new_empty
     pz = e(B, T, 16) if u_prior_l is not None else e(0)
@@ -359,6 +362,7 @@ def mtrssm_rollout_bwd_op(
     d_feature: Optional[Tensor], d_prior_h: Optional[Tensor], d_prior_l: Optional[Tensor], d_post_h: Optional[Tensor],
     d_post_l: Optional[Tensor], d_pz_h: Optional[Tensor], d_pz_l: Optional[Tensor], d_kl_l: Optional[Tensor],
     d_kl_h: Optional[Tensor], KL: int, KH: int, l_tau: float, h_tau: float, precision: int, kl_wq: float, kl_wp: float,
+    obs_projected: bool,  # no default: the dispatcher strips trailing default-valued arguments, which changes the backward's arity
 ) -> List[Tensor]:
     with _on_device(actions, weights, embed_a, embed_v, state, feature, prior_h, prior_l, post_h, post_l, saved, d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h):
         B, T, A = actions.shape
@@ -369,7 +373,8 @@ def mtrssm_rollout_bwd_op(
         flat = torch.zeros(sum(sizes), device=dev)
         gws = [g.view_as(t) for g, t in zip(flat.split(sizes), weights)]
         e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
-        d_actions, d_ea, d_ev = e(B, T, A), e(B, T, 64), e(B, T, 64)
+        EW = 32 if obs_projected else 64  # width of the embedding inputs and of their gradients
+        d_actions, d_ea, d_ev = e(B, T, A), e(B, T, EW), e(B, T, EW)
         d_state = [e(B, 32), e(B, 32), e(B, 32), e(B, 32), e(B, 16), e(B, 16)]
         dpre = torch.empty(B, T, _lib.MTRSSM_DPRE_FLOATS, device=dev, dtype=_lib.record_dtype(precision))
         w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
@@ -386,27 +391,27 @@ def mtrssm_rollout_bwd_op(
         gin = _fill(_lib.MtrssmInputGrads(),
                     ["d_actions", "d_embed_a", "d_embed_v", *("d_" + n for n in _MT_STATE), "dpre"],
                     (d_actions, d_ea, d_ev, *d_state, dpre))
-        _lib.call("rssm_mtrssm_rollout_bwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision), w, inp, out, up, gin, gw)
+        _lib.call("rssm_mtrssm_rollout_bwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision, obs_projected), w, inp, out, up, gin, gw)
         return [flat, d_actions, d_ea, d_ev, *d_state]  # flat = all weight grads, split by the caller
 
 
 @mtrssm_rollout_bwd_op.register_fake
 def _(weights, actions, embed_a, embed_v, state, feature, prior_h, prior_l, post_h, post_l, saved, d_feature, d_prior_h,  # noqa: ANN001
-      d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp):
+      d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, obs_projected):
     return [actions.new_empty(sum(t.numel() for t in weights)), torch.empty_like(actions), torch.empty_like(embed_a),
             torch.empty_like(embed_v), *[torch.empty_like(t) for t in state]]
 
 
 def _mt_setup(ctx, inputs, output) -> None:  # noqa: ANN001
     (weights, actions, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, u_prior_h, KL, KH, l_tau, h_tau, precision,
-     kl_wq, kl_wp, save) = inputs
+     kl_wq, kl_wp, save, obs_projected) = inputs
     feature, hidden_h, hidden_l, prior_h, prior_l, post_h, post_l, pz_h, pz_l, kl_l, kl_h, saved = output
     if not save:
         raise RuntimeError("mtrssm_rollout was called with save=False but a gradient is required")
     ctx.set_materialize_grads(False)
     ctx.nw = len(weights)
     ctx.has_prior_stoch = u_prior_l is not None
-    ctx.cfg = (KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp)
+    ctx.cfg = (KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, obs_projected)
     ctx.save_for_backward(*weights, actions, embed_a, embed_v, *state, feature, prior_h, prior_l, post_h, post_l, saved)
 
 
@@ -420,17 +425,17 @@ def _mt_backward(ctx, grads):  # noqa: ANN001
     actions, embed_a, embed_v = t[ctx.nw: ctx.nw + 3]
     state = list(t[ctx.nw + 3: ctx.nw + 9])
     feature, prior_h, prior_l, post_h, post_l, saved = t[ctx.nw + 9:]
-    KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp = ctx.cfg
+    KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, obs_projected = ctx.cfg
     hp = ctx.has_prior_stoch
     res = mtrssm_rollout_bwd_op(
         weights, actions, embed_a, embed_v, state, feature, prior_h, prior_l, post_h, post_l, saved, d_feature, d_prior_h,
         d_prior_l, d_post_h, d_post_l, d_pz_h if hp else None, d_pz_l if hp else None, d_kl_l, d_kl_h, KL, KH, l_tau, h_tau,
-        precision, kl_wq, kl_wp,
+        precision, kl_wq, kl_wp, obs_projected,
     )
     flat, d_actions, d_ea, d_ev = res[:4]
     d_state = list(res[4:])
     gws = [g.view_as(w) for g, w in zip(flat.split([w.numel() for w in weights]), weights)]
-    return (gws, d_actions, d_ea, d_ev, d_state, None, None, None, None, None, None, None, None, None, None, None, None)
+    return (gws, d_actions, d_ea, d_ev, d_state, None, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 mtrssm_rollout_op.register_autograd(_mt_backward, setup_context=_mt_setup)
@@ -441,10 +446,17 @@ def mtrssm_rollout(
     hidden_h0: Tensor, hidden_l0: Tensor, stoch_h0: Tensor, stoch_l0: Tensor, u_post_l: Tensor, u_post_h: Tensor,
     u_prior_l: Optional[Tensor] = None, u_prior_h: Optional[Tensor] = None, class_size_l: int = 4, class_size_h: int = 2,
     l_tau: float = 2.0, h_tau: float = 4.0, precision: int = _lib.PRECISION_FP32, use_kl_balancing: bool = True,
+    obs_projected: bool = False,
 ) -> dict[str, Tensor]:
     """Fused MoPoE-MMTRSSM rollout_representation on encoder outputs (mmtrssm/mopoe_mmtrssm/core.py:364-494).
 
     feature [B,T,96] = [deter_h | stoch_h | deter_l | stoch_l] (mmtrssm/state.py:51).
+
+    `obs_projected=True` (bf16 fused policy only): `embed_a` / `embed_v` are the PRE-MULTIPLIED first-layer
+    partials `e @ W1[:, 32:].T` of the two modality heads, [B,T,32] -- one big GEMM before the loop (or the encoder's last Linear
+    with the merged weight) instead of 2 x 16 small MMAs and 512 B of embedding reads per (b,t) inside it.  The kernels use
+    `W1[:, :32]` only; the returned gradients of `embed_*` are those of the partials, and `W1[:, 32:]` gets its gradient from the
+    caller's GEMM through autograd (`obs_projection` below does exactly that).
     """
     state = [deter_h0, deter_l0, hidden_h0, hidden_l0, stoch_h0, stoch_l0]
     save = torch.is_grad_enabled() and any(t.requires_grad for t in (*weights, actions, embed_a, embed_v, *state))
@@ -452,7 +464,7 @@ def mtrssm_rollout(
     out = mtrssm_rollout_op(
         [_c(w) for w in weights], _c(actions), _c(embed_a), _c(embed_v), [_c(s) for s in state], _c(u_post_l), _c(u_post_h),
         _c(u_prior_l), _c(u_prior_h),
-        class_size_l, class_size_h, float(l_tau), float(h_tau), precision, wq, wp, save,
+        class_size_l, class_size_h, float(l_tau), float(h_tau), precision, wq, wp, save, obs_projected,
     )
     names = ("feature hidden_h hidden_l prior_probs_h prior_probs_l post_probs_h post_probs_l prior_stoch_h prior_stoch_l "
              "kl_l kl_h").split()
@@ -460,6 +472,13 @@ def mtrssm_rollout(
     if u_prior_l is None:
         res["prior_stoch_h"] = res["prior_stoch_l"] = None
     return res
+
+
+def obs_projection(embed: Tensor, w1: Tensor, deter_size: int = 32) -> Tensor:
+    """The hoisted half of a modality head's first layer: `embed @ W1[:, deter_size:].T` for ALL (b,t) in one GEMM
+    (fp32, differentiable: autograd gives `d embed` and the `W1[:, deter_size:]` columns of `d W1`).  Feed the result to
+    `mtrssm_rollout(..., obs_projected=True)`."""
+    return torch.nn.functional.linear(embed.float(), w1[:, deter_size:].float())
 
 
 @torch.library.custom_op("mtrssm_b200::mtrssm_imagine", mutates_args=())

@@ -376,3 +376,35 @@ def test_base_rssm_shared_step_matches_the_reference_base_class(golden_dir):
     torch.testing.assert_close(got.deter.cpu(), im["deter"], rtol=1e-5, atol=2e-6)
     torch.testing.assert_close(got.stoch.cpu(), im["stoch"], rtol=1e-5, atol=2e-6)
     torch.testing.assert_close(got.distribution.probs.cpu(), im["probs"], rtol=1e-5, atol=2e-6)
+
+
+def test_mmtrssm_hoisted_obs_projection_trains_like_the_plain_model(golden_dir):
+    """SURVEY §8 f2 at model level: `hoist_obs_projection = True` (same parameters, same state_dict) under autocast.  The two paths
+    round differently, so a few of the 2880 categorical draws of this batch may flip (the op-level test against the teacher-forced
+    oracle is the parity test, tests/test_rollout_gpu.py); here: same loss dict within 2 %, a gradient on exactly the same
+    parameters (incl. both halves of the modality heads' first-layer weights and the encoders), each pointing the same way."""
+    g = torch.load(golden_dir / "mtrssm_cfg2.pt")
+    inp = g["inputs"]
+    batch = tuple(t.cuda() for t in H.golden_batch(g))
+    noise = [inp["u_h0"], inp["u_l0"], inp["u_post_l"], inp["u_post_h"], inp["u_prior_l"], inp["u_prior_h"]]
+    results = {}
+    for hoist in (False, True):
+        model = H.build_mtrssm_model()
+        model.load_state_dict(g["full_state_dict"], strict=True)
+        model.cuda()
+        model.hoist_obs_projection = hoist
+        with H.RandQueue(noise) as q, torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = model.shared_step(batch)
+            assert not q.values
+        loss["loss"].backward()
+        results[hoist] = (loss, {k: p.grad for k, p in model.named_parameters() if p.grad is not None})
+    rep = H.Report("MoPoE_MMTRSSM hoist_obs_projection vs plain bf16 path")
+    for k, v in results[False][0].items():
+        rep.check(k, results[True][0][k], v, rtol=2e-2, atol=2e-2)
+    rep.finish()
+    assert set(results[True][1]) == set(results[False][1])
+    for k, gref in results[False][1].items():
+        got = results[True][1][k]
+        assert bool(torch.isfinite(got).all()), k
+        cos = torch.nn.functional.cosine_similarity(got.flatten().float(), gref.flatten().float(), dim=0)
+        assert float(cos) > 0.95, (k, float(cos))

@@ -603,3 +603,50 @@ def test_unsupported_sizes_and_devices_fail_loudly(ops):
     odd["actions"] = torch.randn(4, 3, 5, device="cuda")
     with pytest.raises(RuntimeError):
         R.mrssm_rollout(w, **odd)
+
+
+# ---------------------------------------------------------------------------------------------------
+# pre-multiplied first-layer partials (obs_projected) -- forward and every gradient
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T", [(48, 8), (300, 30)])
+def test_mtrssm_obs_projected_matches_oracle_and_plain_path(ops, B, T):
+    """`obs_projected=True` (the embedding half of the modality heads' first layer hoisted into one GEMM before the loop, mopoe_mmtrssm/
+    core.py:259-260 reassociated) against the fp32 oracle, teacher-forced on the kernel's draws: states / probabilities within the
+    stated bf16 tolerance, every gradient -- including d embed and the FULL d W1 (kernel part W1[:, :32] + GEMM part W1[:, 32:]) --
+    within 2e-2 of scale.  fp32 / two-kernel policies must refuse the mode."""
+    R, P = ops
+    from multimodal_mtrssm_b200 import _lib
+
+    dims = H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    inp = H.mtrssm_inputs(B, T, dims)
+    inp["u_prior_l"] = inp["u_prior_h"] = None
+    up = {k: v for k, v in mtrssm_upstream(B, T, dims).items() if not k.startswith("prior_stoch")}
+    w = {k: v.cuda().requires_grad_(True) for k, v in params.items()}
+    x = cuda(inp)
+    for k in MT_GRAD_IN:
+        x[k] = x[k].requires_grad_(True)
+    xin = dict(x)
+    xin["embed_a"] = R.obs_projection(x["embed_a"], w["audio_representation.rnn_to_post_projector.0.weight"])
+    xin["embed_v"] = R.obs_projection(x["embed_v"], w["vision_representation.rnn_to_post_projector.0.weight"])
+    assert xin["embed_a"].shape == (B, T, 32)
+    got = R.mtrssm_rollout(P.mtrssm_weight_list(w), class_size_l=dims["KL"], class_size_h=dims["KH"], l_tau=dims["l_tau"], h_tau=dims["h_tau"],
+                           precision=_lib.PRECISION_BF16_FUSED, obs_projected=True, **xin)
+    sum((got[k] * up[k].cuda()).sum() for k in up).backward()
+    f = got["feature"].detach().cpu()
+    idx_h = f[..., 32:48].reshape(B, T, dims["CH"], dims["KH"]).argmax(-1)
+    idx_l = f[..., 80:].reshape(B, T, dims["CL"], dims["KL"]).argmax(-1)
+    want, w_ref, x_ref = oracle_mtrssm(params, inp, dims, grad=True, upstream=up, forced=(idx_l, idx_h))
+    rep = H.Report(f"mtrssm obs_projected B={B} T={T} vs teacher-forced oracle")
+    rep.check("deter_l", f[..., 48:80], want["deter_l"], rtol=0, atol=3e-2)
+    for k in ("hidden_l", "post_probs_l", "post_probs_h", "prior_probs_l"):
+        rep.check(k, got[k], want[k], rtol=0, atol=3e-2)
+    for k in MT_GRAD_IN:
+        rep.check("d " + k, x[k].grad, x_ref[k].grad, rtol=0, atol=2e-2 * float(x_ref[k].grad.abs().max()))
+    for k in w:
+        rep.check("d " + k.replace("rnn_to_post_projector", "post"), w[k].grad, w_ref[k].grad, rtol=0, atol=2e-2 * float(w_ref[k].grad.abs().max()))
+    rep.finish()
+    for prec in (_lib.PRECISION_FP32, _lib.PRECISION_BF16):
+        with pytest.raises(RuntimeError, match="obs_projected"):
+            R.mtrssm_rollout(P.mtrssm_weight_list(w), precision=prec, obs_projected=True,
+                             **{k: (v.detach() if v is not None else None) for k, v in xin.items()})
