@@ -123,7 +123,7 @@ class ClockSampler:
 class DirectMtrssm:
     """Pre-allocated buffers + direct C-ABI calls: exactly the three kernels of the hot path, no allocator traffic."""
 
-    def __init__(self, B: int, T: int, precision: int, device: torch.device, prior_sample: bool = True) -> None:
+    def __init__(self, B: int, T: int, precision: int, device: torch.device, prior_sample: bool = True, obs_projected: bool = False) -> None:
         from multimodal_mtrssm_b200 import _lib, synthetic
         from multimodal_mtrssm_b200.params import mtrssm_weight_list
 
@@ -132,6 +132,12 @@ class DirectMtrssm:
         self.params = {k: v.to(device) for k, v in synthetic.mtrssm_params().items()}
         self.weights = mtrssm_weight_list(self.params)
         self.inp = {k: v.to(device) for k, v in synthetic.mtrssm_batch(B, T, prior_noise=prior_sample).items()}
+        EW = 64
+        if obs_projected:  # the kernels take e @ W1[:, 32:].T ([B,T,32]) computed by one GEMM before the loop
+            EW = 32
+            for m, key in (("audio", "embed_a"), ("vision", "embed_v")):
+                w1 = self.params[f"{m}_representation.rnn_to_post_projector.0.weight"]
+                self.inp[key] = (self.inp[key] @ w1[:, 32:].T).contiguous()
         g = torch.Generator().manual_seed(7)
         self.d_feature = torch.randn(B, T, 96, generator=g).to(device)
         self.d_kl = torch.full((B, T), 1.0 / (B * T), device=device)
@@ -145,7 +151,7 @@ class DirectMtrssm:
         if prior_sample:  # the prior MTState's own draws (mmtrssm/state.py:48-49): what the model API launches
             self.out["prior_stoch_h"], self.out["prior_stoch_l"] = e(B, T, 16), e(B, T, 16)
         self.gin = {
-            "d_actions": e(B, T, 6), "d_embed_a": e(B, T, 64), "d_embed_v": e(B, T, 64), "d_deter_h0": e(B, 32), "d_deter_l0": e(B, 32),
+            "d_actions": e(B, T, 6), "d_embed_a": e(B, T, EW), "d_embed_v": e(B, T, EW), "d_deter_h0": e(B, 32), "d_deter_l0": e(B, 32),
             "d_hidden_h0": e(B, 32), "d_hidden_l0": e(B, 32), "d_stoch_h0": e(B, 16), "d_stoch_l0": e(B, 16),
             "dpre": torch.empty(B, T, _lib.MTRSSM_DPRE_FLOATS, device=device, dtype=_lib.record_dtype(precision)),
         }
@@ -157,7 +163,7 @@ class DirectMtrssm:
         self.gws = gws2[0]
         L = _lib
         self.c_dims = L.MtrssmDims(B=B, T=T, A=6, E=64, HD=32, LD=32, HH=32, HR=32, CL=4, KL=4, CH=8, KH=2, l_tau=2.0, h_tau=4.0,
-                                   precision=precision)
+                                   precision=precision, obs_projected=int(obs_projected))
         fill = lambda st, d: [setattr(st, k, L.ptr(v)) for k, v in d.items()] and st  # noqa: E731
         self.c_w = fill(L.MtrssmWeights(), dict(zip(L.MT_WEIGHT_FIELDS, self.weights)))
         self.c_gws = [fill(L.MtrssmWeightGrads(), dict(zip(L.MT_WEIGHT_FIELDS, g_))) for g_ in gws2]
@@ -251,7 +257,7 @@ def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
 
 
 def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int, device: torch.device, host_bf16: bool = False,
-             prior_sample: bool = True) -> dict:
+             prior_sample: bool = True, obs_projected: bool = False) -> dict:
     """Same metric through the public API with HOST buffers, as a training step sees it: the step's encoder outputs,
     actions and initial state are copied from pinned host memory (H2D), the noise is drawn on the device (as
     MoPoE_MMTRSSM.rollout_representation does), the rollout + autograd run through `rollout_ops.mtrssm_rollout`, the
@@ -266,6 +272,10 @@ def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int
     params = {k: v.to(device).requires_grad_(True) for k, v in synthetic.mtrssm_params().items()}
     weights = mtrssm_weight_list(params)
     batch = synthetic.mtrssm_batch(B, T, prior_noise=prior_sample)
+    if obs_projected:  # side measurement only: the host holds the pre-multiplied partials (what a merged encoder layer emits)
+        cpu_params = synthetic.mtrssm_params()
+        for m, key in (("audio", "embed_a"), ("vision", "embed_v")):
+            batch[key] = (batch[key] @ cpu_params[f"{m}_representation.rnn_to_post_projector.0.weight"][:, 32:].T).contiguous()
     # host_bf16 (side measurement only): the two embedding tensors wait on the host in bf16 -- what an autocast encoder emits and
     # what the bf16 policy's contractions consume anyway (the op widens them on the device) -- halving the PCIe bytes
     half = lambda k, v: v.bfloat16() if host_bf16 and k.startswith("embed_") else v  # noqa: E731
@@ -287,7 +297,7 @@ def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int
             pre.submit(host)
         dev = dict(dev)
         dev.update({k: torch.rand(s, device=device) for k, s in noise_shapes.items()})
-        out = R.mtrssm_rollout(weights, precision=precision, **dev)
+        out = R.mtrssm_rollout(weights, precision=precision, obs_projected=obs_projected, **dev)
         loss = (out["feature"] @ readout).sum() + out["kl_l"].mean() + out["kl_h"].mean()
         grads = torch.autograd.grad(loss, weights)
         pre.release(slot)
@@ -796,6 +806,16 @@ def main() -> None:
         extras["reference_eager_on_this_gpu"]["speedup_of_value"] = (B * T / (res["total_ms"] / args.steps * 1e-3)) / extras["reference_eager_on_this_gpu"]["value"]
         summary["x_vs_oracle_eager_same_gpu_same_batch"] = round(extras["reference_eager_on_this_gpu"]["speedup_of_value"], 1)
         extras["e2e_bf16_host_embeddings"] = time_e2e(B, T, precision, 10, 4, 1, device, host_bf16=True, prior_sample=prior_sample)
+        if precision == _lib.PRECISION_BF16_FUSED:  # SURVEY §8 f2 (MoPoE_MMTRSSM.hoist_obs_projection): pre-multiplied first-layer partials
+            pj = DirectMtrssm(B, T, precision, device, prior_sample, obs_projected=True)
+            rp = time_direct(pj, n2, 3, 1)
+            del pj
+            ep = time_e2e(B, T, precision, 10, 4, 1, device, prior_sample=prior_sample, obs_projected=True)
+            extras["obs_projected_f2"] = {"ms_per_step": rp["total_ms"] / n2, "fwd_ms": rp["fwd_ms"], "bwd_ms": rp["bwd_ms"] + rp["wgrad_ms"],
+                                          "value": B * T * n2 / (rp["total_ms"] * 1e-3), "e2e": ep,
+                                          "note": "kernel boundary carries e @ W1[:, 32:].T (32 floats per modality instead of 64): the GEMM that "
+                                                  "produces it (or the merged encoder layer) is outside this number"}
+            summary["obs_projected_f2"] = {"ms_per_step": round(rp["total_ms"] / n2, 4), "e2e_steps_per_s": round(ep["value"])}
         extras["likelihood_f3"] = time_likelihood(device, peak)
     if world > 1:
         import torch.distributed as dist

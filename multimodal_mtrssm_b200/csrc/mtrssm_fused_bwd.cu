@@ -118,17 +118,20 @@ __device__ __forceinline__ void load_op(float (&c)[NT][4], const unsigned char* 
 }
 
 // cp.async a run of `n` (<= 8) consecutive record chunks, first record chunk c0, of step t into the operand image at `dst0`
-// (address of the image of chunk c0).  Lane -> chunk c0 + (lane & 7), rows (lane >> 3) + 4j.
+// (address of the image of chunk c0).  Lane -> row (lane & 15), chunk pair member (lane >> 4): the 16 lanes of a half warp write
+// the 16 rows of ONE chunk = 256 contiguous bytes (conflict-free), lanes L and L + 16 read the two halves of one 32-byte sector.
+// (The first version mapped 8 lanes to 8 chunks of one row: 256-byte strides, 8-way bank conflicts -- 32 shared-memory wavefronts
+// per instruction instead of 4, 27 % of the kernel's shared-memory traffic: profiles/r2_g_ncu_summary.txt.)
 __device__ __forceinline__ void stage_chunks(unsigned char* dst0, const __nv_bfloat16* saved, int c0, int n, int row0, int B, int T, int t,
                                              int lane) {
-    const int c8 = lane & 7, rq = lane >> 3;
-    if (c8 < n) {
-        unsigned char* d = dst0 + c8 * fz::CH + rq * 16;
+    const int rr = lane & 15, half = lane >> 4;
+    const size_t idx = (size_t)min(row0 + rr, B - 1) * T + t;
+    const __nv_bfloat16* src = saved + idx * MTRSSM_SAVED_BF16 + 8 * c0;
+    unsigned char* d = dst0 + (rr >> 3) * 128 + (rr & 7) * 16;  // row rr of a chunk: k-group rr / 8, row rr % 8
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const size_t idx = (size_t)min(row0 + rq + 4 * j, B - 1) * T + t;
-            cp_async16(d + j * 64, saved + idx * MTRSSM_SAVED_BF16 + 8 * (c0 + c8));  // rows rq, rq+4 | rq+8, rq+12 -> +0, +64 | +128, +192
-        }
+    for (int j = 0; j < 4; ++j) {
+        const int c = 2 * j + half;
+        if (c < n) cp_async16(d + c * fz::CH, src + 8 * c);
     }
 }
 
