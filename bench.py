@@ -146,7 +146,8 @@ class DirectMtrssm:
             "feature": e(B, T, 96), "hidden_h": e(B, T, 32), "hidden_l": e(B, T, 32),
             "prior_probs_h": e(B, T, 8, 2), "prior_probs_l": e(B, T, 4, 4), "post_probs_h": e(B, T, 8, 2), "post_probs_l": e(B, T, 4, 4),
             "kl_l": e(B, T), "kl_h": e(B, T),
-            "saved": torch.empty(B, T, _lib.mtrssm_saved_elems(precision), device=device, dtype=_lib.record_dtype(precision)),
+            "saved": torch.empty(_lib.mtrssm_saved_rows(B, precision), T, _lib.mtrssm_saved_elems(precision), device=device,
+                                 dtype=_lib.record_dtype(precision)),
         }
         if prior_sample:  # the prior MTState's own draws (mmtrssm/state.py:48-49): what the model API launches
             self.out["prior_stoch_h"], self.out["prior_stoch_l"] = e(B, T, 16), e(B, T, 16)

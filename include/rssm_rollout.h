@@ -205,7 +205,10 @@ typedef struct {
     float *post_probs_h, *post_probs_l;
     float *prior_stoch_h, *prior_stoch_l;   /* [B,T,HS] [B,T,LS]; may be NULL */
     float *kl_l, *kl_h;                     /* [B,T] each */
-    void *saved;                            /* [B,T,MTRSSM_SAVED_FLOATS] record elements; NULL = inference */
+    void *saved;                            /* opaque record for the backward; NULL = inference.  RSSM_PRECISION_FP32 / _BF16:
+                                               [B,T,MTRSSM_SAVED_FLOATS] fp32 / bf16 elements.  RSSM_PRECISION_BF16_FUSED: bf16, TILE-BLOCKED
+                                               [ceil(B/16)][T][MTRSSM_SAVED_FLOATS/8][16][8] = ceil(B/16)*16 * T * MTRSSM_SAVED_FLOATS
+                                               elements (size it for B rounded up to a multiple of 16; 16-byte aligned) */
 } RssmMtrssmOutputs;
 
 typedef struct {

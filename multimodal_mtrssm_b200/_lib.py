@@ -172,6 +172,12 @@ def record_dtype(precision: int) -> torch.dtype:
     return torch.float32 if precision == PRECISION_FP32 else torch.bfloat16
 
 
+def mtrssm_saved_rows(B: int, precision: int) -> int:
+    """Rows of the MMTRSSM saved record: B, or B rounded up to the 16-sequence tile for the tile-blocked record of
+    PRECISION_BF16_FUSED (include/rssm_rollout.h, RssmMtrssmOutputs.saved)."""
+    return (B + 15) // 16 * 16 if precision == PRECISION_BF16_FUSED else B
+
+
 def mtrssm_saved_elems(precision: int) -> int:
     """Elements per (b,t) of the MMTRSSM saved record (include/rssm_rollout.h)."""
     return MTRSSM_SAVED_FLOATS

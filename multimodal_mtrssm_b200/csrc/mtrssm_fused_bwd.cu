@@ -135,6 +135,20 @@ __device__ __forceinline__ void stage_chunks(unsigned char* dst0, const __nv_bfl
     }
 }
 
+// Tile-blocked record (MtrssmBwdArgs.rec_tiled): chunks c0 .. c0+n-1 of a tile-step are n x 256 CONTIGUOUS bytes in global memory
+// AND in the operand image: the warp copies them as a linear run of 16-byte pieces (piece = lane + 32 i), whole 128-byte lines on
+// both sides -- 4 shared-memory wavefronts per instruction where the row-layout gather above needs 32 (one per lane).
+// (A cp.async.bulk per run was measured as well: no faster at the bench size, slower for one tile -- fence + single-lane issue.)
+__device__ __forceinline__ void stage_chunks_tiled(unsigned char* dst0, const __nv_bfloat16* saved, int c0, int n, int tile_row, int T, int t,
+                                                   int lane) {
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(saved + ((size_t)tile_row * T + t) * (MTRSSM_SAVED_BF16 * 16) + (size_t)c0 * 128);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int piece = lane + 32 * i;
+        if (piece < n * 16) cp_async16(dst0 + piece * 16, src + piece * 16);
+    }
+}
+
 // d logits (16) -> through W2^T -> * ELU'(hidden) -> dY1; both land in the dY operand image; returns dY1 as A operand
 __device__ __forceinline__ void head_bwd_op(const float (&dlogit)[2][4], const uint2* w2t, const float (&hid)[4][4], unsigned char* dy,
                                             int y_logit, int y1, AFrag<1, 2>& f1, const Rows& r, int lane) {
@@ -384,13 +398,20 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                     }
                 }
             };
+            const bool tiled = p.rec_tiled != 0;
             auto stage_logits = [&](int t) {  // LA, LV: read by registers only, refilled right after the MoPoE math
-                if (t >= 0) stage_chunks(svop + 20 * fz2::CH, saved, 20, 4, row0, p.B, T, t, lane);
+                if (t >= 0) {
+                    if (tiled) stage_chunks_tiled(svop + 20 * fz2::CH, saved, 20, 4, row0 >> 4, T, t, lane);
+                    else stage_chunks(svop + 20 * fz2::CH, saved, 20, 4, row0, p.B, T, t, lane);
+                }
                 stage_prl(t);
                 cp_async_commit();
             };
             auto stage_rest = [&](int t) {  // a / v hiddens: free once this warp's MMAs have completed
-                if (t >= 0) stage_chunks(svop + 12 * fz2::CH, saved, 12, 8, row0, p.B, T, t, lane);
+                if (t >= 0) {
+                    if (tiled) stage_chunks_tiled(svop + 12 * fz2::CH, saved, 12, 8, row0 >> 4, T, t, lane);
+                    else stage_chunks(svop + 12 * fz2::CH, saved, 12, 8, row0, p.B, T, t, lane);
+                }
                 cp_async_commit();
             };
             // the embedding operand images (chunks 24..39) are converted from the fp32 inputs by this warp itself, in the window
@@ -563,10 +584,15 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
             float* stFT = reinterpret_cast<float*>(my + fz2::FT);
             float* stPR = reinterpret_cast<float*>(my + fz2::PR) - bst::PR;  // bstage_pr adds bst::PR itself
             uint32_t ph_df = 0, ph_ft = 0, ph_e = 0, ph_end = 0;
+            const bool tiled = p.rec_tiled != 0;
             auto stage_hid = [&](int t) {  // lp, hp, hq hiddens: free once the E-group MMA has completed
                 if (t >= 0) {
-                    stage_chunks(svop, saved, 0, 8, row0, p.B, T, t, lane);
-                    stage_chunks(svop + 8 * fz2::CH, saved, 8, 4, row0, p.B, T, t, lane);
+                    if (tiled) {
+                        stage_chunks_tiled(svop, saved, 0, 12, row0 >> 4, T, t, lane);
+                    } else {
+                        stage_chunks(svop, saved, 0, 8, row0, p.B, T, t, lane);
+                        stage_chunks(svop + 8 * fz2::CH, saved, 8, 4, row0, p.B, T, t, lane);
+                    }
                 }
                 cp_async_commit();
             };

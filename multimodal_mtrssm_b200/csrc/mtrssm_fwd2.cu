@@ -122,11 +122,35 @@ __device__ __forceinline__ void add_staged_projected(float (&acc)[4][4], const f
     }
 }
 
+// Where a step's saved record goes.  Row layout: [B][T][saved_ld] (A / B = this lane's two rows).  Tile-blocked layout
+// (RSSM_PRECISION_BF16_FUSED): `tile` = the tile-step's contiguous block [26 chunks][16 rows][8 bf16] -- exactly the tcgen05 operand
+// image the fused backward wants, so it stages a head's hiddens with ONE bulk copy; a warp's record stores of one step land in
+// one 6.5 KB block instead of 16 rows x 5 segments scattered at a T x 416-byte stride.  All 16 rows are written (the pad rows of
+// the last tile hold copies of the last real row: they meet zero dY rows in the weight-gradient MMAs and must stay finite).
+struct RecDst {
+    __nv_bfloat16 *A, *B, *tile;
+    __device__ __forceinline__ explicit operator bool() const { return A != nullptr || tile != nullptr; }
+};
+template <int NT, bool TILED>
+__device__ __forceinline__ void store_rec_dst(const float (&c)[NT][4], const RecDst& d, int col0, const Rows& r) {
+    if constexpr (TILED) {
+#pragma unroll
+        for (int j = 0; j < NT / 2; ++j) {
+            __nv_bfloat16* q = d.tile + ((col0 + 16 * j) / 8 + (r.t >> 1)) * 128 + r.g * 8 + (r.t & 1) * 4;
+            *reinterpret_cast<uint2*>(q) = make_uint2(pack_bf16(c[2 * j][0], c[2 * j][1]), pack_bf16(c[2 * j + 1][0], c[2 * j + 1][1]));
+            *reinterpret_cast<uint2*>(q + 64) = make_uint2(pack_bf16(c[2 * j][2], c[2 * j][3]), pack_bf16(c[2 * j + 1][2], c[2 * j + 1][3]));
+        }
+    } else {
+        store_rec<NT>(c, d.A + col0, d.B + col0, r);
+    }
+}
+
 // hidden -> ELU -> (saved) -> logits, as head_l2 of mtrssm_kernels.cu (NS = 1)
-__device__ __forceinline__ void head2_l2(float (&acc)[4][4], float (&logits)[2][4], const float* bias2, const uint2* w2, __nv_bfloat16* svA,
-                                         __nv_bfloat16* svB, int sv_off, const Rows& r, int lane) {
+template <bool TILED>
+__device__ __forceinline__ void head2_l2(float (&acc)[4][4], float (&logits)[2][4], const float* bias2, const uint2* w2, const RecDst& sv,
+                                         int sv_off, const Rows& r, int lane) {
     map_c<4>(acc, EluOp<true>{});
-    if (svA) store_rec<4>(acc, svA + sv_off, svB + sv_off, r);
+    if (sv) store_rec_dst<4, TILED>(acc, sv, sv_off, r);
     AFrag<1, 2> f1;
     to_afrag<1, 2>(f1, acc);
     init_bias<2>(logits, bias2, r.t);
@@ -134,7 +158,7 @@ __device__ __forceinline__ void head2_l2(float (&acc)[4][4], float (&logits)[2][
 }
 
 // blockDim.x = 64 * (tiles per CTA), 1 .. 8 tiles: small batches run few tiles per CTA to reach more SMs
-template <int KL, int KH>
+template <int KL, int KH, bool TILED>
 __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs p) {
     constexpr int NS = 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -237,8 +261,11 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
             if (prior_draws) fetch_uniforms<KH>(p.u_prior_h, (size_t)r.rA * T, (size_t)r.rB * T, lane, upA, upB);
             for (int t = 0; t < T; ++t) {
                 const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
-                __nv_bfloat16* svA = saved ? saved + iA * p.saved_ld : nullptr;
-                __nv_bfloat16* svB = saved ? saved + iB * p.saved_ld : nullptr;
+                RecDst sv{nullptr, nullptr, nullptr};
+                if (saved != nullptr) {
+                    if constexpr (TILED) sv.tile = saved + ((size_t)tile * T + t) * (MTRSSM_SAVED_BF16 * 16);
+                    else sv.A = saved + iA * p.saved_ld, sv.B = saved + iB * p.saved_ld;
+                }
                 const float* stage = stage_base + (t & 1) * stg::FLOATS;
                 cp_async_wait_all();
                 __syncwarp();
@@ -294,7 +321,7 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                     float acc[4][4], lg[2][4];
                     init_bias<4>(acc, bias + mt::B_HP1, r.t);
                     gemm<NS, 2, 4>(acc, dhf, wblk<NS>(W, mt::HP1), lane);
-                    head2_l2(acc, lg, bias + mt::B_HP2, wblk<NS>(W, mt::HP2), svA, svB, mts::HP_HID, r, lane);
+                    head2_l2<TILED>(acc, lg, bias + mt::B_HP2, wblk<NS>(W, mt::HP2), sv, mts::HP_HID, r, lane);
                     softmax_groups<KH, true>(lg, pph);
                     store_c<2>(pph, p.prior_probs_h + iA * 16, p.prior_probs_h + iB * 16, r);
                 }
@@ -310,7 +337,7 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                     init_bias<4>(acc, bias + mt::B_HQ1, r.t);
                     gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, mt::HQ1L), lane);
                     gemm<NS, 2, 4>(acc, dhf, wblk<NS>(W, mt::HQ1H), lane);
-                    head2_l2(acc, lg, bias + mt::B_HQ2, wblk<NS>(W, mt::HQ2), svA, svB, mts::HQ_HID, r, lane);
+                    head2_l2<TILED>(acc, lg, bias + mt::B_HQ2, wblk<NS>(W, mt::HQ2), sv, mts::HQ_HID, r, lane);
                     softmax_groups<KH, true>(lg, q);
                     store_c<2>(q, p.post_probs_h + iA * 16, p.post_probs_h + iB * 16, r);
                     sample_onehot<KH>(q, stage + stg::U1 + r.g * 8, stage + stg::U1 + (r.g + 8) * 8, zs, lane);
@@ -333,8 +360,11 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
             if (prior_draws) fetch_uniforms<KL>(p.u_prior_l, (size_t)r.rA * T, (size_t)r.rB * T, lane, upA, upB);
             for (int t = 0; t < T; ++t) {
                 const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
-                __nv_bfloat16* svA = saved ? saved + iA * p.saved_ld : nullptr;
-                __nv_bfloat16* svB = saved ? saved + iB * p.saved_ld : nullptr;
+                RecDst sv{nullptr, nullptr, nullptr};
+                if (saved != nullptr) {
+                    if constexpr (TILED) sv.tile = saved + ((size_t)tile * T + t) * (MTRSSM_SAVED_BF16 * 16);
+                    else sv.A = saved + iA * p.saved_ld, sv.B = saved + iB * p.saved_ld;
+                }
                 const float* stage = stage_base + (t & 1) * stg::FLOATS;
                 cp_async_wait_all();
                 __syncwarp();
@@ -366,9 +396,9 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                 // ---- lower posterior: modality heads on d_l (:422-433), MoPoE fusion (:436-455), sample (:456) ----------
                 float la[2][4], lv[2][4];
                 gemm<NS, 2, 4>(acca, dlf, wblk<NS>(W, mt::A1H), lane);
-                head2_l2(acca, la, bias + mt::B_A2, wblk<NS>(W, mt::A2), svA, svB, mts::A_HID, r, lane);
+                head2_l2<TILED>(acca, la, bias + mt::B_A2, wblk<NS>(W, mt::A2), sv, mts::A_HID, r, lane);
                 gemm<NS, 2, 4>(accv, dlf, wblk<NS>(W, mt::V1H), lane);
-                head2_l2(accv, lv, bias + mt::B_V2, wblk<NS>(W, mt::V2), svA, svB, mts::V_HID, r, lane);
+                head2_l2<TILED>(accv, lv, bias + mt::B_V2, wblk<NS>(W, mt::V2), sv, mts::V_HID, r, lane);
                 float q[2][4];
                 {
                     float lsa[2][4], lsv[2][4], mixed[2][4], zs[2][4];
@@ -385,9 +415,9 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                     store_c<2>(zs, p.feature + iA * F + 80, p.feature + iB * F + 80, r);
                 }
                 store_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r);
-                if (svA) {
-                    store_rec<2>(la, svA + mts::LA, svB + mts::LA, r);
-                    store_rec<2>(lv, svA + mts::LV, svB + mts::LV, r);
+                if (sv) {
+                    store_rec_dst<2, TILED>(la, sv, mts::LA, r);
+                    store_rec_dst<2, TILED>(lv, sv, mts::LV, r);
                 }
                 // ---- lower prior (:285-286): off the recurrence, in the shadow of the state warp's cells -------------------
                 float ppl[2][4];
@@ -395,7 +425,7 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                     float acc[4][4], lg[2][4];
                     init_bias<4>(acc, bias + mt::B_LP1, r.t);
                     gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, mt::LP1), lane);
-                    head2_l2(acc, lg, bias + mt::B_LP2, wblk<NS>(W, mt::LP2), svA, svB, mts::LP_HID, r, lane);
+                    head2_l2<TILED>(acc, lg, bias + mt::B_LP2, wblk<NS>(W, mt::LP2), sv, mts::LP_HID, r, lane);
                     softmax_groups<KL, true>(lg, ppl);
                     store_c<2>(ppl, p.prior_probs_l + iA * 16, p.prior_probs_l + iB * 16, r);
                 }
@@ -428,7 +458,7 @@ static cudaError_t launch_fwd2_k(const MtrssmFwdArgs& a, cudaStream_t s) {
     while (tpc < 8 && (ntiles + tpc - 1) / tpc > sms) tpc *= 2;
     const int groups = (ntiles + tpc - 1) / tpc;
     const size_t smem = (size_t)mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float) + (size_t)tpc * f2::TILE_BYTES;
-    auto kernel = mtrssm_fwd2_kernel<KL, KH>;
+    auto kernel = a.rec_tiled ? mtrssm_fwd2_kernel<KL, KH, true> : mtrssm_fwd2_kernel<KL, KH, false>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)((size_t)mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float) + 8 * f2::TILE_BYTES));
     if (err != cudaSuccess) return err;

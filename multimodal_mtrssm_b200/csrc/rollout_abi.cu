@@ -600,6 +600,8 @@ static int mtrssm_fwd_common(const RssmMtrssmDims* d, const RssmMtrssmWeights* w
     a.kl_l = out->kl_l, a.kl_h = out->kl_h, a.saved = imagine ? nullptr : out->saved;
     a.saved_ld = mt_saved_ld(d->precision);
     a.obs_projected = imagine ? 0 : d->obs_projected;
+    a.rec_tiled = d->precision == RSSM_PRECISION_BF16_FUSED && getenv("RSSM_REC_ROW_LAYOUT") == nullptr ? 1 : 0;  // tile-blocked saved record
+                                                                                 // (include/rssm_rollout.h); the env var is for A/B timing
     g_launches.fetch_add(1);
     // bf16 policies, posterior rollout: two warps per tile (mtrssm_fwd2.cu); imagination and the fp32-parity policy: one warp per tile
     if (!imagine && d->precision != RSSM_PRECISION_FP32 && getenv("RSSM_FWD_ONE_WARP") == nullptr)
@@ -646,7 +648,10 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
     a.d_deter_h0 = gin->d_deter_h0, a.d_deter_l0 = gin->d_deter_l0, a.d_hidden_h0 = gin->d_hidden_h0;
     a.d_hidden_l0 = gin->d_hidden_l0, a.d_stoch_h0 = gin->d_stoch_h0, a.d_stoch_l0 = gin->d_stoch_l0;
     a.obs_projected = d->obs_projected;
+    a.rec_tiled = fused && getenv("RSSM_REC_ROW_LAYOUT") == nullptr ? 1 : 0;
     if (d->obs_projected && !fused) return fail("obs_projected needs the fused backward (gw != NULL, RSSM_PRECISION_BF16_FUSED)");
+    if (d->precision == RSSM_PRECISION_BF16_FUSED && !fused)
+        return fail("RSSM_PRECISION_BF16_FUSED writes the saved record tile-blocked: its backward needs the weight-gradient pointers (gw != NULL)");
     if (fused) {
         const float* const* gp = reinterpret_cast<const float* const*>(gw);
         for (size_t i = 0; i < sizeof(RssmMtrssmWeightGrads) / sizeof(float*); ++i)
@@ -663,6 +668,9 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
 int rssm_mtrssm_wgrad(const RssmMtrssmDims* d, const RssmMtrssmInputs* in, const RssmMtrssmOutputs* fo, const void* dpre,
                       const RssmMtrssmWeightGrads* gw, void* stream) {
     if (check_mtrssm(d)) return 1;
+    if (d->precision == RSSM_PRECISION_BF16_FUSED)
+        return fail("rssm_mtrssm_wgrad reads the row-layout record of RSSM_PRECISION_BF16 / _FP32; RSSM_PRECISION_BF16_FUSED computes the "
+                    "weight gradients inside rssm_mtrssm_rollout_bwd");
     REQUIRE(in); REQUIRE(fo); REQUIRE(dpre); REQUIRE(gw);
     REQUIRE(in->actions); REQUIRE(in->embed_a); REQUIRE(in->embed_v); REQUIRE(in->deter_h0); REQUIRE(in->deter_l0);
     REQUIRE(in->stoch_h0); REQUIRE(in->stoch_l0); REQUIRE(fo->feature); REQUIRE(fo->saved);

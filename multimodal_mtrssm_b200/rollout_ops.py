@@ -331,7 +331,8 @@ def mtrssm_rollout_op(
         has_prior = u_prior_l is not None
         pz_h, pz_l = (e(B, T, 16), e(B, T, 16)) if has_prior else (e(0), e(0))
         kl_l, kl_h = e(B, T), e(B, T)
-        saved = torch.empty(B, T, _lib.mtrssm_saved_elems(precision), device=dev, dtype=_lib.record_dtype(precision)) if save else e(0)
+        saved = (torch.empty(_lib.mtrssm_saved_rows(B, precision), T, _lib.mtrssm_saved_elems(precision), device=dev,
+                             dtype=_lib.record_dtype(precision)) if save else e(0))
         w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
         inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE, "u_post_l", "u_post_h", "u_prior_l", "u_prior_h"],
                     (actions, embed_a, embed_v, *state, u_post_l, u_post_h, u_prior_l, u_prior_h))
@@ -352,7 +353,8 @@ def _(weights, actions, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, 
     e = actions.new_empty
     pz = e(B, T, 16) if u_prior_l is not None else e(0)
     return [e(B, T, 96), e(B, T, 32), e(B, T, 32), e(B, T, 16 // KH, KH), e(B, T, 16 // KL, KL), e(B, T, 16 // KH, KH),
-            e(B, T, 16 // KL, KL), pz, torch.empty_like(pz), e(B, T), e(B, T), e(B, T, _lib.mtrssm_saved_elems(precision), dtype=_lib.record_dtype(precision)) if save else e(0)]
+            e(B, T, 16 // KL, KL), pz, torch.empty_like(pz), e(B, T), e(B, T),
+            e(_lib.mtrssm_saved_rows(B, precision), T, _lib.mtrssm_saved_elems(precision), dtype=_lib.record_dtype(precision)) if save else e(0)]
 
 
 @torch.library.custom_op("mtrssm_b200::mtrssm_rollout_bwd", mutates_args=())
