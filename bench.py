@@ -123,7 +123,8 @@ class ClockSampler:
 class DirectMtrssm:
     """Pre-allocated buffers + direct C-ABI calls: exactly the three kernels of the hot path, no allocator traffic."""
 
-    def __init__(self, B: int, T: int, precision: int, device: torch.device, prior_sample: bool = True, obs_projected: bool = False) -> None:
+    def __init__(self, B: int, T: int, precision: int, device: torch.device, prior_sample: bool = True, obs_projected: bool = False,
+                 grouped: bool | None = None) -> None:
         from multimodal_mtrssm_b200 import _lib, synthetic
         from multimodal_mtrssm_b200.params import mtrssm_weight_list
 
@@ -142,15 +143,25 @@ class DirectMtrssm:
         self.d_feature = torch.randn(B, T, 96, generator=g).to(device)
         self.d_kl = torch.full((B, T), 1.0 / (B * T), device=device)
         e = lambda *s: torch.empty(*s, device=device)  # noqa: E731
-        self.out = {
-            "feature": e(B, T, 96), "hidden_h": e(B, T, 32), "hidden_l": e(B, T, 32),
-            "prior_probs_h": e(B, T, 8, 2), "prior_probs_l": e(B, T, 4, 4), "post_probs_h": e(B, T, 8, 2), "post_probs_l": e(B, T, 4, 4),
-            "kl_l": e(B, T), "kl_h": e(B, T),
-            "saved": torch.empty(_lib.mtrssm_saved_rows(B, precision), T, _lib.mtrssm_saved_elems(precision), device=device,
-                                 dtype=_lib.record_dtype(precision)),
-        }
-        if prior_sample:  # the prior MTState's own draws (mmtrssm/state.py:48-49): what the model API launches
-            self.out["prior_stoch_h"], self.out["prior_stoch_l"] = e(B, T, 16), e(B, T, 16)
+        # bf16 fused policy: the outputs of a (b,t) share one 1 KB row (include/rssm_rollout.h, RssmMtrssmOutputs.ld_*), as
+        # rollout_ops.mtrssm_rollout allocates them; the other policies keep one dense tensor per output
+        self.grouped = self.fused if grouped is None else grouped
+        saved = torch.empty(_lib.mtrssm_saved_rows(B, precision), T, _lib.mtrssm_saved_elems(precision), device=device,
+                            dtype=_lib.record_dtype(precision))
+        if self.grouped:
+            self.row, self.kl = e(B, T, _lib.MT_ROW_PITCH), e(B, T, 2)
+            off = _lib.MT_ROW_OFFSETS
+            width = lambda k: 96 if k == "feature" else 32 if k.startswith("hidden") else 16  # noqa: E731
+            self.out = {k: self.row[..., o:o + width(k)] for k, o in off.items() if prior_sample or not k.startswith("prior_stoch")}
+            self.out.update(kl_l=self.kl[..., 0], kl_h=self.kl[..., 1], saved=saved)
+        else:
+            self.out = {
+                "feature": e(B, T, 96), "hidden_h": e(B, T, 32), "hidden_l": e(B, T, 32),
+                "prior_probs_h": e(B, T, 8, 2), "prior_probs_l": e(B, T, 4, 4), "post_probs_h": e(B, T, 8, 2),
+                "post_probs_l": e(B, T, 4, 4), "kl_l": e(B, T), "kl_h": e(B, T), "saved": saved,
+            }
+            if prior_sample:  # the prior MTState's own draws (mmtrssm/state.py:48-49): what the model API launches
+                self.out["prior_stoch_h"], self.out["prior_stoch_l"] = e(B, T, 16), e(B, T, 16)
         self.gin = {
             "d_actions": e(B, T, 6), "d_embed_a": e(B, T, EW), "d_embed_v": e(B, T, EW), "d_deter_h0": e(B, 32), "d_deter_l0": e(B, 32),
             "d_hidden_h0": e(B, 32), "d_hidden_l0": e(B, 32), "d_stoch_h0": e(B, 16), "d_stoch_l0": e(B, 16),
@@ -170,7 +181,12 @@ class DirectMtrssm:
         self.c_gws = [fill(L.MtrssmWeightGrads(), dict(zip(L.MT_WEIGHT_FIELDS, g_))) for g_ in gws2]
         self.c_gw = self.c_gws[0]
         self.c_in = fill(L.MtrssmInputs(), self.inp)
-        self.c_out = fill(L.MtrssmOutputs(), self.out)
+        self.c_out = L.MtrssmOutputs()
+        for k, v in self.out.items():
+            setattr(self.c_out, k, v.data_ptr())
+        if self.grouped:
+            self.c_out.ld_feature = self.c_out.ld_hidden = self.c_out.ld_probs = self.c_out.ld_stoch = L.MT_ROW_PITCH
+            self.c_out.ld_kl = 2
         self.c_up = fill(L.MtrssmUpstream(), {"d_feature": self.d_feature, "d_kl_l": self.d_kl, "d_kl_h": self.d_kl})
         self.c_up.kl_wq, self.c_up.kl_wp = 0.2, 0.8
         self.c_gin = fill(L.MtrssmInputGrads(), self.gin)

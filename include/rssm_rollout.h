@@ -62,6 +62,7 @@ extern "C" {
 #define MTRSSM_DPRE_FLOATS 304  /* weight-gradient kernel read bulk-copied 32-row slabs with ldmatrix in place              */
 /* (the fused backward reads the same saved record as the two-kernel backward) */
 #define MTRSSM_SAVED_BF16 MTRSSM_SAVED_FLOATS
+#define MTRSSM_ROW_PITCH 256   /* floats per (b,t) row of the grouped outputs (RssmMtrssmOutputs.ld_*) */
 
 /* ---- MoPoE-MRSSM -------------------------------------------------------------------------------------- */
 typedef struct {
@@ -209,6 +210,17 @@ typedef struct {
                                                [B,T,MTRSSM_SAVED_FLOATS] fp32 / bf16 elements.  RSSM_PRECISION_BF16_FUSED: bf16, TILE-BLOCKED
                                                [ceil(B/16)][T][MTRSSM_SAVED_FLOATS/8][16][8] = ceil(B/16)*16 * T * MTRSSM_SAVED_FLOATS
                                                elements (size it for B rounded up to a multiple of 16; 16-byte aligned) */
+    /* Row pitches in floats (ABI v5).  All 0 = DENSE outputs: every tensor above contiguous [B,T,w].  Or the GROUPED row of a (b,t):
+       one [B,T,MTRSSM_ROW_PITCH] buffer
+       [feature 0:96 | hidden_h 96:128 | hidden_l 128:160 | prior_probs_h 160:176 | prior_probs_l 176:192 | post_probs_h 192:208 |
+       post_probs_l 208:224 | prior_stoch_h 224:240 | prior_stoch_l 240:256] -- every pointer above points INTO that buffer (16-byte
+       aligned, any column order) and ld_feature = ld_hidden = ld_probs = ld_stoch = MTRSSM_ROW_PITCH -- plus one [B,T,2] buffer
+       [kl_l | kl_h] with ld_kl = 2.  A row-step then writes eight whole 128-byte lines of one 1 KB row instead of ten partial-line
+       segments (forward 0.56 -> 0.49 ms at the bench batch; profiles/r2_p_grouped_rows_ab.txt).  The pitches are compile-time
+       constants of the kernels, so no other value is accepted.  Grouped rows are honoured by rssm_mtrssm_rollout_fwd and the
+       fused rssm_mtrssm_rollout_bwd under RSSM_PRECISION_BF16_FUSED (the layout the Python ops use); every other entry point /
+       policy needs 0. */
+    int ld_feature, ld_hidden, ld_probs, ld_stoch, ld_kl;
 } RssmMtrssmOutputs;
 
 typedef struct {

@@ -75,8 +75,13 @@ MtrssmOutputs = _struct(
     _ptrs(
         "feature hidden_h hidden_l prior_probs_h prior_probs_l post_probs_h post_probs_l "
         "prior_stoch_h prior_stoch_l kl_l kl_h saved"
-    ),
+    )
+    + [(n, C.c_int) for n in "ld_feature ld_hidden ld_probs ld_stoch ld_kl".split()],  # row pitches, 0 = natural (ABI v5)
 )
+# grouped per-(b,t) output row of the bf16 fused policy (include/rssm_rollout.h): float offsets inside the [B,T,256] buffer
+MT_ROW_PITCH = 256
+MT_ROW_OFFSETS = {"feature": 0, "hidden_h": 96, "hidden_l": 128, "prior_probs_h": 160, "prior_probs_l": 176, "post_probs_h": 192,
+                  "post_probs_l": 208, "prior_stoch_h": 224, "prior_stoch_l": 240}
 MtrssmUpstream = _struct(
     "RssmMtrssmUpstream",
     _ptrs(

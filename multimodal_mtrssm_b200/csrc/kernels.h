@@ -155,6 +155,7 @@ struct MtrssmFwdArgs {
     void* saved;
     int saved_ld;    // elements per (b,t) row of `saved`
     int obs_projected;  // 1: embed_a / embed_v are the pre-multiplied first-layer partials [B,T,32] (include/rssm_rollout.h)
+    int ld_feature;  // 0 = dense outputs; MTRSSM_ROW_PITCH = grouped rows (RssmMtrssmOutputs.ld_*: all pitches 256, kl 2)
     int rec_tiled;      // 1: `saved` is TILE-BLOCKED: [ceil(B/16)][T][26 chunks][16 rows][8 bf16] -- a tile-step's record is one contiguous
                         // 6.5 KB block already in the tcgen05 operand-image order (RSSM_PRECISION_BF16_FUSED); 0: [B][T][saved_ld]
 };
@@ -174,7 +175,8 @@ struct MtrssmBwdArgs {
     float *d_actions, *d_embed_a, *d_embed_v;
     float *d_deter_h0, *d_deter_l0, *d_hidden_h0, *d_hidden_l0, *d_stoch_h0, *d_stoch_l0;
     int obs_projected;  // 1: d_embed_a / d_embed_v are [B,T,32] = d of the pre-multiplied partials; no embedding operand images
-    int rec_tiled;      // as in MtrssmFwdArgs (the fused backward reads the tile-blocked record with bulk copies)
+    int rec_tiled;      // as in MtrssmFwdArgs (the fused backward stages the tile-blocked record as contiguous runs)
+    int ld_feature;  // 0 = dense forward outputs; MTRSSM_ROW_PITCH = grouped rows
 };
 
 cudaError_t launch_mtrssm_fwd(const MtrssmFwdArgs& a, int precision, bool imagine, cudaStream_t s);

@@ -79,6 +79,8 @@ __device__ __forceinline__ void bulk_rows(float* dst, int pitch_words, const cha
 }
 
 // the four probability tensors of step t (one cp.async group): lane -> chunk column c8 = lane & 7 of the rows rq + 4j
+// LDP: row pitch (floats) of the probability tensors -- 16 (dense) or MTRSSM_ROW_PITCH (grouped rows)
+template <int LDP = 16>
 __device__ __forceinline__ void bstage_pr(float* st, const MtrssmBwdArgs& p, int row0, int t, int lane) {
     if (t >= 0) {
         const int c8 = lane & 7, rq = lane >> 3;
@@ -87,11 +89,12 @@ __device__ __forceinline__ void bstage_pr(float* st, const MtrssmBwdArgs& p, int
         const bool hi = (c8 >> 2) != 0;
         const float* src0 = hi ? p.post_probs_l : p.post_probs_h;
         const float* src1 = hi ? p.prior_probs_l : p.prior_probs_h;
+        constexpr int ldP = LDP;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const size_t idx = (size_t)min(row0 + rq + 4 * j, p.B - 1) * p.T + t;
-            cp_async16(d2 + j * 256, src0 + idx * 16 + 4 * (c8 & 3));
-            cp_async16(d2 + j * 256 + 32, src1 + idx * 16 + 4 * (c8 & 3));
+            cp_async16(d2 + j * 256, src0 + idx * ldP + 4 * (c8 & 3));
+            cp_async16(d2 + j * 256 + 32, src1 + idx * ldP + 4 * (c8 & 3));
         }
     }
     cp_async_commit();

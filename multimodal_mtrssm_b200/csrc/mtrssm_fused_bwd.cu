@@ -267,7 +267,8 @@ __device__ __forceinline__ void xch_load(float (&c)[NT][4], const float* buf, in
 // work: it converts the feature row and the fp32 embeddings into the tcgen05 operand images, issues the end-of-step MMA group
 // (and the embedding MMA), computes the embedding / action gradients from the dY images (d_embed = dY1 . W1e, d_action = dY_l .
 // W_in) and stores them, and refills the feature-row stage.  12 warps per SM instead of 8, <= 168 registers each.
-template <int KL, int KH, int WPT>
+// GROUPED: the forward's outputs share one MTRSSM_ROW_PITCH-float row per (b,t) (RssmMtrssmOutputs.ld_*); compile-time pitches
+template <int KL, int KH, int WPT, bool GROUPED>
 __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const MtrssmBwdArgs p, const FusedFlushTable ft) {
     constexpr int NS = 1;
     static_assert(WPT == 2 || WPT == 3, "two (core, mod) or three (core, mod, aux) warps per tile");
@@ -356,6 +357,10 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
         // named barriers of the tile.  X: mod -> core (+ aux) "my dY columns and XDDL are complete"; Y: core -> mod "d stoch_l is in
         // XDZL"; Z (three warps): core -> aux "my dY columns are complete and I am done with the feature-row stage"
         const int bar_x = 1 + WPT * tile, bar_y = 2 + WPT * tile, bar_z = 3 + WPT * tile;
+        // row pitches of the grouped forward outputs (include/rssm_rollout.h: feature | hidden | probabilities | prior draws share one
+        // 1 KB row per (b,t)); natural widths when the caller keeps them in separate tensors
+        constexpr size_t ft_pitch = (size_t)(GROUPED ? MTRSSM_ROW_PITCH : 96) * sizeof(float);
+        constexpr int ldP = GROUPED ? MTRSSM_ROW_PITCH : 16;
         constexpr int X_COUNT = 32 * WPT;
         (void)bar_z;
 
@@ -394,7 +399,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const size_t idx = (size_t)min(row0 + rq + 4 * j, p.B - 1) * T + t;
-                        cp_async16(d2 + j * 128, src + idx * 16 + 4 * (c8 & 3));
+                        cp_async16(d2 + j * 128, src + idx * ldP + 4 * (c8 & 3));
                     }
                 }
             };
@@ -598,8 +603,8 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
             };
             bulk_rows(stDF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, T - 1, &bars[fz2::BAR_DF], lane);
             if constexpr (WPT == 2)
-                bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
-            bstage_pr(stPR, p, row0, T - 1, lane);  // cp.async groups per step, in issue order: PR(t-1) | HID(t-1)
+                bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), ft_pitch, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
+            bstage_pr<ldP>(stPR, p, row0, T - 1, lane);  // cp.async groups per step, in issue order: PR(t-1) | HID(t-1)
             stage_hid(T - 1);
             const float* dkl_src = (r.t < 2) ? p.d_kl_h : p.d_kl_l;  // quad lanes: 0 kl_h row A, 1 kl_h row B, 2 kl_l row A, 3 kl_l row B
             const size_t dkl_row = (size_t)((r.t & 1) ? r.rB : r.rA) * T;
@@ -662,7 +667,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                     load_staged<2, true>(q, stPR + bst::PR, 64, 0, r.g, r.t);
                     load_staged<2, true>(pp, stPR + bst::PR, 64, 32, r.g, r.t);
                     __syncwarp();  // every lane is done with PR: refill it for the next (earlier) step
-                    bstage_pr(stPR, p, row0, t - 1, lane);
+                    bstage_pr<ldP>(stPR, p, row0, t - 1, lane);
                     add_global<2>(dzh, p.d_post_probs_h, iA * 16, iB * 16, r.t);
                     zero_c<2>(dpp);
                     add_global<2>(dpp, p.d_prior_probs_h, iA * 16, iB * 16, r.t);
@@ -703,7 +708,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                     load_staged<2, false>(zl, stFT, bst::DF_LD, 80, r.g, r.t);
                     __syncwarp();
                     if (t > 0)
-                        bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, t - 1, &bars[fz2::BAR_FT], lane);
+                        bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), ft_pitch, 384, row0, p.B, T, t - 1, &bars[fz2::BAR_FT], lane);
                     // X operands: bf16 [d_l | d_h | z_l | z_h](t) and [action(t+1) | ones]
                     store_op<4>(dl, dop, 0, r);
                     store_op<4>(dh, dop, 32, r);
@@ -847,7 +852,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                     prefetch_bulk_l2(p.embed_v + j, 256);
                 }
             };
-            bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
+            bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), ft_pitch, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
             const bool emb = !p.obs_projected;  // obs_projected: no embedding operand images, no embedding MMA, no d_embed GEMMs here
             if (emb) embed_prefetch(T - 2);
             // the fp32 embeddings of a step are requested one step ahead (registers) and converted at the top of their step
@@ -924,7 +929,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 }
                 FZ_TS(7);
                 if (t > 0)
-                    bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), 384, 384, row0, p.B, T, t - 1, &bars[fz2::BAR_FT], lane);
+                    bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), ft_pitch, 384, row0, p.B, T, t - 1, &bars[fz2::BAR_FT], lane);
                 if (p.d_actions != nullptr) {  // d a = dY_l . W_in[:, :A] (l_rnn._input2h, :283-284)
                     AFrag<NS, 2> fl;
                     to_afrag<NS, 2>(fl, pl);
@@ -1084,8 +1089,11 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
 #endif
         return cudaGetLastError();
     };
+    const bool grouped = a.ld_feature != 0;
 #define FUSED_DISPATCH(KLv, KHv) \
-    if (a.KL == KLv && a.KH == KHv) return wpt == 2 ? launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 2>) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 3>);
+    if (a.KL == KLv && a.KH == KHv)                                                                                                   \
+        return wpt == 2 ? (grouped ? launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 2, true>) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 2, false>)) \
+                        : (grouped ? launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 3, true>) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 3, false>));
     FUSED_DISPATCH(4, 2)
 #ifndef RSSM_EXP_ONLY_DEFAULT
     FUSED_DISPATCH(4, 4)

@@ -158,8 +158,12 @@ __device__ __forceinline__ void head2_l2(float (&acc)[4][4], float (&logits)[2][
 }
 
 // blockDim.x = 64 * (tiles per CTA), 1 .. 8 tiles: small batches run few tiles per CTA to reach more SMs
-template <int KL, int KH, bool TILED>
+// LAYOUT: 0 = row-layout record, dense outputs (bf16 two-kernel policy); 1 = tile-blocked record, dense outputs; 2 = tile-blocked
+// record, GROUPED outputs (one 256-float row per (b,t), RssmMtrssmOutputs.ld_*).  The pitches are compile-time constants: runtime
+// pitches cost 3-4% on the latency-bound one-tile rollouts (64-bit IMADs in front of every store; profiles/r2_p_grouped_rows_ab.txt)
+template <int KL, int KH, int LAYOUT>
 __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs p) {
+    constexpr bool TILED = LAYOUT >= 1, GROUPED = LAYOUT == 2;
     constexpr int NS = 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2* W = reinterpret_cast<uint2*>(smem_raw);
@@ -226,6 +230,8 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
     const int bar_d = 2 * pair, bar_z = 2 * pair + 1;  // d_l: state -> obs;  z_l: obs -> state
     __nv_bfloat16* saved = reinterpret_cast<__nv_bfloat16*>(p.saved);
     const bool prior_draws = p.u_prior_l != nullptr;
+    constexpr int ldF = GROUPED ? MTRSSM_ROW_PITCH : F, ldH = GROUPED ? MTRSSM_ROW_PITCH : 32, ldP = GROUPED ? MTRSSM_ROW_PITCH : 16,
+                  ldS = GROUPED ? MTRSSM_ROW_PITCH : 16, ldK = GROUPED ? 2 : 1;
 
     // persistent over tiles: a warp pair walks tiles blockIdx.x * TPC + pair, + gridDim.x * TPC, ... (tiles are independent)
     for (int tile = blockIdx.x * TPC + pair; tile < ntiles; tile += gridDim.x * TPC) {
@@ -311,10 +317,10 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                         dh[nt][j] = Math<true>::tanh(uh[nt][j]);
                     }
                 to_afrag<NS, 2>(dhf, dh);
-                store_c<4>(dh, p.feature + iA * F, p.feature + iB * F, r);
-                store_c<4>(dl, p.feature + iA * F + 48, p.feature + iB * F + 48, r);
-                store_c<4>(uh, p.hidden_h + iA * 32, p.hidden_h + iB * 32, r);
-                store_c<4>(ul, p.hidden_l + iA * 32, p.hidden_l + iB * 32, r);
+                store_c<4>(dh, p.feature + iA * ldF, p.feature + iB * ldF, r);
+                store_c<4>(dl, p.feature + iA * ldF + 48, p.feature + iB * ldF + 48, r);
+                store_c<4>(uh, p.hidden_h + iA * ldH, p.hidden_h + iB * ldH, r);
+                store_c<4>(ul, p.hidden_l + iA * ldH, p.hidden_l + iB * ldH, r);
                 // ---- higher prior (:311-312) ------------------------------------------------------------------------------
                 float pph[2][4];
                 {
@@ -323,12 +329,12 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                     gemm<NS, 2, 4>(acc, dhf, wblk<NS>(W, mt::HP1), lane);
                     head2_l2<TILED>(acc, lg, bias + mt::B_HP2, wblk<NS>(W, mt::HP2), sv, mts::HP_HID, r, lane);
                     softmax_groups<KH, true>(lg, pph);
-                    store_c<2>(pph, p.prior_probs_h + iA * 16, p.prior_probs_h + iB * 16, r);
+                    store_c<2>(pph, p.prior_probs_h + iA * ldP, p.prior_probs_h + iB * ldP, r);
                 }
                 if (prior_draws) {  // the prior MTState's own draw (state.py:48)
                     float zh[2][4];
                     sample_onehot_regs<KH>(pph, upA, upB, zh, lane);
-                    if (p.prior_stoch_h != nullptr) store_c<2>(zh, p.prior_stoch_h + iA * 16, p.prior_stoch_h + iB * 16, r);
+                    if (p.prior_stoch_h != nullptr) store_c<2>(zh, p.prior_stoch_h + iA * ldS, p.prior_stoch_h + iB * ldS, r);
                     if (t + 1 < T) fetch_uniforms<KH>(p.u_prior_h, iA + 1, iB + 1, lane, upA, upB);
                 }
                 // ---- higher posterior on [d_l ; d_h] (:315-317), sample (:464) -------------------------------------------
@@ -339,15 +345,15 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                     gemm<NS, 2, 4>(acc, dhf, wblk<NS>(W, mt::HQ1H), lane);
                     head2_l2<TILED>(acc, lg, bias + mt::B_HQ2, wblk<NS>(W, mt::HQ2), sv, mts::HQ_HID, r, lane);
                     softmax_groups<KH, true>(lg, q);
-                    store_c<2>(q, p.post_probs_h + iA * 16, p.post_probs_h + iB * 16, r);
+                    store_c<2>(q, p.post_probs_h + iA * ldP, p.post_probs_h + iB * ldP, r);
                     sample_onehot<KH>(q, stage + stg::U1 + r.g * 8, stage + stg::U1 + (r.g + 8) * 8, zs, lane);
-                    store_c<2>(zs, p.feature + iA * F + 32, p.feature + iB * F + 32, r);
+                    store_c<2>(zs, p.feature + iA * ldF + 32, p.feature + iB * ldF + 32, r);
                     to_afrag<NS, 1>(zhf, zs);
                     float kl[2];
                     kl_rows<true>(q, pph, kl);
                     if (r.t == 0) {
-                        if (r.vA) p.kl_h[iA] = kl[0];
-                        if (r.vB) p.kl_h[iB] = kl[1];
+                        if (r.vA) p.kl_h[iA * ldK] = kl[0];
+                        if (r.vB) p.kl_h[iB * ldK] = kl[1];
                     }
                 }
             }
@@ -412,9 +418,9 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
 #pragma unroll
                     for (int i = 0; i < 4; ++i) xz[i * 32 + lane] = zlf.r[0][0][i];
                     pair_arrive(bar_z);  // z_l(t) is in XZ: the state warp's next cells may run
-                    store_c<2>(zs, p.feature + iA * F + 80, p.feature + iB * F + 80, r);
+                    store_c<2>(zs, p.feature + iA * ldF + 80, p.feature + iB * ldF + 80, r);
                 }
-                store_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r);
+                store_c<2>(q, p.post_probs_l + iA * ldP, p.post_probs_l + iB * ldP, r);
                 if (sv) {
                     store_rec_dst<2, TILED>(la, sv, mts::LA, r);
                     store_rec_dst<2, TILED>(lv, sv, mts::LV, r);
@@ -427,19 +433,19 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                     gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, mt::LP1), lane);
                     head2_l2<TILED>(acc, lg, bias + mt::B_LP2, wblk<NS>(W, mt::LP2), sv, mts::LP_HID, r, lane);
                     softmax_groups<KL, true>(lg, ppl);
-                    store_c<2>(ppl, p.prior_probs_l + iA * 16, p.prior_probs_l + iB * 16, r);
+                    store_c<2>(ppl, p.prior_probs_l + iA * ldP, p.prior_probs_l + iB * ldP, r);
                 }
                 if (prior_draws) {  // the prior MTState's own draw (state.py:49)
                     float zl[2][4];
                     sample_onehot_regs<KL>(ppl, upA, upB, zl, lane);
-                    if (p.prior_stoch_l != nullptr) store_c<2>(zl, p.prior_stoch_l + iA * 16, p.prior_stoch_l + iB * 16, r);
+                    if (p.prior_stoch_l != nullptr) store_c<2>(zl, p.prior_stoch_l + iA * ldS, p.prior_stoch_l + iB * ldS, r);
                     if (t + 1 < T) fetch_uniforms<KL>(p.u_prior_l, iA + 1, iB + 1, lane, upA, upB);
                 }
                 float kl[2];
                 kl_rows<true>(q, ppl, kl);
                 if (r.t == 0) {
-                    if (r.vA) p.kl_l[iA] = kl[0];
-                    if (r.vB) p.kl_l[iB] = kl[1];
+                    if (r.vA) p.kl_l[iA * ldK] = kl[0];
+                    if (r.vB) p.kl_l[iB * ldK] = kl[1];
                 }
             }
         }
@@ -458,7 +464,8 @@ static cudaError_t launch_fwd2_k(const MtrssmFwdArgs& a, cudaStream_t s) {
     while (tpc < 8 && (ntiles + tpc - 1) / tpc > sms) tpc *= 2;
     const int groups = (ntiles + tpc - 1) / tpc;
     const size_t smem = (size_t)mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float) + (size_t)tpc * f2::TILE_BYTES;
-    auto kernel = a.rec_tiled ? mtrssm_fwd2_kernel<KL, KH, true> : mtrssm_fwd2_kernel<KL, KH, false>;
+    auto kernel = !a.rec_tiled ? mtrssm_fwd2_kernel<KL, KH, 0> : a.ld_feature == 0 ? mtrssm_fwd2_kernel<KL, KH, 1> : mtrssm_fwd2_kernel<KL, KH, 2>;
+    if (!a.rec_tiled && a.ld_feature != 0) return cudaErrorInvalidValue;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)((size_t)mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float) + 8 * f2::TILE_BYTES));
     if (err != cudaSuccess) return err;

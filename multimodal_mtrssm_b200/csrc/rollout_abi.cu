@@ -602,6 +602,14 @@ static int mtrssm_fwd_common(const RssmMtrssmDims* d, const RssmMtrssmWeights* w
     a.obs_projected = imagine ? 0 : d->obs_projected;
     a.rec_tiled = d->precision == RSSM_PRECISION_BF16_FUSED && getenv("RSSM_REC_ROW_LAYOUT") == nullptr ? 1 : 0;  // tile-blocked saved record
                                                                                  // (include/rssm_rollout.h); the env var is for A/B timing
+    a.ld_feature = out->ld_feature;
+    if ((out->ld_feature | out->ld_hidden | out->ld_probs | out->ld_stoch | out->ld_kl) != 0) {  // grouped rows
+        if (imagine || !a.rec_tiled) return fail("grouped output rows (ld_* != 0) need the posterior rollout under RSSM_PRECISION_BF16_FUSED; pass 0 here");
+        if (out->ld_feature != MTRSSM_ROW_PITCH || out->ld_hidden != MTRSSM_ROW_PITCH || out->ld_probs != MTRSSM_ROW_PITCH ||
+            out->ld_stoch != MTRSSM_ROW_PITCH || out->ld_kl != 2)
+            return fail("output row pitches %d %d %d %d %d: all 0 (dense) or %d %d %d %d 2 (grouped rows)", out->ld_feature, out->ld_hidden,
+                        out->ld_probs, out->ld_stoch, out->ld_kl, MTRSSM_ROW_PITCH, MTRSSM_ROW_PITCH, MTRSSM_ROW_PITCH, MTRSSM_ROW_PITCH);
+    }
     g_launches.fetch_add(1);
     // bf16 policies, posterior rollout: two warps per tile (mtrssm_fwd2.cu); imagination and the fp32-parity policy: one warp per tile
     if (!imagine && d->precision != RSSM_PRECISION_FP32 && getenv("RSSM_FWD_ONE_WARP") == nullptr)
@@ -649,6 +657,12 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
     a.d_hidden_l0 = gin->d_hidden_l0, a.d_stoch_h0 = gin->d_stoch_h0, a.d_stoch_l0 = gin->d_stoch_l0;
     a.obs_projected = d->obs_projected;
     a.rec_tiled = fused && getenv("RSSM_REC_ROW_LAYOUT") == nullptr ? 1 : 0;
+    a.ld_feature = fo->ld_feature;
+    if ((fo->ld_feature | fo->ld_probs) != 0) {
+        if (!fused) return fail("grouped output rows (ld_* != 0) need the fused backward; pass 0 here");
+        if (fo->ld_feature != MTRSSM_ROW_PITCH || fo->ld_probs != MTRSSM_ROW_PITCH)
+            return fail("forward-output row pitches %d %d: both 0 (dense) or both %d (grouped rows)", fo->ld_feature, fo->ld_probs, MTRSSM_ROW_PITCH);
+    }
     if (d->obs_projected && !fused) return fail("obs_projected needs the fused backward (gw != NULL, RSSM_PRECISION_BF16_FUSED)");
     if (d->precision == RSSM_PRECISION_BF16_FUSED && !fused)
         return fail("RSSM_PRECISION_BF16_FUSED writes the saved record tile-blocked: its backward needs the weight-gradient pointers (gw != NULL)");

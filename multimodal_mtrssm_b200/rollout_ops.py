@@ -443,6 +443,156 @@ def _mt_backward(ctx, grads):  # noqa: ANN001
 mtrssm_rollout_op.register_autograd(_mt_backward, setup_context=_mt_setup)
 
 
+# ---- bf16 fused policy: GROUPED outputs ----------------------------------------------------------------------------------------
+# feature | hidden_h | hidden_l | the four probability tensors | the two prior draws of a (b,t) share ONE 1 KB row of a [B,T,256]
+# buffer (kl_l | kl_h one [B,T,2]): a row-step writes eight whole 128-byte lines instead of ten partial-line segments (forward
+# 0.559 -> 0.495 ms at the bench batch).  A custom op may not return tensors that alias each other, so the raw ops below return /
+# take the row buffer, and `_MtrssmGroupedFn` (an autograd.Function over them) hands out the strided views and routes each view's
+# gradient straight to the backward op -- autograd never assembles a dense gradient of the row.
+def _fill_row_outputs(out, row: Tensor, kl: Tensor, has_prior: bool) -> None:  # noqa: ANN001
+    base = row.data_ptr()
+    for name, off in _lib.MT_ROW_OFFSETS.items():
+        if name.startswith("prior_stoch") and not has_prior:
+            continue
+        setattr(out, name, base + 4 * off)
+    out.kl_l, out.kl_h = kl.data_ptr(), kl.data_ptr() + 4
+    out.ld_feature = out.ld_hidden = out.ld_probs = out.ld_stoch = _lib.MT_ROW_PITCH
+    out.ld_kl = 2
+
+
+@torch.library.custom_op("mtrssm_b200::mtrssm_rollout_grouped", mutates_args=())
+def mtrssm_rollout_grouped_op(
+    weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, state: Sequence[Tensor],
+    u_post_l: Tensor, u_post_h: Tensor, u_prior_l: Optional[Tensor], u_prior_h: Optional[Tensor],
+    KL: int, KH: int, l_tau: float, h_tau: float, precision: int, save: bool, obs_projected: bool,
+) -> List[Tensor]:
+    """-> [row [B,T,256], kl [B,T,2], saved]; no autograd of its own (see _MtrssmGroupedFn)."""
+    with _on_device(actions, weights, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, u_prior_h):
+        _mt_check(weights, embed_a, state, obs_projected)
+        B, T, _ = actions.shape
+        dev = actions.device
+        row = torch.empty(B, T, _lib.MT_ROW_PITCH, device=dev)
+        kl = torch.empty(B, T, 2, device=dev)
+        if u_prior_l is None:
+            row[..., 224:].zero_()  # the prior-draw columns are not written
+        saved = (torch.empty(_lib.mtrssm_saved_rows(B, precision), T, _lib.mtrssm_saved_elems(precision), device=dev,
+                             dtype=_lib.record_dtype(precision)) if save else torch.empty(0, device=dev))
+        w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
+        inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE, "u_post_l", "u_post_h", "u_prior_l", "u_prior_h"],
+                    (actions, embed_a, embed_v, *state, u_post_l, u_post_h, u_prior_l, u_prior_h))
+        out = _lib.MtrssmOutputs()
+        _fill_row_outputs(out, row, kl, u_prior_l is not None)
+        out.saved = ptr(saved) if save else None
+        _lib.call("rssm_mtrssm_rollout_fwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision, obs_projected), w, inp, out)
+        return [row, kl, saved]
+
+
+@mtrssm_rollout_grouped_op.register_fake
+def _(weights, actions, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, u_prior_h, KL, KH, l_tau, h_tau, precision, save,  # noqa: ANN001
+      obs_projected):
+    B, T, _ = actions.shape
+    e = actions.new_empty
+    return [e(B, T, _lib.MT_ROW_PITCH), e(B, T, 2),
+            e(_lib.mtrssm_saved_rows(B, precision), T, _lib.mtrssm_saved_elems(precision), dtype=_lib.record_dtype(precision)) if save else e(0)]
+
+
+@torch.library.custom_op("mtrssm_b200::mtrssm_rollout_grouped_bwd", mutates_args=())
+def mtrssm_rollout_grouped_bwd_op(
+    weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, state: Sequence[Tensor], row: Tensor, saved: Tensor,
+    d_feature: Optional[Tensor], d_prior_h: Optional[Tensor], d_prior_l: Optional[Tensor], d_post_h: Optional[Tensor],
+    d_post_l: Optional[Tensor], d_pz_h: Optional[Tensor], d_pz_l: Optional[Tensor], d_kl_l: Optional[Tensor], d_kl_h: Optional[Tensor],
+    KL: int, KH: int, l_tau: float, h_tau: float, precision: int, kl_wq: float, kl_wp: float, obs_projected: bool,
+) -> List[Tensor]:
+    """Fused backward over the grouped row.  -> [flat weight grads, d_actions, d_embed_a, d_embed_v, *d_state]."""
+    with _on_device(actions, weights, embed_a, embed_v, state, row, saved, d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h,
+                    d_pz_l, d_kl_l, d_kl_h):
+        B, T, A = actions.shape
+        dev = actions.device
+        if d_feature is None:
+            d_feature = torch.zeros(B, T, 96, device=dev)
+        sizes = [t.numel() for t in weights]
+        flat = torch.zeros(sum(sizes), device=dev)
+        gws = [g.view_as(t) for g, t in zip(flat.split(sizes), weights)]
+        e = lambda *s: torch.empty(*s, device=dev)  # noqa: E731
+        EW = 32 if obs_projected else 64
+        d_actions, d_ea, d_ev = e(B, T, A), e(B, T, EW), e(B, T, EW)
+        d_state = [e(B, 32), e(B, 32), e(B, 32), e(B, 32), e(B, 16), e(B, 16)]
+        w = _fill(_lib.MtrssmWeights(), _lib.MT_WEIGHT_FIELDS, weights)
+        gw = _fill(_lib.MtrssmWeightGrads(), _lib.MT_WEIGHT_FIELDS, gws)
+        inp = _fill(_lib.MtrssmInputs(), ["actions", "embed_a", "embed_v", *_MT_STATE], (actions, embed_a, embed_v, *state))
+        out = _lib.MtrssmOutputs()
+        _fill_row_outputs(out, row, row, True)  # the backward reads feature and the probabilities only
+        out.kl_l = out.kl_h = None
+        out.saved = ptr(saved)
+        up = _fill(
+            _lib.MtrssmUpstream(),
+            "d_feature d_prior_probs_h d_prior_probs_l d_post_probs_h d_post_probs_l d_prior_stoch_h d_prior_stoch_l d_kl_l d_kl_h".split(),
+            tuple(_c(t) for t in (d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h)),
+        )
+        up.kl_wq, up.kl_wp = kl_wq, kl_wp
+        gin = _fill(_lib.MtrssmInputGrads(), ["d_actions", "d_embed_a", "d_embed_v", *("d_" + n for n in _MT_STATE)],
+                    (d_actions, d_ea, d_ev, *d_state))
+        _lib.call("rssm_mtrssm_rollout_bwd", _mt_dims(actions, KL, KH, l_tau, h_tau, precision, obs_projected), w, inp, out, up, gin, gw)
+        return [flat, d_actions, d_ea, d_ev, *d_state]
+
+
+@mtrssm_rollout_grouped_bwd_op.register_fake
+def _(weights, actions, embed_a, embed_v, state, row, saved, d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l,  # noqa: ANN001
+      d_kl_l, d_kl_h, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, obs_projected):
+    return [actions.new_empty(sum(t.numel() for t in weights)), torch.empty_like(actions), torch.empty_like(embed_a),
+            torch.empty_like(embed_v), *[torch.empty_like(t) for t in state]]
+
+
+class _MtrssmGroupedFn(torch.autograd.Function):
+    """Autograd of the grouped rollout.  forward(cfg, *tensors): tensors = 28 weights, actions, embed_a, embed_v, 6 state tensors,
+    u_post_l, u_post_h, u_prior_l, u_prior_h (the last two may be None) -> the 11 outputs of `mtrssm_rollout` as strided views."""
+
+    NW = len(_lib.MT_WEIGHT_FIELDS)
+
+    @staticmethod
+    def forward(ctx, cfg, *t):  # noqa: ANN001
+        nw = _MtrssmGroupedFn.NW
+        weights, (actions, embed_a, embed_v), state = list(t[:nw]), t[nw:nw + 3], list(t[nw + 3:nw + 9])
+        u_post_l, u_post_h, u_prior_l, u_prior_h = t[nw + 9:nw + 13]
+        KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, save, obs_projected = cfg
+        row, kl, saved = mtrssm_rollout_grouped_op(weights, actions, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, u_prior_h,
+                                                   KL, KH, l_tau, h_tau, precision, save, obs_projected)
+        o = _lib.MT_ROW_OFFSETS
+        B, T, _ = actions.shape
+        v = lambda name, w: row[..., o[name]:o[name] + w]  # noqa: E731
+        has_prior = u_prior_l is not None
+        outs = (
+            v("feature", 96), v("hidden_h", 32), v("hidden_l", 32),
+            v("prior_probs_h", 16).unflatten(-1, (16 // KH, KH)), v("prior_probs_l", 16).unflatten(-1, (16 // KL, KL)),
+            v("post_probs_h", 16).unflatten(-1, (16 // KH, KH)), v("post_probs_l", 16).unflatten(-1, (16 // KL, KL)),
+            v("prior_stoch_h", 16) if has_prior else None, v("prior_stoch_l", 16) if has_prior else None,
+            kl[..., 0], kl[..., 1],
+        )
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(outs[1], outs[2])  # hidden_h / hidden_l: gradients into them are not propagated (DESIGN.md §7)
+        if save:
+            ctx.cfg, ctx.has_prior = cfg, has_prior
+            ctx.save_for_backward(*weights, actions, embed_a, embed_v, *state, row, saved)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *g):  # noqa: ANN001
+        d_feature, _dhh, _dhl, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h = g
+        nw = _MtrssmGroupedFn.NW
+        t = ctx.saved_tensors
+        weights, (actions, embed_a, embed_v), state = list(t[:nw]), t[nw:nw + 3], list(t[nw + 3:nw + 9])
+        row, saved = t[nw + 9:]
+        KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, _save, obs_projected = ctx.cfg
+        hp = ctx.has_prior
+        res = mtrssm_rollout_grouped_bwd_op(
+            weights, actions, embed_a, embed_v, state, row, saved, d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l,
+            d_pz_h if hp else None, d_pz_l if hp else None, d_kl_l, d_kl_h, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, obs_projected,
+        )
+        flat, d_actions, d_ea, d_ev = res[:4]
+        gws = [x.view_as(w) for x, w in zip(flat.split([w.numel() for w in weights]), weights)]
+        return (None, *gws, d_actions, d_ea, d_ev, *res[4:], None, None, None, None)
+
+
 def mtrssm_rollout(
     weights: Sequence[Tensor], *, actions: Tensor, embed_a: Tensor, embed_v: Tensor, deter_h0: Tensor, deter_l0: Tensor,
     hidden_h0: Tensor, hidden_l0: Tensor, stoch_h0: Tensor, stoch_l0: Tensor, u_post_l: Tensor, u_post_h: Tensor,
@@ -463,13 +613,18 @@ def mtrssm_rollout(
     state = [deter_h0, deter_l0, hidden_h0, hidden_l0, stoch_h0, stoch_l0]
     save = torch.is_grad_enabled() and any(t.requires_grad for t in (*weights, actions, embed_a, embed_v, *state))
     wq, wp = kl_path_weights(use_kl_balancing)
+    names = ("feature hidden_h hidden_l prior_probs_h prior_probs_l post_probs_h post_probs_l prior_stoch_h prior_stoch_l "
+             "kl_l kl_h").split()
+    if precision == _lib.PRECISION_BF16_FUSED:  # grouped outputs (one 1 KB row per (b,t)), tile-blocked record, fused backward
+        cfg = (class_size_l, class_size_h, float(l_tau), float(h_tau), precision, wq, wp, save, bool(obs_projected))
+        outs = _MtrssmGroupedFn.apply(cfg, *[_c(w) for w in weights], _c(actions), _c(embed_a), _c(embed_v), *[_c(s) for s in state],
+                                      _c(u_post_l), _c(u_post_h), _c(u_prior_l), _c(u_prior_h))
+        return dict(zip(names, outs))
     out = mtrssm_rollout_op(
         [_c(w) for w in weights], _c(actions), _c(embed_a), _c(embed_v), [_c(s) for s in state], _c(u_post_l), _c(u_post_h),
         _c(u_prior_l), _c(u_prior_h),
         class_size_l, class_size_h, float(l_tau), float(h_tau), precision, wq, wp, save, obs_projected,
     )
-    names = ("feature hidden_h hidden_l prior_probs_h prior_probs_l post_probs_h post_probs_l prior_stoch_h prior_stoch_l "
-             "kl_l kl_h").split()
     res = dict(zip(names, out[:-1]))
     if u_prior_l is None:
         res["prior_stoch_h"] = res["prior_stoch_l"] = None

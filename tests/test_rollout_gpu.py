@@ -498,6 +498,50 @@ def test_mtrssm_bf16_fused_backward_matches_two_kernel_backward(ops, B, T, dims)
     rep.finish()
 
 
+@pytest.mark.parametrize("B,T,prior", [(45, 7, True), (16, 3, False)])
+def test_mtrssm_grouped_output_rows_match_dense_outputs(ops, B, T, prior):
+    """The bf16 fused policy through `mtrssm_rollout` writes the outputs of a (b,t) into one 1 KB row (RssmMtrssmOutputs.ld_* = 256,
+    strided views handed out); the same policy through the raw op keeps one dense tensor per output (ld_* = 0).  Same kernels, only
+    the row pitches differ: forward bit-identical; gradients equal up to the atomic summation order of the weight gradients."""
+    R, P = ops
+    dims = H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    inp = H.mtrssm_inputs(B, T, dims)
+    if not prior:
+        inp = {k: v for k, v in inp.items() if not k.startswith("u_prior")}
+    up = mtrssm_upstream(B, T, dims)
+    if not prior:
+        up = {k: v for k, v in up.items() if not k.startswith("prior_stoch")}
+    og, wg, xg = run_mtrssm(R, P, params, inp, dims, precision=2, grad=True, upstream=up)
+    assert og["feature"].stride(-2) == 256 and og["post_probs_l"].data_ptr() == og["feature"].data_ptr() + 4 * 208
+    assert (og["prior_stoch_h"] is None) == (not prior)
+    # dense: the autograd-registered custom op with natural pitches
+    w = {k: v.cuda().requires_grad_(True) for k, v in params.items()}
+    x = cuda(inp)
+    for k in MT_GRAD_IN:
+        x[k] = x[k].requires_grad_(True)
+    st = [x[k] for k in ("deter_h0", "deter_l0", "hidden_h0", "hidden_l0", "stoch_h0", "stoch_l0")]
+    res = R.mtrssm_rollout_op(P.mtrssm_weight_list(w), x["actions"], x["embed_a"], x["embed_v"], st, x["u_post_l"], x["u_post_h"],
+                              x.get("u_prior_l"), x.get("u_prior_h"), dims["KL"], dims["KH"], dims["l_tau"], dims["h_tau"], 2, 0.2, 0.8,
+                              True, False)
+    names = ("feature", "hidden_h", "hidden_l", "prior_probs_h", "prior_probs_l", "post_probs_h", "post_probs_l", "prior_stoch_h",
+             "prior_stoch_l", "kl_l", "kl_h")
+    od = dict(zip(names, res[:-1]))
+    assert od["feature"].is_contiguous()
+    sum((od[k] * up[k].cuda()).sum() for k in up).backward()
+    torch.cuda.synchronize()
+    for k in names:
+        if og[k] is not None:
+            assert torch.equal(og[k], od[k]), k
+    rep = H.Report(f"mtrssm grouped rows vs dense outputs B={B} T={T} prior={prior}")
+    for k in MT_GRAD_IN:
+        assert torch.equal(xg[k].grad, x[k].grad), k
+    for k in w:
+        scale = float(w[k].grad.abs().max())
+        rep.check("d " + k, wg[k].grad, w[k].grad, rtol=0, atol=1e-5 * max(scale, 1e-3))
+    rep.finish()
+
+
 def test_mtrssm_fwd2_matches_one_warp_kernel(ops, monkeypatch):
     """The two-warps-per-tile forward (mtrssm_fwd2.cu, the bf16 default) against the one-warp kernel (RSSM_FWD_ONE_WARP=1): same
     arithmetic and operand roundings, one fp32 summation order differs, so single steps agree to fp32 rounding of the bf16-operand
