@@ -394,7 +394,9 @@ def time_train_step(B: int, T: int, world: int, device: torch.device, autocast: 
     standins.materialize(model, model.feature_dim)
     model.to(device).train()
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3, capturable=graphed)
-    bucket = dp.FlatGradBucket(model.parameters())
+    # eager step: readiness-ordered buckets (the decoders' and the rollout's allreduce run under the encoders' backward);
+    # graph step: one flat bucket inside the replay
+    bucket = dp.FlatGradBucket(model.parameters()) if graphed or world == 1 else dp.OverlappedGradBuckets(model.parameters())
     g = torch.Generator().manual_seed(1234)
     frames = lambda: (torch.rand(B, T, 1, 32, 32, generator=g) * 2 - 1).to(device)  # noqa: E731
     act = synthetic.actions(B, T, g).to(device)

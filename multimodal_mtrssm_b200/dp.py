@@ -78,6 +78,121 @@ class FlatGradBucket:
         return n
 
 
+class OverlappedGradBuckets:
+    """Readiness-ordered gradient buckets: the allreduce of a bucket starts (asynchronously, on the collective's own stream) the
+    moment the LAST gradient of that bucket has been accumulated, so it runs under the rest of the backward pass.  In the
+    training step of the default models the gradients become ready as: decoders -> all rollout weights at once (one fused
+    backward kernel) -> encoders; with the decoders' and the rollout's buckets already in flight only the encoders' bucket is
+    exposed after `loss.backward()` returns.  (`FlatGradBucket` -- one allreduce after the backward -- stays for the CUDA-graph
+    step, where the whole step is one replay.)
+
+    The FIRST step runs synchronously and records, from per-parameter `post_accumulate_grad` hooks, WHICH parameters receive a
+    gradient and in WHAT ORDER; parameters that never do (MoPoE-MMTRSSM's dummy `transition.*` / `l_posterior.*`) are left out,
+    and the others are cut into buckets of about `bucket_bytes` along that order.  Every rank runs the same model code, so the
+    order -- hence the bucket layout and the order of the collectives -- is the same on every rank; it is checked once by
+    allreducing a checksum of the layout.  Use:
+
+        buckets = OverlappedGradBuckets(model.parameters())
+        ... loss.backward(); buckets.finish()        # every step; gradients are averaged in place when finish() returns
+    """
+
+    def __init__(self, params: Iterable[nn.Parameter], group: dist.ProcessGroup | None = None, bucket_bytes: int = 1 << 20) -> None:
+        self.params = [p for p in params if p.requires_grad]
+        self.group, self.bucket_bytes = group, bucket_bytes
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._order: list[int] = []          # first step: parameter indices in the order their gradients became ready
+        self._bucket_of: dict[int, int] = {}  # parameter index -> bucket
+        self._buckets: list[list[int]] = []
+        self._flat: list[Tensor] = []
+        self._pending: list[int] = []
+        self._works: list[object | None] = []
+        self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+
+    @property
+    def _active(self) -> bool:
+        return dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _on_grad(self, p: nn.Parameter) -> None:
+        i = self._index[id(p)]
+        if not self._buckets:  # recording step
+            self._order.append(i)
+            return
+        b = self._bucket_of.get(i)
+        if b is None:
+            msg = "a parameter that had no gradient in the first step received one now: rebuild OverlappedGradBuckets"
+            raise RuntimeError(msg)
+        self._pending[b] -= 1
+        if self._pending[b] == 0 and self._active:
+            self._launch(b)
+
+    def _launch(self, b: int) -> None:
+        grads = [self.params[i].grad for i in self._buckets[b]]
+        torch.cat([g.reshape(-1).float() for g in grads], out=self._flat[b])
+        self._works[b] = dist.all_reduce(self._flat[b], group=self.group, async_op=True)
+
+    def _build(self) -> None:
+        order = list(dict.fromkeys(self._order))  # a shared parameter fires once per accumulation: keep the first
+        cur, size = [], 0
+        for i in order:
+            cur.append(i)
+            size += self.params[i].numel() * 4
+            if size >= self.bucket_bytes:
+                self._buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self._buckets.append(cur)
+        for b, idx in enumerate(self._buckets):
+            for i in idx:
+                self._bucket_of[i] = b
+        dev = self.params[order[0]].grad.device if order else torch.device("cpu")
+        self._flat = [torch.empty(sum(self.params[i].numel() for i in idx), dtype=torch.float32, device=dev) for idx in self._buckets]
+        self._works = [None] * len(self._buckets)
+        if self._active:  # same layout on every rank?
+            sig = torch.tensor([float(sum((k + 1) * (i + 1) for k, i in enumerate(order)) % 1000003), float(len(self._buckets))], device=dev)
+            lo, hi = sig.clone(), sig.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+            if not torch.equal(lo, hi):
+                msg = "ranks disagree on the gradient-readiness order; use FlatGradBucket"
+                raise RuntimeError(msg)
+
+    def finish(self) -> int:
+        """Call after `backward()`: waits for the buckets in flight, averages, writes the gradients back.  Returns the number of
+        elements reduced."""
+        first = not self._buckets
+        if first:
+            self._build()
+        if not self._active:
+            self._pending = [len(idx) for idx in self._buckets]
+            return 0
+        world = dist.get_world_size(self.group)
+        n = 0
+        for b, idx in enumerate(self._buckets):
+            if self._works[b] is None:  # recording step, or (defensively) a bucket whose last hook did not fire
+                if not first and self._pending[b] != 0:
+                    msg = f"bucket {b}: {self._pending[b]} gradients missing after backward"
+                    raise RuntimeError(msg)
+                self._launch(b)
+            self._works[b].wait()
+            self._works[b] = None
+            flat = self._flat[b].div_(world)
+            off = 0
+            for i in idx:
+                g = self.params[i].grad
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+            n += off
+        self._pending = [len(idx) for idx in self._buckets]
+        return n
+
+    allreduce = finish  # drop-in for FlatGradBucket in `train_step`
+
+    def remove_hooks(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
 def broadcast_parameters(module: nn.Module, src: int = 0, group: dist.ProcessGroup | None = None) -> None:
     """Make every rank start from rank `src`'s parameters and buffers."""
     if not dist.is_initialized():
@@ -86,10 +201,11 @@ def broadcast_parameters(module: nn.Module, src: int = 0, group: dist.ProcessGro
         dist.broadcast(t.data, src=src, group=group)
 
 
-def train_step(model: nn.Module, batch: Sequence[Tensor], optimizer: torch.optim.Optimizer, bucket: FlatGradBucket,
+def train_step(model: nn.Module, batch: Sequence[Tensor], optimizer: torch.optim.Optimizer, bucket: "FlatGradBucket | OverlappedGradBuckets",
                clip: float | None = 10.0) -> dict[str, Tensor]:
-    """One data-parallel step on this rank's shard: forward/backward, flat-bucket allreduce, clip, optimiser step.
-    (`gradient_clip_val: 10`, AdamW: mopoe_*/configs/default.yaml:103-122.)"""
+    """One data-parallel step on this rank's shard: forward/backward, gradient allreduce, clip, optimiser step.
+    (`gradient_clip_val: 10`, AdamW: mopoe_*/configs/default.yaml:103-122.)  With `OverlappedGradBuckets` the allreduce of the
+    decoders' and the rollout's gradients runs under the encoders' backward; `FlatGradBucket` reduces once after it."""
     optimizer.zero_grad(set_to_none=True)
     out = model.training_step(tuple(batch), 0)
     out["loss"].backward()

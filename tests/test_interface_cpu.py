@@ -316,6 +316,33 @@ assert all(p.grad is None for p in dead.parameters()) and n == sum(p.numel() for
 m = reduce_metrics({"loss": loss, "k": torch.tensor(float(rank))})
 torch.testing.assert_close(m["k"], torch.tensor(0.5))
 torch.testing.assert_close(m["loss"], (ref(x) - y).square().mean().detach(), rtol=1e-5, atol=1e-6)
+# readiness-ordered overlapped buckets: three steps (recording step + two hook-driven ones), tiny buckets -> several collectives
+from multimodal_mtrssm_b200.dp import OverlappedGradBuckets, train_step
+class Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.enc, self.mid, self.dec, self.dead = torch.nn.Linear(6, 8), torch.nn.Linear(8, 8), torch.nn.Linear(8, 1), torch.nn.Linear(3, 3)
+    def training_step(self, batch, _):
+        x, y = batch
+        return {"loss": (self.dec(torch.tanh(self.mid(torch.tanh(self.enc(x))))) - y).square().mean()}
+torch.manual_seed(7 + rank)
+toy, full = Toy(), Toy()
+broadcast_parameters(toy)
+full.load_state_dict(toy.state_dict())
+ob = OverlappedGradBuckets(toy.parameters(), bucket_bytes=64)
+opt_t, opt_f = torch.optim.SGD(toy.parameters(), lr=0.1), torch.optim.SGD(full.parameters(), lr=0.1)
+for step in range(3):
+    train_step(toy, (xs, ys), opt_t, ob, clip=None)
+    opt_f.zero_grad()
+    full.training_step((x, y), 0)["loss"].backward()
+    for (name, a), b in zip(toy.named_parameters(), full.parameters()):
+        if name.startswith("dead"):
+            assert a.grad is None
+        else:
+            torch.testing.assert_close(a.grad, b.grad, rtol=1e-5, atol=1e-6)
+    opt_f.step()
+assert len(ob._buckets) >= 3 and [toy.dec.weight is ob.params[i] for i in ob._buckets[0]].count(True) == 1   # decoder first
+assert sum(len(b) for b in ob._buckets) == 6
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
