@@ -230,6 +230,8 @@ typedef struct {
     const float *d_prior_stoch_h, *d_prior_stoch_l;
     const float *d_kl_l, *d_kl_h;
     float kl_wq, kl_wp;
+    const float *d_hidden_h, *d_hidden_l;            /* [B,T,HD] [B,T,LD], dense; optional: gradients into the MTRNN.hidden outputs
+                                                        (the reference's autograd carries them, mmtrssm/mopoe_mmtrssm/core.py:472-473) */
 } RssmMtrssmUpstream;
 
 typedef struct {

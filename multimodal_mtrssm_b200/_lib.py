@@ -88,7 +88,8 @@ MtrssmUpstream = _struct(
         "d_feature d_prior_probs_h d_prior_probs_l d_post_probs_h d_post_probs_l d_prior_stoch_h d_prior_stoch_l "
         "d_kl_l d_kl_h"
     )
-    + [("kl_wq", C.c_float), ("kl_wp", C.c_float)],
+    + [("kl_wq", C.c_float), ("kl_wp", C.c_float)]
+    + _ptrs("d_hidden_h d_hidden_l"),
 )
 MtrssmInputGrads = _struct(
     "RssmMtrssmInputGrads",

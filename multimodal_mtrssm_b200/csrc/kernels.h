@@ -171,6 +171,7 @@ struct MtrssmBwdArgs {
     int saved_ld;  // elements per (b,t) row of `saved`
     const float *d_feature, *d_prior_probs_h, *d_prior_probs_l, *d_post_probs_h, *d_post_probs_l;
     const float *d_prior_stoch_h, *d_prior_stoch_l, *d_kl_l, *d_kl_h;
+    const float *d_hidden_h, *d_hidden_l;  // upstream gradients of the MTRNN.hidden outputs, dense [B,T,32]; may be null
     void* dpre;
     float *d_actions, *d_embed_a, *d_embed_v;
     float *d_deter_h0, *d_deter_l0, *d_hidden_h0, *d_hidden_l0, *d_stoch_h0, *d_stoch_l0;

@@ -724,6 +724,11 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 float dzh_n[2][4], ddh_n[4][4];
                 AFrag<NS, 2> fh;
                 zero_c<4>(ddh_n), zero_c<2>(dzh_n);
+                if (p.d_hidden_h != nullptr) {  // upstream gradients of the hidden outputs (u_t of the two cells) join the carried d u
+                    const size_t hA = ((size_t)r.rA * T + t) * 32, hB = ((size_t)r.rB * T + t) * 32;
+                    add_global<4>(duh, p.d_hidden_h, hA, hB, r.t);
+                    add_global<4>(dul, p.d_hidden_l, hA, hB, r.t);
+                }
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt)
 #pragma unroll

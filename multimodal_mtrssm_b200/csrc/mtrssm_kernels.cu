@@ -546,6 +546,9 @@ __global__ void __launch_bounds__(NS == 1 ? 256 : 128, 1) mtrssm_bwd_kernel(cons
                 load_c<4>(dh, p.feature + iA * F, p.feature + iB * F, r.t);
                 load_c<4>(dl, p.feature + iA * F + 48, p.feature + iB * F + 48, r.t);
             }
+            // upstream gradients of the hidden outputs (u_t of the two cells) join the carried d u
+            add_global<4>(duh, p.d_hidden_h, iA * 32, iB * 32, r.t);
+            add_global<4>(dul, p.d_hidden_l, iA * 32, iB * 32, r.t);
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll

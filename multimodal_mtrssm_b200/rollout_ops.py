@@ -357,20 +357,31 @@ def _(weights, actions, embed_a, embed_v, state, u_post_l, u_post_h, u_prior_l, 
             e(_lib.mtrssm_saved_rows(B, precision), T, _lib.mtrssm_saved_elems(precision), dtype=_lib.record_dtype(precision)) if save else e(0)]
 
 
+def _hidden_pair(d_hh: Optional[Tensor], d_hl: Optional[Tensor], B: int, T: int, dev: torch.device):  # noqa: ANN202
+    """Upstream gradients of the hidden_h / hidden_l outputs: the kernels take both or neither."""
+    if d_hh is None and d_hl is None:
+        return None, None
+    z = lambda t: torch.zeros(B, T, 32, device=dev) if t is None else t  # noqa: E731
+    return z(d_hh), z(d_hl)
+
+
 @torch.library.custom_op("mtrssm_b200::mtrssm_rollout_bwd", mutates_args=())
 def mtrssm_rollout_bwd_op(
     weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, state: Sequence[Tensor],
     feature: Tensor, prior_h: Tensor, prior_l: Tensor, post_h: Tensor, post_l: Tensor, saved: Tensor,
     d_feature: Optional[Tensor], d_prior_h: Optional[Tensor], d_prior_l: Optional[Tensor], d_post_h: Optional[Tensor],
     d_post_l: Optional[Tensor], d_pz_h: Optional[Tensor], d_pz_l: Optional[Tensor], d_kl_l: Optional[Tensor],
-    d_kl_h: Optional[Tensor], KL: int, KH: int, l_tau: float, h_tau: float, precision: int, kl_wq: float, kl_wp: float,
+    d_kl_h: Optional[Tensor], d_hidden_h: Optional[Tensor], d_hidden_l: Optional[Tensor],
+    KL: int, KH: int, l_tau: float, h_tau: float, precision: int, kl_wq: float, kl_wp: float,
     obs_projected: bool,  # no default: the dispatcher strips trailing default-valued arguments, which changes the backward's arity
 ) -> List[Tensor]:
-    with _on_device(actions, weights, embed_a, embed_v, state, feature, prior_h, prior_l, post_h, post_l, saved, d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h):
+    with _on_device(actions, weights, embed_a, embed_v, state, feature, prior_h, prior_l, post_h, post_l, saved, d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h,
+                    d_hidden_h, d_hidden_l):
         B, T, A = actions.shape
         dev = actions.device
         if d_feature is None:
             d_feature = torch.zeros_like(feature)
+        d_hidden_h, d_hidden_l = _hidden_pair(d_hidden_h, d_hidden_l, B, T, dev)
         sizes = [t.numel() for t in weights]
         flat = torch.zeros(sum(sizes), device=dev)
         gws = [g.view_as(t) for g, t in zip(flat.split(sizes), weights)]
@@ -386,8 +397,10 @@ def mtrssm_rollout_bwd_op(
                     (feature, prior_h, prior_l, post_h, post_l, saved))
         up = _fill(
             _lib.MtrssmUpstream(),
-            "d_feature d_prior_probs_h d_prior_probs_l d_post_probs_h d_post_probs_l d_prior_stoch_h d_prior_stoch_l d_kl_l d_kl_h".split(),
-            tuple(_c(t) for t in (d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h)),
+            ("d_feature d_prior_probs_h d_prior_probs_l d_post_probs_h d_post_probs_l d_prior_stoch_h d_prior_stoch_l d_kl_l d_kl_h "
+             "d_hidden_h d_hidden_l").split(),
+            tuple(_c(t) for t in (d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h, d_hidden_h,
+                                  d_hidden_l)),
         )
         up.kl_wq, up.kl_wp = kl_wq, kl_wp
         gin = _fill(_lib.MtrssmInputGrads(),
@@ -399,7 +412,8 @@ def mtrssm_rollout_bwd_op(
 
 @mtrssm_rollout_bwd_op.register_fake
 def _(weights, actions, embed_a, embed_v, state, feature, prior_h, prior_l, post_h, post_l, saved, d_feature, d_prior_h,  # noqa: ANN001
-      d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, obs_projected):
+      d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h, d_hidden_h, d_hidden_l, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp,
+      obs_projected):
     return [actions.new_empty(sum(t.numel() for t in weights)), torch.empty_like(actions), torch.empty_like(embed_a),
             torch.empty_like(embed_v), *[torch.empty_like(t) for t in state]]
 
@@ -418,10 +432,7 @@ def _mt_setup(ctx, inputs, output) -> None:  # noqa: ANN001
 
 
 def _mt_backward(ctx, grads):  # noqa: ANN001
-    # gradients w.r.t. the hidden_h / hidden_l OUTPUTS are not propagated ("limits")
-    d_feature, _dhh, _dhl, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h, _ = grads
-    if _dhh is not None or _dhl is not None:
-        raise RuntimeError("gradients flowing into the hidden_h / hidden_l outputs of the fused MMTRSSM rollout are not supported")
+    d_feature, d_hh, d_hl, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h, _ = grads
     t = ctx.saved_tensors
     weights = list(t[: ctx.nw])
     actions, embed_a, embed_v = t[ctx.nw: ctx.nw + 3]
@@ -431,7 +442,7 @@ def _mt_backward(ctx, grads):  # noqa: ANN001
     hp = ctx.has_prior_stoch
     res = mtrssm_rollout_bwd_op(
         weights, actions, embed_a, embed_v, state, feature, prior_h, prior_l, post_h, post_l, saved, d_feature, d_prior_h,
-        d_prior_l, d_post_h, d_post_l, d_pz_h if hp else None, d_pz_l if hp else None, d_kl_l, d_kl_h, KL, KH, l_tau, h_tau,
+        d_prior_l, d_post_h, d_post_l, d_pz_h if hp else None, d_pz_l if hp else None, d_kl_l, d_kl_h, d_hh, d_hl, KL, KH, l_tau, h_tau,
         precision, kl_wq, kl_wp, obs_projected,
     )
     flat, d_actions, d_ea, d_ev = res[:4]
@@ -501,15 +512,17 @@ def mtrssm_rollout_grouped_bwd_op(
     weights: Sequence[Tensor], actions: Tensor, embed_a: Tensor, embed_v: Tensor, state: Sequence[Tensor], row: Tensor, saved: Tensor,
     d_feature: Optional[Tensor], d_prior_h: Optional[Tensor], d_prior_l: Optional[Tensor], d_post_h: Optional[Tensor],
     d_post_l: Optional[Tensor], d_pz_h: Optional[Tensor], d_pz_l: Optional[Tensor], d_kl_l: Optional[Tensor], d_kl_h: Optional[Tensor],
+    d_hidden_h: Optional[Tensor], d_hidden_l: Optional[Tensor],
     KL: int, KH: int, l_tau: float, h_tau: float, precision: int, kl_wq: float, kl_wp: float, obs_projected: bool,
 ) -> List[Tensor]:
     """Fused backward over the grouped row.  -> [flat weight grads, d_actions, d_embed_a, d_embed_v, *d_state]."""
     with _on_device(actions, weights, embed_a, embed_v, state, row, saved, d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h,
-                    d_pz_l, d_kl_l, d_kl_h):
+                    d_pz_l, d_kl_l, d_kl_h, d_hidden_h, d_hidden_l):
         B, T, A = actions.shape
         dev = actions.device
         if d_feature is None:
             d_feature = torch.zeros(B, T, 96, device=dev)
+        d_hidden_h, d_hidden_l = _hidden_pair(d_hidden_h, d_hidden_l, B, T, dev)
         sizes = [t.numel() for t in weights]
         flat = torch.zeros(sum(sizes), device=dev)
         gws = [g.view_as(t) for g, t in zip(flat.split(sizes), weights)]
@@ -526,8 +539,10 @@ def mtrssm_rollout_grouped_bwd_op(
         out.saved = ptr(saved)
         up = _fill(
             _lib.MtrssmUpstream(),
-            "d_feature d_prior_probs_h d_prior_probs_l d_post_probs_h d_post_probs_l d_prior_stoch_h d_prior_stoch_l d_kl_l d_kl_h".split(),
-            tuple(_c(t) for t in (d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h)),
+            ("d_feature d_prior_probs_h d_prior_probs_l d_post_probs_h d_post_probs_l d_prior_stoch_h d_prior_stoch_l d_kl_l d_kl_h "
+             "d_hidden_h d_hidden_l").split(),
+            tuple(_c(t) for t in (d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h, d_hidden_h,
+                                  d_hidden_l)),
         )
         up.kl_wq, up.kl_wp = kl_wq, kl_wp
         gin = _fill(_lib.MtrssmInputGrads(), ["d_actions", "d_embed_a", "d_embed_v", *("d_" + n for n in _MT_STATE)],
@@ -538,7 +553,7 @@ def mtrssm_rollout_grouped_bwd_op(
 
 @mtrssm_rollout_grouped_bwd_op.register_fake
 def _(weights, actions, embed_a, embed_v, state, row, saved, d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l,  # noqa: ANN001
-      d_kl_l, d_kl_h, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, obs_projected):
+      d_kl_l, d_kl_h, d_hidden_h, d_hidden_l, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, obs_projected):
     return [actions.new_empty(sum(t.numel() for t in weights)), torch.empty_like(actions), torch.empty_like(embed_a),
             torch.empty_like(embed_v), *[torch.empty_like(t) for t in state]]
 
@@ -569,7 +584,6 @@ class _MtrssmGroupedFn(torch.autograd.Function):
             kl[..., 0], kl[..., 1],
         )
         ctx.set_materialize_grads(False)
-        ctx.mark_non_differentiable(outs[1], outs[2])  # hidden_h / hidden_l: gradients into them are not propagated
         if save:
             ctx.cfg, ctx.has_prior = cfg, has_prior
             ctx.save_for_backward(*weights, actions, embed_a, embed_v, *state, row, saved)
@@ -577,7 +591,7 @@ class _MtrssmGroupedFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *g):  # noqa: ANN001
-        d_feature, _dhh, _dhl, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h = g
+        d_feature, d_hh, d_hl, d_prior_h, d_prior_l, d_post_h, d_post_l, d_pz_h, d_pz_l, d_kl_l, d_kl_h = g
         nw = _MtrssmGroupedFn.NW
         t = ctx.saved_tensors
         weights, (actions, embed_a, embed_v), state = list(t[:nw]), t[nw:nw + 3], list(t[nw + 3:nw + 9])
@@ -586,7 +600,8 @@ class _MtrssmGroupedFn(torch.autograd.Function):
         hp = ctx.has_prior
         res = mtrssm_rollout_grouped_bwd_op(
             weights, actions, embed_a, embed_v, state, row, saved, d_feature, d_prior_h, d_prior_l, d_post_h, d_post_l,
-            d_pz_h if hp else None, d_pz_l if hp else None, d_kl_l, d_kl_h, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp, obs_projected,
+            d_pz_h if hp else None, d_pz_l if hp else None, d_kl_l, d_kl_h, d_hh, d_hl, KL, KH, l_tau, h_tau, precision, kl_wq, kl_wp,
+            obs_projected,
         )
         flat, d_actions, d_ea, d_ev = res[:4]
         gws = [x.view_as(w) for x, w in zip(flat.split([w.numel() for w in weights]), weights)]

@@ -347,6 +347,8 @@ def mtrssm_upstream(B, T, dims, seed=7):
         "post_probs_l": r(B, T, dims["CL"], dims["KL"]), "post_probs_h": r(B, T, dims["CH"], dims["KH"]),
         "prior_probs_l": r(B, T, dims["CL"], dims["KL"]), "prior_probs_h": r(B, T, dims["CH"], dims["KH"]),
         "prior_stoch_l": r(B, T, 16), "prior_stoch_h": r(B, T, 16),
+        # gradients into the MTRNN.hidden outputs (the reference's autograd carries them, mmtrssm/mopoe_mmtrssm/core.py:472-473)
+        "hidden_h": r(B, T, 32), "hidden_l": r(B, T, 32),
     }
 
 
@@ -476,8 +478,8 @@ def test_mtrssm_bf16_teacher_forced(ops):
 def test_mtrssm_bf16_fused_backward_matches_two_kernel_backward(ops, B, T, dims):
     """RSSM_PRECISION_BF16_FUSED (BPTT + weight gradients in one kernel, tcgen05 / TMEM accumulators) against
     RSSM_PRECISION_BF16 (BPTT kernel + mma.sync weight-gradient kernel): the forward is bit-identical, the data gradients run
-    the same arithmetic up to the fp32 summation order and the bf16 operand roundings that order can flip (4e-3 of scale, data
-    gradients; 2e-3 of scale, weight gradients)."""
+    the same arithmetic up to the fp32 summation order and the bf16 operand roundings that order can flip (6e-3 of scale, data
+    gradients -- measured 4.4e-3 at T = 131 with every output incl. the hiddens receiving a gradient; 2e-3 of scale, weight gradients)."""
     R, P = ops
     params = H.make_params(H.MT_SHAPES)
     inp = H.mtrssm_inputs(B, T, dims)
@@ -491,7 +493,7 @@ def test_mtrssm_bf16_fused_backward_matches_two_kernel_backward(ops, B, T, dims)
     # the bf16 rounding (2^-9) of an MMA operand downstream, so the paths agree to a few bf16 ulps, not bit for bit
     for k in MT_GRAD_IN:
         scale = float(x1[k].grad.abs().max())
-        rep.check("d " + k, x2[k].grad, x1[k].grad, rtol=0, atol=4e-3 * max(scale, 1e-3))
+        rep.check("d " + k, x2[k].grad, x1[k].grad, rtol=0, atol=6e-3 * max(scale, 1e-3))
     for k in w1:
         scale = float(w1[k].grad.abs().max())
         rep.check("d " + k.replace("rnn_to_post_projector", "post"), w2[k].grad, w1[k].grad, rtol=0, atol=2e-3 * max(scale, 1e-3))
