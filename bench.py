@@ -213,15 +213,24 @@ class DirectMtrssm:
 def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
     import torch.distributed as dist
 
-    works = [None, None]  # the in-flight allreduce of each gradient bucket
+    # N > 1: ONE exchange per step, the mean of the 66 KB weight-gradient bucket, on the compute stream right after the backward.
+    # Preferred: our one-shot kernel over NVLink peer memory (dp.P2pGradAllreduce); if the GPUs cannot map each other, NCCL.
+    # (An asynchronous NCCL allreduce under the next step was measured and is WORSE at 8 GPUs, profiles/r2_u_bench_8gpu.json:
+    # the collective's CTAs displace CTAs of the persistent rollout kernels, which then finish late by the whole delay.)
     count = [0]
+    comm, reduced, mode = None, None, "none"
+    if world > 1:
+        from multimodal_mtrssm_b200 import dp
+
+        try:
+            comm = dp.P2pGradAllreduce(run.flat_grads[0].numel())
+            reduced = torch.empty_like(run.flat_grads[0])
+            mode = "one-shot allreduce kernel over NVLink peer memory (rssm_p2p_allreduce_mean)"
+        except RuntimeError as e:
+            mode = f"NCCL allreduce on the compute stream (peer mapping unavailable: {str(e)[:120]})"
 
     def step(evs=None):
         k = count[0] & 1
-        count[0] += 1
-        if works[k] is not None:  # bucket k is about to be rewritten: its allreduce (two steps ago) must have finished
-            works[k].wait()
-            works[k] = None
         if evs:
             evs[0].record()
         run.fwd()
@@ -235,16 +244,17 @@ def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
             evs[2].record()
         if not run.fused:
             run.wgrad(k)
-        if world > 1:  # one NCCL allreduce of the 66 KB bucket per step, on NCCL's stream: it overlaps the NEXT step's kernels
-            works[k] = dist.all_reduce(run.flat_grads[k], async_op=True)
+        if comm is not None:
+            comm.allreduce(count[0], run.flat_grads[k], reduced)
+        elif world > 1:
+            dist.all_reduce(run.flat_grads[k])
+        count[0] += 1
         if evs:
             evs[3].record()
 
     def drain():
-        for k in range(2):
-            if works[k] is not None:
-                works[k].wait()
-                works[k] = None
+        if comm is not None:
+            comm.check()  # synchronises; raises if a rank gave up waiting for a peer
 
     for _ in range(warmup):
         step()
@@ -269,8 +279,18 @@ def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t)
     seg = [[e[i].elapsed_time(e[i + 1]) for e in evs] for i in range(3)]
+    if comm is not None:  # the peer result equals NCCL's on the last step's bucket (checked outside the timed region)
+        ref = run.flat_grads[(count[0] - 1) & 1].clone()
+        dist.all_reduce(ref)
+        ref /= world
+        err = float((ref - reduced).abs().max() / ref.abs().max().clamp_min(1e-30))
+        if err > 1e-5:
+            raise SystemExit(f"p2p allreduce disagrees with NCCL: relative error {err}")
+        torch.cuda.synchronize()
+        dist.barrier()
+        comm.close()
     return {"total_ms": total_ms, "fwd_ms": statistics.mean(seg[0]), "bwd_ms": statistics.mean(seg[1]),
-            "wgrad_ms": statistics.mean(seg[2])}
+            "wgrad_ms": statistics.mean(seg[2]), "allreduce": mode}
 
 
 def time_e2e(B: int, T: int, precision: int, steps: int, warmup: int, world: int, device: torch.device, host_bf16: bool = False,
@@ -635,7 +655,7 @@ def workload_config(B: int, T: int, world: int, prior_sample: bool) -> dict:
     cfg = {
         "workload": "cfg2: MoPoE-MMTRSSM default.yaml sizes (hd=ld=32, hs=ls=16, E=64, A=6), rollout fwd+bwd on synthetic "
                     "vision+audio embeddings/actions", "batch_per_gpu": B, "seq_len": T, "global_batch": world * B,
-        "parallelism": f"dp{world} (batch-sharded, one flat-bucket NCCL allreduce of the weight gradients)" if world > 1 else "single GPU",
+        "parallelism": f"dp{world} (batch-sharded, one mean-allreduce of the flat weight-gradient bucket per step)" if world > 1 else "single GPU",
         "prior_samples": "drawn and written (what MoPoE_MMTRSSM.rollout_representation launches)" if prior_sample else "not drawn (bytes subtracted)",
     }
     cfg["l2"] = f"inputs {input_mb:.0f} MB + outputs/records per step exceed the 126 MB L2 (no flush needed)"
@@ -867,6 +887,7 @@ def main() -> None:
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if precision == _lib.PRECISION_FP32 else "bf16", "data": "synthetic",
         "config": workload_config(B, T, world, prior_sample),
+        "allreduce": res.get("allreduce"),
         "kernel_ms": seg,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": what, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,

@@ -285,6 +285,38 @@ size_t rssm_gaussian_nll_workspace_bytes(void);
 int rssm_gaussian_nll_fwd(const RssmNllPair *pairs, int n_pairs, int pred_dtype, void *workspace, size_t workspace_bytes, void *stream);
 int rssm_gaussian_nll_bwd(const RssmNllPair *pairs, int n_pairs, int pred_dtype, void *stream);
 
+/* ---- data parallelism: one-shot mean-allreduce of the gradient bucket over peer memory ----------------------------------
+   SURVEY.md 8(e): the batch-sharded rollout exchanges ONE small bucket per step (the weight gradients, 66 KB at the default sizes;
+   the reference: Lightning DDP's NCCL allreduce, mopoe_mmtrssm/configs/default.yaml trainer.strategy).  One process per GPU of one
+   NVLink / NVSwitch box, at most RSSM_P2P_MAX_RANKS ranks.  Every rank
+     1. rssm_p2p_alloc()s a region (cudaMalloc, zero-filled): [flags: 2 slots x RSSM_P2P_MAX_RANKS u32 | pad to 256 B |
+        bucket slot 0: n floats | bucket slot 1: n floats], sized by rssm_p2p_region_bytes(n);
+     2. rssm_p2p_export()s a 64-byte handle, exchanges the handles with its peers by any host-side means (the Python host:
+        torch.distributed.all_gather_object), and rssm_p2p_import()s each peer's handle (cudaIpc; peer access is enabled lazily);
+     3. after its backward calls rssm_p2p_allreduce_mean(): `src` (this rank's gradients, n floats of ordinary device memory) is
+        copied into bucket slot (step & 1) of its OWN region -- or src == NULL and the caller has filled that slot in place (measured:
+        a backward that accumulates its atomics directly into the peer-mapped allocation runs 2x slower, so the Python host copies)
+        -- then out[0:n] = mean over ranks of that slot's buckets, read straight from peer memory by one kernel (flag exchange with
+        release / acquire at system scope, identical summation order on every rank).  `out` may be `src` (in place).
+   `step` counts the calls (0, 1, 2, ...) and must advance by one per call on every rank; the slots alternate so that a rank may
+   refill slot (step & 1) as soon as its call of step + 1 has completed on its stream.  A peer that never arrives makes the kernel
+   give up after `timeout_ms` (the result is then not written and rssm_p2p_status() returns 1 after synchronisation). */
+#define RSSM_P2P_MAX_RANKS 8
+typedef struct {
+    int world, rank;
+    void *regions[RSSM_P2P_MAX_RANKS]; /* device pointers of every rank's region as mapped in THIS process ([rank] = own) */
+    size_t n;                          /* floats per bucket */
+} RssmP2pComm;
+size_t rssm_p2p_region_bytes(size_t n);
+int rssm_p2p_alloc(size_t bytes, void **region);
+int rssm_p2p_free(void *region);
+int rssm_p2p_export(void *region, unsigned char handle[64]);
+int rssm_p2p_import(const unsigned char handle[64], void **peer_region);
+int rssm_p2p_close(void *peer_region);
+float *rssm_p2p_bucket(void *region, size_t n, int slot);   /* address of bucket `slot` inside a region */
+int rssm_p2p_allreduce_mean(const RssmP2pComm *comm, long long step, const float *src, float *out, int timeout_ms, void *stream);
+int rssm_p2p_status(const RssmP2pComm *comm);              /* 0 = ok, 1 = a call timed out (reads the status word; synchronises) */
+
 /* ---- misc ------------------------------------------------------------------------------------------------ */
 int rssm_abi_version(void);
 const char *rssm_last_error(void);

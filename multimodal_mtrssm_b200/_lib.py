@@ -111,7 +111,11 @@ EXPORTS = (
     "rssm_abi_version", "rssm_last_error", "rssm_kernel_launch_count",
     "rssm_mrssm_saved_bytes", "rssm_mrssm_workspace_bytes",
     "rssm_gaussian_nll_fwd", "rssm_gaussian_nll_bwd", "rssm_gaussian_nll_workspace_bytes",
+    "rssm_p2p_region_bytes", "rssm_p2p_alloc", "rssm_p2p_free", "rssm_p2p_export", "rssm_p2p_import", "rssm_p2p_close",
+    "rssm_p2p_bucket", "rssm_p2p_allreduce_mean", "rssm_p2p_status",
 )
+P2P_MAX_RANKS = 8
+P2pComm = _struct("RssmP2pComm", [("world", C.c_int), ("rank", C.c_int), ("regions", C.c_void_p * P2P_MAX_RANKS), ("n", C.c_size_t)])
 
 
 @lru_cache(maxsize=1)
@@ -146,6 +150,17 @@ def lib() -> C.CDLL:
     handle.rssm_gaussian_nll_fwd.argtypes = [P, C.c_int, C.c_int, P, C.c_size_t, P]
     handle.rssm_gaussian_nll_bwd.restype = C.c_int
     handle.rssm_gaussian_nll_bwd.argtypes = [P, C.c_int, C.c_int, P]
+    handle.rssm_p2p_region_bytes.restype = C.c_size_t
+    handle.rssm_p2p_region_bytes.argtypes = [C.c_size_t]
+    handle.rssm_p2p_alloc.argtypes = [C.c_size_t, C.POINTER(P)]
+    handle.rssm_p2p_free.argtypes = [P]
+    handle.rssm_p2p_export.argtypes = [P, C.c_char_p]
+    handle.rssm_p2p_import.argtypes = [C.c_char_p, C.POINTER(P)]
+    handle.rssm_p2p_close.argtypes = [P]
+    handle.rssm_p2p_bucket.restype = P
+    handle.rssm_p2p_bucket.argtypes = [P, C.c_size_t, C.c_int]
+    handle.rssm_p2p_allreduce_mean.argtypes = [P, C.c_longlong, P, P, C.c_int, P]
+    handle.rssm_p2p_status.argtypes = [P]
     if handle.rssm_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{LIB.name}: ABI version {handle.rssm_abi_version()} != {ABI_VERSION}")
     return handle

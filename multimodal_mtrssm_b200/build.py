@@ -12,7 +12,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "librssm_rollout.so"
-SOURCES = ("mrssm_kernels.cu", "mrssm_wide_fwd.cu", "mrssm_wide_bwd.cu", "mrssm_wide_wgrad.cu", "mtrssm_kernels.cu", "mtrssm_fwd2.cu", "mtrssm_fused_bwd.cu", "wgrad_kernel.cu", "likelihood_kernel.cu", "rollout_abi.cu")
+SOURCES = ("mrssm_kernels.cu", "mrssm_wide_fwd.cu", "mrssm_wide_bwd.cu", "mrssm_wide_wgrad.cu", "mtrssm_kernels.cu", "mtrssm_fwd2.cu", "mtrssm_fused_bwd.cu", "wgrad_kernel.cu", "likelihood_kernel.cu", "p2p_allreduce.cu", "rollout_abi.cu")
 NVCC_FLAGS = (
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false",

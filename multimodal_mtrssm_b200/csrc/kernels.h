@@ -1,5 +1,6 @@
 // Internal launch interface between the C-ABI layer (rollout_abi.cu) and the kernels.
 #pragma once
+#include <cstdint>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -255,5 +256,19 @@ struct NllArgs {
 };
 int nll_ctas_per_segment(int nseg);
 cudaError_t launch_gaussian_nll(const NllArgs& a, bool backward, cudaStream_t s);
+
+// ---- one-shot peer-memory allreduce of the gradient bucket (p2p_allreduce.cu) ----------------------------------------------
+constexpr int P2P_MAX_RANKS = 8;
+struct P2pAllreduceArgs {
+    const float* data[P2P_MAX_RANKS];  // every rank's bucket of this slot (peer-mapped; [rank] = the local one)
+    uint32_t* flags[P2P_MAX_RANKS];    // every rank's flag rows [2 slots][P2P_MAX_RANKS] (peer-mapped)
+    float* out;                        // local result (mean over ranks), n floats
+    uint32_t* status;                  // local word, set to 1 on timeout
+    size_t n;
+    int world, rank, slot;
+    uint32_t epoch;
+    long long timeout_cycles;
+};
+cudaError_t launch_p2p_allreduce_mean(const P2pAllreduceArgs& a, cudaStream_t s);
 
 }  // namespace rssm

@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 
 #include "kernels.h"
 #include "wide_common.cuh"
@@ -802,6 +803,76 @@ int rssm_gaussian_nll_bwd(const RssmNllPair* pairs, int n_pairs, int pred_dtype,
     if (nll_args(pairs, n_pairs, pred_dtype, true, &a)) return 1;
     g_launches.fetch_add(1);
     return check_cuda(rssm::launch_gaussian_nll(a, true, static_cast<cudaStream_t>(stream)), "gaussian nll backward launch");
+}
+
+
+// ---- one-shot peer-memory allreduce of the gradient bucket ------------------------------------------------------------------
+// region layout: [flags 2 x 8 u32 = 64 B | status word @64 | pad to 256 B | bucket 0 | bucket 1], buckets 256-byte aligned
+static size_t p2p_bucket_stride(size_t n) { return (n * sizeof(float) + 255) / 256 * 256; }
+size_t rssm_p2p_region_bytes(size_t n) { return 256 + 2 * p2p_bucket_stride(n); }
+float* rssm_p2p_bucket(void* region, size_t n, int slot) {
+    return reinterpret_cast<float*>(static_cast<char*>(region) + 256 + (size_t)(slot & 1) * p2p_bucket_stride(n));
+}
+int rssm_p2p_alloc(size_t bytes, void** region) {
+    REQUIRE(region);
+    if (bytes < 256) return fail("p2p region too small (%zu bytes): size it with rssm_p2p_region_bytes", bytes);
+    if (check_cuda(cudaMalloc(region, bytes), "p2p region cudaMalloc")) return 1;
+    return check_cuda(cudaMemset(*region, 0, bytes), "p2p region memset");
+}
+int rssm_p2p_free(void* region) { return check_cuda(cudaFree(region), "p2p region cudaFree"); }
+int rssm_p2p_export(void* region, unsigned char handle[64]) {
+    REQUIRE(region); REQUIRE(handle);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    if (check_cuda(cudaIpcGetMemHandle(&h, region), "cudaIpcGetMemHandle")) return 1;
+    memcpy(handle, &h, 64);
+    return 0;
+}
+int rssm_p2p_import(const unsigned char handle[64], void** peer_region) {
+    REQUIRE(handle); REQUIRE(peer_region);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    return check_cuda(cudaIpcOpenMemHandle(peer_region, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle (peer access between the GPUs of this box)");
+}
+int rssm_p2p_close(void* peer_region) { return check_cuda(cudaIpcCloseMemHandle(peer_region), "cudaIpcCloseMemHandle"); }
+static int p2p_check(const RssmP2pComm* c) {
+    REQUIRE(c);
+    if (c->world < 1 || c->world > RSSM_P2P_MAX_RANKS || c->rank < 0 || c->rank >= c->world)
+        return fail("p2p comm: world %d / rank %d (at most %d ranks of one box)", c->world, c->rank, RSSM_P2P_MAX_RANKS);
+    for (int r = 0; r < c->world; ++r)
+        if (c->regions[r] == nullptr) return fail("p2p comm: region of rank %d is NULL", r);
+    if (c->n < 1) return fail("p2p comm: empty bucket");
+    return 0;
+}
+int rssm_p2p_allreduce_mean(const RssmP2pComm* c, long long step, const float* src, float* out, int timeout_ms, void* stream) {
+    if (p2p_check(c)) return 1;
+    REQUIRE(out);
+    if (step < 0) return fail("p2p allreduce: step must count up from 0 (got %lld)", step);
+    if (!aligned16(out)) return fail("p2p allreduce: out must be 16-byte aligned");
+    rssm::P2pAllreduceArgs a{};
+    a.world = c->world, a.rank = c->rank, a.n = c->n, a.slot = (int)(step & 1), a.out = out;
+    a.epoch = (uint32_t)(step / 2 + 1);  // monotonic per slot, never 0 (the flags start zero-filled)
+    for (int r = 0; r < c->world; ++r) {
+        a.data[r] = rssm_p2p_bucket(c->regions[r], c->n, a.slot);
+        a.flags[r] = static_cast<uint32_t*>(c->regions[r]);
+    }
+    a.status = static_cast<uint32_t*>(c->regions[c->rank]) + 16;
+    if (src != nullptr &&
+        check_cuda(cudaMemcpyAsync(rssm_p2p_bucket(c->regions[c->rank], c->n, a.slot), src, c->n * sizeof(float), cudaMemcpyDeviceToDevice,
+                                   static_cast<cudaStream_t>(stream)), "p2p allreduce: copy into the peer-mapped bucket"))
+        return 1;
+    // clock64 ticks per millisecond: a generous constant (2.5 GHz) -- cudaDevAttrClockRate is a slow driver query (it put 0.6 ms of
+    // host time into every step when asked per call), and the bound only has to be "long enough, but not forever"
+    a.timeout_cycles = (long long)(timeout_ms > 0 ? timeout_ms : 2000) * 2500000LL;
+    g_launches.fetch_add(1);
+    return check_cuda(rssm::launch_p2p_allreduce_mean(a, static_cast<cudaStream_t>(stream)), "p2p allreduce launch");
+}
+int rssm_p2p_status(const RssmP2pComm* c) {
+    if (p2p_check(c)) return -1;
+    uint32_t v = 0;
+    if (check_cuda(cudaMemcpy(&v, static_cast<uint32_t*>(c->regions[c->rank]) + 16, 4, cudaMemcpyDeviceToHost), "p2p status read")) return -1;
+    if (v) fail("a p2p allreduce timed out waiting for its peers");
+    return (int)v;
 }
 
 }  // extern "C"

@@ -193,6 +193,108 @@ class OverlappedGradBuckets:
         self._handles = []
 
 
+class _DeviceView:
+    """`__cuda_array_interface__` over raw device memory, so torch can wrap a region of the peer-mapped allocation."""
+
+    def __init__(self, ptr: int, n_floats: int) -> None:
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+
+class P2pGradAllreduce:
+    """One-shot mean-allreduce of a small fp32 gradient bucket over NVLink / NVSwitch peer memory
+    (`rssm_p2p_allreduce_mean`, csrc/p2p_allreduce.cu): every rank keeps the bucket in a cudaIpc-mapped allocation, a single
+    kernel exchanges one flag per peer and reads all ranks' buckets straight from peer memory.  For the rollout's 66 KB bucket
+    this replaces a latency-bound NCCL allreduce (~37 us per step at 8 GPUs) on the compute stream.
+
+        comm = P2pGradAllreduce(n_floats)            # collective: every rank of `group` (one box, <= 8 ranks) must call it
+        ... backward writes the weight gradients into `flat` (ordinary device memory) ...
+        comm.allreduce(step, flat)                   # flat = mean over ranks, in place; `step` = 0, 1, 2, ... the same on every rank
+
+    The handles travel through `torch.distributed.all_gather_object` once, at construction.  Raises if peer access between the
+    ranks' GPUs cannot be had (the caller then keeps NCCL)."""
+
+    def __init__(self, n_floats: int, group: dist.ProcessGroup | None = None, device: torch.device | None = None,
+                 timeout_ms: int = 5000) -> None:
+        import ctypes as C
+
+        from . import _lib
+
+        if not dist.is_initialized():
+            raise RuntimeError("P2pGradAllreduce needs an initialised torch.distributed process group")
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.P2P_MAX_RANKS:
+            raise RuntimeError(f"P2pGradAllreduce: at most {_lib.P2P_MAX_RANKS} ranks of one box (got {self.world})")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        self.n, self.timeout_ms, self._lib, self._C = n_floats, timeout_ms, _lib, C
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            nbytes = lib.rssm_p2p_region_bytes(n_floats)
+            own = C.c_void_p()
+            if lib.rssm_p2p_alloc(nbytes, C.byref(own)):
+                raise RuntimeError(f"rssm_p2p_alloc failed: {lib.rssm_last_error().decode()}")
+            self._own = own.value
+            handle = C.create_string_buffer(64)
+            if lib.rssm_p2p_export(self._own, handle):
+                raise RuntimeError(f"rssm_p2p_export failed: {lib.rssm_last_error().decode()}")
+            handles: list = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.comm = _lib.P2pComm(world=self.world, rank=self.rank, n=n_floats)
+            self._imported = []
+            errors = []
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.comm.regions[r] = self._own
+                    continue
+                peer = C.c_void_p()
+                if lib.rssm_p2p_import(h, C.byref(peer)):
+                    errors.append(f"rank {r}: {lib.rssm_last_error().decode()}")
+                    continue
+                self.comm.regions[r] = peer.value
+                self._imported.append(peer.value)
+            ok = torch.tensor([0.0 if errors else 1.0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # every rank keeps or drops the peer path together
+            if float(ok) == 0.0:
+                self.close()
+                raise RuntimeError("P2pGradAllreduce: peer mapping failed" + (": " + "; ".join(errors) if errors else " on another rank"))
+            self._buckets = [torch.as_tensor(_DeviceView(lib.rssm_p2p_bucket(self._own, n_floats, k), n_floats), device=self.device)
+                             for k in range(2)]
+
+    def bucket(self, step: int) -> Tensor:
+        return self._buckets[step & 1]
+
+    def allreduce(self, step: int, src: Tensor | None, out: Tensor | None = None) -> None:
+        """out[0:n] = mean over ranks, on the current stream of this rank's device.  `src`: this rank's gradients (ordinary device
+        memory; copied into the peer-mapped bucket of this step first) -- or None when the caller filled `bucket(step)` in place.
+        `out` defaults to `src` (in place)."""
+        out = src if out is None else out
+        for t in (src, out):
+            if t is not None and (t.numel() != self.n or t.dtype != torch.float32 or not t.is_contiguous() or t.device != self.device):
+                raise RuntimeError("P2pGradAllreduce.allreduce: contiguous fp32 tensors of the bucket's size on this device, please")
+        if out is None:
+            raise RuntimeError("P2pGradAllreduce.allreduce: give `src` or `out`")
+        with torch.cuda.device(self.device):
+            C, lib = self._C, self._lib.lib()
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            if lib.rssm_p2p_allreduce_mean(C.byref(self.comm), step, C.c_void_p(src.data_ptr()) if src is not None else None,
+                                           C.c_void_p(out.data_ptr()), self.timeout_ms, stream):
+                raise RuntimeError(f"rssm_p2p_allreduce_mean failed: {lib.rssm_last_error().decode()}")
+
+    def check(self) -> None:
+        """Synchronises and raises if a call gave up waiting for a peer."""
+        if self._lib.lib().rssm_p2p_status(self._C.byref(self.comm)) != 0:
+            raise RuntimeError("P2pGradAllreduce: a peer did not arrive within the timeout")
+
+    def close(self) -> None:
+        lib = self._lib.lib()
+        for p in getattr(self, "_imported", []):
+            lib.rssm_p2p_close(p)
+        self._imported = []
+        self._buckets = []
+        if getattr(self, "_own", None):
+            lib.rssm_p2p_free(self._own)
+            self._own = None
+
+
 def broadcast_parameters(module: nn.Module, src: int = 0, group: dist.ProcessGroup | None = None) -> None:
     """Make every rank start from rank `src`'s parameters and buffers."""
     if not dist.is_initialized():
