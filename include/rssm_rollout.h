@@ -294,9 +294,8 @@ int rssm_gaussian_nll_bwd(const RssmNllPair *pairs, int n_pairs, int pred_dtype,
      2. rssm_p2p_export()s a 64-byte handle, exchanges the handles with its peers by any host-side means (the Python host:
         torch.distributed.all_gather_object), and rssm_p2p_import()s each peer's handle (cudaIpc; peer access is enabled lazily);
      3. after its backward calls rssm_p2p_allreduce_mean(): `src` (this rank's gradients, n floats of ordinary device memory) is
-        copied into bucket slot (step & 1) of its OWN region -- or src == NULL and the caller has filled that slot in place (measured:
-        a backward that accumulates its atomics directly into the peer-mapped allocation runs 2x slower, so the Python host copies)
-        -- then out[0:n] = mean over ranks of that slot's buckets, read straight from peer memory by one kernel (flag exchange with
+        copied into bucket slot (step & 1) of its OWN region (a 66 KB device copy on the same stream) -- or src == NULL and the
+        caller has filled that slot in place -- then out[0:n] = mean over ranks of that slot's buckets, read straight from peer memory by one kernel (flag exchange with
         release / acquire at system scope, identical summation order on every rank).  `out` may be `src` (in place).
    `step` counts the calls (0, 1, 2, ...) and must advance by one per call on every rank; the slots alternate so that a rank may
    refill slot (step & 1) as soon as its call of step + 1 has completed on its stream.  A peer that never arrives makes the kernel
