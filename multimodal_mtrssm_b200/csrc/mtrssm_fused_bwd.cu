@@ -43,12 +43,18 @@
 #ifdef FZ_TIMING
 #include <stdio.h>
 __device__ long long fz_dbg[3][1024][12];
+__device__ long long fz_grp[64];  // CTA 0, thread 0: kernel entry, prologue done, per group {start, end}, epilogue start / end
+#define FZ_GS(i)                                                   \
+    do {                                                           \
+        if (threadIdx.x == 0 && blockIdx.x == 0) fz_grp[i] = clock64(); \
+    } while (0)
 #define FZ_TS(i)                                                                                                  \
     do {                                                                                                          \
         if (lane == 0 && blockIdx.x == 0 && tile == 0 && grp == (int)blockIdx.x && t < 1024) fz_dbg[role][t][i] = clock64(); \
     } while (0)
 #else
 #define FZ_TS(i) do {} while (0)
+#define FZ_GS(i) do {} while (0)
 #endif
 
 namespace rssm {
@@ -278,6 +284,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
     uint2* W = reinterpret_cast<uint2*>(smem_raw);
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int A = p.A;
+    FZ_GS(0);
     __shared__ PackTable tb;
     if (tid == 0) {
         using namespace mt;
@@ -341,7 +348,9 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
     // accumulating the weight gradients in the SAME TMEM columns, so the weight packing above, the TMEM allocation and the
     // read-back + atomics below happen once per SM instead of once per group (4 groups per SM at the bench size).
     const int tpc = nthr / (32 * WPT), ngroups = ((p.B + 15) / 16 + tpc - 1) / tpc;
+    FZ_GS(1);
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    FZ_GS(2 + 2 * (grp / (int)gridDim.x));
     const int row0 = (grp * tpc + tile) * 16;
     if (row0 < p.B) {
         const Rows r = make_rows(row0, p.B, lane);
@@ -626,6 +635,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                     bulk_rows(stDF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, T - 2,
                               &bars[fz2::BAR_DF], lane);
             }
+            FZ_GS(20 + 2 * (grp / (int)gridDim.x));
             for (int t = T - 1; t >= 0; --t) {
                 const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
                 const float dkl_cur = dkl_next;
@@ -844,6 +854,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 }
                 FZ_TS(11);
             }
+            FZ_GS(21 + 2 * (grp / (int)gridDim.x));
             if constexpr (WPT == 2) pair_initial_state(ph_end);
             cp_async_wait_all();
         } else {
@@ -964,7 +975,9 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
         }
         nbar_sync(bar_g, 32 * WPT);
     }
+    FZ_GS(3 + 2 * (grp / (int)gridDim.x));
     }  // tile groups
+    FZ_GS(40);
     // ---- epilogue: TMEM accumulators -> global weight gradients (one atomicAdd per element per CTA) -----------------------
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -998,6 +1011,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    FZ_GS(41);
 }
 
 // ---- host side: which TMEM block goes where ------------------------------------------------------------------------------
@@ -1091,6 +1105,17 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
                 fprintf(stderr, "   %-20s %8.0f   (sum of intervals %.0f)\n", "WHOLE STEP", step / (hi - lo), tot);
             }
         }
+          if (getenv("RSSM_FZ_TIMING")) {
+            cudaDeviceSynchronize();
+            long long gs[64];
+            cudaMemcpyFromSymbol(gs, fz_grp, sizeof(gs));
+            const int ng = (groups + sms - 1) / sms;
+            fprintf(stderr, "[fz groups] thread 0 of CTA 0, cycles: prologue %lld", gs[1] - gs[0]);
+            for (int g2 = 0; g2 < ng && g2 < 16; ++g2)
+                fprintf(stderr, " | group %d: %lld = before the step loop %lld + %d steps %lld + after %lld", g2, gs[3 + 2 * g2] - gs[2 + 2 * g2],
+                        gs[20 + 2 * g2] - gs[2 + 2 * g2], a.T, gs[21 + 2 * g2] - gs[20 + 2 * g2], gs[3 + 2 * g2] - gs[21 + 2 * g2]);
+            fprintf(stderr, " | epilogue %lld | total %lld\n", gs[41] - gs[40], gs[41] - gs[0]);
+          }
 #endif
         return cudaGetLastError();
     };
