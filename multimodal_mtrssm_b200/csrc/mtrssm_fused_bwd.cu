@@ -44,9 +44,17 @@
 #include <stdio.h>
 __device__ long long fz_dbg[3][1024][12];
 __device__ long long fz_grp[64];  // CTA 0, thread 0: kernel entry, prologue done, per group {start, end}, epilogue start / end
+__device__ long long fz_cta[256][3];  // per CTA: globaltimer at entry / exit (ns), SM id
 #define FZ_GS(i)                                                   \
     do {                                                           \
         if (threadIdx.x == 0 && blockIdx.x == 0) fz_grp[i] = clock64(); \
+        if (threadIdx.x == 0 && ((i) == 0 || (i) == 41) && blockIdx.x < 256) {                      \
+            long long gt_;                                                                          \
+            unsigned sm_;                                                                           \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                 \
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));                                        \
+            fz_cta[blockIdx.x][(i) == 0 ? 0 : 1] = gt_, fz_cta[blockIdx.x][2] = sm_;                \
+        }                                                                                           \
     } while (0)
 #define FZ_TS(i)                                                                                                  \
     do {                                                                                                          \
@@ -1115,6 +1123,14 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
                 fprintf(stderr, " | group %d: %lld = before the step loop %lld + %d steps %lld + after %lld", g2, gs[3 + 2 * g2] - gs[2 + 2 * g2],
                         gs[20 + 2 * g2] - gs[2 + 2 * g2], a.T, gs[21 + 2 * g2] - gs[20 + 2 * g2], gs[3 + 2 * g2] - gs[21 + 2 * g2]);
             fprintf(stderr, " | epilogue %lld | total %lld\n", gs[41] - gs[40], gs[41] - gs[0]);
+            static long long ct[256][3];
+            cudaMemcpyFromSymbol(ct, fz_cta, sizeof(ct));
+            const int nc = groups < sms ? groups : sms;
+            long long t0 = ct[0][0], t1 = 0;
+            for (int c = 0; c < nc; ++c) t0 = ct[c][0] < t0 ? ct[c][0] : t0, t1 = ct[c][1] > t1 ? ct[c][1] : t1;
+            fprintf(stderr, "[fz ctas] %d CTAs, kernel span %.1f us; per CTA (sm: start offset us, duration us):", nc, (t1 - t0) * 1e-3);
+            for (int c = 0; c < nc; ++c) fprintf(stderr, " %lld:%.1f,%.1f", ct[c][2], (ct[c][0] - t0) * 1e-3, (ct[c][1] - ct[c][0]) * 1e-3);
+            fprintf(stderr, "\n");
           }
 #endif
         return cudaGetLastError();
