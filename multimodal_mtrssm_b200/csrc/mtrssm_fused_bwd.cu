@@ -321,11 +321,15 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
     __syncthreads();
     pack_run<NS>(tb, tid, nthr);
     const int lane = tid & 31, warp = tid >> 5, tile = warp / WPT, role = warp % WPT;  // role 0 = core, 1 = mod, 2 = aux
-    unsigned char* my = smem_raw + (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + (size_t)tile * fz2::BYTES;
+    // one tile per CTA (batches of at most one tile per SM, e.g. cfg4's 16 tiles): 128 threads = the tile's three warps + one
+    // HELPER warp that only takes part in the CTA-wide steps (weight packing, TMEM zeroing and read-back need four warps)
+    const bool active = tile < nthr / (32 * WPT);
+    unsigned char* my = smem_raw + (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + (size_t)(active ? tile : 0) * fz2::BYTES;
     // zero the tile's images and exchange buffers once (the warps of the tile split the range)
-    for (int i = lane + 32 * role; i < fz2::BYTES / 16; i += 32 * WPT) reinterpret_cast<uint4*>(my)[i] = make_uint4(0u, 0u, 0u, 0u);
-    uint64_t* bars = bars_all[tile];
-    if (role == 0 && lane == 0) {
+    if (active)
+        for (int i = lane + 32 * role; i < fz2::BYTES / 16; i += 32 * WPT) reinterpret_cast<uint4*>(my)[i] = make_uint4(0u, 0u, 0u, 0u);
+    uint64_t* bars = bars_all[active ? tile : 0];
+    if (active && role == 0 && lane == 0) {
 #pragma unroll
         for (int i = 0; i < fz2::NBAR; ++i) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
     for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     FZ_GS(2 + 2 * (grp / (int)gridDim.x));
     const int row0 = (grp * tpc + tile) * 16;
-    if (row0 < p.B) {
+    if (active && row0 < p.B) {
         const Rows r = make_rows(row0, p.B, lane);
         const int T = p.T;
         const __nv_bfloat16* saved = reinterpret_cast<const __nv_bfloat16*>(p.saved);
@@ -1071,11 +1075,12 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
         add_flush(u, g.h_d2h_b, z::T_C + 32, 32, 104, 1, 1, 0);
         add_flush(u, g.h_in_b, z::T_C + 32, 32, 104, 1, 1, 0);
     }
-    // tiles per CTA: 4 fill an SM's shared memory; small batches use 2 (the TMEM read-back needs four warps) to reach more SMs
-    const int tiles = (a.B + 15) / 16, tpc = tiles > 2 * 148 ? 4 : 2;
-    const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + tpc * (size_t)fz2::BYTES;
     // warps per tile: 3 (core, mod, aux) by default; RSSM_BWD_TWO_WARP=1 selects the two-warp kernel (A/B measurements)
     const int wpt = getenv("RSSM_BWD_TWO_WARP") != nullptr ? 2 : 3;
+    // tiles per CTA: 4 fill an SM's shared memory; small batches use 2, or 1 (three-warp kernel: + a helper warp, the TMEM
+    // read-back needs four warps) when every tile can have an SM of its own -- two tiles sharing an SM run 20 % slower per step
+    const int tiles = (a.B + 15) / 16, tpc = tiles > 2 * 148 ? 4 : (tiles > 148 || tiles < 2 || wpt != 3 || getenv("RSSM_BWD_TWO_TILES")) ? 2 : 1;  // (a lone tile keeps the six-warp CTA: faster weight packing)
+    const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + tpc * (size_t)fz2::BYTES;
     if (a.obs_projected && wpt != 3) return cudaErrorNotSupported;  // the pre-multiplied-partials mode lives in the three-warp kernel
     auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1084,7 +1089,7 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int groups = (tiles + tpc - 1) / tpc;  // one resident CTA per SM (shared memory): persistent over its groups
-        kernel<<<groups < sms ? groups : sms, 32 * wpt * tpc, smem, s>>>(a, u);
+        kernel<<<groups < sms ? groups : sms, tpc == 1 ? 128 : 32 * wpt * tpc, smem, s>>>(a, u);
 #ifdef FZ_TIMING
         if (getenv("RSSM_FZ_TIMING")) {
             static long long h[3][1024][12];
