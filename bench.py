@@ -226,7 +226,8 @@ def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
             comm = dp.P2pGradAllreduce(run.flat_grads[0].numel())
             reduced = torch.empty_like(run.flat_grads[0])
             mode = "one-shot allreduce kernel over NVLink peer memory (rssm_p2p_allreduce_mean)"
-        except RuntimeError as e:
+        except Exception as e:  # noqa: BLE001  (no peer mapping on this box / container: every rank raises together, see dp.py)
+            comm = None
             mode = f"NCCL allreduce on the compute stream (peer mapping unavailable: {str(e)[:120]})"
 
     def step(evs=None):
