@@ -131,27 +131,11 @@ __device__ __forceinline__ void load_op(float (&c)[NT][4], const unsigned char* 
     }
 }
 
-// cp.async a run of `n` (<= 8) consecutive record chunks, first record chunk c0, of step t into the operand image at `dst0`
-// (address of the image of chunk c0).  Lane -> row (lane & 15), chunk pair member (lane >> 4): the 16 lanes of a half warp write
-// the 16 rows of ONE chunk = 256 contiguous bytes (conflict-free), lanes L and L + 16 read the two halves of one 32-byte sector.
-// (The first version mapped 8 lanes to 8 chunks of one row: 256-byte strides, 8-way bank conflicts -- 32 shared-memory wavefronts
-// per instruction instead of 4, 27 % of the kernel's shared-memory traffic: profiles/r2_g_ncu_summary.txt.)
-__device__ __forceinline__ void stage_chunks(unsigned char* dst0, const __nv_bfloat16* saved, int c0, int n, int row0, int B, int T, int t,
-                                             int lane) {
-    const int rr = lane & 15, half = lane >> 4;
-    const size_t idx = (size_t)min(row0 + rr, B - 1) * T + t;
-    const __nv_bfloat16* src = saved + idx * MTRSSM_SAVED_BF16 + 8 * c0;
-    unsigned char* d = dst0 + (rr >> 3) * 128 + (rr & 7) * 16;  // row rr of a chunk: k-group rr / 8, row rr % 8
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = 2 * j + half;
-        if (c < n) cp_async16(d + c * fz::CH, src + 8 * c);
-    }
-}
-
+// (Round 1 / early round 2 staged a ROW-layout record [B][T][208] here: a gather of 16-byte pieces at a T x 416-byte stride, one
+// shared-memory wavefront per lane.  The fused policy's record is tile-blocked now; the row layout lives on in the two-kernel path.)
 // Tile-blocked record (MtrssmBwdArgs.rec_tiled): chunks c0 .. c0+n-1 of a tile-step are n x 256 CONTIGUOUS bytes in global memory
 // AND in the operand image: the warp copies them as a linear run of 16-byte pieces (piece = lane + 32 i), whole 128-byte lines on
-// both sides -- 4 shared-memory wavefronts per instruction where the row-layout gather above needs 32 (one per lane).
+// both sides -- 4 shared-memory wavefronts per instruction where a row-layout gather needs 32 (one per lane).
 // (A cp.async.bulk per run was measured as well: no faster at the bench size, slower for one tile -- fence + single-lane issue.)
 __device__ __forceinline__ void stage_chunks_tiled(unsigned char* dst0, const __nv_bfloat16* saved, int c0, int n, int tile_row, int T, int t,
                                                    int lane) {
@@ -281,8 +265,11 @@ __device__ __forceinline__ void xch_load(float (&c)[NT][4], const float* buf, in
 // work: it converts the feature row and the fp32 embeddings into the tcgen05 operand images, issues the end-of-step MMA group
 // (and the embedding MMA), computes the embedding / action gradients from the dY images (d_embed = dY1 . W1e, d_action = dY_l .
 // W_in) and stores them, and refills the feature-row stage.  12 warps per SM instead of 8, <= 168 registers each.
-// GROUPED: the forward's outputs share one MTRSSM_ROW_PITCH-float row per (b,t) (RssmMtrssmOutputs.ld_*); compile-time pitches
-template <int KL, int KH, int WPT, bool GROUPED>
+// GROUPED: the forward's outputs share one MTRSSM_ROW_PITCH-float row per (b,t) (RssmMtrssmOutputs.ld_*); compile-time pitches.
+// PROJ: pre-multiplied observation partials (dims.obs_projected; three-warp kernel only).  The saved record is always tile-blocked.
+// (Layout / mode switches are template parameters, not runtime flags: the dead branches of an 8 k-instruction kernel cost 2.4 % at
+// the bench batch -- 15 % of this kernel's stall samples are instruction fetch.)
+template <int KL, int KH, int WPT, bool GROUPED, bool PROJ>
 __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const MtrssmBwdArgs p, const FusedFlushTable ft) {
     constexpr int NS = 1;
     static_assert(WPT == 2 || WPT == 3, "two (core, mod) or three (core, mod, aux) warps per tile");
@@ -424,19 +411,16 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                     }
                 }
             };
-            const bool tiled = p.rec_tiled != 0;
-            auto stage_logits = [&](int t) {  // LA, LV: read by registers only, refilled right after the MoPoE math
+                        auto stage_logits = [&](int t) {  // LA, LV: read by registers only, refilled right after the MoPoE math
                 if (t >= 0) {
-                    if (tiled) stage_chunks_tiled(svop + 20 * fz2::CH, saved, 20, 4, row0 >> 4, T, t, lane);
-                    else stage_chunks(svop + 20 * fz2::CH, saved, 20, 4, row0, p.B, T, t, lane);
+                    stage_chunks_tiled(svop + 20 * fz2::CH, saved, 20, 4, row0 >> 4, T, t, lane);
                 }
                 stage_prl(t);
                 cp_async_commit();
             };
             auto stage_rest = [&](int t) {  // a / v hiddens: free once this warp's MMAs have completed
                 if (t >= 0) {
-                    if (tiled) stage_chunks_tiled(svop + 12 * fz2::CH, saved, 12, 8, row0 >> 4, T, t, lane);
-                    else stage_chunks(svop + 12 * fz2::CH, saved, 12, 8, row0, p.B, T, t, lane);
+                    stage_chunks_tiled(svop + 12 * fz2::CH, saved, 12, 8, row0 >> 4, T, t, lane);
                 }
                 cp_async_commit();
             };
@@ -560,7 +544,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 float ddl[4][4];
                 zero_c<4>(ddl);
                 AFrag<NS, 2> f1a, f1v;
-                if (WPT == 3 && p.obs_projected) {
+                if constexpr (PROJ) {
                     head_bwd_elu(dla, wblk<NS>(W, mt::T_A2), eluA, dy, fz::Y_LA, fz::Y_A1, f1a, r, lane, p.d_embed_a + iA * 32, p.d_embed_a + iB * 32);
                     head_bwd_elu(dlv, wblk<NS>(W, mt::T_V2), eluV, dy, fz::Y_LV, fz::Y_V1, f1v, r, lane, p.d_embed_v + iA * 32, p.d_embed_v + iB * 32);
                 } else {
@@ -610,15 +594,9 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
             float* stFT = reinterpret_cast<float*>(my + fz2::FT);
             float* stPR = reinterpret_cast<float*>(my + fz2::PR) - bst::PR;  // bstage_pr adds bst::PR itself
             uint32_t ph_df = 0, ph_ft = 0, ph_e = 0, ph_end = 0;
-            const bool tiled = p.rec_tiled != 0;
-            auto stage_hid = [&](int t) {  // lp, hp, hq hiddens: free once the E-group MMA has completed
+                        auto stage_hid = [&](int t) {  // lp, hp, hq hiddens: free once the E-group MMA has completed
                 if (t >= 0) {
-                    if (tiled) {
-                        stage_chunks_tiled(svop, saved, 0, 12, row0 >> 4, T, t, lane);
-                    } else {
-                        stage_chunks(svop, saved, 0, 8, row0, p.B, T, t, lane);
-                        stage_chunks(svop + 8 * fz2::CH, saved, 8, 4, row0, p.B, T, t, lane);
-                    }
+                    stage_chunks_tiled(svop, saved, 0, 12, row0 >> 4, T, t, lane);
                 }
                 cp_async_commit();
             };
@@ -881,7 +859,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 }
             };
             bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), ft_pitch, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
-            const bool emb = !p.obs_projected;  // obs_projected: no embedding operand images, no embedding MMA, no d_embed GEMMs here
+            constexpr bool emb = !PROJ;  // obs_projected: no embedding operand images, no embedding MMA, no d_embed GEMMs here
             if (emb) embed_prefetch(T - 2);
             // the fp32 embeddings of a step are requested one step ahead (registers) and converted at the top of their step
             float ea[8][4], ev[8][4];
@@ -1081,6 +1059,7 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
     // read-back needs four warps) when every tile can have an SM of its own -- two tiles sharing an SM run 20 % slower per step
     const int tiles = (a.B + 15) / 16, tpc = tiles > 2 * 148 ? 4 : (tiles > 148 || tiles < 2 || wpt != 3 || getenv("RSSM_BWD_TWO_TILES")) ? 2 : 1;  // (a lone tile keeps the six-warp CTA: faster weight packing)
     const size_t smem = (size_t)mt::BWD_TILES * 32 * sizeof(uint2) + tpc * (size_t)fz2::BYTES;
+    if (!a.rec_tiled) return cudaErrorInvalidValue;  // the fused backward reads the tile-blocked record only
     if (a.obs_projected && wpt != 3) return cudaErrorNotSupported;  // the pre-multiplied-partials mode lives in the three-warp kernel
     auto launch = [&](auto kernel) -> cudaError_t {
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1142,9 +1121,11 @@ cudaError_t launch_mtrssm_bwd_fused(const MtrssmBwdArgs& a, const RssmMtrssmWeig
     };
     const bool grouped = a.ld_feature != 0;
 #define FUSED_DISPATCH(KLv, KHv) \
-    if (a.KL == KLv && a.KH == KHv)                                                                                                   \
-        return wpt == 2 ? (grouped ? launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 2, true>) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 2, false>)) \
-                        : (grouped ? launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 3, true>) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 3, false>));
+    if (a.KL == KLv && a.KH == KHv) {                                                                                                  \
+        if (wpt == 2) return grouped ? launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 2, true, false>) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 2, false, false>); \
+        if (a.obs_projected) return grouped ? launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 3, true, true>) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 3, false, true>); \
+        return grouped ? launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 3, true, false>) : launch(mtrssm_bwd_fused2_kernel<KLv, KHv, 3, false, false>);              \
+    }
     FUSED_DISPATCH(4, 2)
 #ifndef RSSM_EXP_ONLY_DEFAULT
     FUSED_DISPATCH(4, 4)

@@ -601,8 +601,7 @@ static int mtrssm_fwd_common(const RssmMtrssmDims* d, const RssmMtrssmWeights* w
     a.kl_l = out->kl_l, a.kl_h = out->kl_h, a.saved = imagine ? nullptr : out->saved;
     a.saved_ld = mt_saved_ld(d->precision);
     a.obs_projected = imagine ? 0 : d->obs_projected;
-    a.rec_tiled = d->precision == RSSM_PRECISION_BF16_FUSED && getenv("RSSM_REC_ROW_LAYOUT") == nullptr ? 1 : 0;  // tile-blocked saved record
-                                                                                 // (include/rssm_rollout.h); the env var is for A/B timing
+    a.rec_tiled = d->precision == RSSM_PRECISION_BF16_FUSED ? 1 : 0;  // tile-blocked saved record (include/rssm_rollout.h)
     a.ld_feature = out->ld_feature;
     if ((out->ld_feature | out->ld_hidden | out->ld_probs | out->ld_stoch | out->ld_kl) != 0) {  // grouped rows
         if (imagine || !a.rec_tiled) return fail("grouped output rows (ld_* != 0) need the posterior rollout under RSSM_PRECISION_BF16_FUSED; pass 0 here");
@@ -658,7 +657,7 @@ int rssm_mtrssm_rollout_bwd(const RssmMtrssmDims* d, const RssmMtrssmWeights* w,
     a.d_deter_h0 = gin->d_deter_h0, a.d_deter_l0 = gin->d_deter_l0, a.d_hidden_h0 = gin->d_hidden_h0;
     a.d_hidden_l0 = gin->d_hidden_l0, a.d_stoch_h0 = gin->d_stoch_h0, a.d_stoch_l0 = gin->d_stoch_l0;
     a.obs_projected = d->obs_projected;
-    a.rec_tiled = fused && getenv("RSSM_REC_ROW_LAYOUT") == nullptr ? 1 : 0;
+    a.rec_tiled = fused ? 1 : 0;
     a.ld_feature = fo->ld_feature;
     if ((fo->ld_feature | fo->ld_probs) != 0) {
         if (!fused) return fail("grouped output rows (ld_* != 0) need the fused backward; pass 0 here");
