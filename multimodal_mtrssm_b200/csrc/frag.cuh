@@ -721,6 +721,104 @@ __device__ __forceinline__ void mopoe_mix(const float (&ls_a)[2][4], const float
         }
 }
 
+// ---- probability-domain MoPoE (bf16 policies) -----------------------------------------------------------------------------
+// With pa = softmax_16(la), pv = softmax_16(lv):  exp(mixed) = (pa + pv + pa pv) / 3, so the per-group softmax of `mixed`
+// (MultiOneHotFactory on the fused logits, mopoe_mrssm/core.py:241-251) is  q = s / sum_group(s),  s = pa + pv + pa pv,
+// and the responsibilities are ra = (pa + pa pv) / s, rv = (pv + pa pv) / s: no logarithm and one exponential per logit
+// instead of four.  If a whole group underflows (flat log-probabilities below ~ -69 in BOTH modalities) the callers fall
+// back to the log-domain functions above (warp-uniform branch, never taken at sane logit scales).
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// softmax over the FLAT 16 columns
+__device__ __forceinline__ void softmax_flat_fast(const float (&x)[2][4], float (&p)[2][4]) {
+    constexpr float L2E = 1.4426950408889634f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float m[2] = {fmaxf(x[0][2 * h], x[0][2 * h + 1]), fmaxf(x[1][2 * h], x[1][2 * h + 1])};
+        group_reduce<16, true>(m);
+        const float nm = -m[0] * L2E;
+        float e[2][2], s[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            e[nt][0] = ex2_ftz(fmaf(x[nt][2 * h], L2E, nm));
+            e[nt][1] = ex2_ftz(fmaf(x[nt][2 * h + 1], L2E, nm));
+            s[nt] = e[nt][0] + e[nt][1];
+        }
+        group_reduce<16, false>(s);
+        const float inv = rcp_ftz(s[0]);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) p[nt][2 * h] = e[nt][0] * inv, p[nt][2 * h + 1] = e[nt][1] * inv;
+    }
+}
+constexpr float MOPOE_TINY = 1e-30f;
+// fused posterior probabilities q (groups of K) from the two modality logits
+template <int K>
+__device__ __forceinline__ void mopoe_posterior_fast(const float (&la)[2][4], const float (&lv)[2][4], float (&q)[2][4]) {
+    float pa[2][4], pv[2][4];
+    softmax_flat_fast(la, pa);
+    softmax_flat_fast(lv, pv);
+    float lo = 1.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float s[2][2], g[2];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            s[nt][0] = fmaf(pa[nt][2 * h], pv[nt][2 * h], pa[nt][2 * h] + pv[nt][2 * h]);
+            s[nt][1] = fmaf(pa[nt][2 * h + 1], pv[nt][2 * h + 1], pa[nt][2 * h + 1] + pv[nt][2 * h + 1]);
+            g[nt] = s[nt][0] + s[nt][1];
+        }
+        group_reduce<K, false>(g);
+        lo = fminf(lo, fminf(g[0], g[1]));
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const float inv = rcp_ftz(g[nt]);
+            q[nt][2 * h] = s[nt][0] * inv, q[nt][2 * h + 1] = s[nt][1] * inv;
+        }
+    }
+    if (__any_sync(FULL, !(lo >= MOPOE_TINY))) {  // a whole group underflowed: log-domain evaluation
+        float lsa[2][4], lsv[2][4], mixed[2][4];
+        log_softmax_flat<true>(la, lsa);
+        log_softmax_flat<true>(lv, lsv);
+        mopoe_mix<true>(lsa, lsv, mixed, nullptr, nullptr);
+        softmax_groups<K, true>(mixed, q);
+    }
+}
+// backward side: softmax(la), softmax(lv) (all the flat log-softmax backward needs) and the two responsibilities
+__device__ __forceinline__ void mopoe_responsibilities_fast(const float (&la)[2][4], const float (&lv)[2][4], float (&pa)[2][4],
+                                                            float (&pv)[2][4], float (&ra)[2][4], float (&rv)[2][4]) {
+    softmax_flat_fast(la, pa);
+    softmax_flat_fast(lv, pv);
+    float lo = 1.f;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float pf = pa[nt][j] * pv[nt][j], s = pa[nt][j] + pv[nt][j] + pf;
+            const float inv = rcp_ftz(s);
+            lo = fminf(lo, s);
+            ra[nt][j] = (pa[nt][j] + pf) * inv;
+            rv[nt][j] = (pv[nt][j] + pf) * inv;
+        }
+    if (__any_sync(FULL, !(lo >= MOPOE_TINY))) {
+        float lsa[2][4], lsv[2][4], mixed[2][4];
+        log_softmax_flat<true>(la, lsa);
+        log_softmax_flat<true>(lv, lsv);
+        mopoe_mix<true>(lsa, lsv, mixed, ra, rv);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pa[nt][j] = Math<true>::exp(lsa[nt][j]), pv[nt][j] = Math<true>::exp(lsv[nt][j]);
+    }
+}
+
 // Inverse-CDF categorical draw (A2): idx = min(K-1, #{k : cdf_k <= u}), cdf accumulated in class order.
 // p: per-group probabilities (2 tiles); uA/uB: pointers to this row's uniforms u[c], c = 0..16/K-1.
 // Writes the exact one-hot into z (C-tile layout).
@@ -827,8 +925,18 @@ __device__ __forceinline__ void kl_rows_bwd(const float (&q)[2][4], const float 
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float g = dkl[j >> 1];
-            dq[nt][j] += g * wq * (clamp_log<FAST>(q[nt][j]) - clamp_log<FAST>(p[nt][j]) + 1.f);
-            dp[nt][j] -= g * wp * Math<FAST>::div(q[nt][j], fmaxf(p[nt][j], 1.1920928955078125e-07f));
+            if constexpr (FAST) {
+                // one reciprocal serves both halves: log q - log p = log(q / p) (the upper clamp of p, 1 - eps, moves the ratio by
+                // at most 1.2e-7 relative)
+                const float eps = 1.1920928955078125e-07f;
+                const float rp = rcp_ftz(fmaxf(p[nt][j], eps));
+                const float qc = fminf(fmaxf(q[nt][j], eps), 1.f - eps);
+                dq[nt][j] += g * wq * (Math<true>::log(qc * rp) + 1.f);
+                dp[nt][j] -= g * wp * (q[nt][j] * rp);
+            } else {
+                dq[nt][j] += g * wq * (clamp_log<FAST>(q[nt][j]) - clamp_log<FAST>(p[nt][j]) + 1.f);
+                dp[nt][j] -= g * wp * Math<FAST>::div(q[nt][j], fmaxf(p[nt][j], 1.1920928955078125e-07f));
+            }
         }
 }
 

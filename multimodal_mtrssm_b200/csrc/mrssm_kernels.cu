@@ -281,12 +281,13 @@ __global__ void __launch_bounds__(128) mrssm_fwd_kernel(const MrssmFwdArgs p) {
                 for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) mixed[nt][j] = la[nt][j];
-            } else {
-                log_softmax_flat<NS == 1>(la, lsa);
-                log_softmax_flat<NS == 1>(lv, lsv);
-                mopoe_mix<NS == 1>(lsa, lsv, mixed, nullptr, nullptr);
+            } else if constexpr (NS != 1) {
+                log_softmax_flat<false>(la, lsa);
+                log_softmax_flat<false>(lv, lsv);
+                mopoe_mix<false>(lsa, lsv, mixed, nullptr, nullptr);
             }
-            softmax_groups<K, NS == 1>(mixed, q);
+            if (NS == 1 && !p.unimodal) mopoe_posterior_fast<K>(la, lv, q);  // probability-domain MoPoE (frag.cuh)
+            else softmax_groups<K, NS == 1>(mixed, q);
             store_c<2>(q, p.post_probs + iA * 16, p.post_probs + iB * 16, r);
             if (STAGED) sample_onehot<K>(q, stage + stg::U0 + r.g * 8, stage + stg::U0 + (r.g + 8) * 8, zs, lane);
             else sample_onehot<K>(q, p.u_post + iA * C, p.u_post + iB * C, zs, lane);

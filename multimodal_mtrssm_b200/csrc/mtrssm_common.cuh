@@ -67,6 +67,9 @@ __device__ __forceinline__ int sw32(int chunk, int row) { return chunk ^ (4 * (r
 // Issue one bulk copy per row (lanes 0..15) of `bytes` from src + idx(row) * ld_bytes into dst + row * pitch_words.
 // Every lane has finished reading the buffer (the caller's __syncwarp); the proxy fence orders those generic-proxy
 // reads before the async-proxy writes.
+// (One lane issuing all 16 copies from warp-uniform addresses needs 100 instead of 170 instructions per call -- the bulk-copy
+// instruction takes uniform operands, so the 16 lanes below are serialised by a vote loop -- but is 5 % SLOWER at the bench batch:
+// measured, profiles/r2_ab_variants.txt.)
 __device__ __forceinline__ void bulk_rows(float* dst, int pitch_words, const char* src, size_t ld_bytes, uint32_t bytes, int row0, int B,
                                           int T, int t, uint64_t* bar, int lane) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

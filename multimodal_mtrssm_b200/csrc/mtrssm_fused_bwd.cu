@@ -95,18 +95,27 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {  // MN-major, no
 __host__ __device__ constexpr uint32_t umma_idesc(int N) {  // bf16 x bf16 -> fp32, A and B MN-major, M = 128
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, int N) {
+// The descriptors' high words are one constant (SBO, version) and the low word is (address >> 4) | LBO << 16: the callers keep the
+// low words of their images (desc_lo, once per group) and add compile-time chunk offsets -- ~5 instructions per MMA in the
+// single-lane issue block instead of ~20 (shift / mask / or / 64-bit assembly of both descriptors).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fffu) | ((uint32_t)(128 >> 4) << 16); }
+constexpr uint32_t DESC_HI = (uint32_t)(256 >> 4) | (1u << 14);
+__host__ __device__ constexpr uint32_t desc_off(int bytes) { return (uint32_t)bytes >> 4; }  // shared memory is < 256 KB: the 14-bit field cannot carry
+__device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, int N) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-        "l"(umma_desc(a_saddr)), "l"(umma_desc(b_saddr)), "r"(umma_idesc(N)), "r"(1u)
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(umma_idesc(N)), "r"(1u), "r"(DESC_HI)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// C tiles (NT/2 blocks of 16 columns, starting at operand column col0) -> bf16 operand chunks; dead rows are written as zero
+// C tiles (NT/2 blocks of 16 columns, starting at operand column col0) -> bf16 operand chunks.  Rows of sequences beyond the batch
+// are never written: a tile's images are zeroed once per group (and a row's validity does not change within a group), so they
+// stay zero and contribute nothing to the weight gradients -- predicated stores instead of two selects per store.
 template <int NT>
 __device__ __forceinline__ void store_op(const float (&c)[NT][4], unsigned char* op, int col0, const Rows& r) {
 #pragma unroll
@@ -114,8 +123,8 @@ __device__ __forceinline__ void store_op(const float (&c)[NT][4], unsigned char*
         unsigned char* q = op + ((col0 + 16 * j) / 8 + (r.t >> 1)) * fz::CH + r.g * 16 + (r.t & 1) * 8;
         const uint2 a = make_uint2(pack_bf16(c[2 * j][0], c[2 * j][1]), pack_bf16(c[2 * j + 1][0], c[2 * j + 1][1]));
         const uint2 b = make_uint2(pack_bf16(c[2 * j][2], c[2 * j][3]), pack_bf16(c[2 * j + 1][2], c[2 * j + 1][3]));
-        *reinterpret_cast<uint2*>(q) = r.vA ? a : make_uint2(0u, 0u);        // row g     (k-group 0)
-        *reinterpret_cast<uint2*>(q + 128) = r.vB ? b : make_uint2(0u, 0u);  // row g + 8 (k-group 1)
+        if (r.vA) *reinterpret_cast<uint2*>(q) = a;        // row g     (k-group 0)
+        if (r.vB) *reinterpret_cast<uint2*>(q + 128) = b;  // row g + 8 (k-group 1)
     }
 }
 template <int NT>
@@ -137,13 +146,13 @@ __device__ __forceinline__ void load_op(float (&c)[NT][4], const unsigned char* 
 // AND in the operand image: the warp copies them as a linear run of 16-byte pieces (piece = lane + 32 i), whole 128-byte lines on
 // both sides -- 4 shared-memory wavefronts per instruction where a row-layout gather needs 32 (one per lane).
 // (A cp.async.bulk per run was measured as well: no faster at the bench size, slower for one tile -- fence + single-lane issue.)
-__device__ __forceinline__ void stage_chunks_tiled(unsigned char* dst0, const __nv_bfloat16* saved, int c0, int n, int tile_row, int T, int t,
-                                                   int lane) {
-    const unsigned char* src = reinterpret_cast<const unsigned char*>(saved + ((size_t)tile_row * T + t) * (MTRSSM_SAVED_BF16 * 16) + (size_t)c0 * 128);
+// `tile_rec` = the tile's record of step 0, this lane's piece (saved + tile * T * 6656 B + lane * 16: computed once per group)
+__device__ __forceinline__ void stage_chunks_tiled(unsigned char* dst0, const unsigned char* tile_rec, int c0, int n, int t, int lane) {
+    const unsigned char* src = tile_rec + (size_t)(uint32_t)t * (MTRSSM_SAVED_BF16 * 16 * 2) + c0 * 256;
+    unsigned char* dst = dst0 + lane * 16;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        const int piece = lane + 32 * i;
-        if (piece < n * 16) cp_async16(dst0 + piece * 16, src + piece * 16);
+        if (lane + 32 * i < n * 16) cp_async16(dst + 512 * i, src + 512 * i);
     }
 }
 
@@ -206,13 +215,13 @@ __device__ __forceinline__ void load_action_columns(float (&actc)[2][4], const f
 // The single-warp kernel above needs ~46 KB of shared memory per tile, i.e. four tiles = four warps per SM = one warp per
 // scheduler, and every dependent-instruction latency is exposed.  A backward step has two branches that are independent
 // given the carried gradients and join only at the two cells:
-//     "core" warp: lower prior head, higher posterior + prior heads, the two leaky-integrator cells (owns ddl ddh dul duh dzh)
-//     "mod"  warp: MoPoE-fusion backward, audio and vision heads (receives dzl, returns its contribution to ddl)
+//     "core" warp: higher posterior + prior heads, the two leaky-integrator cells (owns ddl ddh dul duh dzh)
+//     "mod"  warp: MoPoE-fusion backward, audio and vision heads, lower prior head (receives dzl, returns its contribution to ddl)
 // They share the tile's staged inputs and operand images and exchange 3 KB per step through shared memory, ordered by two
 // named barriers (X: mod -> core "my heads are done", Y: core -> mod "dzl of the next step is ready").  Same footprint per
 // tile, twice the warps per SM, and a per-step critical path of (MoPoE + two modality heads) + cells.
-// MMAs are issued by the warp that owns the operands: mod issues {[a|v hid] x [LA|LV], [embed_a|embed_v] x [A1|V1]},
-// core issues {[lp|hp|hq hid] x [LPL|HPL|HQL]} after its heads and {deter x all first layers, cells, biases} at the cells.
+// MMAs are issued by the warp that owns the operands: mod issues {[a|v hid] x [LA|LV], [lp hid] x [LPL], [embed_a|embed_v] x [A1|V1]},
+// core issues {[hp|hq hid] x [HPL|HQL]} after its heads and {deter x all first layers, cells, biases} at the cells.
 // =====================================================================================================================
 namespace fz2 {
 constexpr int CH = fz::CH;
@@ -307,7 +316,9 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
     }
     __syncthreads();
     pack_run<NS>(tb, tid, nthr);
-    const int lane = tid & 31, warp = tid >> 5, tile = warp / WPT, role = warp % WPT;  // role 0 = core, 1 = mod, 2 = aux
+    // the warp index as a BROADCAST value: the compiler then knows tile / role / row0 (and every address derived from them) are
+    // warp-uniform -- uniform registers and uniform branches instead of per-lane integer arithmetic
+    const int lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), tile = warp / WPT, role = warp % WPT;  // role 0 = core, 1 = mod, 2 = aux
     // one tile per CTA (batches of at most one tile per SM, e.g. cfg4's 16 tiles): 128 threads = the tile's three warps + one
     // HELPER warp that only takes part in the CTA-wide steps (weight packing, TMEM zeroing and read-back need four warps)
     const bool active = tile < nthr / (32 * WPT);
@@ -354,14 +365,17 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
     if (active && row0 < p.B) {
         const Rows r = make_rows(row0, p.B, lane);
         const int T = p.T;
-        const __nv_bfloat16* saved = reinterpret_cast<const __nv_bfloat16*>(p.saved);
+        // this lane's 16-byte piece of the tile's saved record of step 0 (tile-blocked: 6656 contiguous bytes per tile-step)
+        const unsigned char* tile_rec =
+            reinterpret_cast<const unsigned char*>(p.saved) + (size_t)(row0 >> 4) * T * (MTRSSM_SAVED_BF16 * 16 * 2) + lane * 16;
         unsigned char* dop = my + fz2::DOP;
         unsigned char* svop = my + fz2::SVOP;
         unsigned char* zop = my + fz2::ZOP;
         unsigned char* dy = my + fz2::DYOP;
         float* xddl = reinterpret_cast<float*>(my + fz2::XDDL);
         float* xdzl = reinterpret_cast<float*>(my + fz2::XDZL);
-        const uint32_t s_dop = smem_u32(dop), s_sv = smem_u32(svop), s_dy = smem_u32(dy), s_ones = smem_u32(zop) + 5 * fz2::CH;
+        const uint32_t s_dop = desc_lo(smem_u32(dop)), s_sv = desc_lo(smem_u32(svop)), s_dy = desc_lo(smem_u32(dy)),
+                       s_ones = desc_lo(smem_u32(zop) + 5 * fz2::CH);  // descriptor low words of the tile's images
         // named barriers of the tile.  X: mod -> core (+ aux) "my dY columns and XDDL are complete"; Y: core -> mod "d stoch_l is in
         // XDZL"; Z (three warps): core -> aux "my dY columns are complete and I am done with the feature-row stage"
         const int bar_x = 1 + WPT * tile, bar_y = 2 + WPT * tile, bar_z = 3 + WPT * tile;
@@ -390,7 +404,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
             FZ_FENCE();
             __syncwarp();
             if (FZ_MMA && lane == 0) {
-                umma_acc(tmem + fz2::T_C, s_dop, s_dy + (fz::Y_L / 8) * fz2::CH, 64);  // buffer 0 holds step 0's [L | H]
+                umma_acc(tmem + fz2::T_C, s_dop, s_dy + desc_off((fz::Y_L / 8) * fz2::CH), 64);  // buffer 0 holds step 0's [L | H]
                 umma_commit(&bars[fz2::BAR_END]);
             }
             FZ_WAIT(&bars[fz2::BAR_END], ph_end);
@@ -399,28 +413,31 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
         if (role == 1) {
             // ============================== mod warp: MoPoE backward + audio / vision heads ===============================
             float* stPRL = reinterpret_cast<float*>(my + fz2::PRL);  // [16][32]: post_l | prior_l, swizzled like PR
+            // (row index x T and the lane's source / destination are fixed for the group: per step one add and one wide multiply-add
+            // per copy instead of a clamp and two 64-bit multiplies)
+            const int prl_c8 = lane & 7, prl_rq = lane >> 3;
+            float* prl_dst = stPRL + prl_rq * 32 + 4 * (prl_c8 ^ (4 * (prl_rq & 1)));
+            const float* prl_src = ((prl_c8 >> 2) ? p.prior_probs_l : p.post_probs_l) + 4 * (prl_c8 & 3);
+            uint32_t prl_row[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) prl_row[j] = (uint32_t)min(row0 + prl_rq + 4 * j, p.B - 1) * (uint32_t)T;
             auto stage_prl = [&](int t) {
                 if (t >= 0) {
-                    const int c8 = lane & 7, rq = lane >> 3;
-                    float* d2 = stPRL + rq * 32 + 4 * (c8 ^ (4 * (rq & 1)));
-                    const float* src = (c8 >> 2) ? p.prior_probs_l : p.post_probs_l;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const size_t idx = (size_t)min(row0 + rq + 4 * j, p.B - 1) * T + t;
-                        cp_async16(d2 + j * 128, src + idx * ldP + 4 * (c8 & 3));
-                    }
+                    for (int j = 0; j < 4; ++j) cp_async16(prl_dst + j * 128, prl_src + (size_t)(prl_row[j] + (uint32_t)t) * ldP);
                 }
             };
                         auto stage_logits = [&](int t) {  // LA, LV: read by registers only, refilled right after the MoPoE math
                 if (t >= 0) {
-                    stage_chunks_tiled(svop + 20 * fz2::CH, saved, 20, 4, row0 >> 4, T, t, lane);
+                    stage_chunks_tiled(svop + 20 * fz2::CH, tile_rec, 20, 4, t, lane);
                 }
                 stage_prl(t);
                 cp_async_commit();
             };
-            auto stage_rest = [&](int t) {  // a / v hiddens: free once this warp's MMAs have completed
+            auto stage_rest = [&](int t) {  // a / v / lp hiddens: free once this warp's MMAs have completed
                 if (t >= 0) {
-                    stage_chunks_tiled(svop + 12 * fz2::CH, saved, 12, 8, row0 >> 4, T, t, lane);
+                    stage_chunks_tiled(svop + 12 * fz2::CH, tile_rec, 12, 8, t, lane);
+                    stage_chunks_tiled(svop, tile_rec, 0, 4, t, lane);  // lp hidden
                 }
                 cp_async_commit();
             };
@@ -434,7 +451,9 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 load_c<8>(e, p.embed_v + jA, p.embed_v + jB, r.t);
                 store_op<8>(e, svop, 32 * 8, r);
             };
-            auto embed_prefetch = [&](int t) {  // lanes 0..15: one 256-byte row of each embedding
+            // lanes 0..15: one 256-byte row of each embedding into L2.  (Per-lane `prefetch.global.L2` of the same lines is 1.7 % SLOWER
+            // at the bench batch although it saves ~260 issue slots per step: profiles/r2_ab_variants.txt)
+            auto embed_prefetch = [&](int t) {
                 if (t >= 0 && lane < 16) {
                     const size_t j = ((size_t)min(row0 + lane, p.B - 1) * T + t) * 64;
                     prefetch_bulk_l2(p.embed_a + j, 256);
@@ -463,28 +482,25 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 __syncwarp();
                 FZ_TS(1);
                 float q[2][4], dzl_pre[2][4], lsa[2][4], lsv[2][4], ra[2][4], rv[2][4];
+                float dlg_lp[2][4];  // d logits of the lower prior head (this warp owns the whole "l" side of the KL term)
                 {
-                    float pp[2][4], dpp[2][4], la[2][4], lv[2][4], mixed[2][4];
+                    float pp[2][4], dpp[2][4], la[2][4], lv[2][4];
                     load_staged<2, true>(q, stPRL, 32, 0, r.g, r.t);
                     load_staged<2, true>(pp, stPRL, 32, 16, r.g, r.t);
                     zero_c<2>(dzl_pre), zero_c<2>(dpp);
                     add_global<2>(dzl_pre, p.d_post_probs_l, iA * 16, iB * 16, r.t);
-                    if (p.d_kl_l != nullptr) {
+                    add_global<2>(dpp, p.d_prior_probs_l, iA * 16, iB * 16, r.t);
+                    add_global<2>(dpp, p.d_prior_stoch_l, iA * 16, iB * 16, r.t);
+                    {   // (the shuffles stay outside the branch: inside it they compile to a guarded collective, ~20 instructions each)
                         const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 0), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 1)};
-                        kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dzl_pre, dpp);  // the prior half (dpp) belongs to the core warp
+                        if (p.d_kl_l != nullptr) kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dzl_pre, dpp);
                     }
+                    softmax_groups_bwd<KL>(pp, dpp, dlg_lp);
                     load_op<2>(la, svop, mts::LA, r.g, r.t);
                     load_op<2>(lv, svop, mts::LV, r.g, r.t);
-                    log_softmax_flat<true>(la, lsa);
-                    log_softmax_flat<true>(lv, lsv);
-                    mopoe_mix<true>(lsa, lsv, mixed, ra, rv);
-#pragma unroll
-                    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            lsa[nt][j] = Math<true>::exp(lsa[nt][j]);  // softmax(la), softmax(lv): all the log-softmax backward needs
-                            lsv[nt][j] = Math<true>::exp(lsv[nt][j]);
-                        }
+                    // lsa / lsv = softmax(la) / softmax(lv) (all the flat log-softmax backward needs), ra / rv = the mixture
+                    // responsibilities, evaluated in the probability domain (frag.cuh)
+                    mopoe_responsibilities_fast(la, lv, lsa, lsv, ra, rv);
                 }
                 __syncwarp();
                 FZ_TS(2);
@@ -501,6 +517,20 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                         eluA[nt][j] = elu_grad_from_out(eluA[nt][j]);
                         eluV[nt][j] = elu_grad_from_out(eluV[nt][j]);
                     }
+                // ---- lower prior head (moved here from the core warp, which is the longest instruction stream of a tile: this warp
+                // waited a third of its time at the hand-over barrier).  It depends on nothing that is carried, so it runs before the
+                // hand-over; its d deter_l joins this warp's contribution (XDDL).  This warp's dY columns (LPL, LP1, LA, A1, LV, V1)
+                // were last read by the end-of-step MMAs of step t+1 (and by its own MMAs, waited for at the end of that step) ------
+                if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
+                float ddl[4][4];
+                zero_c<4>(ddl);
+                {
+                    float hid[4][4];
+                    AFrag<NS, 2> f1;
+                    load_op<4>(hid, svop, mts::LP_HID, r.g, r.t);
+                    head_bwd_op(dlg_lp, wblk<NS>(W, mt::T_LP2), hid, dy, fz::Y_LPL, fz::Y_LP1, f1, r, lane);
+                    gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_LP1), lane);
+                }
                 // ---- the recurrence's critical section: d stoch_l(t) -> ... -> contribution to d deter_l(t) --------------------
                 FZ_TS(3);
                 nbar_sync(bar_y);  // d stoch_l of step t is in XDZL
@@ -537,12 +567,8 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                             }
                     }
                 }
-                // this warp's dY columns (LA, A1, LV, V1) were last read by the core warp's end-of-step MMAs of step t+1
                 FZ_TS(5);
-                if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
                 FZ_TS(6);
-                float ddl[4][4];
-                zero_c<4>(ddl);
                 AFrag<NS, 2> f1a, f1v;
                 if constexpr (PROJ) {
                     head_bwd_elu(dla, wblk<NS>(W, mt::T_A2), eluA, dy, fz::Y_LA, fz::Y_A1, f1a, r, lane, p.d_embed_a + iA * 32, p.d_embed_a + iB * 32);
@@ -560,8 +586,11 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 // ---- off the critical path: this warp's weight-gradient MMAs, the embedding gradients, next step's staging -------
                 __syncwarp();
                 if (FZ_MMA && lane == 0) {
-                    umma_acc(tmem + fz2::T_M, s_sv + 12 * fz2::CH, s_dy + (fz::Y_LA / 8) * fz2::CH, 32);
-                    if constexpr (WPT == 2) umma_acc(tmem + fz2::T_EMB, s_sv + 24 * fz2::CH, s_dy + (fz::Y_A1 / 8) * fz2::CH, 64);
+                    umma_acc(tmem + fz2::T_M, s_sv + desc_off(12 * fz2::CH), s_dy + desc_off((fz::Y_LA / 8) * fz2::CH), 32);
+                    // [lp hid | ..] x [LPL]: the first 16 columns of the T_E tile (rows 32..127 of the window -- hp / hq / a hiddens,
+                    // possibly mid-refill by the core warp -- land in accumulator rows that are never read back)
+                    umma_acc(tmem + fz2::T_E, s_sv, s_dy + desc_off((fz::Y_LPL / 8) * fz2::CH), 16);
+                    if constexpr (WPT == 2) umma_acc(tmem + fz2::T_EMB, s_sv + desc_off(24 * fz2::CH), s_dy + desc_off((fz::Y_A1 / 8) * fz2::CH), 64);
                     umma_commit(&bars[fz2::BAR_M]);
                 }
                 if constexpr (WPT == 2) {  // three warps per tile: the aux warp computes the embedding gradients from the dY image
@@ -594,15 +623,17 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
             float* stFT = reinterpret_cast<float*>(my + fz2::FT);
             float* stPR = reinterpret_cast<float*>(my + fz2::PR) - bst::PR;  // bstage_pr adds bst::PR itself
             uint32_t ph_df = 0, ph_ft = 0, ph_e = 0, ph_end = 0;
-                        auto stage_hid = [&](int t) {  // lp, hp, hq hiddens: free once the E-group MMA has completed
+                        auto stage_hid = [&](int t) {  // hp, hq hiddens: free once the E-group MMA has completed
                 if (t >= 0) {
-                    stage_chunks_tiled(svop, saved, 0, 12, row0 >> 4, T, t, lane);
+                    stage_chunks_tiled(svop + 4 * fz2::CH, tile_rec, 4, 8, t, lane);
                 }
                 cp_async_commit();
             };
             bulk_rows(stDF, bst::DF_LD, reinterpret_cast<const char*>(p.d_feature), 384, bst::DF_BYTES, row0, p.B, T, T - 1, &bars[fz2::BAR_DF], lane);
             if constexpr (WPT == 2)
                 bulk_rows(stFT, bst::DF_LD, reinterpret_cast<const char*>(p.feature), ft_pitch, 384, row0, p.B, T, T - 1, &bars[fz2::BAR_FT], lane);
+            // the four probability tensors of a step (one cp.async group): lane -> chunk column c8 of the rows rq + 4j; as bstage_pr
+            // (mtrssm_common.cuh) with the row offsets, sources and destination hoisted out of the time loop
             bstage_pr<ldP>(stPR, p, row0, T - 1, lane);  // cp.async groups per step, in issue order: PR(t-1) | HID(t-1)
             stage_hid(T - 1);
             const float* dkl_src = (r.t < 2) ? p.d_kl_h : p.d_kl_l;  // quad lanes: 0 kl_h row A, 1 kl_h row B, 2 kl_l row A, 3 kl_l row B
@@ -642,24 +673,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 float actc[2][4];
                 zero_c<2>(actc);
                 if constexpr (WPT == 2) load_action_columns(actc, p.actions, iA + 1, iB + 1, A, t + 1 < T, r);
-                // ---- lower prior head -------------------------------------------------------------------------------------
-                {
-                    float q[2][4], pp[2][4], dq[2][4], dpp[2][4], dlg[2][4];
-                    load_staged<2, true>(q, stPR + bst::PR, 64, 16, r.g, r.t);
-                    load_staged<2, true>(pp, stPR + bst::PR, 64, 48, r.g, r.t);
-                    zero_c<2>(dpp), zero_c<2>(dq);
-                    add_global<2>(dpp, p.d_prior_probs_l, iA * 16, iB * 16, r.t);
-                    add_global<2>(dpp, p.d_prior_stoch_l, iA * 16, iB * 16, r.t);
-                    if (p.d_kl_l != nullptr) {
-                        const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 2), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 3)};
-                        kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dq, dpp);  // the posterior half (dq) belongs to the mod warp
-                    }
-                    AFrag<NS, 2> f1;
-                    softmax_groups_bwd<KL>(pp, dpp, dlg);
-                    load_op<4>(hid, svop, mts::LP_HID, r.g, r.t);
-                    head_bwd_op(dlg, wblk<NS>(W, mt::T_LP2), hid, dy, fz::Y_LPL, fz::Y_LP1, f1, r, lane);
-                    gemm<NS, 2, 4>(ddl, f1, wblk<NS>(W, mt::T_LP1), lane);
-                }
+                // (the lower prior head runs in the mod warp)
                 FZ_TS(2);
                 // ---- higher layer: posterior + prior heads ----------------------------------------------------------------
                 {
@@ -672,9 +686,9 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                     zero_c<2>(dpp);
                     add_global<2>(dpp, p.d_prior_probs_h, iA * 16, iB * 16, r.t);
                     add_global<2>(dpp, p.d_prior_stoch_h, iA * 16, iB * 16, r.t);
-                    if (p.d_kl_h != nullptr) {
+                    {
                         const float dkl[2] = {__shfl_sync(FULL, dkl_cur, (lane & ~3) + 0), __shfl_sync(FULL, dkl_cur, (lane & ~3) + 1)};
-                        kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dzh, dpp);
+                        if (p.d_kl_h != nullptr) kl_rows_bwd<true>(q, pp, dkl, p.kl_wq, p.kl_wp, dzh, dpp);
                     }
                     float dlg[2][4];
                     AFrag<NS, 2> f1;
@@ -689,11 +703,11 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                     gemm<NS, 2, 4>(ddh, f1, wblk<NS>(W, mt::T_HP1), lane);
                 }
                 FZ_TS(3);
-                // second-layer weight gradients of this warp's three heads
+                // second-layer weight gradients of this warp's two heads
                 FZ_FENCE();
                 __syncwarp();
                 if (FZ_MMA && lane == 0) {
-                    umma_acc(tmem + fz2::T_E, s_sv, s_dy + (fz::Y_LPL / 8) * fz2::CH, 48);
+                    umma_acc(tmem + fz2::T_E + 16, s_sv, s_dy + desc_off((fz::Y_HPL / 8) * fz2::CH), 32);  // [.. | hp | hq hid | ..] x [HPL | HQL]
                     umma_commit(&bars[fz2::BAR_E]);
                 }
                 FZ_TS(4);
@@ -788,10 +802,10 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 } else {
                     __syncwarp();
                     if (FZ_MMA && lane == 0) {
-                        umma_acc(tmem + fz2::T_D1, s_dop, s_dy + (fz::Y_HQ1 / 8) * fz2::CH, 160);
-                        if (t < T - 1) umma_acc(tmem + fz2::T_C, s_dop, s_dy + ((fz::Y_L + 64 * ((t + 1) & 1)) / 8) * fz2::CH, 64);
+                        umma_acc(tmem + fz2::T_D1, s_dop, s_dy + desc_off((fz::Y_HQ1 / 8) * fz2::CH), 160);
+                        if (t < T - 1) umma_acc(tmem + fz2::T_C, s_dop, s_dy + desc_off(((fz::Y_L + 64 * ((t + 1) & 1)) / 8) * fz2::CH), 64);
                         umma_acc(tmem + fz2::T_B, s_dy, s_ones, 16);                     // dY columns   0..127
-                        umma_acc(tmem + fz2::T_B + 16, s_dy + 16 * fz2::CH, s_ones, 16);  // dY columns 128..239 (+ junk)
+                        umma_acc(tmem + fz2::T_B + 16, s_dy + desc_off(16 * fz2::CH), s_ones, 16);  // dY columns 128..239 (+ junk)
                         umma_commit(&bars[fz2::BAR_END]);
                     }
                 }
@@ -851,7 +865,9 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
             // ============================== aux warp (WPT == 3): operand images, MMAs, input gradients ======================
             float* stFT = reinterpret_cast<float*>(my + fz2::FT);
             uint32_t ph_ft = 0, ph_end = 0;
-            auto embed_prefetch = [&](int t) {  // lanes 0..15: one 256-byte row of each embedding into L2
+            // lanes 0..15: one 256-byte row of each embedding into L2.  (Per-lane `prefetch.global.L2` of the same lines is 1.7 % SLOWER
+            // at the bench batch although it saves ~260 issue slots per step: profiles/r2_ab_variants.txt)
+            auto embed_prefetch = [&](int t) {
                 if (t >= 0 && lane < 16) {
                     const size_t j = ((size_t)min(row0 + lane, p.B - 1) * T + t) * 64;
                     prefetch_bulk_l2(p.embed_a + j, 256);
@@ -869,12 +885,21 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 load_c<8>(ea, p.embed_a + jA, p.embed_a + jB, r.t);
                 load_c<8>(ev, p.embed_v + jA, p.embed_v + jB, r.t);
             }
+            // [action(t+1) | ones] columns, fetched one step ahead as well (a load next to its use costs a DRAM round trip per step)
+            float actc[2][4];
+            zero_c<2>(actc);
+            load_action_columns(actc, p.actions, 0, 0, A, false, r);  // step T-1 pairs with no action: the ones column only
             for (int t = T - 1; t >= 0; --t) {
                 const size_t iA = (size_t)r.rA * T + t, iB = (size_t)r.rB * T + t;
                 FZ_TS(0);
                 // the MMAs of step t+1 are done with the operand images
                 if (t < T - 1) FZ_WAIT(&bars[fz2::BAR_END], ph_end), ph_end ^= 1;
                 FZ_TS(1);
+                store_op<2>(actc, zop, 32, r);
+                if (t > 0) {  // the action of step t, used by step t-1
+                    zero_c<2>(actc);
+                    load_action_columns(actc, p.actions, iA, iB, A, true, r);
+                }
                 if (emb) {
                     store_op<8>(ea, svop, 24 * 8, r);
                     store_op<8>(ev, svop, 32 * 8, r);
@@ -887,9 +912,7 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 }
                 FZ_TS(2);
                 {   // X operands: bf16 [d_l | d_h | z_l | z_h](t) and [action(t+1) | ones]
-                    float actc[2][4], c4[4][4], c2[2][4];
-                    zero_c<2>(actc);
-                    load_action_columns(actc, p.actions, iA + 1, iB + 1, A, t + 1 < T, r);
+                    float c4[4][4], c2[2][4];
                     mbar_wait(&bars[fz2::BAR_FT], ph_ft), ph_ft ^= 1;  // the feature row of step t has landed
                     load_staged<4, false>(c4, stFT, bst::DF_LD, 48, r.g, r.t);
                     store_op<4>(c4, dop, 0, r);
@@ -899,7 +922,6 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                     store_op<2>(c2, zop, 0, r);
                     load_staged<2, false>(c2, stFT, bst::DF_LD, 32, r.g, r.t);
                     store_op<2>(c2, zop, 16, r);
-                    store_op<2>(actc, zop, 32, r);
                 }
                 FZ_TS(3);
                 // ---- the mod warp's dY columns: embedding gradients d e = dY1 . W1[:, 32:] (mopoe_mmtrssm/core.py:259-260) ------
@@ -926,11 +948,11 @@ __global__ void __launch_bounds__(128 * WPT, 1) mtrssm_bwd_fused2_kernel(const M
                 FZ_FENCE();
                 __syncwarp();
                 if (FZ_MMA && lane == 0) {
-                    if (emb) umma_acc(tmem + fz2::T_EMB, s_sv + 24 * fz2::CH, s_dy + (fz::Y_A1 / 8) * fz2::CH, 64);
-                    umma_acc(tmem + fz2::T_D1, s_dop, s_dy + (fz::Y_HQ1 / 8) * fz2::CH, 160);
-                    if (t < T - 1) umma_acc(tmem + fz2::T_C, s_dop, s_dy + ((fz::Y_L + 64 * ((t + 1) & 1)) / 8) * fz2::CH, 64);
+                    if (emb) umma_acc(tmem + fz2::T_EMB, s_sv + desc_off(24 * fz2::CH), s_dy + desc_off((fz::Y_A1 / 8) * fz2::CH), 64);
+                    umma_acc(tmem + fz2::T_D1, s_dop, s_dy + desc_off((fz::Y_HQ1 / 8) * fz2::CH), 160);
+                    if (t < T - 1) umma_acc(tmem + fz2::T_C, s_dop, s_dy + desc_off(((fz::Y_L + 64 * ((t + 1) & 1)) / 8) * fz2::CH), 64);
                     umma_acc(tmem + fz2::T_B, s_dy, s_ones, 16);                     // dY columns   0..127
-                    umma_acc(tmem + fz2::T_B + 16, s_dy + 16 * fz2::CH, s_ones, 16);  // dY columns 128..239 (+ junk)
+                    umma_acc(tmem + fz2::T_B + 16, s_dy + desc_off(16 * fz2::CH), s_ones, 16);  // dY columns 128..239 (+ junk)
                     umma_commit(&bars[fz2::BAR_END]);
                 }
                 FZ_TS(7);

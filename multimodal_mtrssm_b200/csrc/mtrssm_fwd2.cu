@@ -407,11 +407,8 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                 head2_l2<TILED>(accv, lv, bias + mt::B_V2, wblk<NS>(W, mt::V2), sv, mts::V_HID, r, lane);
                 float q[2][4];
                 {
-                    float lsa[2][4], lsv[2][4], mixed[2][4], zs[2][4];
-                    log_softmax_flat<true>(la, lsa);
-                    log_softmax_flat<true>(lv, lsv);
-                    mopoe_mix<true>(lsa, lsv, mixed, nullptr, nullptr);
-                    softmax_groups<KL, true>(mixed, q);
+                    float zs[2][4];
+                    mopoe_posterior_fast<KL>(la, lv, q);  // probability-domain MoPoE (frag.cuh): q = s / sum_group(s)
                     sample_onehot<KL>(q, stage + stg::U0 + r.g * 8, stage + stg::U0 + (r.g + 8) * 8, zs, lane);
                     AFrag<NS, 1> zlf;
                     to_afrag<NS, 1>(zlf, zs);

@@ -261,11 +261,16 @@ __global__ void __launch_bounds__(128, NS == 1 ? RSSM_MIN_CTAS : 1) mtrssm_fwd_k
         }
         FW_TS(5);
         {
-            float lsa[2][4], lsv[2][4], mixed[2][4], q[2][4], zs[2][4];
-            log_softmax_flat<NS == 1>(la, lsa);
-            log_softmax_flat<NS == 1>(lv, lsv);
-            mopoe_mix<NS == 1>(lsa, lsv, mixed, nullptr, nullptr);
-            softmax_groups<KL, NS == 1>(mixed, q);
+            float q[2][4], zs[2][4];
+            if constexpr (NS == 1) {
+                mopoe_posterior_fast<KL>(la, lv, q);  // probability-domain MoPoE (frag.cuh)
+            } else {
+                float lsa[2][4], lsv[2][4], mixed[2][4];
+                log_softmax_flat<false>(la, lsa);
+                log_softmax_flat<false>(lv, lsv);
+                mopoe_mix<false>(lsa, lsv, mixed, nullptr, nullptr);
+                softmax_groups<KL, false>(mixed, q);
+            }
             store_c<2>(q, p.post_probs_l + iA * 16, p.post_probs_l + iB * 16, r);
             if (STAGED) sample_onehot<KL>(q, stage + stg::U0 + r.g * 8, stage + stg::U0 + (r.g + 8) * 8, zs, lane);
             else sample_onehot<KL>(q, p.u_post_l + iA * CL, p.u_post_l + iB * CL, zs, lane);

@@ -23,7 +23,12 @@ def timeit(fn, n):
 
 
 layouts = (True, False) if "--ab" in sys.argv else (False,) if "--dense" in sys.argv else (True,)
-for B, T, n in ((37888, 30, 20), (16384, 30, 20), (4096, 30, 20), (256, 30, 20), (8, 30, 20), (256, 512, 5), (16, 512, 5)):
+sizes = ((37888, 30, 20), (16384, 30, 20), (4096, 30, 20), (256, 30, 20), (8, 30, 20), (256, 512, 5), (16, 512, 5))
+if "--only-bench" in sys.argv:
+    sizes = ((37888, 30, 3),)
+if "--ab-sizes" in sys.argv:
+    sizes = ((37888, 30, 20), (4096, 30, 20), (256, 512, 5))
+for B, T, n in sizes:
   for grouped in layouts:
     run = DirectMtrssm(B, T, _lib.PRECISION_BF16_FUSED, torch.device("cuda"), prior_sample=prior, grouped=grouped)
     f, b = timeit(run.fwd, n), timeit(run.bwd_fused, n)

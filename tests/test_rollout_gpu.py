@@ -599,6 +599,45 @@ def test_mtrssm_bf16_backward_vs_oracle(ops, precision):
     rep.finish()
 
 
+@pytest.mark.parametrize("precision", [1, 2])
+def test_mtrssm_bf16_extreme_logits_take_the_log_domain_fallback(ops, precision):
+    """The bf16 policies evaluate the MoPoE fusion in the probability domain (frag.cuh: q = s / sum_group(s), s = pa + pv + pa pv)
+    and fall back to the log-domain formulas when a whole group underflows.  With the modality heads' output layers scaled by
+    1000 the flat log-probabilities span hundreds of nats in BOTH modalities, so the fallback runs on most rows: everything must
+    stay finite and normalised, the draws one-hot, the gradients finite, and wherever the fp32 oracle (teacher-forced) is certain
+    about a group (p > 0.999) the kernel must pick the same class."""
+    R, P = ops
+    B, T, dims = 80, 6, H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    big = [k for k in params if ("audio" in k or "vision" in k) and k.endswith("2.weight")]
+    assert len(big) == 2, list(params)
+    for k in big:
+        params[k] = params[k] * 1000.0
+    inp = H.mtrssm_inputs(B, T, dims)
+    up = {k: v for k, v in mtrssm_upstream(B, T, dims).items()}
+    got, w, x = run_mtrssm(R, P, params, inp, dims, precision=precision, grad=True, upstream=up)
+    for k, v in got.items():
+        assert bool(torch.isfinite(v).all()), k
+    q = got["post_probs_l"].detach()
+    s = q.sum(-1)
+    assert torch.allclose(s, torch.ones_like(s), atol=2e-3)
+    zl = got["feature"].detach()[..., 80:].reshape(B, T, dims["CL"], dims["KL"])
+    assert bool(((zl == 0) | (zl == 1)).all()) and bool((zl.sum(-1) == 1).all())
+    for k in MT_GRAD_IN:
+        assert bool(torch.isfinite(x[k].grad).all()), k
+    for k in w:
+        assert w[k].grad is None or bool(torch.isfinite(w[k].grad).all()), k
+    f = got["feature"].detach().cpu()
+    idx_h = f[..., 32:48].reshape(B, T, dims["CH"], dims["KH"]).argmax(-1)
+    idx_l = f[..., 80:].reshape(B, T, dims["CL"], dims["KL"]).argmax(-1)
+    want, _, _ = oracle_mtrssm(params, inp, dims, forced=(idx_l, idx_h))
+    ref = want["post_probs_l"].reshape(B, T, dims["CL"], dims["KL"])
+    sure = ref.amax(-1) > 0.999
+    assert float(sure.float().mean()) > 0.5  # the test really is in the extreme regime
+    agree = (q.cpu().reshape(B, T, dims["CL"], dims["KL"]).argmax(-1) == ref.argmax(-1))[sure]
+    assert float(agree.float().mean()) > 0.97, float(agree.float().mean())
+
+
 # ---------------------------------------------------------------------------------------------------
 # size-independent properties at benchmark scale, error behaviour
 # ---------------------------------------------------------------------------------------------------
