@@ -49,18 +49,31 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // splits (x0,x1) into NS bf16x2 words: out[0]=hi, out[1]=mid, out[2]=lo
 template <int NS>
 __device__ __forceinline__ void split_pack(float x0, float x1, uint32_t (&out)[NS]) {
-    __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-    {
+    if constexpr (NS == 3) {
+#ifdef RSSM_SPLIT_RN  // round-to-nearest split (first version): four float->bf16 conversions on the quarter-rate XU pipe per pair
+        __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
         __nv_bfloat162 v(h0, h1);
         out[0] = *reinterpret_cast<uint32_t*>(&v);
-    }
-    if constexpr (NS == 3) {
         float r0 = x0 - __bfloat162float(h0), r1 = x1 - __bfloat162float(h1);
         __nv_bfloat16 m0 = __float2bfloat16_rn(r0), m1 = __float2bfloat16_rn(r1);
         float s0 = r0 - __bfloat162float(m0), s1 = r1 - __bfloat162float(m1);
         __nv_bfloat162 vm(m0, m1);
         out[1] = *reinterpret_cast<uint32_t*>(&vm);
         out[2] = pack_bf16(s0, s1);
+#else
+        // EXACT split by truncation: hi = the top 16 bits of x (8 significant bits), mid = the top 16 bits of x - hi, lo = the rest
+        // (<= 8 significant bits, so it is a bf16 as it stands): x = hi + mid + lo bit for bit, and the whole split is integer
+        // masks, two subtractions and three byte permutes per pair
+        const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
+        const float r0 = x0 - __uint_as_float(u0 & 0xffff0000u), r1 = x1 - __uint_as_float(u1 & 0xffff0000u);
+        const uint32_t v0 = __float_as_uint(r0), v1 = __float_as_uint(r1);
+        const float s0 = r0 - __uint_as_float(v0 & 0xffff0000u), s1 = r1 - __uint_as_float(v1 & 0xffff0000u);
+        out[0] = __byte_perm(u0, u1, 0x7632);  // (low half, high half) = (upper 16 bits of the first, of the second value)
+        out[1] = __byte_perm(v0, v1, 0x7632);
+        out[2] = __byte_perm(__float_as_uint(s0), __float_as_uint(s1), 0x7632);
+#endif
+    } else {
+        out[0] = pack_bf16(x0, x1);
     }
 }
 
@@ -574,14 +587,30 @@ struct Math {
 template <bool FAST>
 struct MathUnused {
 #endif
-    // FAST: single MUFU ops with flush-to-zero (no denormal guard code around them)
+    // FAST: single MUFU ops with flush-to-zero (no denormal guard code around them).
+    // !FAST (fp32-parity policy): fp32-accurate to a few ulp, but SHORT.  The libm calls (expf 25, logf 30, tanhf 35, expm1f 30, IEEE
+    // division 10 instructions, each inlined ~250 times per step) made the one-warp kernels 11 k instructions = 176 KB of code
+    // per step against a 32 KB instruction cache: ncu showed 55 % of the fp32 forward's stall cycles as instruction fetch.  The
+    // MUFU units are accurate to 2^-22 relative (ex2, lg2) / 1 ulp (rcp); what libm adds is argument handling, done here by a
+    // compensated product (exp), a Newton step (division) and short series near zero (tanh, expm1).  -DRSSM_LIBM restores libm.
+    static __device__ __forceinline__ float mufu_ex2(float x) {
+        float y;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    }
     static __device__ __forceinline__ float exp(float x) {
         if constexpr (FAST) {
-            float y;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
-            return y;
+            return mufu_ex2(x * 1.4426950408889634f);
         } else {
+#ifdef RSSM_LIBM
             return expf(x);
+#else
+            // x log2(e) in two parts: the rounding error of the leading product is recovered by an FMA, the tail of the constant added
+            const float t = x * 1.4426950216293335f;
+            const float e = fmaf(x, 1.4426950216293335f, -t) + x * 1.9259629911266175e-8f;
+            const float y = mufu_ex2(t);
+            return fmaf(y, e * 0.6931471805599453f, y);  // 2^e = 1 + e ln 2 + O(e^2), |e| < 2^-22 |t|
+#endif
         }
     }
     static __device__ __forceinline__ float log(float x) {
@@ -590,7 +619,13 @@ struct MathUnused {
             asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
             return y * 0.6931471805599453f;
         } else {
+#ifdef RSSM_LIBM
             return logf(x);
+#else
+            float y;
+            asm("lg2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+            return y * 0.6931471805599453f;
+#endif
         }
     }
     static __device__ __forceinline__ float div(float a, float b) {
@@ -599,7 +634,14 @@ struct MathUnused {
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(b));
             return a * y;
         } else {
+#ifdef RSSM_LIBM
             return a / b;
+#else
+            float r;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+            r = fmaf(r, fmaf(-b, r, 1.f), r);  // one Newton step: < 1 ulp (the operands here are sums of exponentials, never denormal)
+            return a * r;
+#endif
         }
     }
     static __device__ __forceinline__ float tanh(float x) {
@@ -608,11 +650,32 @@ struct MathUnused {
             asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
             return y;
         } else {
+#ifdef RSSM_LIBM
             return tanhf(x);
+#else
+            const float ax = fabsf(x), x2 = x * x;
+            const float e = exp(-2.f * ax);
+            const float big = div(1.f - e, 1.f + e);                                       // cancels for small |x| ...
+            const float small = ax * fmaf(x2, fmaf(x2, 0.13333333f, -0.33333334f), 1.f);   // ... where the series is exact to 5e-8 relative
+            return copysignf(ax < 0.1f ? small : big, x);
+#endif
         }
     }
     static __device__ __forceinline__ float sigmoid(float x) { return div(1.f, 1.f + exp(-x)); }
-    static __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : (FAST ? exp(x) - 1.f : expm1f(x)); }
+    static __device__ __forceinline__ float elu(float x) {
+        if constexpr (FAST) {
+            return x > 0.f ? x : exp(x) - 1.f;
+        } else {
+#ifdef RSSM_LIBM
+            return x > 0.f ? x : expm1f(x);
+#else
+            // exp(x) - 1 cancels near zero: Taylor series to x^5 there (1.4e-9 absolute at |x| = 0.1)
+            const float series = x * fmaf(x, fmaf(x, fmaf(x, fmaf(x, 8.3333333e-3f, 4.1666668e-2f), 0.16666667f), 0.5f), 1.f);
+            const float m = x > -0.1f ? series : exp(x) - 1.f;
+            return x > 0.f ? x : m;
+#endif
+        }
+    }
 };
 // d ELU / d pre, from the POST-activation value y: y > 0 -> 1, else exp(x) = y + 1
 __device__ __forceinline__ float elu_grad_from_out(float y) { return fminf(y, 0.f) + 1.f; }

@@ -244,15 +244,18 @@ template <int NS>
 __device__ __forceinline__ void stage_convert(__nv_bfloat16* sm, const float* raw, int stride, int plane, int raw_cpr,
                                               const uint8_t* __restrict__ chunk_of_raw, int tid) {
     constexpr int ROWS = rows_of(NS);
-    for (int i = tid; i < ROWS * raw_cpr; i += THREADS) {
-        const int row = i / raw_cpr, k = i - row * raw_cpr;
-        const float4 v = *reinterpret_cast<const float4*>(raw + (size_t)i * 4);
-        uint32_t lo[NS], hi[NS];
-        split_pack<NS>(v.x, v.y, lo);
-        split_pack<NS>(v.z, v.w, hi);
-        const int off = row * stride + chunk_of_raw[k] * 4;
+    // a warp walks whole rows, its lanes the row's chunks: no integer division by the run-time chunk count (it was a quarter of
+    // the kernel's instructions, ncu)
+    for (int row = tid >> 5; row < ROWS; row += THREADS / 32) {
+        for (int k = tid & 31; k < raw_cpr; k += 32) {
+            const float4 v = *reinterpret_cast<const float4*>(raw + ((size_t)row * raw_cpr + k) * 4);
+            uint32_t lo[NS], hi[NS];
+            split_pack<NS>(v.x, v.y, lo);
+            split_pack<NS>(v.z, v.w, hi);
+            const int off = row * stride + chunk_of_raw[k] * 4;
 #pragma unroll
-        for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(sm + (size_t)s * plane + off) = make_uint2(lo[s], hi[s]);
+            for (int s = 0; s < NS; ++s) *reinterpret_cast<uint2*>(sm + (size_t)s * plane + off) = make_uint2(lo[s], hi[s]);
+        }
     }
 }
 
