@@ -298,6 +298,26 @@ __global__ void __launch_bounds__(THREADS, NS == 1 ? 2 : 1) wgrad_mma_kernel(con
     for (int i = 0; i < MAX_TILES; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
 
     const int nblocks = (a.B * a.T + ROWS - 1) / ROWS;
+    if constexpr (NS == 3) {
+        // fp32 records: every segment lands in the raw area and is converted into the operand planes, so the raw area is free as
+        // soon as the conversion is done -- the NEXT block's copies are issued there and stream in under this block's MMAs
+        int blk = blockIdx.x;
+        if (blk < nblocks) stage_issue<NS>(sm, raw, stride, raw_cpr, segs, seg_slot, a.nseg, a.B, a.T, blk * ROWS, &bar, tid);
+        for (; blk < nblocks; blk += gridDim.x) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            mbar_wait(&bar, phase);
+            phase ^= 1;
+            __syncthreads();
+            stage_convert<NS>(sm, raw, stride, plane, raw_cpr, chunk_of_raw, tid);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our reads of the raw area before the next bulk writes
+            __syncthreads();
+            if (blk + (int)gridDim.x < nblocks)
+                stage_issue<NS>(sm, raw, stride, raw_cpr, segs, seg_slot, a.nseg, a.B, a.T, (blk + (int)gridDim.x) * ROWS, &bar, tid);
+            if (MODEL == 0) program_mtrssm<NS, 0>(acc, sm, stride, plane, a.out, warp, lane);
+            else program_mrssm<NS, 0>(acc, sm, stride, plane, a.out, warp, lane);
+            __syncthreads();  // the planes may be rewritten
+        }
+    } else
     for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         stage_issue<NS>(sm, raw, stride, raw_cpr, segs, seg_slot, a.nseg, a.B, a.T, blk * ROWS, &bar, tid);
         asm volatile("cp.async.wait_group 0;" ::: "memory");
