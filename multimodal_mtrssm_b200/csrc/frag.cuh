@@ -120,41 +120,65 @@ __device__ __forceinline__ void to_afrag(AFrag<NS, KT>& a, const float (&c)[2 * 
 }
 
 // acc[NT tiles] += A[16 x 16KT] * B, B = packed weight block in shared memory laid out
-// [split][kt][nt][lane] as uint2 (see pack_weight)
-template <int NS, int KT, int NT>
+// [split][kt][nt / 2][lane][nt & 1] as uint2 (bfrag_slot): one 16-byte load per n-tile pair
+template <int NS, int KT, int NT, bool PAIRED = true>
 __device__ __forceinline__ void gemm(float (&acc)[NT][4], const AFrag<NS, KT>& a, const uint2* __restrict__ w, int lane) {
-    constexpr int SPLIT = KT * NT * 32;
+    static_assert(NT % 2 == 0, "B fragments are stored in n-tile pairs");
+    if constexpr (!PAIRED) {
+        static_assert(NS == 1, "the unpaired layout is used by the bf16 two-warp forward only");
+#pragma unroll
+        for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_bf16(acc[nt], a.r[0][kt], w[(kt * NT + nt) * 32 + lane]);
+        return;
+    }
+    constexpr int SPLIT = KT * NT * 16;  // uint4 units per split plane
+    const uint4* __restrict__ w4 = reinterpret_cast<const uint4*>(w);
 #pragma unroll
     for (int kt = 0; kt < KT; ++kt) {
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const uint2* p = w + (kt * NT + nt) * 32 + lane;
-            const uint2 bh = p[0];
+        for (int np = 0; np < NT / 2; ++np) {
+            const uint4* p = w4 + (kt * (NT / 2) + np) * 32 + lane;
+            const uint4 bh = p[0];
             if constexpr (NS == 1) {
-                mma_bf16(acc[nt], a.r[0][kt], bh);
+                mma_bf16(acc[2 * np], a.r[0][kt], make_uint2(bh.x, bh.y));
+                mma_bf16(acc[2 * np + 1], a.r[0][kt], make_uint2(bh.z, bh.w));
             } else {
-                const uint2 bm = p[SPLIT], bl = p[2 * SPLIT];
-                mma_bf16(acc[nt], a.r[0][kt], bl);  // smallest terms first
-                mma_bf16(acc[nt], a.r[2][kt], bh);
-                mma_bf16(acc[nt], a.r[1][kt], bm);
-                mma_bf16(acc[nt], a.r[0][kt], bm);
-                mma_bf16(acc[nt], a.r[1][kt], bh);
-                mma_bf16(acc[nt], a.r[0][kt], bh);
+                const uint4 bm = p[SPLIT], bl = p[2 * SPLIT];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint2 xh = h == 0 ? make_uint2(bh.x, bh.y) : make_uint2(bh.z, bh.w);
+                    const uint2 xm = h == 0 ? make_uint2(bm.x, bm.y) : make_uint2(bm.z, bm.w);
+                    const uint2 xl = h == 0 ? make_uint2(bl.x, bl.y) : make_uint2(bl.z, bl.w);
+                    mma_bf16(acc[2 * np + h], a.r[0][kt], xl);  // smallest terms first
+                    mma_bf16(acc[2 * np + h], a.r[2][kt], xh);
+                    mma_bf16(acc[2 * np + h], a.r[1][kt], xm);
+                    mma_bf16(acc[2 * np + h], a.r[0][kt], xm);
+                    mma_bf16(acc[2 * np + h], a.r[1][kt], xh);
+                    mma_bf16(acc[2 * np + h], a.r[0][kt], xh);
+                }
             }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// weight packing (cooperative, whole CTA, once per launch)
-// ------------------------------------------------------------------------------------------
 // Packs B[k][n] for k in [0,16KT), n in [0,8NT):
 //   TRANS == false:  B[k][n] = W[(n0+n)*ld + k0 + k]   (y = x W^T, forward; PyTorch [out,in] weight)
 //   TRANS == true :  B[k][n] = W[(n0+k)*ld + k0 + n]   (dx = dy W,  data gradient)
-// with zero padding outside k < kvalid / n < nvalid.  dst layout [split][kt][nt][lane] uint2.
+// with zero padding outside k < kvalid / n < nvalid.  dst layout [split][kt][nt / 2][lane][nt & 1] uint2 (bfrag_slot).
 // logical column of MMA C/B column position q (0..7) of n-tile nt, and of A/B k position kp (0..15) of k-tile kt
 __host__ __device__ constexpr int lcol(int nt, int q) { return 16 * (nt >> 1) + 4 * (q >> 1) + 2 * (nt & 1) + (q & 1); }
 __host__ __device__ constexpr int lk(int kt, int kp) { return 16 * kt + 4 * ((kp & 7) >> 1) + 2 * (kp >> 3) + (kp & 1); }
+
+// uint2 slot of the B fragment of (k-tile kt, n-tile nt) for `lane` inside a packed block: the fragments of an n-tile PAIR sit side
+// by side, so gemm() fetches both with one 16-byte shared-memory load (half the LDS instructions in the MIO queue of kernels whose
+// stall profile is short-scoreboard + MIO throttle; same bytes)
+// (paired = false: one fragment per 8-byte load, [kt][nt][lane] -- lower latency to the first MMA of a short dependent chain: the
+// two-warp forward uses it when a CTA runs a single tile, where pairing measured 4 % slower per step and 3 % faster at the bench batch)
+__host__ __device__ constexpr int bfrag_slot(int kt, int nt, int NT, int lane, bool paired = true) {
+    return paired ? ((kt * (NT >> 1) + (nt >> 1)) * 32 + lane) * 2 + (nt & 1) : (kt * NT + nt) * 32 + lane;
+}
 
 template <int NS, bool TRANS>
 __device__ __forceinline__ void pack_weight(uint2* __restrict__ dst, const float* __restrict__ W, int ld, int n0, int k0,
@@ -177,7 +201,7 @@ __device__ __forceinline__ void pack_weight(uint2* __restrict__ dst, const float
         split_pack<NS>(w[0], w[1], lo);
         split_pack<NS>(w[2], w[3], hi);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) dst[s * total + idx] = make_uint2(lo[s], hi[s]);
+        for (int s = 0; s < NS; ++s) dst[s * total + bfrag_slot(kt, nt, NT, lane)] = make_uint2(lo[s], hi[s]);
     }
 }
 
@@ -193,6 +217,7 @@ struct PackDesc {
     int ld;
     short n0, k0, kvalid, nvalid;
     unsigned char KT, NT, trans, tile0;  // tile0: first flattened tile of this block
+    unsigned char paired;                // B fragments in n-tile pairs (bfrag_slot)
 };
 struct PackTable {
     int nblocks, ntiles;
@@ -202,11 +227,11 @@ struct PackTable {
 
 // called by ONE thread per block; same arguments as pack_weight
 __device__ __forceinline__ void pack_add(PackTable& tb, bool trans, uint2* dst, const float* W, int ld, int n0, int k0, int kvalid,
-                                         int nvalid, int KT, int NT) {
+                                         int nvalid, int KT, int NT, bool paired = true) {
     const int b = tb.nblocks++;
     PackDesc& d = tb.d[b];
     d.dst = dst, d.W = W, d.ld = ld, d.n0 = (short)n0, d.k0 = (short)k0, d.kvalid = (short)kvalid, d.nvalid = (short)nvalid;
-    d.KT = (unsigned char)KT, d.NT = (unsigned char)NT, d.trans = trans ? 1 : 0, d.tile0 = (unsigned char)tb.ntiles;
+    d.KT = (unsigned char)KT, d.NT = (unsigned char)NT, d.trans = trans ? 1 : 0, d.tile0 = (unsigned char)tb.ntiles, d.paired = paired ? 1 : 0;
     for (int t = 0; t < KT * NT; ++t) tb.tile2blk[tb.ntiles + t] = (unsigned char)b;
     tb.ntiles += KT * NT;
 }
@@ -233,7 +258,7 @@ __device__ __forceinline__ void pack_run(const PackTable& tb, int tid, int nthre
                 const int g = lane >> 2, t = lane & 3;
                 const int n = lcol(nt, g);
                 total[u] = d.KT * d.NT * 32;
-                out[u] = d.dst + tile * 32 + lane;
+                out[u] = d.dst + bfrag_slot(kt, nt, d.NT, lane, d.paired != 0);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int k = lk(kt, 2 * t + (j & 1) + ((j >> 1) << 3));

@@ -146,7 +146,7 @@ __device__ __forceinline__ void store_rec_dst(const float (&c)[NT][4], const Rec
 }
 
 // hidden -> ELU -> (saved) -> logits, as head_l2 of mtrssm_kernels.cu (NS = 1)
-template <bool TILED>
+template <bool TILED, bool PAIRED>
 __device__ __forceinline__ void head2_l2(float (&acc)[4][4], float (&logits)[2][4], const float* bias2, const uint2* w2, const RecDst& sv,
                                          int sv_off, const Rows& r, int lane) {
     map_c<4>(acc, EluOp<true>{});
@@ -154,14 +154,15 @@ __device__ __forceinline__ void head2_l2(float (&acc)[4][4], float (&logits)[2][
     AFrag<1, 2> f1;
     to_afrag<1, 2>(f1, acc);
     init_bias<2>(logits, bias2, r.t);
-    gemm<1, 2, 2>(logits, f1, w2, lane);
+    gemm<1, 2, 2, PAIRED>(logits, f1, w2, lane);
 }
 
 // blockDim.x = 64 * (tiles per CTA), 1 .. 8 tiles: small batches run few tiles per CTA to reach more SMs
 // LAYOUT: 0 = row-layout record, dense outputs (bf16 two-kernel policy); 1 = tile-blocked record, dense outputs; 2 = tile-blocked
 // record, GROUPED outputs (one 256-float row per (b,t), RssmMtrssmOutputs.ld_*).  The pitches are compile-time constants: runtime
 // pitches cost 3-4% on the latency-bound one-tile rollouts (64-bit IMADs in front of every store; profiles/r2_p_grouped_rows_ab.txt)
-template <int KL, int KH, int LAYOUT>
+// PAIRED: B fragments fetched in n-tile pairs (frag.cuh, bfrag_slot): faster when several tiles share an SM, slower on a lone tile's chain
+template <int KL, int KH, int LAYOUT, bool PAIRED>
 __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs p) {
     constexpr bool TILED = LAYOUT >= 1, GROUPED = LAYOUT == 2;
     constexpr int NS = 1;
@@ -176,25 +177,25 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
         using namespace mt;
         const int ldin = A + 32;
         tb.nblocks = tb.ntiles = 0;
-        pack_add(tb, false, wblk<NS>(W, L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4);
-        pack_add(tb, false, wblk<NS>(W, L_IN_ZL), p.w.l_in_w, ldin, 0, A, 16, 32, 1, 4);
-        pack_add(tb, false, wblk<NS>(W, L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 16, 32, 1, 4);
-        pack_add(tb, false, wblk<NS>(W, L_IN_A), p.w.l_in_w, ldin, 0, 0, A, 32, 1, 4);
-        pack_add(tb, false, wblk<NS>(W, H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4);
-        pack_add(tb, false, wblk<NS>(W, H_IN), p.w.h_in_w, 16, 0, 0, 16, 32, 1, 4);
-        pack_add(tb, false, wblk<NS>(W, LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4);
-        pack_add(tb, false, wblk<NS>(W, LP2), p.w.lp_w2, 32, 0, 0, 32, 16, 2, 2);
-        pack_add(tb, false, wblk<NS>(W, HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4);
-        pack_add(tb, false, wblk<NS>(W, HP2), p.w.hp_w2, 32, 0, 0, 32, 16, 2, 2);
-        pack_add(tb, false, wblk<NS>(W, HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4);
-        pack_add(tb, false, wblk<NS>(W, HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4);
-        pack_add(tb, false, wblk<NS>(W, HQ2), p.w.hq_w2, 32, 0, 0, 32, 16, 2, 2);
-        pack_add(tb, false, wblk<NS>(W, A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4);
-        pack_add(tb, false, wblk<NS>(W, A1E), p.w.au_w1, 96, 0, 32, 64, 32, 4, 4);
-        pack_add(tb, false, wblk<NS>(W, A2), p.w.au_w2, 32, 0, 0, 32, 16, 2, 2);
-        pack_add(tb, false, wblk<NS>(W, V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4);
-        pack_add(tb, false, wblk<NS>(W, V1E), p.w.vi_w1, 96, 0, 32, 64, 32, 4, 4);
-        pack_add(tb, false, wblk<NS>(W, V2), p.w.vi_w2, 32, 0, 0, 32, 16, 2, 2);
+        pack_add(tb, false, wblk<NS>(W, L_D2H), p.w.l_d2h_w, 32, 0, 0, 32, 32, 2, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, L_IN_ZL), p.w.l_in_w, ldin, 0, A, 16, 32, 1, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, L_IN_ZH), p.w.l_in_w, ldin, 0, A + 16, 16, 32, 1, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, L_IN_A), p.w.l_in_w, ldin, 0, 0, A, 32, 1, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, H_D2H), p.w.h_d2h_w, 32, 0, 0, 32, 32, 2, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, H_IN), p.w.h_in_w, 16, 0, 0, 16, 32, 1, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, LP1), p.w.lp_w1, 32, 0, 0, 32, 32, 2, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, LP2), p.w.lp_w2, 32, 0, 0, 32, 16, 2, 2, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, HP1), p.w.hp_w1, 32, 0, 0, 32, 32, 2, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, HP2), p.w.hp_w2, 32, 0, 0, 32, 16, 2, 2, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, HQ1L), p.w.hq_w1, 64, 0, 0, 32, 32, 2, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, HQ1H), p.w.hq_w1, 64, 0, 32, 32, 32, 2, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, HQ2), p.w.hq_w2, 32, 0, 0, 32, 16, 2, 2, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, A1H), p.w.au_w1, 96, 0, 0, 32, 32, 2, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, A1E), p.w.au_w1, 96, 0, 32, 64, 32, 4, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, A2), p.w.au_w2, 32, 0, 0, 32, 16, 2, 2, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, V1H), p.w.vi_w1, 96, 0, 0, 32, 32, 2, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, V1E), p.w.vi_w1, 96, 0, 32, 64, 32, 4, 4, PAIRED);
+        pack_add(tb, false, wblk<NS>(W, V2), p.w.vi_w2, 32, 0, 0, 32, 16, 2, 2, PAIRED);
     }
     {  // the biases, while thread 0 fills the table
         using namespace mt;
@@ -283,18 +284,18 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                 load_a_staged_act<NS>(fa, stage + stg::ACT, r.g, r.t);
                 // everything of the two cells that does not need z_l(t-1) ...
                 init_bias<4>(pl, bias + mt::B_L, r.t);
-                gemm<NS, 2, 4>(pl, dlf, wblk<NS>(W, mt::L_D2H), lane);
+                gemm<NS, 2, 4, PAIRED>(pl, dlf, wblk<NS>(W, mt::L_D2H), lane);
                 init_bias<4>(ph, bias + mt::B_H, r.t);
-                gemm<NS, 2, 4>(ph, dhf, wblk<NS>(W, mt::H_D2H), lane);
+                gemm<NS, 2, 4, PAIRED>(ph, dhf, wblk<NS>(W, mt::H_D2H), lane);
                 if (t > 0) {  // ... then z_l of the previous step from the obs warp
                     pair_sync(bar_z);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) zlf.r[0][0][i] = xz[i * 32 + lane];
                 }
-                gemm<NS, 1, 4>(pl, zlf, wblk<NS>(W, mt::L_IN_ZL), lane);
-                gemm<NS, 1, 4>(pl, zhf, wblk<NS>(W, mt::L_IN_ZH), lane);
-                gemm<NS, 1, 4>(pl, fa, wblk<NS>(W, mt::L_IN_A), lane);
-                gemm<NS, 1, 4>(ph, zhf, wblk<NS>(W, mt::H_IN), lane);
+                gemm<NS, 1, 4, PAIRED>(pl, zlf, wblk<NS>(W, mt::L_IN_ZL), lane);
+                gemm<NS, 1, 4, PAIRED>(pl, zhf, wblk<NS>(W, mt::L_IN_ZH), lane);
+                gemm<NS, 1, 4, PAIRED>(pl, fa, wblk<NS>(W, mt::L_IN_A), lane);
+                gemm<NS, 1, 4, PAIRED>(ph, zhf, wblk<NS>(W, mt::H_IN), lane);
                 float dl[4][4], dh[4][4];
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt)
@@ -326,8 +327,8 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                 {
                     float acc[4][4], lg[2][4];
                     init_bias<4>(acc, bias + mt::B_HP1, r.t);
-                    gemm<NS, 2, 4>(acc, dhf, wblk<NS>(W, mt::HP1), lane);
-                    head2_l2<TILED>(acc, lg, bias + mt::B_HP2, wblk<NS>(W, mt::HP2), sv, mts::HP_HID, r, lane);
+                    gemm<NS, 2, 4, PAIRED>(acc, dhf, wblk<NS>(W, mt::HP1), lane);
+                    head2_l2<TILED, PAIRED>(acc, lg, bias + mt::B_HP2, wblk<NS>(W, mt::HP2), sv, mts::HP_HID, r, lane);
                     softmax_groups<KH, true>(lg, pph);
                     store_c<2>(pph, p.prior_probs_h + iA * ldP, p.prior_probs_h + iB * ldP, r);
                 }
@@ -341,9 +342,9 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                 {
                     float acc[4][4], lg[2][4], q[2][4], zs[2][4];
                     init_bias<4>(acc, bias + mt::B_HQ1, r.t);
-                    gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, mt::HQ1L), lane);
-                    gemm<NS, 2, 4>(acc, dhf, wblk<NS>(W, mt::HQ1H), lane);
-                    head2_l2<TILED>(acc, lg, bias + mt::B_HQ2, wblk<NS>(W, mt::HQ2), sv, mts::HQ_HID, r, lane);
+                    gemm<NS, 2, 4, PAIRED>(acc, dlf, wblk<NS>(W, mt::HQ1L), lane);
+                    gemm<NS, 2, 4, PAIRED>(acc, dhf, wblk<NS>(W, mt::HQ1H), lane);
+                    head2_l2<TILED, PAIRED>(acc, lg, bias + mt::B_HQ2, wblk<NS>(W, mt::HQ2), sv, mts::HQ_HID, r, lane);
                     softmax_groups<KH, true>(lg, q);
                     store_c<2>(q, p.post_probs_h + iA * ldP, p.post_probs_h + iB * ldP, r);
                     sample_onehot<KH>(q, stage + stg::U1 + r.g * 8, stage + stg::U1 + (r.g + 8) * 8, zs, lane);
@@ -389,9 +390,9 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                 } else {
                     AFrag<NS, 4> fe;
                     load_a_staged64<NS>(fe, stage + stg::EA, r.g, r.t);
-                    gemm<NS, 4, 4>(acca, fe, wblk<NS>(W, mt::A1E), lane);
+                    gemm<NS, 4, 4, PAIRED>(acca, fe, wblk<NS>(W, mt::A1E), lane);
                     load_a_staged64<NS>(fe, stage + stg::EV, r.g, r.t);
-                    gemm<NS, 4, 4>(accv, fe, wblk<NS>(W, mt::V1E), lane);
+                    gemm<NS, 4, 4, PAIRED>(accv, fe, wblk<NS>(W, mt::V1E), lane);
                 }
                 AFrag<NS, 2> dlf;
                 pair_sync(bar_d);  // d_l(t) is in XD
@@ -401,10 +402,10 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                     for (int i = 0; i < 4; ++i) dlf.r[0][kt][i] = xd[(kt * 4 + i) * 32 + lane];
                 // ---- lower posterior: modality heads on d_l (:422-433), MoPoE fusion (:436-455), sample (:456) ----------
                 float la[2][4], lv[2][4];
-                gemm<NS, 2, 4>(acca, dlf, wblk<NS>(W, mt::A1H), lane);
-                head2_l2<TILED>(acca, la, bias + mt::B_A2, wblk<NS>(W, mt::A2), sv, mts::A_HID, r, lane);
-                gemm<NS, 2, 4>(accv, dlf, wblk<NS>(W, mt::V1H), lane);
-                head2_l2<TILED>(accv, lv, bias + mt::B_V2, wblk<NS>(W, mt::V2), sv, mts::V_HID, r, lane);
+                gemm<NS, 2, 4, PAIRED>(acca, dlf, wblk<NS>(W, mt::A1H), lane);
+                head2_l2<TILED, PAIRED>(acca, la, bias + mt::B_A2, wblk<NS>(W, mt::A2), sv, mts::A_HID, r, lane);
+                gemm<NS, 2, 4, PAIRED>(accv, dlf, wblk<NS>(W, mt::V1H), lane);
+                head2_l2<TILED, PAIRED>(accv, lv, bias + mt::B_V2, wblk<NS>(W, mt::V2), sv, mts::V_HID, r, lane);
                 float q[2][4];
                 {
                     float zs[2][4];
@@ -427,8 +428,8 @@ __global__ void __launch_bounds__(512, 1) mtrssm_fwd2_kernel(const MtrssmFwdArgs
                 {
                     float acc[4][4], lg[2][4];
                     init_bias<4>(acc, bias + mt::B_LP1, r.t);
-                    gemm<NS, 2, 4>(acc, dlf, wblk<NS>(W, mt::LP1), lane);
-                    head2_l2<TILED>(acc, lg, bias + mt::B_LP2, wblk<NS>(W, mt::LP2), sv, mts::LP_HID, r, lane);
+                    gemm<NS, 2, 4, PAIRED>(acc, dlf, wblk<NS>(W, mt::LP1), lane);
+                    head2_l2<TILED, PAIRED>(acc, lg, bias + mt::B_LP2, wblk<NS>(W, mt::LP2), sv, mts::LP_HID, r, lane);
                     softmax_groups<KL, true>(lg, ppl);
                     store_c<2>(ppl, p.prior_probs_l + iA * ldP, p.prior_probs_l + iB * ldP, r);
                 }
@@ -461,7 +462,10 @@ static cudaError_t launch_fwd2_k(const MtrssmFwdArgs& a, cudaStream_t s) {
     while (tpc < 8 && (ntiles + tpc - 1) / tpc > sms) tpc *= 2;
     const int groups = (ntiles + tpc - 1) / tpc;
     const size_t smem = (size_t)mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float) + (size_t)tpc * f2::TILE_BYTES;
-    auto kernel = !a.rec_tiled ? mtrssm_fwd2_kernel<KL, KH, 0> : a.ld_feature == 0 ? mtrssm_fwd2_kernel<KL, KH, 1> : mtrssm_fwd2_kernel<KL, KH, 2>;
+    // a lone tile per CTA (small batches, long horizons) is a serial dependent chain: unpaired B fragments there (grouped layout only)
+    auto kernel = !a.rec_tiled ? mtrssm_fwd2_kernel<KL, KH, 0, true>
+                  : a.ld_feature == 0 ? mtrssm_fwd2_kernel<KL, KH, 1, true>
+                  : tpc == 1 ? mtrssm_fwd2_kernel<KL, KH, 2, false> : mtrssm_fwd2_kernel<KL, KH, 2, true>;
     if (!a.rec_tiled && a.ld_feature != 0) return cudaErrorInvalidValue;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)((size_t)mt::FWD_TILES * 32 * sizeof(uint2) + mt::FWD_BIAS * sizeof(float) + 8 * f2::TILE_BYTES));
