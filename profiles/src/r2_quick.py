@@ -25,13 +25,15 @@ def timeit(fn, n):
 layouts = (True, False) if "--ab" in sys.argv else (False,) if "--dense" in sys.argv else (True,)
 sizes = ((37888, 30, 20), (16384, 30, 20), (4096, 30, 20), (256, 30, 20), (8, 30, 20), (256, 512, 5), (16, 512, 5))
 if "--only-bench" in sys.argv:
-    sizes = ((37888, 30, 3),)
+    sizes = ((37888, 30, 20 if "--pipeline" in sys.argv else 3),)
 if "--ab-sizes" in sys.argv:
     sizes = ((37888, 30, 20), (4096, 30, 20), (256, 512, 5))
 for B, T, n in sizes:
   for grouped in layouts:
     run = DirectMtrssm(B, T, _lib.PRECISION_BF16_FUSED, torch.device("cuda"), prior_sample=prior, grouped=grouped)
     f, b = timeit(run.fwd, n), timeit(run.bwd_fused, n)
+    if "--pipeline" in sys.argv:  # the two kernels alternating, as in a training step (each also drains the other's dirty L2 lines)
+        print(f"  alternating fwd -> bwd: {timeit(lambda: (run.fwd(), run.bwd_fused()), n):.4f} ms per pair", end="  |  ")
     print("grouped rows " if grouped else "dense outputs", end=" ")
     bytes_step = (3120 if prior else 3120 - 256) * B * T
     print(f"B={B:6d} T={T:4d} prior_sample={prior}: fwd {f:.4f} ms  fused bwd {b:.4f} ms  step {f + b:.4f} ms  "
