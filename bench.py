@@ -197,9 +197,11 @@ class DirectMtrssm:
     def bwd_data(self) -> None:
         self.lib.call("rssm_mtrssm_rollout_bwd", self.c_dims, self.c_w, self.c_in, self.c_out, self.c_up, self.c_gin, None)
 
-    def bwd_fused(self, k: int = 0) -> None:
-        """bf16 path: BPTT + weight gradients in one kernel (no dpre round trip); gradients into bucket k."""
-        self.flat_grads[k].zero_()
+    def bwd_fused(self, k: int = 0, zero: bool = True) -> None:
+        """bf16 path: BPTT + weight gradients in one kernel (no dpre round trip); gradients into bucket k (zeroed here unless the
+        caller already did)."""
+        if zero:
+            self.flat_grads[k].zero_()
         self.lib.call("rssm_mtrssm_rollout_bwd", self.c_dims, self.c_w, self.c_in, self.c_out, self.c_up, self.c_gin, self.c_gws[k])
 
     def wgrad(self, k: int = 0) -> None:
@@ -232,13 +234,15 @@ def time_direct(run: DirectMtrssm, steps: int, warmup: int, world: int) -> dict:
 
     def step(evs=None):
         k = count[0] & 1
+        if run.fused:  # the step's gradient bucket is cleared at the top of the step: part of the step, not of a kernel's own interval
+            run.flat_grads[k].zero_()
         if evs:
             evs[0].record()
         run.fwd()
         if evs:
             evs[1].record()
         if run.fused:
-            run.bwd_fused(k)
+            run.bwd_fused(k, zero=False)
         else:
             run.bwd_data()
         if evs:
