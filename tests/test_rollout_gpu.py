@@ -575,6 +575,30 @@ def test_mtrssm_fwd2_matches_one_warp_kernel(ops, monkeypatch):
         assert bool((same | (margin < 1e-5)).all()), key
 
 
+def test_mtrssm_fused_backward_two_warp_variant_matches_three_warp_kernel(ops, monkeypatch):
+    """RSSM_BWD_TWO_WARP=1 selects the two-warps-per-tile instantiation of the fused backward (kept for A/B measurements): same
+    arithmetic per row, so data gradients agree to fp32 rounding and weight gradients to the summation order of the TMEM
+    accumulation (1e-5 of each tensor's scale).  Ragged batch, several tile groups, prior draws on."""
+    R, P = ops
+    B, T, dims = 333, 7, H.MT_DIMS
+    params = H.make_params(H.MT_SHAPES)
+    inp = H.mtrssm_inputs(B, T, dims)
+    up = mtrssm_upstream(B, T, dims)
+    _, w3, x3 = run_mtrssm(R, P, params, inp, dims, precision=2, grad=True, upstream=up)
+    monkeypatch.setenv("RSSM_BWD_TWO_WARP", "1")
+    _, w2, x2 = run_mtrssm(R, P, params, inp, dims, precision=2, grad=True, upstream=up)
+    monkeypatch.delenv("RSSM_BWD_TWO_WARP")
+    rep = H.Report("mtrssm fused backward: two-warp variant vs three-warp kernel")
+    for k in MT_GRAD_IN:
+        rep.check("d " + k, x2[k].grad, x3[k].grad, rtol=0, atol=1e-5 * max(float(x3[k].grad.abs().max()), 1e-3))
+    for k in w3:
+        if w3[k].grad is None:
+            assert w2[k].grad is None, k
+            continue
+        rep.check("d " + k, w2[k].grad, w3[k].grad, rtol=0, atol=1e-5 * max(float(w3[k].grad.abs().max()), 1e-3))
+    rep.finish()
+
+
 @pytest.mark.parametrize("precision", [1, 2])
 def test_mtrssm_bf16_backward_vs_oracle(ops, precision):
     """Gradients of the bf16 tensor-core paths against the fp32 oracle, teacher-forced on the kernel's own draws (as in
